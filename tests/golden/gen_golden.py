@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""Generate the committed golden fixtures by running the UNMODIFIED reference in this container.
+
+    python tests/golden/gen_golden.py          # needs /root/reference; writes tests/golden/*.npz|json
+
+The reference has no tests or vectors of its own, so these fixtures -- outputs
+of the reference's own Python game logic on seeded inputs -- are what pins the C oracle
+(oracle/ppad_oracle.c), which in turn checks the CUDA kernels on the GPU box where the reference
+does not exist.  Inputs are produced with numpy's PCG64 (seeded); skyfall is injected (patch 3 of
+ref_harness.py), so nothing depends on the reference's wall-clock-seeded Mersenne Twister except
+the episode fixtures, which seed ``random`` explicitly.
+"""
+import json
+import os
+import random
+import sys
+import time
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_harness as rh  # noqa: E402
+
+INT2ENGLISH = {v: k for k, v in rh.ENGLISH2INT.items()}
+ACTIONS = ["up", "down", "left", "right", "pass"]
+LOGCAP = 64
+
+
+def random_walk_board(rng, rows, cols, ncolors, max_moves):
+    """A full random board, then a random finger walk (swaps), like a played position."""
+    board = rng.integers(0, ncolors, size=(rows, cols)).astype(np.int8)
+    f = [int(rng.integers(rows)), int(rng.integers(cols))]
+    for _ in range(int(rng.integers(0, max_moves + 1))):
+        d = int(rng.integers(4))
+        t = [f[0] + (d == 1) - (d == 0), f[1] + (d == 3) - (d == 2)]
+        if 0 <= t[0] < rows and 0 <= t[1] < cols:
+            board[f[0], f[1]], board[t[0], t[1]] = board[t[0], t[1]], board[f[0], f[1]]
+            f = t
+    return board, f
+
+
+def pack_log(per_iter):
+    flat = [c | (n << 8) for it in per_iter for (c, n) in it]
+    out = np.zeros(LOGCAP, np.uint16)
+    out[:min(len(flat), LOGCAP)] = flat[:LOGCAP]
+    return out, len(flat)
+
+
+def gen_kat(ref):
+    env5 = rh.make_env(5, 6, skyfall_damage=False)
+    cases = []
+    boards = [np.array(b) for b in ref.solved_boards.boards]
+    names = ["solved_%02d" % i for i in range(len(boards))]
+    extra = {
+        "two_disjoint_red_runs": [[0, 0, 0, 1, 2, 3], [1, 2, 1, 2, 3, 1], [2, 1, 2, 0, 0, 0], [1, 2, 3, 1, 2, 3], [2, 3, 1, 2, 3, 1]],
+        "bridged_red_runs": [[0, 0, 0, 1, 2, 3], [1, 2, 0, 0, 3, 1], [2, 1, 2, 0, 0, 0], [1, 2, 3, 1, 2, 3], [2, 3, 1, 2, 3, 1]],
+        "row_col_row": [[0, 0, 0, 1, 2, 3], [1, 2, 0, 2, 3, 1], [2, 1, 0, 0, 0, 2], [1, 2, 3, 1, 2, 3], [2, 3, 1, 2, 3, 1]],
+        "island_min_is_unmatched": [[0, 1, 1, 1, 2, 3], [0, 2, 3, 4, 5, 4], [3, 0, 0, 0, 4, 5], [0, 4, 5, 3, 2, 1], [0, 0, 0, 2, 3, 4]],
+        "all_one_colour": [[2] * 6] * 5,
+        "no_match": [[0, 1, 2, 3, 4, 5], [1, 2, 3, 4, 5, 0], [2, 3, 4, 5, 0, 1], [3, 4, 5, 0, 1, 2], [4, 5, 0, 1, 2, 3]],
+        "with_empties": [[-1, -1, -1, 1, 2, 3], [0, 0, 0, 2, 3, 1], [2, 1, -1, 0, 0, 0], [1, 2, -1, 1, 2, 3], [2, 3, -1, 2, 3, 1]],
+        "jammers": [[6, 6, 6, 1, 2, 3], [0, 0, 0, 2, 3, 1], [2, 1, 5, 5, 5, 5], [1, 2, 3, 1, 2, 3], [2, 3, 1, 2, 3, 1]],
+    }
+    for k, v in extra.items():
+        names.append(k)
+        boards.append(np.array(v))
+    for name, b in zip(names, boards):
+        r = rh.resolve(env5, b, False, [])
+        combos = [list(c) for it in r["combos"] for c in it]
+        cases.append(dict(name=name, board=b.astype(int).tolist(), combos=combos,
+                          reward_hex=float(r["reward"]).hex(), reward=r["reward"],
+                          final_board=r["final_board"].astype(int).tolist()))
+    # the survey's move + skyfall known answer (SURVEY.md section 8c last row)
+    env = rh.make_env(5, 6, skyfall_damage=True, board=np.array(extra["two_disjoint_red_runs"]), finger=[0, 0])
+    rr = random.Random(42)
+    orbs = [rr.randrange(6) for _ in range(64)]
+    env.step("right")
+    env.step("down")
+    r = rh.resolve(env, env.board, True, orbs)
+    cases.append(dict(name="move_right_down_then_pass_skyfall", board=np.array(extra["two_disjoint_red_runs"]).tolist(),
+                      actions=[3, 1], orbs=orbs, board_after_moves=env.board.astype(int).tolist(),
+                      finger_after_moves=[int(v) for v in env.finger],
+                      combos=[list(c) for it in r["combos"] for c in it], consumed=r["consumed"], depth=r["depth"],
+                      reward_hex=float(r["reward"]).hex(), reward=r["reward"],
+                      final_board=r["final_board"].astype(int).tolist()))
+    with open(os.path.join(HERE, "kat.json"), "w") as f:
+        json.dump(dict(generated_by="tests/golden/gen_golden.py", cases=cases), f, indent=0)
+    print("kat.json:", len(cases), "cases")
+
+
+def gen_resolve(rows, cols, n_walk, n_adv, seed, tag, team=None, skyfall_rates=None):
+    rng = np.random.default_rng(seed)
+    env_on = rh.make_env(rows, cols, skyfall_damage=True, team=team)
+    S = 512
+    recs = []
+    t0 = time.time()
+    i = 0
+    while len(recs) < n_walk + n_adv:
+        adversarial = len(recs) >= n_walk
+        if adversarial:
+            ncol = int(rng.integers(2, 5))
+            board = rng.integers(0, ncol, size=(rows, cols)).astype(np.int8)
+            p = rng.dirichlet(np.ones(ncol) * 0.7)
+            orbs = rng.choice(ncol, size=S, p=p).astype(np.uint8)
+        else:
+            board, _ = random_walk_board(rng, rows, cols, 6, 60)
+            orbs = rng.integers(0, 6, size=S).astype(np.uint8)
+        sd = bool(rng.random() < 0.85) or adversarial
+        i += 1
+        try:
+            r = rh.resolve(env_on, board, sd, orbs)
+        except IndexError:
+            continue  # cascade outlived the injected sequence: not a usable vector
+        log, nlog = pack_log(r["combos"])
+        if nlog > LOGCAP:
+            continue
+        recs.append((board, orbs[:256] if r["consumed"] <= 256 else None, sd, r, log))
+        if recs[-1][1] is None:
+            recs.pop()
+    K = len(recs)
+    np.savez_compressed(
+        os.path.join(HERE, "resolve_%s.npz" % tag),
+        boards=np.stack([r[0] for r in recs]).astype(np.int8),
+        orbs=np.stack([r[1] for r in recs]).astype(np.uint8),
+        skyfall_damage=np.array([r[2] for r in recs], np.uint8),
+        reward=np.array([r[3]["reward"] for r in recs], np.float64),
+        n_combos=np.array([sum(len(it) for it in r[3]["combos"]) for r in recs], np.int32),
+        depth=np.array([r[3]["depth"] for r in recs], np.int32),
+        consumed=np.array([r[3]["consumed"] for r in recs], np.int32),
+        final_boards=np.stack([r[3]["final_board"] for r in recs]).astype(np.int8),
+        combo_log=np.stack([r[4] for r in recs]))
+    d = np.array([r[3]["depth"] for r in recs])
+    print("resolve_%s.npz: %d cases (%d tried) in %.0fs; depth hist %s max consumed %d" % (
+        tag, K, i, time.time() - t0, np.bincount(d).tolist(), max(r[3]["consumed"] for r in recs)))
+
+
+def gen_episodes(rows, cols, n_ep, length, seed, tag):
+    """Reference reset() + PlayerAction.sample() walks; every step is also evaluated with
+    calculate_reward(board=env.board, skyfall_damage=True) (the pattern of simulation.py:117-119)."""
+    rng = np.random.default_rng(seed)
+    S = 64
+    out = dict(init_boards=[], init_fingers=[], actions=[], boards=[], fingers=[], orbs=[], reward=[],
+               n_combos=[], depth=[], consumed=[], pass_reward=[], pass_orbs=[], recorded_rewards=[])
+    for e in range(n_ep):
+        rh.set_clock(seed * 1000 + e)   # game.py:72,302 seed the global MT from "datetime.now()"
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            env = rh.load().game.PAD(dim_row=rows, dim_col=cols, skyfall_damage=True)
+        out["init_boards"].append(env.board.astype(np.int8).copy())
+        out["init_fingers"].append(env.finger.astype(np.int32).copy())
+        acts, boards, fingers, orbs_l, rew, nc, dep, con = [], [], [], [], [], [], [], []
+        for t in range(length):
+            env.action_space.finger = env.finger
+            a = env.action_space.sample()
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                env.step(a)
+            orbs = rng.integers(0, 6, size=S).astype(np.uint8)
+            r = rh.resolve(env, env.board, True, orbs)
+            acts.append(ACTIONS.index(a))
+            boards.append(env.board.astype(np.int8).copy())
+            fingers.append(env.finger.astype(np.int32).copy())
+            orbs_l.append(orbs)
+            rew.append(r["reward"])
+            nc.append(sum(len(it) for it in r["combos"]))
+            dep.append(r["depth"])
+            con.append(r["consumed"])
+        porbs = rng.integers(0, 6, size=S).astype(np.uint8)
+        inj = rh.InjectedSkyfall(porbs)
+        env.random_orb = inj
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            env.step("pass")
+        out["pass_reward"].append(float(env.rewards[-1]))
+        out["pass_orbs"].append(porbs)
+        out["recorded_rewards"].append(np.array(env.rewards, np.float64))
+        assert len(env.observations) == length + 1 and len(env.actions) == length + 1
+        for k, v in (("actions", acts), ("boards", boards), ("fingers", fingers), ("orbs", orbs_l),
+                     ("reward", rew), ("n_combos", nc), ("depth", dep), ("consumed", con)):
+            out[k].append(np.array(v))
+    np.savez_compressed(os.path.join(HERE, "episodes_%s.npz" % tag), **{k: np.stack(v) for k, v in out.items()})
+    print("episodes_%s.npz: %d episodes x %d steps" % (tag, n_ep, length))
+
+
+def gen_onehot(ref):
+    rng = np.random.default_rng(7)
+    res = {}
+    import types
+    for rows, cols in ((5, 6), (6, 7)):
+        B = 64
+        boards = rng.integers(-1, 8, size=(B, rows, cols)).astype(int)
+        fingers = np.stack([rng.integers(0, rows, B), rng.integers(0, cols, B)], 1).astype(int)
+        me = types.SimpleNamespace(st_shape=(rows, cols, 7))
+        states = ref.agent01.Agent01.board_finger_to_state(me, boards, fingers)
+        assert states.dtype == np.float64 and set(np.unique(states)) <= {0.0, 1.0}
+        res["boards_%dx%d" % (rows, cols)] = boards.astype(np.int8)
+        res["fingers_%dx%d" % (rows, cols)] = fingers.astype(np.int32)
+        res["states_%dx%d" % (rows, cols)] = states.astype(np.uint8)
+    np.savez_compressed(os.path.join(HERE, "onehot.npz"), **res)
+    print("onehot.npz")
+
+
+def gen_reset():
+    rng = np.random.default_rng(11)
+    res = {}
+    for rows, cols in ((5, 6), (6, 7)):
+        K, S = 48, rows * cols * 40
+        streams, boards, consumed = [], [], []
+        env = rh.make_env(rows, cols)
+        for _ in range(K):
+            orbs = rng.integers(0, 6, size=S).astype(np.uint8)
+            inj = rh.InjectedSkyfall(orbs)
+            env.random_orb = inj
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                b, f = env.reset(finger=np.array([1, 2]))
+            streams.append(orbs)
+            boards.append(b.astype(np.int8).copy())
+            consumed.append(inj.cursor)
+        res["orbs_%dx%d" % (rows, cols)] = np.stack(streams)
+        res["boards_%dx%d" % (rows, cols)] = np.stack(boards)
+        res["consumed_%dx%d" % (rows, cols)] = np.array(consumed, np.int32)
+    np.savez_compressed(os.path.join(HERE, "reset_injected.npz"), **res)
+    print("reset_injected.npz: attempts hist", np.bincount(res["consumed_5x6"] // 30).tolist())
+
+
+CUSTOM_TEAM = [dict(name="A", color_1="red", color_2="red", atk=1234, hp=1, rcv=1),
+               dict(name="B", color_1="blue", color_2="red", atk=987.5, hp=1, rcv=1),
+               dict(name="C", color_1="green", color_2=None, atk=1511, hp=1, rcv=1),
+               dict(name="D", color_1="light", color_2="dark", atk=2048, hp=1, rcv=1),
+               dict(name="E", color_1="dark", color_2="green", atk=777, hp=1, rcv=1)]
+
+
+def gen_damage():
+    rng = np.random.default_rng(13)
+    res = {}
+    for tag, team in (("default", None), ("custom", CUSTOM_TEAM)):
+        env = rh.make_env(5, 6, team=team)
+        K, M = 4000, 24
+        colors = np.full((K, M), -1, np.int32)
+        counts = np.zeros((K, M), np.int32)
+        lens = rng.integers(0, M + 1, size=K)
+        rewards = np.zeros(K, np.float64)
+        for i in range(K):
+            n = int(lens[i])
+            colors[i, :n] = rng.integers(0, 7, size=n)
+            counts[i, :n] = rng.integers(3, 31, size=n)
+            combos = [dict(color=INT2ENGLISH[int(colors[i, j])], N=np.float64(counts[i, j]), enhanced=None, shape=None)
+                      for j in range(n)]
+            rewards[i] = float(env.damage(combos))
+        res.update({"colors_" + tag: colors, "counts_" + tag: counts, "lens_" + tag: lens.astype(np.int32),
+                    "rewards_" + tag: rewards})
+    np.savez_compressed(os.path.join(HERE, "damage.npz"), **res)
+    with open(os.path.join(HERE, "custom_team.json"), "w") as f:
+        json.dump(CUSTOM_TEAM, f)
+    print("damage.npz")
+
+
+def gen_discount(ref):
+    rng = np.random.default_rng(17)
+    K, L = 200, 40
+    rewards = np.zeros((K, L))
+    lens = rng.integers(1, L + 1, size=K)
+    out_log, out_lin = np.zeros((K, L)), np.zeros((K, L))
+    gammas = rng.uniform(0.5, 0.99, size=K)
+    for i in range(K):
+        n = int(lens[i])
+        r = np.where(rng.random(n) < 0.3, rng.uniform(0, 40000, n), 0.0)
+        if i % 10 == 0:
+            r[:] = 0
+        rewards[i, :n] = r
+        out_log[i, :n] = ref.agent_utils.discount(list(r), gammas[i], log10=True)
+        out_lin[i, :n] = ref.agent_utils.discount(list(r), gammas[i], log10=False)
+    np.savez_compressed(os.path.join(HERE, "discount.npz"), rewards=rewards, lens=lens.astype(np.int32),
+                        gammas=gammas, out_log=out_log, out_lin=out_lin)
+    print("discount.npz")
+
+
+def gen_legal(ref):
+    """illegal_actions (utils.py:73-83) and the support of PlayerAction.sample (player.py:38-66)."""
+    res = {}
+    for rows, cols in ((5, 6), (6, 7)):
+        illegal = np.zeros((rows, cols), np.uint8)
+        sample_mask = np.zeros((rows, cols, 5), np.uint8)
+        for r in range(rows):
+            for c in range(cols):
+                f = np.array([r, c])
+                s = ref.pad_utils.illegal_actions(f, dim_row=rows, dim_col=cols)
+                illegal[r, c] = sum(1 << ACTIONS.index(a) for a in s)
+                for prev in range(5):
+                    pa = ref.player.PlayerAction(finger=f, dim_row=rows, dim_col=cols)
+                    pa.previous_action = ACTIONS[prev]
+                    random.seed(r * 100 + c * 10 + prev)
+                    m = 0
+                    for _ in range(300):
+                        m |= 1 << ACTIONS.index(pa.sample())
+                    sample_mask[r, c, prev] = m
+        res["illegal_%dx%d" % (rows, cols)] = illegal
+        res["sample_%dx%d" % (rows, cols)] = sample_mask
+    np.savez_compressed(os.path.join(HERE, "legal.npz"), **res)
+    print("legal.npz")
+
+
+def gen_random_orb(ref):
+    """random_orb (game.py:458-470) with random.random() pinned to x / 2^32."""
+    rng = np.random.default_rng(19)
+    probs = [[1 / 6] * 6 + [0] * 4,
+             [0.3, 0.2, 0.1, 0.1, 0.1, 0.1, 0.1, 0, 0, 0],
+             [0.5, 0, 0.25, 0, 0.25, 0, 0, 0, 0, 0],
+             [0, 0, 0, 0.125, 0.125, 0.75, 0, 0, 0, 0],
+             [0.05, 0.15, 0.2, 0.1, 0.3, 0.1, 0.1, 0, 0, 0]]
+    xs = np.concatenate([rng.integers(0, 2 ** 32, size=3000, dtype=np.uint64),
+                         np.array([0, 1, 2 ** 32 - 1, 2 ** 31, 715827882, 715827883, 1431655765, 1431655766,
+                                   2147483648, 2863311530, 2863311531, 3579139413, 3579139414], np.uint64)])
+    # add the exact threshold neighbours of every cumulative sum
+    extra = []
+    for p in probs:
+        c = 0.0
+        for v in p:
+            c += v
+            t = int(c * 2 ** 32)
+            extra += [max(0, min(2 ** 32 - 1, t + d)) for d in (-1, 0, 1)]
+    xs = np.concatenate([xs, np.array(extra, np.uint64)])
+    out = np.zeros((len(probs), len(xs)), np.uint8)
+    real = ref.game.random.random
+    try:
+        for i, p in enumerate(probs):
+            for j, x in enumerate(xs):
+                ref.game.random.random = lambda x=x: int(x) / 4294967296.0
+                out[i, j] = ref.game.PAD.random_orb(p)
+    finally:
+        ref.game.random.random = real
+    np.savez_compressed(os.path.join(HERE, "random_orb.npz"), probs=np.array(probs, np.float64),
+                        xs=xs.astype(np.uint32), orbs=out)
+    print("random_orb.npz")
+
+
+def main():
+    ref = rh.load()
+    gen_kat(ref)
+    gen_onehot(ref)
+    gen_damage()
+    gen_discount(ref)
+    gen_legal(ref)
+    gen_random_orb(ref)
+    gen_reset()
+    gen_episodes(5, 6, 24, 30, 101, "5x6")
+    gen_episodes(6, 7, 10, 24, 102, "6x7")
+    gen_resolve(5, 6, 2500, 300, 201, "5x6")
+    gen_resolve(6, 7, 1000, 150, 202, "6x7")
+    gen_resolve(5, 6, 400, 0, 203, "5x6_custom_team", team=CUSTOM_TEAM)
+
+
+if __name__ == "__main__":
+    main()
