@@ -1,0 +1,158 @@
+/*
+ * ppad_b200.h -- C ABI of the B200-native batched Puzzle & Dragons environment.
+ *
+ * The reference (nuwapi/P-PAD) is pure Python and has no FFI: its boundary for this path is the
+ * duck-typed `PAD` object (ppad/pad/game.py:28-470) plus two free functions
+ * (ppad/pad/utils.py:26-83) and one agent method (ppad/agent/agent01.py:254-273).  Each entry point
+ * below names the reference interface it replaces for a batch of n boards; the Python layer in
+ * p-pad_b200/ rebuilds the reference's object surface on top of them via ctypes.
+ *
+ * Conventions
+ *   - every pointer is a caller-owned DEVICE pointer unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls only
+ *     enqueue work, they never synchronise;
+ *   - return value: 0 = PPAD_OK, otherwise a ppad_status; ppad_strerror() names it and
+ *     ppad_last_error() holds the detail (thread-local);
+ *   - per-board faults never abort a launch: they are reported in the flags byte of `info`;
+ *   - there is NO CPU path: without a CUDA device every compute entry point returns PPAD_ERR_CUDA.
+ *
+ * Packed state record ("state"), one per board, ppad_state_bytes(rows, cols) bytes:
+ *   5x6 (<= 32 cells): uint32 b0, b1, b2, meta                    (16 B, one uint4)
+ *   6x7 (<= 64 cells): uint64 b0, b1, b2; uint32 meta, reserved   (32 B, two uint4)
+ *   bit i of plane bj = bit j of the orb code of cell i = row * cols + col;
+ *   codes 0..6 = red, blue, green, light, dark, heal, jammer (game.py:236-246), 7 = empty (-1);
+ *   meta = finger cell [0,6) | previous action [6,9) (4 = 'pass') | accepted moves this episode [9,25).
+ */
+#ifndef PPAD_B200_H
+#define PPAD_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PPAD_ABI_VERSION 1
+#define PPAD_MAX_TEAM_UNITS 8
+
+typedef enum ppad_status {
+    PPAD_OK = 0,
+    PPAD_ERR_INVALID = 1,       /* bad argument (message in ppad_last_error) */
+    PPAD_ERR_UNSUPPORTED = 2,   /* board size / orb type / dtype without a kernel instantiation */
+    PPAD_ERR_CUDA = 3           /* CUDA runtime error, including "no device" */
+} ppad_status;
+
+/* actions: player.py:24, simulation.py:236 */
+enum { PPAD_UP = 0, PPAD_DOWN = 1, PPAD_LEFT = 2, PPAD_RIGHT = 3, PPAD_PASS = 4, PPAD_SAMPLE = 255 };
+
+/* flags byte (info >> 24) */
+enum {
+    PPAD_FLAG_REJECTED = 0x01,          /* move off the board: state unchanged (game.py:353 raises ValueError) */
+    PPAD_FLAG_SKYFALL_EXHAUSTED = 0x02, /* injected orbs ran out, the Philox stream took over */
+    PPAD_FLAG_CASCADE_CAP = 0x04,       /* cascade stopped at cfg.cascade_cap iterations */
+    PPAD_FLAG_NO_LEGAL_MOVE = 0x08,     /* random policy found an empty legal set */
+    PPAD_FLAG_BAD_ACTION = 0x10,        /* action id outside 0..4 */
+    PPAD_FLAG_RESET_CAP = 0x20,         /* reset gave up after cfg.reset_cap attempts */
+    PPAD_FLAG_UNSUPPORTED_ORB = 0x40,   /* pack saw a value outside -1..6 (stored as empty) */
+    PPAD_FLAG_EPISODE_DONE = 0x80       /* a pass was processed and the board auto-reset */
+};
+
+/* info word: n_combos | depth << 8 | consumed << 16 | flags << 24, each field saturating at 255 */
+#define PPAD_INFO_COMBOS(i) ((i) & 0xFFu)
+#define PPAD_INFO_DEPTH(i) (((i) >> 8) & 0xFFu)
+#define PPAD_INFO_CONSUMED(i) (((i) >> 16) & 0xFFu)
+#define PPAD_INFO_FLAGS(i) (((i) >> 24) & 0xFFu)
+
+typedef enum ppad_dtype { PPAD_I8 = 1, PPAD_I32 = 4, PPAD_I64 = 8 } ppad_dtype;
+typedef enum ppad_obs_dtype { PPAD_OBS_F32 = 0, PPAD_OBS_U8 = 1 } ppad_obs_dtype;
+
+/* Environment constants: the keyword arguments of PAD.__init__ (game.py:39-50) that reach the hot path. */
+typedef struct ppad_config {
+    int32_t rows, cols;              /* dim_row, dim_col: (5,6) and (6,7) are instantiated */
+    int32_t skyfall_damage;          /* game.py:45,387: cascade with drop + skyfall, or a single cancel */
+    int32_t cascade_cap;             /* the reference has none; 0 = unlimited */
+    int32_t reset_cap;               /* rejection-sampling attempts in reset; 0 = unlimited */
+    int32_t team_size;               /* game.py:47, parameters.py:54-89 */
+    int32_t team_color_1[PPAD_MAX_TEAM_UNITS];   /* orb type 0..4, or -1 for None */
+    int32_t team_color_2[PPAD_MAX_TEAM_UNITS];
+    double  team_atk[PPAD_MAX_TEAM_UNITS];
+    double  skyfall[10];             /* game.py:42, parameters.py:43; types 7..9 must have rate 0 */
+    uint64_t seed;                   /* Philox4x32-10 key (replaces random.seed(datetime.now()), game.py:72,302) */
+} ppad_config;
+
+typedef struct ppad_ctx ppad_ctx;   /* immutable after creation; usable from any stream of its device */
+
+/* parameters.py:43,54-89 + PAD() defaults */
+void ppad_default_config(ppad_config *cfg);
+/* PAD.__init__ (game.py:39-120) validation; `device` is a CUDA ordinal */
+int ppad_create(const ppad_config *cfg, int device, ppad_ctx **out);
+void ppad_destroy(ppad_ctx *ctx);
+int ppad_abi_version(void);
+const char *ppad_strerror(int status);
+const char *ppad_last_error(void);
+int64_t ppad_state_bytes(int rows, int cols);
+/* kernels launched by this library since load (all contexts, all threads) */
+uint64_t ppad_launch_count(void);
+
+/* PAD.board / PAD.finger / action_space.previous_action (game.py:88,94,117) <-> packed state.
+ * boards [n, rows, cols] of `dtype`; fingers [n, 2] (row, col) of `dtype`; prev [n] uint8 or NULL
+ * (= 'pass'); moves [n] uint16 or NULL (= 0); flags [n] uint8 or NULL. */
+int ppad_pack(const ppad_ctx *ctx, int64_t n, const void *boards, const void *fingers, int dtype,
+              const uint8_t *prev, const uint16_t *moves, void *state, uint8_t *flags, void *stream);
+int ppad_unpack(const ppad_ctx *ctx, int64_t n, const void *state, void *boards, void *fingers, int dtype,
+                uint8_t *prev, uint16_t *moves, void *stream);
+
+/* PAD.reset (game.py:282-323) for n boards: combo-free random boards by rejection, random finger,
+ * previous action 'pass'.  Orbs come from the injected nibble slab first (slab != NULL: n_inj orbs per
+ * board, slab_words uint32 per board, orb d at word d >> 3, bits 4 * (d & 7)) and then from the Philox
+ * stream (env0 + i, step).  fingers_in [n, 2] int32 or NULL (= Philox).  flags [n] uint8 or NULL. */
+int ppad_reset(const ppad_ctx *ctx, int64_t n, uint64_t env0, uint32_t step, const uint32_t *slab,
+               int32_t slab_words, int32_t n_inj, const int32_t *fingers_in, void *state, uint8_t *flags,
+               uint8_t *consumed, void *stream);
+
+/* One env step of n boards: the fused hot path.
+ *   action      = actions ? actions[i] : (max_moves > 0 && moves >= max_moves ? PASS : random legal move)
+ *                 (PlayerAction.sample, player.py:38-66; PPAD_SAMPLE in actions[i] also samples)
+ *   move        : PAD.apply_action + PAD.swap (game.py:122-155,429-456); off-board -> FLAG_REJECTED
+ *   evaluate    : on PASS, or on every accepted move when eval_moves != 0 (the look-ahead pattern
+ *                 env.step(a); env.calculate_reward(...) of simulation.py:117-119):
+ *                 PAD.calculate_reward (game.py:364-405) = cancel -> drop -> fill_board until stable,
+ *                 on a COPY of the board, then PAD.damage (game.py:157-199) in float64
+ *   auto_reset  : after a PASS, PAD.reset for that board (step-keyed Philox), FLAG_EPISODE_DONE
+ *   obs         : Agent01.board_finger_to_state (agent01.py:254-273) of the state written back
+ * Outputs may be NULL.  final_state receives the board AFTER the cascade (debug / parity only).
+ * combo_log [n, log_cap] uint16 = colour | N << 8 per combo in reference order. */
+typedef struct ppad_step_args {
+    int64_t n;
+    uint64_t env0;                /* global id of board 0 of this slab (sharding: rank * n_local) */
+    uint32_t step;                /* global step index: Philox counter word */
+    int32_t eval_moves, auto_reset, max_moves;
+    void *state;                  /* in/out */
+    const uint8_t *actions;       /* [n] or NULL */
+    const uint32_t *slab;         /* injected skyfall, [n, slab_words] or NULL */
+    int32_t slab_words, n_inj;
+    uint8_t *action_out;          /* [n] action actually taken */
+    double *reward;               /* [n] float64 */
+    uint32_t *info;               /* [n] */
+    void *final_state;            /* [n] packed, or NULL */
+    uint16_t *combo_log;          /* [n, log_cap] or NULL */
+    int32_t log_cap;
+    void *obs;                    /* [n, rows, cols, 7] or NULL */
+    int32_t obs_dtype;            /* ppad_obs_dtype */
+} ppad_step_args;
+int ppad_step(const ppad_ctx *ctx, const ppad_step_args *args, void *stream);
+
+/* Agent01.board_finger_to_state (agent01.py:254-273): state -> [n, rows, cols, 7] NHWC */
+int ppad_encode_obs(const ppad_ctx *ctx, int64_t n, const void *state, void *obs, int obs_dtype, void *stream);
+
+/* pad_utils.cancel (utils.py:26-70): one in-place cancel; n_combos [n] uint8; combo_log as above */
+int ppad_cancel(const ppad_ctx *ctx, int64_t n, void *state, uint8_t *n_combos, uint16_t *combo_log,
+                int32_t log_cap, void *stream);
+
+/* pad_utils.illegal_actions (utils.py:73-83) / the support of PlayerAction.sample (player.py:46-62):
+ * mask [n] uint8, bit a = action a is a legal non-reversing move; bits 4..7 = off-board moves. */
+int ppad_legal_mask(const ppad_ctx *ctx, int64_t n, const void *state, uint8_t *mask, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

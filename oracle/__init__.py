@@ -180,8 +180,22 @@ def discount(rewards, gamma, log10=True):
 
 
 def step_batch(cfg, boards, fingers, prev, moves=None, actions=None, eval_moves=True, auto_reset=False,
-               max_moves=0, inj=None, env0=0, step=0, want_final=False):
-    """One batched env step; boards/fingers/prev/moves are updated in place (kernel contract)."""
+               max_moves=0, inj=None, env0=0, step=0, want_final=False, threads=1):
+    """One batched env step; boards/fingers/prev/moves are updated in place (kernel contract).
+    threads > 1 splits the batch into contiguous slices run on a thread pool (ctypes drops the GIL)."""
+    n = boards.shape[0]
+    if threads > 1 and n >= 2 * threads:
+        from concurrent.futures import ThreadPoolExecutor
+        edges = [n * k // threads for k in range(threads + 1)]
+
+        def run(k):
+            sl = slice(edges[k], edges[k + 1])
+            return step_batch(cfg, boards[sl], fingers[sl], prev[sl], None if moves is None else moves[sl],
+                              None if actions is None else np.ascontiguousarray(actions[sl]), eval_moves, auto_reset,
+                              max_moves, None if inj is None else inj[sl], env0 + edges[k], step, want_final, 1)
+        with ThreadPoolExecutor(threads) as ex:
+            parts = list(ex.map(run, range(threads)))
+        return tuple(None if parts[0][j] is None else np.concatenate([p[j] for p in parts]) for j in range(4))
     assert boards.dtype == np.int8 and fingers.dtype == np.int32 and prev.dtype == np.uint8
     assert boards.flags.c_contiguous and fingers.flags.c_contiguous
     n = boards.shape[0]

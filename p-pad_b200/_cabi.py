@@ -1,0 +1,97 @@
+"""ctypes binding of libppad_b200.so (include/ppad_b200.h).  There is no CPU path: if the library
+is missing or a call fails, this module raises."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libppad_b200.so")
+MAX_TEAM_UNITS = 8
+
+OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
+UP, DOWN, LEFT, RIGHT, PASS, SAMPLE = 0, 1, 2, 3, 4, 255
+FLAG_REJECTED, FLAG_SKYFALL_EXHAUSTED, FLAG_CASCADE_CAP, FLAG_NO_LEGAL_MOVE = 0x01, 0x02, 0x04, 0x08
+FLAG_BAD_ACTION, FLAG_RESET_CAP, FLAG_UNSUPPORTED_ORB, FLAG_EPISODE_DONE = 0x10, 0x20, 0x40, 0x80
+I8, I32, I64 = 1, 4, 8
+OBS_F32, OBS_U8 = 0, 1
+
+
+class Config(C.Structure):
+    """struct ppad_config"""
+    _fields_ = [("rows", C.c_int32), ("cols", C.c_int32), ("skyfall_damage", C.c_int32),
+                ("cascade_cap", C.c_int32), ("reset_cap", C.c_int32), ("team_size", C.c_int32),
+                ("team_color_1", C.c_int32 * MAX_TEAM_UNITS), ("team_color_2", C.c_int32 * MAX_TEAM_UNITS),
+                ("team_atk", C.c_double * MAX_TEAM_UNITS), ("skyfall", C.c_double * 10), ("seed", C.c_uint64)]
+
+
+class StepArgs(C.Structure):
+    """struct ppad_step_args"""
+    _fields_ = [("n", C.c_int64), ("env0", C.c_uint64), ("step", C.c_uint32), ("eval_moves", C.c_int32),
+                ("auto_reset", C.c_int32), ("max_moves", C.c_int32), ("state", C.c_void_p),
+                ("actions", C.c_void_p), ("slab", C.c_void_p), ("slab_words", C.c_int32), ("n_inj", C.c_int32),
+                ("action_out", C.c_void_p), ("reward", C.c_void_p), ("info", C.c_void_p),
+                ("final_state", C.c_void_p), ("combo_log", C.c_void_p), ("log_cap", C.c_int32),
+                ("obs", C.c_void_p), ("obs_dtype", C.c_int32)]
+
+
+# every symbol include/ppad_b200.h declares (tests/test_cabi_symbols.py checks the header against this)
+SYMBOLS = ["ppad_default_config", "ppad_create", "ppad_destroy", "ppad_abi_version", "ppad_strerror",
+           "ppad_last_error", "ppad_state_bytes", "ppad_launch_count", "ppad_pack", "ppad_unpack", "ppad_reset",
+           "ppad_step", "ppad_encode_obs", "ppad_cancel", "ppad_legal_mask"]
+
+
+class PPADError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__("ppad_b200 status %d: %s" % (status, message))
+        self.status = status
+        self.detail = message
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library.  Raises if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s is missing: build it with __graft_entry__.build() (nvcc, sm_100a). "
+                          "ppad_b200 has no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, u32, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64
+    L.ppad_default_config.argtypes = [C.POINTER(Config)]
+    L.ppad_default_config.restype = None
+    L.ppad_create.argtypes = [C.POINTER(Config), C.c_int, C.POINTER(vp)]
+    L.ppad_destroy.argtypes = [vp]
+    L.ppad_destroy.restype = None
+    L.ppad_strerror.argtypes = [C.c_int]
+    L.ppad_strerror.restype = C.c_char_p
+    L.ppad_last_error.restype = C.c_char_p
+    L.ppad_state_bytes.argtypes = [C.c_int, C.c_int]
+    L.ppad_state_bytes.restype = i64
+    L.ppad_launch_count.restype = u64
+    L.ppad_pack.argtypes = [vp, i64, vp, vp, C.c_int, vp, vp, vp, vp, vp]
+    L.ppad_unpack.argtypes = [vp, i64, vp, vp, vp, C.c_int, vp, vp, vp]
+    L.ppad_reset.argtypes = [vp, i64, u64, u32, vp, i32, i32, vp, vp, vp, vp, vp]
+    L.ppad_step.argtypes = [vp, C.POINTER(StepArgs), vp]
+    L.ppad_encode_obs.argtypes = [vp, i64, vp, vp, C.c_int, vp]
+    L.ppad_cancel.argtypes = [vp, i64, vp, vp, vp, i32, vp]
+    L.ppad_legal_mask.argtypes = [vp, i64, vp, vp, vp]
+    for name in SYMBOLS:
+        getattr(L, name)
+    if L.ppad_abi_version() != 1:
+        raise ImportError("libppad_b200.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+def check(status):
+    if status != OK:
+        L = lib()
+        raise PPADError(status, "%s: %s" % (L.ppad_strerror(status).decode(), L.ppad_last_error().decode()))
+
+
+def default_config():
+    cfg = Config()
+    lib().ppad_default_config(C.byref(cfg))
+    return cfg

@@ -1,0 +1,236 @@
+"""BatchedPAD -- n independent Puzzle & Dragons boards resident on one GPU.
+
+The tensor-level API over the C ABI (include/ppad_b200.h).  PyTorch is plumbing here: it owns the
+device memory and the stream; every operation is one hand-written sm_100a kernel launched through
+ctypes.  The semantics per board are those of the reference's ``PAD`` object
+(ppad/pad/game.py:28-470); the single-env drop-in facade lives in ``ppad_b200.pad.game``.
+"""
+import ctypes as C
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .config import make_config
+from .layout import state_words
+
+ACTION_NAMES = ['up', 'down', 'left', 'right', 'pass']        # player.py:24
+ACTION_IDS = {name: i for i, name in enumerate(ACTION_NAMES)}  # simulation.py:236
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class BatchedPAD:
+    """n boards of dim_row x dim_col on ``device``; keyword arguments as ``PAD.__init__`` (game.py:39-50).
+
+    ``env0`` is the global id of board 0 (sharding: rank * n); Philox streams are keyed by
+    (seed, env0 + i, step), so a rollout does not depend on how boards are split across GPUs.
+    """
+
+    def __init__(self, n, dim_row=5, dim_col=6, skyfall=None, skyfall_damage=True, team=None, seed=0,
+                 device=None, env0=0, cascade_cap=255, reset_cap=64):
+        if not torch.cuda.is_available():
+            raise RuntimeError("ppad_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _cabi.lib()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.n = int(n)
+        self.dim_row, self.dim_col = int(dim_row), int(dim_col)
+        self.cells = self.dim_row * self.dim_col
+        self.skyfall_damage = bool(skyfall_damage)
+        self.env0 = int(env0)
+        self.step_index = 0
+        self.cfg = make_config(dim_row, dim_col, skyfall, skyfall_damage, team, seed, cascade_cap, reset_cap)
+        handle = C.c_void_p()
+        _cabi.check(self.lib.ppad_create(C.byref(self.cfg), self.device.index, C.byref(handle)))
+        self._ctx = handle
+        self.words = state_words(self.dim_row, self.dim_col)
+        assert self.lib.ppad_state_bytes(self.dim_row, self.dim_col) == 4 * self.words
+        # packed state records (int32 view of the uint32 words of include/ppad_b200.h)
+        self.state = torch.zeros((self.n, self.words), dtype=torch.int32, device=self.device)
+
+    def __del__(self):
+        ctx, self._ctx = getattr(self, "_ctx", None), None
+        if ctx:
+            self.lib.ppad_destroy(ctx)
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _dev(self, x, dtype):
+        if x is None:
+            return None
+        if isinstance(x, torch.Tensor):
+            return x.to(device=self.device, dtype=dtype).contiguous()
+        return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype).to(self.device)
+
+    def _slab(self, injected):
+        """injected: None, or a uint8 [n, S] orb sequence (tensor/array), or (slab_int32 [n, W], n_inj)."""
+        if injected is None:
+            return None, 0, 0
+        if isinstance(injected, tuple):
+            slab, n_inj = injected
+            slab = self._dev(slab, torch.int32)
+            return slab, slab.shape[1], int(n_inj)
+        orbs = self._dev(injected, torch.uint8)
+        n, s = orbs.shape
+        words = (s + 7) // 8
+        pad = torch.zeros((n, words * 8), dtype=torch.int64, device=self.device)
+        pad[:, :s] = orbs & 15
+        shifts = 4 * torch.arange(8, device=self.device, dtype=torch.int64)
+        packed = (pad.view(n, words, 8) << shifts).sum(dim=2)
+        slab = (packed & 0xFFFFFFFF).to(torch.int64)
+        slab = torch.where(slab >= 2 ** 31, slab - 2 ** 32, slab).to(torch.int32).contiguous()
+        return slab, words, s
+
+    # ------------------------------------------------------------------ state in / out
+    def set_state(self, boards, fingers, prev=None, moves=None):
+        """PAD.board / PAD.finger / previous_action (game.py:88,94,117) -> packed state. Returns flags [n] uint8."""
+        boards = self._dev(boards, torch.int64).reshape(self.n, self.cells)
+        fingers = self._dev(fingers, torch.int64).reshape(self.n, 2)
+        prev = self._dev(prev, torch.uint8)
+        moves = None if moves is None else self._dev(moves, torch.int16)
+        flags = torch.zeros(self.n, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ppad_pack(self._ctx, self.n, _ptr(boards), _ptr(fingers), _cabi.I64, _ptr(prev),
+                                           _ptr(moves), _ptr(self.state), _ptr(flags), self._stream()))
+        return flags
+
+    def get_state(self, state=None):
+        """-> SimpleNamespace(boards int64 [n, rows, cols], fingers int64 [n, 2], prev uint8 [n], moves int16 [n])"""
+        state = self.state if state is None else state
+        n = state.shape[0]
+        boards = torch.empty((n, self.dim_row, self.dim_col), dtype=torch.int64, device=self.device)
+        fingers = torch.empty((n, 2), dtype=torch.int64, device=self.device)
+        prev = torch.empty(n, dtype=torch.uint8, device=self.device)
+        moves = torch.empty(n, dtype=torch.int16, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ppad_unpack(self._ctx, n, _ptr(state), _ptr(boards), _ptr(fingers), _cabi.I64,
+                                             _ptr(prev), _ptr(moves), self._stream()))
+        return SimpleNamespace(boards=boards, fingers=fingers, prev=prev, moves=moves)
+
+    def snapshot(self):
+        """Checkpoint of the env slab (the batched analogue of the record PAD.backtrack pops, game.py:407-427)."""
+        return self.state.clone(), self.step_index
+
+    def restore(self, snap):
+        self.state.copy_(snap[0])
+        self.step_index = snap[1]
+
+    # ------------------------------------------------------------------ reset / step
+    def reset(self, boards=None, fingers=None, injected=None, step=None):
+        """PAD.reset (game.py:282-323) for every board; returns flags [n] uint8.
+
+        boards given: adopt them (fingers default to Philox draws unless given).
+        boards None : rejection-sample combo-free boards (injected orbs first, then Philox)."""
+        step = self._next_step(step)
+        if boards is not None:
+            if fingers is None:
+                tmp = BatchedPAD.reset(self, None, None, None, step)
+                fingers = self.get_state().fingers
+                del tmp
+            return self.set_state(boards, fingers)
+        slab, words, n_inj = self._slab(injected)
+        fin = None if fingers is None else self._dev(fingers, torch.int32).reshape(self.n, 2)
+        flags = torch.zeros(self.n, dtype=torch.uint8, device=self.device)
+        self.last_reset_consumed = torch.zeros(self.n, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ppad_reset(self._ctx, self.n, self.env0, step, _ptr(slab), words, n_inj, _ptr(fin),
+                                            _ptr(self.state), _ptr(flags), _ptr(self.last_reset_consumed),
+                                            self._stream()))
+        return flags
+
+    def _next_step(self, step):
+        if step is None:
+            step = self.step_index
+        self.step_index = int(step) + 1
+        return int(step) & 0xFFFFFFFF
+
+    def step(self, actions=None, eval_moves=False, auto_reset=False, max_moves=0, injected=None, obs=None,
+             want_final=False, log_cap=0, step=None, out=None):
+        """One env step of all boards (ppad_step).  actions: None (random legal moves / forced pass at
+        max_moves), or uint8 [n] ids 0..4 (255 = sample).  obs: None, 'f32' or 'u8', or a preallocated tensor.
+        Returns SimpleNamespace(action, reward, info, obs, final_state, combo_log); ``out`` reuses buffers."""
+        step = self._next_step(step)
+        n = self.n
+        out = out if out is not None else SimpleNamespace()
+        if getattr(out, "reward", None) is None:
+            out.action = torch.empty(n, dtype=torch.uint8, device=self.device)
+            out.reward = torch.empty(n, dtype=torch.float64, device=self.device)
+            out.info = torch.empty(n, dtype=torch.int32, device=self.device)
+        obs_dtype = _cabi.OBS_F32
+        if isinstance(obs, torch.Tensor):
+            out.obs = obs
+            obs_dtype = _cabi.OBS_F32 if obs.dtype == torch.float32 else _cabi.OBS_U8
+        elif obs is not None:
+            obs_dtype = {'f32': _cabi.OBS_F32, 'u8': _cabi.OBS_U8}[obs]
+            want = torch.float32 if obs == 'f32' else torch.uint8
+            if getattr(out, "obs", None) is None or out.obs.dtype != want:
+                out.obs = torch.empty((n, self.dim_row, self.dim_col, 7), dtype=want, device=self.device)
+        else:
+            out.obs = None
+        out.final_state = torch.empty_like(self.state) if want_final else None
+        out.combo_log = torch.zeros((n, log_cap), dtype=torch.int16, device=self.device) if log_cap else None
+        acts = self._dev(actions, torch.uint8)
+        slab, words, n_inj = self._slab(injected)
+        a = _cabi.StepArgs()
+        a.n, a.env0, a.step = n, self.env0, step
+        a.eval_moves, a.auto_reset, a.max_moves = int(bool(eval_moves)), int(bool(auto_reset)), int(max_moves)
+        a.state = self.state.data_ptr()
+        a.actions = acts.data_ptr() if acts is not None else None
+        a.slab = slab.data_ptr() if slab is not None else None
+        a.slab_words, a.n_inj = words, n_inj
+        a.action_out, a.reward, a.info = out.action.data_ptr(), out.reward.data_ptr(), out.info.data_ptr()
+        a.final_state = out.final_state.data_ptr() if want_final else None
+        a.combo_log = out.combo_log.data_ptr() if log_cap else None
+        a.log_cap = int(log_cap)
+        a.obs = out.obs.data_ptr() if out.obs is not None else None
+        a.obs_dtype = obs_dtype
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ppad_step(self._ctx, C.byref(a), self._stream()))
+        return out
+
+    def calculate_reward(self, injected=None, want_final=False, log_cap=0, step=None):
+        """PAD.calculate_reward (game.py:364-405) of every board, on a copy: the state is not modified."""
+        acts = torch.full((self.n,), _cabi.PASS, dtype=torch.uint8, device=self.device)
+        return self.step(acts, injected=injected, want_final=want_final, log_cap=log_cap, step=step)
+
+    # ------------------------------------------------------------------ single-purpose kernels
+    def encode_obs(self, dtype='f32', state=None, out=None):
+        """Agent01.board_finger_to_state (agent01.py:254-273): [n, rows, cols, 7]"""
+        state = self.state if state is None else state
+        n = state.shape[0]
+        tdt = torch.float32 if dtype == 'f32' else torch.uint8
+        if out is None:
+            out = torch.empty((n, self.dim_row, self.dim_col, 7), dtype=tdt, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ppad_encode_obs(self._ctx, n, _ptr(state), _ptr(out),
+                                                 _cabi.OBS_F32 if dtype == 'f32' else _cabi.OBS_U8, self._stream()))
+        return out
+
+    def cancel(self, log_cap=16):
+        """pad_utils.cancel (utils.py:26-70) in place on every board -> (n_combos uint8 [n], combo_log int16 [n, log_cap])"""
+        n_combos = torch.empty(self.n, dtype=torch.uint8, device=self.device)
+        log = torch.zeros((self.n, log_cap), dtype=torch.int16, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ppad_cancel(self._ctx, self.n, _ptr(self.state), _ptr(n_combos), _ptr(log), log_cap,
+                                             self._stream()))
+        return n_combos, log
+
+    def legal_mask(self):
+        """uint8 [n]: bits 0..3 = legal non-reversing moves (player.py:52-62), bits 4..7 = off-board moves (utils.py:73-83)"""
+        mask = torch.empty(self.n, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ppad_legal_mask(self._ctx, self.n, _ptr(self.state), _ptr(mask), self._stream()))
+        return mask
+
+    @staticmethod
+    def split_info(info):
+        """info int32 [n] -> (n_combos, depth, consumed, flags) int32 tensors"""
+        u = info.to(torch.int64) & 0xFFFFFFFF
+        return u & 0xFF, (u >> 8) & 0xFF, (u >> 16) & 0xFF, (u >> 24) & 0xFF

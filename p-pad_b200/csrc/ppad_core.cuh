@@ -1,0 +1,725 @@
+// ppad_core.cuh -- per-board game logic on bit-sliced boards (sm_100a device code).
+//
+// One thread owns one board.  A board of R x C cells (R*C <= 64) lives in three machine words
+// b0,b1,b2: bit i of plane j is bit j of the 3-bit orb code of cell i = row*C + col (row 0 = top,
+// gravity towards larger rows; reference orientation, ppad/pad/game.py:30-38).  Codes 0..6 are the
+// orb types red, blue, green, light, dark, heal, jammer (game.py:236-246); 7 = empty (-1).
+// Bits >= R*C of every plane are zero.  With this layout every step of the reference's hot path
+// is a handful of LOP3/SHF instructions:
+//   * "same colour as my right/down neighbour" is three XORs and an OR across the planes,
+//   * 3-runs are two shift-ANDs of that edge mask (utils.py:47-54),
+//   * islands (utils.py:86-111) are the closure of a seed under the two edge masks,
+//   * gravity (game.py:201-221) moves whole rows of bits, skyfall (game.py:232-256) walks the
+//     empties in ascending bit order, which IS the reference's row-major order.
+//
+// The functions are __host__ __device__ so that tests/hostcore/ can compile the very same code
+// with g++ and fuzz it against the CPU oracle without a GPU.  That host build is test
+// infrastructure only: the shipped library (ppad_capi.cu) contains device code only and has no
+// CPU path.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define PPAD_HD __host__ __device__ __forceinline__
+#else
+#define PPAD_HD inline
+#endif
+
+namespace ppad {
+
+// ---------------------------------------------------------------------------------------------
+// small portability shims (device intrinsics / host builtins)
+// ---------------------------------------------------------------------------------------------
+PPAD_HD int popc(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+PPAD_HD int popc(uint64_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __popcll(x);
+#else
+    return __builtin_popcountll(x);
+#endif
+}
+// index of the lowest set bit (x != 0)
+PPAD_HD int ctz(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+PPAD_HD int ctz(uint64_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __ffsll((long long)x) - 1;
+#else
+    return __builtin_ctzll(x);
+#endif
+}
+// IEEE-754 round-to-nearest double ops that can never be contracted into an FMA: the reward
+// (game.py:157-199) is order- and contraction-sensitive.  Host build uses -ffp-contract=off.
+PPAD_HD double dmul(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+PPAD_HD double dadd(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+PPAD_HD uint32_t mulhi32(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-board fault bits and info word (mirrors include/ppad_b200.h)
+// ---------------------------------------------------------------------------------------------
+enum : uint32_t {
+    FLAG_REJECTED = 0x01, FLAG_SKYFALL_EXHAUSTED = 0x02, FLAG_CASCADE_CAP = 0x04, FLAG_NO_LEGAL_MOVE = 0x08,
+    FLAG_BAD_ACTION = 0x10, FLAG_RESET_CAP = 0x20, FLAG_UNSUPPORTED_ORB = 0x40, FLAG_EPISODE_DONE = 0x80
+};
+enum : uint32_t { STREAM_SKYFALL = 0, STREAM_ACTION = 1, STREAM_RESET = 2, STREAM_FINGER = 3, STREAM_POLICY = 4 };
+enum : int { ACT_UP = 0, ACT_DOWN = 1, ACT_LEFT = 2, ACT_RIGHT = 3, ACT_PASS = 4 };
+
+PPAD_HD uint32_t sat255(int v) { return v > 255 ? 255u : (uint32_t)v; }
+PPAD_HD uint32_t make_info(int n_combos, int depth, int consumed, uint32_t flags)
+{
+    return sat255(n_combos) | (sat255(depth) << 8) | (sat255(consumed) << 16) | ((flags & 0xFFu) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+// geometry
+// ---------------------------------------------------------------------------------------------
+template <bool WIDE> struct WordOf { typedef uint32_t type; };
+template <> struct WordOf<true> { typedef uint64_t type; };
+
+template <int R_, int C_>
+struct Geom {
+    static constexpr int R = R_, C = C_, CELLS = R_ * C_;
+    static_assert(CELLS <= 64 && R_ >= 3 && C_ >= 3, "unsupported board size");
+    typedef typename WordOf<(CELLS > 32)>::type W;
+    static constexpr int WBITS = 8 * (int)sizeof(W);
+    static constexpr W ONE = 1;
+    static constexpr W BOARD = CELLS == WBITS ? ~(W)0 : (((W)1 << (CELLS % WBITS)) - 1);
+    static constexpr W col_mask(int c)
+    {
+        W m = 0;
+        for (int r = 0; r < R_; r++) m |= (W)1 << (r * C_ + c);
+        return m;
+    }
+    static constexpr W row_mask(int r) { return (((W)1 << C_) - 1) << (r * C_); }
+    static constexpr W NOT_LASTCOL = BOARD & ~col_mask(C_ - 1);
+    static constexpr W NOT_FIRSTCOL = BOARD & ~col_mask(0);
+    static constexpr W NOT_LASTROW = BOARD & ~row_mask(R_ - 1);
+    static constexpr int OBS_CH = 7;                      // agent01.py:263 fixes 7 channels
+    static constexpr int OBS_ELEMS = CELLS * OBS_CH;      // 210 (5x6) / 294 (6x7)
+    // bytes of one packed state record in HBM
+    static constexpr int STATE_BYTES = sizeof(W) == 4 ? 16 : 32;
+};
+
+template <class G>
+struct Board {
+    typename G::W b0, b1, b2;
+};
+
+// meta word: finger cell [0,6) | previous action [6,9) | accepted moves this episode [9,25)
+PPAD_HD uint32_t meta_pack(int finger, int prev, int moves)
+{
+    return (uint32_t)finger | ((uint32_t)prev << 6) | ((uint32_t)moves << 9);
+}
+PPAD_HD int meta_finger(uint32_t m) { return (int)(m & 63u); }
+PPAD_HD int meta_prev(uint32_t m) { return (int)((m >> 6) & 7u); }
+PPAD_HD int meta_moves(uint32_t m) { return (int)((m >> 9) & 0xFFFFu); }
+
+template <class G>
+struct State {
+    Board<G> b;
+    uint32_t meta;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011).  Counter = (env_lo, env_hi, step, stream << 24 | block),
+// key = seed: results do not depend on how envs are sharded over GPUs.
+// ---------------------------------------------------------------------------------------------
+struct U4 {
+    uint32_t x, y, z, w;
+};
+
+PPAD_HD U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t lo0 = 0xD2511F53u * c.x, hi0 = mulhi32(0xD2511F53u, c.x);
+        const uint32_t lo1 = 0xCD9E8D57u * c.z, hi1 = mulhi32(0xCD9E8D57u, c.z);
+        U4 n;
+        n.x = hi1 ^ c.y ^ k0;
+        n.y = lo1;
+        n.z = hi0 ^ c.w ^ k1;
+        n.w = lo0;
+        c = n;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return c;
+}
+
+struct RngKey {
+    uint32_t k0, k1, env_lo, env_hi, step;
+};
+
+// the d-th 32-bit draw of (env, step, stream)
+PPAD_HD uint32_t philox_draw(const RngKey &k, uint32_t stream, uint32_t d)
+{
+    U4 c;
+    c.x = k.env_lo;
+    c.y = k.env_hi;
+    c.z = k.step;
+    c.w = (stream << 24) | (d >> 2);
+    const U4 o = philox4x32_10(c, k.k0, k.k1);
+    const uint32_t l = d & 3u;
+    return l == 0 ? o.x : (l == 1 ? o.y : (l == 2 ? o.z : o.w));
+}
+
+// Categorical skyfall draw.  game.py:458-470 returns the first i with cumsum(prob)[i] >= u and
+// prob[i] > 0; with u = x / 2^32 that is x <= thr[i] for thr[i] = floor(cumsum[i] * 2^32) (host
+// computes thr, tests/test_host_logic.py checks it against the float rule).  valid bit i = prob[i] > 0.
+struct SkyfallTable {
+    uint32_t thr[7];
+    uint32_t valid;
+};
+
+PPAD_HD int orb_from_u32(const SkyfallTable &t, uint32_t x)
+{
+    int orb = 6;   // host guarantees the last valid type has thr = 0xFFFFFFFF, so this is never kept
+#pragma unroll
+    for (int i = 6; i >= 0; i--)
+        if (x <= t.thr[i] && ((t.valid >> i) & 1u)) orb = i;
+    return orb;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Orb source: an injected per-board sequence first (4-bit nibbles, 8 per uint32, orb d in word
+// d >> 3 at bit 4 * (d & 7)), then the Philox stream at the same draw index d.
+// ---------------------------------------------------------------------------------------------
+struct OrbSource {
+    const uint32_t *slab;   // this board's words, or nullptr
+    int n_inj;              // injected orbs available; < 0 = pure Philox (no EXHAUSTED flag)
+    int cursor;             // orbs handed out so far
+    uint32_t stream;
+    uint32_t word;          // cached slab word
+    int word_idx;
+    U4 blk;                 // cached Philox block
+    int blk_idx;
+    bool exhausted;
+
+    PPAD_HD void init(const uint32_t *slab_, int n_inj_, uint32_t stream_)
+    {
+        slab = slab_;
+        n_inj = slab_ ? n_inj_ : -1;
+        cursor = 0;
+        stream = stream_;
+        word = 0;
+        word_idx = -1;
+        blk_idx = -1;
+        exhausted = false;
+        blk.x = blk.y = blk.z = blk.w = 0;
+    }
+
+    PPAD_HD int next(const RngKey &key, const SkyfallTable &sky)
+    {
+        const int d = cursor++;
+        if (d < n_inj) {
+            const int wi = d >> 3;
+            if (wi != word_idx) {
+                word = slab[wi];
+                word_idx = wi;
+            }
+            return (int)((word >> (4 * (d & 7))) & 15u);
+        }
+        if (n_inj >= 0) exhausted = true;
+        const int bi = d >> 2;
+        if (bi != blk_idx) {
+            U4 c;
+            c.x = key.env_lo;
+            c.y = key.env_hi;
+            c.z = key.step;
+            c.w = (stream << 24) | (uint32_t)bi;
+            blk = philox4x32_10(c, key.k0, key.k1);
+            blk_idx = bi;
+        }
+        const int l = d & 3;
+        const uint32_t x = l == 0 ? blk.x : (l == 1 ? blk.y : (l == 2 ? blk.z : blk.w));
+        return orb_from_u32(sky, x);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Team table for the reward (game.py:157-199, parameters.py:54-89): for each attack colour
+// (orb types 0..4) the (multiplier, atk) of the matching units in team order.
+// ---------------------------------------------------------------------------------------------
+#define PPAD_MAX_TEAM 8
+struct TeamTable {
+    double mult[5][PPAD_MAX_TEAM];
+    double atk[5][PPAD_MAX_TEAM];
+    int32_t n[8];   // n[0..4] used
+};
+
+struct Tally {
+    double t0, t1, t2, t3, t4;   // damage_tracker by orb type: red, blue, green, light, dark
+    int n_combos;
+
+    PPAD_HD void init()
+    {
+        t0 = t1 = t2 = t3 = t4 = 0.0;
+        n_combos = 0;
+    }
+    // one combo (game.py:169-190): tracker[colour] += (mult * (1 + 0.25 (N - 3))) * atk per unit
+    PPAD_HD void add(const TeamTable &team, int colour, int N)
+    {
+        n_combos++;
+        if (colour > 4) return;   // heal / jammer: counts as a combo, no unit matches
+        const double f = 1.0 + 0.25 * (double)(N - 3);   // exact
+        const int nu = team.n[colour];
+        for (int u = 0; u < nu; u++) {
+            const double t = dmul(dmul(team.mult[colour][u], f), team.atk[colour][u]);
+            t0 = colour == 0 ? dadd(t0, t) : t0;
+            t1 = colour == 1 ? dadd(t1, t) : t1;
+            t2 = colour == 2 ? dadd(t2, t) : t2;
+            t3 = colour == 3 ? dadd(t3, t) : t3;
+            t4 = colour == 4 ? dadd(t4, t) : t4;
+        }
+    }
+    // game.py:193-199: every tracker *= 1 + 0.25 (#combos - 1); sum in dict order blue, red,
+    // green, dark, light starting from the int 0
+    PPAD_HD double total() const
+    {
+        const double m = 1.0 + 0.25 * (double)(n_combos - 1);
+        double s = dmul(t1, m);
+        s = dadd(s, dmul(t0, m));
+        s = dadd(s, dmul(t2, m));
+        s = dadd(s, dmul(t4, m));
+        s = dadd(s, dmul(t3, m));
+        return s;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// board primitives
+// ---------------------------------------------------------------------------------------------
+template <class G>
+PPAD_HD typename G::W empties(const Board<G> &b)
+{
+    return b.b0 & b.b1 & b.b2;   // bits >= CELLS are zero in every plane
+}
+
+template <class G>
+PPAD_HD int code_at(const Board<G> &b, int cell)
+{
+    return (int)(((b.b0 >> cell) & 1) | (((b.b1 >> cell) & 1) << 1) | (((b.b2 >> cell) & 1) << 2));
+}
+
+template <class G>
+PPAD_HD void set_code(Board<G> &b, int cell, int code)
+{
+    typedef typename G::W W;
+    const W bit = G::ONE << cell;
+    b.b0 = (b.b0 & ~bit) | ((W)(code & 1) << cell);
+    b.b1 = (b.b1 & ~bit) | ((W)((code >> 1) & 1) << cell);
+    b.b2 = (b.b2 & ~bit) | ((W)((code >> 2) & 1) << cell);
+}
+
+// swap the codes of cells i and j (game.py:429-456)
+template <class G>
+PPAD_HD void swap_cells(Board<G> &b, int i, int j)
+{
+    typedef typename G::W W;
+    W x;
+    x = ((b.b0 >> i) ^ (b.b0 >> j)) & 1;
+    b.b0 ^= (x << i) | (x << j);
+    x = ((b.b1 >> i) ^ (b.b1 >> j)) & 1;
+    b.b1 ^= (x << i) | (x << j);
+    x = ((b.b2 >> i) ^ (b.b2 >> j)) & 1;
+    b.b2 ^= (x << i) | (x << j);
+}
+
+// Edge masks and matched cells.  er bit i: cell i is non-empty and has the colour of cell i+1 in
+// the same row; ed bit i: same for the cell below.  A 3-run is two consecutive edges
+// (utils.py:47-54).  Returns the mask of all cells lying in some 3-run.
+template <class G>
+PPAD_HD typename G::W match_mask(const Board<G> &b, typename G::W &er, typename G::W &ed)
+{
+    typedef typename G::W W;
+    constexpr int C = G::C;
+    const W ne = ~(b.b0 & b.b1 & b.b2);
+    const W xr = (b.b0 ^ (b.b0 >> 1)) | (b.b1 ^ (b.b1 >> 1)) | (b.b2 ^ (b.b2 >> 1));
+    const W xd = (b.b0 ^ (b.b0 >> C)) | (b.b1 ^ (b.b1 >> C)) | (b.b2 ^ (b.b2 >> C));
+    er = ~xr & ne & G::NOT_LASTCOL;
+    ed = ~xd & ne & G::NOT_LASTROW;
+    const W h = er & (er >> 1);
+    const W v = ed & (ed >> C);
+    return h | (h << 1) | (h << 2) | v | (v << C) | (v << (2 * C));
+}
+
+// closure of g under the same-colour adjacency (the island flood fill of utils.py:86-111)
+template <class G>
+PPAD_HD typename G::W closure(typename G::W g, typename G::W er, typename G::W ed)
+{
+    typedef typename G::W W;
+    constexpr int C = G::C;
+    for (;;) {
+        const W n = g | ((g & er) << 1) | ((g >> 1) & er) | ((g & ed) << C) | ((g >> C) & ed);
+        if (n == g) return g;
+        g = n;
+    }
+}
+
+// One cancel() (utils.py:26-70): emits (colour, N) per combo in the reference's order -- ascending
+// row-major index of each island's first cell -- then erases the matched cells.
+// Islands are taken over ALL cells of a colour (matched or not), so two runs bridged by unmatched
+// orbs of the same colour are one combo (hard part 2).
+template <class G, class F>
+PPAD_HD int cancel_board(Board<G> &b, F &&on_combo)
+{
+    typedef typename G::W W;
+    W er, ed;
+    const W m = match_mask<G>(b, er, ed);
+    if (m == 0) return 0;
+    W todo = closure<G>(m, er, ed);   // every island that holds a matched cell
+    int n = 0;
+    while (todo) {
+        const W seed = todo & (~todo + 1);          // lowest cell = that island's first cell
+        const W comp = closure<G>(seed, er, ed);
+        on_combo(code_at<G>(b, ctz(seed)), popc(comp & m));
+        todo &= ~comp;
+        n++;
+    }
+    b.b0 |= m;
+    b.b1 |= m;
+    b.b2 |= m;
+    return n;
+}
+
+// gravity (game.py:201-221): every orb with an empty cell directly below moves down one row,
+// repeated until nothing moves
+template <class G>
+PPAD_HD void drop_board(Board<G> &b)
+{
+    typedef typename G::W W;
+    constexpr int C = G::C;
+    for (;;) {
+        const W e = empties<G>(b);
+        const W fall = ~e & (e >> C) & G::BOARD;
+        if (fall == 0) return;
+        const W dst = fall << C;
+        b.b0 = (b.b0 & ~dst) | ((b.b0 & fall) << C) | fall;
+        b.b1 = (b.b1 & ~dst) | ((b.b1 & fall) << C) | fall;
+        b.b2 = (b.b2 & ~dst) | ((b.b2 & fall) << C) | fall;
+    }
+}
+
+// skyfall (game.py:232-256): empties in ascending cell index = row-major, one draw each
+template <class G>
+PPAD_HD void fill_board(Board<G> &b, OrbSource &src, const RngKey &key, const SkyfallTable &sky)
+{
+    typedef typename G::W W;
+    W e = empties<G>(b);
+    while (e) {
+        const W bit = e & (~e + 1);
+        const int code = src.next(key, sky);
+        if (!(code & 1)) b.b0 ^= bit;
+        if (!(code & 2)) b.b1 ^= bit;
+        if (!(code & 4)) b.b2 ^= bit;
+        e ^= bit;
+    }
+}
+
+// fill_board(reset=True): every cell gets a draw, row-major
+template <class G>
+PPAD_HD void refill_all(Board<G> &b, OrbSource &src, const RngKey &key, const SkyfallTable &sky)
+{
+    typedef typename G::W W;
+    W p0 = 0, p1 = 0, p2 = 0;
+    for (int i = 0; i < G::CELLS; i++) {
+        const int code = src.next(key, sky);
+        p0 |= (W)(code & 1) << i;
+        p1 |= (W)((code >> 1) & 1) << i;
+        p2 |= (W)((code >> 2) & 1) << i;
+    }
+    b.b0 = p0;
+    b.b1 = p1;
+    b.b2 = p2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// calculate_reward (game.py:364-405) on a copy of the board
+// ---------------------------------------------------------------------------------------------
+struct ResolveOut {
+    double reward;
+    int n_combos, depth, consumed;
+    uint32_t flags;
+};
+
+struct LogSink {
+    uint16_t *log;   // colour | N << 8 per combo, may be nullptr
+    int cap, n;
+    PPAD_HD void put(int colour, int N)
+    {
+        if (log && n < cap) log[n] = (uint16_t)(colour | (N << 8));
+        n++;
+    }
+};
+
+template <class G>
+PPAD_HD ResolveOut resolve_board(Board<G> &b, bool skyfall_damage, int cascade_cap, const TeamTable &team,
+                                 OrbSource &src, const RngKey &key, const SkyfallTable &sky, LogSink &sink)
+{
+    Tally tally;
+    tally.init();
+    ResolveOut out;
+    out.depth = 0;
+    out.flags = 0;
+    for (;;) {
+        const int m = cancel_board<G>(b, [&](int colour, int N) {
+            tally.add(team, colour, N);
+            sink.put(colour, N);
+        });
+        if (m == 0) break;
+        out.depth++;
+        if (!skyfall_damage) break;
+        if (cascade_cap > 0 && out.depth >= cascade_cap) {
+            out.flags |= FLAG_CASCADE_CAP;
+            break;
+        }
+        drop_board<G>(b);
+        fill_board<G>(b, src, key, sky);
+    }
+    if (src.exhausted) out.flags |= FLAG_SKYFALL_EXHAUSTED;
+    out.n_combos = tally.n_combos;
+    out.consumed = src.cursor;
+    out.reward = tally.n_combos ? tally.total() : 0.0;
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// moves, legality, random policy
+// ---------------------------------------------------------------------------------------------
+// player.py:52-62: bit a set = action a allowed (not the reverse of prev, not off the board)
+template <class G>
+PPAD_HD int legal_mask(int finger, int prev)
+{
+    const int r = finger / G::C, c = finger - r * G::C;
+    int m = 15;
+    if (r <= 0) m &= ~1;
+    if (r >= G::R - 1) m &= ~2;
+    if (c <= 0) m &= ~4;
+    if (c >= G::C - 1) m &= ~8;
+    if (prev < 4) m &= ~(1 << (prev ^ 1));   // opposite of up(0)/down(1)/left(2)/right(3)
+    return m;
+}
+
+// uniform over the legal set, one Philox draw (stream ACTION, draw 0); -1 when the set is empty
+PPAD_HD int sample_from_mask(int mask, uint32_t x)
+{
+    const int n = popc((uint32_t)mask);
+    if (n == 0) return -1;
+    int pick = (int)mulhi32(x, (uint32_t)n);
+    int a = -1;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const bool on = (mask >> i) & 1;
+        if (on && pick == 0 && a < 0) a = i;
+        if (on) pick--;
+    }
+    return a;
+}
+
+// apply_action (game.py:122-155): false = 'rejected' (off the board), state untouched
+template <class G>
+PPAD_HD bool apply_move(State<G> &s, int action)
+{
+    const int f = meta_finger(s.meta);
+    const int r = f / G::C, c = f - r * G::C;
+    int t;
+    if (action == ACT_UP) {
+        if (r - 1 < 0) return false;
+        t = f - G::C;
+    } else if (action == ACT_DOWN) {
+        if (r + 1 > G::R - 1) return false;
+        t = f + G::C;
+    } else if (action == ACT_LEFT) {
+        if (c - 1 < 0) return false;
+        t = f - 1;
+    } else {
+        if (c + 1 > G::C - 1) return false;
+        t = f + 1;
+    }
+    swap_cells<G>(s.b, f, t);
+    int moves = meta_moves(s.meta);
+    if (moves < 0xFFFF) moves++;
+    s.meta = meta_pack(t, action, moves);
+    return true;
+}
+
+// reset (game.py:303-315): refill the whole board until it holds no 3-run
+template <class G>
+PPAD_HD uint32_t reset_board(State<G> &s, int reset_cap, OrbSource &src, const RngKey &key, const SkyfallTable &sky,
+                             int finger_in)
+{
+    typedef typename G::W W;
+    uint32_t flags = 0;
+    int attempts = 0;
+    for (;;) {
+        refill_all<G>(s.b, src, key, sky);
+        attempts++;
+        W er, ed;
+        if (match_mask<G>(s.b, er, ed) == 0) break;
+        if (reset_cap > 0 && attempts >= reset_cap) {
+            flags |= FLAG_RESET_CAP;
+            break;
+        }
+    }
+    if (src.exhausted) flags |= FLAG_SKYFALL_EXHAUSTED;
+    int finger = finger_in;
+    if (finger < 0) {
+        const int r = (int)mulhi32(philox_draw(key, STREAM_FINGER, 0), (uint32_t)G::R);
+        const int c = (int)mulhi32(philox_draw(key, STREAM_FINGER, 1), (uint32_t)G::C);
+        finger = r * G::C + c;
+    }
+    s.meta = meta_pack(finger, ACT_PASS, 0);   // previous_action = 'pass' (game.py:299)
+    return flags;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one env step of one board (the kernel body; see include/ppad_b200.h: ppad_step)
+// ---------------------------------------------------------------------------------------------
+struct StepParams {
+    RngKey key;              // env_lo/env_hi are overwritten per board
+    SkyfallTable sky;
+    TeamTable team;
+    int32_t skyfall_damage, cascade_cap, reset_cap;
+    int32_t eval_moves, auto_reset, max_moves;
+    int32_t n_inj, slab_words, log_cap;
+};
+
+struct StepOut {
+    double reward;
+    uint32_t info;
+    int action;
+};
+
+template <class G>
+PPAD_HD StepOut step_board(State<G> &s, Board<G> &final_board, const StepParams &p, uint64_t env, int action_in,
+                           const uint32_t *slab, uint16_t *log)
+{
+    RngKey key = p.key;
+    key.env_lo = (uint32_t)env;
+    key.env_hi = (uint32_t)(env >> 32);
+    uint32_t flags = 0;
+    int action = action_in;   // < 0: sample
+    if (action < 0) {
+        if (p.max_moves > 0 && meta_moves(s.meta) >= p.max_moves) {
+            action = ACT_PASS;   // episode length cap (simulation.py:50-52)
+        } else {
+            action = sample_from_mask(legal_mask<G>(meta_finger(s.meta), meta_prev(s.meta)),
+                                      philox_draw(key, STREAM_ACTION, 0));
+            if (action < 0) {
+                action = 255;
+                flags |= FLAG_NO_LEGAL_MOVE;
+            }
+        }
+    }
+    bool evaluate = false;
+    if (action == ACT_PASS) {
+        evaluate = true;
+    } else if (action < ACT_PASS) {
+        if (apply_move<G>(s, action)) evaluate = p.eval_moves != 0;
+        else flags |= FLAG_REJECTED;
+    } else if (!(flags & FLAG_NO_LEGAL_MOVE)) {
+        flags |= FLAG_BAD_ACTION;
+    }
+    StepOut out;
+    out.action = action;
+    out.reward = 0.0;
+    int n_combos = 0, depth = 0, consumed = 0;
+    final_board = s.b;
+    if (evaluate) {
+        OrbSource src;
+        src.init(slab, p.n_inj, STREAM_SKYFALL);
+        LogSink sink;
+        sink.log = log;
+        sink.cap = p.log_cap;
+        sink.n = 0;
+        const ResolveOut r = resolve_board<G>(final_board, p.skyfall_damage != 0, p.cascade_cap, p.team, src, key,
+                                              p.sky, sink);
+        out.reward = r.reward;
+        n_combos = r.n_combos;
+        depth = r.depth;
+        consumed = r.consumed;
+        flags |= r.flags;
+    }
+    if (action == ACT_PASS && p.auto_reset) {
+        OrbSource src;
+        src.init(nullptr, -1, STREAM_RESET);
+        flags |= FLAG_EPISODE_DONE | reset_board<G>(s, p.reset_cap, src, key, p.sky, -1);
+    }
+    out.info = make_info(n_combos, depth, consumed, flags);
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// conversions between plain int boards and packed state (value -1 -> 7; 0..6 kept; others flagged)
+// ---------------------------------------------------------------------------------------------
+template <class G, class T>
+PPAD_HD uint32_t pack_cells(Board<G> &b, const T *cells)
+{
+    typedef typename G::W W;
+    W p0 = 0, p1 = 0, p2 = 0;
+    uint32_t flags = 0;
+    for (int i = 0; i < G::CELLS; i++) {
+        const long long v = (long long)cells[i];
+        int code;
+        if (v == -1) code = 7;
+        else if (v >= 0 && v <= 6) code = (int)v;
+        else {
+            code = 7;
+            flags |= FLAG_UNSUPPORTED_ORB;
+        }
+        p0 |= (W)(code & 1) << i;
+        p1 |= (W)((code >> 1) & 1) << i;
+        p2 |= (W)((code >> 2) & 1) << i;
+    }
+    b.b0 = p0;
+    b.b1 = p1;
+    b.b2 = p2;
+    return flags;
+}
+
+template <class G, class T>
+PPAD_HD void unpack_cells(const Board<G> &b, T *cells)
+{
+    for (int i = 0; i < G::CELLS; i++) {
+        const int code = code_at<G>(b, i);
+        cells[i] = (T)(code == 7 ? -1 : code);
+    }
+}
+
+}   // namespace ppad

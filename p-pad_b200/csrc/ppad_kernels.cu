@@ -1,0 +1,624 @@
+// ppad_kernels.cu -- sm_100a kernels and the C ABI of include/ppad_b200.h.
+//
+// Thread-per-board: a warp owns 32 consecutive boards, state I/O is one (or two) 16-byte vector
+// accesses per board, fully coalesced.  The one-hot observation -- the only large stream, 840 B
+// per 5x6 board against 16 B of state -- is emitted warp-cooperatively: every lane builds the
+// 210-bit occupancy mask of its board, the warp lays the 32 masks end to end in shared memory as one
+// 6720-bit stream, and then each lane expands 4 bits at a time through a 16-entry float4 table into
+// 16-byte streaming stores to consecutive addresses (512 contiguous bytes per warp instruction).
+//
+// Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/ppad_b200.h"
+#include "ppad_core.cuh"
+#include "ppad_params.h"
+
+using namespace ppad;
+
+namespace {
+
+constexpr int BLOCK = 256;
+
+// ------------------------------------------------------------------------------------------------
+// packed state I/O
+// ------------------------------------------------------------------------------------------------
+template <class G, bool WIDE = (sizeof(typename G::W) == 8)>
+struct StateIO;
+
+template <class G>
+struct StateIO<G, false> {
+    static __device__ __forceinline__ State<G> load(const void *base, int64_t i)
+    {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(base) + i);
+        State<G> s;
+        s.b.b0 = v.x;
+        s.b.b1 = v.y;
+        s.b.b2 = v.z;
+        s.meta = v.w;
+        return s;
+    }
+    static __device__ __forceinline__ void store(void *base, int64_t i, const Board<G> &b, uint32_t meta)
+    {
+        reinterpret_cast<uint4 *>(base)[i] = make_uint4(b.b0, b.b1, b.b2, meta);
+    }
+};
+
+template <class G>
+struct StateIO<G, true> {
+    static __device__ __forceinline__ State<G> load(const void *base, int64_t i)
+    {
+        const uint4 lo = __ldg(reinterpret_cast<const uint4 *>(base) + 2 * i);
+        const uint4 hi = __ldg(reinterpret_cast<const uint4 *>(base) + 2 * i + 1);
+        State<G> s;
+        s.b.b0 = (uint64_t)lo.x | ((uint64_t)lo.y << 32);
+        s.b.b1 = (uint64_t)lo.z | ((uint64_t)lo.w << 32);
+        s.b.b2 = (uint64_t)hi.x | ((uint64_t)hi.y << 32);
+        s.meta = hi.z;
+        return s;
+    }
+    static __device__ __forceinline__ void store(void *base, int64_t i, const Board<G> &b, uint32_t meta)
+    {
+        uint4 *p = reinterpret_cast<uint4 *>(base) + 2 * i;
+        p[0] = make_uint4((uint32_t)b.b0, (uint32_t)(b.b0 >> 32), (uint32_t)b.b1, (uint32_t)(b.b1 >> 32));
+        p[1] = make_uint4((uint32_t)b.b2, (uint32_t)(b.b2 >> 32), meta, 0u);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// one-hot observation emission (agent01.py:254-273), warp-cooperative
+// ------------------------------------------------------------------------------------------------
+template <class G>
+struct ObsGeom {
+    static constexpr int NB = G::OBS_ELEMS;          // bits (= elements) per board
+    static constexpr int NW = (NB + 31) / 32 + 1;    // words of a shifted per-board mask
+    static constexpr int CNT_LO = NB / 32;           // a board owns CNT_LO or CNT_LO + 1 stream words
+    static constexpr int WARP_WORDS = NB;            // 32 boards * NB bits / 32
+    static_assert(NB % 2 == 0, "obs tail handling assumes an even element count per board");
+};
+
+struct ObsShared {
+    float4 lut_f32[16];
+    uint32_t lut_u8[16];
+};
+
+__device__ __forceinline__ void obs_init_luts(ObsShared &sh)
+{
+    if (threadIdx.x < 16) {
+        const unsigned b = threadIdx.x;
+        sh.lut_f32[b] = make_float4((b & 1) ? 1.f : 0.f, (b & 2) ? 1.f : 0.f, (b & 4) ? 1.f : 0.f, (b & 8) ? 1.f : 0.f);
+        sh.lut_u8[b] = (b & 1) | ((b & 2) << 7) | ((b & 4) << 14) | ((b & 8) << 21);
+    }
+}
+
+// Every lane of the warp must call this (lanes without a board pass valid = false).
+// `stream` is this warp's NB-word shared buffer; obs_warp points at the obs of the warp's first board.
+template <class G>
+__device__ __forceinline__ void emit_obs(const State<G> &s, bool valid, int n_valid, uint32_t *stream,
+                                         const ObsShared &sh, void *obs_warp, int obs_dtype)
+{
+    typedef ObsGeom<G> OG;
+    constexpr int NB = OG::NB, NW = OG::NW;
+    const int lane = threadIdx.x & 31;
+
+    // 1. this board's NB-bit mask: bit 7 * cell + channel
+    uint32_t w[NW];
+#pragma unroll
+    for (int j = 0; j < NW; j++) w[j] = 0;
+    if (valid) {
+        const int finger = meta_finger(s.meta);
+#pragma unroll
+        for (int i = 0; i < G::CELLS; i++) {
+            uint32_t oh = (1u << code_at<G>(s.b, i)) & 0x3Fu;   // channels 0..5 = colour planes
+            oh |= (i == finger) ? 0x40u : 0u;                   // channel 6 = finger
+            constexpr int dummy = 0;
+            (void)dummy;
+            const int pos = 7 * i, wi = pos >> 5, sft = pos & 31;
+            w[wi] |= oh << sft;
+            if (sft > 25) w[wi + 1] |= oh >> (32 - sft);
+        }
+    }
+
+    // 2. place it at bit NB * lane of the warp's stream; neighbours share one boundary word
+    const int off = NB * lane, word0 = off >> 5, sft = off & 31;
+    const int cnt = ((NB * (lane + 1)) >> 5) - word0;
+    uint32_t t[NW];
+    t[0] = w[0] << sft;
+#pragma unroll
+    for (int j = 1; j < NW; j++) t[j] = __funnelshift_l(w[j - 1], w[j], sft);
+    const uint32_t tail = cnt == OG::CNT_LO ? t[OG::CNT_LO] : t[OG::CNT_LO + 1];
+    uint32_t carry = __shfl_up_sync(0xFFFFFFFFu, tail, 1);
+    if (lane == 0) carry = 0;
+    t[0] |= carry;
+#pragma unroll
+    for (int j = 0; j <= OG::CNT_LO; j++)
+        if (j < cnt) stream[word0 + j] = t[j];
+    __syncwarp();
+
+    // 3. expand: 4 stream bits -> one 16-byte store, consecutive lanes -> consecutive addresses
+    const int valid_elems = n_valid * NB;
+    if (obs_dtype == PPAD_OBS_F32) {
+        float4 *out4 = reinterpret_cast<float4 *>(obs_warp);
+        const int sh4 = (lane & 7) * 4;
+#pragma unroll 4
+        for (int q = lane; q < 8 * NB; q += 32) {
+            const int e = 4 * q;
+            if (e >= valid_elems) break;
+            const float4 v = sh.lut_f32[(stream[q >> 3] >> sh4) & 15u];
+            if (e + 4 <= valid_elems) __stcs(out4 + q, v);
+            else __stcs(reinterpret_cast<float2 *>(out4 + q), make_float2(v.x, v.y));
+        }
+    } else {
+        uint4 *out4 = reinterpret_cast<uint4 *>(obs_warp);
+        const int sh16 = (lane & 1) * 16;
+        for (int q = lane; q < 2 * NB; q += 32) {
+            const int e = 16 * q;
+            if (e >= valid_elems) break;
+            const uint32_t b16 = (stream[q >> 1] >> sh16) & 0xFFFFu;
+            const uint4 v = make_uint4(sh.lut_u8[b16 & 15u], sh.lut_u8[(b16 >> 4) & 15u], sh.lut_u8[(b16 >> 8) & 15u],
+                                       sh.lut_u8[b16 >> 12]);
+            if (e + 16 <= valid_elems) {
+                __stcs(out4 + q, v);
+            } else {
+                uint8_t *o = reinterpret_cast<uint8_t *>(out4 + q);
+                for (int k = 0; k < valid_elems - e; k++) o[k] = (uint8_t)((b16 >> k) & 1u);
+            }
+        }
+    }
+    __syncwarp();
+}
+
+template <class G>
+__device__ __forceinline__ void *obs_warp_ptr(void *obs, int64_t warp_board0, int obs_dtype)
+{
+    const size_t elems = (size_t)warp_board0 * G::OBS_ELEMS;
+    return obs_dtype == PPAD_OBS_F32 ? (void *)(reinterpret_cast<float *>(obs) + elems)
+                                     : (void *)(reinterpret_cast<uint8_t *>(obs) + elems);
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+struct StepKernelArgs {
+    StepParams p;
+    int64_t n;
+    uint64_t env0;
+    void *state;
+    const uint8_t *actions;
+    const uint32_t *slab;
+    uint8_t *action_out;
+    double *reward;
+    uint32_t *info;
+    void *final_state;
+    uint16_t *combo_log;
+    void *obs;
+    int32_t obs_dtype;
+};
+
+template <class G, bool OBS>
+__global__ void __launch_bounds__(BLOCK) step_kernel(const __grid_constant__ StepKernelArgs a)
+{
+    __shared__ ObsShared obs_sh;
+    __shared__ uint32_t obs_stream[OBS ? (BLOCK / 32) * ObsGeom<G>::WARP_WORDS : 1];
+    if (OBS) {
+        obs_init_luts(obs_sh);
+        __syncthreads();
+    }
+    const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    const bool valid = i < a.n;
+    State<G> s;
+    s.b.b0 = s.b.b1 = s.b.b2 = 0;
+    s.meta = 0;
+    if (valid) {
+        s = StateIO<G>::load(a.state, i);
+        int action = -1;
+        if (a.actions) {
+            action = a.actions[i];
+            if (action == PPAD_SAMPLE) action = -1;
+        }
+        Board<G> fin;
+        const StepOut o = step_board<G>(s, fin, a.p, a.env0 + (uint64_t)i, action,
+                                        a.slab ? a.slab + (size_t)i * a.p.slab_words : nullptr,
+                                        a.combo_log ? a.combo_log + (size_t)i * a.p.log_cap : nullptr);
+        StateIO<G>::store(a.state, i, s.b, s.meta);
+        if (a.action_out) a.action_out[i] = (uint8_t)o.action;
+        if (a.reward) a.reward[i] = o.reward;
+        if (a.info) a.info[i] = o.info;
+        if (a.final_state) StateIO<G>::store(a.final_state, i, fin, s.meta);
+    }
+    if (OBS) {
+        const int64_t warp0 = i - (threadIdx.x & 31);
+        if (warp0 < a.n) {
+            const int n_valid = (int)(a.n - warp0 < 32 ? a.n - warp0 : 32);
+            emit_obs<G>(s, valid, n_valid, obs_stream + (threadIdx.x >> 5) * ObsGeom<G>::WARP_WORDS, obs_sh,
+                        obs_warp_ptr<G>(a.obs, warp0, a.obs_dtype), a.obs_dtype);
+        }
+    }
+}
+
+template <class G>
+__global__ void __launch_bounds__(BLOCK) encode_kernel(int64_t n, const void *state, void *obs, int obs_dtype)
+{
+    __shared__ ObsShared obs_sh;
+    __shared__ uint32_t obs_stream[(BLOCK / 32) * ObsGeom<G>::WARP_WORDS];
+    obs_init_luts(obs_sh);
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    const bool valid = i < n;
+    State<G> s;
+    s.b.b0 = s.b.b1 = s.b.b2 = 0;
+    s.meta = 0;
+    if (valid) s = StateIO<G>::load(state, i);
+    const int64_t warp0 = i - (threadIdx.x & 31);
+    if (warp0 < n) {
+        const int n_valid = (int)(n - warp0 < 32 ? n - warp0 : 32);
+        emit_obs<G>(s, valid, n_valid, obs_stream + (threadIdx.x >> 5) * ObsGeom<G>::WARP_WORDS, obs_sh,
+                    obs_warp_ptr<G>(obs, warp0, obs_dtype), obs_dtype);
+    }
+}
+
+struct ResetKernelArgs {
+    StepParams p;
+    int64_t n;
+    uint64_t env0;
+    const uint32_t *slab;
+    const int32_t *fingers_in;
+    void *state;
+    uint8_t *flags;
+    uint8_t *consumed;
+};
+
+template <class G>
+__global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ ResetKernelArgs a)
+{
+    const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= a.n) return;
+    RngKey key = a.p.key;
+    const uint64_t env = a.env0 + (uint64_t)i;
+    key.env_lo = (uint32_t)env;
+    key.env_hi = (uint32_t)(env >> 32);
+    OrbSource src;
+    src.init(a.slab ? a.slab + (size_t)i * a.p.slab_words : nullptr, a.p.n_inj, STREAM_RESET);
+    int finger = -1;
+    if (a.fingers_in) finger = a.fingers_in[2 * i] * G::C + a.fingers_in[2 * i + 1];
+    State<G> s;
+    const uint32_t flags = reset_board<G>(s, a.p.reset_cap, src, key, a.p.sky, finger);
+    StateIO<G>::store(a.state, i, s.b, s.meta);
+    if (a.flags) a.flags[i] = (uint8_t)flags;
+    if (a.consumed) a.consumed[i] = (uint8_t)sat255(src.cursor);
+}
+
+template <class G, class T>
+__global__ void __launch_bounds__(BLOCK) pack_kernel(int64_t n, const T *boards, const T *fingers, const uint8_t *prev,
+                                                     const uint16_t *moves, void *state, uint8_t *flags)
+{
+    const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= n) return;
+    Board<G> b;
+    const uint32_t f = pack_cells<G, T>(b, boards + (size_t)i * G::CELLS);
+    const int finger = (int)fingers[2 * i] * G::C + (int)fingers[2 * i + 1];
+    StateIO<G>::store(state, i, b, meta_pack(finger, prev ? prev[i] : ACT_PASS, moves ? moves[i] : 0));
+    if (flags) flags[i] = (uint8_t)f;
+}
+
+template <class G, class T>
+__global__ void __launch_bounds__(BLOCK) unpack_kernel(int64_t n, const void *state, T *boards, T *fingers, uint8_t *prev,
+                                                       uint16_t *moves)
+{
+    const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= n) return;
+    const State<G> s = StateIO<G>::load(state, i);
+    if (boards) unpack_cells<G, T>(s.b, boards + (size_t)i * G::CELLS);
+    const int f = meta_finger(s.meta);
+    if (fingers) {
+        fingers[2 * i] = (T)(f / G::C);
+        fingers[2 * i + 1] = (T)(f % G::C);
+    }
+    if (prev) prev[i] = (uint8_t)meta_prev(s.meta);
+    if (moves) moves[i] = (uint16_t)meta_moves(s.meta);
+}
+
+template <class G>
+__global__ void __launch_bounds__(BLOCK) cancel_kernel(int64_t n, void *state, uint8_t *n_combos, uint16_t *combo_log,
+                                                       int log_cap)
+{
+    const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= n) return;
+    State<G> s = StateIO<G>::load(state, i);
+    LogSink sink;
+    sink.log = combo_log ? combo_log + (size_t)i * log_cap : nullptr;
+    sink.cap = log_cap;
+    sink.n = 0;
+    const int m = cancel_board<G>(s.b, [&](int colour, int N) { sink.put(colour, N); });
+    StateIO<G>::store(state, i, s.b, s.meta);
+    if (n_combos) n_combos[i] = (uint8_t)sat255(m);
+}
+
+template <class G>
+__global__ void __launch_bounds__(BLOCK) legal_kernel(int64_t n, const void *state, uint8_t *mask)
+{
+    const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= n) return;
+    const State<G> s = StateIO<G>::load(state, i);
+    const int f = meta_finger(s.meta);
+    const int off = (~legal_mask<G>(f, ACT_PASS)) & 15;   // off-board moves only (utils.py:73-83)
+    mask[i] = (uint8_t)(legal_mask<G>(f, meta_prev(s.meta)) | (off << 4));
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+thread_local std::string g_last_error;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int status, const std::string &msg)
+{
+    g_last_error = msg;
+    return status;
+}
+
+int cuda_check(cudaError_t e, const char *what)
+{
+    if (e == cudaSuccess) return PPAD_OK;
+    return fail(PPAD_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+int after_launch(const char *name)
+{
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cuda_check(cudaGetLastError(), name);
+}
+
+inline unsigned grid_for(int64_t n) { return (unsigned)((n + BLOCK - 1) / BLOCK); }
+
+typedef Geom<5, 6> G56;
+typedef Geom<6, 7> G67;
+
+}   // namespace
+
+struct ppad_ctx {
+    ppad_config cfg;
+    int device;
+    int geom;   // 0 = 5x6, 1 = 6x7
+    StepParams base;
+};
+
+#define PPAD_DISPATCH(ctx, EXPR)                 \
+    do {                                         \
+        if ((ctx)->geom == 0) { typedef G56 G; EXPR; } \
+        else { typedef G67 G; EXPR; }            \
+    } while (0)
+
+template <class G, class T>
+static void launch_pack(int64_t n, const void *boards, const void *fingers, const uint8_t *prev, const uint16_t *moves,
+                        void *state, uint8_t *flags, cudaStream_t st)
+{
+    pack_kernel<G, T><<<grid_for(n), BLOCK, 0, st>>>(n, (const T *)boards, (const T *)fingers, prev, moves, state, flags);
+}
+
+template <class G, class T>
+static void launch_unpack(int64_t n, const void *state, void *boards, void *fingers, uint8_t *prev, uint16_t *moves,
+                          cudaStream_t st)
+{
+    unpack_kernel<G, T><<<grid_for(n), BLOCK, 0, st>>>(n, state, (T *)boards, (T *)fingers, prev, moves);
+}
+
+extern "C" {
+
+void ppad_default_config(ppad_config *cfg)
+{
+    // parameters.py:54-89 (default_team) and :43 (default_skyfall); orb types per parameters.py:20-29
+    static const int c1[6] = {4, 3, 1, 2, 0, 1};
+    static const int c2[6] = {4, 3, 2, 0, 1, -1};
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->rows = 5;
+    cfg->cols = 6;
+    cfg->skyfall_damage = 1;
+    cfg->cascade_cap = 255;
+    cfg->reset_cap = 64;
+    cfg->team_size = 6;
+    for (int i = 0; i < 6; i++) {
+        cfg->team_color_1[i] = c1[i];
+        cfg->team_color_2[i] = c2[i];
+        cfg->team_atk[i] = 1000.0;
+    }
+    for (int i = 0; i < 6; i++) cfg->skyfall[i] = 1.0 / 6;
+}
+
+int ppad_abi_version(void) { return PPAD_ABI_VERSION; }
+
+const char *ppad_strerror(int status)
+{
+    switch (status) {
+    case PPAD_OK: return "ok";
+    case PPAD_ERR_INVALID: return "invalid argument";
+    case PPAD_ERR_UNSUPPORTED: return "unsupported configuration";
+    case PPAD_ERR_CUDA: return "CUDA error";
+    default: return "unknown status";
+    }
+}
+
+const char *ppad_last_error(void) { return g_last_error.c_str(); }
+
+int64_t ppad_state_bytes(int rows, int cols)
+{
+    if (rows == 5 && cols == 6) return G56::STATE_BYTES;
+    if (rows == 6 && cols == 7) return G67::STATE_BYTES;
+    return -1;
+}
+
+uint64_t ppad_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int ppad_create(const ppad_config *cfg, int device, ppad_ctx **out)
+{
+    if (!cfg || !out) return fail(PPAD_ERR_INVALID, "null argument");
+    *out = nullptr;
+    ppad_ctx *ctx = new (std::nothrow) ppad_ctx;
+    if (!ctx) return fail(PPAD_ERR_INVALID, "out of memory");
+    std::memset(ctx, 0, sizeof(*ctx));
+    ctx->cfg = *cfg;
+    ctx->device = device;
+    std::string err;
+    if (const int r = build_params(*cfg, ctx->base, ctx->geom, err)) {
+        delete ctx;
+        return fail(r, err);
+    }
+    int count = 0;
+    const cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || device < 0 || device >= count) {
+        delete ctx;
+        return fail(PPAD_ERR_CUDA, std::string("no usable CUDA device ") + std::to_string(device) + ": " +
+                                       (e != cudaSuccess ? cudaGetErrorString(e) : "ordinal out of range") +
+                                       " (this library has no CPU path)");
+    }
+    *out = ctx;
+    return PPAD_OK;
+}
+
+void ppad_destroy(ppad_ctx *ctx) { delete ctx; }
+
+static int enter(const ppad_ctx *ctx, int64_t n)
+{
+    if (!ctx) return fail(PPAD_ERR_INVALID, "null context");
+    if (n < 0 || n > ((int64_t)1 << 40)) return fail(PPAD_ERR_INVALID, "bad batch size");
+    return cuda_check(cudaSetDevice(ctx->device), "cudaSetDevice");
+}
+
+int ppad_pack(const ppad_ctx *ctx, int64_t n, const void *boards, const void *fingers, int dtype, const uint8_t *prev,
+              const uint16_t *moves, void *state, uint8_t *flags, void *stream)
+{
+    if (int r = enter(ctx, n)) return r;
+    if (!boards || !fingers || !state) return fail(PPAD_ERR_INVALID, "ppad_pack: null pointer");
+    if (n == 0) return PPAD_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+    case PPAD_I8: PPAD_DISPATCH(ctx, (launch_pack<G, int8_t>(n, boards, fingers, prev, moves, state, flags, st))); break;
+    case PPAD_I32: PPAD_DISPATCH(ctx, (launch_pack<G, int32_t>(n, boards, fingers, prev, moves, state, flags, st))); break;
+    case PPAD_I64: PPAD_DISPATCH(ctx, (launch_pack<G, int64_t>(n, boards, fingers, prev, moves, state, flags, st))); break;
+    default: return fail(PPAD_ERR_UNSUPPORTED, "ppad_pack: dtype must be PPAD_I8, PPAD_I32 or PPAD_I64");
+    }
+    return after_launch("pack_kernel");
+}
+
+int ppad_unpack(const ppad_ctx *ctx, int64_t n, const void *state, void *boards, void *fingers, int dtype, uint8_t *prev,
+                uint16_t *moves, void *stream)
+{
+    if (int r = enter(ctx, n)) return r;
+    if (!state) return fail(PPAD_ERR_INVALID, "ppad_unpack: null state");
+    if (n == 0) return PPAD_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+    case PPAD_I8: PPAD_DISPATCH(ctx, (launch_unpack<G, int8_t>(n, state, boards, fingers, prev, moves, st))); break;
+    case PPAD_I32: PPAD_DISPATCH(ctx, (launch_unpack<G, int32_t>(n, state, boards, fingers, prev, moves, st))); break;
+    case PPAD_I64: PPAD_DISPATCH(ctx, (launch_unpack<G, int64_t>(n, state, boards, fingers, prev, moves, st))); break;
+    default: return fail(PPAD_ERR_UNSUPPORTED, "ppad_unpack: dtype must be PPAD_I8, PPAD_I32 or PPAD_I64");
+    }
+    return after_launch("unpack_kernel");
+}
+
+int ppad_reset(const ppad_ctx *ctx, int64_t n, uint64_t env0, uint32_t step, const uint32_t *slab, int32_t slab_words,
+               int32_t n_inj, const int32_t *fingers_in, void *state, uint8_t *flags, uint8_t *consumed, void *stream)
+{
+    if (int r = enter(ctx, n)) return r;
+    if (!state) return fail(PPAD_ERR_INVALID, "ppad_reset: null state");
+    if (slab && (slab_words <= 0 || n_inj < 0 || n_inj > slab_words * 8))
+        return fail(PPAD_ERR_INVALID, "ppad_reset: need 0 <= n_inj <= 8 * slab_words");
+    if (n == 0) return PPAD_OK;
+    ResetKernelArgs a;
+    a.p = ctx->base;
+    a.p.key.step = step;
+    a.p.n_inj = slab ? n_inj : -1;
+    a.p.slab_words = slab_words;
+    a.n = n;
+    a.env0 = env0;
+    a.slab = slab;
+    a.fingers_in = fingers_in;
+    a.state = state;
+    a.flags = flags;
+    a.consumed = consumed;
+    PPAD_DISPATCH(ctx, (reset_kernel<G><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(a)));
+    return after_launch("reset_kernel");
+}
+
+int ppad_step(const ppad_ctx *ctx, const ppad_step_args *args, void *stream)
+{
+    if (!args) return fail(PPAD_ERR_INVALID, "ppad_step: null args");
+    if (int r = enter(ctx, args->n)) return r;
+    if (!args->state) return fail(PPAD_ERR_INVALID, "ppad_step: null state");
+    if (args->slab && (args->slab_words <= 0 || args->n_inj < 0 || args->n_inj > args->slab_words * 8))
+        return fail(PPAD_ERR_INVALID, "ppad_step: need 0 <= n_inj <= 8 * slab_words");
+    if (args->combo_log && args->log_cap <= 0) return fail(PPAD_ERR_INVALID, "ppad_step: combo_log needs log_cap > 0");
+    if (args->obs && args->obs_dtype != PPAD_OBS_F32 && args->obs_dtype != PPAD_OBS_U8)
+        return fail(PPAD_ERR_UNSUPPORTED, "ppad_step: obs_dtype must be PPAD_OBS_F32 or PPAD_OBS_U8");
+    if (args->obs && ((uintptr_t)args->obs & 15)) return fail(PPAD_ERR_INVALID, "ppad_step: obs must be 16-byte aligned");
+    if (((uintptr_t)args->state & 15) || (args->final_state && ((uintptr_t)args->final_state & 15)))
+        return fail(PPAD_ERR_INVALID, "ppad_step: state must be 16-byte aligned");
+    if (args->n == 0) return PPAD_OK;
+    StepKernelArgs a;
+    a.p = ctx->base;
+    a.p.key.step = args->step;
+    a.p.eval_moves = args->eval_moves;
+    a.p.auto_reset = args->auto_reset;
+    a.p.max_moves = args->max_moves;
+    a.p.n_inj = args->slab ? args->n_inj : -1;
+    a.p.slab_words = args->slab_words;
+    a.p.log_cap = args->log_cap;
+    a.n = args->n;
+    a.env0 = args->env0;
+    a.state = args->state;
+    a.actions = args->actions;
+    a.slab = args->slab;
+    a.action_out = args->action_out;
+    a.reward = args->reward;
+    a.info = args->info;
+    a.final_state = args->final_state;
+    a.combo_log = args->combo_log;
+    a.obs = args->obs;
+    a.obs_dtype = args->obs_dtype;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (args->obs) PPAD_DISPATCH(ctx, (step_kernel<G, true><<<grid_for(a.n), BLOCK, 0, st>>>(a)));
+    else PPAD_DISPATCH(ctx, (step_kernel<G, false><<<grid_for(a.n), BLOCK, 0, st>>>(a)));
+    return after_launch("step_kernel");
+}
+
+int ppad_encode_obs(const ppad_ctx *ctx, int64_t n, const void *state, void *obs, int obs_dtype, void *stream)
+{
+    if (int r = enter(ctx, n)) return r;
+    if (!state || !obs) return fail(PPAD_ERR_INVALID, "ppad_encode_obs: null pointer");
+    if (obs_dtype != PPAD_OBS_F32 && obs_dtype != PPAD_OBS_U8)
+        return fail(PPAD_ERR_UNSUPPORTED, "ppad_encode_obs: obs_dtype must be PPAD_OBS_F32 or PPAD_OBS_U8");
+    if ((uintptr_t)obs & 15) return fail(PPAD_ERR_INVALID, "ppad_encode_obs: obs must be 16-byte aligned");
+    if (n == 0) return PPAD_OK;
+    PPAD_DISPATCH(ctx, (encode_kernel<G><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(n, state, obs, obs_dtype)));
+    return after_launch("encode_kernel");
+}
+
+int ppad_cancel(const ppad_ctx *ctx, int64_t n, void *state, uint8_t *n_combos, uint16_t *combo_log, int32_t log_cap,
+                void *stream)
+{
+    if (int r = enter(ctx, n)) return r;
+    if (!state) return fail(PPAD_ERR_INVALID, "ppad_cancel: null state");
+    if (combo_log && log_cap <= 0) return fail(PPAD_ERR_INVALID, "ppad_cancel: combo_log needs log_cap > 0");
+    if (n == 0) return PPAD_OK;
+    PPAD_DISPATCH(ctx, (cancel_kernel<G><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(n, state, n_combos, combo_log,
+                                                                                         log_cap)));
+    return after_launch("cancel_kernel");
+}
+
+int ppad_legal_mask(const ppad_ctx *ctx, int64_t n, const void *state, uint8_t *mask, void *stream)
+{
+    if (int r = enter(ctx, n)) return r;
+    if (!state || !mask) return fail(PPAD_ERR_INVALID, "ppad_legal_mask: null pointer");
+    if (n == 0) return PPAD_OK;
+    PPAD_DISPATCH(ctx, (legal_kernel<G><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(n, state, mask)));
+    return after_launch("legal_kernel");
+}
+
+}   // extern "C"

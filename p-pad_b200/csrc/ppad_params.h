@@ -1,0 +1,96 @@
+// ppad_params.h -- host-side translation of ppad_config (the PAD.__init__ keyword arguments,
+// ppad/pad/game.py:39-68) into the tables the kernels read.  Host code only.
+#pragma once
+#include <cmath>
+#include <cstring>
+#include <string>
+
+#include "../../include/ppad_b200.h"
+#include "ppad_core.cuh"
+
+namespace ppad {
+
+// returns PPAD_OK or an error status with `err` set; geom: 0 = 5x6, 1 = 6x7
+inline int build_params(const ppad_config &cfg, StepParams &p, int &geom, std::string &err)
+{
+    std::memset(&p, 0, sizeof(p));
+    // PAD.__init__ checks, game.py:54-68 (same messages)
+    double sum = 0;
+    for (int i = 0; i < 10; i++) {
+        if (cfg.skyfall[i] < 0) {
+            err = "ERROR: Skyfall rates should be a positive number!";
+            return PPAD_ERR_INVALID;
+        }
+        sum += cfg.skyfall[i];
+    }
+    if (std::fabs(sum - 1) > 1e-4) {
+        err = "ERROR: Skyfall rates should add up to 1!";
+        return PPAD_ERR_INVALID;
+    }
+    if (cfg.cols < 0 || cfg.rows < 0) {
+        err = "ERROR: Board dimensions should be positive integers!";
+        return PPAD_ERR_INVALID;
+    }
+    if (cfg.cols * cfg.rows < 13) {
+        err = "ERROR: The board should allow at least 13 orbs. Please increase board size!";
+        return PPAD_ERR_INVALID;
+    }
+    if (cfg.rows == 5 && cfg.cols == 6) geom = 0;
+    else if (cfg.rows == 6 && cfg.cols == 7) geom = 1;
+    else {
+        err = "only 5x6 and 6x7 boards have kernel instantiations";
+        return PPAD_ERR_UNSUPPORTED;
+    }
+    if (cfg.skyfall[7] > 0 || cfg.skyfall[8] > 0 || cfg.skyfall[9] > 0) {
+        err = "orb types 7..9 (poison, mortal poison, bomb) do not fit the 3-bit state";
+        return PPAD_ERR_UNSUPPORTED;
+    }
+    if (cfg.team_size < 0 || cfg.team_size > PPAD_MAX_TEAM_UNITS) {
+        err = "team_size out of range";
+        return PPAD_ERR_INVALID;
+    }
+    p.key.k0 = (uint32_t)cfg.seed;
+    p.key.k1 = (uint32_t)(cfg.seed >> 32);
+    // skyfall thresholds: first i with cumsum[i] >= x / 2^32 and prob[i] > 0 (game.py:464-470);
+    // cumsum * 2^32 is exact in double, so x <= floor(cumsum * 2^32) is the same predicate
+    double cum = 0;
+    int last_valid = -1;
+    for (int i = 0; i < 7; i++) {
+        cum += cfg.skyfall[i];
+        const double t = std::floor(cum * 4294967296.0);
+        p.sky.thr[i] = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+        if (cfg.skyfall[i] > 0) {
+            p.sky.valid |= 1u << i;
+            last_valid = i;
+        }
+    }
+    if (last_valid < 0 || p.sky.thr[last_valid] != 0xFFFFFFFFu) {
+        err = "skyfall rates sum too far below 1: the reference's fall-through (game.py:470) would emit bombs";
+        return PPAD_ERR_UNSUPPORTED;
+    }
+    // team table, game.py:171-180: per attack colour the (multiplier, atk) of matching units in team order
+    for (int u = 0; u < cfg.team_size; u++) {
+        const int a = cfg.team_color_1[u], b = cfg.team_color_2[u];
+        if (a > 4 || b > 4 || a < -1 || b < -1) {
+            err = "team colours must be red, blue, green, light, dark or None "
+                  "(the reference's damage_tracker has no other keys, game.py:163-167)";
+            return PPAD_ERR_UNSUPPORTED;
+        }
+        for (int colour = 0; colour < 5; colour++) {
+            double m;
+            if (a == b && b == colour) m = 1.1;
+            else if (a == colour) m = 1;
+            else if (b == colour) m = 0.3;
+            else continue;
+            const int k = p.team.n[colour]++;
+            p.team.mult[colour][k] = m;
+            p.team.atk[colour][k] = cfg.team_atk[u];
+        }
+    }
+    p.skyfall_damage = cfg.skyfall_damage;
+    p.cascade_cap = cfg.cascade_cap;
+    p.reset_cap = cfg.reset_cap;
+    return PPAD_OK;
+}
+
+}   // namespace ppad

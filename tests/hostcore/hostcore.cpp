@@ -1,0 +1,183 @@
+// hostcore.cpp -- TEST INFRASTRUCTURE ONLY.
+// Compiles the per-board device code (p-pad_b200/csrc/ppad_core.cuh, __host__ __device__) with g++
+// so that the bit-sliced core can be fuzzed against the CPU oracle in the GPU-less build container
+// (tests/test_hostcore_vs_oracle.py).  Nothing in the product loads this library; the shipped
+// libppad_b200.so has device code only.
+#include <cstdint>
+#include <cstring>
+#include <string>
+
+#include "../../p-pad_b200/csrc/ppad_core.cuh"
+#include "../../p-pad_b200/csrc/ppad_params.h"
+
+using namespace ppad;
+
+namespace {
+
+template <class G>
+void step_batch(const StepParams &base, int64_t n, uint64_t env0, int8_t *boards, int32_t *fingers, uint8_t *prev,
+                uint16_t *moves, const uint8_t *actions, const uint32_t *slab, uint8_t *action_out, double *reward,
+                uint32_t *info, int8_t *final_boards, uint16_t *combo_log)
+{
+    for (int64_t i = 0; i < n; i++) {
+        State<G> s;
+        pack_cells<G, int8_t>(s.b, boards + i * G::CELLS);
+        s.meta = meta_pack(fingers[2 * i] * G::C + fingers[2 * i + 1], prev[i], moves ? moves[i] : 0);
+        int action = actions ? actions[i] : -1;
+        if (action == 255) action = -1;
+        Board<G> fin;
+        const StepOut o = step_board<G>(s, fin, base, env0 + (uint64_t)i, action,
+                                        slab ? slab + (size_t)i * base.slab_words : nullptr,
+                                        combo_log ? combo_log + (size_t)i * base.log_cap : nullptr);
+        unpack_cells<G, int8_t>(s.b, boards + i * G::CELLS);
+        const int f = meta_finger(s.meta);
+        fingers[2 * i] = f / G::C;
+        fingers[2 * i + 1] = f % G::C;
+        prev[i] = (uint8_t)meta_prev(s.meta);
+        if (moves) moves[i] = (uint16_t)meta_moves(s.meta);
+        if (action_out) action_out[i] = (uint8_t)o.action;
+        if (reward) reward[i] = o.reward;
+        if (info) info[i] = o.info;
+        if (final_boards) unpack_cells<G, int8_t>(fin, final_boards + i * G::CELLS);
+    }
+}
+
+template <class G>
+void reset_batch(const StepParams &base, int64_t n, uint64_t env0, const uint32_t *slab, const int32_t *fingers_in,
+                 int8_t *boards, int32_t *fingers, uint8_t *flags, int32_t *consumed)
+{
+    for (int64_t i = 0; i < n; i++) {
+        RngKey key = base.key;
+        const uint64_t env = env0 + (uint64_t)i;
+        key.env_lo = (uint32_t)env;
+        key.env_hi = (uint32_t)(env >> 32);
+        OrbSource src;
+        src.init(slab ? slab + (size_t)i * base.slab_words : nullptr, base.n_inj, STREAM_RESET);
+        State<G> s;
+        const int fin = fingers_in ? fingers_in[2 * i] * G::C + fingers_in[2 * i + 1] : -1;
+        const uint32_t fl = reset_board<G>(s, base.reset_cap, src, key, base.sky, fin);
+        unpack_cells<G, int8_t>(s.b, boards + i * G::CELLS);
+        const int f = meta_finger(s.meta);
+        fingers[2 * i] = f / G::C;
+        fingers[2 * i + 1] = f % G::C;
+        if (flags) flags[i] = (uint8_t)fl;
+        if (consumed) consumed[i] = src.cursor;
+    }
+}
+
+template <class G>
+void cancel_batch(int64_t n, int8_t *boards, uint8_t *n_combos, uint16_t *combo_log, int log_cap)
+{
+    for (int64_t i = 0; i < n; i++) {
+        Board<G> b;
+        pack_cells<G, int8_t>(b, boards + i * G::CELLS);
+        LogSink sink;
+        sink.log = combo_log ? combo_log + (size_t)i * log_cap : nullptr;
+        sink.cap = log_cap;
+        sink.n = 0;
+        const int m = cancel_board<G>(b, [&](int colour, int N) { sink.put(colour, N); });
+        unpack_cells<G, int8_t>(b, boards + i * G::CELLS);
+        if (n_combos) n_combos[i] = (uint8_t)sat255(m);
+    }
+}
+
+template <class G>
+void drop_batch(int64_t n, int8_t *boards)
+{
+    for (int64_t i = 0; i < n; i++) {
+        Board<G> b;
+        pack_cells<G, int8_t>(b, boards + i * G::CELLS);
+        drop_board<G>(b);
+        unpack_cells<G, int8_t>(b, boards + i * G::CELLS);
+    }
+}
+
+std::string g_err;
+
+}   // namespace
+
+extern "C" {
+
+const char *hostcore_last_error() { return g_err.c_str(); }
+
+int hostcore_step_batch(const ppad_config *cfg, int64_t n, uint64_t env0, uint32_t step, int8_t *boards, int32_t *fingers,
+                        uint8_t *prev, uint16_t *moves, const uint8_t *actions, int eval_moves, int auto_reset,
+                        int max_moves, const uint32_t *slab, int slab_words, int n_inj, uint8_t *action_out,
+                        double *reward, uint32_t *info, int8_t *final_boards, uint16_t *combo_log, int log_cap)
+{
+    StepParams p;
+    int geom;
+    if (int r = build_params(*cfg, p, geom, g_err)) return r;
+    p.key.step = step;
+    p.eval_moves = eval_moves;
+    p.auto_reset = auto_reset;
+    p.max_moves = max_moves;
+    p.n_inj = slab ? n_inj : -1;
+    p.slab_words = slab_words;
+    p.log_cap = log_cap;
+    if (geom == 0)
+        step_batch<Geom<5, 6>>(p, n, env0, boards, fingers, prev, moves, actions, slab, action_out, reward, info,
+                               final_boards, combo_log);
+    else
+        step_batch<Geom<6, 7>>(p, n, env0, boards, fingers, prev, moves, actions, slab, action_out, reward, info,
+                               final_boards, combo_log);
+    return 0;
+}
+
+int hostcore_reset(const ppad_config *cfg, int64_t n, uint64_t env0, uint32_t step, const uint32_t *slab, int slab_words,
+                   int n_inj, const int32_t *fingers_in, int8_t *boards, int32_t *fingers, uint8_t *flags,
+                   int32_t *consumed)
+{
+    StepParams p;
+    int geom;
+    if (int r = build_params(*cfg, p, geom, g_err)) return r;
+    p.key.step = step;
+    p.n_inj = slab ? n_inj : -1;
+    p.slab_words = slab_words;
+    if (geom == 0) reset_batch<Geom<5, 6>>(p, n, env0, slab, fingers_in, boards, fingers, flags, consumed);
+    else reset_batch<Geom<6, 7>>(p, n, env0, slab, fingers_in, boards, fingers, flags, consumed);
+    return 0;
+}
+
+int hostcore_cancel(int rows, int cols, int64_t n, int8_t *boards, uint8_t *n_combos, uint16_t *combo_log, int log_cap)
+{
+    if (rows == 5 && cols == 6) cancel_batch<Geom<5, 6>>(n, boards, n_combos, combo_log, log_cap);
+    else if (rows == 6 && cols == 7) cancel_batch<Geom<6, 7>>(n, boards, n_combos, combo_log, log_cap);
+    else return 2;
+    return 0;
+}
+
+int hostcore_drop(int rows, int cols, int64_t n, int8_t *boards)
+{
+    if (rows == 5 && cols == 6) drop_batch<Geom<5, 6>>(n, boards);
+    else if (rows == 6 && cols == 7) drop_batch<Geom<6, 7>>(n, boards);
+    else return 2;
+    return 0;
+}
+
+int hostcore_sky_table(const ppad_config *cfg, uint32_t thr[7], uint32_t *valid)
+{
+    StepParams p;
+    int geom;
+    if (int r = build_params(*cfg, p, geom, g_err)) return r;
+    std::memcpy(thr, p.sky.thr, sizeof(p.sky.thr));
+    *valid = p.sky.valid;
+    return 0;
+}
+
+int hostcore_orb_from_u32(const ppad_config *cfg, uint32_t x)
+{
+    StepParams p;
+    int geom;
+    if (build_params(*cfg, p, geom, g_err)) return -1;
+    return orb_from_u32(p.sky, x);
+}
+
+void hostcore_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    U4 c = {ctr[0], ctr[1], ctr[2], ctr[3]};
+    const U4 o = philox4x32_10(c, key[0], key[1]);
+    out[0] = o.x; out[1] = o.y; out[2] = o.z; out[3] = o.w;
+}
+
+}   // extern "C"

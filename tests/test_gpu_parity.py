@@ -1,0 +1,329 @@
+"""Parity of the CUDA path (through the C ABI, via BatchedPAD) with the CPU oracle and with the
+fixtures the reference itself produced.  Everything here needs a GPU: run with -m gpu on the B200.
+Integer, byte and index results are compared bit-exact; the float64 reward is compared by bit pattern."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+import oracle as orc  # noqa: E402
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def pb():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import ppad_b200
+    ppad_b200._cabi.lib()   # fail loudly if the extension is not built
+    return ppad_b200
+
+
+def bits(x):
+    return np.ascontiguousarray(x, np.float64).view(np.uint64)
+
+
+def u32(t):
+    return t.cpu().numpy().view(np.uint32)
+
+
+def random_boards(rng, n, rows, cols, kind):
+    if kind == "uniform6":
+        b = rng.integers(0, 6, size=(n, rows, cols))
+    elif kind == "few":
+        b = rng.integers(0, 3, size=(n, rows, cols))
+    else:
+        b = rng.integers(-1, 7, size=(n, rows, cols))
+    return np.ascontiguousarray(b, np.int8)
+
+
+def test_kat_through_cabi(pb):
+    cases = json.load(open(os.path.join(G, "kat.json")))["cases"]
+    plain = [c for c in cases if "actions" not in c]
+    env = pb.BatchedPAD(len(plain), 5, 6, skyfall_damage=False)
+    env.set_state(np.array([c["board"] for c in plain]), np.zeros((len(plain), 2), int))
+    out = env.calculate_reward(want_final=True, log_cap=32)
+    reward = out.reward.cpu().numpy()
+    info = u32(out.info)
+    log = out.combo_log.cpu().numpy().view(np.uint16)
+    final = env.get_state(out.final_state).boards.cpu().numpy()
+    for i, c in enumerate(plain):
+        assert float(reward[i]).hex() == c["reward_hex"], c["name"]
+        assert [[int(v) & 0xFF, int(v) >> 8] for v in log[i, :info[i] & 0xFF]] == c["combos"], c["name"]
+        assert final[i].tolist() == c["final_board"], c["name"]
+    # a pass leaves the board untouched (game.py:366)
+    assert np.array_equal(env.get_state().boards.cpu().numpy(), np.array([c["board"] for c in plain]))
+    # the moves + skyfall known answer
+    c = [c for c in cases if "actions" in c][0]
+    env = pb.BatchedPAD(1, 5, 6, skyfall_damage=True)
+    env.set_state(np.array([c["board"]]), np.zeros((1, 2), int))
+    for a in c["actions"]:
+        o = env.step(np.array([a], np.uint8))
+        assert float(o.reward[0]) == 0.0 and int(o.info[0]) == 0
+    st = env.get_state()
+    assert st.boards[0].cpu().numpy().tolist() == c["board_after_moves"]
+    assert st.fingers[0].cpu().numpy().tolist() == c["finger_after_moves"]
+    o = env.calculate_reward(injected=np.array([c["orbs"]], np.uint8), want_final=True)
+    assert float(o.reward[0]).hex() == c["reward_hex"] and (u32(o.info)[0] >> 16) & 0xFF == c["consumed"]
+    assert env.get_state(o.final_state).boards[0].cpu().numpy().tolist() == c["final_board"]
+
+
+@pytest.mark.parametrize("tag,rows,cols,team", [("5x6", 5, 6, None), ("6x7", 6, 7, None),
+                                                 ("5x6_custom_team", 5, 6, "custom")])
+def test_resolve_golden_vectors(pb, tag, rows, cols, team):
+    z = np.load(os.path.join(G, "resolve_%s.npz" % tag))
+    t = json.load(open(os.path.join(G, "custom_team.json"))) if team else None
+    for sd in (0, 1):
+        sel = np.nonzero(z["skyfall_damage"] == sd)[0]
+        k = len(sel)
+        env = pb.BatchedPAD(k, rows, cols, skyfall_damage=bool(sd), team=t, cascade_cap=0)
+        env.set_state(z["boards"][sel], np.zeros((k, 2), int))
+        out = env.calculate_reward(injected=z["orbs"][sel], want_final=True, log_cap=64)
+        info = u32(out.info)
+        assert np.array_equal(bits(out.reward.cpu().numpy()), bits(z["reward"][sel]))
+        assert np.array_equal(info & 0xFF, np.minimum(z["n_combos"][sel], 255))
+        assert np.array_equal((info >> 8) & 0xFF, z["depth"][sel])
+        assert np.array_equal((info >> 16) & 0xFF, np.minimum(z["consumed"][sel], 255))
+        assert not (info >> 24).any()
+        assert np.array_equal(env.get_state(out.final_state).boards.cpu().numpy(), z["final_boards"][sel])
+        assert np.array_equal(out.combo_log.cpu().numpy().view(np.uint16), z["combo_log"][sel])
+
+
+@pytest.mark.parametrize("tag,rows,cols", [("5x6", 5, 6), ("6x7", 6, 7)])
+def test_episode_golden_vectors(pb, tag, rows, cols):
+    z = np.load(os.path.join(G, "episodes_%s.npz" % tag))
+    E, L = z["actions"].shape
+    env = pb.BatchedPAD(E, rows, cols, cascade_cap=0)
+    env.set_state(z["init_boards"], z["init_fingers"])
+    for t in range(L):
+        o = env.step(z["actions"][:, t], eval_moves=True, injected=z["orbs"][:, t])
+        st = env.get_state()
+        assert np.array_equal(st.boards.cpu().numpy(), z["boards"][:, t])
+        assert np.array_equal(st.fingers.cpu().numpy(), z["fingers"][:, t])
+        info = u32(o.info)
+        assert np.array_equal(bits(o.reward.cpu().numpy()), bits(z["reward"][:, t]))
+        assert np.array_equal(info & 0xFF, z["n_combos"][:, t]) and np.array_equal((info >> 8) & 0xFF, z["depth"][:, t])
+        assert np.array_equal((info >> 16) & 0xFF, z["consumed"][:, t]) and not (info >> 24).any()
+    o = env.calculate_reward(injected=z["pass_orbs"])
+    assert np.array_equal(bits(o.reward.cpu().numpy()), bits(z["pass_reward"]))
+
+
+@pytest.mark.parametrize("rows,cols", [(5, 6), (6, 7)])
+@pytest.mark.parametrize("mode", ["injected", "philox", "injected_short", "no_skyfall"])
+def test_step_fuzz_vs_oracle(pb, rows, cols, mode):
+    rng = np.random.default_rng(2000 + rows + len(mode))
+    n, steps = 50000 + 17, 8
+    seed = 0x1234567890ABCDEF
+    ocfg = orc.make_cfg(rows, cols, skyfall_damage=(mode != "no_skyfall"), seed=seed)
+    env = pb.BatchedPAD(n, rows, cols, skyfall_damage=(mode != "no_skyfall"), seed=seed, env0=(1 << 32) - 1000)
+    kind = ["uniform6", "few", "jammer_empty"][rows % 3] if mode != "philox" else "uniform6"
+    boards = random_boards(rng, n, rows, cols, kind)
+    fingers = np.stack([rng.integers(0, rows, n), rng.integers(0, cols, n)], 1).astype(np.int32)
+    prev = np.full(n, 4, np.uint8)
+    moves = np.zeros(n, np.uint16)
+    assert not env.set_state(boards, fingers).any()
+    S = {"injected": 256, "philox": 0, "injected_short": 8, "no_skyfall": 16}[mode]
+    for t in range(steps):
+        inj = rng.integers(0, 6, size=(n, S)).astype(np.uint8) if S else None
+        actions = None if t % 3 == 2 else rng.integers(0, 5, size=n).astype(np.uint8)
+        if t == 4:
+            actions[:50] = 9
+        kw = dict(eval_moves=(t % 4 != 3), auto_reset=(t % 2 == 0), max_moves=5)
+        a0, r0, i0, f0 = orc.step_batch(ocfg, boards, fingers, prev, moves, actions=actions, inj=inj,
+                                        env0=(1 << 32) - 1000, step=t, want_final=True, **kw)
+        o = env.step(actions, injected=inj, step=t, want_final=True, obs='u8', **kw)
+        st = env.get_state()
+        assert np.array_equal(o.action.cpu().numpy(), a0), t
+        assert np.array_equal(st.boards.cpu().numpy(), boards) and np.array_equal(st.fingers.cpu().numpy(), fingers), t
+        assert np.array_equal(st.prev.cpu().numpy(), prev) and np.array_equal(st.moves.cpu().numpy().view(np.uint16), moves), t
+        assert np.array_equal(u32(o.info), i0), t
+        assert np.array_equal(bits(o.reward.cpu().numpy()), bits(r0)), t
+        assert np.array_equal(env.get_state(o.final_state).boards.cpu().numpy(), f0), t
+        assert np.array_equal(o.obs.cpu().numpy(), orc.onehot(boards, fingers).astype(np.uint8)), t
+
+
+@pytest.mark.parametrize("rows,cols", [(5, 6), (6, 7)])
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 255, 257, 1000])
+def test_obs_ragged_batches(pb, rows, cols, n):
+    rng = np.random.default_rng(n)
+    boards = random_boards(rng, n, rows, cols, "jammer_empty")
+    fingers = np.stack([rng.integers(0, rows, n), rng.integers(0, cols, n)], 1).astype(np.int32)
+    env = pb.BatchedPAD(n, rows, cols)
+    env.set_state(boards, fingers)
+    want = orc.onehot(boards, fingers)
+    # guard rows after the batch must stay untouched
+    for dtype, tdt in (("f32", torch.float32), ("u8", torch.uint8)):
+        buf = torch.full((n + 3, rows, cols, 7), 9, dtype=tdt, device=env.device)
+        env.encode_obs(dtype, out=buf[:n])
+        got = buf.cpu().numpy()
+        assert np.array_equal(got[:n], want.astype(got.dtype)) and (got[n:] == 9).all()
+        buf.fill_(9)
+        env.step(np.full(n, 4, np.uint8), obs=buf[:n])
+        got = buf.cpu().numpy()
+        assert np.array_equal(got[:n], want.astype(got.dtype)) and (got[n:] == 9).all()
+
+
+def test_obs_golden(pb):
+    z = np.load(os.path.join(G, "onehot.npz"))
+    for rows, cols in ((5, 6), (6, 7)):
+        s = "%dx%d" % (rows, cols)
+        b = z["boards_" + s].copy()
+        keep = b <= 6          # types 7..9 do not fit the 3-bit state: checked separately below
+        b[~keep] = -1
+        env = pb.BatchedPAD(len(b), rows, cols)
+        env.set_state(b, z["fingers_" + s])
+        want = z["states_" + s].copy()
+        assert np.array_equal(env.encode_obs('u8').cpu().numpy(), want)   # 6..9 and -1 are all-zero channels anyway
+        assert np.array_equal(env.encode_obs('f32').cpu().numpy(), want.astype(np.float32))
+
+
+def test_pack_unpack_and_unsupported_orbs(pb):
+    rng = np.random.default_rng(3)
+    for rows, cols in ((5, 6), (6, 7)):
+        n = 777
+        boards = rng.integers(-1, 10, size=(n, rows, cols)).astype(np.int64)
+        fingers = np.stack([rng.integers(0, rows, n), rng.integers(0, cols, n)], 1)
+        prev = rng.integers(0, 5, n).astype(np.uint8)
+        moves = rng.integers(0, 60000, n).astype(np.uint16)
+        env = pb.BatchedPAD(n, rows, cols)
+        flags = env.set_state(boards, fingers, prev, moves.view(np.int16)).cpu().numpy()
+        bad = (boards > 6).any(axis=(1, 2))
+        assert np.array_equal(flags != 0, bad) and set(np.unique(flags)) <= {0, 0x40}
+        st = env.get_state()
+        want = np.where(boards > 6, -1, boards)
+        assert np.array_equal(st.boards.cpu().numpy(), want) and np.array_equal(st.fingers.cpu().numpy(), fingers)
+        assert np.array_equal(st.prev.cpu().numpy(), prev)
+        assert np.array_equal(st.moves.cpu().numpy().view(np.uint16), moves)
+        # device layout == documented host layout
+        ok = ~bad
+        host = pb.layout.pack_state(want[ok], fingers[ok], prev[ok], moves[ok])
+        assert np.array_equal(env.state.cpu().numpy().view(np.uint32)[ok], host)
+
+
+def test_reset_golden_and_properties(pb):
+    z = np.load(os.path.join(G, "reset_injected.npz"))
+    for rows, cols in ((5, 6), (6, 7)):
+        s = "%dx%d" % (rows, cols)
+        k = len(z["orbs_" + s])
+        env = pb.BatchedPAD(k, rows, cols, reset_cap=0, seed=99)
+        flags = env.reset(fingers=np.tile([1, 2], (k, 1)), injected=z["orbs_" + s])
+        st = env.get_state()
+        assert not flags.any() and np.array_equal(st.boards.cpu().numpy(), z["boards_" + s])
+        assert (st.fingers.cpu().numpy() == [1, 2]).all() and (st.prev.cpu().numpy() == 4).all()
+        assert np.array_equal(env.last_reset_consumed.cpu().numpy(), np.minimum(z["consumed_" + s], 255))
+        # Philox reset vs oracle + property: no combos, all cells 0..5
+        n = 5000
+        env = pb.BatchedPAD(n, rows, cols, seed=99, env0=12345)
+        assert not env.reset(step=9).any()
+        st = env.get_state()
+        boards = st.boards.cpu().numpy()
+        ocfg = orc.make_cfg(rows, cols, seed=99)
+        for i in range(0, n, 50):
+            b, f, c, fl = orc.reset(ocfg, env=12345 + i, step=9)
+            assert np.array_equal(b, boards[i]) and np.array_equal(f, st.fingers[i].cpu().numpy())
+        assert boards.min() >= 0 and boards.max() <= 5
+        n_combos, _ = env.cancel()
+        assert not n_combos.any()
+
+
+def test_cancel_and_legal_mask(pb):
+    rng = np.random.default_rng(4)
+    z = np.load(os.path.join(G, "legal.npz"))
+    for rows, cols in ((5, 6), (6, 7)):
+        n = 3000
+        boards = random_boards(rng, n, rows, cols, "few")
+        fingers = np.stack([rng.integers(0, rows, n), rng.integers(0, cols, n)], 1).astype(np.int32)
+        prev = rng.integers(0, 5, n).astype(np.uint8)
+        env = pb.BatchedPAD(n, rows, cols)
+        env.set_state(boards, fingers, prev)
+        mask = env.legal_mask().cpu().numpy()
+        s = "%dx%d" % (rows, cols)
+        assert np.array_equal(mask & 15, z["sample_" + s][fingers[:, 0], fingers[:, 1], prev])
+        assert np.array_equal(mask >> 4, z["illegal_" + s][fingers[:, 0], fingers[:, 1]])
+        n_combos, log = env.cancel(log_cap=16)
+        after = env.get_state().boards.cpu().numpy()
+        log = log.cpu().numpy().view(np.uint16)
+        for i in range(0, n, 7):
+            b = boards[i].copy()
+            combos = orc.cancel(b)
+            assert int(n_combos[i]) == len(combos) and np.array_equal(b, after[i])
+            assert [int(v) for v in log[i, :len(combos)]] == [c | (k << 8) for c, k in combos]
+
+
+def test_full_size_one_million_boards(pb):
+    """BASELINE.json configs[1]: 2^20 boards, random legal moves, injected skyfall; every board of
+    every step against the oracle, plus size-independent properties."""
+    n, rows, cols, T = 1 << 20, 5, 6, 3
+    rng = np.random.default_rng(42)
+    env = pb.BatchedPAD(n, rows, cols, seed=2024)
+    assert not env.reset(step=0).any()
+    st = env.get_state()
+    boards = st.boards.cpu().numpy().astype(np.int8)
+    fingers = st.fingers.cpu().numpy().astype(np.int32)
+    prev = np.full(n, 4, np.uint8)
+    moves = np.zeros(n, np.uint16)
+    ocfg = orc.make_cfg(rows, cols, seed=2024)
+    halves = [pb.BatchedPAD(n // 2, rows, cols, seed=2024, env0=e) for e in (0, n // 2)]
+    halves[0].state.copy_(env.state[:n // 2])
+    halves[1].state.copy_(env.state[n // 2:])
+    depth_hist = np.zeros(256, np.int64)
+    for t in range(1, T + 1):
+        inj = rng.integers(0, 6, size=(n, 32)).astype(np.uint8)
+        before = env.state.clone()
+        o = env.step(None, eval_moves=True, injected=inj, step=t, obs='f32')
+        a0, r0, i0, _ = orc.step_batch(ocfg, boards, fingers, prev, moves, actions=None, inj=inj, step=t)
+        assert np.array_equal(o.action.cpu().numpy(), a0)
+        assert np.array_equal(bits(o.reward.cpu().numpy()), bits(r0))
+        assert np.array_equal(u32(o.info), i0)
+        st = env.get_state()
+        assert np.array_equal(st.boards.cpu().numpy(), boards) and np.array_equal(st.fingers.cpu().numpy(), fingers)
+        depth_hist += np.bincount((i0 >> 8) & 0xFF, minlength=256)
+        # sharding invariance: two half slabs with env0 offsets reproduce the full slab
+        for h, sl in zip(halves, (slice(0, n // 2), slice(n // 2, n))):
+            oh = h.step(None, eval_moves=True, injected=inj[sl], step=t)
+            assert torch.equal(h.state, env.state[sl]) and torch.equal(oh.reward, o.reward[sl])
+            assert torch.equal(oh.info, o.info[sl])
+        # the obs decodes back to the state; a move permutes the orbs (same multiset per board)
+        obs = o.obs
+        dec = torch.where(obs[..., :6].sum(-1) > 0, obs[..., :6].argmax(-1), torch.full_like(obs[..., 0], -1, dtype=torch.int64))
+        assert torch.equal(dec, st.boards)
+        assert torch.equal(obs[..., 6].reshape(n, -1).argmax(1), st.fingers[:, 0] * cols + st.fingers[:, 1])
+        old = env.get_state(before).boards.reshape(n, -1).sort(1).values
+        assert torch.equal(old, st.boards.reshape(n, -1).sort(1).values)
+        # evaluating again with the same skyfall is idempotent and leaves the state alone
+        snap = env.state.clone()
+        again = env.calculate_reward(injected=inj, step=t)
+        assert torch.equal(again.reward, o.reward) and torch.equal(snap, env.state)
+    assert depth_hist[1:].sum() > 0.3 * n * T and depth_hist[3:].sum() > 0   # cascades really happen
+
+
+def test_empty_batch_and_errors(pb):
+    env = pb.BatchedPAD(0, 5, 6)
+    o = env.step(None, obs='f32')
+    assert o.reward.numel() == 0
+    with pytest.raises(pb._cabi.PPADError) as e:
+        pb.BatchedPAD(4, 4, 4)
+    assert e.value.status == pb._cabi.ERR_UNSUPPORTED
+    with pytest.raises(pb._cabi.PPADError) as e:
+        pb.BatchedPAD(4, 3, 4)
+    assert "at least 13 orbs" in str(e.value)
+    with pytest.raises(pb._cabi.PPADError) as e:
+        pb.BatchedPAD(4, skyfall=[0.5, 0.4, 0, 0, 0, 0, 0, 0, 0, 0])
+    assert "add up to 1" in str(e.value)
+    with pytest.raises(pb._cabi.PPADError):
+        pb.BatchedPAD(4, skyfall=[0.5, 0.4, 0, 0, 0, 0, 0, 0, 0, 0.1])
+
+
+def test_launch_counter_counts_kernels(pb):
+    L = pb._cabi.lib()
+    env = pb.BatchedPAD(64, 5, 6)
+    c0 = L.ppad_launch_count()
+    env.reset()
+    env.step(None, eval_moves=True)
+    env.encode_obs()
+    assert L.ppad_launch_count() - c0 == 3

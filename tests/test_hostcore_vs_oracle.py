@@ -1,0 +1,179 @@
+"""The per-board device code (p-pad_b200/csrc/ppad_core.cuh), compiled for the host as test
+infrastructure, against the CPU oracle and the reference-generated fixtures.  CPU only: this is how
+the bit-sliced kernels are debugged in the GPU-less container; tests/test_gpu_parity.py repeats the
+comparison through the C ABI on the B200."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle as orc
+import hostcore_lib as hc
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def bits(x):
+    return np.asarray(x, np.float64).view(np.uint64)
+
+
+def random_boards(rng, n, rows, cols, kind):
+    if kind == "uniform6":
+        b = rng.integers(0, 6, size=(n, rows, cols))
+    elif kind == "few":
+        b = rng.integers(0, rng.integers(2, 5), size=(n, rows, cols))
+    elif kind == "jammer_empty":
+        b = rng.integers(-1, 7, size=(n, rows, cols))
+    else:
+        raise ValueError(kind)
+    return np.ascontiguousarray(b, np.int8)
+
+
+@pytest.mark.parametrize("rows,cols", [(5, 6), (6, 7)])
+@pytest.mark.parametrize("kind", ["uniform6", "few", "jammer_empty"])
+def test_cancel_and_drop_fuzz(rows, cols, kind):
+    rng = np.random.default_rng(hash((rows, kind)) & 0xFFFF)
+    n = 4000
+    boards = random_boards(rng, n, rows, cols, kind)
+    mine = boards.copy()
+    n_combos, log = hc.cancel(mine, log_cap=32)
+    for i in range(n):
+        b = boards[i].copy()
+        combos = orc.cancel(b)
+        assert n_combos[i] == len(combos), i
+        assert [int(v) for v in log[i, :len(combos)]] == [c | (k << 8) for c, k in combos], i
+        assert np.array_equal(b, mine[i]), i
+        orc.drop(b)
+        boards[i] = b
+    hc.drop(mine)
+    assert np.array_equal(mine, boards)
+
+
+@pytest.mark.parametrize("rows,cols", [(5, 6), (6, 7)])
+@pytest.mark.parametrize("mode", ["injected", "philox", "injected_short", "no_skyfall"])
+def test_step_batch_fuzz(rows, cols, mode):
+    rng = np.random.default_rng(1000 + rows + len(mode))
+    n, steps = 3000, 12
+    ocfg = orc.make_cfg(rows, cols, skyfall_damage=(mode != "no_skyfall"), seed=0x1234567890ABCDEF)
+    cfg = hc.cfg_from_oracle(ocfg)
+    kind = ["uniform6", "few", "jammer_empty"][rows % 3] if mode != "philox" else "uniform6"
+    boards = random_boards(rng, n, rows, cols, kind)
+    fingers = np.stack([rng.integers(0, rows, n), rng.integers(0, cols, n)], 1).astype(np.int32)
+    prev = np.full(n, 4, np.uint8)
+    moves = np.zeros(n, np.uint16)
+    mine = [boards.copy(), fingers.copy(), prev.copy(), moves.copy()]
+    S = {"injected": 256, "philox": 0, "injected_short": 8, "no_skyfall": 16}[mode]
+    seen_flags = 0
+    for t in range(steps):
+        inj = rng.integers(0, 6, size=(n, S)).astype(np.uint8) if S else None
+        if t % 3 == 2:
+            actions = None                                   # in-kernel random policy
+        else:
+            actions = rng.integers(0, 5, size=n).astype(np.uint8)   # includes off-board moves and passes
+            if t == 4:
+                actions[:50] = 9                             # bad action ids
+        kw = dict(actions=actions, eval_moves=(t % 4 != 3), auto_reset=(t % 2 == 0), max_moves=5,
+                  inj=inj, env0=77777, step=t, want_final=True)
+        a0, r0, i0, f0 = orc.step_batch(ocfg, boards, fingers, prev, moves, **kw)
+        a1, r1, i1, f1, _ = hc.step_batch(cfg, *mine, **kw)
+        assert np.array_equal(a0, a1), t
+        assert np.array_equal(boards, mine[0]) and np.array_equal(fingers, mine[1]), t
+        assert np.array_equal(prev, mine[2]) and np.array_equal(moves, mine[3]), t
+        assert np.array_equal(i0, i1), (t, np.nonzero(i0 != i1)[0][:5])
+        assert np.array_equal(bits(r0), bits(r1)), t
+        assert np.array_equal(f0, f1), t
+        seen_flags |= int(np.bitwise_or.reduce(i0 >> 24))
+    assert seen_flags & orc.FLAG_REJECTED and seen_flags & orc.FLAG_BAD_ACTION and seen_flags & orc.FLAG_EPISODE_DONE
+    if mode == "injected_short":
+        assert seen_flags & orc.FLAG_SKYFALL_EXHAUSTED
+
+
+def test_cascade_cap_flag():
+    # a one-colour skyfall never stabilises: both sides stop at the cap and say so
+    ocfg = orc.make_cfg(5, 6, True, skyfall=[1, 0, 0, 0, 0, 0, 0, 0, 0, 0], cascade_cap=7)
+    cfg = hc.cfg_from_oracle(ocfg)
+    boards = np.zeros((4, 5, 6), np.int8)
+    args = lambda: (boards.copy(), np.zeros((4, 2), np.int32), np.full(4, 4, np.uint8), np.zeros(4, np.uint16))
+    _, r0, i0, _ = orc.step_batch(ocfg, *args(), actions=np.full(4, 4, np.uint8))
+    _, r1, i1, _, _ = hc.step_batch(cfg, *args(), actions=np.full(4, 4, np.uint8))
+    assert np.array_equal(i0, i1) and np.array_equal(bits(r0), bits(r1))
+    assert ((i0 >> 24) & orc.FLAG_CASCADE_CAP).all() and (((i0 >> 8) & 0xFF) == 7).all()
+
+
+@pytest.mark.parametrize("tag,rows,cols,team", [("5x6", 5, 6, None), ("6x7", 6, 7, None),
+                                                 ("5x6_custom_team", 5, 6, "custom")])
+def test_resolve_golden_vectors(tag, rows, cols, team):
+    """straight against what the reference produced"""
+    z = np.load(os.path.join(G, "resolve_%s.npz" % tag))
+    t = json.load(open(os.path.join(G, "custom_team.json"))) if team else None
+    n = len(z["boards"])
+    for sd in (0, 1):
+        sel = np.nonzero(z["skyfall_damage"] == sd)[0]
+        cfg = hc.cfg_from_oracle(orc.make_cfg(rows, cols, skyfall_damage=sd, team=t, cascade_cap=0))
+        boards = np.ascontiguousarray(z["boards"][sel])
+        k = len(sel)
+        _, reward, info, final, log = hc.step_batch(
+            cfg, boards, np.zeros((k, 2), np.int32), np.full(k, 4, np.uint8), None, actions=np.full(k, 4, np.uint8),
+            inj=np.ascontiguousarray(z["orbs"][sel]), want_final=True, log_cap=64)
+        assert np.array_equal(bits(reward), bits(z["reward"][sel]))
+        assert np.array_equal(info & 0xFF, np.minimum(z["n_combos"][sel], 255))
+        assert np.array_equal((info >> 8) & 0xFF, z["depth"][sel])
+        assert np.array_equal((info >> 16) & 0xFF, np.minimum(z["consumed"][sel], 255))
+        assert not (info >> 24).any()
+        assert np.array_equal(final, z["final_boards"][sel])
+        assert np.array_equal(log, z["combo_log"][sel])
+    assert n >= 400
+
+
+def test_kat_golden():
+    cases = json.load(open(os.path.join(G, "kat.json")))["cases"]
+    cfg = hc.cfg_from_oracle(orc.make_cfg(5, 6, skyfall_damage=False))
+    for c in cases:
+        if "actions" in c:
+            continue
+        b = np.array([c["board"]], np.int8)
+        _, reward, info, final, log = hc.step_batch(cfg, b, np.zeros((1, 2), np.int32), np.full(1, 4, np.uint8), None,
+                                                    actions=np.full(1, 4, np.uint8), want_final=True, log_cap=32)
+        assert float(reward[0]).hex() == c["reward_hex"], c["name"]
+        assert [[int(v) & 0xFF, int(v) >> 8] for v in log[0, :info[0] & 0xFF]] == c["combos"], c["name"]
+        assert final[0].tolist() == c["final_board"], c["name"]
+
+
+def test_reset_golden_and_philox():
+    z = np.load(os.path.join(G, "reset_injected.npz"))
+    for rows, cols in ((5, 6), (6, 7)):
+        s = "%dx%d" % (rows, cols)
+        ocfg = orc.make_cfg(rows, cols, reset_cap=0, seed=99)
+        cfg = hc.cfg_from_oracle(ocfg)
+        k = len(z["orbs_" + s])
+        boards, fingers, flags, consumed = hc.reset(cfg, k, inj=z["orbs_" + s], fingers_in=np.tile([1, 2], (k, 1)))
+        assert np.array_equal(boards, z["boards_" + s]) and np.array_equal(consumed, z["consumed_" + s])
+        assert not flags.any() and (fingers == [1, 2]).all()
+        # pure Philox reset: hostcore vs oracle, env ids straddling 2^32
+        boards, fingers, flags, consumed = hc.reset(cfg, 300, env0=(1 << 32) - 100, step=5)
+        for i in range(300):
+            b, f, c, fl = orc.reset(ocfg, env=(1 << 32) - 100 + i, step=5)
+            assert np.array_equal(b, boards[i]) and np.array_equal(f, fingers[i]) and c == consumed[i] and fl == flags[i]
+            assert orc.cancel(b.copy()) == []
+
+
+def test_sky_thresholds_match_float_rule():
+    z = np.load(os.path.join(G, "random_orb.npz"))
+    for i, p in enumerate(z["probs"]):
+        cfg = hc.cfg_from_oracle(orc.make_cfg(skyfall=p))
+        thr, valid = hc.sky_table(cfg)
+        assert valid == sum(1 << j for j in range(7) if p[j] > 0)
+        for j in range(0, len(z["xs"]), 7):
+            assert hc.orb_from_u32(cfg, int(z["xs"][j])) == z["orbs"][i, j]
+        for j in range(len(z["xs"]) - 80, len(z["xs"])):   # the threshold neighbours
+            assert hc.orb_from_u32(cfg, int(z["xs"][j])) == z["orbs"][i, j]
+
+
+def test_philox_matches_oracle():
+    rng = np.random.default_rng(5)
+    for _ in range(50):
+        ctr = [int(v) for v in rng.integers(0, 2 ** 32, 4)]
+        key = [int(v) for v in rng.integers(0, 2 ** 32, 2)]
+        assert hc.philox(ctr, key) == orc.philox4x32(ctr, key)
+    assert hc.philox([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
