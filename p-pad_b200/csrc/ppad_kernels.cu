@@ -495,8 +495,8 @@ int ppad_pack(const ppad_ctx *ctx, int64_t n, const void *boards, const void *fi
               const uint16_t *moves, void *state, uint8_t *flags, void *stream)
 {
     if (int r = enter(ctx, n)) return r;
-    if (!boards || !fingers || !state) return fail(PPAD_ERR_INVALID, "ppad_pack: null pointer");
     if (n == 0) return PPAD_OK;
+    if (!boards || !fingers || !state) return fail(PPAD_ERR_INVALID, "ppad_pack: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     switch (dtype) {
     case PPAD_I8: PPAD_DISPATCH(ctx, (launch_pack<G, int8_t>(n, boards, fingers, prev, moves, state, flags, st))); break;
@@ -511,8 +511,8 @@ int ppad_unpack(const ppad_ctx *ctx, int64_t n, const void *state, void *boards,
                 uint16_t *moves, void *stream)
 {
     if (int r = enter(ctx, n)) return r;
-    if (!state) return fail(PPAD_ERR_INVALID, "ppad_unpack: null state");
     if (n == 0) return PPAD_OK;
+    if (!state) return fail(PPAD_ERR_INVALID, "ppad_unpack: null state");
     cudaStream_t st = (cudaStream_t)stream;
     switch (dtype) {
     case PPAD_I8: PPAD_DISPATCH(ctx, (launch_unpack<G, int8_t>(n, state, boards, fingers, prev, moves, st))); break;
@@ -527,10 +527,10 @@ int ppad_reset(const ppad_ctx *ctx, int64_t n, uint64_t env0, uint32_t step, con
                int32_t n_inj, const int32_t *fingers_in, void *state, uint8_t *flags, uint8_t *consumed, void *stream)
 {
     if (int r = enter(ctx, n)) return r;
+    if (n == 0) return PPAD_OK;
     if (!state) return fail(PPAD_ERR_INVALID, "ppad_reset: null state");
     if (slab && (slab_words <= 0 || n_inj < 0 || n_inj > slab_words * 8))
         return fail(PPAD_ERR_INVALID, "ppad_reset: need 0 <= n_inj <= 8 * slab_words");
-    if (n == 0) return PPAD_OK;
     ResetKernelArgs a;
     a.p = ctx->base;
     a.p.key.step = step;
@@ -551,6 +551,7 @@ int ppad_step(const ppad_ctx *ctx, const ppad_step_args *args, void *stream)
 {
     if (!args) return fail(PPAD_ERR_INVALID, "ppad_step: null args");
     if (int r = enter(ctx, args->n)) return r;
+    if (args->n == 0) return PPAD_OK;
     if (!args->state) return fail(PPAD_ERR_INVALID, "ppad_step: null state");
     if (args->slab && (args->slab_words <= 0 || args->n_inj < 0 || args->n_inj > args->slab_words * 8))
         return fail(PPAD_ERR_INVALID, "ppad_step: need 0 <= n_inj <= 8 * slab_words");
@@ -560,7 +561,6 @@ int ppad_step(const ppad_ctx *ctx, const ppad_step_args *args, void *stream)
     if (args->obs && ((uintptr_t)args->obs & 15)) return fail(PPAD_ERR_INVALID, "ppad_step: obs must be 16-byte aligned");
     if (((uintptr_t)args->state & 15) || (args->final_state && ((uintptr_t)args->final_state & 15)))
         return fail(PPAD_ERR_INVALID, "ppad_step: state must be 16-byte aligned");
-    if (args->n == 0) return PPAD_OK;
     StepKernelArgs a;
     a.p = ctx->base;
     a.p.key.step = args->step;
@@ -591,11 +591,11 @@ int ppad_step(const ppad_ctx *ctx, const ppad_step_args *args, void *stream)
 int ppad_encode_obs(const ppad_ctx *ctx, int64_t n, const void *state, void *obs, int obs_dtype, void *stream)
 {
     if (int r = enter(ctx, n)) return r;
+    if (n == 0) return PPAD_OK;
     if (!state || !obs) return fail(PPAD_ERR_INVALID, "ppad_encode_obs: null pointer");
     if (obs_dtype != PPAD_OBS_F32 && obs_dtype != PPAD_OBS_U8)
         return fail(PPAD_ERR_UNSUPPORTED, "ppad_encode_obs: obs_dtype must be PPAD_OBS_F32 or PPAD_OBS_U8");
     if ((uintptr_t)obs & 15) return fail(PPAD_ERR_INVALID, "ppad_encode_obs: obs must be 16-byte aligned");
-    if (n == 0) return PPAD_OK;
     PPAD_DISPATCH(ctx, (encode_kernel<G><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(n, state, obs, obs_dtype)));
     return after_launch("encode_kernel");
 }
@@ -604,9 +604,9 @@ int ppad_cancel(const ppad_ctx *ctx, int64_t n, void *state, uint8_t *n_combos, 
                 void *stream)
 {
     if (int r = enter(ctx, n)) return r;
+    if (n == 0) return PPAD_OK;
     if (!state) return fail(PPAD_ERR_INVALID, "ppad_cancel: null state");
     if (combo_log && log_cap <= 0) return fail(PPAD_ERR_INVALID, "ppad_cancel: combo_log needs log_cap > 0");
-    if (n == 0) return PPAD_OK;
     PPAD_DISPATCH(ctx, (cancel_kernel<G><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(n, state, n_combos, combo_log,
                                                                                          log_cap)));
     return after_launch("cancel_kernel");
@@ -615,8 +615,8 @@ int ppad_cancel(const ppad_ctx *ctx, int64_t n, void *state, uint8_t *n_combos, 
 int ppad_legal_mask(const ppad_ctx *ctx, int64_t n, const void *state, uint8_t *mask, void *stream)
 {
     if (int r = enter(ctx, n)) return r;
-    if (!state || !mask) return fail(PPAD_ERR_INVALID, "ppad_legal_mask: null pointer");
     if (n == 0) return PPAD_OK;
+    if (!state || !mask) return fail(PPAD_ERR_INVALID, "ppad_legal_mask: null pointer");
     PPAD_DISPATCH(ctx, (legal_kernel<G><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(n, state, mask)));
     return after_launch("legal_kernel");
 }
