@@ -138,6 +138,8 @@ typedef struct ppad_step_args {
     int32_t log_cap;
     void *obs;                    /* [n, rows, cols, 7] or NULL */
     int32_t obs_dtype;            /* ppad_obs_dtype */
+    int32_t skyfall_damage;       /* -1 = cfg.skyfall_damage; 0 / 1 = the skyfall_damage argument of
+                                     PAD.calculate_reward (game.py:364) for this call */
 } ppad_step_args;
 int ppad_step(const ppad_ctx *ctx, const ppad_step_args *args, void *stream);
 
@@ -151,6 +153,58 @@ int ppad_cancel(const ppad_ctx *ctx, int64_t n, void *state, uint8_t *n_combos, 
 /* pad_utils.illegal_actions (utils.py:73-83) / the support of PlayerAction.sample (player.py:46-62):
  * mask [n] uint8, bit a = action a is a legal non-reversing move; bits 4..7 = off-board moves. */
 int ppad_legal_mask(const ppad_ctx *ctx, int64_t n, const void *state, uint8_t *mask, void *stream);
+
+/* PlayerAction.sample (player.py:38-66): one uniformly random legal non-reversing move per board
+ * (255 when there is none), from the same Philox draw the in-kernel policy of ppad_step uses, so
+ * ppad_sample_actions(step) followed by ppad_step(actions, step) equals ppad_step(NULL, step). */
+int ppad_sample_actions(const ppad_ctx *ctx, int64_t n, uint64_t env0, uint32_t step, const void *state,
+                        int32_t include_pass, uint8_t *actions, void *stream);
+
+/* PAD.drop (game.py:201-221) in place */
+int ppad_drop(const ppad_ctx *ctx, int64_t n, void *state, void *stream);
+
+/* PAD.fill_board (game.py:232-256) in place: empties (or every cell when reset_all != 0) in row-major
+ * order, one orb each, from draw index draw0 of the (slab, Philox skyfall stream) source. */
+int ppad_fill(const ppad_ctx *ctx, int64_t n, uint64_t env0, uint32_t step, int32_t draw0, int32_t reset_all,
+              const uint32_t *slab, int32_t slab_words, int32_t n_inj, void *state, uint8_t *flags, uint8_t *consumed,
+              void *stream);
+
+/* PAD.damage (game.py:157-199) of explicit combo lists: combo_log [n, log_cap] = colour | N << 8 in
+ * order, n_combos [n] -> reward [n] float64 */
+int ppad_damage(const ppad_ctx *ctx, int64_t n, const uint16_t *combo_log, int32_t log_cap, const uint8_t *n_combos,
+                double *reward, void *stream);
+
+/* ---- the callers either side of the env step ---------------------------- */
+
+/* permutation_mapping (smart_data.py:94-108) in place: maps [n, 8] uint8, orb type t -> maps[i][t] (t = 0..6;
+ * empty cells stay empty; byte 7 is padding) */
+int ppad_permute(const ppad_ctx *ctx, int64_t n, void *state, const uint8_t *maps, void *stream);
+
+typedef enum ppad_select_method { PPAD_SELECT_MAX = 0, PPAD_SELECT_BOLTZMANN = 1 } ppad_select_method;
+
+/* Agent01.act after the network (agent01.py:173-218): q [n, 5] float32 -> actions [n].
+ * Off-board moves and the reverse of the previous action get -inf (agent01.py:173-190); epsilon-greedy
+ * (agent01.py:193-201), then argmax or a Boltzmann draw exp(beta q) / sum (agent01.py:203-213) from the
+ * Philox POLICY stream of (env0 + i, step).  max_moves > 0 forces PASS at the episode length cap
+ * (simulation.py:50-52). */
+int ppad_select_actions(const ppad_ctx *ctx, int64_t n, uint64_t env0, uint32_t step, const void *state, const float *q,
+                        int32_t method, float beta, float epsilon, int32_t max_moves, uint8_t *actions, void *stream);
+
+/* ppad.discount (agent/utils.py:22-51) in place over n trajectories rewards [n, max_len] float64 with
+ * lengths [n] int32 (NULL = max_len): optional log10 of positive rewards, reverse scan
+ * cur = cur * gamma + r, optional normalisation. */
+int ppad_discount(const ppad_ctx *ctx, int64_t n, int32_t max_len, double *rewards, const int32_t *lengths, double gamma,
+                  int32_t log10_flag, int32_t norm, void *stream);
+
+/* Experience replay ring (simulation.py:294-306) of (packed state, action, reward) rows.
+ * push: row i (if keep == NULL or keep[i]) goes to ring slot (cursor + (slot ? slot[i] : i)) % capacity.
+ * sample: k uniform rows of the first `size` ring rows (Philox, keyed by step); index (may be NULL) gets the rows. */
+int ppad_replay_push(const ppad_ctx *ctx, int64_t n, int64_t capacity, int64_t cursor, const void *state,
+                     const uint8_t *action, const double *reward, const uint8_t *keep, const int64_t *slot,
+                     void *r_state, uint8_t *r_action, double *r_reward, void *stream);
+int ppad_replay_sample(const ppad_ctx *ctx, int64_t k, int64_t size, uint32_t step, const void *r_state,
+                       const uint8_t *r_action, const double *r_reward, void *state, uint8_t *action, double *reward,
+                       int64_t *index, void *stream);
 
 #ifdef __cplusplus
 }

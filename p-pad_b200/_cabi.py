@@ -13,6 +13,7 @@ FLAG_REJECTED, FLAG_SKYFALL_EXHAUSTED, FLAG_CASCADE_CAP, FLAG_NO_LEGAL_MOVE = 0x
 FLAG_BAD_ACTION, FLAG_RESET_CAP, FLAG_UNSUPPORTED_ORB, FLAG_EPISODE_DONE = 0x10, 0x20, 0x40, 0x80
 I8, I32, I64 = 1, 4, 8
 OBS_F32, OBS_U8 = 0, 1
+SELECT_MAX, SELECT_BOLTZMANN = 0, 1
 
 
 class Config(C.Structure):
@@ -30,13 +31,15 @@ class StepArgs(C.Structure):
                 ("actions", C.c_void_p), ("slab", C.c_void_p), ("slab_words", C.c_int32), ("n_inj", C.c_int32),
                 ("action_out", C.c_void_p), ("reward", C.c_void_p), ("info", C.c_void_p),
                 ("final_state", C.c_void_p), ("combo_log", C.c_void_p), ("log_cap", C.c_int32),
-                ("obs", C.c_void_p), ("obs_dtype", C.c_int32)]
+                ("obs", C.c_void_p), ("obs_dtype", C.c_int32), ("skyfall_damage", C.c_int32)]
 
 
 # every symbol include/ppad_b200.h declares (tests/test_cabi_symbols.py checks the header against this)
 SYMBOLS = ["ppad_default_config", "ppad_create", "ppad_destroy", "ppad_abi_version", "ppad_strerror",
            "ppad_last_error", "ppad_state_bytes", "ppad_launch_count", "ppad_pack", "ppad_unpack", "ppad_reset",
-           "ppad_step", "ppad_encode_obs", "ppad_cancel", "ppad_legal_mask"]
+           "ppad_step", "ppad_encode_obs", "ppad_cancel", "ppad_legal_mask", "ppad_sample_actions", "ppad_drop",
+           "ppad_fill", "ppad_damage", "ppad_select_actions", "ppad_discount", "ppad_replay_push",
+           "ppad_replay_sample", "ppad_permute"]
 
 
 class PPADError(RuntimeError):
@@ -77,6 +80,15 @@ def lib():
     L.ppad_encode_obs.argtypes = [vp, i64, vp, vp, C.c_int, vp]
     L.ppad_cancel.argtypes = [vp, i64, vp, vp, vp, i32, vp]
     L.ppad_legal_mask.argtypes = [vp, i64, vp, vp, vp]
+    L.ppad_sample_actions.argtypes = [vp, i64, u64, u32, vp, i32, vp, vp]
+    L.ppad_drop.argtypes = [vp, i64, vp, vp]
+    L.ppad_fill.argtypes = [vp, i64, u64, u32, i32, i32, vp, i32, i32, vp, vp, vp, vp]
+    L.ppad_damage.argtypes = [vp, i64, vp, i32, vp, vp, vp]
+    L.ppad_permute.argtypes = [vp, i64, vp, vp, vp]
+    L.ppad_select_actions.argtypes = [vp, i64, u64, u32, vp, vp, i32, C.c_float, C.c_float, i32, vp, vp]
+    L.ppad_discount.argtypes = [vp, i64, i32, vp, vp, C.c_double, i32, i32, vp]
+    L.ppad_replay_push.argtypes = [vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.ppad_replay_sample.argtypes = [vp, i64, i64, u32, vp, vp, vp, vp, vp, vp, vp, vp]
     for name in SYMBOLS:
         getattr(L, name)
     if L.ppad_abi_version() != 1:

@@ -53,6 +53,18 @@ class BatchedPAD:
         # packed state records (int32 view of the uint32 words of include/ppad_b200.h)
         self.state = torch.zeros((self.n, self.words), dtype=torch.int32, device=self.device)
 
+    def like(self, n, env0=None):
+        """A fresh slab of n boards with the same game configuration (used for search expansions)."""
+        other = BatchedPAD.__new__(BatchedPAD)
+        other.__dict__.update({k: v for k, v in self.__dict__.items() if k not in ("state", "_ctx")})
+        other.n = int(n)
+        other.env0 = self.env0 if env0 is None else int(env0)
+        handle = C.c_void_p()
+        _cabi.check(self.lib.ppad_create(C.byref(self.cfg), self.device.index, C.byref(handle)))
+        other._ctx = handle
+        other.state = torch.zeros((other.n, self.words), dtype=torch.int32, device=self.device)
+        return other
+
     def __del__(self):
         ctx, self._ctx = getattr(self, "_ctx", None), None
         if ctx:
@@ -131,9 +143,10 @@ class BatchedPAD:
         step = self._next_step(step)
         if boards is not None:
             if fingers is None:
-                tmp = BatchedPAD.reset(self, None, None, None, step)
+                # random fingers from the Philox FINGER stream: do a plain reset, keep only its fingers
+                self.step_index = step
+                self.reset(step=step)
                 fingers = self.get_state().fingers
-                del tmp
             return self.set_state(boards, fingers)
         slab, words, n_inj = self._slab(injected)
         fin = None if fingers is None else self._dev(fingers, torch.int32).reshape(self.n, 2)
@@ -152,7 +165,7 @@ class BatchedPAD:
         return int(step) & 0xFFFFFFFF
 
     def step(self, actions=None, eval_moves=False, auto_reset=False, max_moves=0, injected=None, obs=None,
-             want_final=False, log_cap=0, step=None, out=None):
+             want_final=False, log_cap=0, step=None, out=None, skyfall_damage=None):
         """One env step of all boards (ppad_step).  actions: None (random legal moves / forced pass at
         max_moves), or uint8 [n] ids 0..4 (255 = sample).  obs: None, 'f32' or 'u8', or a preallocated tensor.
         Returns SimpleNamespace(action, reward, info, obs, final_state, combo_log); ``out`` reuses buffers."""
@@ -191,14 +204,55 @@ class BatchedPAD:
         a.log_cap = int(log_cap)
         a.obs = out.obs.data_ptr() if out.obs is not None else None
         a.obs_dtype = obs_dtype
+        a.skyfall_damage = -1 if skyfall_damage is None else int(bool(skyfall_damage))
         with torch.cuda.device(self.device):
             _cabi.check(self.lib.ppad_step(self._ctx, C.byref(a), self._stream()))
         return out
 
-    def calculate_reward(self, injected=None, want_final=False, log_cap=0, step=None):
+    def calculate_reward(self, injected=None, want_final=False, log_cap=0, step=None, skyfall_damage=None):
         """PAD.calculate_reward (game.py:364-405) of every board, on a copy: the state is not modified."""
         acts = torch.full((self.n,), _cabi.PASS, dtype=torch.uint8, device=self.device)
-        return self.step(acts, injected=injected, want_final=want_final, log_cap=log_cap, step=step)
+        return self.step(acts, injected=injected, want_final=want_final, log_cap=log_cap, step=step,
+                         skyfall_damage=skyfall_damage)
+
+    def sample_actions(self, include_pass=False, step=None):
+        """PlayerAction.sample (player.py:38-66) for every board -> uint8 [n] (255 = no legal move).
+        Uses the draw the in-kernel policy of step(actions=None) would use at the same step index and does
+        not advance step_index."""
+        step = self.step_index if step is None else int(step)
+        actions = torch.empty(self.n, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ppad_sample_actions(self._ctx, self.n, self.env0, step & 0xFFFFFFFF, _ptr(self.state),
+                                                     int(bool(include_pass)), _ptr(actions), self._stream()))
+        return actions
+
+    def drop(self):
+        """PAD.drop (game.py:201-221) in place"""
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ppad_drop(self._ctx, self.n, _ptr(self.state), self._stream()))
+
+    def fill_board(self, reset=False, injected=None, draw0=0, step=None):
+        """PAD.fill_board (game.py:232-256) in place -> (flags uint8 [n], consumed uint8 [n])"""
+        step = self.step_index if step is None else int(step)
+        slab, words, n_inj = self._slab(injected)
+        flags = torch.empty(self.n, dtype=torch.uint8, device=self.device)
+        consumed = torch.empty(self.n, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ppad_fill(self._ctx, self.n, self.env0, step & 0xFFFFFFFF, int(draw0), int(bool(reset)),
+                                           _ptr(slab), words, n_inj, _ptr(self.state), _ptr(flags), _ptr(consumed),
+                                           self._stream()))
+        return flags, consumed
+
+    def damage(self, combo_log, n_combos):
+        """PAD.damage (game.py:157-199): combo_log int16/uint16 [n, cap] (colour | N << 8), n_combos uint8 [n]"""
+        combo_log = self._dev(combo_log, torch.int16)
+        n_combos = self._dev(n_combos, torch.uint8)
+        n = combo_log.shape[0]
+        reward = torch.empty(n, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ppad_damage(self._ctx, n, _ptr(combo_log), combo_log.shape[1], _ptr(n_combos),
+                                             _ptr(reward), self._stream()))
+        return reward
 
     # ------------------------------------------------------------------ single-purpose kernels
     def encode_obs(self, dtype='f32', state=None, out=None):
@@ -228,6 +282,45 @@ class BatchedPAD:
         with torch.cuda.device(self.device):
             _cabi.check(self.lib.ppad_legal_mask(self._ctx, self.n, _ptr(self.state), _ptr(mask), self._stream()))
         return mask
+
+    def permute_colours(self, maps):
+        """permutation_mapping (smart_data.py:94-108) in place: maps uint8 [n, <= 8], orb type t -> maps[i][t]"""
+        m = self._dev(maps, torch.uint8)
+        full = torch.arange(8, dtype=torch.uint8, device=self.device).repeat(self.n, 1)
+        full[:, :m.shape[1]] = m
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ppad_permute(self._ctx, self.n, _ptr(self.state), _ptr(full.contiguous()), self._stream()))
+
+    # ------------------------------------------------------------------ callers either side of the step
+    def select_actions(self, q, method='max', beta=None, epsilon=0.0, max_moves=0, step=None):
+        """Agent01.act after the network (agent01.py:173-218): q float32 [n, 5] -> uint8 [n] action ids.
+        Uses the Philox POLICY stream of the step index the NEXT step() call will use; does not advance it."""
+        method = str(method).lower()
+        if method not in ('max', 'boltzmann'):
+            raise Exception('ERROR: Unknown action method!')
+        if method == 'boltzmann' and beta is None:
+            raise Exception('ERROR: Provide a value for beta!')
+        step = self.step_index if step is None else int(step)
+        q = self._dev(q, torch.float32).reshape(self.n, 5)
+        actions = torch.empty(self.n, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ppad_select_actions(
+                self._ctx, self.n, self.env0, step & 0xFFFFFFFF, _ptr(self.state), _ptr(q),
+                _cabi.SELECT_MAX if method == 'max' else _cabi.SELECT_BOLTZMANN, float(beta or 0.0), float(epsilon),
+                int(max_moves), _ptr(actions), self._stream()))
+        return actions
+
+    def discount(self, rewards, gamma, lengths=None, norm=False, log10=True):
+        """ppad.discount (agent/utils.py:22-51) for a batch of trajectories: rewards float64 [m, T] (a copy is
+        discounted and returned), lengths int32 [m] or None."""
+        r = self._dev(rewards, torch.float64).clone()
+        if r.dim() == 1:
+            r = r[None]
+        lengths = None if lengths is None else self._dev(lengths, torch.int32)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ppad_discount(self._ctx, r.shape[0], r.shape[1], _ptr(r), _ptr(lengths), float(gamma),
+                                               int(bool(log10)), int(bool(norm)), self._stream()))
+        return r
 
     @staticmethod
     def split_info(info):

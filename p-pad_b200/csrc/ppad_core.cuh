@@ -519,6 +519,15 @@ PPAD_HD ResolveOut resolve_board(Board<G> &b, bool skyfall_damage, int cascade_c
     return out;
 }
 
+// damage (game.py:157-199) of an explicit combo list: log[i] = colour | N << 8
+PPAD_HD double damage_of_log(const TeamTable &team, const uint16_t *log, int n)
+{
+    Tally tally;
+    tally.init();
+    for (int i = 0; i < n; i++) tally.add(team, log[i] & 0xFF, log[i] >> 8);
+    return tally.n_combos ? tally.total() : 0.0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // moves, legality, random policy
 // ---------------------------------------------------------------------------------------------
@@ -536,7 +545,8 @@ PPAD_HD int legal_mask(int finger, int prev)
     return m;
 }
 
-// uniform over the legal set, one Philox draw (stream ACTION, draw 0); -1 when the set is empty
+// uniform over the legal set (bits 0..4; bit 4 = pass when the caller allows it), one Philox draw
+// (stream ACTION, draw 0); -1 when the set is empty
 PPAD_HD int sample_from_mask(int mask, uint32_t x)
 {
     const int n = popc((uint32_t)mask);
@@ -544,7 +554,7 @@ PPAD_HD int sample_from_mask(int mask, uint32_t x)
     int pick = (int)mulhi32(x, (uint32_t)n);
     int a = -1;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
+    for (int i = 0; i < 5; i++) {
         const bool on = (mask >> i) & 1;
         if (on && pick == 0 && a < 0) a = i;
         if (on) pick--;
@@ -618,6 +628,7 @@ struct StepParams {
     int32_t skyfall_damage, cascade_cap, reset_cap;
     int32_t eval_moves, auto_reset, max_moves;
     int32_t n_inj, slab_words, log_cap;
+    int32_t draw0;   // first draw index of a stand-alone fill (ppad_fill)
 };
 
 struct StepOut {

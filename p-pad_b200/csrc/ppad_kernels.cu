@@ -19,6 +19,7 @@
 
 #include "../../include/ppad_b200.h"
 #include "ppad_core.cuh"
+#include "ppad_agent.cuh"
 #include "ppad_params.h"
 
 using namespace ppad;
@@ -352,6 +353,160 @@ __global__ void __launch_bounds__(BLOCK) legal_kernel(int64_t n, const void *sta
     mask[i] = (uint8_t)(legal_mask<G>(f, meta_prev(s.meta)) | (off << 4));
 }
 
+// PlayerAction.sample (player.py:38-66): same draw as the in-kernel policy of step_kernel
+template <class G>
+__global__ void __launch_bounds__(BLOCK) sample_kernel(int64_t n, uint64_t env0, RngKey key, const void *state,
+                                                       int include_pass, uint8_t *actions)
+{
+    const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= n) return;
+    const State<G> s = StateIO<G>::load(state, i);
+    const uint64_t env = env0 + (uint64_t)i;
+    key.env_lo = (uint32_t)env;
+    key.env_hi = (uint32_t)(env >> 32);
+    int mask = legal_mask<G>(meta_finger(s.meta), meta_prev(s.meta));
+    // with include_pass the reference rejects 'pass' right after a pass / reset (player.py:52-53)
+    if (include_pass && meta_prev(s.meta) != ACT_PASS) mask |= 16;
+    const int a = sample_from_mask(mask, philox_draw(key, STREAM_ACTION, 0));
+    actions[i] = (uint8_t)(a < 0 ? 255 : a);
+}
+
+// PAD.drop (game.py:201-221), in place
+template <class G>
+__global__ void __launch_bounds__(BLOCK) drop_kernel(int64_t n, void *state)
+{
+    const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= n) return;
+    State<G> s = StateIO<G>::load(state, i);
+    drop_board<G>(s.b);
+    StateIO<G>::store(state, i, s.b, s.meta);
+}
+
+// PAD.fill_board (game.py:232-256), in place; draws start at index p.draw0 of the skyfall stream
+template <class G>
+__global__ void __launch_bounds__(BLOCK) fill_kernel(const __grid_constant__ ResetKernelArgs a, int reset_all)
+{
+    const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= a.n) return;
+    RngKey key = a.p.key;
+    const uint64_t env = a.env0 + (uint64_t)i;
+    key.env_lo = (uint32_t)env;
+    key.env_hi = (uint32_t)(env >> 32);
+    OrbSource src;
+    src.init(a.slab ? a.slab + (size_t)i * a.p.slab_words : nullptr, a.p.n_inj, STREAM_SKYFALL);
+    src.cursor = a.p.draw0;
+    State<G> s = StateIO<G>::load(a.state, i);
+    if (reset_all) refill_all<G>(s.b, src, key, a.p.sky);
+    else fill_board<G>(s.b, src, key, a.p.sky);
+    StateIO<G>::store(a.state, i, s.b, s.meta);
+    if (a.flags) a.flags[i] = (uint8_t)(src.exhausted ? FLAG_SKYFALL_EXHAUSTED : 0);
+    if (a.consumed) a.consumed[i] = (uint8_t)sat255(src.cursor - a.p.draw0);
+}
+
+// PAD.damage (game.py:157-199) of explicit combo lists
+__global__ void __launch_bounds__(BLOCK) damage_kernel(int64_t n, const __grid_constant__ TeamTable team,
+                                                       const uint16_t *combo_log, int log_cap, const uint8_t *n_combos,
+                                                       double *reward)
+{
+    const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= n) return;
+    const int m = n_combos[i] < log_cap ? n_combos[i] : log_cap;
+    reward[i] = damage_of_log(team, combo_log + (size_t)i * log_cap, m);
+}
+
+// permutation_mapping (smart_data.py:94-108): every orb type t of board i becomes maps[i][t]
+template <class G>
+__global__ void __launch_bounds__(BLOCK) permute_kernel(int64_t n, void *state, const uint8_t *maps)
+{
+    typedef typename G::W W;
+    const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= n) return;
+    State<G> s = StateIO<G>::load(state, i);
+    const uint2 m2 = *reinterpret_cast<const uint2 *>(maps + 8 * i);
+    const uint64_t lut = (uint64_t)m2.x | ((uint64_t)m2.y << 32);
+    W p0 = 0, p1 = 0, p2 = 0;
+#pragma unroll
+    for (int c = 0; c < G::CELLS; c++) {
+        const int code = code_at<G>(s.b, c);
+        const int to = code == 7 ? 7 : (int)((lut >> (8 * code)) & 7);
+        p0 |= (W)(to & 1) << c;
+        p1 |= (W)((to >> 1) & 1) << c;
+        p2 |= (W)((to >> 2) & 1) << c;
+    }
+    s.b.b0 = p0;
+    s.b.b1 = p1;
+    s.b.b2 = p2;
+    StateIO<G>::store(state, i, s.b, s.meta);
+}
+
+// Agent01.act after the network (agent01.py:173-218): Q-values -> one action per board
+template <class G>
+__global__ void __launch_bounds__(BLOCK) select_kernel(int64_t n, uint64_t env0, RngKey key, const void *state,
+                                                       const float *q, int method, float beta, float epsilon,
+                                                       int max_moves, uint8_t *actions)
+{
+    const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= n) return;
+    const State<G> s = StateIO<G>::load(state, i);
+    const uint64_t env = env0 + (uint64_t)i;
+    key.env_lo = (uint32_t)env;
+    key.env_hi = (uint32_t)(env >> 32);
+    if (max_moves > 0 && meta_moves(s.meta) >= max_moves) {   // simulation.py:50-52: episode length cap
+        actions[i] = ACT_PASS;
+        return;
+    }
+    float qi[5];
+#pragma unroll
+    for (int a = 0; a < 5; a++) qi[a] = __ldg(q + 5 * i + a);
+    const U4 blk = philox4x32_10(U4{key.env_lo, key.env_hi, key.step, STREAM_POLICY << 24}, key.k0, key.k1);
+    actions[i] = (uint8_t)select_action<G>(qi, meta_finger(s.meta), meta_prev(s.meta), method, beta, epsilon, blk.x, blk.y);
+}
+
+// ppad.discount (agent/utils.py:22-51) for n trajectories stored row-major [n, max_len]
+__global__ void __launch_bounds__(BLOCK) discount_kernel(int64_t n, int max_len, double *rewards, const int32_t *lengths,
+                                                         double gamma, int log10_flag, int norm)
+{
+    const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= n) return;
+    int len = lengths ? lengths[i] : max_len;
+    len = len < 0 ? 0 : (len > max_len ? max_len : len);
+    discount_trajectory(rewards + (size_t)i * max_len, len, gamma, log10_flag, norm);
+}
+
+// experience replay ring (simulation.py:294-306): rows are (packed state, action, reward)
+__global__ void __launch_bounds__(BLOCK) replay_push_kernel(int64_t n, int words, int64_t capacity, int64_t cursor,
+                                                            const uint32_t *state, const uint8_t *action,
+                                                            const double *reward, const uint8_t *keep,
+                                                            const int64_t *slot, uint32_t *r_state, uint8_t *r_action,
+                                                            double *r_reward)
+{
+    const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= n) return;
+    if (keep && !keep[i]) return;
+    const int64_t d = (cursor + (slot ? slot[i] : i)) % capacity;
+    for (int w = 0; w < words; w++) r_state[d * words + w] = state[i * words + w];
+    r_action[d] = action[i];
+    r_reward[d] = reward[i];
+}
+
+__global__ void __launch_bounds__(BLOCK) replay_sample_kernel(int64_t k, int words, int64_t size, RngKey key,
+                                                              const uint32_t *r_state, const uint8_t *r_action,
+                                                              const double *r_reward, uint32_t *state, uint8_t *action,
+                                                              double *reward, int64_t *index)
+{
+    const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= k) return;
+    key.env_lo = (uint32_t)i;
+    key.env_hi = (uint32_t)((uint64_t)i >> 32);
+    const uint32_t hi = philox_draw(key, STREAM_POLICY, 2), lo = philox_draw(key, STREAM_POLICY, 3);
+    const uint64_t x = ((uint64_t)hi << 32) | lo;
+    const int64_t j = (int64_t)__umul64hi(x, (uint64_t)size);   // uniform in [0, size)
+    for (int w = 0; w < words; w++) state[i * words + w] = r_state[j * words + w];
+    action[i] = r_action[j];
+    reward[i] = r_reward[j];
+    if (index) index[i] = j;
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -570,6 +725,7 @@ int ppad_step(const ppad_ctx *ctx, const ppad_step_args *args, void *stream)
     a.p.n_inj = args->slab ? args->n_inj : -1;
     a.p.slab_words = args->slab_words;
     a.p.log_cap = args->log_cap;
+    if (args->skyfall_damage >= 0) a.p.skyfall_damage = args->skyfall_damage;
     a.n = args->n;
     a.env0 = args->env0;
     a.state = args->state;
@@ -619,6 +775,132 @@ int ppad_legal_mask(const ppad_ctx *ctx, int64_t n, const void *state, uint8_t *
     if (!state || !mask) return fail(PPAD_ERR_INVALID, "ppad_legal_mask: null pointer");
     PPAD_DISPATCH(ctx, (legal_kernel<G><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(n, state, mask)));
     return after_launch("legal_kernel");
+}
+
+int ppad_sample_actions(const ppad_ctx *ctx, int64_t n, uint64_t env0, uint32_t step, const void *state,
+                        int32_t include_pass, uint8_t *actions, void *stream)
+{
+    if (int r = enter(ctx, n)) return r;
+    if (n == 0) return PPAD_OK;
+    if (!state || !actions) return fail(PPAD_ERR_INVALID, "ppad_sample_actions: null pointer");
+    RngKey key = ctx->base.key;
+    key.step = step;
+    PPAD_DISPATCH(ctx, (sample_kernel<G><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(n, env0, key, state,
+                                                                                         include_pass, actions)));
+    return after_launch("sample_kernel");
+}
+
+int ppad_drop(const ppad_ctx *ctx, int64_t n, void *state, void *stream)
+{
+    if (int r = enter(ctx, n)) return r;
+    if (n == 0) return PPAD_OK;
+    if (!state) return fail(PPAD_ERR_INVALID, "ppad_drop: null state");
+    PPAD_DISPATCH(ctx, (drop_kernel<G><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(n, state)));
+    return after_launch("drop_kernel");
+}
+
+int ppad_fill(const ppad_ctx *ctx, int64_t n, uint64_t env0, uint32_t step, int32_t draw0, int32_t reset_all,
+              const uint32_t *slab, int32_t slab_words, int32_t n_inj, void *state, uint8_t *flags, uint8_t *consumed,
+              void *stream)
+{
+    if (int r = enter(ctx, n)) return r;
+    if (n == 0) return PPAD_OK;
+    if (!state) return fail(PPAD_ERR_INVALID, "ppad_fill: null state");
+    if (draw0 < 0) return fail(PPAD_ERR_INVALID, "ppad_fill: draw0 must be >= 0");
+    if (slab && (slab_words <= 0 || n_inj < 0 || n_inj > slab_words * 8))
+        return fail(PPAD_ERR_INVALID, "ppad_fill: need 0 <= n_inj <= 8 * slab_words");
+    ResetKernelArgs a;
+    a.p = ctx->base;
+    a.p.key.step = step;
+    a.p.n_inj = slab ? n_inj : -1;
+    a.p.slab_words = slab_words;
+    a.p.draw0 = draw0;
+    a.n = n;
+    a.env0 = env0;
+    a.slab = slab;
+    a.fingers_in = nullptr;
+    a.state = state;
+    a.flags = flags;
+    a.consumed = consumed;
+    PPAD_DISPATCH(ctx, (fill_kernel<G><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(a, reset_all)));
+    return after_launch("fill_kernel");
+}
+
+int ppad_damage(const ppad_ctx *ctx, int64_t n, const uint16_t *combo_log, int32_t log_cap, const uint8_t *n_combos,
+                double *reward, void *stream)
+{
+    if (int r = enter(ctx, n)) return r;
+    if (n == 0) return PPAD_OK;
+    if (!combo_log || !n_combos || !reward || log_cap <= 0) return fail(PPAD_ERR_INVALID, "ppad_damage: bad argument");
+    damage_kernel<<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(n, ctx->base.team, combo_log, log_cap, n_combos, reward);
+    return after_launch("damage_kernel");
+}
+
+int ppad_permute(const ppad_ctx *ctx, int64_t n, void *state, const uint8_t *maps, void *stream)
+{
+    if (int r = enter(ctx, n)) return r;
+    if (n == 0) return PPAD_OK;
+    if (!state || !maps) return fail(PPAD_ERR_INVALID, "ppad_permute: null pointer");
+    if ((uintptr_t)maps & 7) return fail(PPAD_ERR_INVALID, "ppad_permute: maps must be 8-byte aligned");
+    PPAD_DISPATCH(ctx, (permute_kernel<G><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(n, state, maps)));
+    return after_launch("permute_kernel");
+}
+
+int ppad_select_actions(const ppad_ctx *ctx, int64_t n, uint64_t env0, uint32_t step, const void *state, const float *q,
+                        int32_t method, float beta, float epsilon, int32_t max_moves, uint8_t *actions, void *stream)
+{
+    if (int r = enter(ctx, n)) return r;
+    if (n == 0) return PPAD_OK;
+    if (!state || !q || !actions) return fail(PPAD_ERR_INVALID, "ppad_select_actions: null pointer");
+    if (method != SELECT_MAX && method != SELECT_BOLTZMANN)
+        return fail(PPAD_ERR_INVALID, "ERROR: Unknown action method!");
+    RngKey key = ctx->base.key;
+    key.step = step;
+    PPAD_DISPATCH(ctx, (select_kernel<G><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(
+                           n, env0, key, state, q, method, beta, epsilon, max_moves, actions)));
+    return after_launch("select_kernel");
+}
+
+int ppad_discount(const ppad_ctx *ctx, int64_t n, int32_t max_len, double *rewards, const int32_t *lengths, double gamma,
+                  int32_t log10_flag, int32_t norm, void *stream)
+{
+    if (int r = enter(ctx, n)) return r;
+    if (n == 0 || max_len == 0) return PPAD_OK;
+    if (!rewards || max_len < 0) return fail(PPAD_ERR_INVALID, "ppad_discount: bad argument");
+    discount_kernel<<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(n, max_len, rewards, lengths, gamma, log10_flag, norm);
+    return after_launch("discount_kernel");
+}
+
+int ppad_replay_push(const ppad_ctx *ctx, int64_t n, int64_t capacity, int64_t cursor, const void *state,
+                     const uint8_t *action, const double *reward, const uint8_t *keep, const int64_t *slot,
+                     void *r_state, uint8_t *r_action, double *r_reward, void *stream)
+{
+    if (int r = enter(ctx, n)) return r;
+    if (n == 0) return PPAD_OK;
+    if (!state || !action || !reward || !r_state || !r_action || !r_reward || capacity <= 0 || cursor < 0)
+        return fail(PPAD_ERR_INVALID, "ppad_replay_push: bad argument");
+    const int words = (int)(ppad_state_bytes(ctx->cfg.rows, ctx->cfg.cols) / 4);
+    replay_push_kernel<<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(n, words, capacity, cursor, (const uint32_t *)state,
+                                                                        action, reward, keep, slot, (uint32_t *)r_state,
+                                                                        r_action, r_reward);
+    return after_launch("replay_push_kernel");
+}
+
+int ppad_replay_sample(const ppad_ctx *ctx, int64_t k, int64_t size, uint32_t step, const void *r_state,
+                       const uint8_t *r_action, const double *r_reward, void *state, uint8_t *action, double *reward,
+                       int64_t *index, void *stream)
+{
+    if (int r = enter(ctx, k)) return r;
+    if (k == 0) return PPAD_OK;
+    if (!r_state || !r_action || !r_reward || !state || !action || !reward || size <= 0)
+        return fail(PPAD_ERR_INVALID, "ppad_replay_sample: bad argument");
+    const int words = (int)(ppad_state_bytes(ctx->cfg.rows, ctx->cfg.cols) / 4);
+    RngKey key = ctx->base.key;
+    key.step = step;
+    replay_sample_kernel<<<grid_for(k), BLOCK, 0, (cudaStream_t)stream>>>(k, words, size, key, (const uint32_t *)r_state,
+                                                                          r_action, r_reward, (uint32_t *)state, action,
+                                                                          reward, index);
+    return after_launch("replay_sample_kernel");
 }
 
 }   // extern "C"

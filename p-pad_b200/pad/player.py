@@ -1,0 +1,42 @@
+"""PlayerAction -- the action space object of the reference env (ppad/pad/player.py:22-66)."""
+import numpy as np
+
+
+class PlayerAction:
+    # player.py:24-30
+    player_action = ['up', 'down', 'left', 'right', 'pass']
+    opposite_actions = {'up': 'down', 'down': 'up', 'left': 'right', 'right': 'left', 'pass': 'pass'}
+
+    def __init__(self, finger, dim_row, dim_col, env=None, seed=0):
+        self.previous_action = None
+        self.finger = finger
+        self.dim_row = dim_row
+        self.dim_col = dim_col
+        self._env = env          # the PAD facade that owns this action space (shares its GPU slab)
+        self._seed = seed
+        self._venv = None
+        self._draws = 0
+
+    def _slab(self):
+        if self._env is not None:
+            return self._env._venv
+        if self._venv is None:
+            from ..batched import BatchedPAD
+            self._venv = BatchedPAD(1, self.dim_row, self.dim_col, seed=self._seed)
+        return self._venv
+
+    def sample(self, type='random', include_pass=False):
+        """A uniformly random legal move that is not the exact reverse of previous_action (player.py:38-66),
+        drawn on the GPU (ppad_sample_actions): same support and distribution as the reference's rejection loop,
+        Philox instead of the process-global Mersenne Twister."""
+        if type != 'random':
+            raise Exception('ERROR: Unknown player action type!')
+        venv = self._slab()
+        prev = self.previous_action if self.previous_action in self.player_action else 'pass'
+        board = np.zeros((1, self.dim_row, self.dim_col), dtype=np.int64)
+        venv.set_state(board, np.asarray(self.finger).reshape(1, 2), prev=np.array([self.player_action.index(prev)], np.uint8))
+        self._draws += 1
+        a = int(venv.sample_actions(include_pass=include_pass, step=0x40000000 + self._draws)[0])
+        if a == 255:
+            raise Exception('ERROR: no legal move from finger {0}'.format(self.finger))
+        return self.player_action[a]

@@ -1,0 +1,50 @@
+"""Free functions of the reference env (ppad/pad/utils.py:26-111) on top of the CUDA kernels."""
+import numpy as np
+
+from . import parameters
+
+_slabs = {}
+
+
+def _slab(rows, cols):
+    key = (rows, cols)
+    if key not in _slabs:
+        from ..batched import BatchedPAD
+        _slabs[key] = BatchedPAD(1, rows, cols)
+    return _slabs[key]
+
+
+def cancel(board):
+    """Cancel all 3+ connected orbs of `board` IN PLACE and return the combos, as ppad.pad.utils.cancel
+    (utils.py:26-70): a list of {'color', 'N', 'enhanced', 'shape'} in the reference's order."""
+    rows, cols = board.shape
+    venv = _slab(rows, cols)
+    flags = venv.set_state(np.asarray(board)[None], np.zeros((1, 2), dtype=np.int64))
+    if int(flags[0]):
+        raise NotImplementedError('orb types 7..9 do not fit the 3-bit board state of ppad_b200')
+    n_combos, log = venv.cancel(log_cap=(rows * cols) // 3)
+    n = int(n_combos[0])
+    log = log[0, :n].cpu().numpy().view(np.uint16)
+    board[...] = venv.get_state().boards[0].cpu().numpy()
+    return [{'color': parameters.int2english[int(v) & 0xFF], 'N': np.float64(int(v) >> 8),
+             'enhanced': None, 'shape': None} for v in log]
+
+
+def illegal_actions(finger, dim_row=5, dim_col=6):
+    """Set of off-board directions (utils.py:73-83), read from bits 4..7 of ppad_legal_mask."""
+    venv = _slab(dim_row, dim_col) if (dim_row, dim_col) in ((5, 6), (6, 7)) else None
+    if venv is None:
+        raise NotImplementedError('only 5x6 and 6x7 boards have kernel instantiations')
+    venv.set_state(np.zeros((1, dim_row, dim_col), dtype=np.int64), np.asarray(finger).reshape(1, 2))
+    mask = int(venv.legal_mask()[0]) >> 4
+    names = ['up', 'down', 'left', 'right']
+    return {names[a] for a in range(4) if (mask >> a) & 1}
+
+
+def detect_island(board, island, x, y, orb_type):
+    raise NotImplementedError('detect_island is internal to cancel(): islands are computed inside the CUDA kernel '
+                              '(closure of the same-colour edge masks, csrc/ppad_core.cuh)')
+
+
+def episode2gif(*args, **kwargs):
+    raise NotImplementedError('rendering (utils.py:114-268) is out of scope of ppad_b200 (SURVEY.md section 2, #16)')

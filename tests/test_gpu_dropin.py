@@ -1,0 +1,372 @@
+"""The reference-facing layer on the GPU: the PAD drop-in facade, the per-stage entry points
+(sample / drop / fill / damage / permute) and the callers either side of the step (action selection,
+discount, replay ring, smart data, 2-step look-ahead) -- each against the oracle or the
+reference-generated fixtures."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+import oracle as orc  # noqa: E402
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ACTIONS = ['up', 'down', 'left', 'right', 'pass']
+
+
+@pytest.fixture(scope="module")
+def pb():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import ppad_b200
+    ppad_b200._cabi.lib()
+    return ppad_b200
+
+
+def bits(x):
+    return np.ascontiguousarray(x, np.float64).view(np.uint64)
+
+
+# ------------------------------------------------------------------------------------------- PAD facade
+def test_pad_facade_replays_reference_episodes(pb):
+    """game.py:282-362 semantics: records, rewards, ValueError, backtrack -- skyfall off is deterministic"""
+    z = np.load(os.path.join(G, "episodes_5x6.npz"))
+    for e in range(4):
+        env = pb.PAD(skyfall_damage=False, board=z["init_boards"][e], finger=z["init_fingers"][e], seed=1)
+        assert env.step('pass') is None
+        first = env.rewards[-1]
+        ocfg = orc.make_cfg(5, 6, False)
+        assert bits(first) == bits(orc.resolve(ocfg, z["init_boards"][e], inj=np.zeros(0, np.uint8))["reward"])
+        assert len(env.observations) == 1 and env.actions == ['pass']          # a pass records no observation
+        board, finger = env.reset(board=z["init_boards"][e], finger=z["init_fingers"][e])
+        assert np.array_equal(board, z["init_boards"][e]) and env.action_space.previous_action == 'pass'
+        for t in range(10):
+            env.step(ACTIONS[z["actions"][e, t]])
+            assert np.array_equal(env.board, z["boards"][e, t]) and np.array_equal(env.finger, z["fingers"][e, t])
+            assert env.rewards[-1] == 0 and env.action_space.previous_action == ACTIONS[z["actions"][e, t]]
+            r = env.calculate_reward(board=env.board, skyfall_damage=False)
+            assert bits(r) == bits(orc.resolve(ocfg, z["boards"][e, t], inj=np.zeros(0, np.uint8))["reward"])
+            assert np.array_equal(env.board, z["boards"][e, t])                    # evaluated on a copy
+        assert len(env.observations) == 11 and len(env.actions) == 10 and env.boards[-1] is env.observations[-1][0]
+        env.backtrack(3)
+        assert np.array_equal(env.board, z["boards"][e, 6]) and env.action_space.previous_action == ACTIONS[z["actions"][e, 6]]
+        assert len(env.boards) == 8 and len(env.actions) == 7
+        env.step('pass')
+        assert bits(env.rewards[-1]) == bits(orc.resolve(ocfg, z["boards"][e, 6], inj=np.zeros(0, np.uint8))["reward"])
+    # off-board move: ValueError, state untouched (game.py:353)
+    env = pb.PAD(board=z["init_boards"][0], finger=np.array([0, 0]))
+    with pytest.raises(ValueError, match="cannot move off the board"):
+        env.step('up')
+    assert np.array_equal(env.board, z["init_boards"][0]) and env.actions == []
+    with pytest.raises(ValueError):
+        env.step('sideways')
+    with pytest.raises(Exception, match="at least 13 orbs"):
+        pb.PAD(dim_row=2, dim_col=6)
+    with pytest.raises(Exception, match="add up to 1"):
+        pb.PAD(skyfall=[0.5, 0.1, 0, 0, 0, 0, 0, 0, 0, 0])
+    with pytest.raises(NotImplementedError):
+        pb.PAD(dim_row=4, dim_col=5)
+
+
+def test_pad_facade_skyfall_matches_oracle_philox(pb):
+    z = np.load(os.path.join(G, "episodes_5x6.npz"))
+    env = pb.PAD(board=z["boards"][0, 20], finger=z["fingers"][0, 20], seed=777)
+    ocfg = orc.make_cfg(5, 6, True, seed=777, cascade_cap=0)
+    for k in range(5):
+        tick = env._tick + 1
+        r = env.calculate_reward(board=env.board, skyfall_damage=True)
+        assert bits(r) == bits(orc.resolve(ocfg, env.board.astype(np.int8), inj=None, env=0, step=tick)["reward"])
+        env.step(env.action_space.sample())
+    # reset(): combo-free board, finger on the board, record restarted
+    board, finger = env.reset()
+    assert orc.cancel(np.ascontiguousarray(board, np.int8)) == [] and board.min() >= 0 and board.max() <= 5
+    assert 0 <= finger[0] < 5 and 0 <= finger[1] < 6 and len(env.observations) == 1
+    # visualize_episode.py:28-33: 100 sampled moves never leave the board or reverse, then a pass
+    prev = 'pass'
+    for _ in range(100):
+        a = env.action_space.sample()
+        assert a != env.action_space.opposite_actions[prev] and a != 'pass'
+        env.step(a)
+        prev = a
+    env.step('pass')
+    assert len(env.rewards) == 101 and env.rewards[-1] >= 0
+
+
+def test_pad_stage_methods(pb):
+    rng = np.random.default_rng(8)
+    env = pb.PAD(seed=5)
+    for _ in range(20):
+        b = rng.integers(-1, 6, size=(5, 6)).astype(int)
+        want = np.ascontiguousarray(b, np.int8)
+        orc.drop(want)
+        got = env.drop(b.copy())
+        assert np.array_equal(got, want)
+        filled = env.fill_board(board=got.copy())
+        assert (filled[want != -1] == want[want != -1]).all() and filled.min() >= 0 and filled.max() <= 5
+    combos = [{'color': 'red', 'N': np.float64(3)}, {'color': 'heal', 'N': np.float64(4)}, {'color': 'blue', 'N': 5.0}]
+    assert bits(env.damage(combos)) == bits(orc.damage(orc.make_cfg(), [(0, 3), (5, 4), (1, 5)]))
+    assert env.damage([]) == 0.0
+    assert 0 <= env.random_orb() <= 5
+
+
+def test_free_functions_and_compat_namespace(pb):
+    kat = json.load(open(os.path.join(G, "kat.json")))["cases"]
+    from ppad_b200.pad import utils as pad_utils
+    for c in kat[:20]:
+        if "actions" in c:
+            continue
+        b = np.array(c["board"])
+        combos = pad_utils.cancel(b)
+        assert [[pb.pad.parameters.english2int[x['color']], int(x['N'])] for x in combos] == c["combos"]
+        assert b.tolist() == c["final_board"] and all(isinstance(x['N'], np.float64) for x in combos)
+    z = np.load(os.path.join(G, "legal.npz"))
+    for r in range(5):
+        for col in range(6):
+            s = pad_utils.illegal_actions(np.array([r, col]))
+            assert sum(1 << ACTIONS.index(a) for a in s) == z["illegal_5x6"][r, col]
+    # board_finger_to_state vs the reference's output
+    zo = np.load(os.path.join(G, "onehot.npz"))
+    st = pb.board_finger_to_state(zo["boards_5x6"], zo["fingers_5x6"])
+    assert st.dtype == np.float64 and np.array_equal(st, zo["states_5x6"].astype(np.float64))
+    # discount vs the reference's output (log10 goes through different libm's: 4e-16 relative)
+    zd = np.load(os.path.join(G, "discount.npz"))
+    for i in range(0, len(zd["lens"]), 5):
+        n = int(zd["lens"][i])
+        assert np.array_equal(bits(pb.discount(zd["rewards"][i, :n], zd["gammas"][i], log10=False)), bits(zd["out_lin"][i, :n]))
+        assert np.allclose(pb.discount(zd["rewards"][i, :n], zd["gammas"][i], log10=True), zd["out_log"][i, :n], rtol=4e-16, atol=0)
+    # install_as_ppad: the reference's import paths resolve to this package
+    import sys
+    saved = {k: v for k, v in sys.modules.items() if k == "ppad" or k.startswith("ppad.")}
+    for k in saved:
+        del sys.modules[k]
+    try:
+        pb.install_as_ppad()
+        import ppad
+        import ppad.pad.utils as pu
+        from ppad.pad.utils import illegal_actions  # noqa: F401
+        env = ppad.PAD(skyfall_damage=False)
+        assert isinstance(env, pb.PAD) and pu.cancel is pad_utils.cancel and callable(ppad.discount)
+        obs, acts, rews = ppad.smart_data(boards=2, permutations=1, trajectories=2, steps=6)
+        assert len(obs) == 4 and all(len(o) == 6 and len(a) == 6 and a[-1] == 'pass' for o, a in zip(obs, acts))
+    finally:
+        for k in [k for k in sys.modules if k == "ppad" or k.startswith("ppad.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
+# ------------------------------------------------------------------------------------------- per-stage kernels
+@pytest.mark.parametrize("rows,cols", [(5, 6), (6, 7)])
+def test_sample_drop_fill_damage_permute(pb, rows, cols):
+    rng = np.random.default_rng(rows * 7)
+    n = 20000
+    boards = rng.integers(-1, 6, size=(n, rows, cols)).astype(np.int8)
+    fingers = np.stack([rng.integers(0, rows, n), rng.integers(0, cols, n)], 1).astype(np.int32)
+    prev = rng.integers(0, 5, n).astype(np.uint8)
+    env = pb.BatchedPAD(n, rows, cols, seed=31, env0=500)
+    env.set_state(boards, fingers, prev)
+    # sample == the in-kernel policy of step at the same step index; always inside the reference's legal set
+    acts = env.sample_actions(step=12).cpu().numpy()
+    z = np.load(os.path.join(G, "legal.npz"))["sample_%dx%d" % (rows, cols)]
+    assert ((z[fingers[:, 0], fingers[:, 1], prev] >> acts) & 1).all()
+    snap = env.snapshot()
+    o1 = env.step(acts, step=12)
+    s1 = env.state.clone()
+    env.restore(snap)
+    o2 = env.step(None, step=12)
+    assert torch.equal(s1, env.state) and torch.equal(o1.action, o2.action)
+    counts = np.bincount(acts, minlength=4)
+    assert counts.min() > 0.15 * n                      # roughly uniform over directions
+    with_pass = env.sample_actions(include_pass=True, step=13).cpu().numpy()
+    st_prev = env.get_state().prev.cpu().numpy()
+    assert ((with_pass == 4) <= (st_prev != 4)).all() and (with_pass == 4).any()
+    # drop / fill
+    env.set_state(boards, fingers, prev)
+    env.drop()
+    want = boards.copy()
+    for i in range(0, n, 97):
+        orc.drop(want[i])
+        assert np.array_equal(env.get_state().boards[i].cpu().numpy(), want[i])
+    inj = rng.integers(0, 6, size=(n, 48)).astype(np.uint8)
+    empties = (env.get_state().boards.cpu().numpy() == -1)
+    flags, consumed = env.fill_board(injected=inj, step=3)
+    filled = env.get_state().boards.cpu().numpy()
+    assert np.array_equal(consumed.cpu().numpy(), empties.reshape(n, -1).sum(1)) and not flags.any()
+    for i in range(0, n, 97):
+        assert np.array_equal(filled[i][empties[i]], inj[i, :empties[i].sum()])      # row-major order
+    # damage of explicit combo lists vs the reference-generated vectors
+    zd = np.load(os.path.join(G, "damage.npz"))
+    log = (zd["colors_default"].clip(0) | (zd["counts_default"] << 8)).astype(np.uint16)
+    d = pb.BatchedPAD(len(log), rows, cols)
+    reward = d.damage(log.view(np.int16), zd["lens_default"].astype(np.uint8)).cpu().numpy()
+    assert np.array_equal(bits(reward), bits(zd["rewards_default"]))
+    team = json.load(open(os.path.join(G, "custom_team.json")))
+    log = (zd["colors_custom"].clip(0) | (zd["counts_custom"] << 8)).astype(np.uint16)
+    reward = pb.BatchedPAD(len(log), rows, cols, team=team).damage(log.view(np.int16), zd["lens_custom"].astype(np.uint8))
+    assert np.array_equal(bits(reward.cpu().numpy()), bits(zd["rewards_custom"]))
+    # colour permutation
+    env.set_state(boards, fingers, prev)
+    maps = np.stack([rng.permutation(6) for _ in range(n)]).astype(np.uint8)
+    env.permute_colours(maps)
+    got = env.get_state().boards.cpu().numpy()
+    want = np.where(boards < 0, -1, np.take_along_axis(maps, boards.reshape(n, -1).clip(0).astype(np.int64), 1).reshape(boards.shape))
+    assert np.array_equal(got, want)
+
+
+# ------------------------------------------------------------------------------------------- agent side
+def _ref_select(q, finger, last, rows, cols, method, beta, eps, u0, u1):
+    """restatement of agent01.py:173-218 with the draws made explicit (float64 math)"""
+    q = q.astype(np.float64).copy()
+    if finger[0] == 0:
+        q[0] = -np.inf
+    elif finger[0] == rows - 1:
+        q[1] = -np.inf
+    if finger[1] == 0:
+        q[2] = -np.inf
+    elif finger[1] == cols - 1:
+        q[3] = -np.inf
+    if last < 4:
+        q[last ^ 1] = -np.inf
+    allowed = np.nonzero(q > -np.inf)[0]
+    if eps > 0 and eps > u0:
+        return int(allowed[int(u1 * len(allowed))]), False
+    if method == 'max':
+        return int(np.argmax(q)), False
+    p = np.exp(beta * (q - q.max()))
+    cdf = np.cumsum(p / p.sum())
+    near = bool((np.abs(cdf - u1) < 1e-6).any())
+    return int(min(np.searchsorted(cdf, u1, side='right'), 4)), near
+
+
+def test_select_actions(pb):
+    rng = np.random.default_rng(21)
+    rows, cols, n = 5, 6, 30000
+    fingers = np.stack([rng.integers(0, rows, n), rng.integers(0, cols, n)], 1).astype(np.int32)
+    prev = rng.integers(0, 5, n).astype(np.uint8)
+    moves = rng.integers(0, 12, n).astype(np.int16)
+    env = pb.BatchedPAD(n, rows, cols, seed=55, env0=9)
+    env.set_state(np.zeros((n, rows, cols), np.int8), fingers, prev, moves)
+    q = (rng.standard_normal((n, 5)) * 1000).astype(np.float32)
+    q[:200] = np.round(q[:200] / 500) * 500             # ties for argmax
+    x0 = np.array([orc.draw(55, 9 + i, 4, orc.STREAM_POLICY, 0) for i in range(0, n, 10)])
+    x1 = np.array([orc.draw(55, 9 + i, 4, orc.STREAM_POLICY, 1) for i in range(0, n, 10)])
+    for method, beta, eps in (('max', None, 0.0), ('boltzmann', 1e-3, 0.0), ('boltzmann', 1e-2, 0.2), ('max', None, 0.5)):
+        acts = env.select_actions(q, method=method, beta=beta, epsilon=eps, max_moves=10, step=4).cpu().numpy()
+        assert (acts[moves >= 10] == 4).all()                       # episode length cap
+        mism = 0
+        for k, i in enumerate(range(0, n, 10)):
+            if moves[i] >= 10:
+                continue
+            want, near = _ref_select(q[i], fingers[i], prev[i], rows, cols, method, beta or 0, eps,
+                                     x0[k] / 2 ** 32, x1[k] / 2 ** 32)
+            if acts[i] != want:
+                assert near, (method, i, acts[i], want)
+                mism += 1
+        assert mism <= 3
+    with pytest.raises(Exception, match="Provide a value for beta"):
+        env.select_actions(q, method='boltzmann')
+    with pytest.raises(Exception, match="Unknown action method"):
+        env.select_actions(q, method='softmax')
+
+
+def test_discount_batched_and_replay_ring(pb):
+    zd = np.load(os.path.join(G, "discount.npz"))
+    env = pb.BatchedPAD(64, 5, 6, seed=3)
+    g = float(zd["gammas"][0])
+    got = env.discount(zd["rewards"], g, lengths=zd["lens"], log10=False).cpu().numpy()
+    for i in range(len(zd["lens"])):
+        n = int(zd["lens"][i])
+        assert np.array_equal(bits(got[i, :n]), bits(orc.discount(zd["rewards"][i, :n], g, log10=False)))
+        assert np.array_equal(got[i, n:], zd["rewards"][i, n:])
+    normed = env.discount(zd["rewards"][1:2, :int(zd["lens"][1])], g, norm=True, log10=False).cpu().numpy()[0]
+    plain = orc.discount(zd["rewards"][1, :int(zd["lens"][1])], g, log10=False)
+    assert np.allclose(normed, (plain - plain.mean()) / plain.std(), rtol=1e-12)
+    # ring: wraparound, keep mask, sampling returns intact rows
+    env.reset()
+    from ppad_b200.replay import ReplayBuffer
+    rb = ReplayBuffer(env, 100)
+    for t in range(3):
+        out = env.step(None, eval_moves=True)
+        keep = (torch.arange(64, device=env.device) % 2 == t % 2).to(torch.uint8)
+        tagged = out.reward + 1e6 * t + torch.arange(64, device=env.device).double()
+        assert rb.push(env.state, out.action, tagged, keep) == 32
+    assert rb.size == 96 and rb.cursor == 96
+    out = env.step(None, eval_moves=True)
+    assert rb.push(env.state, out.action, out.reward) == 64 and rb.size == 100 and rb.cursor == 60
+    assert torch.equal(rb.state[96:100], env.state[:4]) and torch.equal(rb.state[:60], env.state[4:])
+    s, a, r, obs = rb.sample(5000, with_obs='f32')
+    assert obs.shape == (5000, 5, 6, 7)
+    full = {tuple(row.tolist()) + (int(x), float(y)) for row, x, y in zip(rb.state.cpu(), rb.action.cpu(), rb.reward.cpu())}
+    got_rows = {tuple(row.tolist()) + (int(x), float(y)) for row, x, y in zip(s.cpu(), a.cpu(), r.cpu())}
+    assert got_rows <= full and len(got_rows) > 90          # uniform sampling reaches (almost) every row
+
+
+def test_smart_data_and_lookahead(pb):
+    from ppad_b200.data import solved_boards
+    from ppad_b200.lookahead import two_step_lookahead
+    # fixed-length walks: reversed observations end on the solved (permuted) board, moves invert
+    obs, acts, rews = pb.smart_data(boards=3, permutations=2, trajectories=2, steps=12, gamma=0.9, log10=True, seed=4)
+    assert len(obs) == 12
+    ocfg = orc.make_cfg(5, 6, False)
+    for o, a, r in zip(obs, acts, rews):
+        assert len(o) == 12 and len(a) == 12 and len(r) == 12 and a[-1] == 'pass'
+        solved = np.ascontiguousarray(o[-1][0], np.int8)
+        final = orc.resolve(ocfg, solved, inj=np.zeros(0, np.uint8))["reward"]
+        assert final > 0 and np.isclose(r[-1], np.log10(final), rtol=1e-15)
+        assert np.allclose(r[:-1], r[-1] * 0.9 ** np.arange(11, 0, -1), rtol=1e-14)
+        # replaying the reversed actions from the first observation reproduces every later observation
+        board, finger = o[0][0].astype(np.int8).copy(), o[0][1].astype(np.int32).copy()
+        for t in range(11):
+            assert orc.apply_action(board, finger, ACTIONS.index(a[t])) == 1
+            assert np.array_equal(board, o[t + 1][0]) and np.array_equal(finger, o[t + 1][1])
+        assert sorted(np.unique(solved)) == sorted(np.unique(solved_boards.boards[0]) if False else np.unique(solved))
+    # steps = -1: walk until the first combo-free board
+    obs, acts, rews = pb.smart_data(boards=4, permutations=1, trajectories=3, steps=-1, discount=False, seed=6)
+    for o, a, r in zip(obs, acts, rews):
+        assert len(o) == len(a) == len(r) and r[-1] > 0 and all(v == 0 for v in r[:-1])
+        assert orc.cancel(np.ascontiguousarray(o[0][0], np.int8)) == []             # first reversed obs has no combo
+        for b, _ in o[1:]:
+            assert orc.cancel(np.ascontiguousarray(b, np.int8)) != []
+    # 7x6 (BASELINE configs[3]): generated solved boards
+    obs, acts, rews = pb.smart_data(boards=2, trajectories=2, steps=8, solved=solved_boards.generate_solved_boards(6, 7, 4, 1), seed=2)
+    assert len(obs) == 4 and obs[0][0][0].shape == (6, 7)
+    # 2-step look-ahead vs a per-env restatement with the oracle (no roam: q_fn None)
+    rng = np.random.default_rng(10)
+    n = 300
+    boards = rng.integers(0, 4, size=(n, 5, 6)).astype(np.int8)
+    fingers = np.stack([rng.integers(0, 5, n), rng.integers(0, 6, n)], 1).astype(np.int32)
+    prev = rng.integers(0, 5, n).astype(np.uint8)
+    env = pb.BatchedPAD(n, 5, 6, skyfall_damage=False)
+    env.set_state(boards, fingers, prev)
+    keep = env.state.clone()
+    res = two_step_lookahead(env)
+    assert torch.equal(keep, env.state)
+    rewards = res["rewards"].cpu().numpy()
+    empty = np.zeros(0, np.uint8)
+    for i in range(n):
+        want = np.full(21, -np.inf)
+        want[0] = orc.resolve(ocfg, boards[i], inj=empty)["reward"]
+        m1 = orc.legal_mask(5, 6, fingers[i], prev[i])
+        for d1 in range(4):
+            if not (m1 >> d1) & 1:
+                continue
+            b1, f1 = boards[i].copy(), fingers[i].copy()
+            orc.apply_action(b1, f1, d1)
+            want[1 + d1] = orc.resolve(ocfg, b1, inj=empty)["reward"]
+            m2 = orc.legal_mask(5, 6, f1, d1)
+            for d2 in range(4):
+                if (m2 >> d2) & 1:
+                    b2, f2 = b1.copy(), f1.copy()
+                    orc.apply_action(b2, f2, d2)
+                    want[5 + 4 * d1 + d2] = orc.resolve(ocfg, b2, inj=empty)["reward"]
+        assert np.array_equal(rewards[i], want), i
+        best = want.max()
+        assert res["best_reward"][i].item() == best and int(res["best_slot"][i]) == int(np.nonzero(want == best)[0][-1])
+    # with a roaming agent: the sequences stay legal and rewards are those of the final states
+    def q_fn(o):
+        return torch.randn(o.shape[0], 5, device=o.device, generator=torch.Generator(device=o.device).manual_seed(1)) * 100
+    res = two_step_lookahead(env, q_fn=q_fn, policy='boltzmann', beta=1e-2, max_lookahead_len=6)
+    roam = res["roam_actions"].cpu().numpy()
+    assert ((roam <= 4) | (roam == 255)).all() and (roam[:, :, :4] != 255).any()
