@@ -697,6 +697,54 @@ PPAD_HD StepOut step_board(State<G> &s, Board<G> &final_board, const StepParams 
 }
 
 // ---------------------------------------------------------------------------------------------
+// one-hot observation as a bit mask (agent01.py:254-273): bit 7 * cell + channel of w[], channels
+// 0..5 = (orb type == channel), channel 6 = finger.  Built a board row at a time: the C cells of colour
+// plane k in row r are spread to stride 7 by ONE widening multiply -- bit j of x = rowbits << k lands at
+// j + k + 6 m for every term 2^(6 m) of 0x41041041, and m = j is the wanted 7 j + k; the other products
+// fall on bits the mask drops, and no two products share a bit (j < 6), so there are no carries.
+// w must be zero-initialised and hold (7 * CELLS + 31) / 32 + 1 words.
+// ---------------------------------------------------------------------------------------------
+PPAD_HD uint32_t funnel_l(uint32_t lo, uint32_t hi, int s)   // high word of (hi:lo) << s, 0 <= s < 32
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(lo, hi, s);
+#else
+    return s ? (hi << s) | (lo >> (32 - s)) : hi;
+#endif
+}
+
+template <class G, int NW>
+PPAD_HD void obs_mask(const State<G> &s, uint32_t (&w)[NW])
+{
+    typedef typename G::W W;
+    constexpr int C = G::C, RB = 7 * C;                       // obs bits per board row
+    constexpr int CM = C < 6 ? C : 6;                         // columns handled by the multiply
+    W plane[7];
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+        plane[k] = ((k & 1) ? s.b.b0 : ~s.b.b0) & ((k & 2) ? s.b.b1 : ~s.b.b1) & ((k & 4) ? s.b.b2 : ~s.b.b2) & G::BOARD;
+    plane[6] = G::ONE << meta_finger(s.meta);                 // channel 6 = finger
+#pragma unroll
+    for (int r = 0; r < G::R; r++) {
+        uint64_t row = 0;
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+            uint64_t keep = 0;
+#pragma unroll
+            for (int j = 0; j < CM; j++) keep |= (uint64_t)1 << (7 * j + k);
+            const uint32_t x = (uint32_t)((plane[k] >> (r * C)) & ((1u << CM) - 1)) << k;
+            row |= ((uint64_t)x * 0x41041041ull) & keep;
+            if (C > 6) row |= (uint64_t)((plane[k] >> (r * C + 6)) & 1) << (42 + k);
+        }
+        const int o = RB * r, wi = o >> 5, sft = o & 31;
+        const uint32_t lo = (uint32_t)row, hi = (uint32_t)(row >> 32);
+        w[wi] |= lo << sft;
+        w[wi + 1] |= funnel_l(lo, hi, sft);
+        if (sft + RB > 64) w[wi + 2] |= hi >> (32 - sft);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // conversions between plain int boards and packed state (value -1 -> 7; 0..6 kept; others flagged)
 // ---------------------------------------------------------------------------------------------
 template <class G, class T>

@@ -113,19 +113,7 @@ __device__ __forceinline__ void emit_obs(const State<G> &s, bool valid, int n_va
     uint32_t w[NW];
 #pragma unroll
     for (int j = 0; j < NW; j++) w[j] = 0;
-    if (valid) {
-        const int finger = meta_finger(s.meta);
-#pragma unroll
-        for (int i = 0; i < G::CELLS; i++) {
-            uint32_t oh = (1u << code_at<G>(s.b, i)) & 0x3Fu;   // channels 0..5 = colour planes
-            oh |= (i == finger) ? 0x40u : 0u;                   // channel 6 = finger
-            constexpr int dummy = 0;
-            (void)dummy;
-            const int pos = 7 * i, wi = pos >> 5, sft = pos & 31;
-            w[wi] |= oh << sft;
-            if (sft > 25) w[wi + 1] |= oh >> (32 - sft);
-        }
-    }
+    if (valid) obs_mask<G, NW>(s, w);
 
     // 2. place it at bit NB * lane of the warp's stream; neighbours share one boundary word
     const int off = NB * lane, word0 = off >> 5, sft = off & 31;
@@ -148,13 +136,30 @@ __device__ __forceinline__ void emit_obs(const State<G> &s, bool valid, int n_va
     if (obs_dtype == PPAD_OBS_F32) {
         float4 *out4 = reinterpret_cast<float4 *>(obs_warp);
         const int sh4 = (lane & 7) * 4;
-#pragma unroll 4
-        for (int q = lane; q < 8 * NB; q += 32) {
-            const int e = 4 * q;
-            if (e >= valid_elems) break;
-            const float4 v = sh.lut_f32[(stream[q >> 3] >> sh4) & 15u];
-            if (e + 4 <= valid_elems) __stcs(out4 + q, v);
-            else __stcs(reinterpret_cast<float2 *>(out4 + q), make_float2(v.x, v.y));
+        if (n_valid == 32) {
+            // full warp: straight-line code, 5 instructions per 16-byte store (LDS, rotate, mask, LDS.128, STG.128)
+            const char *lut = reinterpret_cast<const char *>(sh.lut_f32);
+            const uint32_t *src = stream + (lane >> 3);
+            float4 *dst = out4 + lane;
+            const int rot = (sh4 + 28) & 31;                      // rotate right so the nibble sits at bits 4..7
+            constexpr int FULL = (8 * NB) / 32, REST = (8 * NB) % 32;
+#pragma unroll
+            for (int it = 0; it < FULL; it++) {
+                const uint32_t idx16 = __funnelshift_r(src[4 * it], src[4 * it], rot) & 0xF0u;
+                __stcs(dst + 32 * it, *reinterpret_cast<const float4 *>(lut + idx16));
+            }
+            if (REST && lane < REST) {
+                const uint32_t idx16 = __funnelshift_r(src[4 * FULL], src[4 * FULL], rot) & 0xF0u;
+                __stcs(dst + 32 * FULL, *reinterpret_cast<const float4 *>(lut + idx16));
+            }
+        } else {
+            for (int q = lane; q < 8 * NB; q += 32) {
+                const int e = 4 * q;
+                if (e >= valid_elems) break;
+                const float4 v = sh.lut_f32[(stream[q >> 3] >> sh4) & 15u];
+                if (e + 4 <= valid_elems) __stcs(out4 + q, v);
+                else __stcs(reinterpret_cast<float2 *>(out4 + q), make_float2(v.x, v.y));
+            }
         }
     } else {
         uint4 *out4 = reinterpret_cast<uint4 *>(obs_warp);

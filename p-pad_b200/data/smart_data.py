@@ -17,9 +17,11 @@ from . import solved_boards
 _OPPOSITE = np.array([1, 0, 3, 2, 4], np.uint8)
 
 
-def smart_data_batched(solved, picks, maps, steps=100, max_walk=200, seed=0, device=None):
+def smart_data_batched(solved, picks, maps, steps=100, max_walk=5000, seed=0, device=None):
     """solved: list of [R, C] boards; picks int [m] index of the solved board of each trajectory;
     maps uint8 [m, 6+] colour permutation of each trajectory.
+    With steps = -1 the walk of a board ends at its first combo-free position (the reference loops without
+    bound, smart_data.py:75-79); max_walk bounds the launch count, boards still unfinished then are cut there.
     Returns dict(states int32 [m, T, words] walk states in WALK order, actions uint8 [m, T-1] walk moves,
     lengths int32 [m] number of observations, final_reward float64 [m], venv)."""
     rows, cols = solved[0].shape
@@ -58,7 +60,7 @@ def smart_data_batched(solved, picks, maps, steps=100, max_walk=200, seed=0, dev
 
 
 def smart_data(boards=1, permutations=1, trajectories=1, steps=100, discount=True, gamma=0.9, log10=True,
-               allowed_orbs=solved_boards.allowed_orbs, solved=None, seed=0, device=None):
+               allowed_orbs=solved_boards.allowed_orbs, solved=None, seed=0, device=None, max_walk=5000):
     """Same arguments and return format as the reference's smart_data (smart_data.py:27-91):
     (observations, actions, rewards), one entry per trajectory; observations are lists of (board, finger)."""
     solved = solved_boards.boards if solved is None else solved
@@ -82,7 +84,8 @@ def smart_data(boards=1, permutations=1, trajectories=1, steps=100, discount=Tru
                 maps.append(current.copy())
     if not picks:
         return [], [], []
-    res = smart_data_batched(solved, np.array(picks), np.stack(maps), steps=steps, seed=seed, device=device)
+    res = smart_data_batched(solved, np.array(picks), np.stack(maps), steps=steps, max_walk=max_walk, seed=seed,
+                             device=device)
     venv = res['venv']
     m, t_max = res['states'].shape[:2]
     st = venv.get_state(res['states'].reshape(m * t_max, -1))

@@ -92,6 +92,22 @@ void drop_batch(int64_t n, int8_t *boards)
     }
 }
 
+template <class G>
+void obs_batch(int64_t n, const int8_t *boards, const int32_t *fingers, uint8_t *out)
+{
+    constexpr int NB = G::OBS_ELEMS, NW = (NB + 31) / 32 + 1;
+    for (int64_t i = 0; i < n; i++) {
+        State<G> s;
+        pack_cells<G, int8_t>(s.b, boards + i * G::CELLS);
+        s.meta = meta_pack(fingers[2 * i] * G::C + fingers[2 * i + 1], 4, 0);
+        uint32_t w[NW] = {0};
+        obs_mask<G, NW>(s, w);
+        for (int e = 0; e < NB; e++) out[i * NB + e] = (w[e >> 5] >> (e & 31)) & 1;
+        for (int e = NB; e < 32 * NW; e++)
+            if ((w[e >> 5] >> (e & 31)) & 1) out[i * NB] = 99;   // bits beyond the board must stay clear
+    }
+}
+
 std::string g_err;
 
 }   // namespace
@@ -151,6 +167,14 @@ int hostcore_drop(int rows, int cols, int64_t n, int8_t *boards)
 {
     if (rows == 5 && cols == 6) drop_batch<Geom<5, 6>>(n, boards);
     else if (rows == 6 && cols == 7) drop_batch<Geom<6, 7>>(n, boards);
+    else return 2;
+    return 0;
+}
+
+int hostcore_obs(int rows, int cols, int64_t n, const int8_t *boards, const int32_t *fingers, uint8_t *out)
+{
+    if (rows == 5 && cols == 6) obs_batch<Geom<5, 6>>(n, boards, fingers, out);
+    else if (rows == 6 && cols == 7) obs_batch<Geom<6, 7>>(n, boards, fingers, out);
     else return 2;
     return 0;
 }

@@ -86,6 +86,13 @@ def drop(boards):
     assert lib().hostcore_drop(rows, cols, C.c_int64(n), _p(boards)) == 0
 
 
+def obs(boards, fingers):
+    n, rows, cols = boards.shape
+    out = np.zeros((n, rows, cols, 7), np.uint8)
+    assert lib().hostcore_obs(rows, cols, C.c_int64(n), _p(boards), _p(np.ascontiguousarray(fingers, np.int32)), _p(out)) == 0
+    return out
+
+
 def sky_table(cfg):
     thr = (C.c_uint32 * 7)()
     valid = C.c_uint32(0)

@@ -211,7 +211,7 @@ def test_sample_drop_fill_damage_permute(pb, rows, cols):
     maps = np.stack([rng.permutation(6) for _ in range(n)]).astype(np.uint8)
     env.permute_colours(maps)
     got = env.get_state().boards.cpu().numpy()
-    want = np.where(boards < 0, -1, np.take_along_axis(maps, boards.reshape(n, -1).clip(0).astype(np.int64), 1).reshape(boards.shape))
+    want = np.where(boards < 0, -1, np.take_along_axis(maps.astype(np.int64), boards.reshape(n, -1).clip(0).astype(np.int64), 1).reshape(boards.shape))
     assert np.array_equal(got, want)
 
 

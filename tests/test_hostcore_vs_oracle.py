@@ -158,6 +158,19 @@ def test_reset_golden_and_philox():
             assert orc.cancel(b.copy()) == []
 
 
+@pytest.mark.parametrize("rows,cols", [(5, 6), (6, 7)])
+def test_obs_mask_matches_onehot(rows, cols):
+    rng = np.random.default_rng(77 + rows)
+    n = 5000
+    boards = random_boards(rng, n, rows, cols, "jammer_empty")
+    fingers = np.stack([rng.integers(0, rows, n), rng.integers(0, cols, n)], 1).astype(np.int32)
+    assert np.array_equal(hc.obs(boards, fingers), orc.onehot(boards, fingers).astype(np.uint8))
+    z = np.load(os.path.join(G, "onehot.npz"))
+    s = "%dx%d" % (rows, cols)
+    b = np.where(z["boards_" + s] > 6, -1, z["boards_" + s]).astype(np.int8)
+    assert np.array_equal(hc.obs(b, z["fingers_" + s]), z["states_" + s])
+
+
 def test_sky_thresholds_match_float_rule():
     z = np.load(os.path.join(G, "random_orb.npz"))
     for i, p in enumerate(z["probs"]):
