@@ -140,6 +140,14 @@ typedef struct ppad_step_args {
     int32_t obs_dtype;            /* ppad_obs_dtype */
     int32_t skyfall_damage;       /* -1 = cfg.skyfall_damage; 0 / 1 = the skyfall_damage argument of
                                      PAD.calculate_reward (game.py:364) for this call */
+    /* optional whole finger paths instead of one action (BASELINE configs[2]): paths [n, path_words]
+     * uint32, 16 moves per word, move t = (paths[i][t >> 4] >> 2 * (t & 15)) & 3; board i applies
+     * path_lens ? path_lens[i] : path_len moves like that many PAD.step(move) calls (off-board moves are
+     * skipped and flagged REJECTED), then is evaluated once when eval_moves != 0.  action_out = last
+     * accepted move (255 = none). */
+    const uint32_t *paths;
+    const uint16_t *path_lens;
+    int32_t path_words, path_len;
 } ppad_step_args;
 int ppad_step(const ppad_ctx *ctx, const ppad_step_args *args, void *stream);
 

@@ -216,3 +216,33 @@ def step_batch(cfg, boards, fingers, prev, moves=None, actions=None, eval_moves=
         inj.shape[1] if inj is not None else 0, inj.shape[1] if inj is not None else 0,
         _p(action_out, C.c_uint8), _p(reward, C.c_double), _p(info, C.c_uint32), _p(final, C.c_int8))
     return action_out, reward, info, final
+
+
+def path_batch(cfg, boards, fingers, prev, moves, paths, lens=None, eval_moves=True, inj=None, env0=0, step=0,
+               want_final=False, threads=1):
+    """Whole finger paths: paths uint8 [n, L] move ids; boards/fingers/prev/moves updated in place."""
+    n = boards.shape[0]
+    paths = np.ascontiguousarray(paths, np.uint8)
+    lens = np.ascontiguousarray(np.full(n, paths.shape[1]) if lens is None else lens, np.uint16)
+    if threads > 1 and n >= 2 * threads:
+        from concurrent.futures import ThreadPoolExecutor
+        edges = [n * k // threads for k in range(threads + 1)]
+
+        def run(k):
+            sl = slice(edges[k], edges[k + 1])
+            return path_batch(cfg, boards[sl], fingers[sl], prev[sl], None if moves is None else moves[sl], paths[sl],
+                              lens[sl], eval_moves, None if inj is None else inj[sl], env0 + edges[k], step, want_final, 1)
+        with ThreadPoolExecutor(threads) as ex:
+            parts = list(ex.map(run, range(threads)))
+        return tuple(None if parts[0][j] is None else np.concatenate([p[j] for p in parts]) for j in range(4))
+    action_out = np.zeros(n, np.uint8)
+    reward = np.zeros(n, np.float64)
+    info = np.zeros(n, np.uint32)
+    final = np.zeros_like(boards) if want_final else None
+    lib().ppad_oracle_path_batch(
+        C.byref(cfg), C.c_int64(n), C.c_uint64(env0), C.c_uint32(step), _p(boards, C.c_int8), _p(fingers, C.c_int32),
+        _p(prev, C.c_uint8), _p(moves, C.c_uint16), _p(paths, C.c_uint8), paths.shape[1], _p(lens, C.c_uint16),
+        int(bool(eval_moves)), _p(inj, C.c_uint8), inj.shape[1] if inj is not None else 0,
+        inj.shape[1] if inj is not None else 0, _p(action_out, C.c_uint8), _p(reward, C.c_double), _p(info, C.c_uint32),
+        _p(final, C.c_int8))
+    return action_out, reward, info, final

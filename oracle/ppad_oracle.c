@@ -398,3 +398,42 @@ void ppad_oracle_step_batch(const ppad_oracle_cfg *cfg, int64_t n, uint64_t env0
                       ((uint32_t)sat255(res.consumed) << 16) | ((uint32_t)(flags & 0xFF) << 24);
     }
 }
+
+/* ------------------------------------------------------------------ whole finger paths (kernel contract)
+ * Board i applies lens[i] moves paths[i * path_stride + t] (ids 0..3) like that many PAD.step(move) calls
+ * (game.py:329-362; off-board moves are skipped and flagged), then is evaluated once when eval != 0. */
+void ppad_oracle_path_batch(const ppad_oracle_cfg *cfg, int64_t n, uint64_t env0, uint32_t step,
+                            int8_t *boards, int32_t *fingers, uint8_t *prev, uint16_t *moves,
+                            const uint8_t *paths, int path_stride, const uint16_t *lens, int eval,
+                            const uint8_t *inj, int inj_stride, int n_inj,
+                            uint8_t *action_out, double *reward, uint32_t *info, int8_t *final_boards)
+{
+    const int cells = cfg->rows * cfg->cols;
+    for (int64_t i = 0; i < n; i++) {
+        int8_t *board = boards + i * cells;
+        int32_t *finger = fingers + 2 * i;
+        int flags = 0, last = 255;
+        for (int t = 0; t < lens[i]; t++) {
+            const int a = paths[(size_t)i * (size_t)path_stride + t] & 3;
+            if (ppad_oracle_apply_action(board, cfg->rows, cfg->cols, finger, a)) {
+                prev[i] = (uint8_t)a;
+                last = a;
+                if (moves && moves[i] < 65535) moves[i]++;
+            } else {
+                flags |= PPAD_OR_REJECTED;
+            }
+        }
+        ppad_oracle_result res = {0.0, 0, 0, 0, 0};
+        if (eval)
+            ppad_oracle_resolve(cfg, board, inj ? inj + (size_t)i * (size_t)inj_stride : 0, inj ? n_inj : -1,
+                                env0 + (uint64_t)i, step, &res, final_boards ? final_boards + i * cells : 0, 0, 0);
+        else if (final_boards)
+            memcpy(final_boards + i * cells, board, (size_t)cells);
+        flags |= res.flags;
+        if (action_out) action_out[i] = (uint8_t)last;
+        if (reward) reward[i] = res.reward;
+        if (info)
+            info[i] = (uint32_t)sat255(res.n_combos) | ((uint32_t)sat255(res.depth) << 8) |
+                      ((uint32_t)sat255(res.consumed) << 16) | ((uint32_t)(flags & 0xFF) << 24);
+    }
+}

@@ -119,6 +119,13 @@ void ppad_oracle_step_batch(const ppad_oracle_cfg *cfg, int64_t n, uint64_t env0
                             const uint8_t *inj, int inj_stride, int n_inj,
                             uint8_t *action_out, double *reward, uint32_t *info, int8_t *final_boards);
 
+/* Whole finger paths (include/ppad_b200.h: ppad_step_args.paths): lens[i] moves per board, one byte each */
+void ppad_oracle_path_batch(const ppad_oracle_cfg *cfg, int64_t n, uint64_t env0, uint32_t step,
+                            int8_t *boards, int32_t *fingers, uint8_t *prev, uint16_t *moves,
+                            const uint8_t *paths, int path_stride, const uint16_t *lens, int eval,
+                            const uint8_t *inj, int inj_stride, int n_inj,
+                            uint8_t *action_out, double *reward, uint32_t *info, int8_t *final_boards);
+
 #ifdef __cplusplus
 }
 #endif

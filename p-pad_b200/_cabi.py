@@ -31,7 +31,8 @@ class StepArgs(C.Structure):
                 ("actions", C.c_void_p), ("slab", C.c_void_p), ("slab_words", C.c_int32), ("n_inj", C.c_int32),
                 ("action_out", C.c_void_p), ("reward", C.c_void_p), ("info", C.c_void_p),
                 ("final_state", C.c_void_p), ("combo_log", C.c_void_p), ("log_cap", C.c_int32),
-                ("obs", C.c_void_p), ("obs_dtype", C.c_int32), ("skyfall_damage", C.c_int32)]
+                ("obs", C.c_void_p), ("obs_dtype", C.c_int32), ("skyfall_damage", C.c_int32),
+                ("paths", C.c_void_p), ("path_lens", C.c_void_p), ("path_words", C.c_int32), ("path_len", C.c_int32)]
 
 
 # every symbol include/ppad_b200.h declares (tests/test_cabi_symbols.py checks the header against this)

@@ -165,7 +165,7 @@ class BatchedPAD:
         return int(step) & 0xFFFFFFFF
 
     def step(self, actions=None, eval_moves=False, auto_reset=False, max_moves=0, injected=None, obs=None,
-             want_final=False, log_cap=0, step=None, out=None, skyfall_damage=None):
+             want_final=False, log_cap=0, step=None, out=None, skyfall_damage=None, paths=None, path_lens=None):
         """One env step of all boards (ppad_step).  actions: None (random legal moves / forced pass at
         max_moves), or uint8 [n] ids 0..4 (255 = sample).  obs: None, 'f32' or 'u8', or a preallocated tensor.
         Returns SimpleNamespace(action, reward, info, obs, final_state, combo_log); ``out`` reuses buffers."""
@@ -205,9 +205,29 @@ class BatchedPAD:
         a.obs = out.obs.data_ptr() if out.obs is not None else None
         a.obs_dtype = obs_dtype
         a.skyfall_damage = -1 if skyfall_damage is None else int(bool(skyfall_damage))
+        if paths is not None:
+            # whole finger paths: (packed int32 [n, W], L) or a uint8 [n, L] array of move ids 0..3
+            if isinstance(paths, tuple):
+                packed, plen = self._dev(paths[0], torch.int32), int(paths[1])
+            else:
+                packed, plen = self.pack_paths(paths)
+            lens = None if path_lens is None else self._dev(path_lens, torch.int16)
+            a.paths, a.path_words, a.path_len = packed.data_ptr(), packed.shape[1], plen
+            a.path_lens = lens.data_ptr() if lens is not None else None
         with torch.cuda.device(self.device):
             _cabi.check(self.lib.ppad_step(self._ctx, C.byref(a), self._stream()))
         return out
+
+    def pack_paths(self, moves):
+        """uint8 [n, L] move ids 0..3 -> (int32 [n, ceil(L / 16)] with 2 bits per move, L)"""
+        m = self._dev(moves, torch.uint8)
+        n, length = m.shape
+        words = max(1, (length + 15) // 16)
+        pad = torch.zeros((n, words * 16), dtype=torch.int64, device=self.device)
+        pad[:, :length] = m & 3
+        packed = (pad.view(n, words, 16) << (2 * torch.arange(16, device=self.device, dtype=torch.int64))).sum(dim=2)
+        packed = torch.where(packed >= 2 ** 31, packed - 2 ** 32, packed).to(torch.int32).contiguous()
+        return packed, length
 
     def calculate_reward(self, injected=None, want_final=False, log_cap=0, step=None, skyfall_damage=None):
         """PAD.calculate_reward (game.py:364-405) of every board, on a copy: the state is not modified."""

@@ -472,12 +472,6 @@ PPAD_HD void refill_all(Board<G> &b, OrbSource &src, const RngKey &key, const Sk
 // ---------------------------------------------------------------------------------------------
 // calculate_reward (game.py:364-405) on a copy of the board
 // ---------------------------------------------------------------------------------------------
-struct ResolveOut {
-    double reward;
-    int n_combos, depth, consumed;
-    uint32_t flags;
-};
-
 struct LogSink {
     uint16_t *log;   // colour | N << 8 per combo, may be nullptr
     int cap, n;
@@ -488,35 +482,62 @@ struct LogSink {
     }
 };
 
+// The state one board carries from one cascade iteration to the next.  The kernel parks it in shared
+// memory between iterations so that boards still cascading can be re-packed into dense warps.
 template <class G>
-PPAD_HD ResolveOut resolve_board(Board<G> &b, bool skyfall_damage, int cascade_cap, const TeamTable &team,
-                                 OrbSource &src, const RngKey &key, const SkyfallTable &sky, LogSink &sink)
-{
+struct CascadeItem {
+    Board<G> b;
     Tally tally;
-    tally.init();
-    ResolveOut out;
-    out.depth = 0;
-    out.flags = 0;
-    for (;;) {
-        const int m = cancel_board<G>(b, [&](int colour, int N) {
-            tally.add(team, colour, N);
-            sink.put(colour, N);
-        });
-        if (m == 0) break;
-        out.depth++;
-        if (!skyfall_damage) break;
-        if (cascade_cap > 0 && out.depth >= cascade_cap) {
-            out.flags |= FLAG_CASCADE_CAP;
-            break;
-        }
-        drop_board<G>(b);
-        fill_board<G>(b, src, key, sky);
+    int depth;
+    int cursor;        // skyfall orbs drawn so far
+    bool exhausted;    // the injected slab ran out
+    uint32_t flags;
+
+    PPAD_HD void init(const Board<G> &board, uint32_t flags0)
+    {
+        b = board;
+        tally.init();
+        depth = 0;
+        cursor = 0;
+        exhausted = false;
+        flags = flags0;
     }
-    if (src.exhausted) out.flags |= FLAG_SKYFALL_EXHAUSTED;
-    out.n_combos = tally.n_combos;
-    out.consumed = src.cursor;
-    out.reward = tally.n_combos ? tally.total() : 0.0;
-    return out;
+    PPAD_HD double reward() const { return tally.n_combos ? tally.total() : 0.0; }
+    PPAD_HD uint32_t info() const
+    {
+        return make_info(tally.n_combos, depth, cursor, flags | (exhausted ? (uint32_t)FLAG_SKYFALL_EXHAUSTED : 0u));
+    }
+};
+
+// One iteration of the loop of calculate_reward (game.py:371-397): cancel; stop if nothing matched, if
+// cascades are off or at the cap; else drop and fill.  Returns true when the refilled board matches again.
+template <class G>
+PPAD_HD bool cascade_round(CascadeItem<G> &it, bool skyfall_damage, int cascade_cap, const TeamTable &team,
+                           const uint32_t *slab, int n_inj, const RngKey &key, const SkyfallTable &sky, uint16_t *log,
+                           int log_cap)
+{
+    typedef typename G::W W;
+    const int m = cancel_board<G>(it.b, [&](int colour, int N) {
+        if (log && it.tally.n_combos < log_cap) log[it.tally.n_combos] = (uint16_t)(colour | (N << 8));
+        it.tally.add(team, colour, N);
+    });
+    if (m == 0) return false;
+    it.depth++;
+    if (!skyfall_damage) return false;
+    if (cascade_cap > 0 && it.depth >= cascade_cap) {
+        it.flags |= FLAG_CASCADE_CAP;
+        return false;
+    }
+    drop_board<G>(it.b);
+    OrbSource src;
+    src.init(slab, n_inj, STREAM_SKYFALL);
+    src.cursor = it.cursor;
+    src.exhausted = it.exhausted;
+    fill_board<G>(it.b, src, key, sky);
+    it.cursor = src.cursor;
+    it.exhausted = src.exhausted;
+    W er, ed;
+    return match_mask<G>(it.b, er, ed) != 0;
 }
 
 // damage (game.py:157-199) of an explicit combo list: log[i] = colour | N << 8
@@ -637,14 +658,20 @@ struct StepOut {
     int action;
 };
 
+struct StepPrefix {
+    int action;
+    uint32_t flags;
+    bool evaluate;
+};
+
+// Everything of one env step except the cascade: pick the action, apply the move, decide whether the
+// board is evaluated.  `s` is updated in place (a pass leaves it alone, game.py:366).
 template <class G>
-PPAD_HD StepOut step_board(State<G> &s, Board<G> &final_board, const StepParams &p, uint64_t env, int action_in,
-                           const uint32_t *slab, uint16_t *log)
+PPAD_HD StepPrefix step_prefix(State<G> &s, const StepParams &p, const RngKey &key, int action_in)
 {
-    RngKey key = p.key;
-    key.env_lo = (uint32_t)env;
-    key.env_hi = (uint32_t)(env >> 32);
-    uint32_t flags = 0;
+    StepPrefix o;
+    o.flags = 0;
+    o.evaluate = false;
     int action = action_in;   // < 0: sample
     if (action < 0) {
         if (p.max_moves > 0 && meta_moves(s.meta) >= p.max_moves) {
@@ -654,45 +681,79 @@ PPAD_HD StepOut step_board(State<G> &s, Board<G> &final_board, const StepParams 
                                       philox_draw(key, STREAM_ACTION, 0));
             if (action < 0) {
                 action = 255;
-                flags |= FLAG_NO_LEGAL_MOVE;
+                o.flags |= FLAG_NO_LEGAL_MOVE;
             }
         }
     }
-    bool evaluate = false;
     if (action == ACT_PASS) {
-        evaluate = true;
+        o.evaluate = true;
     } else if (action < ACT_PASS) {
-        if (apply_move<G>(s, action)) evaluate = p.eval_moves != 0;
-        else flags |= FLAG_REJECTED;
-    } else if (!(flags & FLAG_NO_LEGAL_MOVE)) {
-        flags |= FLAG_BAD_ACTION;
+        if (apply_move<G>(s, action)) o.evaluate = p.eval_moves != 0;
+        else o.flags |= FLAG_REJECTED;
+    } else if (!(o.flags & FLAG_NO_LEGAL_MOVE)) {
+        o.flags |= FLAG_BAD_ACTION;
     }
+    o.action = action;
+    return o;
+}
+
+// A whole finger path in one go (BASELINE configs[2]: "max-length finger paths"): len moves, 2 bits each,
+// 16 per uint32 (move t in word t >> 4 at bits 2 * (t & 15)), applied like len calls of step(move);
+// off-board moves are skipped and flagged.  The board is evaluated afterwards when eval_moves is set.
+template <class G>
+PPAD_HD StepPrefix path_prefix(State<G> &s, const StepParams &p, const uint32_t *path, int len)
+{
+    StepPrefix o;
+    o.flags = 0;
+    o.action = 255;
+    uint32_t word = 0;
+    for (int t = 0; t < len; t++) {
+        if ((t & 15) == 0) word = path[t >> 4];
+        const int a = (int)((word >> (2 * (t & 15))) & 3u);
+        if (apply_move<G>(s, a)) o.action = a;
+        else o.flags |= FLAG_REJECTED;
+    }
+    o.evaluate = p.eval_moves != 0;
+    return o;
+}
+
+// PAD.reset after a processed pass (auto_reset): returns the extra flags
+template <class G>
+PPAD_HD uint32_t step_auto_reset(State<G> &s, const StepParams &p, const RngKey &key)
+{
+    OrbSource src;
+    src.init(nullptr, -1, STREAM_RESET);
+    return FLAG_EPISODE_DONE | reset_board<G>(s, p.reset_cap, src, key, p.sky, -1);
+}
+
+PPAD_HD RngKey board_key(const StepParams &p, uint64_t env)
+{
+    RngKey key = p.key;
+    key.env_lo = (uint32_t)env;
+    key.env_hi = (uint32_t)(env >> 32);
+    return key;
+}
+
+// The whole step of one board, cascade iterations back to back (what one GPU thread would do without
+// re-binning; tests/hostcore runs this, the kernel runs the same pieces with the rounds re-packed).
+template <class G>
+PPAD_HD StepOut step_board(State<G> &s, Board<G> &final_board, const StepParams &p, uint64_t env, int action_in,
+                           const uint32_t *slab, uint16_t *log, const uint32_t *path = nullptr, int path_len = 0)
+{
+    const RngKey key = board_key(p, env);
+    const StepPrefix pre = path ? path_prefix<G>(s, p, path, path_len) : step_prefix<G>(s, p, key, action_in);
+    CascadeItem<G> it;
+    it.init(s.b, pre.flags);
+    if (pre.evaluate)
+        while (cascade_round<G>(it, p.skyfall_damage != 0, p.cascade_cap, p.team, slab, p.n_inj, key, p.sky, log,
+                                p.log_cap)) {
+        }
+    if (pre.action == ACT_PASS && p.auto_reset) it.flags |= step_auto_reset<G>(s, p, key);
+    final_board = it.b;
     StepOut out;
-    out.action = action;
-    out.reward = 0.0;
-    int n_combos = 0, depth = 0, consumed = 0;
-    final_board = s.b;
-    if (evaluate) {
-        OrbSource src;
-        src.init(slab, p.n_inj, STREAM_SKYFALL);
-        LogSink sink;
-        sink.log = log;
-        sink.cap = p.log_cap;
-        sink.n = 0;
-        const ResolveOut r = resolve_board<G>(final_board, p.skyfall_damage != 0, p.cascade_cap, p.team, src, key,
-                                              p.sky, sink);
-        out.reward = r.reward;
-        n_combos = r.n_combos;
-        depth = r.depth;
-        consumed = r.consumed;
-        flags |= r.flags;
-    }
-    if (action == ACT_PASS && p.auto_reset) {
-        OrbSource src;
-        src.init(nullptr, -1, STREAM_RESET);
-        flags |= FLAG_EPISODE_DONE | reset_board<G>(s, p.reset_cap, src, key, p.sky, -1);
-    }
-    out.info = make_info(n_combos, depth, consumed, flags);
+    out.action = pre.action;
+    out.reward = it.reward();
+    out.info = it.info();
     return out;
 }
 

@@ -206,8 +206,15 @@ struct StepKernelArgs {
     uint16_t *combo_log;
     void *obs;
     int32_t obs_dtype;
+    const uint32_t *paths;
+    const uint16_t *path_lens;
+    int32_t path_words, path_len;
 };
 
+// One thread runs its board's whole step.  (Re-packing still-cascading boards into dense warps between
+// cascade iterations through a shared-memory queue was measured in round 1 and was SLOWER -- 0.195 ms vs
+// 0.160 ms per 2^20-board step: the CTA-wide barriers leave one active warp per CTA during the deep-cascade
+// tail and the lost occupancy costs more than the saved issue slots)
 template <class G, bool OBS>
 __global__ void __launch_bounds__(BLOCK) step_kernel(const __grid_constant__ StepKernelArgs a)
 {
@@ -230,9 +237,15 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const __grid_constant__ Ste
             if (action == PPAD_SAMPLE) action = -1;
         }
         Board<G> fin;
+        int path_len = 0;
+        if (a.paths) {
+            path_len = a.path_lens ? a.path_lens[i] : a.path_len;
+            path_len = path_len > 16 * a.path_words ? 16 * a.path_words : path_len;
+        }
         const StepOut o = step_board<G>(s, fin, a.p, a.env0 + (uint64_t)i, action,
                                         a.slab ? a.slab + (size_t)i * a.p.slab_words : nullptr,
-                                        a.combo_log ? a.combo_log + (size_t)i * a.p.log_cap : nullptr);
+                                        a.combo_log ? a.combo_log + (size_t)i * a.p.log_cap : nullptr,
+                                        a.paths ? a.paths + (size_t)i * a.path_words : nullptr, path_len);
         StateIO<G>::store(a.state, i, s.b, s.meta);
         if (a.action_out) a.action_out[i] = (uint8_t)o.action;
         if (a.reward) a.reward[i] = o.reward;
@@ -743,6 +756,12 @@ int ppad_step(const ppad_ctx *ctx, const ppad_step_args *args, void *stream)
     a.combo_log = args->combo_log;
     a.obs = args->obs;
     a.obs_dtype = args->obs_dtype;
+    a.paths = args->paths;
+    a.path_lens = args->path_lens;
+    a.path_words = args->path_words;
+    a.path_len = args->path_len;
+    if (a.paths && (a.path_words <= 0 || a.path_len < 0))
+        return fail(PPAD_ERR_INVALID, "ppad_step: paths need path_words > 0 and path_len >= 0");
     cudaStream_t st = (cudaStream_t)stream;
     if (args->obs) PPAD_DISPATCH(ctx, (step_kernel<G, true><<<grid_for(a.n), BLOCK, 0, st>>>(a)));
     else PPAD_DISPATCH(ctx, (step_kernel<G, false><<<grid_for(a.n), BLOCK, 0, st>>>(a)));

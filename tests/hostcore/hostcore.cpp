@@ -17,7 +17,8 @@ namespace {
 template <class G>
 void step_batch(const StepParams &base, int64_t n, uint64_t env0, int8_t *boards, int32_t *fingers, uint8_t *prev,
                 uint16_t *moves, const uint8_t *actions, const uint32_t *slab, uint8_t *action_out, double *reward,
-                uint32_t *info, int8_t *final_boards, uint16_t *combo_log)
+                uint32_t *info, int8_t *final_boards, uint16_t *combo_log, const uint32_t *paths = nullptr,
+                int path_words = 0, const uint16_t *path_lens = nullptr)
 {
     for (int64_t i = 0; i < n; i++) {
         State<G> s;
@@ -28,7 +29,8 @@ void step_batch(const StepParams &base, int64_t n, uint64_t env0, int8_t *boards
         Board<G> fin;
         const StepOut o = step_board<G>(s, fin, base, env0 + (uint64_t)i, action,
                                         slab ? slab + (size_t)i * base.slab_words : nullptr,
-                                        combo_log ? combo_log + (size_t)i * base.log_cap : nullptr);
+                                        combo_log ? combo_log + (size_t)i * base.log_cap : nullptr,
+                                        paths ? paths + (size_t)i * path_words : nullptr, paths ? path_lens[i] : 0);
         unpack_cells<G, int8_t>(s.b, boards + i * G::CELLS);
         const int f = meta_finger(s.meta);
         fingers[2 * i] = f / G::C;
@@ -119,7 +121,8 @@ const char *hostcore_last_error() { return g_err.c_str(); }
 int hostcore_step_batch(const ppad_config *cfg, int64_t n, uint64_t env0, uint32_t step, int8_t *boards, int32_t *fingers,
                         uint8_t *prev, uint16_t *moves, const uint8_t *actions, int eval_moves, int auto_reset,
                         int max_moves, const uint32_t *slab, int slab_words, int n_inj, uint8_t *action_out,
-                        double *reward, uint32_t *info, int8_t *final_boards, uint16_t *combo_log, int log_cap)
+                        double *reward, uint32_t *info, int8_t *final_boards, uint16_t *combo_log, int log_cap,
+                        const uint32_t *paths, int path_words, const uint16_t *path_lens)
 {
     StepParams p;
     int geom;
@@ -133,10 +136,10 @@ int hostcore_step_batch(const ppad_config *cfg, int64_t n, uint64_t env0, uint32
     p.log_cap = log_cap;
     if (geom == 0)
         step_batch<Geom<5, 6>>(p, n, env0, boards, fingers, prev, moves, actions, slab, action_out, reward, info,
-                               final_boards, combo_log);
+                               final_boards, combo_log, paths, path_words, path_lens);
     else
         step_batch<Geom<6, 7>>(p, n, env0, boards, fingers, prev, moves, actions, slab, action_out, reward, info,
-                               final_boards, combo_log);
+                               final_boards, combo_log, paths, path_words, path_lens);
     return 0;
 }
 

@@ -38,7 +38,7 @@ def _p(a):
 
 
 def step_batch(cfg, boards, fingers, prev, moves=None, actions=None, eval_moves=True, auto_reset=False,
-               max_moves=0, inj=None, env0=0, step=0, want_final=False, log_cap=0):
+               max_moves=0, inj=None, env0=0, step=0, want_final=False, log_cap=0, paths=None, path_lens=None):
     n = boards.shape[0]
     action_out = np.zeros(n, np.uint8)
     reward = np.zeros(n, np.float64)
@@ -48,11 +48,19 @@ def step_batch(cfg, boards, fingers, prev, moves=None, actions=None, eval_moves=
     slab = ppad_b200.layout.pack_slab(inj) if inj is not None else None
     if actions is not None:
         actions = np.ascontiguousarray(actions, np.uint8)
+    packed = None
+    if paths is not None:
+        paths = np.asarray(paths, np.uint8)
+        words = max(1, (paths.shape[1] + 15) // 16)
+        pad = np.zeros((n, words * 16), np.uint64)
+        pad[:, :paths.shape[1]] = paths & 3
+        packed = np.ascontiguousarray((pad.reshape(n, words, 16) << (2 * np.arange(16, dtype=np.uint64))).sum(2).astype(np.uint32))
+        path_lens = np.ascontiguousarray(path_lens if path_lens is not None else np.full(n, paths.shape[1]), np.uint16)
     r = lib().hostcore_step_batch(
         C.byref(cfg), C.c_int64(n), C.c_uint64(env0), C.c_uint32(step), _p(boards), _p(fingers), _p(prev), _p(moves),
         _p(actions), int(bool(eval_moves)), int(bool(auto_reset)), int(max_moves), _p(slab),
         slab.shape[1] if slab is not None else 0, inj.shape[1] if inj is not None else 0, _p(action_out), _p(reward),
-        _p(info), _p(final), _p(log), log_cap)
+        _p(info), _p(final), _p(log), log_cap, _p(packed), packed.shape[1] if packed is not None else 0, _p(path_lens))
     if r:
         raise RuntimeError(lib().hostcore_last_error().decode())
     return action_out, reward, info, final, log

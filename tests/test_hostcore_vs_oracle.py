@@ -89,6 +89,28 @@ def test_step_batch_fuzz(rows, cols, mode):
         assert seen_flags & orc.FLAG_SKYFALL_EXHAUSTED
 
 
+@pytest.mark.parametrize("rows,cols", [(5, 6), (6, 7)])
+def test_finger_paths(rows, cols):
+    rng = np.random.default_rng(300 + rows)
+    n, L = 2000, 200
+    ocfg = orc.make_cfg(rows, cols, True, seed=5)
+    cfg = hc.cfg_from_oracle(ocfg)
+    boards = random_boards(rng, n, rows, cols, "uniform6")
+    fingers = np.stack([rng.integers(0, rows, n), rng.integers(0, cols, n)], 1).astype(np.int32)
+    paths = rng.integers(0, 4, size=(n, L)).astype(np.uint8)
+    lens = rng.integers(0, L + 1, size=n).astype(np.uint16)
+    lens[:10] = 0
+    inj = rng.integers(0, 6, size=(n, 64)).astype(np.uint8)
+    a = [boards.copy(), fingers.copy(), np.full(n, 4, np.uint8), np.zeros(n, np.uint16)]
+    b = [boards.copy(), fingers.copy(), np.full(n, 4, np.uint8), np.zeros(n, np.uint16)]
+    a0, r0, i0, f0 = orc.path_batch(ocfg, *a, paths, lens, inj=inj, step=2, want_final=True)
+    a1, r1, i1, f1, _ = hc.step_batch(cfg, *b, inj=inj, step=2, want_final=True, paths=paths, path_lens=lens)
+    for u, v in zip(a, b):
+        assert np.array_equal(u, v)
+    assert np.array_equal(a0, a1) and np.array_equal(i0, i1) and np.array_equal(bits(r0), bits(r1)) and np.array_equal(f0, f1)
+    assert ((i0 >> 24) & orc.FLAG_REJECTED).any() and (a0[:10] == 255).all()
+
+
 def test_cascade_cap_flag():
     # a one-colour skyfall never stabilises: both sides stop at the cap and say so
     ocfg = orc.make_cfg(5, 6, True, skyfall=[1, 0, 0, 0, 0, 0, 0, 0, 0, 0], cascade_cap=7)
