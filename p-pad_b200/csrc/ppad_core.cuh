@@ -81,6 +81,24 @@ PPAD_HD double dadd(double a, double b)
     return a + b;
 #endif
 }
+// Warp-level convergence helpers.  The per-board code is full of data-dependent loops; without explicit
+// reconvergence points the compiler is free to let lanes drift apart for the rest of the kernel (measured:
+// 4.5 active lanes per warp instruction).  Every lane of the warp must reach these calls.
+PPAD_HD bool warp_any(bool pred)
+{
+#if defined(__CUDA_ARCH__)
+    return __any_sync(0xFFFFFFFFu, pred) != 0;
+#else
+    return pred;
+#endif
+}
+PPAD_HD void warp_converge()
+{
+#if defined(__CUDA_ARCH__)
+    __syncwarp();
+#endif
+}
+
 PPAD_HD uint32_t mulhi32(uint32_t a, uint32_t b)
 {
 #if defined(__CUDA_ARCH__)
@@ -734,21 +752,32 @@ PPAD_HD RngKey board_key(const StepParams &p, uint64_t env)
     return key;
 }
 
-// The whole step of one board, cascade iterations back to back (what one GPU thread would do without
-// re-binning; tests/hostcore runs this, the kernel runs the same pieces with the rounds re-packed).
+// The whole step of one board.  On the GPU EVERY lane of the warp must call this (lanes past the end of the
+// batch pass live = false): the cascade loop is warp-uniform -- it runs while any lane still cascades and
+// the lanes reconverge after every iteration.
 template <class G>
-PPAD_HD StepOut step_board(State<G> &s, Board<G> &final_board, const StepParams &p, uint64_t env, int action_in,
-                           const uint32_t *slab, uint16_t *log, const uint32_t *path = nullptr, int path_len = 0)
+PPAD_HD StepOut step_board(bool live, State<G> &s, Board<G> &final_board, const StepParams &p, uint64_t env,
+                           int action_in, const uint32_t *slab, uint16_t *log, const uint32_t *path = nullptr,
+                           int path_len = 0)
 {
     const RngKey key = board_key(p, env);
-    const StepPrefix pre = path ? path_prefix<G>(s, p, path, path_len) : step_prefix<G>(s, p, key, action_in);
+    StepPrefix pre;
+    pre.action = 255;
+    pre.flags = 0;
+    pre.evaluate = false;
+    if (live) pre = path ? path_prefix<G>(s, p, path, path_len) : step_prefix<G>(s, p, key, action_in);
+    warp_converge();
     CascadeItem<G> it;
     it.init(s.b, pre.flags);
-    if (pre.evaluate)
-        while (cascade_round<G>(it, p.skyfall_damage != 0, p.cascade_cap, p.team, slab, p.n_inj, key, p.sky, log,
-                                p.log_cap)) {
-        }
-    if (pre.action == ACT_PASS && p.auto_reset) it.flags |= step_auto_reset<G>(s, p, key);
+    bool cascading = live && pre.evaluate;
+    while (warp_any(cascading)) {
+        if (cascading)
+            cascading = cascade_round<G>(it, p.skyfall_damage != 0, p.cascade_cap, p.team, slab, p.n_inj, key, p.sky,
+                                         log, p.log_cap);
+        warp_converge();
+    }
+    if (live && pre.action == ACT_PASS && p.auto_reset) it.flags |= step_auto_reset<G>(s, p, key);
+    warp_converge();
     final_board = it.b;
     StepOut out;
     out.action = pre.action;

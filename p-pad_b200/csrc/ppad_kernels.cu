@@ -50,6 +50,14 @@ struct StateIO<G, false> {
     {
         reinterpret_cast<uint4 *>(base)[i] = make_uint4(b.b0, b.b1, b.b2, meta);
     }
+    // the board planes only; the meta word of the record is left as it is
+    static __device__ __forceinline__ void store_planes(void *base, int64_t i, const Board<G> &b)
+    {
+        uint32_t *p = reinterpret_cast<uint32_t *>(base) + 4 * i;
+        p[0] = b.b0;
+        p[1] = b.b1;
+        p[2] = b.b2;
+    }
 };
 
 template <class G>
@@ -70,6 +78,13 @@ struct StateIO<G, true> {
         uint4 *p = reinterpret_cast<uint4 *>(base) + 2 * i;
         p[0] = make_uint4((uint32_t)b.b0, (uint32_t)(b.b0 >> 32), (uint32_t)b.b1, (uint32_t)(b.b1 >> 32));
         p[1] = make_uint4((uint32_t)b.b2, (uint32_t)(b.b2 >> 32), meta, 0u);
+    }
+    static __device__ __forceinline__ void store_planes(void *base, int64_t i, const Board<G> &b)
+    {
+        uint64_t *p = reinterpret_cast<uint64_t *>(base) + 4 * i;
+        p[0] = b.b0;
+        p[1] = b.b1;
+        p[2] = b.b2;
     }
 };
 
@@ -211,54 +226,185 @@ struct StepKernelArgs {
     int32_t path_words, path_len;
 };
 
-// One thread runs its board's whole step.  (Re-packing still-cascading boards into dense warps between
-// cascade iterations through a shared-memory queue was measured in round 1 and was SLOWER -- 0.195 ms vs
-// 0.160 ms per 2^20-board step: the CTA-wide barriers leave one active warp per CTA during the deep-cascade
-// tail and the lost occupancy costs more than the saved issue slots)
-template <class G, bool OBS>
-__global__ void __launch_bounds__(BLOCK) step_kernel(const __grid_constant__ StepKernelArgs a)
+// Boards that need cascade work, packed to the front of a CTA-wide shared-memory list right after the
+// move: about half of the boards have no match at all, so without this every warp would run its cascade
+// loop at ~50 % lane occupancy from the first iteration on.  After the packing, ceil(matching / 32) dense
+// warps run the cascades to completion (the loop inside is warp-uniform and reconverges every iteration);
+// warps left without work retire at once.  (Re-packing after EVERY iteration was also measured: slower,
+// the CTA barriers leave one live warp per CTA during the deep-cascade tail -- profiles/r01b_*.)
+template <class G>
+struct CascadeList {
+    typename G::W b0[BLOCK], b1[BLOCK], b2[BLOCK];
+    uint32_t tag[BLOCK];          // flags [0,8) | owner thread [8,32)
+    int warp_count[BLOCK / 32];
+};
+
+// CTA-wide stable compaction: every thread with keep == true gets a distinct slot in [0, total), in
+// thread order.  Contains two __syncthreads(); every thread of the CTA must call it.
+template <class G>
+__device__ __forceinline__ int cta_compact(CascadeList<G> &q, bool keep, int &total)
+{
+    const unsigned ballot = __ballot_sync(0xFFFFFFFFu, keep);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) q.warp_count[warp] = __popc(ballot);
+    __syncthreads();
+    int base = 0, sum = 0;
+#pragma unroll
+    for (int w = 0; w < BLOCK / 32; w++) {
+        const int c = q.warp_count[w];
+        if (w < warp) base += c;
+        sum += c;
+    }
+    total = sum;
+    __syncthreads();
+    return base + __popc(ballot & ((1u << lane) - 1u));
+}
+
+template <class G>
+__global__ void __launch_bounds__(BLOCK) step_state_kernel(const __grid_constant__ StepKernelArgs a)
+{
+    __shared__ CascadeList<G> list;
+    typedef typename G::W W;
+    const int tid = threadIdx.x;
+    const int64_t block0 = (int64_t)blockIdx.x * BLOCK;
+    const int64_t i = block0 + tid;
+    const bool valid = i < a.n;
+
+    // ---- phase 1, every thread: action / path, move, optional auto-reset, write-back, first match test
+    State<G> s;
+    s.b.b0 = s.b.b1 = s.b.b2 = 0;
+    s.meta = 0;
+    Board<G> eval_board = s.b;
+    uint32_t flags = 0;
+    bool cascading = false;
+    if (valid) {
+        s = StateIO<G>::load(a.state, i);
+        const RngKey key = board_key(a.p, a.env0 + (uint64_t)i);
+        StepPrefix pre;
+        if (a.paths) {
+            int len = a.path_lens ? a.path_lens[i] : a.path_len;
+            len = len > 16 * a.path_words ? 16 * a.path_words : len;
+            pre = path_prefix<G>(s, a.p, a.paths + (size_t)i * a.path_words, len);
+        } else {
+            int action = -1;
+            if (a.actions) {
+                action = a.actions[i];
+                if (action == PPAD_SAMPLE) action = -1;
+            }
+            pre = step_prefix<G>(s, a.p, key, action);
+        }
+        flags = pre.flags;
+        eval_board = s.b;                       // the cascade works on a copy (game.py:366)
+        if (pre.evaluate) {
+            W er, ed;
+            cascading = match_mask<G>(eval_board, er, ed) != 0;
+        }
+        if (pre.action == ACT_PASS && a.p.auto_reset) flags |= step_auto_reset<G>(s, a.p, key);
+        StateIO<G>::store(a.state, i, s.b, s.meta);
+        if (a.action_out) a.action_out[i] = (uint8_t)pre.action;
+        if (a.final_state) StateIO<G>::store(a.final_state, i, eval_board, s.meta);   // planes rewritten after a cascade
+        if (!cascading) {
+            if (a.reward) a.reward[i] = 0.0;
+            if (a.info) a.info[i] = make_info(0, 0, 0, flags);
+        }
+    }
+    int count;
+    {
+        const int slot = cta_compact<G>(list, cascading, count);
+        if (cascading) {
+            list.b0[slot] = eval_board.b0;
+            list.b1[slot] = eval_board.b1;
+            list.b2[slot] = eval_board.b2;
+            list.tag[slot] = (flags & 0xFFu) | ((uint32_t)tid << 8);
+        }
+    }
+
+    __syncthreads();                            // the packed list is complete
+
+    // ---- phase 2: the first ceil(count / 32) warps run the packed cascades to completion, the rest retire
+    if ((tid & ~31) >= count) return;
+    CascadeItem<G> it;
+    int owner = 0;
+    bool live = false;
+    if ((tid & ~31) < count) {
+        live = tid < count;
+        Board<G> b;
+        b.b0 = b.b1 = b.b2 = 0;
+        uint32_t tag = 0;
+        if (live) {
+            b.b0 = list.b0[tid];
+            b.b1 = list.b1[tid];
+            b.b2 = list.b2[tid];
+            tag = list.tag[tid];
+        }
+        owner = (int)(tag >> 8);
+        it.init(b, tag & 0xFFu);
+    }
+    const int64_t o = block0 + owner;
+    if ((tid & ~31) < count) {
+        const RngKey key = board_key(a.p, a.env0 + (uint64_t)o);
+        const uint32_t *slab = a.slab && live ? a.slab + (size_t)o * a.p.slab_words : nullptr;
+        uint16_t *log = a.combo_log && live ? a.combo_log + (size_t)o * a.p.log_cap : nullptr;
+        const bool sd = a.p.skyfall_damage != 0;
+        bool again = live;
+        while (warp_any(again)) {
+            if (again) again = cascade_round<G>(it, sd, a.p.cascade_cap, a.p.team, slab, a.p.n_inj, key, a.p.sky, log, a.p.log_cap);
+            warp_converge();
+        }
+    }
+    if (live) {
+        if (a.reward) a.reward[o] = it.reward();
+        if (a.info) a.info[o] = it.info();
+        if (a.final_state) StateIO<G>::store_planes(a.final_state, o, it.b);   // meta was written in phase 1
+    }
+}
+
+// The step WITH the one-hot observation: this variant is bound by the 840 B/board store stream, and here
+// keeping all eight warps of a CTA busy (each runs its own boards' cascades, then emits its observation)
+// hides more latency than packing the cascades into fewer warps -- measured 0.159 ms vs 0.162-0.166 ms per
+// 2^20-board step for the packed variants.
+template <class G>
+__global__ void __launch_bounds__(BLOCK) step_obs_kernel(const __grid_constant__ StepKernelArgs a)
 {
     __shared__ ObsShared obs_sh;
-    __shared__ uint32_t obs_stream[OBS ? (BLOCK / 32) * ObsGeom<G>::WARP_WORDS : 1];
-    if (OBS) {
-        obs_init_luts(obs_sh);
-        __syncthreads();
-    }
+    __shared__ uint32_t obs_stream[(BLOCK / 32) * ObsGeom<G>::WARP_WORDS];
+    obs_init_luts(obs_sh);
+    __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     const bool valid = i < a.n;
     State<G> s;
     s.b.b0 = s.b.b1 = s.b.b2 = 0;
     s.meta = 0;
+    int action = -1, path_len = 0;
     if (valid) {
         s = StateIO<G>::load(a.state, i);
-        int action = -1;
         if (a.actions) {
             action = a.actions[i];
             if (action == PPAD_SAMPLE) action = -1;
         }
-        Board<G> fin;
-        int path_len = 0;
         if (a.paths) {
             path_len = a.path_lens ? a.path_lens[i] : a.path_len;
             path_len = path_len > 16 * a.path_words ? 16 * a.path_words : path_len;
         }
-        const StepOut o = step_board<G>(s, fin, a.p, a.env0 + (uint64_t)i, action,
-                                        a.slab ? a.slab + (size_t)i * a.p.slab_words : nullptr,
-                                        a.combo_log ? a.combo_log + (size_t)i * a.p.log_cap : nullptr,
-                                        a.paths ? a.paths + (size_t)i * a.path_words : nullptr, path_len);
+    }
+    // every lane takes part (the cascade loop inside is warp-uniform); lanes past the batch are not live
+    Board<G> fin;
+    const StepOut o = step_board<G>(valid, s, fin, a.p, a.env0 + (uint64_t)i, action,
+                                    a.slab && valid ? a.slab + (size_t)i * a.p.slab_words : nullptr,
+                                    a.combo_log && valid ? a.combo_log + (size_t)i * a.p.log_cap : nullptr,
+                                    a.paths && valid ? a.paths + (size_t)i * a.path_words : nullptr, path_len);
+    if (valid) {
         StateIO<G>::store(a.state, i, s.b, s.meta);
         if (a.action_out) a.action_out[i] = (uint8_t)o.action;
         if (a.reward) a.reward[i] = o.reward;
         if (a.info) a.info[i] = o.info;
         if (a.final_state) StateIO<G>::store(a.final_state, i, fin, s.meta);
     }
-    if (OBS) {
-        const int64_t warp0 = i - (threadIdx.x & 31);
-        if (warp0 < a.n) {
-            const int n_valid = (int)(a.n - warp0 < 32 ? a.n - warp0 : 32);
-            emit_obs<G>(s, valid, n_valid, obs_stream + (threadIdx.x >> 5) * ObsGeom<G>::WARP_WORDS, obs_sh,
-                        obs_warp_ptr<G>(a.obs, warp0, a.obs_dtype), a.obs_dtype);
-        }
+    const int64_t warp0 = i - (threadIdx.x & 31);
+    if (warp0 < a.n) {
+        const int n_valid = (int)(a.n - warp0 < 32 ? a.n - warp0 : 32);
+        emit_obs<G>(s, valid, n_valid, obs_stream + (threadIdx.x >> 5) * ObsGeom<G>::WARP_WORDS, obs_sh,
+                    obs_warp_ptr<G>(a.obs, warp0, a.obs_dtype), a.obs_dtype);
     }
 }
 
@@ -763,9 +909,9 @@ int ppad_step(const ppad_ctx *ctx, const ppad_step_args *args, void *stream)
     if (a.paths && (a.path_words <= 0 || a.path_len < 0))
         return fail(PPAD_ERR_INVALID, "ppad_step: paths need path_words > 0 and path_len >= 0");
     cudaStream_t st = (cudaStream_t)stream;
-    if (args->obs) PPAD_DISPATCH(ctx, (step_kernel<G, true><<<grid_for(a.n), BLOCK, 0, st>>>(a)));
-    else PPAD_DISPATCH(ctx, (step_kernel<G, false><<<grid_for(a.n), BLOCK, 0, st>>>(a)));
-    return after_launch("step_kernel");
+    if (args->obs) PPAD_DISPATCH(ctx, (step_obs_kernel<G><<<grid_for(a.n), BLOCK, 0, st>>>(a)));
+    else PPAD_DISPATCH(ctx, (step_state_kernel<G><<<grid_for(a.n), BLOCK, 0, st>>>(a)));
+    return after_launch(args->obs ? "step_obs_kernel" : "step_state_kernel");
 }
 
 int ppad_encode_obs(const ppad_ctx *ctx, int64_t n, const void *state, void *obs, int obs_dtype, void *stream)

@@ -27,7 +27,7 @@ void step_batch(const StepParams &base, int64_t n, uint64_t env0, int8_t *boards
         int action = actions ? actions[i] : -1;
         if (action == 255) action = -1;
         Board<G> fin;
-        const StepOut o = step_board<G>(s, fin, base, env0 + (uint64_t)i, action,
+        const StepOut o = step_board<G>(true, s, fin, base, env0 + (uint64_t)i, action,
                                         slab ? slab + (size_t)i * base.slab_words : nullptr,
                                         combo_log ? combo_log + (size_t)i * base.log_cap : nullptr,
                                         paths ? paths + (size_t)i * path_words : nullptr, paths ? path_lens[i] : 0);
