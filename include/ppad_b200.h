@@ -67,7 +67,7 @@ typedef enum ppad_obs_dtype { PPAD_OBS_F32 = 0, PPAD_OBS_U8 = 1 } ppad_obs_dtype
 
 /* Environment constants: the keyword arguments of PAD.__init__ (game.py:39-50) that reach the hot path. */
 typedef struct ppad_config {
-    int32_t rows, cols;              /* dim_row, dim_col: (5,6) and (6,7) are instantiated */
+    int32_t rows, cols;              /* dim_row, dim_col: (4,5), (5,6) and (6,7) are instantiated */
     int32_t skyfall_damage;          /* game.py:45,387: cascade with drop + skyfall, or a single cancel */
     int32_t cascade_cap;             /* the reference has none; 0 = unlimited */
     int32_t reset_cap;               /* rejection-sampling attempts in reset; 0 = unlimited */

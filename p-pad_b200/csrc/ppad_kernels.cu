@@ -697,6 +697,7 @@ int after_launch(const char *name)
 
 inline unsigned grid_for(int64_t n) { return (unsigned)((n + BLOCK - 1) / BLOCK); }
 
+typedef Geom<4, 5> G45;
 typedef Geom<5, 6> G56;
 typedef Geom<6, 7> G67;
 
@@ -705,14 +706,15 @@ typedef Geom<6, 7> G67;
 struct ppad_ctx {
     ppad_config cfg;
     int device;
-    int geom;   // 0 = 5x6, 1 = 6x7
+    int geom;   // 0 = 5x6, 1 = 6x7, 2 = 4x5
     StepParams base;
 };
 
-#define PPAD_DISPATCH(ctx, EXPR)                 \
-    do {                                         \
-        if ((ctx)->geom == 0) { typedef G56 G; EXPR; } \
-        else { typedef G67 G; EXPR; }            \
+#define PPAD_DISPATCH(ctx, EXPR)                            \
+    do {                                                    \
+        if ((ctx)->geom == 0) { typedef G56 G; EXPR; }      \
+        else if ((ctx)->geom == 1) { typedef G67 G; EXPR; } \
+        else { typedef G45 G; EXPR; }                       \
     } while (0)
 
 template <class G, class T>
@@ -770,6 +772,7 @@ int64_t ppad_state_bytes(int rows, int cols)
 {
     if (rows == 5 && cols == 6) return G56::STATE_BYTES;
     if (rows == 6 && cols == 7) return G67::STATE_BYTES;
+    if (rows == 4 && cols == 5) return G45::STATE_BYTES;
     return -1;
 }
 

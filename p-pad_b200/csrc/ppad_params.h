@@ -10,7 +10,7 @@
 
 namespace ppad {
 
-// returns PPAD_OK or an error status with `err` set; geom: 0 = 5x6, 1 = 6x7
+// returns PPAD_OK or an error status with `err` set; geom: 0 = 5x6, 1 = 6x7, 2 = 4x5
 inline int build_params(const ppad_config &cfg, StepParams &p, int &geom, std::string &err)
 {
     std::memset(&p, 0, sizeof(p));
@@ -37,8 +37,9 @@ inline int build_params(const ppad_config &cfg, StepParams &p, int &geom, std::s
     }
     if (cfg.rows == 5 && cfg.cols == 6) geom = 0;
     else if (cfg.rows == 6 && cfg.cols == 7) geom = 1;
+    else if (cfg.rows == 4 && cfg.cols == 5) geom = 2;
     else {
-        err = "only 5x6 and 6x7 boards have kernel instantiations";
+        err = "only 4x5, 5x6 and 6x7 boards (rows x cols) have kernel instantiations";
         return PPAD_ERR_UNSUPPORTED;
     }
     if (cfg.skyfall[7] > 0 || cfg.skyfall[8] > 0 || cfg.skyfall[9] > 0) {

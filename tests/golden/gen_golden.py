@@ -351,6 +351,7 @@ def main():
     gen_resolve(5, 6, 2500, 300, 201, "5x6")
     gen_resolve(6, 7, 1000, 150, 202, "6x7")
     gen_resolve(5, 6, 400, 0, 203, "5x6_custom_team", team=CUSTOM_TEAM)
+    gen_resolve(4, 5, 500, 60, 204, "4x5")
 
 
 if __name__ == "__main__":

@@ -137,6 +137,9 @@ int hostcore_step_batch(const ppad_config *cfg, int64_t n, uint64_t env0, uint32
     if (geom == 0)
         step_batch<Geom<5, 6>>(p, n, env0, boards, fingers, prev, moves, actions, slab, action_out, reward, info,
                                final_boards, combo_log, paths, path_words, path_lens);
+    else if (geom == 2)
+        step_batch<Geom<4, 5>>(p, n, env0, boards, fingers, prev, moves, actions, slab, action_out, reward, info,
+                               final_boards, combo_log, paths, path_words, path_lens);
     else
         step_batch<Geom<6, 7>>(p, n, env0, boards, fingers, prev, moves, actions, slab, action_out, reward, info,
                                final_boards, combo_log, paths, path_words, path_lens);
@@ -154,6 +157,7 @@ int hostcore_reset(const ppad_config *cfg, int64_t n, uint64_t env0, uint32_t st
     p.n_inj = slab ? n_inj : -1;
     p.slab_words = slab_words;
     if (geom == 0) reset_batch<Geom<5, 6>>(p, n, env0, slab, fingers_in, boards, fingers, flags, consumed);
+    else if (geom == 2) reset_batch<Geom<4, 5>>(p, n, env0, slab, fingers_in, boards, fingers, flags, consumed);
     else reset_batch<Geom<6, 7>>(p, n, env0, slab, fingers_in, boards, fingers, flags, consumed);
     return 0;
 }
@@ -161,6 +165,7 @@ int hostcore_reset(const ppad_config *cfg, int64_t n, uint64_t env0, uint32_t st
 int hostcore_cancel(int rows, int cols, int64_t n, int8_t *boards, uint8_t *n_combos, uint16_t *combo_log, int log_cap)
 {
     if (rows == 5 && cols == 6) cancel_batch<Geom<5, 6>>(n, boards, n_combos, combo_log, log_cap);
+    else if (rows == 4 && cols == 5) cancel_batch<Geom<4, 5>>(n, boards, n_combos, combo_log, log_cap);
     else if (rows == 6 && cols == 7) cancel_batch<Geom<6, 7>>(n, boards, n_combos, combo_log, log_cap);
     else return 2;
     return 0;
@@ -169,6 +174,7 @@ int hostcore_cancel(int rows, int cols, int64_t n, int8_t *boards, uint8_t *n_co
 int hostcore_drop(int rows, int cols, int64_t n, int8_t *boards)
 {
     if (rows == 5 && cols == 6) drop_batch<Geom<5, 6>>(n, boards);
+    else if (rows == 4 && cols == 5) drop_batch<Geom<4, 5>>(n, boards);
     else if (rows == 6 && cols == 7) drop_batch<Geom<6, 7>>(n, boards);
     else return 2;
     return 0;
@@ -177,6 +183,7 @@ int hostcore_drop(int rows, int cols, int64_t n, int8_t *boards)
 int hostcore_obs(int rows, int cols, int64_t n, const int8_t *boards, const int32_t *fingers, uint8_t *out)
 {
     if (rows == 5 && cols == 6) obs_batch<Geom<5, 6>>(n, boards, fingers, out);
+    else if (rows == 4 && cols == 5) obs_batch<Geom<4, 5>>(n, boards, fingers, out);
     else if (rows == 6 && cols == 7) obs_batch<Geom<6, 7>>(n, boards, fingers, out);
     else return 2;
     return 0;

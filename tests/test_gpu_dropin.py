@@ -68,7 +68,9 @@ def test_pad_facade_replays_reference_episodes(pb):
     with pytest.raises(Exception, match="add up to 1"):
         pb.PAD(skyfall=[0.5, 0.1, 0, 0, 0, 0, 0, 0, 0, 0])
     with pytest.raises(NotImplementedError):
-        pb.PAD(dim_row=4, dim_col=5)
+        pb.PAD(dim_row=4, dim_col=6)
+    small = pb.PAD(dim_row=4, dim_col=5, seed=3)
+    assert small.board.shape == (4, 5) and orc.cancel(np.ascontiguousarray(small.board, np.int8)) == []
 
 
 def test_pad_facade_skyfall_matches_oracle_philox(pb):

@@ -73,7 +73,7 @@ def test_kat_through_cabi(pb):
     assert env.get_state(o.final_state).boards[0].cpu().numpy().tolist() == c["final_board"]
 
 
-@pytest.mark.parametrize("tag,rows,cols,team", [("5x6", 5, 6, None), ("6x7", 6, 7, None),
+@pytest.mark.parametrize("tag,rows,cols,team", [("5x6", 5, 6, None), ("6x7", 6, 7, None), ("4x5", 4, 5, None),
                                                  ("5x6_custom_team", 5, 6, "custom")])
 def test_resolve_golden_vectors(pb, tag, rows, cols, team):
     z = np.load(os.path.join(G, "resolve_%s.npz" % tag))
@@ -113,7 +113,7 @@ def test_episode_golden_vectors(pb, tag, rows, cols):
     assert np.array_equal(bits(o.reward.cpu().numpy()), bits(z["pass_reward"]))
 
 
-@pytest.mark.parametrize("rows,cols", [(5, 6), (6, 7)])
+@pytest.mark.parametrize("rows,cols", [(4, 5), (5, 6), (6, 7)])
 @pytest.mark.parametrize("mode", ["injected", "philox", "injected_short", "no_skyfall"])
 def test_step_fuzz_vs_oracle(pb, rows, cols, mode):
     rng = np.random.default_rng(2000 + rows + len(mode))
@@ -147,7 +147,7 @@ def test_step_fuzz_vs_oracle(pb, rows, cols, mode):
         assert np.array_equal(o.obs.cpu().numpy(), orc.onehot(boards, fingers).astype(np.uint8)), t
 
 
-@pytest.mark.parametrize("rows,cols", [(5, 6), (6, 7)])
+@pytest.mark.parametrize("rows,cols", [(4, 5), (5, 6), (6, 7)])
 @pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 255, 257, 1000])
 def test_obs_ragged_batches(pb, rows, cols, n):
     rng = np.random.default_rng(n)
@@ -310,6 +310,7 @@ def test_empty_batch_and_errors(pb):
     with pytest.raises(pb._cabi.PPADError) as e:
         pb.BatchedPAD(4, 4, 4)
     assert e.value.status == pb._cabi.ERR_UNSUPPORTED
+    assert pb.BatchedPAD(4, 4, 5).words == 4
     with pytest.raises(pb._cabi.PPADError) as e:
         pb.BatchedPAD(4, 3, 4)
     assert "at least 13 orbs" in str(e.value)

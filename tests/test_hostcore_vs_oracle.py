@@ -30,7 +30,7 @@ def random_boards(rng, n, rows, cols, kind):
     return np.ascontiguousarray(b, np.int8)
 
 
-@pytest.mark.parametrize("rows,cols", [(5, 6), (6, 7)])
+@pytest.mark.parametrize("rows,cols", [(4, 5), (5, 6), (6, 7)])
 @pytest.mark.parametrize("kind", ["uniform6", "few", "jammer_empty"])
 def test_cancel_and_drop_fuzz(rows, cols, kind):
     rng = np.random.default_rng(hash((rows, kind)) & 0xFFFF)
@@ -50,7 +50,7 @@ def test_cancel_and_drop_fuzz(rows, cols, kind):
     assert np.array_equal(mine, boards)
 
 
-@pytest.mark.parametrize("rows,cols", [(5, 6), (6, 7)])
+@pytest.mark.parametrize("rows,cols", [(4, 5), (5, 6), (6, 7)])
 @pytest.mark.parametrize("mode", ["injected", "philox", "injected_short", "no_skyfall"])
 def test_step_batch_fuzz(rows, cols, mode):
     rng = np.random.default_rng(1000 + rows + len(mode))
@@ -89,7 +89,7 @@ def test_step_batch_fuzz(rows, cols, mode):
         assert seen_flags & orc.FLAG_SKYFALL_EXHAUSTED
 
 
-@pytest.mark.parametrize("rows,cols", [(5, 6), (6, 7)])
+@pytest.mark.parametrize("rows,cols", [(4, 5), (5, 6), (6, 7)])
 def test_finger_paths(rows, cols):
     rng = np.random.default_rng(300 + rows)
     n, L = 2000, 200
@@ -123,7 +123,7 @@ def test_cascade_cap_flag():
     assert ((i0 >> 24) & orc.FLAG_CASCADE_CAP).all() and (((i0 >> 8) & 0xFF) == 7).all()
 
 
-@pytest.mark.parametrize("tag,rows,cols,team", [("5x6", 5, 6, None), ("6x7", 6, 7, None),
+@pytest.mark.parametrize("tag,rows,cols,team", [("5x6", 5, 6, None), ("6x7", 6, 7, None), ("4x5", 4, 5, None),
                                                  ("5x6_custom_team", 5, 6, "custom")])
 def test_resolve_golden_vectors(tag, rows, cols, team):
     """straight against what the reference produced"""
@@ -180,13 +180,15 @@ def test_reset_golden_and_philox():
             assert orc.cancel(b.copy()) == []
 
 
-@pytest.mark.parametrize("rows,cols", [(5, 6), (6, 7)])
+@pytest.mark.parametrize("rows,cols", [(4, 5), (5, 6), (6, 7)])
 def test_obs_mask_matches_onehot(rows, cols):
     rng = np.random.default_rng(77 + rows)
     n = 5000
     boards = random_boards(rng, n, rows, cols, "jammer_empty")
     fingers = np.stack([rng.integers(0, rows, n), rng.integers(0, cols, n)], 1).astype(np.int32)
     assert np.array_equal(hc.obs(boards, fingers), orc.onehot(boards, fingers).astype(np.uint8))
+    if rows == 4:
+        return
     z = np.load(os.path.join(G, "onehot.npz"))
     s = "%dx%d" % (rows, cols)
     b = np.where(z["boards_" + s] > 6, -1, z["boards_" + s]).astype(np.int8)

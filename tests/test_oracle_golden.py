@@ -48,7 +48,7 @@ def test_kat_moves_then_skyfall():
     assert r["final_board"].tolist() == c["final_board"]
 
 
-@pytest.mark.parametrize("tag,rows,cols,team", [("5x6", 5, 6, None), ("6x7", 6, 7, None),
+@pytest.mark.parametrize("tag,rows,cols,team", [("5x6", 5, 6, None), ("6x7", 6, 7, None), ("4x5", 4, 5, None),
                                                  ("5x6_custom_team", 5, 6, "custom")])
 def test_resolve_vectors(tag, rows, cols, team):
     z = np.load(os.path.join(G, "resolve_%s.npz" % tag))
