@@ -13,6 +13,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -226,143 +227,10 @@ struct StepKernelArgs {
     int32_t path_words, path_len;
 };
 
-// Boards that need cascade work, packed to the front of a CTA-wide shared-memory list right after the
-// move: about half of the boards have no match at all, so without this every warp would run its cascade
-// loop at ~50 % lane occupancy from the first iteration on.  After the packing, ceil(matching / 32) dense
-// warps run the cascades to completion (the loop inside is warp-uniform and reconverges every iteration);
-// warps left without work retire at once.  (Re-packing after EVERY iteration was also measured: slower,
-// the CTA barriers leave one live warp per CTA during the deep-cascade tail -- profiles/r01b_*.)
-template <class G>
-struct CascadeList {
-    typename G::W b0[BLOCK], b1[BLOCK], b2[BLOCK];
-    uint32_t tag[BLOCK];          // flags [0,8) | owner thread [8,32)
-    int warp_count[BLOCK / 32];
-};
-
-// CTA-wide stable compaction: every thread with keep == true gets a distinct slot in [0, total), in
-// thread order.  Contains two __syncthreads(); every thread of the CTA must call it.
-template <class G>
-__device__ __forceinline__ int cta_compact(CascadeList<G> &q, bool keep, int &total)
-{
-    const unsigned ballot = __ballot_sync(0xFFFFFFFFu, keep);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) q.warp_count[warp] = __popc(ballot);
-    __syncthreads();
-    int base = 0, sum = 0;
-#pragma unroll
-    for (int w = 0; w < BLOCK / 32; w++) {
-        const int c = q.warp_count[w];
-        if (w < warp) base += c;
-        sum += c;
-    }
-    total = sum;
-    __syncthreads();
-    return base + __popc(ballot & ((1u << lane) - 1u));
-}
-
-template <class G>
-__global__ void __launch_bounds__(BLOCK) step_state_kernel(const __grid_constant__ StepKernelArgs a)
-{
-    __shared__ CascadeList<G> list;
-    typedef typename G::W W;
-    const int tid = threadIdx.x;
-    const int64_t block0 = (int64_t)blockIdx.x * BLOCK;
-    const int64_t i = block0 + tid;
-    const bool valid = i < a.n;
-
-    // ---- phase 1, every thread: action / path, move, optional auto-reset, write-back, first match test
-    State<G> s;
-    s.b.b0 = s.b.b1 = s.b.b2 = 0;
-    s.meta = 0;
-    Board<G> eval_board = s.b;
-    uint32_t flags = 0;
-    bool cascading = false;
-    if (valid) {
-        s = StateIO<G>::load(a.state, i);
-        const RngKey key = board_key(a.p, a.env0 + (uint64_t)i);
-        StepPrefix pre;
-        if (a.paths) {
-            int len = a.path_lens ? a.path_lens[i] : a.path_len;
-            len = len > 16 * a.path_words ? 16 * a.path_words : len;
-            pre = path_prefix<G>(s, a.p, a.paths + (size_t)i * a.path_words, len);
-        } else {
-            int action = -1;
-            if (a.actions) {
-                action = a.actions[i];
-                if (action == PPAD_SAMPLE) action = -1;
-            }
-            pre = step_prefix<G>(s, a.p, key, action);
-        }
-        flags = pre.flags;
-        eval_board = s.b;                       // the cascade works on a copy (game.py:366)
-        if (pre.evaluate) {
-            W er, ed;
-            cascading = match_mask<G>(eval_board, er, ed) != 0;
-        }
-        if (pre.action == ACT_PASS && a.p.auto_reset) flags |= step_auto_reset<G>(s, a.p, key);
-        StateIO<G>::store(a.state, i, s.b, s.meta);
-        if (a.action_out) a.action_out[i] = (uint8_t)pre.action;
-        if (a.final_state) StateIO<G>::store(a.final_state, i, eval_board, s.meta);   // planes rewritten after a cascade
-        if (!cascading) {
-            if (a.reward) a.reward[i] = 0.0;
-            if (a.info) a.info[i] = make_info(0, 0, 0, flags);
-        }
-    }
-    int count;
-    {
-        const int slot = cta_compact<G>(list, cascading, count);
-        if (cascading) {
-            list.b0[slot] = eval_board.b0;
-            list.b1[slot] = eval_board.b1;
-            list.b2[slot] = eval_board.b2;
-            list.tag[slot] = (flags & 0xFFu) | ((uint32_t)tid << 8);
-        }
-    }
-
-    __syncthreads();                            // the packed list is complete
-
-    // ---- phase 2: the first ceil(count / 32) warps run the packed cascades to completion, the rest retire
-    if ((tid & ~31) >= count) return;
-    CascadeItem<G> it;
-    int owner = 0;
-    bool live = false;
-    if ((tid & ~31) < count) {
-        live = tid < count;
-        Board<G> b;
-        b.b0 = b.b1 = b.b2 = 0;
-        uint32_t tag = 0;
-        if (live) {
-            b.b0 = list.b0[tid];
-            b.b1 = list.b1[tid];
-            b.b2 = list.b2[tid];
-            tag = list.tag[tid];
-        }
-        owner = (int)(tag >> 8);
-        it.init(b, tag & 0xFFu);
-    }
-    const int64_t o = block0 + owner;
-    if ((tid & ~31) < count) {
-        const RngKey key = board_key(a.p, a.env0 + (uint64_t)o);
-        const uint32_t *slab = a.slab && live ? a.slab + (size_t)o * a.p.slab_words : nullptr;
-        uint16_t *log = a.combo_log && live ? a.combo_log + (size_t)o * a.p.log_cap : nullptr;
-        const bool sd = a.p.skyfall_damage != 0;
-        bool again = live;
-        while (warp_any(again)) {
-            if (again) again = cascade_round<G>(it, sd, a.p.cascade_cap, a.p.team, slab, a.p.n_inj, key, a.p.sky, log, a.p.log_cap);
-            warp_converge();
-        }
-    }
-    if (live) {
-        if (a.reward) a.reward[o] = it.reward();
-        if (a.info) a.info[o] = it.info();
-        if (a.final_state) StateIO<G>::store_planes(a.final_state, o, it.b);   // meta was written in phase 1
-    }
-}
-
-// The step WITH the one-hot observation: this variant is bound by the 840 B/board store stream, and here
-// keeping all eight warps of a CTA busy (each runs its own boards' cascades, then emits its observation)
-// hides more latency than packing the cascades into fewer warps -- measured 0.159 ms vs 0.162-0.166 ms per
-// 2^20-board step for the packed variants.
+// The step WITH the one-hot observation, one thread per board.  This variant is bound by the 840 B/board store
+// stream, and keeping all eight warps of a CTA busy (each runs its own boards' cascades in a warp-uniform
+// loop, then emits its observation) overlaps the stores with the integer work best: measured 0.159 ms per
+// 2^20-board step against 0.162-0.166 ms for packing the cascades once and 0.19 ms for the pooled kernel.
 template <class G>
 __global__ void __launch_bounds__(BLOCK) step_obs_kernel(const __grid_constant__ StepKernelArgs a)
 {
@@ -405,6 +273,176 @@ __global__ void __launch_bounds__(BLOCK) step_obs_kernel(const __grid_constant__
         const int n_valid = (int)(a.n - warp0 < 32 ? a.n - warp0 : 32);
         emit_obs<G>(s, valid, n_valid, obs_stream + (threadIdx.x >> 5) * ObsGeom<G>::WARP_WORDS, obs_sh,
                     obs_warp_ptr<G>(a.obs, warp0, a.obs_dtype), a.obs_dtype);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Persistent step kernel with a recirculating cascade pool.
+//
+// Cascade depth is geometric-like (about 45 % of the boards: 0 iterations, 38 %: 1, 12 %: 2, ...), so a warp
+// that keeps its own 32 boards runs every iteration for its unluckiest lane at ~40 % lane occupancy, and
+// packing only once leaves the deep tail to a few lanes.  Here each CTA is persistent and owns a pool of
+// boards that are still cascading, parked in shared memory between iterations:
+//   fill : when the pool is low, run the cheap convergent part (action, move, first match test, write-back) on
+//          the next tile of BLOCK boards and append the boards that matched;
+//   round: the top min(pool, BLOCK) boards run ONE cascade iteration on dense warps; finished boards write
+//          their reward, the others go back to the pool.
+// Deep boards simply stay in the pool while fresh tiles keep streaming in, so every round has (nearly) a
+// full complement of lanes; only the final drain of each CTA runs at low occupancy.  Measured (2^20 boards):
+// 0.089 ms per step against 0.112 ms for one-thread-per-board and 0.098 ms for packing once.
+// The variant that also emits observations (step_obs_kernel) does NOT use the pool: with the 840 B/board
+// store stream the CTA barriers serialise store issue and integer work (0.19 ms vs 0.159 ms).
+// ------------------------------------------------------------------------------------------------
+constexpr int POOL_SLOTS = BLOCK + BLOCK / 2;
+constexpr int POOL_FILL_BELOW = BLOCK / 2;     // fill while pool <= this: pool + BLOCK <= POOL_SLOTS always holds
+
+template <class G>
+struct CascadePool {
+    typename G::W b0[POOL_SLOTS], b1[POOL_SLOTS], b2[POOL_SLOTS];
+    double t0[POOL_SLOTS], t1[POOL_SLOTS], t2[POOL_SLOTS], t3[POOL_SLOTS], t4[POOL_SLOTS];
+    uint32_t counts[POOL_SLOTS];   // n_combos [0,16) | depth [16,24) | flags [24,32)
+    uint32_t source[POOL_SLOTS];   // skyfall cursor [0,16) | injected slab exhausted [16]
+    uint64_t owner[POOL_SLOTS];    // board index within the launch
+    int warp_count[BLOCK / 32];
+
+    __device__ __forceinline__ void put(int slot, const CascadeItem<G> &it, uint64_t own)
+    {
+        b0[slot] = it.b.b0;
+        b1[slot] = it.b.b1;
+        b2[slot] = it.b.b2;
+        t0[slot] = it.tally.t0;
+        t1[slot] = it.tally.t1;
+        t2[slot] = it.tally.t2;
+        t3[slot] = it.tally.t3;
+        t4[slot] = it.tally.t4;
+        const uint32_t nc = it.tally.n_combos > 0xFFFF ? 0xFFFFu : (uint32_t)it.tally.n_combos;
+        counts[slot] = nc | (sat255(it.depth) << 16) | ((it.flags & 0xFFu) << 24);
+        source[slot] = (it.cursor > 0xFFFF ? 0xFFFFu : (uint32_t)it.cursor) | ((it.exhausted ? 1u : 0u) << 16);
+        owner[slot] = own;
+    }
+    __device__ __forceinline__ uint64_t get(int slot, CascadeItem<G> &it) const
+    {
+        it.b.b0 = b0[slot];
+        it.b.b1 = b1[slot];
+        it.b.b2 = b2[slot];
+        it.tally.t0 = t0[slot];
+        it.tally.t1 = t1[slot];
+        it.tally.t2 = t2[slot];
+        it.tally.t3 = t3[slot];
+        it.tally.t4 = t4[slot];
+        const uint32_t c = counts[slot], q = source[slot];
+        it.tally.n_combos = (int)(c & 0xFFFFu);
+        it.depth = (int)((c >> 16) & 0xFFu);
+        it.flags = c >> 24;
+        it.cursor = (int)(q & 0xFFFFu);
+        it.exhausted = (q >> 16) & 1u;
+        return owner[slot];
+    }
+    // CTA-wide stable compaction (two __syncthreads; every thread must call it)
+    __device__ __forceinline__ int compact(bool keep, int &total)
+    {
+        const unsigned ballot = __ballot_sync(0xFFFFFFFFu, keep);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane == 0) warp_count[warp] = __popc(ballot);
+        __syncthreads();
+        int base = 0, sum = 0;
+#pragma unroll
+        for (int w = 0; w < BLOCK / 32; w++) {
+            const int c = warp_count[w];
+            if (w < warp) base += c;
+            sum += c;
+        }
+        total = sum;
+        __syncthreads();
+        return base + __popc(ballot & ((1u << lane) - 1u));
+    }
+};
+
+template <class G>
+__global__ void __launch_bounds__(BLOCK, 4) step_pool_kernel(const __grid_constant__ StepKernelArgs a)
+{
+    __shared__ CascadePool<G> pool;
+    typedef typename G::W W;
+    const int tid = threadIdx.x;
+    const int64_t n_tiles = (a.n + BLOCK - 1) / BLOCK;
+    const bool sd = a.p.skyfall_damage != 0;
+    int64_t tile = blockIdx.x;
+    int pool_count = 0;                          // CTA-uniform
+
+    for (;;) {
+        // ---- fill: the convergent part of the step for one fresh tile, when the pool is low
+        const bool fill = tile < n_tiles && pool_count <= POOL_FILL_BELOW;
+        if (!fill && pool_count == 0) break;    // no tiles left (pool_count == 0 <= POOL_FILL_BELOW) and pool drained
+        if (fill) {
+            const int64_t i = tile * BLOCK + tid;
+            const bool valid = i < a.n;
+            State<G> s;
+            CascadeItem<G> it;
+            bool cascading = false;
+            if (valid) {
+                s = StateIO<G>::load(a.state, i);
+                const RngKey key = board_key(a.p, a.env0 + (uint64_t)i);
+                StepPrefix pre;
+                if (a.paths) {
+                    int len = a.path_lens ? a.path_lens[i] : a.path_len;
+                    len = len > 16 * a.path_words ? 16 * a.path_words : len;
+                    pre = path_prefix<G>(s, a.p, a.paths + (size_t)i * a.path_words, len);
+                } else {
+                    int action = -1;
+                    if (a.actions) {
+                        action = a.actions[i];
+                        if (action == PPAD_SAMPLE) action = -1;
+                    }
+                    pre = step_prefix<G>(s, a.p, key, action);
+                }
+                it.init(s.b, pre.flags);         // the cascade works on a copy (game.py:366)
+                if (pre.evaluate) {
+                    W er, ed;
+                    cascading = match_mask<G>(it.b, er, ed) != 0;
+                }
+                if (pre.action == ACT_PASS && a.p.auto_reset) it.flags |= step_auto_reset<G>(s, a.p, key);
+                StateIO<G>::store(a.state, i, s.b, s.meta);
+                if (a.action_out) a.action_out[i] = (uint8_t)pre.action;
+                if (a.final_state) StateIO<G>::store(a.final_state, i, it.b, s.meta);   // planes rewritten after a cascade
+                if (!cascading) {
+                    if (a.reward) a.reward[i] = 0.0;
+                    if (a.info) a.info[i] = it.info();
+                }
+            }
+            int added;
+            const int slot = pool.compact(cascading, added);
+            if (cascading) pool.put(pool_count + slot, it, (uint64_t)i);
+            pool_count += added;
+            tile += gridDim.x;
+            __syncthreads();                      // every put() of the fill is visible
+        }
+
+        // ---- round: one cascade iteration for the top m boards of the pool, on dense warps
+        const int m = pool_count < BLOCK ? pool_count : BLOCK;
+        const int base = pool_count - m;
+        CascadeItem<G> it;
+        uint64_t own = 0;
+        bool again = false;
+        if (tid < m) {
+            own = pool.get(base + tid, it);
+            const RngKey key = board_key(a.p, a.env0 + own);
+            again = cascade_round<G>(it, sd, a.p.cascade_cap, a.p.team,
+                                     a.slab ? a.slab + (size_t)own * a.p.slab_words : nullptr, a.p.n_inj, key, a.p.sky,
+                                     a.combo_log ? a.combo_log + (size_t)own * a.p.log_cap : nullptr, a.p.log_cap);
+            if (!again) {
+                if (a.reward) a.reward[own] = it.reward();
+                if (a.info) a.info[own] = it.info();
+                if (a.final_state) StateIO<G>::store_planes(a.final_state, own, it.b);   // meta: written by the fill
+            }
+        }
+
+        if (m > 0) {                             // CTA-uniform
+            int survivors;
+            const int slot = pool.compact(again, survivors);   // its first barrier: every get() of the round is done
+            if (again) pool.put(base + slot, it, own);
+            pool_count = base + survivors;
+            __syncthreads();
+        }
     }
 }
 
@@ -708,6 +746,7 @@ struct ppad_ctx {
     int device;
     int geom;   // 0 = 5x6, 1 = 6x7, 2 = 4x5
     StepParams base;
+    int sm_count;
 };
 
 #define PPAD_DISPATCH(ctx, EXPR)                            \
@@ -800,6 +839,8 @@ int ppad_create(const ppad_config *cfg, int device, ppad_ctx **out)
                                        (e != cudaSuccess ? cudaGetErrorString(e) : "ordinal out of range") +
                                        " (this library has no CPU path)");
     }
+    ctx->sm_count = 148;
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     *out = ctx;
     return PPAD_OK;
 }
@@ -912,9 +953,18 @@ int ppad_step(const ppad_ctx *ctx, const ppad_step_args *args, void *stream)
     if (a.paths && (a.path_words <= 0 || a.path_len < 0))
         return fail(PPAD_ERR_INVALID, "ppad_step: paths need path_words > 0 and path_len >= 0");
     cudaStream_t st = (cudaStream_t)stream;
-    if (args->obs) PPAD_DISPATCH(ctx, (step_obs_kernel<G><<<grid_for(a.n), BLOCK, 0, st>>>(a)));
-    else PPAD_DISPATCH(ctx, (step_state_kernel<G><<<grid_for(a.n), BLOCK, 0, st>>>(a)));
-    return after_launch(args->obs ? "step_obs_kernel" : "step_state_kernel");
+    if (args->obs) {
+        PPAD_DISPATCH(ctx, (step_obs_kernel<G><<<grid_for(a.n), BLOCK, 0, st>>>(a)));
+        return after_launch("step_obs_kernel");
+    }
+    // persistent: one wave of CTAs, as many as fit
+    int per_sm = 0;
+    PPAD_DISPATCH(ctx, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_pool_kernel<G>, BLOCK, 0)));
+    const int64_t tiles = (a.n + BLOCK - 1) / BLOCK;
+    int64_t grid = (int64_t)ctx->sm_count * (per_sm > 0 ? per_sm : 1);
+    if (grid > tiles) grid = tiles;
+    PPAD_DISPATCH(ctx, (step_pool_kernel<G><<<(unsigned)grid, BLOCK, 0, st>>>(a)));
+    return after_launch("step_pool_kernel");
 }
 
 int ppad_encode_obs(const ppad_ctx *ctx, int64_t n, const void *state, void *obs, int obs_dtype, void *stream)
