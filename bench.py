@@ -193,8 +193,9 @@ def main():
         return env.step(None, eval_moves=True, injected=(slabs[t % N_SLABS], SLAB_ORBS),
                         obs=obs_buf if with_obs else None, step=t, out=out)
 
-    def timed(fn, k0, count):
-        """barrier + sync, `count` steps between CUDA events on the launch stream, sync; max over ranks (ms)."""
+    def timed(fn, k0, count, finish=None):
+        """barrier + sync, `count` steps between CUDA events on the launch stream, sync; max over ranks (ms).
+        finish(): joins side streams into the launch stream before the closing event."""
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -202,6 +203,8 @@ def main():
         e0.record()
         for t in range(k0, k0 + count):
             fn(t)
+        if finish is not None:
+            finish()
         e1.record()
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -227,31 +230,40 @@ def main():
         so_ms.append(timed(lambda tt: one_step(tt, with_obs=False), t, 1))
     so_ms = float(np.median(so_ms))
 
-    # end to end through the public API with HOST buffers: pinned skyfall slab H2D, step, D2H of the result
-    h_slab = torch.empty((n, SLAB_ORBS // 8), dtype=torch.int32).pin_memory()
-    h_slab.copy_(slabs[0].cpu())
-    d_slab = torch.empty_like(slabs[0])
-    h_reward = torch.empty(n, dtype=torch.float64).pin_memory()
-    h_info = torch.empty(n, dtype=torch.int32).pin_memory()
-    h_action = torch.empty(n, dtype=torch.uint8).pin_memory()
-    h_state = torch.empty((n, env.words), dtype=torch.int32).pin_memory()
+    # end to end through the public host-buffer API (BatchedPAD.host_pipe -> ppad_pipe_step): every step copies that
+    # step's skyfall slab from pinned host memory and reads reward, info, action and the packed state back to pinned
+    # host memory; the call returns only when the results are on the host.  The fp32 one-hot obs stays in HBM.
+    pipe = env.host_pipe(slab_orbs=SLAB_ORBS, chunks=2)     # best of 1..8 on this box (profiles/pipe_probe.py)
+    pipe.slab.copy_(slabs[0].cpu())
+    torch.cuda.synchronize()
 
     def e2e_step(t):
-        d_slab.copy_(h_slab, non_blocking=True)
-        env.step(None, eval_moves=True, injected=(d_slab, SLAB_ORBS), obs=obs_buf, step=t, out=out)
-        h_reward.copy_(out.reward, non_blocking=True)
-        h_info.copy_(out.info, non_blocking=True)
-        h_action.copy_(out.action, non_blocking=True)
-        h_state.copy_(env.state, non_blocking=True)
-        torch.cuda.current_stream().synchronize()      # the caller reads the result every step
+        pipe.step(eval_moves=True, obs=obs_buf, step=t, wait=True)
 
     base = 2 + W + K + 10
     for t in range(base, base + 3):
         e2e_step(t)
-    e2e_k = max(5, min(K, 20))
+    e2e_k = max(5, min(K, 50))
     e2e_ms = timed(e2e_step, base + 3, e2e_k)
-    h2d = h_slab.numel() * 4
-    d2h = h_reward.numel() * 8 + h_info.numel() * 4 + h_action.numel() + h_state.numel() * 4
+    h2d = pipe.slab.numel() * 4
+    d2h = pipe.reward.numel() * 8 + pipe.info.numel() * 4 + pipe.action.numel() + pipe.state.numel() * 4
+    # the same with two steps in flight (double-buffered host buffers; results of step t are read while step t + 1
+    # is on the wire) -- reported separately, the headline e2e above is the synchronous call
+    pipe2 = env.host_pipe(slab_orbs=SLAB_ORBS, chunks=2)
+    pipe2.slab.copy_(slabs[1].cpu())
+    pipes = [pipe, pipe2]
+
+    def e2e_async_step(t):
+        p = pipes[t & 1]
+        p.wait()                       # results of step t - 2 (this buffer pair) are on the host
+        _ = p.reward[0].item()         # "read" them
+        p.step(eval_moves=True, obs=obs_buf, step=t, wait=False)
+
+    for t in range(base + 100, base + 104):
+        e2e_async_step(t)
+    e2e_async_ms = timed(e2e_async_step, base + 104, e2e_k, finish=lambda: [p.join() for p in pipes])
+    for p in pipes:
+        p.wait()
 
     # episode stats of the last step, all-gathered over NVLink (tiny; outside the timed region)
     stats = pdist.gather_stats(pdist.local_stats(out.reward, out.info))
@@ -283,9 +295,11 @@ def main():
                            "note": "same kernel without the obs stream; L2 flushed (256 MiB fill) before every step"},
             "e2e": {"value": total * e2e_k / (e2e_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_k,
-                    "note": "BatchedPAD.step with pinned host buffers: skyfall slab H2D; reward, info, action and "
-                            "packed state (the reference's (board, finger) observation) D2H every step; the fp32 "
-                            "one-hot obs stays in HBM for the device-side agent"},
+                    "note": "HostPipe.step (ppad_pipe_step, 2 chunks on 2 streams) with pinned host buffers, synchronous: "
+                            "skyfall slab H2D; reward, info, action and packed state (the reference's (board, finger) "
+                            "observation) D2H every step; the fp32 one-hot obs stays in HBM for the device-side agent",
+                    "two_steps_in_flight": {"value": total * e2e_k / (e2e_async_ms * 1e-3), "unit": "steps/s",
+                                            "ms_per_step": e2e_async_ms / e2e_k}},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "stats_last_step": stats,

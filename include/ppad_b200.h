@@ -151,6 +151,40 @@ typedef struct ppad_step_args {
 } ppad_step_args;
 int ppad_step(const ppad_ctx *ctx, const ppad_step_args *args, void *stream);
 
+/* The same env step for callers whose inputs and results live in HOST memory -- what the reference's callers
+ * have: PAD.step takes a Python value and appends to Python lists (game.py:329-362).  A pipe owns device
+ * scratch and `chunks` streams; ppad_pipe_step cuts the batch into chunks, and chunk k copies its inputs
+ * host -> device, runs the fused step kernel and copies its results device -> host on its own stream, so the
+ * copies of neighbouring chunks overlap the kernels and each other (PCIe is full duplex).
+ * ppad_pipe_step returns after enqueueing; ppad_pipe_wait blocks until the last enqueued step is complete;
+ * ppad_pipe_join makes `stream` wait for it instead.  Host buffers should be pinned.  The env state and the
+ * observation stay in HBM (state_out_host, if given, receives a copy of the packed state records: the
+ * reference's (board, finger) observation). */
+typedef struct ppad_pipe ppad_pipe;
+typedef struct ppad_host_step_args {
+    int64_t n;
+    uint64_t env0;
+    uint32_t step;
+    int32_t eval_moves, auto_reset, max_moves;
+    int32_t skyfall_damage;          /* -1 = cfg.skyfall_damage */
+    void *state;                     /* DEVICE [n] packed records, in/out */
+    const uint8_t *actions_host;     /* [n] or NULL (= in-kernel random policy) */
+    const uint32_t *slab_host;       /* [n, slab_words] injected skyfall or NULL */
+    int32_t slab_words, n_inj;
+    uint8_t *action_out_host;        /* [n] or NULL */
+    double *reward_host;             /* [n] or NULL */
+    uint32_t *info_host;             /* [n] or NULL */
+    void *state_out_host;            /* [n] packed records or NULL */
+    void *obs;                       /* DEVICE [n, rows, cols, 7] or NULL */
+    int32_t obs_dtype;
+} ppad_host_step_args;
+int ppad_pipe_create(const ppad_ctx *ctx, int64_t n_max, int32_t slab_words_max, int32_t chunks, ppad_pipe **out);
+void ppad_pipe_destroy(ppad_pipe *pipe);
+/* `after_stream`: work already queued there (e.g. ppad_reset) is ordered before the chunks */
+int ppad_pipe_step(ppad_pipe *pipe, const ppad_host_step_args *args, void *after_stream);
+int ppad_pipe_wait(ppad_pipe *pipe);
+int ppad_pipe_join(ppad_pipe *pipe, void *stream);
+
 /* Agent01.board_finger_to_state (agent01.py:254-273): state -> [n, rows, cols, 7] NHWC */
 int ppad_encode_obs(const ppad_ctx *ctx, int64_t n, const void *state, void *obs, int obs_dtype, void *stream);
 

@@ -35,12 +35,23 @@ class StepArgs(C.Structure):
                 ("paths", C.c_void_p), ("path_lens", C.c_void_p), ("path_words", C.c_int32), ("path_len", C.c_int32)]
 
 
+class HostStepArgs(C.Structure):
+    """struct ppad_host_step_args"""
+    _fields_ = [("n", C.c_int64), ("env0", C.c_uint64), ("step", C.c_uint32), ("eval_moves", C.c_int32),
+                ("auto_reset", C.c_int32), ("max_moves", C.c_int32), ("skyfall_damage", C.c_int32),
+                ("state", C.c_void_p), ("actions_host", C.c_void_p), ("slab_host", C.c_void_p),
+                ("slab_words", C.c_int32), ("n_inj", C.c_int32), ("action_out_host", C.c_void_p),
+                ("reward_host", C.c_void_p), ("info_host", C.c_void_p), ("state_out_host", C.c_void_p),
+                ("obs", C.c_void_p), ("obs_dtype", C.c_int32)]
+
+
 # every symbol include/ppad_b200.h declares (tests/test_cabi_symbols.py checks the header against this)
 SYMBOLS = ["ppad_default_config", "ppad_create", "ppad_destroy", "ppad_abi_version", "ppad_strerror",
            "ppad_last_error", "ppad_state_bytes", "ppad_launch_count", "ppad_pack", "ppad_unpack", "ppad_reset",
            "ppad_step", "ppad_encode_obs", "ppad_cancel", "ppad_legal_mask", "ppad_sample_actions", "ppad_drop",
            "ppad_fill", "ppad_damage", "ppad_select_actions", "ppad_discount", "ppad_replay_push",
-           "ppad_replay_sample", "ppad_permute"]
+           "ppad_replay_sample", "ppad_permute", "ppad_pipe_create", "ppad_pipe_destroy", "ppad_pipe_step",
+           "ppad_pipe_wait", "ppad_pipe_join"]
 
 
 class PPADError(RuntimeError):
@@ -86,6 +97,12 @@ def lib():
     L.ppad_fill.argtypes = [vp, i64, u64, u32, i32, i32, vp, i32, i32, vp, vp, vp, vp]
     L.ppad_damage.argtypes = [vp, i64, vp, i32, vp, vp, vp]
     L.ppad_permute.argtypes = [vp, i64, vp, vp, vp]
+    L.ppad_pipe_create.argtypes = [vp, i64, i32, i32, C.POINTER(vp)]
+    L.ppad_pipe_destroy.argtypes = [vp]
+    L.ppad_pipe_destroy.restype = None
+    L.ppad_pipe_step.argtypes = [vp, C.POINTER(HostStepArgs), vp]
+    L.ppad_pipe_wait.argtypes = [vp]
+    L.ppad_pipe_join.argtypes = [vp, vp]
     L.ppad_select_actions.argtypes = [vp, i64, u64, u32, vp, vp, i32, C.c_float, C.c_float, i32, vp, vp]
     L.ppad_discount.argtypes = [vp, i64, i32, vp, vp, C.c_double, i32, i32, vp]
     L.ppad_replay_push.argtypes = [vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]

@@ -747,6 +747,7 @@ struct ppad_ctx {
     int geom;   // 0 = 5x6, 1 = 6x7, 2 = 4x5
     StepParams base;
     int sm_count;
+    int pool_ctas_per_sm;   // resident CTAs of the persistent step_pool_kernel
 };
 
 #define PPAD_DISPATCH(ctx, EXPR)                            \
@@ -841,6 +842,10 @@ int ppad_create(const ppad_config *cfg, int device, ppad_ctx **out)
     }
     ctx->sm_count = 148;
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaSetDevice(device);
+    ctx->pool_ctas_per_sm = 0;
+    PPAD_DISPATCH(ctx, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->pool_ctas_per_sm, step_pool_kernel<G>, BLOCK, 0)));
+    if (ctx->pool_ctas_per_sm <= 0) ctx->pool_ctas_per_sm = 1;
     *out = ctx;
     return PPAD_OK;
 }
@@ -910,11 +915,8 @@ int ppad_reset(const ppad_ctx *ctx, int64_t n, uint64_t env0, uint32_t step, con
     return after_launch("reset_kernel");
 }
 
-int ppad_step(const ppad_ctx *ctx, const ppad_step_args *args, void *stream)
+static int launch_step(const ppad_ctx *ctx, const ppad_step_args *args, cudaStream_t st)
 {
-    if (!args) return fail(PPAD_ERR_INVALID, "ppad_step: null args");
-    if (int r = enter(ctx, args->n)) return r;
-    if (args->n == 0) return PPAD_OK;
     if (!args->state) return fail(PPAD_ERR_INVALID, "ppad_step: null state");
     if (args->slab && (args->slab_words <= 0 || args->n_inj < 0 || args->n_inj > args->slab_words * 8))
         return fail(PPAD_ERR_INVALID, "ppad_step: need 0 <= n_inj <= 8 * slab_words");
@@ -952,19 +954,179 @@ int ppad_step(const ppad_ctx *ctx, const ppad_step_args *args, void *stream)
     a.path_len = args->path_len;
     if (a.paths && (a.path_words <= 0 || a.path_len < 0))
         return fail(PPAD_ERR_INVALID, "ppad_step: paths need path_words > 0 and path_len >= 0");
-    cudaStream_t st = (cudaStream_t)stream;
     if (args->obs) {
         PPAD_DISPATCH(ctx, (step_obs_kernel<G><<<grid_for(a.n), BLOCK, 0, st>>>(a)));
         return after_launch("step_obs_kernel");
     }
     // persistent: one wave of CTAs, as many as fit
-    int per_sm = 0;
-    PPAD_DISPATCH(ctx, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_pool_kernel<G>, BLOCK, 0)));
     const int64_t tiles = (a.n + BLOCK - 1) / BLOCK;
-    int64_t grid = (int64_t)ctx->sm_count * (per_sm > 0 ? per_sm : 1);
+    int64_t grid = (int64_t)ctx->sm_count * ctx->pool_ctas_per_sm;
     if (grid > tiles) grid = tiles;
     PPAD_DISPATCH(ctx, (step_pool_kernel<G><<<(unsigned)grid, BLOCK, 0, st>>>(a)));
     return after_launch("step_pool_kernel");
+}
+
+int ppad_step(const ppad_ctx *ctx, const ppad_step_args *args, void *stream)
+{
+    if (!args) return fail(PPAD_ERR_INVALID, "ppad_step: null args");
+    if (int r = enter(ctx, args->n)) return r;
+    if (args->n == 0) return PPAD_OK;
+    return launch_step(ctx, args, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-buffer pipeline: the env step for callers whose inputs and results live in HOST memory
+// ------------------------------------------------------------------------------------------------
+struct ppad_pipe {
+    const ppad_ctx *ctx;
+    int64_t n_max, chunk;
+    int chunks, slab_words_max;
+    cudaStream_t streams[16];
+    cudaEvent_t done[16], fork;
+    uint32_t *d_slab;
+    uint8_t *d_actions, *d_action_out;
+    double *d_reward;
+    uint32_t *d_info;
+};
+
+int ppad_pipe_create(const ppad_ctx *ctx, int64_t n_max, int32_t slab_words_max, int32_t chunks, ppad_pipe **out)
+{
+    if (!out) return fail(PPAD_ERR_INVALID, "ppad_pipe_create: null out");
+    *out = nullptr;
+    if (int r = enter(ctx, n_max)) return r;
+    if (chunks <= 0) chunks = 4;
+    if (chunks > 16) chunks = 16;
+    if (slab_words_max < 0) return fail(PPAD_ERR_INVALID, "ppad_pipe_create: slab_words_max < 0");
+    ppad_pipe *p = new (std::nothrow) ppad_pipe;
+    if (!p) return fail(PPAD_ERR_INVALID, "out of memory");
+    std::memset(p, 0, sizeof(*p));
+    p->ctx = ctx;
+    p->n_max = n_max;
+    p->chunks = chunks;
+    p->slab_words_max = slab_words_max;
+    p->chunk = ((n_max + chunks - 1) / chunks + BLOCK - 1) / BLOCK * BLOCK;   // CTA-aligned: obs stays 16-byte aligned
+    if (p->chunk == 0) p->chunk = BLOCK;
+    cudaError_t e = cudaSuccess;
+    for (int k = 0; k < chunks && e == cudaSuccess; k++) {
+        e = cudaStreamCreateWithFlags(&p->streams[k], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->done[k], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->fork, cudaEventDisableTiming);
+    const size_t n = (size_t)(n_max > 0 ? n_max : 1);
+    if (e == cudaSuccess && slab_words_max > 0) e = cudaMalloc(&p->d_slab, n * slab_words_max * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_actions, n);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_action_out, n);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_reward, n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_info, n * sizeof(uint32_t));
+    if (e != cudaSuccess) {
+        ppad_pipe_destroy(p);
+        return cuda_check(e, "ppad_pipe_create");
+    }
+    *out = p;
+    return PPAD_OK;
+}
+
+void ppad_pipe_destroy(ppad_pipe *p)
+{
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    for (int k = 0; k < p->chunks; k++) {
+        if (p->streams[k]) {
+            cudaStreamSynchronize(p->streams[k]);
+            cudaStreamDestroy(p->streams[k]);
+        }
+        if (p->done[k]) cudaEventDestroy(p->done[k]);
+    }
+    if (p->fork) cudaEventDestroy(p->fork);
+    cudaFree(p->d_slab);
+    cudaFree(p->d_actions);
+    cudaFree(p->d_action_out);
+    cudaFree(p->d_reward);
+    cudaFree(p->d_info);
+    delete p;
+}
+
+int ppad_pipe_step(ppad_pipe *p, const ppad_host_step_args *h, void *after_stream)
+{
+    if (!p || !h) return fail(PPAD_ERR_INVALID, "ppad_pipe_step: null argument");
+    const ppad_ctx *ctx = p->ctx;
+    if (int r = enter(ctx, h->n)) return r;
+    if (h->n > p->n_max) return fail(PPAD_ERR_INVALID, "ppad_pipe_step: n exceeds the pipe's n_max");
+    if (h->slab_host && (h->slab_words <= 0 || h->slab_words > p->slab_words_max))
+        return fail(PPAD_ERR_INVALID, "ppad_pipe_step: slab_words exceeds the pipe's slab_words_max");
+    if (!h->state) return fail(PPAD_ERR_INVALID, "ppad_pipe_step: null state");
+    if (h->n == 0) return PPAD_OK;
+    const size_t rec = (size_t)ppad_state_bytes(ctx->cfg.rows, ctx->cfg.cols);
+    const size_t obs_elem = h->obs_dtype == PPAD_OBS_F32 ? 4 : 1;
+    const size_t obs_row = (size_t)ctx->cfg.rows * ctx->cfg.cols * 7 * obs_elem;
+    // chunk streams start after whatever the caller has queued on after_stream (e.g. the reset)
+    cudaError_t e = cudaEventRecord(p->fork, (cudaStream_t)after_stream);
+    for (int k = 0; k < p->chunks && e == cudaSuccess; k++) {
+        const int64_t lo = (int64_t)k * p->chunk;
+        if (lo >= h->n) break;
+        const int64_t cnt = h->n - lo < p->chunk ? h->n - lo : p->chunk;
+        cudaStream_t st = p->streams[k];
+        e = cudaStreamWaitEvent(st, p->fork, 0);
+        if (e != cudaSuccess) break;
+        ppad_step_args a;
+        std::memset(&a, 0, sizeof(a));
+        a.n = cnt;
+        a.env0 = h->env0 + (uint64_t)lo;
+        a.step = h->step;
+        a.eval_moves = h->eval_moves;
+        a.auto_reset = h->auto_reset;
+        a.max_moves = h->max_moves;
+        a.skyfall_damage = h->skyfall_damage;
+        a.state = (char *)h->state + (size_t)lo * rec;
+        if (h->actions_host) {
+            e = cudaMemcpyAsync(p->d_actions + lo, h->actions_host + lo, (size_t)cnt, cudaMemcpyHostToDevice, st);
+            a.actions = p->d_actions + lo;
+        }
+        if (e == cudaSuccess && h->slab_host) {
+            const size_t w = (size_t)h->slab_words;
+            e = cudaMemcpyAsync(p->d_slab + (size_t)lo * w, h->slab_host + (size_t)lo * w, (size_t)cnt * w * 4,
+                                cudaMemcpyHostToDevice, st);
+            a.slab = p->d_slab + (size_t)lo * w;
+            a.slab_words = h->slab_words;
+            a.n_inj = h->n_inj;
+        }
+        if (e != cudaSuccess) break;
+        a.action_out = h->action_out_host ? p->d_action_out + lo : nullptr;
+        a.reward = h->reward_host ? p->d_reward + lo : nullptr;
+        a.info = h->info_host ? p->d_info + lo : nullptr;
+        if (h->obs) {
+            a.obs = (char *)h->obs + (size_t)lo * obs_row;
+            a.obs_dtype = h->obs_dtype;
+        }
+        if (int r = launch_step(ctx, &a, st)) return r;
+        if (h->reward_host)
+            e = cudaMemcpyAsync(h->reward_host + lo, p->d_reward + lo, (size_t)cnt * 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && h->info_host)
+            e = cudaMemcpyAsync(h->info_host + lo, p->d_info + lo, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && h->action_out_host)
+            e = cudaMemcpyAsync(h->action_out_host + lo, p->d_action_out + lo, (size_t)cnt, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && h->state_out_host)
+            e = cudaMemcpyAsync((char *)h->state_out_host + (size_t)lo * rec, (char *)h->state + (size_t)lo * rec,
+                                (size_t)cnt * rec, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaEventRecord(p->done[k], st);
+    }
+    return cuda_check(e, "ppad_pipe_step");
+}
+
+int ppad_pipe_wait(ppad_pipe *p)
+{
+    if (!p) return fail(PPAD_ERR_INVALID, "ppad_pipe_wait: null pipe");
+    cudaError_t e = cudaSuccess;
+    for (int k = 0; k < p->chunks && e == cudaSuccess; k++) e = cudaEventSynchronize(p->done[k]);
+    return cuda_check(e, "ppad_pipe_wait");
+}
+
+int ppad_pipe_join(ppad_pipe *p, void *stream)
+{
+    if (!p) return fail(PPAD_ERR_INVALID, "ppad_pipe_join: null pipe");
+    cudaError_t e = cudaSuccess;
+    for (int k = 0; k < p->chunks && e == cudaSuccess; k++) e = cudaStreamWaitEvent((cudaStream_t)stream, p->done[k], 0);
+    return cuda_check(e, "ppad_pipe_join");
 }
 
 int ppad_encode_obs(const ppad_ctx *ctx, int64_t n, const void *state, void *obs, int obs_dtype, void *stream)

@@ -372,3 +372,39 @@ def test_smart_data_and_lookahead(pb):
     res = two_step_lookahead(env, q_fn=q_fn, policy='boltzmann', beta=1e-2, max_lookahead_len=6)
     roam = res["roam_actions"].cpu().numpy()
     assert ((roam <= 4) | (roam == 255)).all() and (roam[:, :, :4] != 255).any()
+
+
+@pytest.mark.parametrize("rows,cols,n", [(5, 6, 100_000 + 37), (6, 7, 33_333), (5, 6, 200)])
+def test_host_pipe_equals_device_step(pb, rows, cols, n):
+    """ppad_pipe_step (host buffers, chunked over streams) == ppad_step (device buffers), incl. a ragged tail"""
+    rng = np.random.default_rng(n)
+    ref = pb.BatchedPAD(n, rows, cols, seed=17, env0=3)
+    ref.reset(step=0)
+    env = pb.BatchedPAD(n, rows, cols, seed=17, env0=3)
+    env.state.copy_(ref.state)
+    pipe = env.host_pipe(slab_orbs=32, chunks=5)
+    obs = torch.zeros((n, rows, cols, 7), dtype=torch.float32, device=env.device)
+    for t in range(1, 6):
+        inj = rng.integers(0, 6, size=(n, 32)).astype(np.uint8)
+        acts = rng.integers(0, 5, size=n).astype(np.uint8)
+        pipe.slab.copy_(torch.from_numpy(pb.layout.pack_slab(inj).view(np.int32)))
+        pipe.actions.copy_(torch.from_numpy(acts))
+        use_actions = t % 2 == 0
+        pipe.step(use_actions=use_actions, eval_moves=True, auto_reset=True, max_moves=3, obs=obs, step=t)
+        want = ref.step(acts if use_actions else None, eval_moves=True, auto_reset=True, max_moves=3, injected=inj,
+                        obs='f32', step=t)
+        assert torch.equal(env.state, ref.state) and torch.equal(pipe.state, ref.state.cpu())
+        assert torch.equal(pipe.reward, want.reward.cpu()) and torch.equal(pipe.info, want.info.cpu())
+        assert torch.equal(pipe.action, want.action.cpu()) and torch.equal(obs, want.obs)
+    # two steps in flight on two pipes, then join
+    pipe2 = env.host_pipe(slab_orbs=32, chunks=3)
+    pipe2.slab.copy_(pipe.slab)
+    pipe.step(eval_moves=True, step=10, wait=False)
+    pipe2.step(eval_moves=True, step=11, wait=False)
+    pipe.wait(), pipe2.wait()
+    inj = rng.integers(0, 6, size=(n, 32)).astype(np.uint8)   # unused draw keeps the rng aligned with nothing; slabs reused
+    w10 = ref.step(None, eval_moves=True, injected=(pipe.slab.to(ref.device), 32), step=10)
+    r10 = w10.reward.clone()
+    w11 = ref.step(None, eval_moves=True, injected=(pipe.slab.to(ref.device), 32), step=11)
+    assert torch.equal(pipe.reward, r10.cpu()) and torch.equal(pipe2.reward, w11.reward.cpu())
+    assert torch.equal(env.state, ref.state)
