@@ -290,8 +290,11 @@ __global__ void __launch_bounds__(BLOCK) step_obs_kernel(const __grid_constant__
 // Deep boards simply stay in the pool while fresh tiles keep streaming in, so every round has (nearly) a
 // full complement of lanes; only the final drain of each CTA runs at low occupancy.  Measured (2^20 boards):
 // 0.089 ms per step against 0.112 ms for one-thread-per-board and 0.098 ms for packing once.
-// The variant that also emits observations (step_obs_kernel) does NOT use the pool: with the 840 B/board
-// store stream the CTA barriers serialise store issue and integer work (0.19 ms vs 0.159 ms).
+// The variant that also emits observations (step_obs_kernel) does NOT use a pool.  Its store stream keeps the
+// SM's memory-instruction queue (MIO) backed up with STG.128; a cascade that lives purely in registers and
+// ALU instructions overlaps that for free, but one that parks boards in shared memory queues its LDS/STS
+// behind the stores.  Measured with fp32 obs: 0.159 ms one thread per board, 0.19 ms with this CTA pool,
+// 0.21 ms with a barrier-free per-warp pool (which ties the CTA pool at 0.090 ms without obs).
 // ------------------------------------------------------------------------------------------------
 constexpr int POOL_SLOTS = BLOCK + BLOCK / 2;
 constexpr int POOL_FILL_BELOW = BLOCK / 2;     // fill while pool <= this: pool + BLOCK <= POOL_SLOTS always holds
