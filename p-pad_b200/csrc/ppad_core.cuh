@@ -14,7 +14,7 @@
 //
 // The functions are __host__ __device__ so that tests/hostcore/ can compile the very same code
 // with g++ and fuzz it against the CPU oracle without a GPU.  That host build is test
-// infrastructure only: the shipped library (ppad_capi.cu) contains device code only and has no
+// infrastructure only: the shipped library (ppad_kernels.cu) contains device code only and has no
 // CPU path.
 #pragma once
 #include <stdint.h>
