@@ -43,22 +43,16 @@ class PAD:
                  finger=None,
                  seed=None,
                  device=None):
-        # game.py:54-68, same messages
-        if abs(sum(skyfall) - 1) > 1e-4:
-            raise Exception('ERROR: Skyfall rates should add up to 1!')
-        for prob in skyfall:
-            if prob < 0:
-                raise Exception('ERROR: Skyfall rates should be a positive number!')
-        for prob in skyfall_locked:
-            if prob < 0 or prob > 1:
-                raise Exception('ERROR: Locked orb probability is between 0 and 1!')
-        for prob in skyfall_enhanced:
-            if prob < 0 or prob > 1:
-                raise Exception('ERROR: Enhanced orb probability is between 0 and 1!')
-        if dim_col < 0 or dim_row < 0:
-            raise Exception('ERROR: Board dimensions should be positive integers!')
-        if dim_col * dim_row < 13:
-            raise Exception('ERROR: The board should allow at least 13 orbs. Please increase board size!')
+        # the argument checks of game.py:54-68, with the reference's messages
+        def require(ok, message):
+            if not ok:
+                raise Exception('ERROR: ' + message)
+        require(abs(sum(skyfall) - 1) <= 1e-4, 'Skyfall rates should add up to 1!')
+        require(all(p >= 0 for p in skyfall), 'Skyfall rates should be a positive number!')
+        require(all(0 <= p <= 1 for p in skyfall_locked), 'Locked orb probability is between 0 and 1!')
+        require(all(0 <= p <= 1 for p in skyfall_enhanced), 'Enhanced orb probability is between 0 and 1!')
+        require(dim_col >= 0 and dim_row >= 0, 'Board dimensions should be positive integers!')
+        require(dim_col * dim_row >= 13, 'The board should allow at least 13 orbs. Please increase board size!')
 
         self.dim_row = dim_row
         self.dim_col = dim_col
@@ -211,10 +205,15 @@ class PAD:
             self.finger = np.copy(finger)
         self.action_space.finger = self.finger
 
-        self.observations.append((np.copy(self.board), np.copy(self.finger)))
-        self.boards.append(self.observations[-1][0])
-        self.fingers.append(self.observations[-1][1])
+        self._record_observation()
         return self.state()
+
+    def _record_observation(self):
+        """append copies of (board, finger); boards[-1] / fingers[-1] alias the tuple's members like the reference's"""
+        snapshot = (self.board.copy(), self.finger.copy())
+        self.observations.append(snapshot)
+        self.boards.append(snapshot[0])
+        self.fingers.append(snapshot[1])
 
     def state(self):
         return self.boards[-1], self.fingers[-1]
@@ -241,9 +240,7 @@ class PAD:
                 raise ValueError('Invalid move, you cannot move off the board!\n'
                                  'Finger = {}, action = {}'.format(self.finger, action))
         if action != 'pass':
-            self.observations.append((np.copy(self.board), np.copy(self.finger)))
-            self.boards.append(self.observations[-1][0])
-            self.fingers.append(self.observations[-1][1])
+            self._record_observation()     # a pass records action and reward only (game.py:357-362)
         self.actions.append(action)
         self.rewards.append(reward)
 
@@ -272,18 +269,10 @@ class PAD:
         if n >= len(self.boards):
             print('ERROR: Cannot backtrack more than the length of the trajectory.')
             exit()
-        for _ in range(n):
-            self.observations.pop()
-            self.boards.pop()
-            self.fingers.pop()
-            self.actions.pop()
-            self.rewards.pop()
-        self.board = np.copy(self.boards[-1])
-        self.finger = np.copy(self.fingers[-1])
-        if len(self.actions) > 0:
-            self.action_space.previous_action = self.actions[-1]
-        else:
-            self.action_space.previous_action = 'pass'
+        for record in (self.observations, self.boards, self.fingers, self.actions, self.rewards):
+            del record[len(record) - n:]
+        self.board, self.finger = self.boards[-1].copy(), self.fingers[-1].copy()
+        self.action_space.previous_action = self.actions[-1] if self.actions else 'pass'
         self.action_space.finger = self.finger
 
     # ------------------------------------------------------------------ game.py:429-456
