@@ -151,6 +151,16 @@ typedef struct ppad_step_args {
 } ppad_step_args;
 int ppad_step(const ppad_ctx *ctx, const ppad_step_args *args, void *stream);
 
+/* `steps` consecutive env steps of the in-kernel random policy in ONE launch (the loop of
+ * visualize_episode.py:28-33 / model_simulation, simulation.py:34-68, for a random policy): boards stay in
+ * registers between steps.  Equivalent to ppad_step(actions = NULL, step = step0 + t, eval_moves, auto_reset,
+ * max_moves) for t = 0..steps-1 without injected skyfall or observation; per board it reports the sum of the
+ * rewards (float64, added in step order), the number of finished episodes, the number of combos and the OR of
+ * the flags bytes.  Outputs may be NULL. */
+int ppad_rollout(const ppad_ctx *ctx, int64_t n, uint64_t env0, uint32_t step0, int32_t steps, int32_t eval_moves,
+                 int32_t auto_reset, int32_t max_moves, void *state, double *reward_sum, uint32_t *episodes,
+                 uint32_t *combos_sum, uint8_t *flags_or, void *stream);
+
 /* The same env step for callers whose inputs and results live in HOST memory -- what the reference's callers
  * have: PAD.step takes a Python value and appends to Python lists (game.py:329-362).  A pipe owns device
  * scratch and `chunks` streams; ppad_pipe_step cuts the batch into chunks, and chunk k copies its inputs

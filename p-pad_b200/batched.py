@@ -229,6 +229,23 @@ class BatchedPAD:
         packed = torch.where(packed >= 2 ** 31, packed - 2 ** 32, packed).to(torch.int32).contiguous()
         return packed, length
 
+    def rollout(self, steps, eval_moves=False, auto_reset=True, max_moves=50, step=None):
+        """`steps` env steps of the in-kernel random policy in ONE launch (ppad_rollout): equals that many
+        step(None, ...) calls.  Returns SimpleNamespace(reward_sum float64 [n], episodes int32 [n],
+        combos_sum int32 [n], flags_or uint8 [n]); step_index advances by `steps`."""
+        step0 = self.step_index if step is None else int(step)
+        self.step_index = step0 + int(steps)
+        out = SimpleNamespace(reward_sum=torch.empty(self.n, dtype=torch.float64, device=self.device),
+                              episodes=torch.empty(self.n, dtype=torch.int32, device=self.device),
+                              combos_sum=torch.empty(self.n, dtype=torch.int32, device=self.device),
+                              flags_or=torch.empty(self.n, dtype=torch.uint8, device=self.device))
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ppad_rollout(self._ctx, self.n, self.env0, step0 & 0xFFFFFFFF, int(steps),
+                                              int(bool(eval_moves)), int(bool(auto_reset)), int(max_moves),
+                                              _ptr(self.state), _ptr(out.reward_sum), _ptr(out.episodes),
+                                              _ptr(out.combos_sum), _ptr(out.flags_or), self._stream()))
+        return out
+
     def calculate_reward(self, injected=None, want_final=False, log_cap=0, step=None, skyfall_damage=None):
         """PAD.calculate_reward (game.py:364-405) of every board, on a copy: the state is not modified."""
         acts = torch.full((self.n,), _cabi.PASS, dtype=torch.uint8, device=self.device)

@@ -758,9 +758,10 @@ PPAD_HD RngKey board_key(const StepParams &p, uint64_t env)
 template <class G>
 PPAD_HD StepOut step_board(bool live, State<G> &s, Board<G> &final_board, const StepParams &p, uint64_t env,
                            int action_in, const uint32_t *slab, uint16_t *log, const uint32_t *path = nullptr,
-                           int path_len = 0)
+                           int path_len = 0, uint32_t step_offset = 0)
 {
-    const RngKey key = board_key(p, env);
+    RngKey key = board_key(p, env);
+    key.step += step_offset;   // fused multi-step rollouts: step index = p.key.step + t
     StepPrefix pre;
     pre.action = 255;
     pre.flags = 0;

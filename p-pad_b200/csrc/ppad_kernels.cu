@@ -276,6 +276,50 @@ __global__ void __launch_bounds__(BLOCK) step_obs_kernel(const __grid_constant__
     }
 }
 
+// T consecutive steps of the in-kernel random policy in one launch: the board stays in registers between
+// steps, only the final state and per-board totals are written.  Equals T calls of ppad_step(actions = NULL,
+// step = step0 + t) without injected skyfall / observation (tests/test_gpu_dropin.py::test_fused_rollout).
+struct RolloutArgs {
+    StepParams p;
+    int64_t n;
+    uint64_t env0;
+    int32_t steps;
+    void *state;
+    double *reward_sum;
+    uint32_t *episodes;
+    uint32_t *combos_sum;
+    uint8_t *flags_or;
+};
+
+template <class G>
+__global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ RolloutArgs a)
+{
+    const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    const bool valid = i < a.n;
+    State<G> s;
+    s.b.b0 = s.b.b1 = s.b.b2 = 0;
+    s.meta = 0;
+    if (valid) s = StateIO<G>::load(a.state, i);
+    double reward_sum = 0.0;
+    uint32_t episodes = 0, combos = 0, flags = 0;
+    for (int t = 0; t < a.steps; t++) {          // every lane runs every step: the cascade loop is warp-uniform
+        Board<G> fin;
+        const StepOut o = step_board<G>(valid, s, fin, a.p, a.env0 + (uint64_t)i, -1, nullptr, nullptr, nullptr, 0,
+                                        (uint32_t)t);
+        reward_sum = ppad::dadd(reward_sum, o.reward);
+        episodes += (o.info >> 31) & 1u;         // FLAG_EPISODE_DONE
+        combos += o.info & 0xFFu;
+        flags |= o.info >> 24;
+    }
+    if (valid) {
+        StateIO<G>::store(a.state, i, s.b, s.meta);
+        if (a.reward_sum) a.reward_sum[i] = reward_sum;
+        if (a.episodes) a.episodes[i] = episodes;
+        if (a.combos_sum) a.combos_sum[i] = combos;
+        if (a.flags_or) a.flags_or[i] = (uint8_t)flags;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Persistent step kernel with a recirculating cascade pool.
 //
@@ -975,6 +1019,32 @@ int ppad_step(const ppad_ctx *ctx, const ppad_step_args *args, void *stream)
     if (int r = enter(ctx, args->n)) return r;
     if (args->n == 0) return PPAD_OK;
     return launch_step(ctx, args, (cudaStream_t)stream);
+}
+
+int ppad_rollout(const ppad_ctx *ctx, int64_t n, uint64_t env0, uint32_t step0, int32_t steps, int32_t eval_moves,
+                 int32_t auto_reset, int32_t max_moves, void *state, double *reward_sum, uint32_t *episodes,
+                 uint32_t *combos_sum, uint8_t *flags_or, void *stream)
+{
+    if (int r = enter(ctx, n)) return r;
+    if (n == 0 || steps == 0) return PPAD_OK;
+    if (!state || steps < 0) return fail(PPAD_ERR_INVALID, "ppad_rollout: bad argument");
+    RolloutArgs a;
+    a.p = ctx->base;
+    a.p.key.step = step0;
+    a.p.eval_moves = eval_moves;
+    a.p.auto_reset = auto_reset;
+    a.p.max_moves = max_moves;
+    a.p.n_inj = -1;
+    a.n = n;
+    a.env0 = env0;
+    a.steps = steps;
+    a.state = state;
+    a.reward_sum = reward_sum;
+    a.episodes = episodes;
+    a.combos_sum = combos_sum;
+    a.flags_or = flags_or;
+    PPAD_DISPATCH(ctx, (rollout_kernel<G><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(a)));
+    return after_launch("rollout_kernel");
 }
 
 // ------------------------------------------------------------------------------------------------

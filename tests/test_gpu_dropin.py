@@ -408,3 +408,30 @@ def test_host_pipe_equals_device_step(pb, rows, cols, n):
     w11 = ref.step(None, eval_moves=True, injected=(pipe.slab.to(ref.device), 32), step=11)
     assert torch.equal(pipe.reward, r10.cpu()) and torch.equal(pipe2.reward, w11.reward.cpu())
     assert torch.equal(env.state, ref.state)
+
+
+@pytest.mark.parametrize("rows,cols", [(5, 6), (6, 7)])
+def test_fused_rollout_equals_sequential_steps(pb, rows, cols):
+    n, T = 30_000 + 5, 23
+    a = pb.BatchedPAD(n, rows, cols, seed=41, env0=77)
+    a.reset(step=0)
+    b = pb.BatchedPAD(n, rows, cols, seed=41, env0=77)
+    b.state.copy_(a.state)
+    for eval_moves in (False, True):
+        step0 = a.step_index
+        rs = torch.zeros(n, dtype=torch.float64, device=a.device)
+        ep = torch.zeros(n, dtype=torch.int64, device=a.device)
+        cs = torch.zeros(n, dtype=torch.int64, device=a.device)
+        fl = torch.zeros(n, dtype=torch.int64, device=a.device)
+        for t in range(T):
+            o = a.step(None, eval_moves=eval_moves, auto_reset=True, max_moves=6)
+            combos, depth, consumed, flags = a.split_info(o.info)
+            rs += o.reward
+            ep += (flags >> 7) & 1
+            cs += combos
+            fl |= flags
+        r = b.rollout(T, eval_moves=eval_moves, auto_reset=True, max_moves=6, step=step0)
+        assert torch.equal(a.state, b.state) and b.step_index == a.step_index
+        assert torch.equal(r.reward_sum, rs) and torch.equal(r.episodes.long(), ep)
+        assert torch.equal(r.combos_sum.long(), cs) and torch.equal(r.flags_or.long(), fl)
+        assert int(ep.min()) >= 3
