@@ -752,6 +752,92 @@ PPAD_HD RngKey board_key(const StepParams &p, uint64_t env)
     return key;
 }
 
+#if defined(__CUDACC__)
+// reset for a whole warp (device only; EVERY lane must call it, `need` says whose board is reset).
+// Rejection sampling is geometric (about 35 % of random 5x6 boards are combo-free), so 32 lanes retrying
+// on their own wait for the unluckiest one (~10 attempts).  Because the orb stream is counter based, ANY
+// lane can generate attempt j of ANY board: the lanes are dealt round-robin over the boards that still need
+// a board and try consecutive attempt indices speculatively; per board the accepted attempt with the LOWEST
+// index wins, which is exactly the one the sequential loop of game.py:303-308 would have stopped at -- same
+// board, same number of orbs consumed.  Typically 3-4 warp iterations instead of ~10.
+template <class G>
+__device__ __forceinline__ uint32_t reset_boards_warp(bool need, State<G> &s, const StepParams &p, uint32_t step,
+                                                      uint64_t env, const uint32_t *slab, int n_inj, int finger_in,
+                                                      int *consumed_out)
+{
+    typedef typename G::W W;
+    const unsigned full = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    RngKey my_key = board_key(p, env);
+    my_key.step = step;
+    const int cap = p.reset_cap;
+    const int my_n_inj = slab ? n_inj : -1;
+    int tried = 0;             // attempts of MY board already generated (by anyone)
+    uint32_t flags = 0;
+    int consumed = 0;
+    unsigned needy = __ballot_sync(full, need);
+    while (needy) {
+        const int cnt = __popc(needy);
+        const int k = lane % cnt, h = lane / cnt;                 // I help the k-th needy board with its h-th next attempt
+        const int owner = __fns(needy, 0, k + 1);
+        const unsigned long long env_o = __shfl_sync(full, (unsigned long long)env, owner);
+        const unsigned long long slab_o = __shfl_sync(full, (unsigned long long)(uintptr_t)slab, owner);
+        const int att = __shfl_sync(full, tried, owner) + h;
+        const bool in_range = cap <= 0 || att < cap;
+        Board<G> b;
+        b.b0 = b.b1 = b.b2 = 0;
+        bool ok = false;
+        if (in_range) {
+            OrbSource src;
+            src.init(reinterpret_cast<const uint32_t *>((uintptr_t)slab_o), n_inj, STREAM_RESET);   // init() ignores n_inj without a slab
+            src.cursor = att * G::CELLS;
+            RngKey key_o = board_key(p, env_o);
+            key_o.step = step;
+            refill_all<G>(b, src, key_o, p.sky);
+            W er, ed;
+            ok = match_mask<G>(b, er, ed) == 0;
+        }
+        const bool last = cap > 0 && att == cap - 1;              // the sequential loop gives up here and keeps the board
+        const bool accept = in_range && (ok || last);
+        // among the lanes that accept for the same owner, the lowest lane holds the lowest attempt index
+        const unsigned grp = __match_any_sync(full, accept ? owner : 32 + lane);
+        unsigned winners = __ballot_sync(full, accept && (__ffs(grp) - 1 == lane));
+        bool got = false;
+        while (winners) {
+            const int w = __ffs(winners) - 1;
+            winners &= winners - 1;
+            const int o = __shfl_sync(full, owner, w);
+            const W w0 = __shfl_sync(full, b.b0, w), w1 = __shfl_sync(full, b.b1, w), w2 = __shfl_sync(full, b.b2, w);
+            const int a_w = __shfl_sync(full, att, w);
+            const int ok_w = __shfl_sync(full, (int)ok, w);
+            if (lane == o) {
+                s.b.b0 = w0;
+                s.b.b1 = w1;
+                s.b.b2 = w2;
+                consumed = (a_w + 1) * G::CELLS;
+                if (!ok_w) flags |= FLAG_RESET_CAP;
+                got = true;
+            }
+        }
+        if (need && got) need = false;
+        else if (need) tried += 32 / cnt + ((int)__popc(needy & ((1u << lane) - 1u)) < 32 % cnt ? 1 : 0);
+        needy = __ballot_sync(full, need);
+    }
+    if (consumed > 0) {
+        if (my_n_inj >= 0 && consumed > my_n_inj) flags |= FLAG_SKYFALL_EXHAUSTED;
+        int finger = finger_in;
+        if (finger < 0) {
+            const int r = (int)mulhi32(philox_draw(my_key, STREAM_FINGER, 0), (uint32_t)G::R);
+            const int c = (int)mulhi32(philox_draw(my_key, STREAM_FINGER, 1), (uint32_t)G::C);
+            finger = r * G::C + c;
+        }
+        s.meta = meta_pack(finger, ACT_PASS, 0);
+    }
+    if (consumed_out) *consumed_out = consumed;
+    return flags;
+}
+#endif
+
 // The whole step of one board.  On the GPU EVERY lane of the warp must call this (lanes past the end of the
 // batch pass live = false): the cascade loop is warp-uniform -- it runs while any lane still cascades and
 // the lanes reconverge after every iteration.
@@ -777,7 +863,15 @@ PPAD_HD StepOut step_board(bool live, State<G> &s, Board<G> &final_board, const 
                                          log, p.log_cap);
         warp_converge();
     }
+#if defined(__CUDA_ARCH__)
+    if (p.auto_reset) {   // kernel-uniform
+        const bool need = live && pre.action == ACT_PASS;
+        const uint32_t f = reset_boards_warp<G>(need, s, p, key.step, env, nullptr, -1, -1, nullptr);
+        if (need) it.flags |= FLAG_EPISODE_DONE | f;
+    }
+#else
     if (live && pre.action == ACT_PASS && p.auto_reset) it.flags |= step_auto_reset<G>(s, p, key);
+#endif
     warp_converge();
     final_board = it.b;
     StepOut out;

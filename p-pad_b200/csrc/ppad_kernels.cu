@@ -426,10 +426,15 @@ __global__ void __launch_bounds__(BLOCK, 4) step_pool_kernel(const __grid_consta
             State<G> s;
             CascadeItem<G> it;
             bool cascading = false;
+            StepPrefix pre;
+            pre.action = 255;
+            pre.flags = 0;
+            pre.evaluate = false;
+            s.b.b0 = s.b.b1 = s.b.b2 = 0;
+            s.meta = 0;
             if (valid) {
                 s = StateIO<G>::load(a.state, i);
                 const RngKey key = board_key(a.p, a.env0 + (uint64_t)i);
-                StepPrefix pre;
                 if (a.paths) {
                     int len = a.path_lens ? a.path_lens[i] : a.path_len;
                     len = len > 16 * a.path_words ? 16 * a.path_words : len;
@@ -442,12 +447,18 @@ __global__ void __launch_bounds__(BLOCK, 4) step_pool_kernel(const __grid_consta
                     }
                     pre = step_prefix<G>(s, a.p, key, action);
                 }
-                it.init(s.b, pre.flags);         // the cascade works on a copy (game.py:366)
-                if (pre.evaluate) {
-                    W er, ed;
-                    cascading = match_mask<G>(it.b, er, ed) != 0;
-                }
-                if (pre.action == ACT_PASS && a.p.auto_reset) it.flags |= step_auto_reset<G>(s, a.p, key);
+            }
+            it.init(s.b, pre.flags);             // the cascade works on a copy (game.py:366)
+            if (valid && pre.evaluate) {
+                W er, ed;
+                cascading = match_mask<G>(it.b, er, ed) != 0;
+            }
+            if (a.p.auto_reset) {                 // kernel-uniform; the reset is warp-cooperative
+                const bool need = valid && pre.action == ACT_PASS;
+                const uint32_t f = reset_boards_warp<G>(need, s, a.p, a.p.key.step, a.env0 + (uint64_t)i, nullptr, -1, -1, nullptr);
+                if (need) it.flags |= FLAG_EPISODE_DONE | f;
+            }
+            if (valid) {
                 StateIO<G>::store(a.state, i, s.b, s.meta);
                 if (a.action_out) a.action_out[i] = (uint8_t)pre.action;
                 if (a.final_state) StateIO<G>::store(a.final_state, i, it.b, s.meta);   // planes rewritten after a cascade
@@ -529,20 +540,20 @@ template <class G>
 __global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ ResetKernelArgs a)
 {
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-    if (i >= a.n) return;
-    RngKey key = a.p.key;
-    const uint64_t env = a.env0 + (uint64_t)i;
-    key.env_lo = (uint32_t)env;
-    key.env_hi = (uint32_t)(env >> 32);
-    OrbSource src;
-    src.init(a.slab ? a.slab + (size_t)i * a.p.slab_words : nullptr, a.p.n_inj, STREAM_RESET);
+    const bool valid = i < a.n;                  // every lane takes part: the rejection sampling is warp-cooperative
     int finger = -1;
-    if (a.fingers_in) finger = a.fingers_in[2 * i] * G::C + a.fingers_in[2 * i + 1];
+    if (valid && a.fingers_in) finger = a.fingers_in[2 * i] * G::C + a.fingers_in[2 * i + 1];
     State<G> s;
-    const uint32_t flags = reset_board<G>(s, a.p.reset_cap, src, key, a.p.sky, finger);
+    s.b.b0 = s.b.b1 = s.b.b2 = 0;
+    s.meta = 0;
+    int consumed = 0;
+    const uint32_t flags = reset_boards_warp<G>(valid, s, a.p, a.p.key.step, a.env0 + (uint64_t)i,
+                                                a.slab && valid ? a.slab + (size_t)i * a.p.slab_words : nullptr,
+                                                a.p.n_inj, finger, &consumed);
+    if (!valid) return;
     StateIO<G>::store(a.state, i, s.b, s.meta);
     if (a.flags) a.flags[i] = (uint8_t)flags;
-    if (a.consumed) a.consumed[i] = (uint8_t)sat255(src.cursor);
+    if (a.consumed) a.consumed[i] = (uint8_t)sat255(consumed);
 }
 
 template <class G, class T>

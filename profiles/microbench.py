@@ -39,3 +39,12 @@ for _ in range(2):
     e1.record()
     torch.cuda.synchronize()
     print("%-28s %.4f ms/step" % ("encode_obs f32", e0.elapsed_time(e1) / 200))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(20):
+        env.reset(step=1000 + t)
+    e1.record()
+    torch.cuda.synchronize()
+    print("%-28s %.4f ms/step" % ("reset (Philox)", e0.elapsed_time(e1) / 20))
+    env.reset(step=0)
