@@ -145,6 +145,68 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_rollout(args, rank, local_rank, world):
+    """BASELINE configs[4] (scaled to --boards per GPU): per step synthetic Q-values q ~ N(0, 1) * 1000 (stand-in for
+    Agent01), masking + Boltzmann selection, env step with auto-reset and fp32 one-hot obs, push of (state, action,
+    reward) into the per-GPU replay ring; every 10 steps an NCCL all-gather of the stats vector and of 32 replay rows
+    per GPU.  The Q-value generation (torch.randn) is inside the timed region, like the agent's forward pass would be."""
+    import torch
+    import torch.distributed as dist
+    import ppad_b200
+    from ppad_b200 import dist as pdist
+    from ppad_b200.replay import ReplayBuffer
+    dev = torch.device("cuda", local_rank)
+    n, K, W = args.boards, args.steps, args.warmup
+    env = ppad_b200.BatchedPAD(n, ROWS, COLS, seed=SEED, device=dev, env0=pdist.shard_env0(rank, n))
+    env.reset(step=0)
+    rb = ReplayBuffer(env, 4 * n)
+    obs = env.encode_obs('f32')
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(99 + rank)
+    q = torch.empty((n, 5), device=dev, dtype=torch.float32)
+    out = None
+    before = torch.empty_like(env.state)
+    stats = None
+
+    def one(t):
+        nonlocal out, stats
+        q.normal_(0.0, 1000.0, generator=gen)
+        actions = env.select_actions(q, method='boltzmann', beta=1e-3, epsilon=0.1, max_moves=50)
+        before.copy_(env.state)
+        out = env.step(actions, auto_reset=True, obs=obs, out=out)
+        rb.push(before, out.action, out.reward)
+        if (t + 1) % 10 == 0:
+            stats = pdist.gather_stats(pdist.local_stats(out.reward, out.info))
+            pdist.gather_replay_sample(rb.state[:rb.size], rb.action[:rb.size], rb.reward[:rb.size], 32, generator=gen)
+
+    for t in range(W):
+        one(t)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(W, W + K):
+        one(t)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    if rank == 0:
+        print(json.dumps({
+            "metric": "env_steps_per_sec_policy_rollout", "value": n * world * K / (ms * 1e-3), "unit": "steps/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32 bitboards + f64 reward + f32 obs", "data": "synthetic",
+            "config": {"workload": "configs[4]: Boltzmann-policy rollout, synthetic Q-values, auto-reset, fp32 obs, device "
+                                   "replay ring, NCCL all-gather of stats + 32 replay rows per GPU every 10 steps",
+                       "boards_per_gpu": n, "collectives_per_10_steps": 4}, "stats_last": stats}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -153,6 +215,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--boards", type=int, default=N_LOCAL, help="boards per GPU (default 2^20 = configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="configs1", choices=["configs1", "rollout"],
+                    help="configs1 = the headline bench (default); rollout = BASELINE configs[4]: Boltzmann-policy "
+                         "rollout with fp32 obs, auto-reset, device replay ring and NCCL stats / replay-sample all-gathers")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -175,6 +240,8 @@ def main():
         dist.barrier()
     import ppad_b200
     from ppad_b200 import dist as pdist
+    if args.workload == "rollout":
+        return run_rollout(args, rank, local_rank, world)
     L = ppad_b200._cabi.lib()
     dev = torch.device("cuda", local_rank)
     n = args.boards

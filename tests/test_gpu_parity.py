@@ -329,3 +329,46 @@ def test_launch_counter_counts_kernels(pb):
     env.step(None, eval_moves=True)
     env.encode_obs()
     assert L.ppad_launch_count() - c0 == 3
+
+
+def test_caps_and_exhaustion_flags_on_device(pb):
+    """reset_cap / cascade_cap / injected-slab exhaustion: the device paths (warp-cooperative reset, pooled and
+    per-thread cascades) stop where the oracle stops and raise the same flags"""
+    rows, cols, n = 5, 6, 1000
+    # a one-colour skyfall can never produce a combo-free board: reset gives up at the cap, identically
+    for cap in (1, 3, 7):
+        ocfg = orc.make_cfg(rows, cols, skyfall=[1, 0, 0, 0, 0, 0, 0, 0, 0, 0], reset_cap=cap, seed=5)
+        env = pb.BatchedPAD(n, rows, cols, skyfall=[1, 0, 0, 0, 0, 0, 0, 0, 0, 0], reset_cap=cap, seed=5)
+        flags = env.reset(step=2).cpu().numpy()
+        assert (flags == orc.FLAG_RESET_CAP).all()
+        assert np.array_equal(env.last_reset_consumed.cpu().numpy(), np.full(n, min(255, cap * rows * cols)))
+        b, f, c, fl = orc.reset(ocfg, env=17, step=2)
+        assert fl == orc.FLAG_RESET_CAP and c == cap * rows * cols
+        assert np.array_equal(env.get_state().boards[17].cpu().numpy(), b) and (b == 0).all()
+    # two colours with a realistic cap: a mix of capped and uncapped boards
+    sky = [0.5, 0.5, 0, 0, 0, 0, 0, 0, 0, 0]
+    ocfg = orc.make_cfg(rows, cols, skyfall=sky, reset_cap=4, cascade_cap=3, seed=9)
+    env = pb.BatchedPAD(n, rows, cols, skyfall=sky, reset_cap=4, cascade_cap=3, seed=9, env0=100)
+    flags = env.reset(step=1).cpu().numpy()
+    st = env.get_state()
+    want_flags = np.zeros(n, np.uint8)
+    for i in range(n):
+        b, f, c, fl = orc.reset(ocfg, env=100 + i, step=1)
+        want_flags[i] = fl
+        assert np.array_equal(st.boards[i].cpu().numpy(), b) and np.array_equal(st.fingers[i].cpu().numpy(), f)
+    assert np.array_equal(flags, want_flags) and 0 < (flags != 0).sum() < n
+    # cascade cap + slab exhaustion in both step kernels (with and without obs)
+    rng = np.random.default_rng(3)
+    inj = rng.integers(0, 2, size=(n, 8)).astype(np.uint8)
+    boards = st.boards.cpu().numpy().astype(np.int8)
+    fingers = st.fingers.cpu().numpy().astype(np.int32)
+    prev, moves = np.full(n, 4, np.uint8), np.zeros(n, np.uint16)
+    a0, r0, i0, f0 = orc.step_batch(ocfg, boards, fingers, prev, moves, actions=None, inj=inj, env0=100, step=2, want_final=True)
+    snap = env.snapshot()
+    for obs in (None, 'f32'):
+        env.restore(snap)
+        o = env.step(None, eval_moves=True, injected=inj, step=2, want_final=True, obs=obs)
+        assert np.array_equal(u32(o.info), i0) and np.array_equal(bits(o.reward.cpu().numpy()), bits(r0))
+        assert np.array_equal(env.get_state(o.final_state).boards.cpu().numpy(), f0)
+    fl = i0 >> 24
+    assert (fl & orc.FLAG_CASCADE_CAP).any() and (fl & orc.FLAG_SKYFALL_EXHAUSTED).any()
