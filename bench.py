@@ -40,6 +40,14 @@ BYTES_STATE_ONLY = 61
 BYTES_WITH_OBS = 61 + ROWS * COLS * 7 * 4
 
 
+def workload_config(n, world):
+    return {"workload": "configs[1]: 2^20 5x6 boards/GPU, random legal move + full cascade resolve + "
+                        "fp32 one-hot obs, injected 32-orb skyfall slab per board-step",
+            "boards_per_gpu": n, "rows": ROWS, "cols": COLS, "skyfall_orbs_per_step": SLAB_ORBS,
+            "l2": "inputs > L2: 881 MB obs stream per step, skyfall slabs rotate over 16 buffers (268 MB)",
+            "parallelism": "env-sharded x%d, no data-path collective" % world}
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -92,11 +100,6 @@ def cpu_port_rate(n_sample, steps, threads):
     boards = np.zeros((n_sample, ROWS, COLS), np.int8)
     fingers = np.zeros((n_sample, 2), np.int32)
     edges = [n_sample * k // threads for k in range(threads + 1)]
-
-    def init(k):
-        for i in range(edges[k], edges[k + 1]):
-            b, f, _, _ = orc.reset(cfg, env=i, step=0)
-            boards[i], fingers[i] = b, f
     # combo-free start boards like PAD.reset; cheap enough to do through the scalar binding on a subsample
     base = min(n_sample, 4096)
     for i in range(base):
@@ -108,12 +111,21 @@ def cpu_port_rate(n_sample, steps, threads):
     prev = np.full(n_sample, 4, np.uint8)
     moves = np.zeros(n_sample, np.uint16)
     inj = rng.integers(0, 6, size=(n_sample, SLAB_ORBS)).astype(np.uint8)
+    obs = np.zeros((n_sample, ROWS, COLS, 7), np.float32)
+    from concurrent.futures import ThreadPoolExecutor
+
+    def work(k, step):
+        sl = slice(edges[k], edges[k + 1])
+        orc.step_batch(cfg, boards[sl], fingers[sl], prev[sl], moves[sl], actions=None, eval_moves=True, inj=inj[sl],
+                       env0=edges[k], step=step)
+        orc.onehot(boards[sl], fingers[sl], out=obs[sl])      # the fp32 one-hot obs, like the GPU step
+
     times = []
-    for t in range(steps):
-        t0 = time.perf_counter()
-        orc.step_batch(cfg, boards, fingers, prev, moves, actions=None, eval_moves=True, inj=inj, step=t + 1,
-                       threads=threads)
-        times.append(time.perf_counter() - t0)
+    with ThreadPoolExecutor(threads) as ex:
+        for t in range(steps):
+            t0 = time.perf_counter()
+            list(ex.map(lambda k: work(k, t + 1), range(threads)))
+            times.append(time.perf_counter() - t0)
     return n_sample / float(np.mean(times)), float(np.mean(times))
 
 
@@ -124,20 +136,22 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n_sample = min(N_LOCAL, (1 << 15) * threads)
-    # warm-up + timed steps, each one env step of the bounded sample
-    cpu_port_rate(min(n_sample, 1 << 14), max(1, min(args.warmup, 2)), threads)
+    # warm-up doubles as calibration: size the per-step sample so that K timed steps take about two minutes at most
+    rate0, _ = cpu_port_rate(min(N_LOCAL, (1 << 12) * threads), max(1, min(args.warmup, 2)), threads)
+    budget_s = 100.0
+    n_sample = int(min(N_LOCAL, max((1 << 10) * threads, rate0 * budget_s / max(1, args.steps))))
+    n_sample -= n_sample % threads
     rate, sec = cpu_port_rate(n_sample, args.steps, threads)
     line = {
         "impl": "reference", "metric": "env_steps_per_sec_incl_cascades", "value": rate, "unit": "steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 bitboards + f64 reward",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8 boards + f64 reward + f32 obs",
         "data": "synthetic",
-        "config": {"workload": "%d 5x6 boards/step sample of configs[1]: random legal move + full cascade resolve, "
-                               "injected 32-orb skyfall (no obs emission on the CPU arm)" % n_sample},
+        "config": workload_config(N_LOCAL, args.gpus),
         "cpu_baseline": {"value": rate, "unit": "steps/s", "cores": threads, "kind": "port",
-                         "sample": "%d boards x %d steps, C port of ppad/pad/game.py + utils.py on %d threads; the "
-                                   "Python reference itself measured ~157 steps/s/core (BASELINE.md section 2)" % (
+                         "sample": "%d boards per step x %d steps of the same workload (move + cascade + fp32 obs), C port "
+                                   "of ppad/pad/game.py + utils.py + agent01.py:254-273 on %d threads; the Python "
+                                   "reference itself measured ~157 steps/s/core (BASELINE.md section 2)" % (
                                        n_sample, args.steps, threads)},
         "e2e": {"value": rate, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -362,11 +376,7 @@ def main():
             "metric": "env_steps_per_sec_incl_cascades", "value": total * K / (ms * 1e-3), "unit": "steps/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32 bitboards + f64 reward + f32 obs", "data": "synthetic",
-            "config": {"workload": "configs[1]: 2^20 5x6 boards/GPU, random legal move + full cascade resolve + "
-                                   "fp32 one-hot obs, injected 32-orb skyfall slab per board-step",
-                       "boards_per_gpu": n, "rows": ROWS, "cols": COLS, "skyfall_orbs_per_step": SLAB_ORBS,
-                       "l2": "inputs > L2: 881 MB obs stream per step, skyfall slabs rotate over 16 buffers (268 MB)",
-                       "parallelism": "env-sharded x%d, no data-path collective" % world},
+            "config": workload_config(n, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "step_kernel<5x6,obs>",
                          "algorithmic_bytes_per_board": BYTES_WITH_OBS},
@@ -395,8 +405,8 @@ def main():
             n_sample = min(N_LOCAL, (1 << 15) * threads)
             rate, sec = cpu_port_rate(n_sample, 2, threads)
             line["cpu_baseline"] = {"value": rate, "unit": "steps/s", "cores": threads, "kind": "port",
-                                    "sample": "%d boards x 2 steps of the same workload (no obs), C port of the "
-                                              "reference's Python path on %d threads, %.1f s/step" % (n_sample, threads, sec)}
+                                    "sample": "%d boards x 2 steps of the same workload (move + cascade + fp32 obs), C port "
+                                              "of the reference's Python path on %d threads, %.1f s/step" % (n_sample, threads, sec)}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -163,11 +163,13 @@ def reset(cfg, inj=None, env=0, step=0, finger=None):
     return board, fout, consumed.value, flags
 
 
-def onehot(boards, fingers):
+def onehot(boards, fingers, out=None):
     boards = np.ascontiguousarray(boards, np.int8)
     fingers = np.ascontiguousarray(fingers, np.int32)
     n, rows, cols = boards.shape
-    out = np.zeros((n, rows, cols, 7), np.float32)
+    if out is None:
+        out = np.zeros((n, rows, cols, 7), np.float32)
+    assert out.dtype == np.float32 and out.flags.c_contiguous and out.shape == (n, rows, cols, 7)
     lib().ppad_oracle_onehot(_p(boards, C.c_int8), _p(fingers, C.c_int32), C.c_int64(n), rows, cols,
                              _p(out, C.c_float))
     return out
