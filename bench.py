@@ -378,7 +378,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "u32 bitboards + f64 reward + f32 obs", "data": "synthetic",
             "config": workload_config(n, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "step_kernel<5x6,obs>",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "step_obs_kernel<Geom<5,6>>",
                          "algorithmic_bytes_per_board": BYTES_WITH_OBS},
             "state_only": {"value": total / (so_ms * 1e-3), "unit": "steps/s", "ms_per_step": so_ms,
                            "hbm_gbs": BYTES_STATE_ONLY * n / (so_ms * 1e-3) / 1e9,
