@@ -74,6 +74,7 @@ class PAD:
                 raise NotImplementedError(e.detail)
             raise Exception(e.detail)
         self._tick = 0            # Philox step counter: one per randomised call
+        self._io_setup()
 
         self.board = -1 * np.ones((self.dim_row, self.dim_col), dtype=int)
         self.locked = np.zeros((self.dim_row, self.dim_col), dtype=int)
@@ -90,34 +91,98 @@ class PAD:
         self.reset(board=board, finger=finger)
 
     # ------------------------------------------------------------------ device round trips
+    # The env's board lives on the GPU as one packed record; `self.board` / `self.finger` are the host mirror the
+    # reference's callers read.  A step is ONE kernel launch plus ONE 48-byte read-back (state, reward, info, action);
+    # the host only converts formats (layout.pack_state / unpack_state).  If a caller assigned or edited the mirror,
+    # the record is re-packed before the next launch.
     def _next_tick(self):
         self._tick += 1
         return self._tick & 0x3FFFFFFF
 
-    def _push(self, board=None):
-        prev = self.action_space.previous_action
-        prev_id = ACTION_IDS.get(prev, 4)
-        flags = self._venv.set_state(np.asarray(self.board if board is None else board)[None],
-                                     np.asarray(self.finger).reshape(1, 2), prev=np.array([prev_id], np.uint8))
-        if int(flags[0]) & _cabi.FLAG_UNSUPPORTED_ORB:
+    def _io_setup(self):
+        import ctypes
+        import torch
+        v = self._venv
+        self._torch, self._ctypes = torch, ctypes
+        # two 64-byte slots: [0] the env's record, [1] scratch for calculate_reward(board=...).
+        # slot layout: state 0..32 | reward 32..40 | info 40..44 | action 44
+        self._io = torch.zeros(128, dtype=torch.uint8, device=v.device)
+        self._io_host = torch.zeros(128, dtype=torch.uint8).pin_memory()
+        self._io_np = self._io_host.numpy()
+        v.state = self._io[:4 * v.words].view(torch.int32).view(1, v.words)   # the env slab IS slot 0
+        self._action_bytes = torch.arange(5, dtype=torch.uint8, device=v.device)
+        self._dev_shadow = None           # (board, finger, prev id) currently packed in slot 0
+
+    def _prev_id(self):
+        return ACTION_IDS.get(self.action_space.previous_action, 4)
+
+    def _write_slot(self, slot, board, finger, prev_id):
+        from .. import layout
+        b = np.asarray(board)
+        if ((b < -1) | (b > 6)).any():
             raise NotImplementedError('orb types 7..9 do not fit the 3-bit board state of ppad_b200')
+        rec = layout.pack_state(b[None], np.asarray(finger).reshape(1, 2), [prev_id]).view(np.uint8).reshape(-1)
+        off = 64 * slot
+        self._io_np[off:off + rec.size] = rec
+        self._io[off:off + 32].copy_(self._io_host[off:off + 32], non_blocking=True)
+
+    def _sync_to_device(self):
+        cur = (self.board, self.finger, self._prev_id())
+        sh = self._dev_shadow
+        if sh is None or sh[2] != cur[2] or not np.array_equal(sh[0], cur[0]) or not np.array_equal(sh[1], cur[1]):
+            self._write_slot(0, *cur)
+            self._dev_shadow = (np.array(cur[0]), np.array(cur[1]), cur[2])
+
+    def _launch(self, slot, action_id, skyfall_damage=None, final=False, log_cap=0):
+        """ppad_step for the one board in `slot`; returns (reward, info, action) after one read-back"""
+        v, torch = self._venv, self._torch
+        base = self._io.data_ptr() + 64 * slot
+        a = _cabi.StepArgs()
+        a.n, a.env0, a.step = 1, v.env0, self._next_tick()
+        a.skyfall_damage = -1 if skyfall_damage is None else int(bool(skyfall_damage))
+        a.state, a.reward, a.info, a.action_out = base, base + 32, base + 40, base + 44
+        a.actions = self._action_bytes.data_ptr() + action_id
+        extra = None
+        if final or log_cap:
+            extra = (torch.empty((1, v.words), dtype=torch.int32, device=v.device),
+                     torch.zeros((1, max(1, log_cap)), dtype=torch.int16, device=v.device))
+            a.final_state, a.combo_log, a.log_cap = extra[0].data_ptr(), extra[1].data_ptr(), max(1, log_cap)
+        with torch.cuda.device(v.device):
+            _cabi.check(v.lib.ppad_step(v._ctx, self._ctypes.byref(a), v._stream()))
+        self._io_host[64 * slot:64 * slot + 48].copy_(self._io[64 * slot:64 * slot + 48])   # blocking read-back
+        raw = self._io_np[64 * slot:64 * slot + 48]
+        reward = np.float64(raw[32:40].view(np.float64)[0])
+        info = int(raw[40:44].view(np.uint32)[0])
+        return reward, info, int(raw[44]), extra
 
     def _pull(self):
-        st = self._venv.get_state()
-        self.board = st.boards[0].cpu().numpy().astype(int)
-        self.finger = st.fingers[0].cpu().numpy().astype(int)
+        from .. import layout
+        words = self._venv.words
+        boards, fingers, _, _ = layout.unpack_state(self._io_np[:4 * words].view(np.uint32).reshape(1, words).copy(),
+                                                    self.dim_row, self.dim_col)
+        self.board = boards[0].astype(int)
+        self.finger = fingers[0].astype(int)
+        self._dev_shadow = (self.board.copy(), self.finger.copy(), self._dev_shadow[2] if self._dev_shadow else 4)
+
+    def _push(self, board=None):
+        """general path for the per-stage methods: (board or self.board, self.finger) -> slot 0 via ppad_pack"""
+        flags = self._venv.set_state(np.asarray(self.board if board is None else board)[None],
+                                     np.asarray(self.finger).reshape(1, 2), prev=np.array([self._prev_id()], np.uint8))
+        self._dev_shadow = None
+        if int(flags[0]) & _cabi.FLAG_UNSUPPORTED_ORB:
+            raise NotImplementedError('orb types 7..9 do not fit the 3-bit board state of ppad_b200')
 
     # ------------------------------------------------------------------ game.py:122-155
     def apply_action(self, action):
         """Swap the finger orb with its neighbour in direction `action`; 'rejected' when that leaves the board."""
         if action not in ('up', 'down', 'left', 'right'):
             return 'accepted'      # the reference falls through its if/elif chain without doing anything
-        self._push()
-        out = self._venv.step(np.array([ACTION_IDS[action]], np.uint8), step=self._next_tick())
-        flags = (int(out.info[0]) >> 24) & 0xFF
-        if flags & _cabi.FLAG_REJECTED:
+        self._sync_to_device()
+        _, info, _, _ = self._launch(0, ACTION_IDS[action])
+        if (info >> 24) & _cabi.FLAG_REJECTED:
             return 'rejected'
         self._pull()
+        self._dev_shadow = (self._dev_shadow[0], self._dev_shadow[1], ACTION_IDS[action])   # the kernel set prev = action
         return 'accepted'
 
     # ------------------------------------------------------------------ game.py:157-199
@@ -139,11 +204,9 @@ class PAD:
     # ------------------------------------------------------------------ game.py:201-221
     def drop(self, board):
         """Move all orbs down into empty cells; `board` is updated in place and returned."""
-        keep = self._venv.state.clone()
         self._push(board)
         self._venv.drop()
         board[...] = self._venv.get_state().boards[0].cpu().numpy()
-        self._venv.state.copy_(keep)
         return board
 
     def visualize(self, filename, shrink=3, animate=True):
@@ -154,11 +217,9 @@ class PAD:
         """Fill empty cells (all cells when reset) row-major with skyfall orbs; in place."""
         if board is None:
             board = self.board
-        keep = self._venv.state.clone()
         self._push(board)
         self._venv.fill_board(reset=reset, step=self._next_tick())
         board[...] = self._venv.get_state().boards[0].cpu().numpy()
-        self._venv.state.copy_(keep)
         return board
 
     def render(self, board=None):
@@ -204,6 +265,7 @@ class PAD:
         if finger is not None:
             self.finger = np.copy(finger)
         self.action_space.finger = self.finger
+        self._dev_shadow = None
 
         self._record_observation()
         return self.state()
@@ -247,20 +309,17 @@ class PAD:
     # ------------------------------------------------------------------ game.py:364-405
     def calculate_reward(self, board=None, skyfall_damage=True, verbose=False):
         """Damage of all combos of `board` (a copy is evaluated; cancel -> drop -> skyfall until stable when
-        skyfall_damage).  One fused kernel launch."""
-        keep = self._venv.state.clone()
-        self._push(self.board if board is None else board)
-        out = self._venv.calculate_reward(step=self._next_tick(), skyfall_damage=skyfall_damage,
-                                          want_final=verbose, log_cap=64 if verbose else 0)
-        reward = np.float64(out.reward[0].item())
+        skyfall_damage).  One fused kernel launch on the scratch record; the env's own record is not touched."""
+        self._write_slot(1, self.board if board is None else board, self.finger, self._prev_id())
+        reward, info, _, extra = self._launch(1, _cabi.PASS, skyfall_damage=skyfall_damage, final=verbose,
+                                              log_cap=64 if verbose else 0)
         if verbose is True:
-            n = int(out.info[0]) & 0xFF
+            n = info & 0xFF
             print('Board after the cascade:')
-            self.render(self._venv.get_state(out.final_state).boards[0].cpu().numpy())
-            log = out.combo_log[0, :min(n, 64)].cpu().numpy().view(np.uint16)
+            self.render(self._venv.get_state(extra[0]).boards[0].cpu().numpy())
+            log = extra[1][0, :min(n, 64)].cpu().numpy().view(np.uint16)
             print([{'color': parameters.int2english[int(v) & 0xFF], 'N': float(int(v) >> 8)} for v in log])
             print('The total damange is:', reward)
-        self._venv.state.copy_(keep)
         return reward
 
     # ------------------------------------------------------------------ game.py:407-427

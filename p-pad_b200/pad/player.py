@@ -31,12 +31,21 @@ class PlayerAction:
         Philox instead of the process-global Mersenne Twister."""
         if type != 'random':
             raise Exception('ERROR: Unknown player action type!')
-        venv = self._slab()
-        prev = self.previous_action if self.previous_action in self.player_action else 'pass'
-        board = np.zeros((1, self.dim_row, self.dim_col), dtype=np.int64)
-        venv.set_state(board, np.asarray(self.finger).reshape(1, 2), prev=np.array([self.player_action.index(prev)], np.uint8))
+        env = self._env
         self._draws += 1
-        a = int(venv.sample_actions(include_pass=include_pass, step=0x40000000 + self._draws)[0])
+        if env is not None and np.array_equal(np.asarray(self.finger), env.finger):
+            # fast path: the env's device record already holds (finger, previous_action)
+            env._sync_to_device()
+            a = int(env._venv.sample_actions(include_pass=include_pass, step=0x40000000 + self._draws)[0])
+        else:
+            venv = self._slab()
+            prev = self.previous_action if self.previous_action in self.player_action else 'pass'
+            board = np.zeros((1, self.dim_row, self.dim_col), dtype=np.int64)
+            venv.set_state(board, np.asarray(self.finger).reshape(1, 2),
+                           prev=np.array([self.player_action.index(prev)], np.uint8))
+            a = int(venv.sample_actions(include_pass=include_pass, step=0x40000000 + self._draws)[0])
+            if env is not None:
+                env._dev_shadow = None     # the env's device record was used as scratch: re-pack before its next step
         if a == 255:
             raise Exception('ERROR: no legal move from finger {0}'.format(self.finger))
         return self.player_action[a]
