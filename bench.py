@@ -341,23 +341,22 @@ def main():
     e2e_ms = timed(e2e_step, base + 3, e2e_k)
     h2d = pipe.slab.numel() * 4
     d2h = pipe.reward.numel() * 8 + pipe.info.numel() * 4 + pipe.action.numel() + pipe.state.numel() * 4
-    # the same with two steps in flight (double-buffered host buffers; results of step t are read while step t + 1
-    # is on the wire) -- reported separately, the headline e2e above is the synchronous call
-    pipe2 = env.host_pipe(slab_orbs=SLAB_ORBS, chunks=2)
-    pipe2.slab.copy_(slabs[1].cpu())
-    pipes = [pipe, pipe2]
+    # the same with two steps in flight (two sets of host buffers on one pipe; the results of step t are read while
+    # step t + 1 is running) -- reported separately, the headline e2e above is the synchronous call
+    pipe2 = env.host_pipe(slab_orbs=SLAB_ORBS, chunks=2, depth=2)
+    for k, b in enumerate(pipe2.buffers):
+        b.slab.copy_(slabs[k].cpu())
 
     def e2e_async_step(t):
-        p = pipes[t & 1]
-        p.wait()                       # results of step t - 2 (this buffer pair) are on the host
-        _ = p.reward[0].item()         # "read" them
-        p.step(eval_moves=True, obs=obs_buf, step=t, wait=False)
+        k = t & 1
+        pipe2.wait(k)                              # results of step t - 2 (this buffer set) are on the host
+        _ = pipe2.buffers[k].reward[0].item()      # "read" them
+        pipe2.step(eval_moves=True, obs=obs_buf, step=t, wait=False, buf=k)
 
     for t in range(base + 100, base + 104):
         e2e_async_step(t)
-    e2e_async_ms = timed(e2e_async_step, base + 104, e2e_k, finish=lambda: [p.join() for p in pipes])
-    for p in pipes:
-        p.wait()
+    e2e_async_ms = timed(e2e_async_step, base + 104, e2e_k, finish=lambda: (pipe2.join(0), pipe2.join(1)))
+    pipe2.wait(0), pipe2.wait(1)
 
     # episode stats of the last step, all-gathered over NVLink (tiny; outside the timed region)
     stats = pdist.gather_stats(pdist.local_stats(out.reward, out.info))
@@ -385,7 +384,7 @@ def main():
                            "note": "same kernel without the obs stream; L2 flushed (256 MiB fill) before every step"},
             "e2e": {"value": total * e2e_k / (e2e_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_k,
-                    "note": "HostPipe.step (ppad_pipe_step, 2 chunks on 2 streams) with pinned host buffers, synchronous: "
+                    "note": "HostPipe.step (ppad_pipe_step, zero copy: the kernel reads / writes the pinned host buffers), synchronous: "
                             "skyfall slab H2D; reward, info, action and packed state (the reference's (board, finger) "
                             "observation) D2H every step; the fp32 one-hot obs stays in HBM for the device-side agent",
                     "two_steps_in_flight": {"value": total * e2e_k / (e2e_async_ms * 1e-3), "unit": "steps/s",

@@ -134,6 +134,7 @@ typedef struct ppad_step_args {
     double *reward;               /* [n] float64 */
     uint32_t *info;               /* [n] */
     void *final_state;            /* [n] packed, or NULL */
+    void *state_copy;             /* [n] packed: a second copy of the state written back (e.g. pinned host memory) or NULL */
     uint16_t *combo_log;          /* [n, log_cap] or NULL */
     int32_t log_cap;
     void *obs;                    /* [n, rows, cols, 7] or NULL */
@@ -166,8 +167,10 @@ int ppad_rollout(const ppad_ctx *ctx, int64_t n, uint64_t env0, uint32_t step0, 
  * scratch and `chunks` streams; ppad_pipe_step cuts the batch into chunks, and chunk k copies its inputs
  * host -> device, runs the fused step kernel and copies its results device -> host on its own stream, so the
  * copies of neighbouring chunks overlap the kernels and each other (PCIe is full duplex).
- * ppad_pipe_step returns after enqueueing; ppad_pipe_wait blocks until the last enqueued step is complete;
- * ppad_pipe_join makes `stream` wait for it instead.  Host buffers should be pinned.  The env state and the
+ * ppad_pipe_step returns after enqueueing; ppad_pipe_wait(slot) blocks until the step last enqueued with that
+ * slot is complete; ppad_pipe_join makes `stream` wait for it instead.  Steps of one pipe execute in the order
+ * they were enqueued (each chunk keeps its stream); `slot` (0 or 1) only names the completion events, so that a
+ * caller with two sets of host buffers can enqueue step t + 1 before it waits for step t.  Host buffers should be pinned.  The env state and the
  * observation stay in HBM (state_out_host, if given, receives a copy of the packed state records: the
  * reference's (board, finger) observation). */
 typedef struct ppad_pipe ppad_pipe;
@@ -191,9 +194,13 @@ typedef struct ppad_host_step_args {
 int ppad_pipe_create(const ppad_ctx *ctx, int64_t n_max, int32_t slab_words_max, int32_t chunks, ppad_pipe **out);
 void ppad_pipe_destroy(ppad_pipe *pipe);
 /* `after_stream`: work already queued there (e.g. ppad_reset) is ordered before the chunks */
-int ppad_pipe_step(ppad_pipe *pipe, const ppad_host_step_args *args, void *after_stream);
-int ppad_pipe_wait(ppad_pipe *pipe);
-int ppad_pipe_join(ppad_pipe *pipe, void *stream);
+int ppad_pipe_step(ppad_pipe *pipe, const ppad_host_step_args *args, void *after_stream, int32_t slot);
+/* Pinned host buffers are handed to the kernel directly (zero copy over unified addressing: the PCIe traffic
+ * overlaps the kernel store by store); pageable buffers, or zero copy switched off, go through the pipe's staging
+ * buffers and chunked cudaMemcpyAsync. */
+int ppad_pipe_set_zero_copy(ppad_pipe *pipe, int32_t enabled);
+int ppad_pipe_wait(ppad_pipe *pipe, int32_t slot);
+int ppad_pipe_join(ppad_pipe *pipe, void *stream, int32_t slot);
 
 /* Agent01.board_finger_to_state (agent01.py:254-273): state -> [n, rows, cols, 7] NHWC */
 int ppad_encode_obs(const ppad_ctx *ctx, int64_t n, const void *state, void *obs, int obs_dtype, void *stream);

@@ -30,7 +30,8 @@ class StepArgs(C.Structure):
                 ("auto_reset", C.c_int32), ("max_moves", C.c_int32), ("state", C.c_void_p),
                 ("actions", C.c_void_p), ("slab", C.c_void_p), ("slab_words", C.c_int32), ("n_inj", C.c_int32),
                 ("action_out", C.c_void_p), ("reward", C.c_void_p), ("info", C.c_void_p),
-                ("final_state", C.c_void_p), ("combo_log", C.c_void_p), ("log_cap", C.c_int32),
+                ("final_state", C.c_void_p), ("state_copy", C.c_void_p), ("combo_log", C.c_void_p),
+                ("log_cap", C.c_int32),
                 ("obs", C.c_void_p), ("obs_dtype", C.c_int32), ("skyfall_damage", C.c_int32),
                 ("paths", C.c_void_p), ("path_lens", C.c_void_p), ("path_words", C.c_int32), ("path_len", C.c_int32)]
 
@@ -51,7 +52,7 @@ SYMBOLS = ["ppad_default_config", "ppad_create", "ppad_destroy", "ppad_abi_versi
            "ppad_step", "ppad_encode_obs", "ppad_cancel", "ppad_legal_mask", "ppad_sample_actions", "ppad_drop",
            "ppad_fill", "ppad_damage", "ppad_select_actions", "ppad_discount", "ppad_replay_push",
            "ppad_replay_sample", "ppad_permute", "ppad_pipe_create", "ppad_pipe_destroy", "ppad_pipe_step",
-           "ppad_pipe_wait", "ppad_pipe_join", "ppad_rollout"]
+           "ppad_pipe_wait", "ppad_pipe_join", "ppad_rollout", "ppad_pipe_set_zero_copy"]
 
 
 class PPADError(RuntimeError):
@@ -101,9 +102,10 @@ def lib():
     L.ppad_pipe_create.argtypes = [vp, i64, i32, i32, C.POINTER(vp)]
     L.ppad_pipe_destroy.argtypes = [vp]
     L.ppad_pipe_destroy.restype = None
-    L.ppad_pipe_step.argtypes = [vp, C.POINTER(HostStepArgs), vp]
-    L.ppad_pipe_wait.argtypes = [vp]
-    L.ppad_pipe_join.argtypes = [vp, vp]
+    L.ppad_pipe_step.argtypes = [vp, C.POINTER(HostStepArgs), vp, i32]
+    L.ppad_pipe_wait.argtypes = [vp, i32]
+    L.ppad_pipe_set_zero_copy.argtypes = [vp, i32]
+    L.ppad_pipe_join.argtypes = [vp, vp, i32]
     L.ppad_select_actions.argtypes = [vp, i64, u64, u32, vp, vp, i32, C.c_float, C.c_float, i32, vp, vp]
     L.ppad_discount.argtypes = [vp, i64, i32, vp, vp, C.c_double, i32, i32, vp]
     L.ppad_replay_push.argtypes = [vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]

@@ -359,9 +359,9 @@ class BatchedPAD:
                                                int(bool(log10)), int(bool(norm)), self._stream()))
         return r
 
-    def host_pipe(self, slab_orbs=32, chunks=4):
+    def host_pipe(self, slab_orbs=32, chunks=2, zero_copy=True, depth=1):
         """A HostPipe for this slab: env steps whose inputs and results are pinned HOST tensors (ppad_pipe_*)."""
-        return HostPipe(self, slab_orbs, chunks)
+        return HostPipe(self, slab_orbs, chunks, zero_copy, depth)
 
     @staticmethod
     def split_info(info):
@@ -374,29 +374,38 @@ class HostPipe:
     """Env steps for callers whose inputs and results live in host memory (the reference's situation:
     PAD.step takes a Python value and appends to Python lists, game.py:329-362).
 
-    The batch is cut into `chunks`; each chunk copies its inputs host -> device, runs the fused step kernel and
-    copies its results device -> host on its own stream, so PCIe traffic in both directions overlaps the kernels.
-    The env state and the one-hot observation stay in HBM.  Buffers are pinned and owned by the pipe:
+    zero_copy (default): the kernel reads the skyfall slab from and writes its results to the pinned host buffers
+    directly (unified addressing), so the PCIe traffic overlaps the kernel store by store.  Otherwise the batch is
+    cut into `chunks`; each chunk copies its inputs host -> device, runs the fused step kernel and copies its
+    results device -> host on its own stream, so PCIe traffic in both directions overlaps the kernels.
+    The env state and the one-hot observation stay in HBM.  Buffers are pinned and owned by the pipe; with
+    depth = 2 there are two sets (``buffers[0]``, ``buffers[1]``) so that step t + 1 can be enqueued before the
+    results of step t are read (steps of one pipe always execute in order):
       in : slab int32 [n, slab_orbs / 8] (nibble-packed skyfall, layout.pack_slab), actions uint8 [n]
       out: action uint8 [n], reward float64 [n], info int32 [n], state int32 [n, words]
+    ``pipe.slab`` etc. are the buffers of set 0.
     """
 
-    def __init__(self, venv, slab_orbs=32, chunks=4):
+    def __init__(self, venv, slab_orbs=32, chunks=2, zero_copy=True, depth=1):
         self.venv = venv
         self.slab_orbs = int(slab_orbs)
         self.slab_words = (self.slab_orbs + 7) // 8
         n = venv.n
         pin = dict(pin_memory=True)
-        self.slab = torch.zeros((n, max(1, self.slab_words)), dtype=torch.int32, **pin)
-        self.actions = torch.zeros(n, dtype=torch.uint8, **pin)
-        self.action = torch.zeros(n, dtype=torch.uint8, **pin)
-        self.reward = torch.zeros(n, dtype=torch.float64, **pin)
-        self.info = torch.zeros(n, dtype=torch.int32, **pin)
-        self.state = torch.zeros((n, venv.words), dtype=torch.int32, **pin)
+        self.buffers = [SimpleNamespace(
+            slab=torch.zeros((n, max(1, self.slab_words)), dtype=torch.int32, **pin),
+            actions=torch.zeros(n, dtype=torch.uint8, **pin),
+            action=torch.zeros(n, dtype=torch.uint8, **pin),
+            reward=torch.zeros(n, dtype=torch.float64, **pin),
+            info=torch.zeros(n, dtype=torch.int32, **pin),
+            state=torch.zeros((n, venv.words), dtype=torch.int32, **pin)) for _ in range(2 if depth > 1 else 1)]
+        for name, value in vars(self.buffers[0]).items():
+            setattr(self, name, value)
         handle = C.c_void_p()
         with torch.cuda.device(venv.device):
             _cabi.check(venv.lib.ppad_pipe_create(venv._ctx, n, self.slab_words, int(chunks), C.byref(handle)))
         self._pipe = handle
+        _cabi.check(venv.lib.ppad_pipe_set_zero_copy(handle, int(bool(zero_copy))))
 
     def __del__(self):
         pipe, self._pipe = getattr(self, "_pipe", None), None
@@ -404,32 +413,33 @@ class HostPipe:
             self.venv.lib.ppad_pipe_destroy(pipe)
 
     def step(self, use_actions=False, use_slab=True, eval_moves=False, auto_reset=False, max_moves=0, obs=None,
-             want_state=True, skyfall_damage=None, step=None, wait=True):
-        """Enqueue one step (inputs are read from self.slab / self.actions, results land in self.reward, self.info,
-        self.action and, with want_state, self.state).  wait=False returns right after enqueueing; call wait()
-        before reading the results or refilling the input buffers."""
+             want_state=True, skyfall_damage=None, step=None, wait=True, buf=0):
+        """Enqueue one step (inputs are read from buffers[buf].slab / .actions, results land in .reward, .info,
+        .action and, with want_state, .state).  wait=False returns right after enqueueing; call wait(buf) before
+        reading the results or refilling that buffer set."""
         v = self.venv
+        b = self.buffers[buf]
         a = _cabi.HostStepArgs()
         a.n, a.env0, a.step = v.n, v.env0, v._next_step(step)
         a.eval_moves, a.auto_reset, a.max_moves = int(bool(eval_moves)), int(bool(auto_reset)), int(max_moves)
         a.skyfall_damage = -1 if skyfall_damage is None else int(bool(skyfall_damage))
         a.state = v.state.data_ptr()
-        a.actions_host = self.actions.data_ptr() if use_actions else None
-        a.slab_host = self.slab.data_ptr() if use_slab and self.slab_words else None
+        a.actions_host = b.actions.data_ptr() if use_actions else None
+        a.slab_host = b.slab.data_ptr() if use_slab and self.slab_words else None
         a.slab_words, a.n_inj = self.slab_words, self.slab_orbs
-        a.action_out_host, a.reward_host, a.info_host = self.action.data_ptr(), self.reward.data_ptr(), self.info.data_ptr()
-        a.state_out_host = self.state.data_ptr() if want_state else None
+        a.action_out_host, a.reward_host, a.info_host = b.action.data_ptr(), b.reward.data_ptr(), b.info.data_ptr()
+        a.state_out_host = b.state.data_ptr() if want_state else None
         if obs is not None:
             a.obs = obs.data_ptr()
             a.obs_dtype = _cabi.OBS_F32 if obs.dtype == torch.float32 else _cabi.OBS_U8
         with torch.cuda.device(v.device):
-            _cabi.check(v.lib.ppad_pipe_step(self._pipe, C.byref(a), v._stream()))
+            _cabi.check(v.lib.ppad_pipe_step(self._pipe, C.byref(a), v._stream(), int(buf)))
             if wait:
-                _cabi.check(v.lib.ppad_pipe_wait(self._pipe))
+                _cabi.check(v.lib.ppad_pipe_wait(self._pipe, int(buf)))
 
-    def wait(self):
-        _cabi.check(self.venv.lib.ppad_pipe_wait(self._pipe))
+    def wait(self, buf=0):
+        _cabi.check(self.venv.lib.ppad_pipe_wait(self._pipe, int(buf)))
 
-    def join(self):
-        """make torch's current stream wait for the last enqueued step (e.g. before reading obs on the device)"""
-        _cabi.check(self.venv.lib.ppad_pipe_join(self._pipe, self.venv._stream()))
+    def join(self, buf=0):
+        """make torch's current stream wait for the step last enqueued with `buf` (e.g. before reading obs on the device)"""
+        _cabi.check(self.venv.lib.ppad_pipe_join(self._pipe, self.venv._stream(), int(buf)))
