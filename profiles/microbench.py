@@ -5,7 +5,8 @@ import torch
 import ppad_b200
 
 n = 1 << 20
-env = ppad_b200.BatchedPAD(n, 5, 6, seed=1)
+ROWS, COLS = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (5, 6)
+env = ppad_b200.BatchedPAD(n, ROWS, COLS, seed=1)
 env.reset(step=0)
 g = torch.Generator(device=env.device).manual_seed(0)
 slabs = [env._slab(torch.randint(0, 6, (n, 32), device=env.device, dtype=torch.uint8, generator=g))[0] for _ in range(8)]
