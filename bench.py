@@ -401,10 +401,10 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
-            n_sample = min(N_LOCAL, (1 << 15) * threads)
-            rate, sec = cpu_port_rate(n_sample, 2, threads)
+            n_sample = N_LOCAL                                   # the whole workload, 3 steps: ~10-20 s of CPU time
+            rate, sec = cpu_port_rate(n_sample, 3, threads)
             line["cpu_baseline"] = {"value": rate, "unit": "steps/s", "cores": threads, "kind": "port",
-                                    "sample": "%d boards x 2 steps of the same workload (move + cascade + fp32 obs), C port "
+                                    "sample": "%d boards x 3 steps of the same workload (move + cascade + fp32 obs), C port "
                                               "of the reference's Python path on %d threads, %.1f s/step" % (n_sample, threads, sec)}
         print(json.dumps(line))
     if world > 1:
