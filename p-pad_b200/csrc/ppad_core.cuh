@@ -317,14 +317,15 @@ struct Tally {
         if (colour > 4) return;   // heal / jammer: counts as a combo, no unit matches
         const double f = 1.0 + 0.25 * (double)(N - 3);   // exact
         const int nu = team.n[colour];
-        for (int u = 0; u < nu; u++) {
-            const double t = dmul(dmul(team.mult[colour][u], f), team.atk[colour][u]);
-            t0 = colour == 0 ? dadd(t0, t) : t0;
-            t1 = colour == 1 ? dadd(t1, t) : t1;
-            t2 = colour == 2 ? dadd(t2, t) : t2;
-            t3 = colour == 3 ? dadd(t3, t) : t3;
-            t4 = colour == 4 ? dadd(t4, t) : t4;
-        }
+        // pick this colour's tracker once, add the units in team order, put it back: plain selects around a short
+        // loop instead of a colour switch per unit (which compiled to indirect branches that split the warp)
+        double tr = colour == 0 ? t0 : (colour == 1 ? t1 : (colour == 2 ? t2 : (colour == 3 ? t3 : t4)));
+        for (int u = 0; u < nu; u++) tr = dadd(tr, dmul(dmul(team.mult[colour][u], f), team.atk[colour][u]));
+        t0 = colour == 0 ? tr : t0;
+        t1 = colour == 1 ? tr : t1;
+        t2 = colour == 2 ? tr : t2;
+        t3 = colour == 3 ? tr : t3;
+        t4 = colour == 4 ? tr : t4;
     }
     // game.py:193-199: every tracker *= 1 + 0.25 (#combos - 1); sum in dict order blue, red,
     // green, dark, light starting from the int 0
