@@ -12,6 +12,7 @@ Differences that are deliberate ("quirks"):
   * ``action is 'pass'`` identity tests become equality tests;
   * orb types 7..9 and boards other than 5x6 / 6x7 raise (no kernel instantiation).
 """
+import random
 import time
 
 import numpy as np
@@ -42,7 +43,9 @@ class PAD:
                  board=None,
                  finger=None,
                  seed=None,
-                 device=None):
+                 device=None,
+                 rng='philox',
+                 clock=None):
         # the argument checks of game.py:54-68, with the reference's messages
         def require(ok, message):
             if not ok:
@@ -66,6 +69,17 @@ class PAD:
         self.observation_space = None
         self.render_dict = parameters.default_render_dict
         self.seed = int(time.time_ns()) & 0xFFFFFFFFFFFFFFFF if seed is None else int(seed)
+        # rng='philox' (default): every draw comes from the GPU's counter-based Philox streams keyed by `seed`.
+        # rng='reference': every draw comes from Python's process-global `random` in exactly the order and number
+        # the reference makes them (game.py:72,253-255,302-315,464; player.py:49) and is handed to the kernels as an
+        # injected orb sequence -- after the same random.seed(...) the env reproduces the reference's trajectories
+        # bit for bit.  `clock` stands in for datetime.now() in the reference's random.seed(datetime.now()) calls
+        # (a callable returning the seed; None = do not reseed).
+        if rng not in ('philox', 'reference'):
+            raise Exception("ERROR: rng must be 'philox' or 'reference'")
+        self.rng = rng
+        self.clock = clock
+        self._reseed()
         try:
             self._venv = BatchedPAD(1, dim_row, dim_col, skyfall=list(skyfall), skyfall_damage=skyfall_damage,
                                     team=team, seed=self.seed, device=device, cascade_cap=0, reset_cap=0)
@@ -89,6 +103,41 @@ class PAD:
         self.action_space = player.PlayerAction(finger=self.finger, dim_row=self.dim_row, dim_col=self.dim_col,
                                                 env=self, seed=self.seed)
         self.reset(board=board, finger=finger)
+
+    # ------------------------------------------------------------------ rng='reference': the host only draws numbers
+    def _reseed(self):
+        if self.rng == 'reference' and self.clock is not None:
+            random.seed(self.clock())          # game.py:72,302
+
+    def _draw_orb(self):
+        """one random_orb(self.skyfall) draw (game.py:458-470) from the global Mersenne Twister"""
+        u = random.random()
+        acc = 0
+        for i, p in enumerate(self.skyfall):
+            acc += p
+            if acc >= u and p > 0:
+                return i
+        return len(self.skyfall) - 1
+
+    def _speculate(self, run, unit, first=2):
+        """Run `run(orbs)` -> number of orbs the kernel consumed, on a pre-drawn orb sequence, then leave the
+        Mersenne Twister exactly where the reference would have left it (rewind, burn `consumed` draws)."""
+        k = first * unit
+        while True:
+            state0 = random.getstate()
+            orbs = np.array([self._draw_orb() for _ in range(k)], np.uint8)
+            if orbs.max(initial=0) > 6:
+                raise NotImplementedError('orb types 7..9 do not fit the 3-bit board state of ppad_b200')
+            consumed = run(orbs)
+            if consumed is not None and consumed <= k:
+                random.setstate(state0)
+                for _ in range(consumed):
+                    random.random()
+                return consumed
+            random.setstate(state0)
+            k *= 4
+            if k > 1 << 14:
+                raise RuntimeError('cascade / reset did not terminate within %d skyfall orbs' % k)
 
     # ------------------------------------------------------------------ device round trips
     # The env's board lives on the GPU as one packed record; `self.board` / `self.finger` are the host mirror the
@@ -133,15 +182,21 @@ class PAD:
             self._write_slot(0, *cur)
             self._dev_shadow = (np.array(cur[0]), np.array(cur[1]), cur[2])
 
-    def _launch(self, slot, action_id, skyfall_damage=None, final=False, log_cap=0):
+    def _launch(self, slot, action_id, skyfall_damage=None, final=False, log_cap=0, injected=None):
         """ppad_step for the one board in `slot`; returns (reward, info, action) after one read-back"""
         v, torch = self._venv, self._torch
+        slab = None
+        if injected is not None:
+            from .. import layout
+            slab = torch.from_numpy(layout.pack_slab(np.asarray(injected, np.uint8)[None]).view(np.int32)).to(v.device)
         base = self._io.data_ptr() + 64 * slot
         a = _cabi.StepArgs()
         a.n, a.env0, a.step = 1, v.env0, self._next_tick()
         a.skyfall_damage = -1 if skyfall_damage is None else int(bool(skyfall_damage))
         a.state, a.reward, a.info, a.action_out = base, base + 32, base + 40, base + 44
         a.actions = self._action_bytes.data_ptr() + action_id
+        if slab is not None:
+            a.slab, a.slab_words, a.n_inj = slab.data_ptr(), slab.shape[1], len(injected)
         extra = None
         if final or log_cap:
             extra = (torch.empty((1, v.words), dtype=torch.int32, device=v.device),
@@ -218,7 +273,13 @@ class PAD:
         if board is None:
             board = self.board
         self._push(board)
-        self._venv.fill_board(reset=reset, step=self._next_tick())
+        if self.rng == 'reference':
+            need = board.size if reset else int((np.asarray(board) == -1).sum())
+            orbs = np.array([self._draw_orb() for _ in range(need)], np.uint8).reshape(1, -1)
+            if need:
+                self._venv.fill_board(reset=reset, injected=orbs, step=self._next_tick())
+        else:
+            self._venv.fill_board(reset=reset, step=self._next_tick())
         board[...] = self._venv.get_state().boards[0].cpu().numpy()
         return board
 
@@ -250,6 +311,32 @@ class PAD:
         self.rewards = []
         self.action_space.previous_action = 'pass'
 
+        self._reseed()
+        if self.rng == 'reference':
+            cells = self.dim_row * self.dim_col
+            if board is None:
+                def attempt(orbs):
+                    # the kernel rejection-samples over the pre-drawn attempts; which one it kept tells the draw count
+                    flags = self._venv.reset(fingers=np.zeros((1, 2), int), injected=orbs[None], step=self._next_tick())
+                    if int(flags[0]) & _cabi.FLAG_SKYFALL_EXHAUSTED:
+                        return None
+                    kept = self._venv.get_state().boards[0].cpu().numpy().reshape(-1)
+                    for a in range(len(orbs) // cells):
+                        if np.array_equal(orbs[a * cells:(a + 1) * cells], kept):
+                            self.board = kept.reshape(self.dim_row, self.dim_col).astype(int)
+                            return (a + 1) * cells
+                    return None
+                self._speculate(attempt, cells, first=6)
+            else:
+                self.board = np.copy(board)
+            if finger is None:
+                self.finger = np.array([random.randint(0, self.dim_row - 1), random.randint(0, self.dim_col - 1)])
+            else:
+                self.finger = np.copy(finger)
+            self.action_space.finger = self.finger
+            self._dev_shadow = None
+            self._record_observation()
+            return self.state()
         tick = self._next_tick()
         if board is None or finger is None:
             # combo-free random board by rejection and/or a random finger, on the GPU
@@ -311,8 +398,22 @@ class PAD:
         """Damage of all combos of `board` (a copy is evaluated; cancel -> drop -> skyfall until stable when
         skyfall_damage).  One fused kernel launch on the scratch record; the env's own record is not touched."""
         self._write_slot(1, self.board if board is None else board, self.finger, self._prev_id())
-        reward, info, _, extra = self._launch(1, _cabi.PASS, skyfall_damage=skyfall_damage, final=verbose,
-                                              log_cap=64 if verbose else 0)
+        if self.rng == 'reference' and skyfall_damage:
+            result = []
+
+            def cascade(orbs):
+                self._write_slot(1, self.board if board is None else board, self.finger, self._prev_id())
+                r = self._launch(1, _cabi.PASS, skyfall_damage=True, final=verbose, log_cap=64 if verbose else 0,
+                                 injected=orbs)
+                if (r[1] >> 24) & _cabi.FLAG_SKYFALL_EXHAUSTED or ((r[1] >> 16) & 0xFF) == 255:
+                    return None
+                result[:] = r
+                return (r[1] >> 16) & 0xFF
+            self._speculate(cascade, 32, first=2)
+            reward, info, _, extra = result
+        else:
+            reward, info, _, extra = self._launch(1, _cabi.PASS, skyfall_damage=skyfall_damage, final=verbose,
+                                                  log_cap=64 if verbose else 0)
         if verbose is True:
             n = info & 0xFF
             print('Board after the cascade:')

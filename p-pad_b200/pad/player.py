@@ -32,6 +32,20 @@ class PlayerAction:
         if type != 'random':
             raise Exception('ERROR: Unknown player action type!')
         env = self._env
+        if env is not None and getattr(env, 'rng', 'philox') == 'reference':
+            # the reference's own rejection loop over the global Mersenne Twister (player.py:46-62): in this mode the
+            # host draws the numbers so that a seeded run replays the reference draw for draw
+            import random
+            num_action = len(self.player_action) - 1 + (1 if include_pass else 0)
+            while True:
+                current = self.player_action[random.randint(0, num_action - 1)]
+                if self.opposite_actions[current] == self.previous_action:
+                    continue
+                if (self.finger[0] >= self.dim_row - 1 and current == 'down') or (self.finger[0] <= 0 and current == 'up'):
+                    continue
+                if (self.finger[1] >= self.dim_col - 1 and current == 'right') or (self.finger[1] <= 0 and current == 'left'):
+                    continue
+                return current
         self._draws += 1
         if env is not None and np.array_equal(np.asarray(self.finger), env.finger):
             # fast path: the env's device record already holds (finger, previous_action)

@@ -337,6 +337,54 @@ def gen_random_orb(ref):
     print("random_orb.npz")
 
 
+def gen_mt_episodes():
+    """Whole episodes of the reference driven by its OWN Mersenne Twister (no injection): seeded through the
+    patched clock, so that PAD(rng='reference', clock=...) of ppad_b200 can be asked to replay them draw for draw."""
+    out = {}
+    for rows, cols in ((5, 6), (6, 7)):
+        recs = dict(seed=[], init_board=[], init_finger=[], actions=[], boards=[], fingers=[], pass_reward=[],
+                    extra_reward=[], board2=[], finger2=[], actions2=[], pass_reward2=[], mt_after=[])
+        for s in range(12):
+            seed = 7000 + 100 * rows + s
+            rh.set_clock(seed)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                env = rh.load().game.PAD(dim_row=rows, dim_col=cols)
+                recs["seed"].append(seed)
+                recs["init_board"].append(env.board.astype(np.int8).copy())
+                recs["init_finger"].append(env.finger.astype(np.int32).copy())
+                acts, boards, fingers = [], [], []
+                for _ in range(25):
+                    a = env.action_space.sample()
+                    env.step(a)
+                    acts.append(ACTIONS.index(a))
+                    boards.append(env.board.astype(np.int8).copy())
+                    fingers.append(env.finger.astype(np.int32).copy())
+                env.step("pass")
+                recs["actions"].append(np.array(acts))
+                recs["boards"].append(np.stack(boards))
+                recs["fingers"].append(np.stack(fingers))
+                recs["pass_reward"].append(float(env.rewards[-1]))
+                recs["extra_reward"].append(float(env.calculate_reward(board=env.board, skyfall_damage=True)))
+                rh.set_clock(seed + 50)
+                env.reset()
+                recs["board2"].append(env.board.astype(np.int8).copy())
+                recs["finger2"].append(env.finger.astype(np.int32).copy())
+                acts = []
+                for _ in range(6):
+                    a = env.action_space.sample(include_pass=True)
+                    env.step(a)
+                    acts.append(ACTIONS.index(a))
+                env.step("pass")
+                recs["actions2"].append(np.array(acts))
+                recs["pass_reward2"].append(float(env.rewards[-1]))
+                recs["mt_after"].append(random.random())       # where the Mersenne Twister stands at the end
+        for k, v in recs.items():
+            out["%s_%dx%d" % (k, rows, cols)] = np.stack(v) if isinstance(v[0], np.ndarray) else np.array(v)
+    np.savez_compressed(os.path.join(HERE, "mt_episodes.npz"), **out)
+    print("mt_episodes.npz")
+
+
 def main():
     ref = rh.load()
     gen_kat(ref)
@@ -346,6 +394,7 @@ def main():
     gen_legal(ref)
     gen_random_orb(ref)
     gen_reset()
+    gen_mt_episodes()
     gen_episodes(5, 6, 24, 30, 101, "5x6")
     gen_episodes(6, 7, 10, 24, 102, "6x7")
     gen_resolve(5, 6, 2500, 300, 201, "5x6")

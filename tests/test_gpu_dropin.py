@@ -413,3 +413,35 @@ def test_host_pipe_equals_device_step(pb, rows, cols, n, zero_copy):
     assert torch.equal(pipe2.buffers[0].reward, r10.cpu()) and torch.equal(pipe2.buffers[1].reward, w11.reward.cpu())
     assert torch.equal(pipe2.buffers[0].state, s10.cpu()) and torch.equal(pipe2.buffers[1].state, ref.state.cpu())
     assert torch.equal(env.state, ref.state)
+
+
+@pytest.mark.parametrize("rows,cols", [(5, 6), (6, 7)])
+def test_reference_rng_mode_replays_the_references_own_episodes(pb, rows, cols):
+    """PAD(rng='reference'): the draws come from Python's global Mersenne Twister in the reference's order, so
+    after the same seeding the facade reproduces whole episodes of the reference -- reset boards, fingers,
+    sampled actions, rewards of passes with skyfall -- and leaves the twister in the same state."""
+    import random
+    z = np.load(os.path.join(G, "mt_episodes.npz"))
+    s = "_%dx%d" % (rows, cols)
+    for e in range(len(z["seed" + s])):
+        clock = [int(z["seed" + s][e])]
+        env = pb.PAD(dim_row=rows, dim_col=cols, rng='reference', clock=lambda: clock[0])
+        assert np.array_equal(env.board, z["init_board" + s][e]) and np.array_equal(env.finger, z["init_finger" + s][e])
+        for t in range(25):
+            a = env.action_space.sample()
+            assert ACTIONS.index(a) == z["actions" + s][e, t], (e, t)
+            env.step(a)
+            assert np.array_equal(env.board, z["boards" + s][e, t]) and np.array_equal(env.finger, z["fingers" + s][e, t])
+        env.step('pass')
+        assert bits(env.rewards[-1]) == bits(z["pass_reward" + s][e])
+        assert bits(env.calculate_reward(board=env.board, skyfall_damage=True)) == bits(z["extra_reward" + s][e])
+        clock[0] += 50
+        board, finger = env.reset()
+        assert np.array_equal(board, z["board2" + s][e]) and np.array_equal(finger, z["finger2" + s][e])
+        for t in range(6):
+            a = env.action_space.sample(include_pass=True)
+            assert ACTIONS.index(a) == z["actions2" + s][e, t]
+            env.step(a)
+        env.step('pass')
+        assert bits(env.rewards[-1]) == bits(z["pass_reward2" + s][e])
+        assert random.random() == z["mt_after" + s][e]
