@@ -10,7 +10,8 @@
  * Conventions
  *   - every pointer is a caller-owned DEVICE pointer unless the name ends in _host;
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls only
- *     enqueue work, they never synchronise;
+ *     enqueue work, they never synchronise (ppad_pipe_wait is the one exception);
+ *   - every call makes the context's device current (cudaSetDevice) and leaves it current;
  *   - return value: 0 = PPAD_OK, otherwise a ppad_status; ppad_strerror() names it and
  *     ppad_last_error() holds the detail (thread-local);
  *   - per-board faults never abort a launch: they are reported in the flags byte of `info`;

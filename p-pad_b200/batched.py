@@ -46,7 +46,8 @@ class BatchedPAD:
         self.step_index = 0
         self.cfg = make_config(dim_row, dim_col, skyfall, skyfall_damage, team, seed, cascade_cap, reset_cap)
         handle = C.c_void_p()
-        _cabi.check(self.lib.ppad_create(C.byref(self.cfg), self.device.index, C.byref(handle)))
+        with torch.cuda.device(self.device):      # the library selects its device; the guard restores torch's
+            _cabi.check(self.lib.ppad_create(C.byref(self.cfg), self.device.index, C.byref(handle)))
         self._ctx = handle
         self.words = state_words(self.dim_row, self.dim_col)
         assert self.lib.ppad_state_bytes(self.dim_row, self.dim_col) == 4 * self.words
@@ -60,7 +61,8 @@ class BatchedPAD:
         other.n = int(n)
         other.env0 = self.env0 if env0 is None else int(env0)
         handle = C.c_void_p()
-        _cabi.check(self.lib.ppad_create(C.byref(self.cfg), self.device.index, C.byref(handle)))
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ppad_create(C.byref(self.cfg), self.device.index, C.byref(handle)))
         other._ctx = handle
         other.state = torch.zeros((other.n, self.words), dtype=torch.int32, device=self.device)
         return other
@@ -438,8 +440,10 @@ class HostPipe:
                 _cabi.check(v.lib.ppad_pipe_wait(self._pipe, int(buf)))
 
     def wait(self, buf=0):
-        _cabi.check(self.venv.lib.ppad_pipe_wait(self._pipe, int(buf)))
+        with torch.cuda.device(self.venv.device):
+            _cabi.check(self.venv.lib.ppad_pipe_wait(self._pipe, int(buf)))
 
     def join(self, buf=0):
         """make torch's current stream wait for the step last enqueued with `buf` (e.g. before reading obs on the device)"""
-        _cabi.check(self.venv.lib.ppad_pipe_join(self._pipe, self.venv._stream(), int(buf)))
+        with torch.cuda.device(self.venv.device):
+            _cabi.check(self.venv.lib.ppad_pipe_join(self._pipe, self.venv._stream(), int(buf)))

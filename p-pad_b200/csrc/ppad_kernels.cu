@@ -1141,6 +1141,8 @@ int ppad_pipe_create(const ppad_ctx *ctx, int64_t n_max, int32_t slab_words_max,
 void ppad_pipe_destroy(ppad_pipe *p)
 {
     if (!p) return;
+    int prev_device = -1;
+    cudaGetDevice(&prev_device);
     cudaSetDevice(p->ctx->device);
     for (int k = 0; k < p->chunks; k++) {
         if (p->streams[k]) {
@@ -1156,6 +1158,7 @@ void ppad_pipe_destroy(ppad_pipe *p)
     cudaFree(p->d_action_out);
     cudaFree(p->d_reward);
     cudaFree(p->d_info);
+    if (prev_device >= 0) cudaSetDevice(prev_device);   // destroy may run from a finaliser: leave the caller's device alone
     delete p;
 }
 
