@@ -227,11 +227,14 @@ struct SkyfallTable {
 
 PPAD_HD int orb_from_u32(const SkyfallTable &t, uint32_t x)
 {
-    int orb = 6;   // host guarantees the last valid type has thr = 0xFFFFFFFF, so this is never kept
+    // thr is non-decreasing and a type with prob 0 repeats its predecessor's threshold, so the first i with
+    // x <= thr[i] is a valid type and equals the NUMBER of thresholds below x -- except for x = 0 when the
+    // leading types have prob 0 (thr = 0): then it is the first valid type.  The host guarantees
+    // thr = 0xFFFFFFFF from the last valid type on, so the count never passes it.
+    int orb = 0;
 #pragma unroll
-    for (int i = 6; i >= 0; i--)
-        if (x <= t.thr[i] && ((t.valid >> i) & 1u)) orb = i;
-    return orb;
+    for (int i = 0; i < 6; i++) orb += x > t.thr[i] ? 1 : 0;
+    return x ? orb : ctz(t.valid);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -326,6 +329,19 @@ struct Tally {
         t2 = colour == 2 ? tr : t2;
         t3 = colour == 3 ? tr : t3;
         t4 = colour == 4 ? tr : t4;
+    }
+    // the same with the colour known at compile time (the colour-major cancel below): no selects at all
+    template <int COLOUR>
+    PPAD_HD void add_c(const TeamTable &team, int N)
+    {
+        n_combos++;
+        if (COLOUR > 4) return;
+        const double f = 1.0 + 0.25 * (double)(N - 3);   // exact
+        double &tr = COLOUR == 0 ? t0 : (COLOUR == 1 ? t1 : (COLOUR == 2 ? t2 : (COLOUR == 3 ? t3 : t4)));
+        constexpr int CI = COLOUR > 4 ? 0 : COLOUR;
+        const int nu = team.n[CI];
+#pragma unroll 1
+        for (int u = 0; u < nu; u++) tr = dadd(tr, dmul(dmul(team.mult[CI][u], f), team.atk[CI][u]));
     }
     // game.py:193-199: every tracker *= 1 + 0.25 (#combos - 1); sum in dict order blue, red,
     // green, dark, light starting from the int 0
@@ -437,6 +453,66 @@ PPAD_HD int cancel_board(Board<G> &b, F &&on_combo)
     return n;
 }
 
+// The cells of orb type COLOUR (bits >= CELLS may be set; AND with a board mask before use).
+template <class G, int COLOUR>
+PPAD_HD typename G::W colour_plane(const Board<G> &b)
+{
+    return ((COLOUR & 1) ? b.b0 : ~b.b0) & ((COLOUR & 2) ? b.b1 : ~b.b1) & ((COLOUR & 4) ? b.b2 : ~b.b2);
+}
+
+// cancel() straight into the reward tally, colour-major: the per-colour trackers of damage() (game.py:163-190)
+// only see the combos of their own colour, so the reference's result depends on the ORDER of combos only
+// within one colour -- and one colour almost always has a single combo per cancel (two need >= 6 matched cells
+// of that colour), which needs no flood fill at all: N = popc(matched & colour).  Colours with >= 6 matched
+// cells are left to one generic loop that peels their islands in the reference's order (utils.py:35-44).
+// m/er/ed are match_mask() of b, m != 0.
+template <class G, int COLOUR>
+PPAD_HD void cancel_colour(const Board<G> &b, typename G::W m, typename G::W &slow, Tally &tally, const TeamTable &team)
+{
+    typedef typename G::W W;
+    const W mc = m & colour_plane<G, COLOUR>(b);
+    const int cnt = popc(mc);
+    if (cnt >= 6) slow |= mc;
+    else if (cnt) tally.add_c<COLOUR>(team, cnt);   // every combo holds >= 3 matched cells: fewer than 6 is ONE island
+}
+
+// With a combo log (parity / debugging; kernel-uniform) every colour takes the generic loop, which then emits the
+// combos in the reference's global order.
+template <class G>
+PPAD_HD void cancel_tally(Board<G> &b, typename G::W m, typename G::W er, typename G::W ed, Tally &tally,
+                          const TeamTable &team, uint16_t *log = nullptr, int log_cap = 0)
+{
+    typedef typename G::W W;
+    W slow = m;
+    if (!log) {
+        slow = 0;
+        cancel_colour<G, 0>(b, m, slow, tally, team);
+        cancel_colour<G, 1>(b, m, slow, tally, team);
+        cancel_colour<G, 2>(b, m, slow, tally, team);
+        cancel_colour<G, 3>(b, m, slow, tally, team);
+        cancel_colour<G, 4>(b, m, slow, tally, team);
+        cancel_colour<G, 5>(b, m, slow, tally, team);
+        cancel_colour<G, 6>(b, m, slow, tally, team);
+    }
+    if (slow) {
+        // usually those cells still form ONE island (an L, T or cross, a run of 6): one flood fill settles it
+        const W first = closure<G>(slow & (~slow + 1), er, ed);
+        W todo = first;
+        if (slow & ~first) todo |= closure<G>(slow & ~first, er, ed);   // all islands that hold those matched cells
+        while (todo) {
+            const W seed = todo & (~todo + 1);      // lowest cell = that island's first cell
+            const W comp = (seed & first) ? first : closure<G>(seed, er, ed);
+            const int colour = code_at<G>(b, ctz(seed)), N = popc(comp & m);
+            if (log && tally.n_combos < log_cap) log[tally.n_combos] = (uint16_t)(colour | (N << 8));
+            tally.add(team, colour, N);
+            todo &= ~comp;
+        }
+    }
+    b.b0 |= m;
+    b.b1 |= m;
+    b.b2 |= m;
+}
+
 // gravity (game.py:201-221): every orb with an empty cell directly below moves down one row,
 // repeated until nothing moves
 template <class G>
@@ -461,6 +537,54 @@ PPAD_HD void fill_board(Board<G> &b, OrbSource &src, const RngKey &key, const Sk
 {
     typedef typename G::W W;
     W e = empties<G>(b);
+    if (e == 0) return;
+    if (src.cursor + popc(e) <= src.n_inj) {
+        // every orb comes from the injected slab: a tight loop over the nibble stream, no source bookkeeping
+        int d = src.cursor;
+        uint32_t word = src.slab[d >> 3] >> (4 * (d & 7));
+        do {
+            const W bit = e & (~e + 1);
+            e ^= bit;
+            // an empty cell has its bit set in all three planes: clear the planes where the code has a 0
+            b.b0 ^= bit & ((W)(word & 1u) - 1);
+            b.b1 ^= bit & ((W)((word >> 1) & 1u) - 1);
+            b.b2 ^= bit & ((W)((word >> 2) & 1u) - 1);
+            d++;
+            word >>= 4;
+            if ((d & 7) == 0 && e) word = src.slab[d >> 3];
+        } while (e);
+        src.cursor = d;
+        src.word_idx = -1;
+        return;
+    }
+    if (src.n_inj < 0) {
+        // pure Philox skyfall: one block per four orbs, the words of a block taken by compile-time index
+        int d = src.cursor;
+        do {
+            U4 c;
+            c.x = key.env_lo;
+            c.y = key.env_hi;
+            c.z = key.step;
+            c.w = (src.stream << 24) | (uint32_t)(d >> 2);
+            const U4 blk = philox4x32_10(c, key.k0, key.k1);
+            const int l0 = d & 3;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (k >= l0 && e) {
+                    const int code = orb_from_u32(sky, k == 0 ? blk.x : (k == 1 ? blk.y : (k == 2 ? blk.z : blk.w)));
+                    const W bit = e & (~e + 1);
+                    e ^= bit;
+                    b.b0 ^= bit & ((W)(code & 1) - 1);
+                    b.b1 ^= bit & ((W)((code >> 1) & 1) - 1);
+                    b.b2 ^= bit & ((W)((code >> 2) & 1) - 1);
+                    d++;
+                }
+            }
+        } while (e);
+        src.cursor = d;
+        src.blk_idx = -1;
+        return;
+    }
     while (e) {
         const W bit = e & (~e + 1);
         const int code = src.next(key, sky);
@@ -528,19 +652,15 @@ struct CascadeItem {
     }
 };
 
-// One iteration of the loop of calculate_reward (game.py:371-397): cancel; stop if nothing matched, if
-// cascades are off or at the cap; else drop and fill.  Returns true when the refilled board matches again.
+// One iteration of the loop of calculate_reward (game.py:371-397), given the match mask m != 0 (and the edge
+// masks) of it.b: cancel; stop if cascades are off or at the cap; else drop, fill and look for matches again.
+// Returns true when the refilled board matches again, with its masks in m / er / ed for the next iteration.
 template <class G>
-PPAD_HD bool cascade_round(CascadeItem<G> &it, bool skyfall_damage, int cascade_cap, const TeamTable &team,
-                           const uint32_t *slab, int n_inj, const RngKey &key, const SkyfallTable &sky, uint16_t *log,
-                           int log_cap)
+PPAD_HD bool cascade_round_m(CascadeItem<G> &it, typename G::W &m, typename G::W &er, typename G::W &ed,
+                             bool skyfall_damage, int cascade_cap, const TeamTable &team, const uint32_t *slab, int n_inj,
+                             const RngKey &key, const SkyfallTable &sky, uint16_t *log, int log_cap)
 {
-    typedef typename G::W W;
-    const int m = cancel_board<G>(it.b, [&](int colour, int N) {
-        if (log && it.tally.n_combos < log_cap) log[it.tally.n_combos] = (uint16_t)(colour | (N << 8));
-        it.tally.add(team, colour, N);
-    });
-    if (m == 0) return false;
+    cancel_tally<G>(it.b, m, er, ed, it.tally, team, log, log_cap);
     it.depth++;
     if (!skyfall_damage) return false;
     if (cascade_cap > 0 && it.depth >= cascade_cap) {
@@ -555,8 +675,20 @@ PPAD_HD bool cascade_round(CascadeItem<G> &it, bool skyfall_damage, int cascade_
     fill_board<G>(it.b, src, key, sky);
     it.cursor = src.cursor;
     it.exhausted = src.exhausted;
-    W er, ed;
-    return match_mask<G>(it.b, er, ed) != 0;
+    m = match_mask<G>(it.b, er, ed);
+    return m != 0;
+}
+
+// The same for a board whose match mask is not at hand (the pooled kernel parks boards between iterations).
+template <class G>
+PPAD_HD bool cascade_round(CascadeItem<G> &it, bool skyfall_damage, int cascade_cap, const TeamTable &team,
+                           const uint32_t *slab, int n_inj, const RngKey &key, const SkyfallTable &sky, uint16_t *log,
+                           int log_cap)
+{
+    typename G::W er, ed;
+    typename G::W m = match_mask<G>(it.b, er, ed);
+    if (m == 0) return false;
+    return cascade_round_m<G>(it, m, er, ed, skyfall_damage, cascade_cap, team, slab, n_inj, key, sky, log, log_cap);
 }
 
 // damage (game.py:157-199) of an explicit combo list: log[i] = colour | N << 8
@@ -858,10 +990,15 @@ PPAD_HD StepOut step_board(bool live, State<G> &s, Board<G> &final_board, const 
     CascadeItem<G> it;
     it.init(s.b, pre.flags);
     bool cascading = live && pre.evaluate;
+    typename G::W m = 0, er = 0, ed = 0;
+    if (cascading) {
+        m = match_mask<G>(it.b, er, ed);
+        cascading = m != 0;
+    }
     while (warp_any(cascading)) {
         if (cascading)
-            cascading = cascade_round<G>(it, p.skyfall_damage != 0, p.cascade_cap, p.team, slab, p.n_inj, key, p.sky,
-                                         log, p.log_cap);
+            cascading = cascade_round_m<G>(it, m, er, ed, p.skyfall_damage != 0, p.cascade_cap, p.team, slab, p.n_inj,
+                                           key, p.sky, log, p.log_cap);
         warp_converge();
     }
 #if defined(__CUDA_ARCH__)

@@ -344,8 +344,15 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
 // behind the stores.  Measured with fp32 obs: 0.159 ms one thread per board, 0.19 ms with this CTA pool,
 // 0.21 ms with a barrier-free per-warp pool (which ties the CTA pool at 0.090 ms without obs).
 // ------------------------------------------------------------------------------------------------
-constexpr int POOL_SLOTS = BLOCK + BLOCK / 2;
-constexpr int POOL_FILL_BELOW = BLOCK / 2;     // fill while pool <= this: pool + BLOCK <= POOL_SLOTS always holds
+#if !defined(PPAD_POOL_BLOCK)
+#define PPAD_POOL_BLOCK 256
+#endif
+#if !defined(PPAD_POOL_MINB)
+#define PPAD_POOL_MINB (1024 / PPAD_POOL_BLOCK)
+#endif
+constexpr int PBLOCK = PPAD_POOL_BLOCK;        // threads per CTA of the pooled kernel
+constexpr int POOL_SLOTS = PBLOCK + PBLOCK / 2;
+constexpr int POOL_FILL_BELOW = PBLOCK / 2;    // fill while pool <= this: pool + PBLOCK <= POOL_SLOTS always holds
 
 template <class G>
 struct CascadePool {
@@ -354,7 +361,7 @@ struct CascadePool {
     uint32_t counts[POOL_SLOTS];   // n_combos [0,16) | depth [16,24) | flags [24,32)
     uint32_t source[POOL_SLOTS];   // skyfall cursor [0,16) | injected slab exhausted [16]
     uint64_t owner[POOL_SLOTS];    // board index within the launch
-    int warp_count[BLOCK / 32];
+    int warp_count[2][PBLOCK / 32];   // double buffered: consecutive compactions alternate, one barrier each
 
     __device__ __forceinline__ void put(int slot, const CascadeItem<G> &it, uint64_t own)
     {
@@ -389,43 +396,45 @@ struct CascadePool {
         it.exhausted = (q >> 16) & 1u;
         return owner[slot];
     }
-    // CTA-wide stable compaction (two __syncthreads; every thread must call it)
-    __device__ __forceinline__ int compact(bool keep, int &total)
+    // CTA-wide stable compaction (ONE __syncthreads; every thread must call it, `phase` alternates 0/1 from call
+    // to call: the counts of call k live in buffer k & 1, and call k + 2 can only overwrite them after every thread
+    // has passed the barrier of call k + 1, i.e. has finished reading them)
+    __device__ __forceinline__ int compact(bool keep, int &total, int phase)
     {
         const unsigned ballot = __ballot_sync(0xFFFFFFFFu, keep);
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        if (lane == 0) warp_count[warp] = __popc(ballot);
+        if (lane == 0) warp_count[phase][warp] = __popc(ballot);
         __syncthreads();
         int base = 0, sum = 0;
 #pragma unroll
-        for (int w = 0; w < BLOCK / 32; w++) {
-            const int c = warp_count[w];
+        for (int w = 0; w < PBLOCK / 32; w++) {
+            const int c = warp_count[phase][w];
             if (w < warp) base += c;
             sum += c;
         }
         total = sum;
-        __syncthreads();
         return base + __popc(ballot & ((1u << lane) - 1u));
     }
 };
 
 template <class G>
-__global__ void __launch_bounds__(BLOCK, 4) step_pool_kernel(const __grid_constant__ StepKernelArgs a)
+__global__ void __launch_bounds__(PBLOCK, PPAD_POOL_MINB) step_pool_kernel(const __grid_constant__ StepKernelArgs a)
 {
     __shared__ CascadePool<G> pool;
     typedef typename G::W W;
     const int tid = threadIdx.x;
-    const int64_t n_tiles = (a.n + BLOCK - 1) / BLOCK;
+    const int64_t n_tiles = (a.n + PBLOCK - 1) / PBLOCK;
     const bool sd = a.p.skyfall_damage != 0;
     int64_t tile = blockIdx.x;
     int pool_count = 0;                          // CTA-uniform
+    int phase = 0;                               // CTA-uniform: which count buffer the next compaction uses
 
     for (;;) {
         // ---- fill: the convergent part of the step for one fresh tile, when the pool is low
         const bool fill = tile < n_tiles && pool_count <= POOL_FILL_BELOW;
         if (!fill && pool_count == 0) break;    // no tiles left (pool_count == 0 <= POOL_FILL_BELOW) and pool drained
         if (fill) {
-            const int64_t i = tile * BLOCK + tid;
+            const int64_t i = tile * PBLOCK + tid;
             const bool valid = i < a.n;
             State<G> s;
             CascadeItem<G> it;
@@ -473,15 +482,16 @@ __global__ void __launch_bounds__(BLOCK, 4) step_pool_kernel(const __grid_consta
                 }
             }
             int added;
-            const int slot = pool.compact(cascading, added);
+            const int slot = pool.compact(cascading, added, phase);
+            phase ^= 1;
             if (cascading) pool.put(pool_count + slot, it, (uint64_t)i);
             pool_count += added;
             tile += gridDim.x;
-            __syncthreads();                      // every put() of the fill is visible
         }
+        __syncthreads();                          // every put() of this fill and of the previous round is visible
 
         // ---- round: one cascade iteration for the top m boards of the pool, on dense warps
-        const int m = pool_count < BLOCK ? pool_count : BLOCK;
+        const int m = pool_count < PBLOCK ? pool_count : PBLOCK;
         const int base = pool_count - m;
         CascadeItem<G> it;
         uint64_t own = 0;
@@ -501,10 +511,10 @@ __global__ void __launch_bounds__(BLOCK, 4) step_pool_kernel(const __grid_consta
 
         if (m > 0) {                             // CTA-uniform
             int survivors;
-            const int slot = pool.compact(again, survivors);   // its first barrier: every get() of the round is done
-            if (again) pool.put(base + slot, it, own);
+            const int slot = pool.compact(again, survivors, phase);   // its barrier: every get() of the round is done
+            phase ^= 1;
+            if (again) pool.put(base + slot, it, own);   // read again only after the barrier at the top of the round
             pool_count = base + survivors;
-            __syncthreads();
         }
     }
 }
@@ -907,7 +917,7 @@ int ppad_create(const ppad_config *cfg, int device, ppad_ctx **out)
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaSetDevice(device);
     ctx->pool_ctas_per_sm = 0;
-    PPAD_DISPATCH(ctx, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->pool_ctas_per_sm, step_pool_kernel<G>, BLOCK, 0)));
+    PPAD_DISPATCH(ctx, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->pool_ctas_per_sm, step_pool_kernel<G>, PBLOCK, 0)));
     if (ctx->pool_ctas_per_sm <= 0) ctx->pool_ctas_per_sm = 1;
     *out = ctx;
     return PPAD_OK;
@@ -1029,10 +1039,10 @@ static int launch_step(const ppad_ctx *ctx, const ppad_step_args *args, cudaStre
         return after_launch("step_obs_kernel<no obs>");
     }
     // persistent: one wave of CTAs, as many as fit
-    const int64_t tiles = (a.n + BLOCK - 1) / BLOCK;
+    const int64_t tiles = (a.n + PBLOCK - 1) / PBLOCK;
     int64_t grid = (int64_t)ctx->sm_count * ctx->pool_ctas_per_sm;
     if (grid > tiles) grid = tiles;
-    PPAD_DISPATCH(ctx, (step_pool_kernel<G><<<(unsigned)grid, BLOCK, 0, st>>>(a)));
+    PPAD_DISPATCH(ctx, (step_pool_kernel<G><<<(unsigned)grid, PBLOCK, 0, st>>>(a)));
     return after_launch("step_pool_kernel");
 }
 

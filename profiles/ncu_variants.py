@@ -3,6 +3,8 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import ppad_b200
+if os.environ.get('PPAD_AB_LIB'):   # profile a variant built by profiles/build_variant.sh
+    ppad_b200._cabi.LIB_PATH = os.path.abspath(os.environ['PPAD_AB_LIB'])
 
 n = 1 << 20
 env = ppad_b200.BatchedPAD(n, 5, 6, seed=1)

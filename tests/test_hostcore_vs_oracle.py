@@ -201,10 +201,9 @@ def test_sky_thresholds_match_float_rule():
         cfg = hc.cfg_from_oracle(orc.make_cfg(skyfall=p))
         thr, valid = hc.sky_table(cfg)
         assert valid == sum(1 << j for j in range(7) if p[j] > 0)
-        for j in range(0, len(z["xs"]), 7):
-            assert hc.orb_from_u32(cfg, int(z["xs"][j])) == z["orbs"][i, j]
-        for j in range(len(z["xs"]) - 80, len(z["xs"])):   # the threshold neighbours
-            assert hc.orb_from_u32(cfg, int(z["xs"][j])) == z["orbs"][i, j]
+        assert (z["xs"] == 0).any()                          # x = 0 with leading zero rates is the special case
+        for j in range(len(z["xs"])):                        # random draws, 0, 2^32 - 1 and the threshold neighbours
+            assert hc.orb_from_u32(cfg, int(z["xs"][j])) == z["orbs"][i, j], (i, j)
 
 
 def test_philox_matches_oracle():
