@@ -232,8 +232,11 @@ struct StepKernelArgs {
 // stream, and keeping all eight warps of a CTA busy (each runs its own boards' cascades in a warp-uniform
 // loop, then emits its observation) overlaps the stores with the integer work best: measured 0.159 ms per
 // 2^20-board step against 0.162-0.166 ms for packing the cascades once and 0.19 ms for the pooled kernel.
+// Four resident CTAs per SM (64 registers) is the measured optimum with fp32 obs: 0.1546 ms against 0.1556 (3),
+// 0.1875 (2), 0.1685 (5, spills) and 0.1731 (6).  Emitting the observation before the cascades (0.167 ms), or
+// before them in the odd warps and after them in the even warps (0.156 ms), is not faster either.
 template <class G, bool OBS>
-__global__ void __launch_bounds__(BLOCK) step_obs_kernel(const __grid_constant__ StepKernelArgs a)
+__global__ void __launch_bounds__(BLOCK, 4) step_obs_kernel(const __grid_constant__ StepKernelArgs a)
 {
     __shared__ ObsShared obs_sh;
     __shared__ uint32_t obs_stream[OBS ? (BLOCK / 32) * ObsGeom<G>::WARP_WORDS : 1];
