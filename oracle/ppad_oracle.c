@@ -271,7 +271,8 @@ int ppad_oracle_sample_action(uint64_t seed, uint64_t env, uint32_t step, int le
     int n = 0;
     for (int a = 0; a < 4; a++) n += (legal_mask >> a) & 1;
     if (n == 0) return -1;
-    const uint32_t x = ppad_oracle_draw(seed, env, step, PPAD_OR_STREAM_ACTION, 0);
+    /* word step & 3 of the block (env, step >> 2, ACTION): four consecutive steps share one Philox block */
+    const uint32_t x = ppad_oracle_draw(seed, env, step >> 2, PPAD_OR_STREAM_ACTION, step & 3u);
     int pick = (int)(((uint64_t)x * (uint64_t)n) >> 32);
     for (int a = 0; a < 4; a++)
         if ((legal_mask >> a) & 1) {

@@ -21,8 +21,10 @@
 
 #if defined(__CUDACC__)
 #define PPAD_HD __host__ __device__ __forceinline__
+#define PPAD_TIGHT_DEFAULT false
 #else
 #define PPAD_HD inline
+#define PPAD_TIGHT_DEFAULT true   // the host build (tests/hostcore) fuzzes the unrolled Philox refill
 #endif
 
 namespace ppad {
@@ -215,6 +217,23 @@ PPAD_HD uint32_t philox_draw(const RngKey &k, uint32_t stream, uint32_t d)
     const U4 o = philox4x32_10(c, k.k0, k.k1);
     const uint32_t l = d & 3u;
     return l == 0 ? o.x : (l == 1 ? o.y : (l == 2 ? o.z : o.w));
+}
+
+// The random policy's draw of (env, step): word step & 3 of the block (env, step >> 2, ACTION stream).  Four
+// consecutive steps share one Philox block, which a fused multi-step rollout computes once for all four.
+PPAD_HD U4 action_block(const RngKey &k)
+{
+    U4 c;
+    c.x = k.env_lo;
+    c.y = k.env_hi;
+    c.z = k.step >> 2;
+    c.w = STREAM_ACTION << 24;
+    return philox4x32_10(c, k.k0, k.k1);
+}
+PPAD_HD uint32_t action_word(const U4 &b, uint32_t step)
+{
+    const uint32_t l = step & 3u;
+    return l == 0 ? b.x : (l == 1 ? b.y : (l == 2 ? b.z : b.w));
 }
 
 // Categorical skyfall draw.  game.py:458-470 returns the first i with cumsum(prob)[i] >= u and
@@ -595,17 +614,47 @@ PPAD_HD void fill_board(Board<G> &b, OrbSource &src, const RngKey &key, const Sk
     }
 }
 
-// fill_board(reset=True): every cell gets a draw, row-major
-template <class G>
+// fill_board(reset=True): every cell gets a draw, row-major.  TIGHT adds the unrolled pure-Philox loop: it pays
+// in the kernels that reset all the time (rollout, reset: 0.49 -> 0.29 ms per 2^20 boards) but its code size
+// slows the step kernels down (0.080 -> 0.087 ms) even though they rarely reset, so they do without it.
+template <class G, bool TIGHT = PPAD_TIGHT_DEFAULT>
 PPAD_HD void refill_all(Board<G> &b, OrbSource &src, const RngKey &key, const SkyfallTable &sky)
 {
     typedef typename G::W W;
     W p0 = 0, p1 = 0, p2 = 0;
-    for (int i = 0; i < G::CELLS; i++) {
-        const int code = src.next(key, sky);
-        p0 |= (W)(code & 1) << i;
-        p1 |= (W)((code >> 1) & 1) << i;
-        p2 |= (W)((code >> 2) & 1) << i;
+    if (TIGHT && src.n_inj < 0) {
+        // pure Philox (the auto-reset of rollouts): one block per four draws, words taken by compile-time index
+        const uint32_t blk0 = (uint32_t)src.cursor >> 2;
+        const int l0 = src.cursor & 3;             // the first block may start in the middle
+        const int nblk = (l0 + G::CELLS + 3) / 4;
+#pragma unroll 2
+        for (int q = 0; q < nblk; q++) {
+            U4 c;
+            c.x = key.env_lo;
+            c.y = key.env_hi;
+            c.z = key.step;
+            c.w = (src.stream << 24) | (blk0 + (uint32_t)q);
+            const U4 blk = philox4x32_10(c, key.k0, key.k1);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int i = 4 * q + k - l0;
+                if (i >= 0 && i < G::CELLS) {
+                    const int code = orb_from_u32(sky, k == 0 ? blk.x : (k == 1 ? blk.y : (k == 2 ? blk.z : blk.w)));
+                    p0 |= (W)(code & 1) << i;
+                    p1 |= (W)((code >> 1) & 1) << i;
+                    p2 |= (W)((code >> 2) & 1) << i;
+                }
+            }
+        }
+        src.cursor += G::CELLS;
+        src.blk_idx = -1;
+    } else {
+        for (int i = 0; i < G::CELLS; i++) {
+            const int code = src.next(key, sky);
+            p0 |= (W)(code & 1) << i;
+            p1 |= (W)((code >> 1) & 1) << i;
+            p2 |= (W)((code >> 2) & 1) << i;
+        }
     }
     b.b0 = p0;
     b.b1 = p1;
@@ -738,22 +787,14 @@ PPAD_HD int sample_from_mask(int mask, uint32_t x)
 template <class G>
 PPAD_HD bool apply_move(State<G> &s, int action)
 {
+    // straight-line: up = row - 1, down = row + 1, left = col - 1, right = col + 1 (game.py:127-155)
     const int f = meta_finger(s.meta);
     const int r = f / G::C, c = f - r * G::C;
-    int t;
-    if (action == ACT_UP) {
-        if (r - 1 < 0) return false;
-        t = f - G::C;
-    } else if (action == ACT_DOWN) {
-        if (r + 1 > G::R - 1) return false;
-        t = f + G::C;
-    } else if (action == ACT_LEFT) {
-        if (c - 1 < 0) return false;
-        t = f - 1;
-    } else {
-        if (c + 1 > G::C - 1) return false;
-        t = f + 1;
-    }
+    const int dr = (action == ACT_DOWN ? 1 : 0) - (action == ACT_UP ? 1 : 0);
+    const int dc = (action == ACT_RIGHT ? 1 : 0) - (action == ACT_LEFT ? 1 : 0);
+    const int nr = r + dr, nc = c + dc;
+    if ((unsigned)nr >= (unsigned)G::R || (unsigned)nc >= (unsigned)G::C) return false;
+    const int t = nr * G::C + nc;
     swap_cells<G>(s.b, f, t);
     int moves = meta_moves(s.meta);
     if (moves < 0xFFFF) moves++;
@@ -818,7 +859,8 @@ struct StepPrefix {
 // Everything of one env step except the cascade: pick the action, apply the move, decide whether the
 // board is evaluated.  `s` is updated in place (a pass leaves it alone, game.py:366).
 template <class G>
-PPAD_HD StepPrefix step_prefix(State<G> &s, const StepParams &p, const RngKey &key, int action_in)
+PPAD_HD StepPrefix step_prefix(State<G> &s, const StepParams &p, const RngKey &key, int action_in,
+                               const U4 *act_blk = nullptr)   // action_block(key) if the caller has it at hand
 {
     StepPrefix o;
     o.flags = 0;
@@ -829,7 +871,7 @@ PPAD_HD StepPrefix step_prefix(State<G> &s, const StepParams &p, const RngKey &k
             action = ACT_PASS;   // episode length cap (simulation.py:50-52)
         } else {
             action = sample_from_mask(legal_mask<G>(meta_finger(s.meta), meta_prev(s.meta)),
-                                      philox_draw(key, STREAM_ACTION, 0));
+                                      action_word(act_blk ? *act_blk : action_block(key), key.step));
             if (action < 0) {
                 action = 255;
                 o.flags |= FLAG_NO_LEGAL_MOVE;
@@ -893,7 +935,7 @@ PPAD_HD RngKey board_key(const StepParams &p, uint64_t env)
 // a board and try consecutive attempt indices speculatively; per board the accepted attempt with the LOWEST
 // index wins, which is exactly the one the sequential loop of game.py:303-308 would have stopped at -- same
 // board, same number of orbs consumed.  Typically 3-4 warp iterations instead of ~10.
-template <class G>
+template <class G, bool TIGHT = false>
 __device__ __forceinline__ uint32_t reset_boards_warp(bool need, State<G> &s, const StepParams &p, uint32_t step,
                                                       uint64_t env, const uint32_t *slab, int n_inj, int finger_in,
                                                       int *consumed_out)
@@ -926,7 +968,7 @@ __device__ __forceinline__ uint32_t reset_boards_warp(bool need, State<G> &s, co
             src.cursor = att * G::CELLS;
             RngKey key_o = board_key(p, env_o);
             key_o.step = step;
-            refill_all<G>(b, src, key_o, p.sky);
+            refill_all<G, TIGHT>(b, src, key_o, p.sky);
             W er, ed;
             ok = match_mask<G>(b, er, ed) == 0;
         }
@@ -974,10 +1016,10 @@ __device__ __forceinline__ uint32_t reset_boards_warp(bool need, State<G> &s, co
 // The whole step of one board.  On the GPU EVERY lane of the warp must call this (lanes past the end of the
 // batch pass live = false): the cascade loop is warp-uniform -- it runs while any lane still cascades and
 // the lanes reconverge after every iteration.
-template <class G>
+template <class G, bool TIGHT_RESET = false>
 PPAD_HD StepOut step_board(bool live, State<G> &s, Board<G> &final_board, const StepParams &p, uint64_t env,
                            int action_in, const uint32_t *slab, uint16_t *log, const uint32_t *path = nullptr,
-                           int path_len = 0, uint32_t step_offset = 0)
+                           int path_len = 0, uint32_t step_offset = 0, const U4 *act_blk = nullptr)
 {
     RngKey key = board_key(p, env);
     key.step += step_offset;   // fused multi-step rollouts: step index = p.key.step + t
@@ -985,7 +1027,7 @@ PPAD_HD StepOut step_board(bool live, State<G> &s, Board<G> &final_board, const 
     pre.action = 255;
     pre.flags = 0;
     pre.evaluate = false;
-    if (live) pre = path ? path_prefix<G>(s, p, path, path_len) : step_prefix<G>(s, p, key, action_in);
+    if (live) pre = path ? path_prefix<G>(s, p, path, path_len) : step_prefix<G>(s, p, key, action_in, act_blk);
     warp_converge();
     CascadeItem<G> it;
     it.init(s.b, pre.flags);
@@ -1004,7 +1046,7 @@ PPAD_HD StepOut step_board(bool live, State<G> &s, Board<G> &final_board, const 
 #if defined(__CUDA_ARCH__)
     if (p.auto_reset) {   // kernel-uniform
         const bool need = live && pre.action == ACT_PASS;
-        const uint32_t f = reset_boards_warp<G>(need, s, p, key.step, env, nullptr, -1, -1, nullptr);
+        const uint32_t f = reset_boards_warp<G, TIGHT_RESET>(need, s, p, key.step, env, nullptr, -1, -1, nullptr);
         if (need) it.flags |= FLAG_EPISODE_DONE | f;
     }
 #else

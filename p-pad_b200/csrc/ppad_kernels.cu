@@ -309,10 +309,17 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
     if (valid) s = StateIO<G>::load(a.state, i);
     double reward_sum = 0.0;
     uint32_t episodes = 0, combos = 0, flags = 0;
+    U4 act_blk = {0, 0, 0, 0};
     for (int t = 0; t < a.steps; t++) {          // every lane runs every step: the cascade loop is warp-uniform
         Board<G> fin;
-        const StepOut o = step_board<G>(valid, s, fin, a.p, a.env0 + (uint64_t)i, -1, nullptr, nullptr, nullptr, 0,
-                                        (uint32_t)t);
+        const uint32_t step = a.p.key.step + (uint32_t)t;
+        if (t == 0 || (step & 3u) == 0) {        // one Philox block holds the action draws of four steps
+            RngKey key = board_key(a.p, a.env0 + (uint64_t)i);
+            key.step = step;
+            act_blk = action_block(key);
+        }
+        const StepOut o = step_board<G, true>(valid, s, fin, a.p, a.env0 + (uint64_t)i, -1, nullptr, nullptr, nullptr,
+                                              0, (uint32_t)t, &act_blk);
         reward_sum = ppad::dadd(reward_sum, o.reward);
         episodes += (o.info >> 31) & 1u;         // FLAG_EPISODE_DONE
         combos += o.info & 0xFFu;
@@ -565,7 +572,7 @@ __global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ Re
     s.b.b0 = s.b.b1 = s.b.b2 = 0;
     s.meta = 0;
     int consumed = 0;
-    const uint32_t flags = reset_boards_warp<G>(valid, s, a.p, a.p.key.step, a.env0 + (uint64_t)i,
+    const uint32_t flags = reset_boards_warp<G, true>(valid, s, a.p, a.p.key.step, a.env0 + (uint64_t)i,
                                                 a.slab && valid ? a.slab + (size_t)i * a.p.slab_words : nullptr,
                                                 a.p.n_inj, finger, &consumed);
     if (!valid) return;
@@ -645,7 +652,7 @@ __global__ void __launch_bounds__(BLOCK) sample_kernel(int64_t n, uint64_t env0,
     int mask = legal_mask<G>(meta_finger(s.meta), meta_prev(s.meta));
     // with include_pass the reference rejects 'pass' right after a pass / reset (player.py:52-53)
     if (include_pass && meta_prev(s.meta) != ACT_PASS) mask |= 16;
-    const int a = sample_from_mask(mask, philox_draw(key, STREAM_ACTION, 0));
+    const int a = sample_from_mask(mask, action_word(action_block(key), key.step));
     actions[i] = (uint8_t)(a < 0 ? 255 : a);
 }
 
