@@ -21,9 +21,11 @@
 
 #if defined(__CUDACC__)
 #define PPAD_HD __host__ __device__ __forceinline__
+#define PPAD_HDC __host__ __device__ constexpr
 #define PPAD_TIGHT_DEFAULT false
 #else
 #define PPAD_HD inline
+#define PPAD_HDC constexpr
 #define PPAD_TIGHT_DEFAULT true   // the host build (tests/hostcore) fuzzes the unrolled Philox refill
 #endif
 
@@ -766,21 +768,35 @@ PPAD_HD int legal_mask(int finger, int prev)
     return m;
 }
 
+// index of the pick-th set bit of a 4-bit mask, as a table of 16 masks x 4 picks x 2 bits in four words
+PPAD_HDC uint32_t nth_bit_lut_word(int w)
+{
+    uint32_t v = 0;
+    for (int e = 0; e < 16; e++) {                 // entry 16 w + e = mask * 4 + pick
+        const int mask = (16 * w + e) >> 2, pick = (16 * w + e) & 3;
+        int seen = 0, a = 0;
+        for (int i = 0; i < 4; i++)
+            if ((mask >> i) & 1) {
+                if (seen == pick) a = i;
+                seen++;
+            }
+        v |= (uint32_t)a << (2 * e);
+    }
+    return v;
+}
+
 // uniform over the legal set (bits 0..4; bit 4 = pass when the caller allows it), one Philox draw
-// (stream ACTION, draw 0); -1 when the set is empty
+// (the action stream's word of this step); -1 when the set is empty
 PPAD_HD int sample_from_mask(int mask, uint32_t x)
 {
+    constexpr uint32_t L0 = nth_bit_lut_word(0), L1 = nth_bit_lut_word(1), L2 = nth_bit_lut_word(2), L3 = nth_bit_lut_word(3);
     const int n = popc((uint32_t)mask);
     if (n == 0) return -1;
-    int pick = (int)mulhi32(x, (uint32_t)n);
-    int a = -1;
-#pragma unroll
-    for (int i = 0; i < 5; i++) {
-        const bool on = (mask >> i) & 1;
-        if (on && pick == 0 && a < 0) a = i;
-        if (on) pick--;
-    }
-    return a;
+    const int pick = (int)mulhi32(x, (uint32_t)n);
+    if ((mask & 16) && pick == n - 1) return ACT_PASS;   // pass is the highest bit, so the last pick
+    const int e = (mask & 15) * 4 + pick;                  // pick <= 3 here
+    const uint32_t w = (e & 32) ? ((e & 16) ? L3 : L2) : ((e & 16) ? L1 : L0);
+    return (int)((w >> (2 * (e & 15))) & 3u);
 }
 
 // apply_action (game.py:122-155): false = 'rejected' (off the board), state untouched
@@ -1029,6 +1045,15 @@ PPAD_HD StepOut step_board(bool live, State<G> &s, Board<G> &final_board, const 
     pre.evaluate = false;
     if (live) pre = path ? path_prefix<G>(s, p, path, path_len) : step_prefix<G>(s, p, key, action_in, act_blk);
     warp_converge();
+    if (!warp_any(live && (pre.evaluate || pre.action == ACT_PASS))) {
+        // a plain move for the whole warp (episode mode: 50 of 51 steps): no cascade, no reset, nothing to tally
+        final_board = s.b;
+        StepOut quick;
+        quick.action = pre.action;
+        quick.reward = 0.0;
+        quick.info = make_info(0, 0, 0, pre.flags);
+        return quick;
+    }
     CascadeItem<G> it;
     it.init(s.b, pre.flags);
     bool cascading = live && pre.evaluate;
