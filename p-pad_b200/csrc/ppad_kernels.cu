@@ -226,6 +226,7 @@ struct StepKernelArgs {
     const uint32_t *paths;
     const uint16_t *path_lens;
     int32_t path_words, path_len;
+    int32_t stage_slab;   // 1: the slab is pinned HOST memory (zero copy), 4 words per board: fetch each row once, up front
 };
 
 // The step WITH the one-hot observation, one thread per board.  This variant is bound by the 840 B/board store
@@ -261,10 +262,22 @@ __global__ void __launch_bounds__(BLOCK, 4) step_obs_kernel(const __grid_constan
             path_len = path_len > 16 * a.path_words ? 16 * a.path_words : path_len;
         }
     }
+    const uint32_t *slab = a.slab && valid ? a.slab + (size_t)i * a.p.slab_words : nullptr;
+    __shared__ uint4 slab_rows[BLOCK];
+    if (a.stage_slab) {   // kernel-uniform
+        // Zero copy: the skyfall slab lives in pinned host memory.  The cascade reads its words lazily, which over
+        // PCIe is one 4-byte round trip per lane and cascade iteration; fetch the board's whole 16-byte row once
+        // instead (512 contiguous bytes per warp, in flight together with the state load) and let the cascade read
+        // it from shared memory.
+        if (slab) {
+            slab_rows[threadIdx.x] = __ldg(reinterpret_cast<const uint4 *>(slab));
+            slab = reinterpret_cast<const uint32_t *>(&slab_rows[threadIdx.x]);
+        }
+        __syncwarp();
+    }
     // every lane takes part (the cascade loop inside is warp-uniform); lanes past the batch are not live
     Board<G> fin;
-    const StepOut o = step_board<G>(valid, s, fin, a.p, a.env0 + (uint64_t)i, action,
-                                    a.slab && valid ? a.slab + (size_t)i * a.p.slab_words : nullptr,
+    const StepOut o = step_board<G>(valid, s, fin, a.p, a.env0 + (uint64_t)i, action, slab,
                                     a.combo_log && valid ? a.combo_log + (size_t)i * a.p.log_cap : nullptr,
                                     a.paths && valid ? a.paths + (size_t)i * a.path_words : nullptr, path_len);
     if (valid) {
@@ -998,7 +1011,8 @@ int ppad_reset(const ppad_ctx *ctx, int64_t n, uint64_t env0, uint32_t step, con
     return after_launch("reset_kernel");
 }
 
-static int launch_step(const ppad_ctx *ctx, const ppad_step_args *args, cudaStream_t st, bool coalesced_results = false)
+static int launch_step(const ppad_ctx *ctx, const ppad_step_args *args, cudaStream_t st, bool coalesced_results = false,
+                       bool stage_host_slab = false)
 {
     if (!args->state) return fail(PPAD_ERR_INVALID, "ppad_step: null state");
     if (args->slab && (args->slab_words <= 0 || args->n_inj < 0 || args->n_inj > args->slab_words * 8))
@@ -1038,6 +1052,7 @@ static int launch_step(const ppad_ctx *ctx, const ppad_step_args *args, cudaStre
     a.path_len = args->path_len;
     if (a.paths && (a.path_words <= 0 || a.path_len < 0))
         return fail(PPAD_ERR_INVALID, "ppad_step: paths need path_words > 0 and path_len >= 0");
+    a.stage_slab = (stage_host_slab && a.slab && a.p.slab_words == 4 && ((uintptr_t)a.slab & 15) == 0) ? 1 : 0;
     if (args->obs) {
         PPAD_DISPATCH(ctx, (step_obs_kernel<G, true><<<grid_for(a.n), BLOCK, 0, st>>>(a)));
         return after_launch("step_obs_kernel");
@@ -1237,7 +1252,7 @@ int ppad_pipe_step(ppad_pipe *p, const ppad_host_step_args *h, void *after_strea
         a.state_copy = h->state_out_host;
         a.obs = h->obs;
         a.obs_dtype = h->obs_dtype;
-        if (int r = launch_step(ctx, &a, st, true)) return r;
+        if (int r = launch_step(ctx, &a, st, true, true)) return r;
         for (int k = 0; k < p->chunks && e == cudaSuccess; k++) e = cudaEventRecord(p->done[slot][k], st);
         return cuda_check(e, "ppad_pipe_step");
     }
