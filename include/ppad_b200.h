@@ -17,11 +17,16 @@
  *   - per-board faults never abort a launch: they are reported in the flags byte of `info`;
  *   - there is NO CPU path: without a CUDA device every compute entry point returns PPAD_ERR_CUDA.
  *
- * Packed state record ("state"), one per board, ppad_state_bytes(rows, cols) bytes:
- *   5x6 (<= 32 cells): uint32 b0, b1, b2, meta                    (16 B, one uint4)
- *   6x7 (<= 64 cells): uint64 b0, b1, b2; uint32 meta, reserved   (32 B, two uint4)
+ * Packed state record ("state"), one per board, ppad_state_bytes_ex(rows, cols, orb_bits) bytes:
+ *   orb_bits = 3 (default: orb types 0..6, everything the default skyfall of parameters.py:43 produces)
+ *     5x6 (<= 32 cells): uint32 b0, b1, b2, meta                    (16 B, one uint4)
+ *     6x7 (<= 64 cells): uint64 b0, b1, b2; uint32 meta, reserved   (32 B, two uint4)
+ *     codes 0..6 = red, blue, green, light, dark, heal, jammer (game.py:236-246), 7 = empty (-1);
+ *   orb_bits = 4 (all ten orb types of game.py:236-246: + 7 poison, 8 mortal poison, 9 bomb)
+ *     5x6: uint32 b0, b1, b2, b3, meta, 3 x reserved                (32 B)
+ *     6x7: uint64 b0, b1, b2, b3; uint32 meta, 3 x reserved         (48 B)
+ *     codes 0..9 = the reference's orb types, 15 = empty (-1);
  *   bit i of plane bj = bit j of the orb code of cell i = row * cols + col;
- *   codes 0..6 = red, blue, green, light, dark, heal, jammer (game.py:236-246), 7 = empty (-1);
  *   meta = finger cell [0,6) | previous action [6,9) (4 = 'pass') | accepted moves this episode [9,25).
  */
 #ifndef PPAD_B200_H
@@ -32,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PPAD_ABI_VERSION 1
+#define PPAD_ABI_VERSION 2
 #define PPAD_MAX_TEAM_UNITS 8
 
 typedef enum ppad_status {
@@ -53,7 +58,7 @@ enum {
     PPAD_FLAG_NO_LEGAL_MOVE = 0x08,     /* random policy found an empty legal set */
     PPAD_FLAG_BAD_ACTION = 0x10,        /* action id outside 0..4 */
     PPAD_FLAG_RESET_CAP = 0x20,         /* reset gave up after cfg.reset_cap attempts */
-    PPAD_FLAG_UNSUPPORTED_ORB = 0x40,   /* pack saw a value outside -1..6 (stored as empty) */
+    PPAD_FLAG_UNSUPPORTED_ORB = 0x40,   /* pack saw a value outside -1..6 (orb_bits 3) / -1..9 (orb_bits 4): stored as empty */
     PPAD_FLAG_EPISODE_DONE = 0x80       /* a pass was processed and the board auto-reset */
 };
 
@@ -76,8 +81,10 @@ typedef struct ppad_config {
     int32_t team_color_1[PPAD_MAX_TEAM_UNITS];   /* orb type 0..4, or -1 for None */
     int32_t team_color_2[PPAD_MAX_TEAM_UNITS];
     double  team_atk[PPAD_MAX_TEAM_UNITS];
-    double  skyfall[10];             /* game.py:42, parameters.py:43; types 7..9 must have rate 0 */
+    double  skyfall[10];             /* game.py:42, parameters.py:43; types 7..9 need orb_bits = 4 */
     uint64_t seed;                   /* Philox4x32-10 key (replaces random.seed(datetime.now()), game.py:72,302) */
+    int32_t orb_bits;                /* 0 or 3: 3-bit orb codes (types 0..6); 4: 4-bit codes (types 0..9) */
+    int32_t reserved;
 } ppad_config;
 
 typedef struct ppad_ctx ppad_ctx;   /* immutable after creation; usable from any stream of its device */
@@ -90,7 +97,8 @@ void ppad_destroy(ppad_ctx *ctx);
 int ppad_abi_version(void);
 const char *ppad_strerror(int status);
 const char *ppad_last_error(void);
-int64_t ppad_state_bytes(int rows, int cols);
+int64_t ppad_state_bytes(int rows, int cols);                       /* orb_bits = 3 */
+int64_t ppad_state_bytes_ex(int rows, int cols, int orb_bits);     /* -1: no such geometry */
 /* kernels launched by this library since load (all contexts, all threads) */
 uint64_t ppad_launch_count(void);
 
@@ -237,7 +245,8 @@ int ppad_damage(const ppad_ctx *ctx, int64_t n, const uint16_t *combo_log, int32
 /* ---- the callers either side of the env step ---------------------------- */
 
 /* permutation_mapping (smart_data.py:94-108) in place: maps [n, 8] uint8, orb type t -> maps[i][t] (t = 0..6;
- * empty cells stay empty; byte 7 is padding) */
+ * empty cells stay empty; byte 7 is padding; with orb_bits = 4 the types 7..9 keep their value -- the reference
+ * only ever permutes allowed_orbs = 0..5, solved_boards.py:25) */
 int ppad_permute(const ppad_ctx *ctx, int64_t n, void *state, const uint8_t *maps, void *stream);
 
 typedef enum ppad_select_method { PPAD_SELECT_MAX = 0, PPAD_SELECT_BOLTZMANN = 1 } ppad_select_method;

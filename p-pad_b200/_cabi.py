@@ -21,7 +21,8 @@ class Config(C.Structure):
     _fields_ = [("rows", C.c_int32), ("cols", C.c_int32), ("skyfall_damage", C.c_int32),
                 ("cascade_cap", C.c_int32), ("reset_cap", C.c_int32), ("team_size", C.c_int32),
                 ("team_color_1", C.c_int32 * MAX_TEAM_UNITS), ("team_color_2", C.c_int32 * MAX_TEAM_UNITS),
-                ("team_atk", C.c_double * MAX_TEAM_UNITS), ("skyfall", C.c_double * 10), ("seed", C.c_uint64)]
+                ("team_atk", C.c_double * MAX_TEAM_UNITS), ("skyfall", C.c_double * 10), ("seed", C.c_uint64),
+                ("orb_bits", C.c_int32), ("reserved", C.c_int32)]
 
 
 class StepArgs(C.Structure):
@@ -48,7 +49,7 @@ class HostStepArgs(C.Structure):
 
 # every symbol include/ppad_b200.h declares (tests/test_cabi_symbols.py checks the header against this)
 SYMBOLS = ["ppad_default_config", "ppad_create", "ppad_destroy", "ppad_abi_version", "ppad_strerror",
-           "ppad_last_error", "ppad_state_bytes", "ppad_launch_count", "ppad_pack", "ppad_unpack", "ppad_reset",
+           "ppad_last_error", "ppad_state_bytes", "ppad_state_bytes_ex", "ppad_launch_count", "ppad_pack", "ppad_unpack", "ppad_reset",
            "ppad_step", "ppad_encode_obs", "ppad_cancel", "ppad_legal_mask", "ppad_sample_actions", "ppad_drop",
            "ppad_fill", "ppad_damage", "ppad_select_actions", "ppad_discount", "ppad_replay_push",
            "ppad_replay_sample", "ppad_permute", "ppad_pipe_create", "ppad_pipe_destroy", "ppad_pipe_step",
@@ -85,6 +86,8 @@ def lib():
     L.ppad_last_error.restype = C.c_char_p
     L.ppad_state_bytes.argtypes = [C.c_int, C.c_int]
     L.ppad_state_bytes.restype = i64
+    L.ppad_state_bytes_ex.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.ppad_state_bytes_ex.restype = i64
     L.ppad_launch_count.restype = u64
     L.ppad_pack.argtypes = [vp, i64, vp, vp, C.c_int, vp, vp, vp, vp, vp]
     L.ppad_unpack.argtypes = [vp, i64, vp, vp, vp, C.c_int, vp, vp, vp]
@@ -112,7 +115,7 @@ def lib():
     L.ppad_replay_sample.argtypes = [vp, i64, i64, u32, vp, vp, vp, vp, vp, vp, vp, vp]
     for name in SYMBOLS:
         getattr(L, name)
-    if L.ppad_abi_version() != 1:
+    if L.ppad_abi_version() != 2:
         raise ImportError("libppad_b200.so ABI version mismatch")
     _lib = L
     return L

@@ -31,7 +31,7 @@ class BatchedPAD:
     """
 
     def __init__(self, n, dim_row=5, dim_col=6, skyfall=None, skyfall_damage=True, team=None, seed=0,
-                 device=None, env0=0, cascade_cap=255, reset_cap=64):
+                 device=None, env0=0, cascade_cap=255, reset_cap=64, orb_bits=None):
         if not torch.cuda.is_available():
             raise RuntimeError("ppad_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _cabi.lib()
@@ -44,13 +44,14 @@ class BatchedPAD:
         self.skyfall_damage = bool(skyfall_damage)
         self.env0 = int(env0)
         self.step_index = 0
-        self.cfg = make_config(dim_row, dim_col, skyfall, skyfall_damage, team, seed, cascade_cap, reset_cap)
+        self.cfg = make_config(dim_row, dim_col, skyfall, skyfall_damage, team, seed, cascade_cap, reset_cap, orb_bits)
+        self.orb_bits = int(self.cfg.orb_bits)   # 3: orb types 0..6; 4: all ten orb types (game.py:236-246)
         handle = C.c_void_p()
         with torch.cuda.device(self.device):      # the library selects its device; the guard restores torch's
             _cabi.check(self.lib.ppad_create(C.byref(self.cfg), self.device.index, C.byref(handle)))
         self._ctx = handle
-        self.words = state_words(self.dim_row, self.dim_col)
-        assert self.lib.ppad_state_bytes(self.dim_row, self.dim_col) == 4 * self.words
+        self.words = state_words(self.dim_row, self.dim_col, self.orb_bits)
+        assert self.lib.ppad_state_bytes_ex(self.dim_row, self.dim_col, self.orb_bits) == 4 * self.words
         # packed state records (int32 view of the uint32 words of include/ppad_b200.h)
         self.state = torch.zeros((self.n, self.words), dtype=torch.int32, device=self.device)
 

@@ -134,10 +134,14 @@ PPAD_HD uint32_t make_info(int n_combos, int depth, int consumed, uint32_t flags
 template <bool WIDE> struct WordOf { typedef uint32_t type; };
 template <> struct WordOf<true> { typedef uint64_t type; };
 
-template <int R_, int C_>
+// NP_ = bit planes per cell: 3 (orb types 0..6, 7 = empty: everything the default skyfall produces) or 4 (orb
+// types 0..9 of game.py:236-246 incl. poison, mortal poison and bomb, 15 = empty).
+template <int R_, int C_, int NP_ = 3>
 struct Geom {
-    static constexpr int R = R_, C = C_, CELLS = R_ * C_;
-    static_assert(CELLS <= 64 && R_ >= 3 && C_ >= 3, "unsupported board size");
+    static constexpr int R = R_, C = C_, CELLS = R_ * C_, NP = NP_;
+    static constexpr int EMPTY = (1 << NP_) - 1;          // code of an empty cell (-1 in the reference)
+    static constexpr int NTYPES = NP_ == 3 ? 7 : 10;      // orb types 0 .. NTYPES - 1
+    static_assert(CELLS <= 64 && R_ >= 3 && C_ >= 3 && (NP_ == 3 || NP_ == 4), "unsupported board size");
     typedef typename WordOf<(CELLS > 32)>::type W;
     static constexpr int WBITS = 8 * (int)sizeof(W);
     static constexpr W ONE = 1;
@@ -154,14 +158,25 @@ struct Geom {
     static constexpr W NOT_LASTROW = BOARD & ~row_mask(R_ - 1);
     static constexpr int OBS_CH = 7;                      // agent01.py:263 fixes 7 channels
     static constexpr int OBS_ELEMS = CELLS * OBS_CH;      // 210 (5x6) / 294 (6x7)
-    // bytes of one packed state record in HBM
-    static constexpr int STATE_BYTES = sizeof(W) == 4 ? 16 : 32;
+    // bytes of one packed state record in HBM: NP planes + the meta word, padded to 16 bytes
+    static constexpr int STATE_BYTES = (NP_ * (int)sizeof(W) + 4 + 15) / 16 * 16;
 };
 
-template <class G>
-struct Board {
-    typename G::W b0, b1, b2;
+template <class W, int NP>
+struct Planes {
+    W b0, b1, b2;
 };
+template <class W>
+struct Planes<W, 4> {
+    W b0, b1, b2, b3;
+};
+template <class G>
+struct Board : Planes<typename G::W, G::NP> {};
+// statement for the fourth plane of the 4-bit geometries
+#define PPAD_P4(...)                    \
+    if constexpr (G::NP > 3) {          \
+        __VA_ARGS__;                    \
+    }
 
 // meta word: finger cell [0,6) | previous action [6,9) | accepted moves this episode [9,25)
 PPAD_HD uint32_t meta_pack(int finger, int prev, int moves)
@@ -242,10 +257,11 @@ PPAD_HD uint32_t action_word(const U4 &b, uint32_t step)
 // prob[i] > 0; with u = x / 2^32 that is x <= thr[i] for thr[i] = floor(cumsum[i] * 2^32) (host
 // computes thr, tests/test_host_logic.py checks it against the float rule).  valid bit i = prob[i] > 0.
 struct SkyfallTable {
-    uint32_t thr[7];
+    uint32_t thr[10];
     uint32_t valid;
 };
 
+template <int NT = 7>   // number of orb types of the geometry (7 or 10)
 PPAD_HD int orb_from_u32(const SkyfallTable &t, uint32_t x)
 {
     // thr is non-decreasing and a type with prob 0 repeats its predecessor's threshold, so the first i with
@@ -254,7 +270,7 @@ PPAD_HD int orb_from_u32(const SkyfallTable &t, uint32_t x)
     // thr = 0xFFFFFFFF from the last valid type on, so the count never passes it.
     int orb = 0;
 #pragma unroll
-    for (int i = 0; i < 6; i++) orb += x > t.thr[i] ? 1 : 0;
+    for (int i = 0; i < NT - 1; i++) orb += x > t.thr[i] ? 1 : 0;
     return x ? orb : ctz(t.valid);
 }
 
@@ -286,6 +302,7 @@ struct OrbSource {
         blk.x = blk.y = blk.z = blk.w = 0;
     }
 
+    template <int NT = 7>
     PPAD_HD int next(const RngKey &key, const SkyfallTable &sky)
     {
         const int d = cursor++;
@@ -310,7 +327,7 @@ struct OrbSource {
         }
         const int l = d & 3;
         const uint32_t x = l == 0 ? blk.x : (l == 1 ? blk.y : (l == 2 ? blk.z : blk.w));
-        return orb_from_u32(sky, x);
+        return orb_from_u32<NT>(sky, x);
     }
 };
 
@@ -384,13 +401,17 @@ struct Tally {
 template <class G>
 PPAD_HD typename G::W empties(const Board<G> &b)
 {
-    return b.b0 & b.b1 & b.b2;   // bits >= CELLS are zero in every plane
+    typename G::W e = b.b0 & b.b1 & b.b2;   // bits >= CELLS are zero in every plane
+    PPAD_P4(e &= b.b3)
+    return e;
 }
 
 template <class G>
 PPAD_HD int code_at(const Board<G> &b, int cell)
 {
-    return (int)(((b.b0 >> cell) & 1) | (((b.b1 >> cell) & 1) << 1) | (((b.b2 >> cell) & 1) << 2));
+    int code = (int)(((b.b0 >> cell) & 1) | (((b.b1 >> cell) & 1) << 1) | (((b.b2 >> cell) & 1) << 2));
+    PPAD_P4(code |= (int)((b.b3 >> cell) & 1) << 3)
+    return code;
 }
 
 template <class G>
@@ -401,6 +422,7 @@ PPAD_HD void set_code(Board<G> &b, int cell, int code)
     b.b0 = (b.b0 & ~bit) | ((W)(code & 1) << cell);
     b.b1 = (b.b1 & ~bit) | ((W)((code >> 1) & 1) << cell);
     b.b2 = (b.b2 & ~bit) | ((W)((code >> 2) & 1) << cell);
+    PPAD_P4(b.b3 = (b.b3 & ~bit) | ((W)((code >> 3) & 1) << cell))
 }
 
 // swap the codes of cells i and j (game.py:429-456)
@@ -415,6 +437,7 @@ PPAD_HD void swap_cells(Board<G> &b, int i, int j)
     b.b1 ^= (x << i) | (x << j);
     x = ((b.b2 >> i) ^ (b.b2 >> j)) & 1;
     b.b2 ^= (x << i) | (x << j);
+    PPAD_P4(x = ((b.b3 >> i) ^ (b.b3 >> j)) & 1; b.b3 ^= (x << i) | (x << j))
 }
 
 // Edge masks and matched cells.  er bit i: cell i is non-empty and has the colour of cell i+1 in
@@ -425,9 +448,10 @@ PPAD_HD typename G::W match_mask(const Board<G> &b, typename G::W &er, typename 
 {
     typedef typename G::W W;
     constexpr int C = G::C;
-    const W ne = ~(b.b0 & b.b1 & b.b2);
-    const W xr = (b.b0 ^ (b.b0 >> 1)) | (b.b1 ^ (b.b1 >> 1)) | (b.b2 ^ (b.b2 >> 1));
-    const W xd = (b.b0 ^ (b.b0 >> C)) | (b.b1 ^ (b.b1 >> C)) | (b.b2 ^ (b.b2 >> C));
+    const W ne = ~empties<G>(b);
+    W xr = (b.b0 ^ (b.b0 >> 1)) | (b.b1 ^ (b.b1 >> 1)) | (b.b2 ^ (b.b2 >> 1));
+    W xd = (b.b0 ^ (b.b0 >> C)) | (b.b1 ^ (b.b1 >> C)) | (b.b2 ^ (b.b2 >> C));
+    PPAD_P4(xr |= b.b3 ^ (b.b3 >> 1); xd |= b.b3 ^ (b.b3 >> C))
     er = ~xr & ne & G::NOT_LASTCOL;
     ed = ~xd & ne & G::NOT_LASTROW;
     const W h = er & (er >> 1);
@@ -471,6 +495,7 @@ PPAD_HD int cancel_board(Board<G> &b, F &&on_combo)
     b.b0 |= m;
     b.b1 |= m;
     b.b2 |= m;
+    PPAD_P4(b.b3 |= m)
     return n;
 }
 
@@ -478,7 +503,9 @@ PPAD_HD int cancel_board(Board<G> &b, F &&on_combo)
 template <class G, int COLOUR>
 PPAD_HD typename G::W colour_plane(const Board<G> &b)
 {
-    return ((COLOUR & 1) ? b.b0 : ~b.b0) & ((COLOUR & 2) ? b.b1 : ~b.b1) & ((COLOUR & 4) ? b.b2 : ~b.b2);
+    typename G::W c = ((COLOUR & 1) ? b.b0 : ~b.b0) & ((COLOUR & 2) ? b.b1 : ~b.b1) & ((COLOUR & 4) ? b.b2 : ~b.b2);
+    PPAD_P4(c &= (COLOUR & 8) ? b.b3 : ~b.b3)
+    return c;
 }
 
 // cancel() straight into the reward tally, colour-major: the per-colour trackers of damage() (game.py:163-190)
@@ -514,6 +541,8 @@ PPAD_HD void cancel_tally(Board<G> &b, typename G::W m, typename G::W er, typena
         cancel_colour<G, 4>(b, m, slow, tally, team);
         cancel_colour<G, 5>(b, m, slow, tally, team);
         cancel_colour<G, 6>(b, m, slow, tally, team);
+        PPAD_P4(cancel_colour<G, 7>(b, m, slow, tally, team); cancel_colour<G, 8>(b, m, slow, tally, team);
+                cancel_colour<G, 9>(b, m, slow, tally, team))
     }
     if (slow) {
         // usually those cells still form ONE island (an L, T or cross, a run of 6): one flood fill settles it
@@ -532,6 +561,7 @@ PPAD_HD void cancel_tally(Board<G> &b, typename G::W m, typename G::W er, typena
     b.b0 |= m;
     b.b1 |= m;
     b.b2 |= m;
+    PPAD_P4(b.b3 |= m)
 }
 
 // gravity (game.py:201-221): every orb with an empty cell directly below moves down one row,
@@ -549,6 +579,7 @@ PPAD_HD void drop_board(Board<G> &b)
         b.b0 = (b.b0 & ~dst) | ((b.b0 & fall) << C) | fall;
         b.b1 = (b.b1 & ~dst) | ((b.b1 & fall) << C) | fall;
         b.b2 = (b.b2 & ~dst) | ((b.b2 & fall) << C) | fall;
+        PPAD_P4(b.b3 = (b.b3 & ~dst) | ((b.b3 & fall) << C) | fall)
     }
 }
 
@@ -570,6 +601,7 @@ PPAD_HD void fill_board(Board<G> &b, OrbSource &src, const RngKey &key, const Sk
             b.b0 ^= bit & ((W)(word & 1u) - 1);
             b.b1 ^= bit & ((W)((word >> 1) & 1u) - 1);
             b.b2 ^= bit & ((W)((word >> 2) & 1u) - 1);
+            PPAD_P4(b.b3 ^= bit & ((W)((word >> 3) & 1u) - 1))
             d++;
             word >>= 4;
             if ((d & 7) == 0 && e) word = src.slab[d >> 3];
@@ -592,12 +624,13 @@ PPAD_HD void fill_board(Board<G> &b, OrbSource &src, const RngKey &key, const Sk
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 if (k >= l0 && e) {
-                    const int code = orb_from_u32(sky, k == 0 ? blk.x : (k == 1 ? blk.y : (k == 2 ? blk.z : blk.w)));
+                    const int code = orb_from_u32<G::NTYPES>(sky, k == 0 ? blk.x : (k == 1 ? blk.y : (k == 2 ? blk.z : blk.w)));
                     const W bit = e & (~e + 1);
                     e ^= bit;
                     b.b0 ^= bit & ((W)(code & 1) - 1);
                     b.b1 ^= bit & ((W)((code >> 1) & 1) - 1);
                     b.b2 ^= bit & ((W)((code >> 2) & 1) - 1);
+                    PPAD_P4(b.b3 ^= bit & ((W)((code >> 3) & 1) - 1))
                     d++;
                 }
             }
@@ -608,10 +641,11 @@ PPAD_HD void fill_board(Board<G> &b, OrbSource &src, const RngKey &key, const Sk
     }
     while (e) {
         const W bit = e & (~e + 1);
-        const int code = src.next(key, sky);
+        const int code = src.template next<G::NTYPES>(key, sky);
         if (!(code & 1)) b.b0 ^= bit;
         if (!(code & 2)) b.b1 ^= bit;
         if (!(code & 4)) b.b2 ^= bit;
+        PPAD_P4(if (!(code & 8)) b.b3 ^= bit)
         e ^= bit;
     }
 }
@@ -623,7 +657,7 @@ template <class G, bool TIGHT = PPAD_TIGHT_DEFAULT>
 PPAD_HD void refill_all(Board<G> &b, OrbSource &src, const RngKey &key, const SkyfallTable &sky)
 {
     typedef typename G::W W;
-    W p0 = 0, p1 = 0, p2 = 0;
+    W p0 = 0, p1 = 0, p2 = 0, p3 = 0;
     if (TIGHT && src.n_inj < 0) {
         // pure Philox (the auto-reset of rollouts): one block per four draws, words taken by compile-time index
         const uint32_t blk0 = (uint32_t)src.cursor >> 2;
@@ -641,10 +675,11 @@ PPAD_HD void refill_all(Board<G> &b, OrbSource &src, const RngKey &key, const Sk
             for (int k = 0; k < 4; k++) {
                 const int i = 4 * q + k - l0;
                 if (i >= 0 && i < G::CELLS) {
-                    const int code = orb_from_u32(sky, k == 0 ? blk.x : (k == 1 ? blk.y : (k == 2 ? blk.z : blk.w)));
+                    const int code = orb_from_u32<G::NTYPES>(sky, k == 0 ? blk.x : (k == 1 ? blk.y : (k == 2 ? blk.z : blk.w)));
                     p0 |= (W)(code & 1) << i;
                     p1 |= (W)((code >> 1) & 1) << i;
                     p2 |= (W)((code >> 2) & 1) << i;
+                    PPAD_P4(p3 |= (W)((code >> 3) & 1) << i)
                 }
             }
         }
@@ -652,15 +687,17 @@ PPAD_HD void refill_all(Board<G> &b, OrbSource &src, const RngKey &key, const Sk
         src.blk_idx = -1;
     } else {
         for (int i = 0; i < G::CELLS; i++) {
-            const int code = src.next(key, sky);
+            const int code = src.template next<G::NTYPES>(key, sky);
             p0 |= (W)(code & 1) << i;
             p1 |= (W)((code >> 1) & 1) << i;
             p2 |= (W)((code >> 2) & 1) << i;
+            PPAD_P4(p3 |= (W)((code >> 3) & 1) << i)
         }
     }
     b.b0 = p0;
     b.b1 = p1;
     b.b2 = p2;
+    PPAD_P4(b.b3 = p3)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -977,6 +1014,7 @@ __device__ __forceinline__ uint32_t reset_boards_warp(bool need, State<G> &s, co
         const bool in_range = cap <= 0 || att < cap;
         Board<G> b;
         b.b0 = b.b1 = b.b2 = 0;
+        PPAD_P4(b.b3 = 0)
         bool ok = false;
         if (in_range) {
             OrbSource src;
@@ -999,12 +1037,15 @@ __device__ __forceinline__ uint32_t reset_boards_warp(bool need, State<G> &s, co
             winners &= winners - 1;
             const int o = __shfl_sync(full, owner, w);
             const W w0 = __shfl_sync(full, b.b0, w), w1 = __shfl_sync(full, b.b1, w), w2 = __shfl_sync(full, b.b2, w);
+            W w3 = 0;
+            PPAD_P4(w3 = __shfl_sync(full, b.b3, w))
             const int a_w = __shfl_sync(full, att, w);
             const int ok_w = __shfl_sync(full, (int)ok, w);
             if (lane == o) {
                 s.b.b0 = w0;
                 s.b.b1 = w1;
                 s.b.b2 = w2;
+                PPAD_P4(s.b.b3 = w3)
                 consumed = (a_w + 1) * G::CELLS;
                 if (!ok_w) flags |= FLAG_RESET_CAP;
                 got = true;
@@ -1112,7 +1153,10 @@ PPAD_HD void obs_mask(const State<G> &s, uint32_t (&w)[NW])
     W plane[7];
 #pragma unroll
     for (int k = 0; k < 6; k++)
+    {
         plane[k] = ((k & 1) ? s.b.b0 : ~s.b.b0) & ((k & 2) ? s.b.b1 : ~s.b.b1) & ((k & 4) ? s.b.b2 : ~s.b.b2) & G::BOARD;
+        PPAD_P4(plane[k] &= ~s.b.b3)   // types 0..5 have bit 3 clear; 6..9 and empty give all-zero colour channels
+    }
     plane[6] = G::ONE << meta_finger(s.meta);                 // channel 6 = finger
 #pragma unroll
     for (int r = 0; r < G::R; r++) {
@@ -1141,24 +1185,26 @@ template <class G, class T>
 PPAD_HD uint32_t pack_cells(Board<G> &b, const T *cells)
 {
     typedef typename G::W W;
-    W p0 = 0, p1 = 0, p2 = 0;
+    W p0 = 0, p1 = 0, p2 = 0, p3 = 0;
     uint32_t flags = 0;
     for (int i = 0; i < G::CELLS; i++) {
         const long long v = (long long)cells[i];
         int code;
-        if (v == -1) code = 7;
-        else if (v >= 0 && v <= 6) code = (int)v;
+        if (v == -1) code = G::EMPTY;
+        else if (v >= 0 && v < G::NTYPES) code = (int)v;
         else {
-            code = 7;
+            code = G::EMPTY;
             flags |= FLAG_UNSUPPORTED_ORB;
         }
         p0 |= (W)(code & 1) << i;
         p1 |= (W)((code >> 1) & 1) << i;
         p2 |= (W)((code >> 2) & 1) << i;
+        PPAD_P4(p3 |= (W)((code >> 3) & 1) << i)
     }
     b.b0 = p0;
     b.b1 = p1;
     b.b2 = p2;
+    PPAD_P4(b.b3 = p3)
     return flags;
 }
 
@@ -1167,7 +1213,7 @@ PPAD_HD void unpack_cells(const Board<G> &b, T *cells)
 {
     for (int i = 0; i < G::CELLS; i++) {
         const int code = code_at<G>(b, i);
-        cells[i] = (T)(code == 7 ? -1 : code);
+        cells[i] = (T)(code == G::EMPTY ? -1 : code);
     }
 }
 

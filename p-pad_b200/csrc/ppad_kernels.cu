@@ -32,11 +32,20 @@ constexpr int BLOCK = 256;
 // ------------------------------------------------------------------------------------------------
 // packed state I/O
 // ------------------------------------------------------------------------------------------------
-template <class G, bool WIDE = (sizeof(typename G::W) == 8)>
+template <class G, bool WIDE = (sizeof(typename G::W) == 8), int NP = G::NP>
 struct StateIO;
 
 template <class G>
-struct StateIO<G, false> {
+__device__ __forceinline__ void clear_state(State<G> &s)
+{
+    s.b.b0 = s.b.b1 = s.b.b2 = 0;
+    PPAD_P4(s.b.b3 = 0)
+    s.meta = 0;
+}
+
+// 32-bit planes, 3-bit codes: {b0, b1, b2, meta} = one uint4
+template <class G>
+struct StateIO<G, false, 3> {
     static __device__ __forceinline__ State<G> load(const void *base, int64_t i)
     {
         const uint4 v = __ldg(reinterpret_cast<const uint4 *>(base) + i);
@@ -61,8 +70,9 @@ struct StateIO<G, false> {
     }
 };
 
+// 64-bit planes, 3-bit codes: {b0, b1}, {b2, meta, 0} = two uint4
 template <class G>
-struct StateIO<G, true> {
+struct StateIO<G, true, 3> {
     static __device__ __forceinline__ State<G> load(const void *base, int64_t i)
     {
         const uint4 lo = __ldg(reinterpret_cast<const uint4 *>(base) + 2 * i);
@@ -86,6 +96,63 @@ struct StateIO<G, true> {
         p[0] = b.b0;
         p[1] = b.b1;
         p[2] = b.b2;
+    }
+};
+
+// 32-bit planes, 4-bit codes: {b0, b1, b2, b3}, {meta, 0, 0, 0} = two uint4
+template <class G>
+struct StateIO<G, false, 4> {
+    static __device__ __forceinline__ State<G> load(const void *base, int64_t i)
+    {
+        const uint4 lo = __ldg(reinterpret_cast<const uint4 *>(base) + 2 * i);
+        const uint4 hi = __ldg(reinterpret_cast<const uint4 *>(base) + 2 * i + 1);
+        State<G> s;
+        s.b.b0 = lo.x;
+        s.b.b1 = lo.y;
+        s.b.b2 = lo.z;
+        s.b.b3 = lo.w;
+        s.meta = hi.x;
+        return s;
+    }
+    static __device__ __forceinline__ void store(void *base, int64_t i, const Board<G> &b, uint32_t meta)
+    {
+        uint4 *p = reinterpret_cast<uint4 *>(base) + 2 * i;
+        p[0] = make_uint4(b.b0, b.b1, b.b2, b.b3);
+        p[1] = make_uint4(meta, 0u, 0u, 0u);
+    }
+    static __device__ __forceinline__ void store_planes(void *base, int64_t i, const Board<G> &b)
+    {
+        reinterpret_cast<uint4 *>(base)[2 * i] = make_uint4(b.b0, b.b1, b.b2, b.b3);
+    }
+};
+
+// 64-bit planes, 4-bit codes: {b0, b1}, {b2, b3}, {meta, 0, 0, 0} = three uint4
+template <class G>
+struct StateIO<G, true, 4> {
+    static __device__ __forceinline__ State<G> load(const void *base, int64_t i)
+    {
+        const uint4 *p = reinterpret_cast<const uint4 *>(base) + 3 * i;
+        const uint4 a = __ldg(p), c = __ldg(p + 1), d = __ldg(p + 2);
+        State<G> s;
+        s.b.b0 = (uint64_t)a.x | ((uint64_t)a.y << 32);
+        s.b.b1 = (uint64_t)a.z | ((uint64_t)a.w << 32);
+        s.b.b2 = (uint64_t)c.x | ((uint64_t)c.y << 32);
+        s.b.b3 = (uint64_t)c.z | ((uint64_t)c.w << 32);
+        s.meta = d.x;
+        return s;
+    }
+    static __device__ __forceinline__ void store(void *base, int64_t i, const Board<G> &b, uint32_t meta)
+    {
+        uint4 *p = reinterpret_cast<uint4 *>(base) + 3 * i;
+        p[0] = make_uint4((uint32_t)b.b0, (uint32_t)(b.b0 >> 32), (uint32_t)b.b1, (uint32_t)(b.b1 >> 32));
+        p[1] = make_uint4((uint32_t)b.b2, (uint32_t)(b.b2 >> 32), (uint32_t)b.b3, (uint32_t)(b.b3 >> 32));
+        p[2] = make_uint4(meta, 0u, 0u, 0u);
+    }
+    static __device__ __forceinline__ void store_planes(void *base, int64_t i, const Board<G> &b)
+    {
+        uint4 *p = reinterpret_cast<uint4 *>(base) + 3 * i;
+        p[0] = make_uint4((uint32_t)b.b0, (uint32_t)(b.b0 >> 32), (uint32_t)b.b1, (uint32_t)(b.b1 >> 32));
+        p[1] = make_uint4((uint32_t)b.b2, (uint32_t)(b.b2 >> 32), (uint32_t)b.b3, (uint32_t)(b.b3 >> 32));
     }
 };
 
@@ -248,8 +315,7 @@ __global__ void __launch_bounds__(BLOCK, 4) step_obs_kernel(const __grid_constan
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     const bool valid = i < a.n;
     State<G> s;
-    s.b.b0 = s.b.b1 = s.b.b2 = 0;
-    s.meta = 0;
+    clear_state<G>(s);
     int action = -1, path_len = 0;
     if (valid) {
         s = StateIO<G>::load(a.state, i);
@@ -317,8 +383,7 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     const bool valid = i < a.n;
     State<G> s;
-    s.b.b0 = s.b.b1 = s.b.b2 = 0;
-    s.meta = 0;
+    clear_state<G>(s);
     if (valid) s = StateIO<G>::load(a.state, i);
     double reward_sum = 0.0;
     uint32_t episodes = 0, combos = 0, flags = 0;
@@ -379,7 +444,7 @@ constexpr int POOL_FILL_BELOW = PBLOCK / 2;    // fill while pool <= this: pool 
 
 template <class G>
 struct CascadePool {
-    typename G::W b0[POOL_SLOTS], b1[POOL_SLOTS], b2[POOL_SLOTS];
+    typename G::W b0[POOL_SLOTS], b1[POOL_SLOTS], b2[POOL_SLOTS], b3[G::NP > 3 ? POOL_SLOTS : 1];
     double t0[POOL_SLOTS], t1[POOL_SLOTS], t2[POOL_SLOTS], t3[POOL_SLOTS], t4[POOL_SLOTS];
     uint32_t counts[POOL_SLOTS];   // n_combos [0,16) | depth [16,24) | flags [24,32)
     uint32_t source[POOL_SLOTS];   // skyfall cursor [0,16) | injected slab exhausted [16]
@@ -391,6 +456,7 @@ struct CascadePool {
         b0[slot] = it.b.b0;
         b1[slot] = it.b.b1;
         b2[slot] = it.b.b2;
+        PPAD_P4(b3[slot] = it.b.b3)
         t0[slot] = it.tally.t0;
         t1[slot] = it.tally.t1;
         t2[slot] = it.tally.t2;
@@ -406,6 +472,7 @@ struct CascadePool {
         it.b.b0 = b0[slot];
         it.b.b1 = b1[slot];
         it.b.b2 = b2[slot];
+        PPAD_P4(it.b.b3 = b3[slot])
         it.tally.t0 = t0[slot];
         it.tally.t1 = t1[slot];
         it.tally.t2 = t2[slot];
@@ -466,8 +533,7 @@ __global__ void __launch_bounds__(PBLOCK, PPAD_POOL_MINB) step_pool_kernel(const
             pre.action = 255;
             pre.flags = 0;
             pre.evaluate = false;
-            s.b.b0 = s.b.b1 = s.b.b2 = 0;
-            s.meta = 0;
+            clear_state<G>(s);
             if (valid) {
                 s = StateIO<G>::load(a.state, i);
                 const RngKey key = board_key(a.p, a.env0 + (uint64_t)i);
@@ -552,8 +618,7 @@ __global__ void __launch_bounds__(BLOCK) encode_kernel(int64_t n, const void *st
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     const bool valid = i < n;
     State<G> s;
-    s.b.b0 = s.b.b1 = s.b.b2 = 0;
-    s.meta = 0;
+    clear_state<G>(s);
     if (valid) s = StateIO<G>::load(state, i);
     const int64_t warp0 = i - (threadIdx.x & 31);
     if (warp0 < n) {
@@ -582,8 +647,7 @@ __global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ Re
     int finger = -1;
     if (valid && a.fingers_in) finger = a.fingers_in[2 * i] * G::C + a.fingers_in[2 * i + 1];
     State<G> s;
-    s.b.b0 = s.b.b1 = s.b.b2 = 0;
-    s.meta = 0;
+    clear_state<G>(s);
     int consumed = 0;
     const uint32_t flags = reset_boards_warp<G, true>(valid, s, a.p, a.p.key.step, a.env0 + (uint64_t)i,
                                                 a.slab && valid ? a.slab + (size_t)i * a.p.slab_words : nullptr,
@@ -722,18 +786,20 @@ __global__ void __launch_bounds__(BLOCK) permute_kernel(int64_t n, void *state, 
     State<G> s = StateIO<G>::load(state, i);
     const uint2 m2 = *reinterpret_cast<const uint2 *>(maps + 8 * i);
     const uint64_t lut = (uint64_t)m2.x | ((uint64_t)m2.y << 32);
-    W p0 = 0, p1 = 0, p2 = 0;
+    W p0 = 0, p1 = 0, p2 = 0, p3 = 0;
 #pragma unroll
     for (int c = 0; c < G::CELLS; c++) {
         const int code = code_at<G>(s.b, c);
-        const int to = code == 7 ? 7 : (int)((lut >> (8 * code)) & 7);
+        const int to = code > 6 ? code : (int)((lut >> (8 * code)) & 7);   // empty cells and types 7..9 stay
         p0 |= (W)(to & 1) << c;
         p1 |= (W)((to >> 1) & 1) << c;
         p2 |= (W)((to >> 2) & 1) << c;
+        PPAD_P4(p3 |= (W)((to >> 3) & 1) << c)
     }
     s.b.b0 = p0;
     s.b.b1 = p1;
     s.b.b2 = p2;
+    PPAD_P4(s.b.b3 = p3)
     StateIO<G>::store(state, i, s.b, s.meta);
 }
 
@@ -834,23 +900,29 @@ inline unsigned grid_for(int64_t n) { return (unsigned)((n + BLOCK - 1) / BLOCK)
 typedef Geom<4, 5> G45;
 typedef Geom<5, 6> G56;
 typedef Geom<6, 7> G67;
+typedef Geom<4, 5, 4> G45W;   // 4-bit orb codes: all ten orb types of game.py:236-246
+typedef Geom<5, 6, 4> G56W;
+typedef Geom<6, 7, 4> G67W;
 
 }   // namespace
 
 struct ppad_ctx {
     ppad_config cfg;
     int device;
-    int geom;   // 0 = 5x6, 1 = 6x7, 2 = 4x5
+    int geom;   // 0 = 5x6, 1 = 6x7, 2 = 4x5; 3..5 = the same with 4-bit orb codes
     StepParams base;
     int sm_count;
     int pool_ctas_per_sm;   // resident CTAs of the persistent step_pool_kernel
 };
 
-#define PPAD_DISPATCH(ctx, EXPR)                            \
-    do {                                                    \
-        if ((ctx)->geom == 0) { typedef G56 G; EXPR; }      \
-        else if ((ctx)->geom == 1) { typedef G67 G; EXPR; } \
-        else { typedef G45 G; EXPR; }                       \
+#define PPAD_DISPATCH(ctx, EXPR)                             \
+    do {                                                     \
+        if ((ctx)->geom == 0) { typedef G56 G; EXPR; }       \
+        else if ((ctx)->geom == 1) { typedef G67 G; EXPR; }  \
+        else if ((ctx)->geom == 2) { typedef G45 G; EXPR; }  \
+        else if ((ctx)->geom == 3) { typedef G56W G; EXPR; } \
+        else if ((ctx)->geom == 4) { typedef G67W G; EXPR; } \
+        else { typedef G45W G; EXPR; }                       \
     } while (0)
 
 template <class G, class T>
@@ -904,13 +976,17 @@ const char *ppad_strerror(int status)
 
 const char *ppad_last_error(void) { return g_last_error.c_str(); }
 
-int64_t ppad_state_bytes(int rows, int cols)
+int64_t ppad_state_bytes_ex(int rows, int cols, int orb_bits)
 {
-    if (rows == 5 && cols == 6) return G56::STATE_BYTES;
-    if (rows == 6 && cols == 7) return G67::STATE_BYTES;
-    if (rows == 4 && cols == 5) return G45::STATE_BYTES;
+    const bool wide = orb_bits == 4;
+    if (orb_bits != 0 && orb_bits != 3 && !wide) return -1;
+    if (rows == 5 && cols == 6) return wide ? G56W::STATE_BYTES : G56::STATE_BYTES;
+    if (rows == 6 && cols == 7) return wide ? G67W::STATE_BYTES : G67::STATE_BYTES;
+    if (rows == 4 && cols == 5) return wide ? G45W::STATE_BYTES : G45::STATE_BYTES;
     return -1;
 }
+
+int64_t ppad_state_bytes(int rows, int cols) { return ppad_state_bytes_ex(rows, cols, 3); }
 
 uint64_t ppad_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
@@ -1208,7 +1284,7 @@ int ppad_pipe_step(ppad_pipe *p, const ppad_host_step_args *h, void *after_strea
         return fail(PPAD_ERR_INVALID, "ppad_pipe_step: slab_words exceeds the pipe's slab_words_max");
     if (!h->state) return fail(PPAD_ERR_INVALID, "ppad_pipe_step: null state");
     if (h->n == 0) return PPAD_OK;
-    const size_t rec = (size_t)ppad_state_bytes(ctx->cfg.rows, ctx->cfg.cols);
+    const size_t rec = (size_t)ppad_state_bytes_ex(ctx->cfg.rows, ctx->cfg.cols, ctx->cfg.orb_bits);
     const size_t obs_elem = h->obs_dtype == PPAD_OBS_F32 ? 4 : 1;
     const size_t obs_row = (size_t)ctx->cfg.rows * ctx->cfg.cols * 7 * obs_elem;
     // chunk streams start after whatever the caller has queued on after_stream (e.g. the reset)
@@ -1467,7 +1543,7 @@ int ppad_replay_push(const ppad_ctx *ctx, int64_t n, int64_t capacity, int64_t c
     if (n == 0) return PPAD_OK;
     if (!state || !action || !reward || !r_state || !r_action || !r_reward || capacity <= 0 || cursor < 0)
         return fail(PPAD_ERR_INVALID, "ppad_replay_push: bad argument");
-    const int words = (int)(ppad_state_bytes(ctx->cfg.rows, ctx->cfg.cols) / 4);
+    const int words = (int)(ppad_state_bytes_ex(ctx->cfg.rows, ctx->cfg.cols, ctx->cfg.orb_bits) / 4);
     replay_push_kernel<<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(n, words, capacity, cursor, (const uint32_t *)state,
                                                                         action, reward, keep, slot, (uint32_t *)r_state,
                                                                         r_action, r_reward);
@@ -1482,7 +1558,7 @@ int ppad_replay_sample(const ppad_ctx *ctx, int64_t k, int64_t size, uint32_t st
     if (k == 0) return PPAD_OK;
     if (!r_state || !r_action || !r_reward || !state || !action || !reward || size <= 0)
         return fail(PPAD_ERR_INVALID, "ppad_replay_sample: bad argument");
-    const int words = (int)(ppad_state_bytes(ctx->cfg.rows, ctx->cfg.cols) / 4);
+    const int words = (int)(ppad_state_bytes_ex(ctx->cfg.rows, ctx->cfg.cols, ctx->cfg.orb_bits) / 4);
     RngKey key = ctx->base.key;
     key.step = step;
     replay_sample_kernel<<<grid_for(k), BLOCK, 0, (cudaStream_t)stream>>>(k, words, size, key, (const uint32_t *)r_state,

@@ -10,7 +10,8 @@
 
 namespace ppad {
 
-// returns PPAD_OK or an error status with `err` set; geom: 0 = 5x6, 1 = 6x7, 2 = 4x5
+// returns PPAD_OK or an error status with `err` set; geom: 0 = 5x6, 1 = 6x7, 2 = 4x5 with 3-bit orb codes,
+// 3..5 = the same boards with 4-bit codes (cfg.orb_bits == 4: orb types 7..9 allowed)
 inline int build_params(const ppad_config &cfg, StepParams &p, int &geom, std::string &err)
 {
     std::memset(&p, 0, sizeof(p));
@@ -42,8 +43,14 @@ inline int build_params(const ppad_config &cfg, StepParams &p, int &geom, std::s
         err = "only 4x5, 5x6 and 6x7 boards (rows x cols) have kernel instantiations";
         return PPAD_ERR_UNSUPPORTED;
     }
-    if (cfg.skyfall[7] > 0 || cfg.skyfall[8] > 0 || cfg.skyfall[9] > 0) {
-        err = "orb types 7..9 (poison, mortal poison, bomb) do not fit the 3-bit state";
+    if (cfg.orb_bits != 0 && cfg.orb_bits != 3 && cfg.orb_bits != 4) {
+        err = "orb_bits must be 3 (orb types 0..6) or 4 (orb types 0..9)";
+        return PPAD_ERR_INVALID;
+    }
+    const bool wide = cfg.orb_bits == 4;
+    if (wide) geom += 3;
+    if (!wide && (cfg.skyfall[7] > 0 || cfg.skyfall[8] > 0 || cfg.skyfall[9] > 0)) {
+        err = "orb types 7..9 (poison, mortal poison, bomb) do not fit the 3-bit state: create the context with orb_bits = 4";
         return PPAD_ERR_UNSUPPORTED;
     }
     if (cfg.team_size < 0 || cfg.team_size > PPAD_MAX_TEAM_UNITS) {
@@ -56,7 +63,7 @@ inline int build_params(const ppad_config &cfg, StepParams &p, int &geom, std::s
     // cumsum * 2^32 is exact in double, so x <= floor(cumsum * 2^32) is the same predicate
     double cum = 0;
     int last_valid = -1;
-    for (int i = 0; i < 7; i++) {
+    for (int i = 0; i < 10; i++) {
         cum += cfg.skyfall[i];
         const double t = std::floor(cum * 4294967296.0);
         p.sky.thr[i] = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;

@@ -6,55 +6,61 @@ tests.  They are format converters, not a compute path: no game logic lives here
 import numpy as np
 
 
-def state_words(rows, cols):
-    """uint32 words per packed state record."""
+def state_words(rows, cols, orb_bits=3):
+    """uint32 words per packed state record (orb_bits planes + the meta word, padded to 16 bytes)."""
     cells = rows * cols
-    if cells <= 32:
-        return 4
-    if cells <= 64:
-        return 8
-    raise ValueError("board too large for the packed state")
+    if cells > 64:
+        raise ValueError("board too large for the packed state")
+    if orb_bits not in (3, 4):
+        raise ValueError("orb_bits must be 3 or 4")
+    plane_words = 1 if cells <= 32 else 2
+    return (orb_bits * plane_words + 1 + 3) // 4 * 4
 
 
-def pack_state(boards, fingers, prev=None, moves=None):
-    """[n, rows, cols] ints (-1 = empty, 0..6) + [n, 2] (row, col) -> uint32 [n, 4 | 8] state records."""
+def pack_state(boards, fingers, prev=None, moves=None, orb_bits=3):
+    """[n, rows, cols] ints (-1 = empty, 0..6 or, with orb_bits = 4, 0..9) + [n, 2] (row, col) -> uint32 state records."""
     boards = np.asarray(boards)
     n, rows, cols = boards.shape
     cells = rows * cols
     fingers = np.asarray(fingers).reshape(n, 2)
     codes = boards.reshape(n, cells).astype(np.int64)
-    if ((codes < -1) | (codes > 6)).any():
-        raise ValueError("orb types must be -1..6 for the 3-bit state")
-    codes = np.where(codes < 0, 7, codes).astype(np.uint64)
+    top = 6 if orb_bits == 3 else 9
+    if ((codes < -1) | (codes > top)).any():
+        raise ValueError("orb types must be -1..%d for the %d-bit state" % (top, orb_bits))
+    codes = np.where(codes < 0, (1 << orb_bits) - 1, codes).astype(np.uint64)
     shifts = np.arange(cells, dtype=np.uint64)
-    planes = [(((codes >> np.uint64(j)) & np.uint64(1)) << shifts).sum(axis=1, dtype=np.uint64) for j in range(3)]
+    planes = [(((codes >> np.uint64(j)) & np.uint64(1)) << shifts).sum(axis=1, dtype=np.uint64) for j in range(orb_bits)]
     prev = np.full(n, 4, np.uint32) if prev is None else np.asarray(prev).astype(np.uint32)
     moves = np.zeros(n, np.uint32) if moves is None else np.asarray(moves).astype(np.uint32)
     meta = (fingers[:, 0] * cols + fingers[:, 1]).astype(np.uint32) | (prev << np.uint32(6)) | (moves << np.uint32(9))
+    out = np.zeros((n, state_words(rows, cols, orb_bits)), np.uint32)
     if cells <= 32:
-        out = np.stack([planes[0].astype(np.uint32), planes[1].astype(np.uint32), planes[2].astype(np.uint32), meta], 1)
+        for j, pl in enumerate(planes):
+            out[:, j] = pl.astype(np.uint32)
+        out[:, orb_bits] = meta
     else:
-        lo = [p.astype(np.uint32) for p in planes]
-        hi = [(p >> np.uint64(32)).astype(np.uint32) for p in planes]
-        out = np.stack([lo[0], hi[0], lo[1], hi[1], lo[2], hi[2], meta, np.zeros(n, np.uint32)], 1)
+        for j, pl in enumerate(planes):
+            out[:, 2 * j] = pl.astype(np.uint32)
+            out[:, 2 * j + 1] = (pl >> np.uint64(32)).astype(np.uint32)
+        out[:, 2 * orb_bits] = meta
     return np.ascontiguousarray(out, np.uint32)
 
 
-def unpack_state(state, rows, cols):
-    """uint32 [n, 4 | 8] -> (boards int8 [n, rows, cols], fingers int32 [n, 2], prev uint8 [n], moves uint16 [n])."""
+def unpack_state(state, rows, cols, orb_bits=3):
+    """uint32 state records -> (boards int8 [n, rows, cols], fingers int32 [n, 2], prev uint8 [n], moves uint16 [n])."""
     state = np.asarray(state, np.uint32)
     n = state.shape[0]
     cells = rows * cols
     if cells <= 32:
-        planes = [state[:, j].astype(np.uint64) for j in range(3)]
-        meta = state[:, 3]
+        planes = [state[:, j].astype(np.uint64) for j in range(orb_bits)]
+        meta = state[:, orb_bits]
     else:
         planes = [state[:, 2 * j].astype(np.uint64) | (state[:, 2 * j + 1].astype(np.uint64) << np.uint64(32))
-                  for j in range(3)]
-        meta = state[:, 6]
+                  for j in range(orb_bits)]
+        meta = state[:, 2 * orb_bits]
     shifts = np.arange(cells, dtype=np.uint64)
     codes = sum((((p[:, None] >> shifts) & np.uint64(1)) << np.uint64(j)) for j, p in enumerate(planes)).astype(np.int8)
-    boards = np.where(codes == 7, -1, codes).astype(np.int8).reshape(n, rows, cols)
+    boards = np.where(codes == (1 << orb_bits) - 1, -1, codes).astype(np.int8).reshape(n, rows, cols)
     f = (meta & 63).astype(np.int32)
     fingers = np.stack([f // cols, f % cols], 1).astype(np.int32)
     return boards, fingers, ((meta >> 6) & 7).astype(np.uint8), ((meta >> 9) & 0xFFFF).astype(np.uint16)

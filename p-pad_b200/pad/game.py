@@ -10,7 +10,9 @@ Differences that are deliberate ("quirks"):
     reference's ``random.seed(datetime.now())``), not the process-global Mersenne Twister;
   * an unknown action string raises ValueError (the reference silently records it as accepted);
   * ``action is 'pass'`` identity tests become equality tests;
-  * orb types 7..9 and boards other than 5x6 / 6x7 raise (no kernel instantiation).
+  * orb types 7..9 (poison, mortal poison, bomb) switch the env to the 4-bit board kernels (orb_bits = 4), on
+    construction when the skyfall produces them, or as soon as a board holding one is handed in; boards other
+    than 4x5 / 5x6 / 6x7 raise (no kernel instantiation).
 """
 import random
 import time
@@ -80,15 +82,9 @@ class PAD:
         self.rng = rng
         self.clock = clock
         self._reseed()
-        try:
-            self._venv = BatchedPAD(1, dim_row, dim_col, skyfall=list(skyfall), skyfall_damage=skyfall_damage,
-                                    team=team, seed=self.seed, device=device, cascade_cap=0, reset_cap=0)
-        except _cabi.PPADError as e:
-            if e.status == _cabi.ERR_UNSUPPORTED:
-                raise NotImplementedError(e.detail)
-            raise Exception(e.detail)
+        self._device = device
+        self._make_venv(None)
         self._tick = 0            # Philox step counter: one per randomised call
-        self._io_setup()
 
         self.board = -1 * np.ones((self.dim_row, self.dim_col), dtype=int)
         self.locked = np.zeros((self.dim_row, self.dim_col), dtype=int)
@@ -103,6 +99,26 @@ class PAD:
         self.action_space = player.PlayerAction(finger=self.finger, dim_row=self.dim_row, dim_col=self.dim_col,
                                                 env=self, seed=self.seed)
         self.reset(board=board, finger=finger)
+
+    def _make_venv(self, orb_bits):
+        """(re)create the one-board device slab; orb_bits None = 4 only if the skyfall produces orb types 7..9"""
+        try:
+            self._venv = BatchedPAD(1, self.dim_row, self.dim_col, skyfall=list(self.skyfall),
+                                    skyfall_damage=self.skyfall_damage, team=self.team, seed=self.seed,
+                                    device=self._device, cascade_cap=0, reset_cap=0, orb_bits=orb_bits)
+        except _cabi.PPADError as e:
+            if e.status == _cabi.ERR_UNSUPPORTED:
+                raise NotImplementedError(e.detail)
+            raise Exception(e.detail)
+        self._io_setup()
+
+    def _fit_codes(self, board):
+        """A board with poison / mortal poison / bomb orbs (types 7..9, game.py:243-246) needs the 4-bit kernels."""
+        b = np.asarray(board)
+        if ((b < -1) | (b > 9)).any():
+            raise NotImplementedError('orb types are -1 (empty) and 0..9 (game.py:236-246)')
+        if self._venv.orb_bits == 3 and (b > 6).any():
+            self._make_venv(4)
 
     # ------------------------------------------------------------------ rng='reference': the host only draws numbers
     def _reseed(self):
@@ -126,8 +142,6 @@ class PAD:
         while True:
             state0 = random.getstate()
             orbs = np.array([self._draw_orb() for _ in range(k)], np.uint8)
-            if orbs.max(initial=0) > 6:
-                raise NotImplementedError('orb types 7..9 do not fit the 3-bit board state of ppad_b200')
             consumed = run(orbs)
             if consumed is not None and consumed <= k:
                 random.setstate(state0)
@@ -141,7 +155,7 @@ class PAD:
 
     # ------------------------------------------------------------------ device round trips
     # The env's board lives on the GPU as one packed record; `self.board` / `self.finger` are the host mirror the
-    # reference's callers read.  A step is ONE kernel launch plus ONE 48-byte read-back (state, reward, info, action);
+    # reference's callers read.  A step is ONE kernel launch plus ONE 80-byte read-back (state, reward, info, action);
     # the host only converts formats (layout.pack_state / unpack_state).  If a caller assigned or edited the mirror,
     # the record is re-packed before the next launch.
     def _next_tick(self):
@@ -153,10 +167,10 @@ class PAD:
         import torch
         v = self._venv
         self._torch, self._ctypes = torch, ctypes
-        # two 64-byte slots: [0] the env's record, [1] scratch for calculate_reward(board=...).
-        # slot layout: state 0..32 | reward 32..40 | info 40..44 | action 44
-        self._io = torch.zeros(128, dtype=torch.uint8, device=v.device)
-        self._io_host = torch.zeros(128, dtype=torch.uint8).pin_memory()
+        # two 128-byte slots: [0] the env's record, [1] scratch for calculate_reward(board=...).
+        # slot layout: state 0..64 (16..48 bytes used) | reward 64..72 | info 72..76 | action 76
+        self._io = torch.zeros(256, dtype=torch.uint8, device=v.device)
+        self._io_host = torch.zeros(256, dtype=torch.uint8).pin_memory()
         self._io_np = self._io_host.numpy()
         v.state = self._io[:4 * v.words].view(torch.int32).view(1, v.words)   # the env slab IS slot 0
         self._action_bytes = torch.arange(5, dtype=torch.uint8, device=v.device)
@@ -168,12 +182,12 @@ class PAD:
     def _write_slot(self, slot, board, finger, prev_id):
         from .. import layout
         b = np.asarray(board)
-        if ((b < -1) | (b > 6)).any():
-            raise NotImplementedError('orb types 7..9 do not fit the 3-bit board state of ppad_b200')
-        rec = layout.pack_state(b[None], np.asarray(finger).reshape(1, 2), [prev_id]).view(np.uint8).reshape(-1)
-        off = 64 * slot
+        self._fit_codes(b)
+        rec = layout.pack_state(b[None], np.asarray(finger).reshape(1, 2), [prev_id],
+                                orb_bits=self._venv.orb_bits).view(np.uint8).reshape(-1)
+        off = 128 * slot
         self._io_np[off:off + rec.size] = rec
-        self._io[off:off + 32].copy_(self._io_host[off:off + 32], non_blocking=True)
+        self._io[off:off + 64].copy_(self._io_host[off:off + 64], non_blocking=True)
 
     def _sync_to_device(self):
         cur = (self.board, self.finger, self._prev_id())
@@ -189,11 +203,11 @@ class PAD:
         if injected is not None:
             from .. import layout
             slab = torch.from_numpy(layout.pack_slab(np.asarray(injected, np.uint8)[None]).view(np.int32)).to(v.device)
-        base = self._io.data_ptr() + 64 * slot
+        base = self._io.data_ptr() + 128 * slot
         a = _cabi.StepArgs()
         a.n, a.env0, a.step = 1, v.env0, self._next_tick()
         a.skyfall_damage = -1 if skyfall_damage is None else int(bool(skyfall_damage))
-        a.state, a.reward, a.info, a.action_out = base, base + 32, base + 40, base + 44
+        a.state, a.reward, a.info, a.action_out = base, base + 64, base + 72, base + 76
         a.actions = self._action_bytes.data_ptr() + action_id
         if slab is not None:
             a.slab, a.slab_words, a.n_inj = slab.data_ptr(), slab.shape[1], len(injected)
@@ -204,28 +218,29 @@ class PAD:
             a.final_state, a.combo_log, a.log_cap = extra[0].data_ptr(), extra[1].data_ptr(), max(1, log_cap)
         with torch.cuda.device(v.device):
             _cabi.check(v.lib.ppad_step(v._ctx, self._ctypes.byref(a), v._stream()))
-        self._io_host[64 * slot:64 * slot + 48].copy_(self._io[64 * slot:64 * slot + 48])   # blocking read-back
-        raw = self._io_np[64 * slot:64 * slot + 48]
-        reward = np.float64(raw[32:40].view(np.float64)[0])
-        info = int(raw[40:44].view(np.uint32)[0])
-        return reward, info, int(raw[44]), extra
+        self._io_host[128 * slot:128 * slot + 80].copy_(self._io[128 * slot:128 * slot + 80])   # blocking read-back
+        raw = self._io_np[128 * slot:128 * slot + 80]
+        reward = np.float64(raw[64:72].view(np.float64)[0])
+        info = int(raw[72:76].view(np.uint32)[0])
+        return reward, info, int(raw[76]), extra
 
     def _pull(self):
         from .. import layout
         words = self._venv.words
         boards, fingers, _, _ = layout.unpack_state(self._io_np[:4 * words].view(np.uint32).reshape(1, words).copy(),
-                                                    self.dim_row, self.dim_col)
+                                                    self.dim_row, self.dim_col, orb_bits=self._venv.orb_bits)
         self.board = boards[0].astype(int)
         self.finger = fingers[0].astype(int)
         self._dev_shadow = (self.board.copy(), self.finger.copy(), self._dev_shadow[2] if self._dev_shadow else 4)
 
     def _push(self, board=None):
         """general path for the per-stage methods: (board or self.board, self.finger) -> slot 0 via ppad_pack"""
+        self._fit_codes(self.board if board is None else board)
         flags = self._venv.set_state(np.asarray(self.board if board is None else board)[None],
                                      np.asarray(self.finger).reshape(1, 2), prev=np.array([self._prev_id()], np.uint8))
         self._dev_shadow = None
         if int(flags[0]) & _cabi.FLAG_UNSUPPORTED_ORB:
-            raise NotImplementedError('orb types 7..9 do not fit the 3-bit board state of ppad_b200')
+            raise NotImplementedError('orb types are -1 (empty) and 0..9 (game.py:236-246)')
 
     # ------------------------------------------------------------------ game.py:122-155
     def apply_action(self, action):
@@ -310,6 +325,8 @@ class PAD:
         self.actions = []
         self.rewards = []
         self.action_space.previous_action = 'pass'
+        if board is not None:
+            self._fit_codes(board)      # poison / mortal poison / bomb orbs: the 4-bit kernels from here on
 
         self._reseed()
         if self.rng == 'reference':

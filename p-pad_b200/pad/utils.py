@@ -6,11 +6,11 @@ from . import parameters
 _slabs = {}
 
 
-def _slab(rows, cols):
-    key = (rows, cols)
+def _slab(rows, cols, orb_bits=3):
+    key = (rows, cols, orb_bits)
     if key not in _slabs:
         from ..batched import BatchedPAD
-        _slabs[key] = BatchedPAD(1, rows, cols)
+        _slabs[key] = BatchedPAD(1, rows, cols, orb_bits=orb_bits)
     return _slabs[key]
 
 
@@ -18,10 +18,10 @@ def cancel(board):
     """Cancel all 3+ connected orbs of `board` IN PLACE and return the combos, as ppad.pad.utils.cancel
     (utils.py:26-70): a list of {'color', 'N', 'enhanced', 'shape'} in the reference's order."""
     rows, cols = board.shape
-    venv = _slab(rows, cols)
+    venv = _slab(rows, cols, 4 if (np.asarray(board) > 6).any() else 3)   # types 7..9: the 4-bit kernels
     flags = venv.set_state(np.asarray(board)[None], np.zeros((1, 2), dtype=np.int64))
     if int(flags[0]):
-        raise NotImplementedError('orb types 7..9 do not fit the 3-bit board state of ppad_b200')
+        raise NotImplementedError('orb types are -1 (empty) and 0..9 (game.py:236-246)')
     n_combos, log = venv.cancel(log_cap=(rows * cols) // 3)
     n = int(n_combos[0])
     log = log[0, :n].cpu().numpy().view(np.uint16)

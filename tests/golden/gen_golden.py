@@ -90,7 +90,8 @@ def gen_kat(ref):
     print("kat.json:", len(cases), "cases")
 
 
-def gen_resolve(rows, cols, n_walk, n_adv, seed, tag, team=None, skyfall_rates=None):
+def gen_resolve(rows, cols, n_walk, n_adv, seed, tag, team=None, skyfall_rates=None, ncolors=6):
+    """ncolors = 10: boards and injected skyfall over ALL orb types of game.py:236-246 (poison, mortal poison, bomb)"""
     rng = np.random.default_rng(seed)
     env_on = rh.make_env(rows, cols, skyfall_damage=True, team=team)
     S = 512
@@ -101,12 +102,13 @@ def gen_resolve(rows, cols, n_walk, n_adv, seed, tag, team=None, skyfall_rates=N
         adversarial = len(recs) >= n_walk
         if adversarial:
             ncol = int(rng.integers(2, 5))
-            board = rng.integers(0, ncol, size=(rows, cols)).astype(np.int8)
+            pal = np.arange(ncol) if ncolors <= 6 else rng.permutation(np.array([0, 3, 5, 6, 7, 8, 9]))[:ncol]
+            board = pal[rng.integers(0, ncol, size=(rows, cols))].astype(np.int8)
             p = rng.dirichlet(np.ones(ncol) * 0.7)
-            orbs = rng.choice(ncol, size=S, p=p).astype(np.uint8)
+            orbs = pal[rng.choice(ncol, size=S, p=p)].astype(np.uint8)
         else:
-            board, _ = random_walk_board(rng, rows, cols, 6, 60)
-            orbs = rng.integers(0, 6, size=S).astype(np.uint8)
+            board, _ = random_walk_board(rng, rows, cols, ncolors, 60)
+            orbs = rng.integers(0, ncolors, size=S).astype(np.uint8)
         sd = bool(rng.random() < 0.85) or adversarial
         i += 1
         try:
@@ -387,6 +389,10 @@ def gen_mt_episodes():
 
 def main():
     ref = rh.load()
+    if "--all10" in sys.argv:      # only the fixtures of the 4-bit (orb types 0..9) kernels
+        gen_resolve(5, 6, 700, 150, 205, "5x6_all10", ncolors=10)
+        gen_resolve(6, 7, 300, 60, 206, "6x7_all10", ncolors=10)
+        return
     gen_kat(ref)
     gen_onehot(ref)
     gen_damage()
@@ -401,6 +407,8 @@ def main():
     gen_resolve(6, 7, 1000, 150, 202, "6x7")
     gen_resolve(5, 6, 400, 0, 203, "5x6_custom_team", team=CUSTOM_TEAM)
     gen_resolve(4, 5, 500, 60, 204, "4x5")
+    gen_resolve(5, 6, 700, 150, 205, "5x6_all10", ncolors=10)
+    gen_resolve(6, 7, 300, 60, 206, "6x7_all10", ncolors=10)
 
 
 if __name__ == "__main__":

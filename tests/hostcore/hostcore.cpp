@@ -12,6 +12,27 @@
 
 using namespace ppad;
 
+// geom: 0 = 5x6, 1 = 6x7, 2 = 4x5 (3-bit orb codes); 3..5 = the same boards with 4-bit codes
+#define HC_DISPATCH(geom, EXPR)                                  \
+    do {                                                         \
+        if ((geom) == 0) { typedef Geom<5, 6> G; EXPR; }         \
+        else if ((geom) == 1) { typedef Geom<6, 7> G; EXPR; }    \
+        else if ((geom) == 2) { typedef Geom<4, 5> G; EXPR; }    \
+        else if ((geom) == 3) { typedef Geom<5, 6, 4> G; EXPR; } \
+        else if ((geom) == 4) { typedef Geom<6, 7, 4> G; EXPR; } \
+        else { typedef Geom<4, 5, 4> G; EXPR; }                  \
+    } while (0)
+
+static int shape_geom(int rows, int cols, int orb_bits)
+{
+    int g;
+    if (rows == 5 && cols == 6) g = 0;
+    else if (rows == 6 && cols == 7) g = 1;
+    else if (rows == 4 && cols == 5) g = 2;
+    else return -1;
+    return orb_bits == 4 ? g + 3 : g;
+}
+
 namespace {
 
 template <class G>
@@ -134,15 +155,8 @@ int hostcore_step_batch(const ppad_config *cfg, int64_t n, uint64_t env0, uint32
     p.n_inj = slab ? n_inj : -1;
     p.slab_words = slab_words;
     p.log_cap = log_cap;
-    if (geom == 0)
-        step_batch<Geom<5, 6>>(p, n, env0, boards, fingers, prev, moves, actions, slab, action_out, reward, info,
-                               final_boards, combo_log, paths, path_words, path_lens);
-    else if (geom == 2)
-        step_batch<Geom<4, 5>>(p, n, env0, boards, fingers, prev, moves, actions, slab, action_out, reward, info,
-                               final_boards, combo_log, paths, path_words, path_lens);
-    else
-        step_batch<Geom<6, 7>>(p, n, env0, boards, fingers, prev, moves, actions, slab, action_out, reward, info,
-                               final_boards, combo_log, paths, path_words, path_lens);
+    HC_DISPATCH(geom, (step_batch<G>(p, n, env0, boards, fingers, prev, moves, actions, slab, action_out, reward, info,
+                                     final_boards, combo_log, paths, path_words, path_lens)));
     return 0;
 }
 
@@ -156,40 +170,36 @@ int hostcore_reset(const ppad_config *cfg, int64_t n, uint64_t env0, uint32_t st
     p.key.step = step;
     p.n_inj = slab ? n_inj : -1;
     p.slab_words = slab_words;
-    if (geom == 0) reset_batch<Geom<5, 6>>(p, n, env0, slab, fingers_in, boards, fingers, flags, consumed);
-    else if (geom == 2) reset_batch<Geom<4, 5>>(p, n, env0, slab, fingers_in, boards, fingers, flags, consumed);
-    else reset_batch<Geom<6, 7>>(p, n, env0, slab, fingers_in, boards, fingers, flags, consumed);
+    HC_DISPATCH(geom, (reset_batch<G>(p, n, env0, slab, fingers_in, boards, fingers, flags, consumed)));
     return 0;
 }
 
-int hostcore_cancel(int rows, int cols, int64_t n, int8_t *boards, uint8_t *n_combos, uint16_t *combo_log, int log_cap)
+int hostcore_cancel(int rows, int cols, int orb_bits, int64_t n, int8_t *boards, uint8_t *n_combos, uint16_t *combo_log,
+                    int log_cap)
 {
-    if (rows == 5 && cols == 6) cancel_batch<Geom<5, 6>>(n, boards, n_combos, combo_log, log_cap);
-    else if (rows == 4 && cols == 5) cancel_batch<Geom<4, 5>>(n, boards, n_combos, combo_log, log_cap);
-    else if (rows == 6 && cols == 7) cancel_batch<Geom<6, 7>>(n, boards, n_combos, combo_log, log_cap);
-    else return 2;
+    const int geom = shape_geom(rows, cols, orb_bits);
+    if (geom < 0) return 2;
+    HC_DISPATCH(geom, (cancel_batch<G>(n, boards, n_combos, combo_log, log_cap)));
     return 0;
 }
 
-int hostcore_drop(int rows, int cols, int64_t n, int8_t *boards)
+int hostcore_drop(int rows, int cols, int orb_bits, int64_t n, int8_t *boards)
 {
-    if (rows == 5 && cols == 6) drop_batch<Geom<5, 6>>(n, boards);
-    else if (rows == 4 && cols == 5) drop_batch<Geom<4, 5>>(n, boards);
-    else if (rows == 6 && cols == 7) drop_batch<Geom<6, 7>>(n, boards);
-    else return 2;
+    const int geom = shape_geom(rows, cols, orb_bits);
+    if (geom < 0) return 2;
+    HC_DISPATCH(geom, (drop_batch<G>(n, boards)));
     return 0;
 }
 
-int hostcore_obs(int rows, int cols, int64_t n, const int8_t *boards, const int32_t *fingers, uint8_t *out)
+int hostcore_obs(int rows, int cols, int orb_bits, int64_t n, const int8_t *boards, const int32_t *fingers, uint8_t *out)
 {
-    if (rows == 5 && cols == 6) obs_batch<Geom<5, 6>>(n, boards, fingers, out);
-    else if (rows == 4 && cols == 5) obs_batch<Geom<4, 5>>(n, boards, fingers, out);
-    else if (rows == 6 && cols == 7) obs_batch<Geom<6, 7>>(n, boards, fingers, out);
-    else return 2;
+    const int geom = shape_geom(rows, cols, orb_bits);
+    if (geom < 0) return 2;
+    HC_DISPATCH(geom, (obs_batch<G>(n, boards, fingers, out)));
     return 0;
 }
 
-int hostcore_sky_table(const ppad_config *cfg, uint32_t thr[7], uint32_t *valid)
+int hostcore_sky_table(const ppad_config *cfg, uint32_t thr[10], uint32_t *valid)
 {
     StepParams p;
     int geom;
@@ -204,7 +214,7 @@ int hostcore_orb_from_u32(const ppad_config *cfg, uint32_t x)
     StepParams p;
     int geom;
     if (build_params(*cfg, p, geom, g_err)) return -1;
-    return orb_from_u32(p.sky, x);
+    return geom >= 3 ? orb_from_u32<10>(p.sky, x) : orb_from_u32<7>(p.sky, x);
 }
 
 void hostcore_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])

@@ -21,7 +21,7 @@ def lib():
     return _lib
 
 
-def cfg_from_oracle(o):
+def cfg_from_oracle(o, orb_bits=None):
     """oracle.Cfg -> ppad_config (same fields, different struct)"""
     cfg = _cabi.Config()
     cfg.rows, cfg.cols, cfg.skyfall_damage = o.rows, o.cols, o.skyfall_damage
@@ -30,6 +30,7 @@ def cfg_from_oracle(o):
         cfg.team_color_1[i], cfg.team_color_2[i], cfg.team_atk[i] = o.team_c1[i], o.team_c2[i], o.team_atk[i]
     for i in range(10):
         cfg.skyfall[i] = o.skyfall[i]
+    cfg.orb_bits = 4 if (orb_bits == 4 or any(o.skyfall[i] > 0 for i in range(7, 10))) else 3
     return cfg
 
 
@@ -81,28 +82,29 @@ def reset(cfg, n, inj=None, env0=0, step=0, fingers_in=None):
     return boards, fingers, flags, consumed
 
 
-def cancel(boards, log_cap=32):
+def cancel(boards, log_cap=32, orb_bits=3):
     n, rows, cols = boards.shape
     n_combos = np.zeros(n, np.uint8)
     log = np.zeros((n, log_cap), np.uint16)
-    assert lib().hostcore_cancel(rows, cols, C.c_int64(n), _p(boards), _p(n_combos), _p(log), log_cap) == 0
+    assert lib().hostcore_cancel(rows, cols, orb_bits, C.c_int64(n), _p(boards), _p(n_combos), _p(log), log_cap) == 0
     return n_combos, log
 
 
-def drop(boards):
+def drop(boards, orb_bits=3):
     n, rows, cols = boards.shape
-    assert lib().hostcore_drop(rows, cols, C.c_int64(n), _p(boards)) == 0
+    assert lib().hostcore_drop(rows, cols, orb_bits, C.c_int64(n), _p(boards)) == 0
 
 
-def obs(boards, fingers):
+def obs(boards, fingers, orb_bits=3):
     n, rows, cols = boards.shape
     out = np.zeros((n, rows, cols, 7), np.uint8)
-    assert lib().hostcore_obs(rows, cols, C.c_int64(n), _p(boards), _p(np.ascontiguousarray(fingers, np.int32)), _p(out)) == 0
+    assert lib().hostcore_obs(rows, cols, orb_bits, C.c_int64(n), _p(boards), _p(np.ascontiguousarray(fingers, np.int32)),
+                              _p(out)) == 0
     return out
 
 
 def sky_table(cfg):
-    thr = (C.c_uint32 * 7)()
+    thr = (C.c_uint32 * 10)()
     valid = C.c_uint32(0)
     r = lib().hostcore_sky_table(C.byref(cfg), thr, C.byref(valid))
     if r:

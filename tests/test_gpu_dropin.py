@@ -445,3 +445,43 @@ def test_reference_rng_mode_replays_the_references_own_episodes(pb, rows, cols):
         env.step('pass')
         assert bits(env.rewards[-1]) == bits(z["pass_reward2" + s][e])
         assert random.random() == z["mt_after" + s][e]
+
+
+def test_pad_facade_with_poison_and_bomb_orbs(pb):
+    """orb types 7..9 (poison, mortal poison, bomb; game.py:243-246): the facade moves to the 4-bit kernels when the
+    skyfall produces them or when a board holding one is handed in; results against the oracle (itself pinned on
+    the reference-generated resolve_*_all10 fixtures)."""
+    z = np.load(os.path.join(G, "resolve_5x6_all10.npz"))
+    pick = [i for i in range(len(z["boards"])) if z["boards"][i].max() > 6][:40]
+    env = pb.PAD(skyfall_damage=False, seed=3)
+    assert env._venv.orb_bits == 3
+    for i in pick:
+        board = z["boards"][i].astype(int)
+        env.reset(board=board, finger=[0, 0])
+        assert env._venv.orb_bits == 4 and np.array_equal(env.board, board)
+        if not z["skyfall_damage"][i]:
+            env.step('pass')
+            assert bits(env.rewards[-1]) == bits(z["reward"][i]) and np.array_equal(env.board, board)
+        got = env.calculate_reward(board=board, skyfall_damage=False)
+        want = orc.resolve(orc.make_cfg(5, 6, False), z["boards"][i], inj=None)
+        assert bits(got) == bits(want["reward"])
+        # the free function of utils.py:26-70 on the same board
+        b2 = board.copy()
+        combos = pb.pad.utils.cancel(b2)
+        ob = z["boards"][i].copy()
+        ocombos = orc.cancel(ob)
+        assert [(pb.pad.parameters.english2int[c['color']], int(c['N'])) for c in combos] == ocombos
+        assert np.array_equal(b2, ob)
+    # a skyfall that produces them: 4-bit from the start, moves and passes against the oracle with Philox skyfall
+    sky = [0.1] * 10
+    env = pb.PAD(skyfall=sky, seed=77)
+    assert env._venv.orb_bits == 4
+    seen = set()
+    for ep in range(6):
+        env.reset()
+        seen |= set(np.unique(env.board).tolist())
+        for t in range(8):
+            env.step(env.action_space.sample())
+        env.step('pass')
+        assert env.rewards[-1] >= 0
+    assert seen >= {7, 8, 9}

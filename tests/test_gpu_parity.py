@@ -37,6 +37,11 @@ def random_boards(rng, n, rows, cols, kind):
         b = rng.integers(0, 6, size=(n, rows, cols))
     elif kind == "few":
         b = rng.integers(0, 3, size=(n, rows, cols))
+    elif kind == "all10":                                   # every orb type of game.py:236-246 and empties
+        b = rng.integers(-1, 10, size=(n, rows, cols))
+    elif kind == "poison_few":                              # few colours, among them types 7..9: big islands
+        pal = np.array([0, 7, 8, 9, 5])[: rng.integers(2, 6)]
+        b = pal[rng.integers(0, len(pal), size=(n, rows, cols))]
     else:
         b = rng.integers(-1, 7, size=(n, rows, cols))
     return np.ascontiguousarray(b, np.int8)
@@ -73,25 +78,37 @@ def test_kat_through_cabi(pb):
     assert env.get_state(o.final_state).boards[0].cpu().numpy().tolist() == c["final_board"]
 
 
-@pytest.mark.parametrize("tag,rows,cols,team", [("5x6", 5, 6, None), ("6x7", 6, 7, None), ("4x5", 4, 5, None),
-                                                 ("5x6_custom_team", 5, 6, "custom")])
-def test_resolve_golden_vectors(pb, tag, rows, cols, team):
+@pytest.mark.parametrize("tag,rows,cols,team,orb_bits", [
+    ("5x6", 5, 6, None, 3), ("6x7", 6, 7, None, 3), ("4x5", 4, 5, None, 3), ("5x6_custom_team", 5, 6, "custom", 3),
+    ("5x6", 5, 6, None, 4), ("6x7", 6, 7, None, 4), ("5x6_all10", 5, 6, None, 4), ("6x7_all10", 6, 7, None, 4)])
+def test_resolve_golden_vectors(pb, tag, rows, cols, team, orb_bits):
+    """what the reference produced, through the C ABI: with the combo log (islands in the reference's order) and
+    without it (the colour-major tally of the production path), with the one-thread-per-board kernel (obs asked
+    for) and the pooled kernel; *_all10 = all ten orb types of game.py:236-246 on the 4-bit kernels"""
     z = np.load(os.path.join(G, "resolve_%s.npz" % tag))
     t = json.load(open(os.path.join(G, "custom_team.json"))) if team else None
     for sd in (0, 1):
         sel = np.nonzero(z["skyfall_damage"] == sd)[0]
         k = len(sel)
-        env = pb.BatchedPAD(k, rows, cols, skyfall_damage=bool(sd), team=t, cascade_cap=0)
-        env.set_state(z["boards"][sel], np.zeros((k, 2), int))
-        out = env.calculate_reward(injected=z["orbs"][sel], want_final=True, log_cap=64)
-        info = u32(out.info)
-        assert np.array_equal(bits(out.reward.cpu().numpy()), bits(z["reward"][sel]))
-        assert np.array_equal(info & 0xFF, np.minimum(z["n_combos"][sel], 255))
-        assert np.array_equal((info >> 8) & 0xFF, z["depth"][sel])
-        assert np.array_equal((info >> 16) & 0xFF, np.minimum(z["consumed"][sel], 255))
-        assert not (info >> 24).any()
-        assert np.array_equal(env.get_state(out.final_state).boards.cpu().numpy(), z["final_boards"][sel])
-        assert np.array_equal(out.combo_log.cpu().numpy().view(np.uint16), z["combo_log"][sel])
+        env = pb.BatchedPAD(k, rows, cols, skyfall_damage=bool(sd), team=t, cascade_cap=0, orb_bits=orb_bits)
+        assert env.orb_bits == orb_bits
+        for log_cap, obs in ((64, None), (0, None), (0, 'u8')):
+            env.set_state(z["boards"][sel], np.zeros((k, 2), int))
+            acts = torch.full((k,), 4, dtype=torch.uint8, device=env.device)
+            out = env.step(acts, injected=z["orbs"][sel], want_final=True, log_cap=log_cap, obs=obs)
+            info = u32(out.info)
+            assert np.array_equal(bits(out.reward.cpu().numpy()), bits(z["reward"][sel]))
+            assert np.array_equal(info & 0xFF, np.minimum(z["n_combos"][sel], 255))
+            assert np.array_equal((info >> 8) & 0xFF, z["depth"][sel])
+            assert np.array_equal((info >> 16) & 0xFF, np.minimum(z["consumed"][sel], 255))
+            assert not (info >> 24).any()
+            assert np.array_equal(env.get_state(out.final_state).boards.cpu().numpy(), z["final_boards"][sel])
+            assert np.array_equal(env.get_state().boards.cpu().numpy(), z["boards"][sel])   # a pass leaves the board alone
+            if log_cap:
+                assert np.array_equal(out.combo_log.cpu().numpy().view(np.uint16), z["combo_log"][sel])
+            if obs:
+                want = orc.onehot(z["boards"][sel], np.zeros((k, 2), np.int32))
+                assert np.array_equal(out.obs.cpu().numpy(), want.astype(np.uint8))
 
 
 @pytest.mark.parametrize("tag,rows,cols", [("5x6", 5, 6), ("6x7", 6, 7)])
@@ -114,22 +131,32 @@ def test_episode_golden_vectors(pb, tag, rows, cols):
 
 
 @pytest.mark.parametrize("rows,cols", [(4, 5), (5, 6), (6, 7)])
-@pytest.mark.parametrize("mode", ["injected", "philox", "injected_short", "no_skyfall"])
+@pytest.mark.parametrize("mode", ["injected", "philox", "injected_short", "no_skyfall", "wide_injected", "wide_philox",
+                                  "wide3_philox"])
 def test_step_fuzz_vs_oracle(pb, rows, cols, mode):
+    """wide_*: the 4-bit kernels with all ten orb types of game.py:236-246 in the boards, the skyfall rates and the
+    injected sequences; wide3_philox: the 4-bit kernels on a workload of the 3-bit ones"""
     rng = np.random.default_rng(2000 + rows + len(mode))
     n, steps = 50000 + 17, 8
     seed = 0x1234567890ABCDEF
-    ocfg = orc.make_cfg(rows, cols, skyfall_damage=(mode != "no_skyfall"), seed=seed)
-    env = pb.BatchedPAD(n, rows, cols, skyfall_damage=(mode != "no_skyfall"), seed=seed, env0=(1 << 32) - 1000)
-    kind = ["uniform6", "few", "jammer_empty"][rows % 3] if mode != "philox" else "uniform6"
+    all10 = mode in ("wide_injected", "wide_philox")
+    sky = [0.05, 0.15, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1] if all10 else None
+    ocfg = orc.make_cfg(rows, cols, skyfall_damage=(mode != "no_skyfall"), seed=seed, skyfall=sky)
+    env = pb.BatchedPAD(n, rows, cols, skyfall_damage=(mode != "no_skyfall"), seed=seed, env0=(1 << 32) - 1000,
+                        skyfall=sky, orb_bits=4 if mode == "wide3_philox" else None)
+    assert env.orb_bits == (4 if mode.startswith("wide") else 3)
+    kind = ["uniform6", "few", "jammer_empty"][rows % 3] if not mode.endswith("philox") else "uniform6"
+    if all10:
+        kind = ["all10", "poison_few", "all10"][rows % 3]
     boards = random_boards(rng, n, rows, cols, kind)
     fingers = np.stack([rng.integers(0, rows, n), rng.integers(0, cols, n)], 1).astype(np.int32)
     prev = np.full(n, 4, np.uint8)
     moves = np.zeros(n, np.uint16)
     assert not env.set_state(boards, fingers).any()
-    S = {"injected": 256, "philox": 0, "injected_short": 8, "no_skyfall": 16}[mode]
+    S = {"injected": 256, "philox": 0, "injected_short": 8, "no_skyfall": 16, "wide_injected": 256, "wide_philox": 0,
+         "wide3_philox": 0}[mode]
     for t in range(steps):
-        inj = rng.integers(0, 6, size=(n, S)).astype(np.uint8) if S else None
+        inj = rng.integers(0, 10 if all10 else 6, size=(n, S)).astype(np.uint8) if S else None
         actions = None if t % 3 == 2 else rng.integers(0, 5, size=n).astype(np.uint8)
         if t == 4:
             actions[:50] = 9
@@ -180,6 +207,11 @@ def test_obs_golden(pb):
         want = z["states_" + s].copy()
         assert np.array_equal(env.encode_obs('u8').cpu().numpy(), want)   # 6..9 and -1 are all-zero channels anyway
         assert np.array_equal(env.encode_obs('f32').cpu().numpy(), want.astype(np.float32))
+        # the 4-bit kernels take the reference's boards as they are
+        wide = pb.BatchedPAD(len(b), rows, cols, orb_bits=4)
+        assert z["boards_" + s].max() > 6 and not wide.set_state(z["boards_" + s], z["fingers_" + s]).any()
+        assert np.array_equal(wide.encode_obs('u8').cpu().numpy(), want)
+        assert np.array_equal(wide.encode_obs('f32').cpu().numpy(), want.astype(np.float32))
 
 
 def test_pack_unpack_and_unsupported_orbs(pb):
@@ -203,6 +235,17 @@ def test_pack_unpack_and_unsupported_orbs(pb):
         ok = ~bad
         host = pb.layout.pack_state(want[ok], fingers[ok], prev[ok], moves[ok])
         assert np.array_equal(env.state.cpu().numpy().view(np.uint32)[ok], host)
+        # the 4-bit state takes every orb type of game.py:236-246; 10 and above are still refused
+        wide = pb.BatchedPAD(n, rows, cols, orb_bits=4)
+        assert wide.state.shape[1] * 4 == wide.lib.ppad_state_bytes_ex(rows, cols, 4) == (32 if rows == 5 else 48)
+        assert not wide.set_state(boards, fingers, prev, moves.view(np.int16)).any()
+        st = wide.get_state()
+        assert np.array_equal(st.boards.cpu().numpy(), boards) and np.array_equal(st.fingers.cpu().numpy(), fingers)
+        assert np.array_equal(st.prev.cpu().numpy(), prev) and np.array_equal(st.moves.cpu().numpy().view(np.uint16), moves)
+        assert np.array_equal(wide.state.cpu().numpy().view(np.uint32), pb.layout.pack_state(boards, fingers, prev, moves, orb_bits=4))
+        b2 = boards.copy()
+        b2[::7, 0, 0] = 10
+        assert np.array_equal(wide.set_state(b2, fingers).cpu().numpy() != 0, (b2 > 9).any(axis=(1, 2)))
 
 
 def test_reset_golden_and_properties(pb):
@@ -317,8 +360,12 @@ def test_empty_batch_and_errors(pb):
     with pytest.raises(pb._cabi.PPADError) as e:
         pb.BatchedPAD(4, skyfall=[0.5, 0.4, 0, 0, 0, 0, 0, 0, 0, 0])
     assert "add up to 1" in str(e.value)
-    with pytest.raises(pb._cabi.PPADError):
-        pb.BatchedPAD(4, skyfall=[0.5, 0.4, 0, 0, 0, 0, 0, 0, 0, 0.1])
+    with pytest.raises(pb._cabi.PPADError) as e:      # bombs do not fit the 3-bit state ...
+        pb.BatchedPAD(4, skyfall=[0.5, 0.4, 0, 0, 0, 0, 0, 0, 0, 0.1], orb_bits=3)
+    assert "orb_bits = 4" in str(e.value)
+    assert pb.BatchedPAD(4, skyfall=[0.5, 0.4, 0, 0, 0, 0, 0, 0, 0, 0.1]).orb_bits == 4   # ... so they get the 4-bit one
+    with pytest.raises(ValueError):
+        pb.BatchedPAD(4, orb_bits=5)
 
 
 def test_launch_counter_counts_kernels(pb):

@@ -25,19 +25,25 @@ def random_boards(rng, n, rows, cols, kind):
         b = rng.integers(0, rng.integers(2, 5), size=(n, rows, cols))
     elif kind == "jammer_empty":
         b = rng.integers(-1, 7, size=(n, rows, cols))
+    elif kind == "all10":                                   # every orb type of game.py:236-246 and empties
+        b = rng.integers(-1, 10, size=(n, rows, cols))
+    elif kind == "poison_few":                              # few colours, among them types 7..9: big islands
+        pal = np.array([0, 7, 8, 9, 5])[: rng.integers(2, 6)]
+        b = pal[rng.integers(0, len(pal), size=(n, rows, cols))]
     else:
         raise ValueError(kind)
     return np.ascontiguousarray(b, np.int8)
 
 
 @pytest.mark.parametrize("rows,cols", [(4, 5), (5, 6), (6, 7)])
-@pytest.mark.parametrize("kind", ["uniform6", "few", "jammer_empty"])
-def test_cancel_and_drop_fuzz(rows, cols, kind):
-    rng = np.random.default_rng(hash((rows, kind)) & 0xFFFF)
+@pytest.mark.parametrize("kind,orb_bits", [("uniform6", 3), ("few", 3), ("jammer_empty", 3), ("uniform6", 4),
+                                           ("jammer_empty", 4), ("all10", 4), ("poison_few", 4)])
+def test_cancel_and_drop_fuzz(rows, cols, kind, orb_bits):
+    rng = np.random.default_rng(sum(map(ord, kind)) * 7 + rows + orb_bits)
     n = 4000
     boards = random_boards(rng, n, rows, cols, kind)
     mine = boards.copy()
-    n_combos, log = hc.cancel(mine, log_cap=32)
+    n_combos, log = hc.cancel(mine, log_cap=32, orb_bits=orb_bits)
     for i in range(n):
         b = boards[i].copy()
         combos = orc.cancel(b)
@@ -46,27 +52,36 @@ def test_cancel_and_drop_fuzz(rows, cols, kind):
         assert np.array_equal(b, mine[i]), i
         orc.drop(b)
         boards[i] = b
-    hc.drop(mine)
+    hc.drop(mine, orb_bits=orb_bits)
     assert np.array_equal(mine, boards)
 
 
 @pytest.mark.parametrize("rows,cols", [(4, 5), (5, 6), (6, 7)])
-@pytest.mark.parametrize("mode", ["injected", "philox", "injected_short", "no_skyfall"])
+@pytest.mark.parametrize("mode", ["injected", "philox", "injected_short", "no_skyfall", "wide_injected", "wide_philox",
+                                  "wide3_injected"])
 def test_step_batch_fuzz(rows, cols, mode):
+    """wide_*: the 4-bit kernels with all ten orb types (skyfall rates and injected orbs for types 7..9);
+    wide3_injected: the 4-bit kernels on a workload the 3-bit kernels also run"""
     rng = np.random.default_rng(1000 + rows + len(mode))
     n, steps = 3000, 12
-    ocfg = orc.make_cfg(rows, cols, skyfall_damage=(mode != "no_skyfall"), seed=0x1234567890ABCDEF)
-    cfg = hc.cfg_from_oracle(ocfg)
-    kind = ["uniform6", "few", "jammer_empty"][rows % 3] if mode != "philox" else "uniform6"
+    wide = mode.startswith("wide")
+    sky = [0.05, 0.15, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1] if mode in ("wide_injected", "wide_philox") else None
+    ocfg = orc.make_cfg(rows, cols, skyfall_damage=(mode != "no_skyfall"), seed=0x1234567890ABCDEF, skyfall=sky)
+    cfg = hc.cfg_from_oracle(ocfg, orb_bits=4 if wide else None)
+    kind = ["uniform6", "few", "jammer_empty"][rows % 3] if not mode.endswith("philox") else "uniform6"
+    if sky:
+        kind = ["all10", "poison_few", "all10"][rows % 3]
     boards = random_boards(rng, n, rows, cols, kind)
     fingers = np.stack([rng.integers(0, rows, n), rng.integers(0, cols, n)], 1).astype(np.int32)
     prev = np.full(n, 4, np.uint8)
     moves = np.zeros(n, np.uint16)
     mine = [boards.copy(), fingers.copy(), prev.copy(), moves.copy()]
-    S = {"injected": 256, "philox": 0, "injected_short": 8, "no_skyfall": 16}[mode]
+    S = {"injected": 256, "philox": 0, "injected_short": 8, "no_skyfall": 16, "wide_injected": 256, "wide_philox": 0,
+         "wide3_injected": 256}[mode]
+    top = 10 if sky else 6
     seen_flags = 0
     for t in range(steps):
-        inj = rng.integers(0, 6, size=(n, S)).astype(np.uint8) if S else None
+        inj = rng.integers(0, top, size=(n, S)).astype(np.uint8) if S else None
         if t % 3 == 2:
             actions = None                                   # in-kernel random policy
         else:
@@ -123,29 +138,33 @@ def test_cascade_cap_flag():
     assert ((i0 >> 24) & orc.FLAG_CASCADE_CAP).all() and (((i0 >> 8) & 0xFF) == 7).all()
 
 
-@pytest.mark.parametrize("tag,rows,cols,team", [("5x6", 5, 6, None), ("6x7", 6, 7, None), ("4x5", 4, 5, None),
-                                                 ("5x6_custom_team", 5, 6, "custom")])
-def test_resolve_golden_vectors(tag, rows, cols, team):
-    """straight against what the reference produced"""
+@pytest.mark.parametrize("tag,rows,cols,team,orb_bits", [
+    ("5x6", 5, 6, None, 3), ("6x7", 6, 7, None, 3), ("4x5", 4, 5, None, 3), ("5x6_custom_team", 5, 6, "custom", 3),
+    ("5x6", 5, 6, None, 4), ("6x7", 6, 7, None, 4), ("5x6_all10", 5, 6, None, 4), ("6x7_all10", 6, 7, None, 4)])
+def test_resolve_golden_vectors(tag, rows, cols, team, orb_bits):
+    """straight against what the reference produced; with the combo log (islands in the reference's order) and
+    without it (the colour-major tally the production kernels run)"""
     z = np.load(os.path.join(G, "resolve_%s.npz" % tag))
     t = json.load(open(os.path.join(G, "custom_team.json"))) if team else None
     n = len(z["boards"])
     for sd in (0, 1):
         sel = np.nonzero(z["skyfall_damage"] == sd)[0]
-        cfg = hc.cfg_from_oracle(orc.make_cfg(rows, cols, skyfall_damage=sd, team=t, cascade_cap=0))
-        boards = np.ascontiguousarray(z["boards"][sel])
+        cfg = hc.cfg_from_oracle(orc.make_cfg(rows, cols, skyfall_damage=sd, team=t, cascade_cap=0), orb_bits=orb_bits)
         k = len(sel)
-        _, reward, info, final, log = hc.step_batch(
-            cfg, boards, np.zeros((k, 2), np.int32), np.full(k, 4, np.uint8), None, actions=np.full(k, 4, np.uint8),
-            inj=np.ascontiguousarray(z["orbs"][sel]), want_final=True, log_cap=64)
-        assert np.array_equal(bits(reward), bits(z["reward"][sel]))
-        assert np.array_equal(info & 0xFF, np.minimum(z["n_combos"][sel], 255))
-        assert np.array_equal((info >> 8) & 0xFF, z["depth"][sel])
-        assert np.array_equal((info >> 16) & 0xFF, np.minimum(z["consumed"][sel], 255))
-        assert not (info >> 24).any()
-        assert np.array_equal(final, z["final_boards"][sel])
-        assert np.array_equal(log, z["combo_log"][sel])
-    assert n >= 400
+        for log_cap in (64, 0):
+            boards = np.ascontiguousarray(z["boards"][sel])
+            _, reward, info, final, log = hc.step_batch(
+                cfg, boards, np.zeros((k, 2), np.int32), np.full(k, 4, np.uint8), None, actions=np.full(k, 4, np.uint8),
+                inj=np.ascontiguousarray(z["orbs"][sel]), want_final=True, log_cap=log_cap)
+            assert np.array_equal(bits(reward), bits(z["reward"][sel]))
+            assert np.array_equal(info & 0xFF, np.minimum(z["n_combos"][sel], 255))
+            assert np.array_equal((info >> 8) & 0xFF, z["depth"][sel])
+            assert np.array_equal((info >> 16) & 0xFF, np.minimum(z["consumed"][sel], 255))
+            assert not (info >> 24).any()
+            assert np.array_equal(final, z["final_boards"][sel])
+            if log_cap:
+                assert np.array_equal(log, z["combo_log"][sel])
+    assert n >= 360
 
 
 def test_kat_golden():
@@ -193,6 +212,12 @@ def test_obs_mask_matches_onehot(rows, cols):
     s = "%dx%d" % (rows, cols)
     b = np.where(z["boards_" + s] > 6, -1, z["boards_" + s]).astype(np.int8)
     assert np.array_equal(hc.obs(b, z["fingers_" + s]), z["states_" + s])
+    # the 4-bit kernels take the reference's boards as they are (orb types up to 9)
+    raw = np.ascontiguousarray(z["boards_" + s], np.int8)
+    assert raw.max() > 6
+    assert np.array_equal(hc.obs(raw, z["fingers_" + s], orb_bits=4), z["states_" + s])
+    wide = random_boards(rng, n, rows, cols, "all10")
+    assert np.array_equal(hc.obs(wide, fingers, orb_bits=4), orc.onehot(wide, fingers).astype(np.uint8))
 
 
 def test_sky_thresholds_match_float_rule():

@@ -49,13 +49,16 @@ def test_kat_moves_then_skyfall():
 
 
 @pytest.mark.parametrize("tag,rows,cols,team", [("5x6", 5, 6, None), ("6x7", 6, 7, None), ("4x5", 4, 5, None),
-                                                 ("5x6_custom_team", 5, 6, "custom")])
+                                                 ("5x6_custom_team", 5, 6, "custom"), ("5x6_all10", 5, 6, None),
+                                                 ("6x7_all10", 6, 7, None)])
 def test_resolve_vectors(tag, rows, cols, team):
     z = np.load(os.path.join(G, "resolve_%s.npz" % tag))
     t = json.load(open(os.path.join(G, "custom_team.json"))) if team else None
     cfgs = {sd: orc.make_cfg(rows, cols, skyfall_damage=sd, team=t, cascade_cap=0) for sd in (0, 1)}
     n = len(z["boards"])
-    assert n >= 400
+    assert n >= 360
+    if tag.endswith("all10"):
+        assert z["boards"].max() == 9 and z["orbs"].max() == 9      # poison, mortal poison and bomb orbs take part
     for i in range(n):
         r = orc.resolve(cfgs[int(z["skyfall_damage"][i])], z["boards"][i], inj=z["orbs"][i])
         assert bits(r["reward"]) == bits(z["reward"][i]), i
