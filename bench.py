@@ -366,11 +366,24 @@ def main():
         total = n * world
         ms_per_step = ms / K
         achieved = BYTES_WITH_OBS * n / (ms_per_step * 1e-3) / 1e9          # GB/s per GPU (max-over-ranks time)
-        traffic = None
+        traffic, prof = None, {}
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["step_kernel_obs_bytes_per_launch"]
+            prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = prof["step_kernel_obs_bytes_per_launch"]
         except Exception:
             pass
+        # integer-issue roofline of the state-only and rollout kernels: warp instructions per launch (ncu, static) over
+        # the launch time measured here, against SMs x 4 schedulers x 1 warp instruction per clock at the sampled clock
+        sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+        issue_peak = sm_count * 4 * (clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0) * 1e6
+
+        def issue(inst, ms_launch):
+            if not inst:
+                return None
+            rate = inst / (ms_launch * 1e-3)
+            return {"warp_instructions_per_launch": inst, "achieved": rate / 1e9, "peak": issue_peak / 1e9,
+                    "unit": "G warp-instr/s", "frac": rate / issue_peak,
+                    "note": "instruction count from the ncu capture under profiles/ (same kernel, same workload)"}
         line = {
             "metric": "env_steps_per_sec_incl_cascades", "value": total * K / (ms * 1e-3), "unit": "steps/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -381,7 +394,8 @@ def main():
                          "algorithmic_bytes_per_board": BYTES_WITH_OBS},
             "state_only": {"value": total / (so_ms * 1e-3), "unit": "steps/s", "ms_per_step": so_ms,
                            "hbm_gbs": BYTES_STATE_ONLY * n / (so_ms * 1e-3) / 1e9,
-                           "note": "same kernel without the obs stream; L2 flushed (256 MiB fill) before every step"},
+                           "issue": issue(prof.get("step_pool_warp_instructions_per_launch"), so_ms),
+                           "note": "same step without the obs stream (step_pool_kernel); L2 flushed (256 MiB fill) before every step"},
             "e2e": {"value": total * e2e_k / (e2e_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_k,
                     "note": "HostPipe.step (ppad_pipe_step, zero copy: the kernel reads / writes the pinned host buffers), synchronous: "
@@ -392,6 +406,7 @@ def main():
             "episode_mode": {"env_step_calls_per_s": total * 102 / (ep_ms * 1e-3), "episodes_per_s": total * 2 / (ep_ms * 1e-3),
                              "fused_env_step_calls_per_s": total * 51 * 4 / (ep_fused_ms * 1e-3),
                              "fused_episodes_per_s": total * 4 / (ep_fused_ms * 1e-3),
+                             "fused_issue": issue(prof.get("rollout_warp_instructions_per_51_step_launch"), ep_fused_ms / 4),
                              "note": "50 random moves + pass (full cascade, Philox skyfall) + auto reset per episode, "
                                      "state-only kernels, one launch per step; fused_* = the 51 steps in one ppad_rollout launch; "
                                      "the reference does ~3.8e3 env.step calls/s per core in this mode"},

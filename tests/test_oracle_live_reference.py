@@ -25,10 +25,12 @@ def test_resolve_live(rows, cols):
     rng = np.random.default_rng(int.from_bytes(os.urandom(4), "little"))
     env = rh.make_env(rows, cols, skyfall_damage=True)
     cfgs = {sd: orc.make_cfg(rows, cols, skyfall_damage=sd, cascade_cap=0) for sd in (0, 1)}
-    for _ in range(120):
+    for k in range(160):
         ncol = int(rng.integers(2, 7))
-        board = rng.integers(0, ncol, size=(rows, cols)).astype(np.int8)
-        orbs = rng.integers(0, ncol, size=400).astype(np.uint8)
+        # every fourth case draws its colours from all ten orb types (poison, mortal poison, bomb: game.py:243-246)
+        pal = np.arange(ncol) if k % 4 else rng.permutation(10)[:ncol]
+        board = pal[rng.integers(0, ncol, size=(rows, cols))].astype(np.int8)
+        orbs = pal[rng.integers(0, ncol, size=400)].astype(np.uint8)
         sd = bool(rng.integers(2))
         try:
             want = rh.resolve(env, board, sd, orbs)
