@@ -282,6 +282,22 @@ def test_discount_batched_and_replay_ring(pb):
         n = int(zd["lens"][i])
         assert np.array_equal(bits(got[i, :n]), bits(orc.discount(zd["rewards"][i, :n], g, log10=False)))
         assert np.array_equal(got[i, n:], zd["rewards"][i, n:])
+    # ragged batches, short and long trajectories
+    rng = np.random.default_rng(8)
+    for m, T in ((1000 + 7, 51), (130, 95), (77, 120), (1, 1)):
+        r = np.where(rng.random((m, T)) < 0.3, rng.uniform(0, 5e4, (m, T)), 0.0)
+        r[::9] = 0.0                                               # all-zero trajectories come back unchanged
+        lens = rng.integers(0, T + 1, m).astype(np.int32)
+        for log10 in (False, True):
+            got = env.discount(r, 0.93, lengths=lens, log10=log10).cpu().numpy()
+            for i in range(0, m, 7):
+                k = int(lens[i])
+                want = orc.discount(r[i, :k], 0.93, log10=log10) if k else r[i, :0]
+                if log10:
+                    assert np.allclose(got[i, :k], want, rtol=1e-14, atol=0), (m, T, i)   # log10: different libm's
+                else:
+                    assert np.array_equal(bits(got[i, :k]), bits(want)), (m, T, i)
+                assert np.array_equal(got[i, k:], r[i, k:])
     normed = env.discount(zd["rewards"][1:2, :int(zd["lens"][1])], g, norm=True, log10=False).cpu().numpy()[0]
     plain = orc.discount(zd["rewards"][1, :int(zd["lens"][1])], g, log10=False)
     assert np.allclose(normed, (plain - plain.mean()) / plain.std(), rtol=1e-12)
