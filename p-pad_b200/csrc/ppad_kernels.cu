@@ -658,17 +658,38 @@ __global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ Re
     if (a.consumed) a.consumed[i] = (uint8_t)sat255(consumed);
 }
 
+// plain int boards -> state.  Like unpack below, through shared memory: the CTA reads its contiguous input region with
+// consecutive threads on consecutive elements and parks one code byte per cell (0x80 = a value that is no orb type);
+// then every thread packs its own board from there.
 template <class G, class T>
 __global__ void __launch_bounds__(BLOCK) pack_kernel(int64_t n, const T *boards, const T *fingers, const uint8_t *prev,
                                                      const uint16_t *moves, void *state, uint8_t *flags)
 {
-    const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    __shared__ uint8_t codes[BLOCK * G::CELLS];
+    const int64_t tile0 = (int64_t)blockIdx.x * BLOCK;
+    const int64_t left = n - tile0;
+    const int count = (int)(left < BLOCK ? left : BLOCK) * G::CELLS;
+    const T *in = boards + (size_t)tile0 * G::CELLS;
+    for (int e = threadIdx.x; e < count; e += BLOCK) {
+        const long long v = (long long)in[e];
+        codes[e] = v == -1 ? (uint8_t)G::EMPTY : ((v >= 0 && v < G::NTYPES) ? (uint8_t)v : (uint8_t)0x80);
+    }
+    __syncthreads();
+    const int64_t i = tile0 + threadIdx.x;
     if (i >= n) return;
+    int8_t cells[G::CELLS];
+    bool bad = false;
+#pragma unroll
+    for (int c = 0; c < G::CELLS; c++) {
+        const uint8_t v = codes[threadIdx.x * G::CELLS + c];
+        bad |= v == 0x80;
+        cells[c] = v == 0x80 || v == G::EMPTY ? (int8_t)-1 : (int8_t)v;
+    }
     Board<G> b;
-    const uint32_t f = pack_cells<G, T>(b, boards + (size_t)i * G::CELLS);
+    pack_cells<G, int8_t>(b, cells);
     const int finger = (int)fingers[2 * i] * G::C + (int)fingers[2 * i + 1];
     StateIO<G>::store(state, i, b, meta_pack(finger, prev ? prev[i] : ACT_PASS, moves ? moves[i] : 0));
-    if (flags) flags[i] = (uint8_t)f;
+    if (flags) flags[i] = (uint8_t)(bad ? FLAG_UNSUPPORTED_ORB : 0);
 }
 
 // state -> plain int boards.  A board is CELLS elements of T (240 B as int64), so one thread per board would write
