@@ -168,13 +168,23 @@ class PAD:
         v = self._venv
         self._torch, self._ctypes = torch, ctypes
         # two 128-byte slots: [0] the env's record, [1] scratch for calculate_reward(board=...).
-        # slot layout: state 0..64 (16..48 bytes used) | reward 64..72 | info 72..76 | action 76
+        # slot layout: state 0..64 (16..48 bytes used) | reward 64..72 | info 72..76 | action 76 | pre-sampled move 77
         self._io = torch.zeros(256, dtype=torch.uint8, device=v.device)
         self._io_host = torch.zeros(256, dtype=torch.uint8).pin_memory()
         self._io_np = self._io_host.numpy()
         v.state = self._io[:4 * v.words].view(torch.int32).view(1, v.words)   # the env slab IS slot 0
         self._action_bytes = torch.arange(5, dtype=torch.uint8, device=v.device)
         self._dev_shadow = None           # (board, finger, prev id) currently packed in slot 0
+        # action_space.sample() right after a step is the common loop (visualize_episode.py:29-31): when the caller
+        # samples, the next step's launch is followed by the sample kernel for the state it leaves behind and the
+        # move comes back with the same read-back -- one device round trip per env.step(sample()) instead of two
+        self._want_presample = False
+        self._presample = (-1, 255)       # (draw index it was made for, action id)
+
+    def _device_is_current(self):
+        sh = self._dev_shadow
+        return (sh is not None and sh[2] == self._prev_id() and np.array_equal(sh[0], self.board)
+                and np.array_equal(sh[1], self.finger))
 
     def _prev_id(self):
         return ACTION_IDS.get(self.action_space.previous_action, 4)
@@ -216,21 +226,35 @@ class PAD:
             extra = (torch.empty((1, v.words), dtype=torch.int32, device=v.device),
                      torch.zeros((1, max(1, log_cap)), dtype=torch.int16, device=v.device))
             a.final_state, a.combo_log, a.log_cap = extra[0].data_ptr(), extra[1].data_ptr(), max(1, log_cap)
+        presample = slot == 0 and self._want_presample and self.rng == 'philox'
         with torch.cuda.device(v.device):
             _cabi.check(v.lib.ppad_step(v._ctx, self._ctypes.byref(a), v._stream()))
+            if presample:
+                idx = self.action_space._draws + 1
+                _cabi.check(v.lib.ppad_sample_actions(v._ctx, 1, v.env0, (0x40000000 + idx) & 0xFFFFFFFF, base, 0,
+                                                      base + 77, v._stream()))
         self._io_host[128 * slot:128 * slot + 80].copy_(self._io[128 * slot:128 * slot + 80])   # blocking read-back
         raw = self._io_np[128 * slot:128 * slot + 80]
+        if slot == 0:
+            self._presample = (idx, int(raw[77])) if presample else (-1, 255)
         reward = np.float64(raw[64:72].view(np.float64)[0])
         info = int(raw[72:76].view(np.uint32)[0])
         return reward, info, int(raw[76]), extra
 
     def _pull(self):
-        from .. import layout
-        words = self._venv.words
-        boards, fingers, _, _ = layout.unpack_state(self._io_np[:4 * words].view(np.uint32).reshape(1, words).copy(),
-                                                    self.dim_row, self.dim_col, orb_bits=self._venv.orb_bits)
-        self.board = boards[0].astype(int)
-        self.finger = fingers[0].astype(int)
+        """slot 0 of the read-back -> self.board / self.finger (format conversion of ONE record: the bit planes are
+        spread with np.unpackbits; layout.unpack_state is the batched equivalent and the tests compare the two)"""
+        v = self._venv
+        cells = self.dim_row * self.dim_col
+        pb = 4 if cells <= 32 else 8                          # bytes per plane
+        bits = np.unpackbits(self._io_np[:pb * v.orb_bits].reshape(v.orb_bits, pb), axis=1, bitorder='little')[:, :cells]
+        codes = bits[0].astype(int)
+        for j in range(1, v.orb_bits):
+            codes += bits[j].astype(int) << j
+        codes[codes == (1 << v.orb_bits) - 1] = -1
+        self.board = codes.reshape(self.dim_row, self.dim_col)
+        f = int(self._io_np[pb * v.orb_bits]) & 63            # meta word: finger cell in bits 0..5
+        self.finger = np.array([f // self.dim_col, f % self.dim_col])
         self._dev_shadow = (self.board.copy(), self.finger.copy(), self._dev_shadow[2] if self._dev_shadow else 4)
 
     def _push(self, board=None):

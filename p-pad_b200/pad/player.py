@@ -47,7 +47,13 @@ class PlayerAction:
                     continue
                 return current
         self._draws += 1
-        if env is not None and np.array_equal(np.asarray(self.finger), env.finger):
+        if env is not None:
+            env._want_presample = True     # the caller samples: let the next step bring the following move along
+        if (env is not None and not include_pass and env._presample[0] == self._draws
+                and np.array_equal(np.asarray(self.finger), env.finger) and env._device_is_current()):
+            # fastest path: the last step already ran the sample kernel for exactly this draw on the state it left
+            a = env._presample[1]
+        elif env is not None and np.array_equal(np.asarray(self.finger), env.finger):
             # fast path: the env's device record already holds (finger, previous_action)
             env._sync_to_device()
             a = int(env._venv.sample_actions(include_pass=include_pass, step=0x40000000 + self._draws)[0])

@@ -95,6 +95,22 @@ def test_pad_facade_skyfall_matches_oracle_philox(pb):
         prev = a
     env.step('pass')
     assert len(env.rewards) == 101 and env.rewards[-1] >= 0
+    # the move that rides along with the previous step's read-back is the one the sample kernel gives for that draw
+    a_env, b_env = pb.PAD(seed=5), pb.PAD(seed=5)
+    assert np.array_equal(a_env.board, b_env.board) and np.array_equal(a_env.finger, b_env.finger)
+    used_fast = 0
+    for t in range(60):
+        act = a_env.action_space.sample()
+        used_fast += a_env._presample[0] == a_env.action_space._draws
+        b_env._want_presample = False                       # b always takes the explicit ppad_sample_actions path
+        b_env._presample = (-1, 255)
+        assert b_env.action_space.sample() == act, t
+        if t == 30:                                          # a caller that edits the board in between: no stale move
+            a_env.board[0, 0], b_env.board[0, 0] = 3, 3
+        a_env.step(act)
+        b_env.step(act)
+        assert np.array_equal(a_env.board, b_env.board) and np.array_equal(a_env.finger, b_env.finger)
+    assert used_fast >= 50
 
 
 def test_pad_stage_methods(pb):
