@@ -170,6 +170,12 @@ int ppad_step(const ppad_ctx *ctx, const ppad_step_args *args, void *stream);
 int ppad_rollout(const ppad_ctx *ctx, int64_t n, uint64_t env0, uint32_t step0, int32_t steps, int32_t eval_moves,
                  int32_t auto_reset, int32_t max_moves, void *state, double *reward_sum, uint32_t *episodes,
                  uint32_t *combos_sum, uint8_t *flags_or, void *stream);
+/* The same, recording the trajectory (the random walks of smart_data.py:69-72 in one launch): traj_state
+ * [steps, n] packed records = the state after every step, traj_action [steps, n] uint8 = the action taken;
+ * time-major so that a warp writes consecutive records.  Either may be NULL. */
+int ppad_rollout_record(const ppad_ctx *ctx, int64_t n, uint64_t env0, uint32_t step0, int32_t steps, int32_t eval_moves,
+                        int32_t auto_reset, int32_t max_moves, void *state, double *reward_sum, uint32_t *episodes,
+                        uint32_t *combos_sum, uint8_t *flags_or, void *traj_state, uint8_t *traj_action, void *stream);
 
 /* The same env step for callers whose inputs and results live in HOST memory -- what the reference's callers
  * have: PAD.step takes a Python value and appends to Python lists (game.py:329-362).  A pipe owns device

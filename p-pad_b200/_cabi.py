@@ -53,7 +53,7 @@ SYMBOLS = ["ppad_default_config", "ppad_create", "ppad_destroy", "ppad_abi_versi
            "ppad_step", "ppad_encode_obs", "ppad_cancel", "ppad_legal_mask", "ppad_sample_actions", "ppad_drop",
            "ppad_fill", "ppad_damage", "ppad_select_actions", "ppad_discount", "ppad_replay_push",
            "ppad_replay_sample", "ppad_permute", "ppad_pipe_create", "ppad_pipe_destroy", "ppad_pipe_step",
-           "ppad_pipe_wait", "ppad_pipe_join", "ppad_rollout", "ppad_pipe_set_zero_copy"]
+           "ppad_pipe_wait", "ppad_pipe_join", "ppad_rollout", "ppad_pipe_set_zero_copy", "ppad_rollout_record"]
 
 
 class PPADError(RuntimeError):
@@ -102,6 +102,7 @@ def lib():
     L.ppad_damage.argtypes = [vp, i64, vp, i32, vp, vp, vp]
     L.ppad_permute.argtypes = [vp, i64, vp, vp, vp]
     L.ppad_rollout.argtypes = [vp, i64, u64, u32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+    L.ppad_rollout_record.argtypes = [vp, i64, u64, u32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
     L.ppad_pipe_create.argtypes = [vp, i64, i32, i32, C.POINTER(vp)]
     L.ppad_pipe_destroy.argtypes = [vp]
     L.ppad_pipe_destroy.restype = None

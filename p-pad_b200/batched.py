@@ -232,21 +232,27 @@ class BatchedPAD:
         packed = torch.where(packed >= 2 ** 31, packed - 2 ** 32, packed).to(torch.int32).contiguous()
         return packed, length
 
-    def rollout(self, steps, eval_moves=False, auto_reset=True, max_moves=50, step=None):
+    def rollout(self, steps, eval_moves=False, auto_reset=True, max_moves=50, step=None, record=False):
         """`steps` env steps of the in-kernel random policy in ONE launch (ppad_rollout): equals that many
         step(None, ...) calls.  Returns SimpleNamespace(reward_sum float64 [n], episodes int32 [n],
-        combos_sum int32 [n], flags_or uint8 [n]); step_index advances by `steps`."""
+        combos_sum int32 [n], flags_or uint8 [n]); step_index advances by `steps`.  record=True adds the trajectory:
+        states int32 [steps, n, words] (the state after every step) and actions uint8 [steps, n], time-major."""
         step0 = self.step_index if step is None else int(step)
         self.step_index = step0 + int(steps)
         out = SimpleNamespace(reward_sum=torch.empty(self.n, dtype=torch.float64, device=self.device),
                               episodes=torch.empty(self.n, dtype=torch.int32, device=self.device),
                               combos_sum=torch.empty(self.n, dtype=torch.int32, device=self.device),
-                              flags_or=torch.empty(self.n, dtype=torch.uint8, device=self.device))
+                              flags_or=torch.empty(self.n, dtype=torch.uint8, device=self.device),
+                              states=None, actions=None)
+        if record:
+            out.states = torch.empty((int(steps), self.n, self.words), dtype=torch.int32, device=self.device)
+            out.actions = torch.empty((int(steps), self.n), dtype=torch.uint8, device=self.device)
         with torch.cuda.device(self.device):
-            _cabi.check(self.lib.ppad_rollout(self._ctx, self.n, self.env0, step0 & 0xFFFFFFFF, int(steps),
-                                              int(bool(eval_moves)), int(bool(auto_reset)), int(max_moves),
-                                              _ptr(self.state), _ptr(out.reward_sum), _ptr(out.episodes),
-                                              _ptr(out.combos_sum), _ptr(out.flags_or), self._stream()))
+            _cabi.check(self.lib.ppad_rollout_record(self._ctx, self.n, self.env0, step0 & 0xFFFFFFFF, int(steps),
+                                                     int(bool(eval_moves)), int(bool(auto_reset)), int(max_moves),
+                                                     _ptr(self.state), _ptr(out.reward_sum), _ptr(out.episodes),
+                                                     _ptr(out.combos_sum), _ptr(out.flags_or), _ptr(out.states),
+                                                     _ptr(out.actions), self._stream()))
         return out
 
     def calculate_reward(self, injected=None, want_final=False, log_cap=0, step=None, skyfall_damage=None):

@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(BLOCK, 4) step_obs_kernel(const __grid_constan
 
 // T consecutive steps of the in-kernel random policy in one launch: the board stays in registers between
 // steps, only the final state and per-board totals are written.  Equals T calls of ppad_step(actions = NULL,
-// step = step0 + t) without injected skyfall / observation (tests/test_gpu_dropin.py::test_fused_rollout).
+// step = step0 + t) without injected skyfall / observation (tests/test_gpu_parity.py::test_fused_rollout_equals_single_steps).
 struct RolloutArgs {
     StepParams p;
     int64_t n;
@@ -375,6 +375,8 @@ struct RolloutArgs {
     uint32_t *episodes;
     uint32_t *combos_sum;
     uint8_t *flags_or;
+    void *traj_state;       // [steps, n] packed records after every step (time-major: coalesced), or NULL
+    uint8_t *traj_action;   // [steps, n] action taken at every step, or NULL
 };
 
 template <class G>
@@ -398,6 +400,8 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
         }
         const StepOut o = step_board<G, true>(valid, s, fin, a.p, a.env0 + (uint64_t)i, -1, nullptr, nullptr, nullptr,
                                               0, (uint32_t)t, &act_blk);
+        if (valid && a.traj_state) StateIO<G>::store(a.traj_state, (int64_t)t * a.n + i, s.b, s.meta);
+        if (valid && a.traj_action) a.traj_action[(int64_t)t * a.n + i] = (uint8_t)o.action;
         reward_sum = ppad::dadd(reward_sum, o.reward);
         episodes += (o.info >> 31) & 1u;         // FLAG_EPISODE_DONE
         combos += o.info & 0xFFu;
@@ -1205,6 +1209,14 @@ int ppad_rollout(const ppad_ctx *ctx, int64_t n, uint64_t env0, uint32_t step0, 
                  int32_t auto_reset, int32_t max_moves, void *state, double *reward_sum, uint32_t *episodes,
                  uint32_t *combos_sum, uint8_t *flags_or, void *stream)
 {
+    return ppad_rollout_record(ctx, n, env0, step0, steps, eval_moves, auto_reset, max_moves, state, reward_sum, episodes,
+                               combos_sum, flags_or, nullptr, nullptr, stream);
+}
+
+int ppad_rollout_record(const ppad_ctx *ctx, int64_t n, uint64_t env0, uint32_t step0, int32_t steps, int32_t eval_moves,
+                        int32_t auto_reset, int32_t max_moves, void *state, double *reward_sum, uint32_t *episodes,
+                        uint32_t *combos_sum, uint8_t *flags_or, void *traj_state, uint8_t *traj_action, void *stream)
+{
     if (int r = enter(ctx, n)) return r;
     if (n == 0 || steps == 0) return PPAD_OK;
     if (!state || steps < 0) return fail(PPAD_ERR_INVALID, "ppad_rollout: bad argument");
@@ -1223,6 +1235,9 @@ int ppad_rollout(const ppad_ctx *ctx, int64_t n, uint64_t env0, uint32_t step0, 
     a.episodes = episodes;
     a.combos_sum = combos_sum;
     a.flags_or = flags_or;
+    a.traj_state = traj_state;
+    a.traj_action = traj_action;
+    if (traj_state && ((uintptr_t)traj_state & 15)) return fail(PPAD_ERR_INVALID, "ppad_rollout_record: traj_state must be 16-byte aligned");
     PPAD_DISPATCH(ctx, (rollout_kernel<G><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(a)));
     return after_launch("rollout_kernel");
 }

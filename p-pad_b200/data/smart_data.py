@@ -35,11 +35,13 @@ def smart_data_batched(solved, picks, maps, steps=100, max_walk=5000, seed=0, de
     states = [venv.state.clone()]
     actions = []
     if steps != -1:
-        for _ in range(steps - 1):
-            out = venv.step(None)                  # random legal non-reversing move, no evaluation
-            actions.append(out.action.clone())
-            states.append(venv.state.clone())
         lengths = torch.full((m,), steps, dtype=torch.int32, device=venv.device)
+        if steps > 1:
+            # the whole random walk (legal non-reversing moves, no evaluation) in ONE launch, trajectory recorded
+            walk = venv.rollout(steps - 1, eval_moves=False, auto_reset=False, max_moves=0, record=True)
+            states = torch.cat([states[0][None], walk.states], 0).permute(1, 0, 2).contiguous()
+            actions = walk.actions.t().contiguous()
+            return dict(states=states, actions=actions, lengths=lengths, final_reward=final_reward, venv=venv)
     else:
         # walk until the first time no combo is left (smart_data.py:73-79); finished boards take PASS, a no-op
         done = torch.zeros(m, dtype=torch.bool, device=venv.device)

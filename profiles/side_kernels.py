@@ -61,3 +61,33 @@ st = env.get_state()
 t("unpack -> int64 boards (16 + 30*8 + 2*8 + 3)", lambda: env.get_state(), 16 + 240 + 16 + 3)
 t("pack <- int64 boards", lambda: env.set_state(st.boards, st.fingers), 16 + 240 + 16 + 1)
 t("encode_obs u8 (16 + 210)", lambda: env.encode_obs('u8'), 226)
+
+# ---- the callers built from those kernels
+import time
+from ppad_b200.lookahead import two_step_lookahead
+from ppad_b200.data.smart_data import smart_data_batched
+from ppad_b200.data import solved_boards
+m = 1 << 16
+small = ppad_b200.BatchedPAD(m, 5, 6, seed=2, skyfall_damage=False)
+small.reset(step=0)
+for _ in range(2):
+    two_step_lookahead(small, q_fn=None)
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for _ in range(5):
+    res = two_step_lookahead(small, q_fn=None)
+torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 5
+print("two_step_lookahead, %d envs x 21 candidates, no roam: %.2f ms  (%.2fe6 envs/s, %.2fe6 candidate evaluations/s)" % (
+    m, dt * 1e3, m / dt / 1e6, 21 * m / dt / 1e6))
+qf = lambda obs: torch.randn((obs.shape[0], 5), device=obs.device) * 1000
+torch.cuda.synchronize(); t0 = time.perf_counter()
+res = two_step_lookahead(small, q_fn=qf, policy='boltzmann', beta=1e-3, max_lookahead_len=10)
+torch.cuda.synchronize(); dt = time.perf_counter() - t0
+print("two_step_lookahead, %d envs, Boltzmann roam up to 10 moves (synthetic q): %.2f ms  (%.2fe6 envs/s)" % (m, dt * 1e3, m / dt / 1e6))
+rngp = torch.Generator().manual_seed(0)
+picks = torch.randint(0, 16, (m,), generator=rngp).numpy()
+maps = torch.stack([torch.randperm(6, generator=rngp) for _ in range(m)]).to(torch.uint8).numpy()
+torch.cuda.synchronize(); t0 = time.perf_counter()
+out = smart_data_batched(solved_boards.boards, picks, maps, steps=100, seed=3)
+torch.cuda.synchronize(); dt = time.perf_counter() - t0
+print("smart_data_batched, %d trajectories x 100 steps: %.1f ms  (%.2fe6 trajectories/s, %.1fe6 walk steps/s)" % (
+    m, dt * 1e3, m / dt / 1e6, 99 * m / dt / 1e6))

@@ -419,3 +419,57 @@ def test_caps_and_exhaustion_flags_on_device(pb):
         assert np.array_equal(env.get_state(o.final_state).boards.cpu().numpy(), f0)
     fl = i0 >> 24
     assert (fl & orc.FLAG_CASCADE_CAP).any() and (fl & orc.FLAG_SKYFALL_EXHAUSTED).any()
+
+
+@pytest.mark.parametrize("rows,cols,orb_bits", [(5, 6, 3), (6, 7, 3), (4, 5, 3), (5, 6, 4)])
+@pytest.mark.parametrize("eval_moves,auto_reset,max_moves", [(False, True, 7), (True, True, 5), (True, False, 0),
+                                                              (False, False, 0)])
+def test_fused_rollout_equals_single_steps(pb, rows, cols, orb_bits, eval_moves, auto_reset, max_moves):
+    """ppad_rollout / ppad_rollout_record (T steps of the in-kernel random policy in one launch, boards in registers,
+    one Philox block per four action draws, unrolled Philox reset) against T launches of ppad_step(actions = NULL) and,
+    step by step, against the oracle."""
+    n, T, step0 = 20_000 + 13, 23, 1001           # step0 % 4 != 0: the first action block starts in the middle
+    sky = [0.1] * 10 if orb_bits == 4 else None
+    a = pb.BatchedPAD(n, rows, cols, seed=99, env0=12345, skyfall=sky)
+    b = pb.BatchedPAD(n, rows, cols, seed=99, env0=12345, skyfall=sky)
+    assert a.orb_bits == orb_bits
+    a.reset(step=0)
+    b.state.copy_(a.state)
+    st0 = a.get_state()
+    fused = a.rollout(T, eval_moves=eval_moves, auto_reset=auto_reset, max_moves=max_moves, step=step0, record=True)
+    reward_sum = torch.zeros(n, dtype=torch.float64, device=a.device)
+    episodes = torch.zeros(n, dtype=torch.int32, device=a.device)
+    combos = torch.zeros(n, dtype=torch.int32, device=a.device)
+    flags = torch.zeros(n, dtype=torch.int32, device=a.device)
+    ocfg = orc.make_cfg(rows, cols, True, seed=99, skyfall=sky)
+    boards = st0.boards.cpu().numpy().astype(np.int8)
+    fingers = st0.fingers.cpu().numpy().astype(np.int32)
+    prev = st0.prev.cpu().numpy().astype(np.uint8)
+    moves = st0.moves.cpu().numpy().view(np.uint16).copy()
+    for t in range(T):
+        o = b.step(None, eval_moves=eval_moves, auto_reset=auto_reset, max_moves=max_moves, step=step0 + t)
+        reward_sum = reward_sum + o.reward                       # the kernel adds in step order, too
+        info = o.info.to(torch.int64) & 0xFFFFFFFF
+        episodes += ((info >> 31) & 1).to(torch.int32)
+        combos += (info & 0xFF).to(torch.int32)
+        flags |= (info >> 24).to(torch.int32)
+        assert torch.equal(fused.states[t], b.state), t
+        assert torch.equal(fused.actions[t], o.action), t
+        if t < 6:                                                # and the oracle agrees with both
+            a0, r0, i0, _ = orc.step_batch(ocfg, boards, fingers, prev, moves, actions=None, eval_moves=eval_moves,
+                                           auto_reset=auto_reset, max_moves=max_moves, env0=12345, step=step0 + t)
+            assert np.array_equal(o.action.cpu().numpy(), a0) and np.array_equal(u32(o.info), i0), t
+            assert np.array_equal(bits(o.reward.cpu().numpy()), bits(r0)), t
+            assert np.array_equal(b.get_state().boards.cpu().numpy(), boards), t
+    assert torch.equal(a.state, b.state)
+    assert torch.equal(fused.reward_sum.view(torch.int64), reward_sum.view(torch.int64))
+    assert torch.equal(fused.episodes, episodes) and torch.equal(fused.combos_sum, combos)
+    assert torch.equal(fused.flags_or.to(torch.int32), flags & 0xFF)
+    if auto_reset and max_moves:
+        assert int(episodes.sum()) > n                           # episodes really ended and restarted inside the launch
+    # without the recording the launch does the same
+    c = pb.BatchedPAD(n, rows, cols, seed=99, env0=12345, skyfall=sky)
+    c.set_state(st0.boards, st0.fingers, st0.prev, st0.moves)
+    plain = c.rollout(T, eval_moves=eval_moves, auto_reset=auto_reset, max_moves=max_moves, step=step0)
+    assert plain.states is None and torch.equal(c.state, a.state)
+    assert torch.equal(plain.reward_sum.view(torch.int64), fused.reward_sum.view(torch.int64))
