@@ -1,7 +1,7 @@
 """ctypes binding of the CPU oracle (oracle/ppad_oracle.c).  TEST INFRASTRUCTURE, NOT PRODUCT.
 
 Importers allowed: tests/, __graft_entry__.smoke(), bench.py's cpu_baseline / --impl reference
-legs.  Nothing under the product package imports this module (tests/test_no_oracle_in_product.py
+legs.  Nothing under the product package imports this module (tests/test_host_logic.py::test_product_never_touches_the_oracle
 greps for it).
 """
 import ctypes as C
