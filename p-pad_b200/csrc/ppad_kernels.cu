@@ -303,8 +303,9 @@ struct StepKernelArgs {
 // Four resident CTAs per SM (64 registers) is the measured optimum with fp32 obs: 0.1546 ms against 0.1556 (3),
 // 0.1875 (2), 0.1685 (5, spills) and 0.1731 (6).  Emitting the observation before the cascades (0.167 ms), or
 // before them in the odd warps and after them in the even warps (0.156 ms), is not faster either.
+// (6x7 with 4-bit codes -- four 64-bit planes -- is the one geometry that does better with 3: 0.221 against 0.240 ms.)
 template <class G, bool OBS>
-__global__ void __launch_bounds__(BLOCK, 4) step_obs_kernel(const __grid_constant__ StepKernelArgs a)
+__global__ void __launch_bounds__(BLOCK, (sizeof(typename G::W) == 8 && G::NP == 4) ? 3 : 4) step_obs_kernel(const __grid_constant__ StepKernelArgs a)
 {
     __shared__ ObsShared obs_sh;
     __shared__ uint32_t obs_stream[OBS ? (BLOCK / 32) * ObsGeom<G>::WARP_WORDS : 1];

@@ -2,6 +2,8 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, ppad_b200
+if os.environ.get("PPAD_AB_LIB"):
+    ppad_b200._cabi.LIB_PATH = os.path.abspath(os.environ["PPAD_AB_LIB"])
 n = 1 << 20
 def t(fn, reps=40):
     for _ in range(3): fn()
