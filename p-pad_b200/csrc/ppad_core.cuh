@@ -1073,7 +1073,9 @@ __device__ __forceinline__ uint32_t reset_boards_warp(bool need, State<G> &s, co
 // The whole step of one board.  On the GPU EVERY lane of the warp must call this (lanes past the end of the
 // batch pass live = false): the cascade loop is warp-uniform -- it runs while any lane still cascades and
 // the lanes reconverge after every iteration.
-template <class G, bool TIGHT_RESET = false>
+// TIGHT_RESET: the auto-reset uses the unrolled Philox refill; HAS_RESET = false compiles the auto-reset out (kernels
+// launched with auto_reset = 0 do not carry its code).
+template <class G, bool TIGHT_RESET = false, bool HAS_RESET = true>
 PPAD_HD StepOut step_board(bool live, State<G> &s, Board<G> &final_board, const StepParams &p, uint64_t env,
                            int action_in, const uint32_t *slab, uint16_t *log, const uint32_t *path = nullptr,
                            int path_len = 0, uint32_t step_offset = 0, const U4 *act_blk = nullptr)
@@ -1110,10 +1112,12 @@ PPAD_HD StepOut step_board(bool live, State<G> &s, Board<G> &final_board, const 
         warp_converge();
     }
 #if defined(__CUDA_ARCH__)
-    if (p.auto_reset) {   // kernel-uniform
-        const bool need = live && pre.action == ACT_PASS;
-        const uint32_t f = reset_boards_warp<G, TIGHT_RESET>(need, s, p, key.step, env, nullptr, -1, -1, nullptr);
-        if (need) it.flags |= FLAG_EPISODE_DONE | f;
+    if constexpr (HAS_RESET) {
+        if (p.auto_reset) {   // kernel-uniform
+            const bool need = live && pre.action == ACT_PASS;
+            const uint32_t f = reset_boards_warp<G, TIGHT_RESET>(need, s, p, key.step, env, nullptr, -1, -1, nullptr);
+            if (need) it.flags |= FLAG_EPISODE_DONE | f;
+        }
     }
 #else
     if (live && pre.action == ACT_PASS && p.auto_reset) it.flags |= step_auto_reset<G>(s, p, key);

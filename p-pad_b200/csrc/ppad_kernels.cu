@@ -304,7 +304,10 @@ struct StepKernelArgs {
 // 0.1875 (2), 0.1685 (5, spills) and 0.1731 (6).  Emitting the observation before the cascades (0.167 ms), or
 // before them in the odd warps and after them in the even warps (0.156 ms), is not faster either.
 // (6x7 with 4-bit codes -- four 64-bit planes -- is the one geometry that does better with 3: 0.221 against 0.240 ms.)
-template <class G, bool OBS>
+// AR: the launch has auto_reset set.  Launches without it run an instantiation that does not contain the reset code
+// at all; those with it get the unrolled Philox refill (a Boltzmann-policy rollout resets 29 % of its boards per step:
+// 0.227 ms per 2^20-board step with fp32 obs against 0.286 ms with the plain refill, profiles/ar_bench.py).
+template <class G, bool OBS, bool AR>
 __global__ void __launch_bounds__(BLOCK, (sizeof(typename G::W) == 8 && G::NP == 4) ? 3 : 4) step_obs_kernel(const __grid_constant__ StepKernelArgs a)
 {
     __shared__ ObsShared obs_sh;
@@ -344,7 +347,7 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(typename G::W) == 8 && G::NP ==
     }
     // every lane takes part (the cascade loop inside is warp-uniform); lanes past the batch are not live
     Board<G> fin;
-    const StepOut o = step_board<G>(valid, s, fin, a.p, a.env0 + (uint64_t)i, action, slab,
+    const StepOut o = step_board<G, AR, AR>(valid, s, fin, a.p, a.env0 + (uint64_t)i, action, slab,
                                     a.combo_log && valid ? a.combo_log + (size_t)i * a.p.log_cap : nullptr,
                                     a.paths && valid ? a.paths + (size_t)i * a.path_words : nullptr, path_len);
     if (valid) {
@@ -512,7 +515,7 @@ struct CascadePool {
     }
 };
 
-template <class G>
+template <class G, bool AR>
 __global__ void __launch_bounds__(PBLOCK, PPAD_POOL_MINB) step_pool_kernel(const __grid_constant__ StepKernelArgs a)
 {
     __shared__ CascadePool<G> pool;
@@ -560,9 +563,9 @@ __global__ void __launch_bounds__(PBLOCK, PPAD_POOL_MINB) step_pool_kernel(const
                 W er, ed;
                 cascading = match_mask<G>(it.b, er, ed) != 0;
             }
-            if (a.p.auto_reset) {                 // kernel-uniform; the reset is warp-cooperative
+            if constexpr (AR) {                   // launches with auto_reset; the reset is warp-cooperative
                 const bool need = valid && pre.action == ACT_PASS;
-                const uint32_t f = reset_boards_warp<G>(need, s, a.p, a.p.key.step, a.env0 + (uint64_t)i, nullptr, -1, -1, nullptr);
+                const uint32_t f = reset_boards_warp<G, true>(need, s, a.p, a.p.key.step, a.env0 + (uint64_t)i, nullptr, -1, -1, nullptr);
                 if (need) it.flags |= FLAG_EPISODE_DONE | f;
             }
             if (valid) {
@@ -1067,7 +1070,7 @@ int ppad_create(const ppad_config *cfg, int device, ppad_ctx **out)
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaSetDevice(device);
     ctx->pool_ctas_per_sm = 0;
-    PPAD_DISPATCH(ctx, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->pool_ctas_per_sm, step_pool_kernel<G>, PBLOCK, 0)));
+    PPAD_DISPATCH(ctx, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->pool_ctas_per_sm, step_pool_kernel<G, true>, PBLOCK, 0)));
     if (ctx->pool_ctas_per_sm <= 0) ctx->pool_ctas_per_sm = 1;
     *out = ctx;
     return PPAD_OK;
@@ -1180,21 +1183,25 @@ static int launch_step(const ppad_ctx *ctx, const ppad_step_args *args, cudaStre
     if (a.paths && (a.path_words <= 0 || a.path_len < 0))
         return fail(PPAD_ERR_INVALID, "ppad_step: paths need path_words > 0 and path_len >= 0");
     a.stage_slab = (stage_host_slab && a.slab && a.p.slab_words == 4 && ((uintptr_t)a.slab & 15) == 0) ? 1 : 0;
+    const bool ar = a.p.auto_reset != 0;
     if (args->obs) {
-        PPAD_DISPATCH(ctx, (step_obs_kernel<G, true><<<grid_for(a.n), BLOCK, 0, st>>>(a)));
+        if (ar) PPAD_DISPATCH(ctx, (step_obs_kernel<G, true, true><<<grid_for(a.n), BLOCK, 0, st>>>(a)));
+        else PPAD_DISPATCH(ctx, (step_obs_kernel<G, true, false><<<grid_for(a.n), BLOCK, 0, st>>>(a)));
         return after_launch("step_obs_kernel");
     }
     if (coalesced_results) {
         // results go straight to host memory: the pooled kernel's scattered 8-byte result writes would become tiny
         // PCIe transactions, one thread per board writes them as full lines
-        PPAD_DISPATCH(ctx, (step_obs_kernel<G, false><<<grid_for(a.n), BLOCK, 0, st>>>(a)));
+        if (ar) PPAD_DISPATCH(ctx, (step_obs_kernel<G, false, true><<<grid_for(a.n), BLOCK, 0, st>>>(a)));
+        else PPAD_DISPATCH(ctx, (step_obs_kernel<G, false, false><<<grid_for(a.n), BLOCK, 0, st>>>(a)));
         return after_launch("step_obs_kernel<no obs>");
     }
     // persistent: one wave of CTAs, as many as fit
     const int64_t tiles = (a.n + PBLOCK - 1) / PBLOCK;
     int64_t grid = (int64_t)ctx->sm_count * ctx->pool_ctas_per_sm;
     if (grid > tiles) grid = tiles;
-    PPAD_DISPATCH(ctx, (step_pool_kernel<G><<<(unsigned)grid, PBLOCK, 0, st>>>(a)));
+    if (ar) PPAD_DISPATCH(ctx, (step_pool_kernel<G, true><<<(unsigned)grid, PBLOCK, 0, st>>>(a)));
+    else PPAD_DISPATCH(ctx, (step_pool_kernel<G, false><<<(unsigned)grid, PBLOCK, 0, st>>>(a)));
     return after_launch("step_pool_kernel");
 }
 
