@@ -137,7 +137,8 @@ def test_step_fuzz_vs_oracle(pb, rows, cols, mode):
     """wide_*: the 4-bit kernels with all ten orb types of game.py:236-246 in the boards, the skyfall rates and the
     injected sequences; wide3_philox: the 4-bit kernels on a workload of the 3-bit ones"""
     rng = np.random.default_rng(2000 + rows + len(mode))
-    n, steps = 50000 + 17, 8
+    # PPAD_FUZZ_N / PPAD_FUZZ_STEPS: a longer soak of the same differential test (default: seconds)
+    n, steps = int(os.environ.get("PPAD_FUZZ_N", 50000 + 17)), int(os.environ.get("PPAD_FUZZ_STEPS", 8))
     seed = 0x1234567890ABCDEF
     all10 = mode in ("wide_injected", "wide_philox")
     sky = [0.05, 0.15, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1] if all10 else None
