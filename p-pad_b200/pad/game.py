@@ -21,7 +21,7 @@ import numpy as np
 
 from . import parameters
 from . import player
-from . import utils as pad_utils
+from . import utils as pad_utils  # noqa: F401  (the reference's game module exposes it under this name)
 from ..batched import ACTION_IDS, BatchedPAD
 from .. import _cabi
 

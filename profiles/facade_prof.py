@@ -1,4 +1,4 @@
-import sys, os, time, cProfile, pstats
+import sys, os, cProfile, pstats
 sys.path.insert(0, os.getcwd())
 import numpy as np, ppad_b200
 env = ppad_b200.PAD(seed=1)
