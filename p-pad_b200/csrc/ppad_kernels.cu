@@ -383,7 +383,7 @@ struct RolloutArgs {
     uint8_t *traj_action;   // [steps, n] action taken at every step, or NULL
 };
 
-template <class G>
+template <class G, bool RECORD>   // RECORD: the trajectory outputs are compiled in only where they are asked for
 __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ RolloutArgs a)
 {
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
@@ -404,8 +404,10 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
         }
         const StepOut o = step_board<G, true>(valid, s, fin, a.p, a.env0 + (uint64_t)i, -1, nullptr, nullptr, nullptr,
                                               0, (uint32_t)t, &act_blk);
-        if (valid && a.traj_state) StateIO<G>::store(a.traj_state, (int64_t)t * a.n + i, s.b, s.meta);
-        if (valid && a.traj_action) a.traj_action[(int64_t)t * a.n + i] = (uint8_t)o.action;
+        if constexpr (RECORD) {
+            if (valid && a.traj_state) StateIO<G>::store(a.traj_state, (int64_t)t * a.n + i, s.b, s.meta);
+            if (valid && a.traj_action) a.traj_action[(int64_t)t * a.n + i] = (uint8_t)o.action;
+        }
         reward_sum = ppad::dadd(reward_sum, o.reward);
         episodes += (o.info >> 31) & 1u;         // FLAG_EPISODE_DONE
         combos += o.info & 0xFFu;
@@ -1246,7 +1248,8 @@ int ppad_rollout_record(const ppad_ctx *ctx, int64_t n, uint64_t env0, uint32_t 
     a.traj_state = traj_state;
     a.traj_action = traj_action;
     if (traj_state && ((uintptr_t)traj_state & 15)) return fail(PPAD_ERR_INVALID, "ppad_rollout_record: traj_state must be 16-byte aligned");
-    PPAD_DISPATCH(ctx, (rollout_kernel<G><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(a)));
+    if (traj_state || traj_action) PPAD_DISPATCH(ctx, (rollout_kernel<G, true><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(a)));
+    else PPAD_DISPATCH(ctx, (rollout_kernel<G, false><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(a)));
     return after_launch("rollout_kernel");
 }
 
