@@ -1191,13 +1191,15 @@ static int launch_step(const ppad_ctx *ctx, const ppad_step_args *args, cudaStre
         else PPAD_DISPATCH(ctx, (step_obs_kernel<G, true, false><<<grid_for(a.n), BLOCK, 0, st>>>(a)));
         return after_launch("step_obs_kernel");
     }
-    if (coalesced_results || (!a.p.eval_moves && !a.actions && !a.paths)) {
+    if (coalesced_results || (!a.p.eval_moves && !a.actions && !a.paths) || !a.p.skyfall_damage) {
         // results go straight to host memory: the pooled kernel's scattered 8-byte result writes would become tiny
         // PCIe transactions, one thread per board writes them as full lines.
         // Steps of the in-kernel random policy that only evaluate passes (eval_moves = 0, no actions given: plain
         // moves until the episode length cap) take this kernel, too: a warp whose boards all just move leaves early,
         // and there is nothing for the pool to pack (episode mode with one launch per step: 4.4e10 against 3.7e10
         // env.step calls/s).  Given actions may all be passes (calculate_reward of a whole slab): those stay pooled.
+        // Without skyfall (skyfall_damage = 0: the look-ahead's and smart data's evaluations) a board is cancelled
+        // once and never cascades, so there is nothing to pool either: 0.027 against 0.033 ms per 2^20 evaluations.
         if (ar) PPAD_DISPATCH(ctx, (step_obs_kernel<G, false, true><<<grid_for(a.n), BLOCK, 0, st>>>(a)));
         else PPAD_DISPATCH(ctx, (step_obs_kernel<G, false, false><<<grid_for(a.n), BLOCK, 0, st>>>(a)));
         return after_launch("step_obs_kernel<no obs>");
