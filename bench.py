@@ -335,10 +335,10 @@ def main():
         pipe.step(eval_moves=True, obs=obs_buf, step=t, wait=True)
 
     base = 2 + W + K + 10
-    for t in range(base, base + 3):
+    for t in range(base, base + 20):           # the PCIe link and the host side need a few steps to leave their idle states
         e2e_step(t)
     e2e_k = max(5, min(K, 50))
-    e2e_ms = timed(e2e_step, base + 3, e2e_k)
+    e2e_ms = timed(e2e_step, base + 20, e2e_k)
     h2d = pipe.slab.numel() * 4
     d2h = pipe.reward.numel() * 8 + pipe.info.numel() * 4 + pipe.action.numel() + pipe.state.numel() * 4
     # the same with two steps in flight (two sets of host buffers on one pipe; the results of step t are read while
@@ -353,9 +353,9 @@ def main():
         _ = pipe2.buffers[k].reward[0].item()      # "read" them
         pipe2.step(eval_moves=True, obs=obs_buf, step=t, wait=False, buf=k)
 
-    for t in range(base + 100, base + 104):
+    for t in range(base + 100, base + 110):
         e2e_async_step(t)
-    e2e_async_ms = timed(e2e_async_step, base + 104, e2e_k, finish=lambda: (pipe2.join(0), pipe2.join(1)))
+    e2e_async_ms = timed(e2e_async_step, base + 110, e2e_k, finish=lambda: (pipe2.join(0), pipe2.join(1)))
     pipe2.wait(0), pipe2.wait(1)
 
     # episode stats of the last step, all-gathered over NVLink (tiny; outside the timed region)

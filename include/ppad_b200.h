@@ -210,9 +210,10 @@ int ppad_pipe_create(const ppad_ctx *ctx, int64_t n_max, int32_t slab_words_max,
 void ppad_pipe_destroy(ppad_pipe *pipe);
 /* `after_stream`: work already queued there (e.g. ppad_reset) is ordered before the chunks */
 int ppad_pipe_step(ppad_pipe *pipe, const ppad_host_step_args *args, void *after_stream, int32_t slot);
-/* Pinned host buffers are handed to the kernel directly (zero copy over unified addressing: the PCIe traffic
- * overlaps the kernel store by store); pageable buffers, or zero copy switched off, go through the pipe's staging
- * buffers and chunked cudaMemcpyAsync. */
+/* enabled = 1: pinned host buffers are handed to the kernel directly (zero copy over unified addressing: the PCIe
+ * traffic overlaps the kernel store by store); 2: only the results are written in place, the skyfall slab and the
+ * actions travel by DMA chunk by chunk (no PCIe read inside a kernel); 0, or pageable buffers: everything goes
+ * through the pipe's staging buffers and chunked cudaMemcpyAsync. */
 int ppad_pipe_set_zero_copy(ppad_pipe *pipe, int32_t enabled);
 int ppad_pipe_wait(ppad_pipe *pipe, int32_t slot);
 int ppad_pipe_join(ppad_pipe *pipe, void *stream, int32_t slot);

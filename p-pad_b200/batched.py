@@ -383,10 +383,13 @@ class HostPipe:
     """Env steps for callers whose inputs and results live in host memory (the reference's situation:
     PAD.step takes a Python value and appends to Python lists, game.py:329-362).
 
-    zero_copy (default): the kernel reads the skyfall slab from and writes its results to the pinned host buffers
-    directly (unified addressing), so the PCIe traffic overlaps the kernel store by store.  Otherwise the batch is
-    cut into `chunks`; each chunk copies its inputs host -> device, runs the fused step kernel and copies its
-    results device -> host on its own stream, so PCIe traffic in both directions overlaps the kernels.
+    zero_copy=True (default): the kernel reads the skyfall slab from and writes its results to the pinned host buffers
+    directly (unified addressing), so the PCIe traffic overlaps the kernel store by store.  zero_copy='hybrid': only
+    the results are written in place; the slab and the actions travel by DMA, one of `chunks` at a time, so that no
+    PCIe read sits inside a kernel (hosts with a long read latency: 0.75 instead of 1.1 ms per 2^20-board step on
+    one box of the pool; 2-3 % slower than full zero copy elsewhere, with 4 or more chunks).
+    zero_copy=False: the batch is cut into `chunks`; each chunk copies its inputs host -> device, runs the fused
+    step kernel and copies its results device -> host on its own stream.
     The env state and the one-hot observation stay in HBM.  Buffers are pinned and owned by the pipe; with
     depth = 2 there are two sets (``buffers[0]``, ``buffers[1]``) so that step t + 1 can be enqueued before the
     results of step t are read (steps of one pipe always execute in order):
@@ -414,7 +417,8 @@ class HostPipe:
         with torch.cuda.device(venv.device):
             _cabi.check(venv.lib.ppad_pipe_create(venv._ctx, n, self.slab_words, int(chunks), C.byref(handle)))
         self._pipe = handle
-        _cabi.check(venv.lib.ppad_pipe_set_zero_copy(handle, int(bool(zero_copy))))
+        self.mode = {True: 'zero_copy', False: 'staged'}.get(zero_copy, zero_copy)
+        _cabi.check(venv.lib.ppad_pipe_set_zero_copy(handle, 2 if zero_copy == 'hybrid' else int(bool(zero_copy))))
 
     def __del__(self):
         pipe, self._pipe = getattr(self, "_pipe", None), None

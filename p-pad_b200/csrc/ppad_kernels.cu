@@ -1370,16 +1370,18 @@ int ppad_pipe_step(ppad_pipe *p, const ppad_host_step_args *h, void *after_strea
     const bool zc = p->zero_copy && host_is_pinned(h->actions_host) && host_is_pinned(h->slab_host) &&
                     host_is_pinned(h->action_out_host) && host_is_pinned(h->reward_host) && host_is_pinned(h->info_host) &&
                     host_is_pinned(h->state_out_host);
-    const int mode = zc ? 1 : 2;
+    // zero_copy 1: the kernel reads the slab from and writes its results to the host buffers; 2 ("hybrid"): the slab
+    // (and given actions) travel by DMA, chunk by chunk on the pipe's streams, and only the results are written in place
+    // by the kernels -- no PCIe read sits inside a kernel, which matters on hosts whose read latency is high
+    const bool hybrid = zc && p->zero_copy == 2;
+    const int mode = zc && !hybrid ? 1 : 2;
     if (p->last_mode && p->last_mode != mode)   // stream <-> board mapping changes: order behind the previous step
         for (int k = 0; k < p->chunks && e == cudaSuccess; k++)
             for (int j = 0; j < p->chunks && e == cudaSuccess; j++)
                 e = cudaStreamWaitEvent(p->streams[k], p->done[p->last_slot][j], 0);
     p->last_mode = mode;
     p->last_slot = slot;
-    if (e == cudaSuccess && zc && host_is_pinned(h->actions_host) && host_is_pinned(h->slab_host) &&
-        host_is_pinned(h->action_out_host) && host_is_pinned(h->reward_host) && host_is_pinned(h->info_host) &&
-        host_is_pinned(h->state_out_host)) {
+    if (e == cudaSuccess && zc && !hybrid) {
         // Zero copy: with unified addressing the kernel reads the skyfall slab from, and writes reward / info /
         // action / the state copy to, the pinned host buffers themselves.  The PCIe traffic then overlaps the
         // kernel store by store instead of chunk by chunk (measured 0.74 ms against 0.87 ms per 2^20-board step).
@@ -1440,14 +1442,25 @@ int ppad_pipe_step(ppad_pipe *p, const ppad_host_step_args *h, void *after_strea
             a.n_inj = h->n_inj;
         }
         if (e != cudaSuccess) break;
-        a.action_out = h->action_out_host ? p->d_action_out + lo : nullptr;
-        a.reward = h->reward_host ? p->d_reward + lo : nullptr;
-        a.info = h->info_host ? p->d_info + lo : nullptr;
+        if (hybrid) {
+            a.action_out = h->action_out_host ? h->action_out_host + lo : nullptr;
+            a.reward = h->reward_host ? h->reward_host + lo : nullptr;
+            a.info = h->info_host ? h->info_host + lo : nullptr;
+            a.state_copy = h->state_out_host ? (char *)h->state_out_host + (size_t)lo * rec : nullptr;
+        } else {
+            a.action_out = h->action_out_host ? p->d_action_out + lo : nullptr;
+            a.reward = h->reward_host ? p->d_reward + lo : nullptr;
+            a.info = h->info_host ? p->d_info + lo : nullptr;
+        }
         if (h->obs) {
             a.obs = (char *)h->obs + (size_t)lo * obs_row;
             a.obs_dtype = h->obs_dtype;
         }
-        if (int r = launch_step(ctx, &a, st)) return r;
+        if (int r = launch_step(ctx, &a, st, hybrid)) return r;
+        if (hybrid) {
+            e = cudaEventRecord(p->done[slot][k], st);
+            continue;
+        }
         if (h->reward_host)
             e = cudaMemcpyAsync(h->reward_host + lo, p->d_reward + lo, (size_t)cnt * 8, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess && h->info_host)
@@ -1465,7 +1478,7 @@ int ppad_pipe_step(ppad_pipe *p, const ppad_host_step_args *h, void *after_strea
 int ppad_pipe_set_zero_copy(ppad_pipe *p, int32_t enabled)
 {
     if (!p) return fail(PPAD_ERR_INVALID, "ppad_pipe_set_zero_copy: null pipe");
-    p->zero_copy = enabled ? 1 : 0;
+    p->zero_copy = enabled == 2 ? 2 : (enabled ? 1 : 0);
     return PPAD_OK;
 }
 

@@ -406,7 +406,7 @@ def test_smart_data_and_lookahead(pb):
     assert ((roam <= 4) | (roam == 255)).all() and (roam[:, :, :4] != 255).any()
 
 
-@pytest.mark.parametrize("zero_copy", [True, False])
+@pytest.mark.parametrize("zero_copy", [True, False, "hybrid"])
 @pytest.mark.parametrize("rows,cols,n", [(5, 6, 100_000 + 37), (6, 7, 33_333), (5, 6, 200)])
 def test_host_pipe_equals_device_step(pb, rows, cols, n, zero_copy):
     """ppad_pipe_step (host buffers, chunked over streams) == ppad_step (device buffers), incl. a ragged tail"""
