@@ -1,0 +1,405 @@
+// ppad_step.cuh -- the env-step kernels (one thread per board with the fused observation; persistent CTAs with a
+// recirculating cascade pool for the state-only step; T fused steps of the random policy) and their per-geometry
+// launchers.  Instantiated once per geometry by ppad_step_inst.cu (-DPPAD_GEOM=0..5), so the geometries compile in
+// parallel; ppad_step.cu holds the C ABI on top of the launchers.
+#pragma once
+#include "ppad_device.cuh"
+
+namespace ppad {
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+struct StepKernelArgs {
+    StepParams p;
+    int64_t n;
+    uint64_t env0;
+    void *state;
+    const uint8_t *actions;
+    const uint32_t *slab;
+    uint8_t *action_out;
+    double *reward;
+    uint32_t *info;
+    void *final_state;
+    void *state_copy;
+    uint16_t *combo_log;
+    void *obs;
+    int32_t obs_dtype;
+    const uint32_t *paths;
+    const uint16_t *path_lens;
+    int32_t path_words, path_len;
+    int32_t stage_slab;   // 1: the slab is pinned HOST memory (zero copy), 4 words per board: fetch each row once, up front
+};
+
+// The step WITH the one-hot observation, one thread per board.  This variant is bound by the 840 B/board store
+// stream, and keeping all eight warps of a CTA busy (each runs its own boards' cascades in a warp-uniform
+// loop, then emits its observation) overlaps the stores with the integer work best: measured 0.159 ms per
+// 2^20-board step against 0.162-0.166 ms for packing the cascades once and 0.19 ms for the pooled kernel.
+// Four resident CTAs per SM (64 registers) is the measured optimum with fp32 obs: 0.1546 ms against 0.1556 (3),
+// 0.1875 (2), 0.1685 (5, spills) and 0.1731 (6).  Emitting the observation before the cascades (0.167 ms), or
+// before them in the odd warps and after them in the even warps (0.156 ms), is not faster either.
+// (6x7 with 4-bit codes -- four 64-bit planes -- is the one geometry that does better with 3: 0.221 against 0.240 ms.)
+// AR: the launch has auto_reset set.  Launches without it run an instantiation that does not contain the reset code
+// at all; those with it get the unrolled Philox refill (a Boltzmann-policy rollout resets 29 % of its boards per step:
+// 0.227 ms per 2^20-board step with fp32 obs against 0.286 ms with the plain refill, profiles/ar_bench.py).
+template <class G, bool OBS, bool AR>
+__global__ void __launch_bounds__(BLOCK, (sizeof(typename G::W) == 8 && G::NP == 4) ? 3 : 4) step_obs_kernel(const __grid_constant__ StepKernelArgs a)
+{
+    __shared__ ObsShared obs_sh;
+    __shared__ uint32_t obs_stream[OBS ? (BLOCK / 32) * ObsGeom<G>::WARP_WORDS : 1];
+    if (OBS) {
+        obs_init_luts(obs_sh);
+        __syncthreads();
+    }
+    const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    const bool valid = i < a.n;
+    State<G> s;
+    clear_state<G>(s);
+    int action = -1, path_len = 0;
+    if (valid) {
+        s = StateIO<G>::load(a.state, i);
+        if (a.actions) {
+            action = a.actions[i];
+            if (action == PPAD_SAMPLE) action = -1;
+        }
+        if (a.paths) {
+            path_len = a.path_lens ? a.path_lens[i] : a.path_len;
+            path_len = path_len > 16 * a.path_words ? 16 * a.path_words : path_len;
+        }
+    }
+    const uint32_t *slab = a.slab && valid ? a.slab + (size_t)i * a.p.slab_words : nullptr;
+    __shared__ uint4 slab_rows[BLOCK];
+    if (a.stage_slab) {   // kernel-uniform
+        // Zero copy: the skyfall slab lives in pinned host memory.  The cascade reads its words lazily, which over
+        // PCIe is one 4-byte round trip per lane and cascade iteration; fetch the board's whole 16-byte row once
+        // instead (512 contiguous bytes per warp, in flight together with the state load) and let the cascade read
+        // it from shared memory.
+        if (slab) {
+            slab_rows[threadIdx.x] = __ldg(reinterpret_cast<const uint4 *>(slab));
+            slab = reinterpret_cast<const uint32_t *>(&slab_rows[threadIdx.x]);
+        }
+        __syncwarp();
+    }
+    // every lane takes part (the cascade loop inside is warp-uniform); lanes past the batch are not live
+    Board<G> fin;
+    const StepOut o = step_board<G, AR, AR>(valid, s, fin, a.p, a.env0 + (uint64_t)i, action, slab,
+                                    a.combo_log && valid ? a.combo_log + (size_t)i * a.p.log_cap : nullptr,
+                                    a.paths && valid ? a.paths + (size_t)i * a.path_words : nullptr, path_len);
+    if (valid) {
+        StateIO<G>::store(a.state, i, s.b, s.meta);
+        if (a.action_out) a.action_out[i] = (uint8_t)o.action;
+        if (a.reward) a.reward[i] = o.reward;
+        if (a.info) a.info[i] = o.info;
+        if (a.final_state) StateIO<G>::store(a.final_state, i, fin, s.meta);
+        if (a.state_copy) StateIO<G>::store(a.state_copy, i, s.b, s.meta);
+    }
+    const int64_t warp0 = i - (threadIdx.x & 31);
+    if (OBS && warp0 < a.n) {
+        const int n_valid = (int)(a.n - warp0 < 32 ? a.n - warp0 : 32);
+        emit_obs<G>(s, valid, n_valid, obs_stream + (threadIdx.x >> 5) * ObsGeom<G>::WARP_WORDS, obs_sh,
+                    obs_warp_ptr<G>(a.obs, warp0, a.obs_dtype), a.obs_dtype);
+    }
+}
+
+// T consecutive steps of the in-kernel random policy in one launch: the board stays in registers between
+// steps, only the final state and per-board totals are written.  Equals T calls of ppad_step(actions = NULL,
+// step = step0 + t) without injected skyfall / observation (tests/test_gpu_parity.py::test_fused_rollout_equals_single_steps).
+struct RolloutArgs {
+    StepParams p;
+    int64_t n;
+    uint64_t env0;
+    int32_t steps;
+    void *state;
+    double *reward_sum;
+    uint32_t *episodes;
+    uint32_t *combos_sum;
+    uint8_t *flags_or;
+    void *traj_state;       // [steps, n] packed records after every step (time-major: coalesced), or NULL
+    uint8_t *traj_action;   // [steps, n] action taken at every step, or NULL
+};
+
+template <class G, bool RECORD>   // RECORD: the trajectory outputs are compiled in only where they are asked for
+__global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ RolloutArgs a)
+{
+    const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    const bool valid = i < a.n;
+    State<G> s;
+    clear_state<G>(s);
+    if (valid) s = StateIO<G>::load(a.state, i);
+    double reward_sum = 0.0;
+    uint32_t episodes = 0, combos = 0, flags = 0;
+    U4 act_blk = {0, 0, 0, 0};
+    for (int t = 0; t < a.steps; t++) {          // every lane runs every step: the cascade loop is warp-uniform
+        Board<G> fin;
+        const uint32_t step = a.p.key.step + (uint32_t)t;
+        if (t == 0 || (step & 3u) == 0) {        // one Philox block holds the action draws of four steps
+            RngKey key = board_key(a.p, a.env0 + (uint64_t)i);
+            key.step = step;
+            act_blk = action_block(key);
+        }
+        const StepOut o = step_board<G, true>(valid, s, fin, a.p, a.env0 + (uint64_t)i, -1, nullptr, nullptr, nullptr,
+                                              0, (uint32_t)t, &act_blk);
+        if constexpr (RECORD) {
+            if (valid && a.traj_state) StateIO<G>::store(a.traj_state, (int64_t)t * a.n + i, s.b, s.meta);
+            if (valid && a.traj_action) a.traj_action[(int64_t)t * a.n + i] = (uint8_t)o.action;
+        }
+        reward_sum = ppad::dadd(reward_sum, o.reward);
+        episodes += (o.info >> 31) & 1u;         // FLAG_EPISODE_DONE
+        combos += o.info & 0xFFu;
+        flags |= o.info >> 24;
+    }
+    if (valid) {
+        StateIO<G>::store(a.state, i, s.b, s.meta);
+        if (a.reward_sum) a.reward_sum[i] = reward_sum;
+        if (a.episodes) a.episodes[i] = episodes;
+        if (a.combos_sum) a.combos_sum[i] = combos;
+        if (a.flags_or) a.flags_or[i] = (uint8_t)flags;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Persistent step kernel with a recirculating cascade pool.
+//
+// Cascade depth is geometric-like (about 45 % of the boards: 0 iterations, 38 %: 1, 12 %: 2, ...), so a warp
+// that keeps its own 32 boards runs every iteration for its unluckiest lane at ~40 % lane occupancy, and
+// packing only once leaves the deep tail to a few lanes.  Here each CTA is persistent and owns a pool of
+// boards that are still cascading, parked in shared memory between iterations:
+//   fill : when the pool is low, run the cheap convergent part (action, move, first match test, write-back) on
+//          the next tile of BLOCK boards and append the boards that matched;
+//   round: the top min(pool, BLOCK) boards run ONE cascade iteration on dense warps; finished boards write
+//          their reward, the others go back to the pool.
+// Deep boards simply stay in the pool while fresh tiles keep streaming in, so every round has (nearly) a
+// full complement of lanes; only the final drain of each CTA runs at low occupancy.  Measured (2^20 boards):
+// 0.089 ms per step against 0.112 ms for one-thread-per-board and 0.098 ms for packing once.
+// The variant that also emits observations (step_obs_kernel) does NOT use a pool.  Its store stream keeps the
+// SM's memory-instruction queue (MIO) backed up with STG.128; a cascade that lives purely in registers and
+// ALU instructions overlaps that for free, but one that parks boards in shared memory queues its LDS/STS
+// behind the stores.  Measured with fp32 obs: 0.159 ms one thread per board, 0.19 ms with this CTA pool,
+// 0.21 ms with a barrier-free per-warp pool (which ties the CTA pool at 0.090 ms without obs).
+// ------------------------------------------------------------------------------------------------
+#if !defined(PPAD_POOL_BLOCK)
+#define PPAD_POOL_BLOCK 256
+#endif
+#if !defined(PPAD_POOL_MINB)
+#define PPAD_POOL_MINB (1024 / PPAD_POOL_BLOCK)
+#endif
+constexpr int PBLOCK = PPAD_POOL_BLOCK;        // threads per CTA of the pooled kernel
+constexpr int POOL_SLOTS = PBLOCK + PBLOCK / 2;
+constexpr int POOL_FILL_BELOW = PBLOCK / 2;    // fill while pool <= this: pool + PBLOCK <= POOL_SLOTS always holds
+
+template <class G>
+struct CascadePool {
+    typename G::W b0[POOL_SLOTS], b1[POOL_SLOTS], b2[POOL_SLOTS], b3[G::NP > 3 ? POOL_SLOTS : 1];
+    double t0[POOL_SLOTS], t1[POOL_SLOTS], t2[POOL_SLOTS], t3[POOL_SLOTS], t4[POOL_SLOTS];
+    uint32_t counts[POOL_SLOTS];   // n_combos [0,16) | depth [16,24) | flags [24,32)
+    uint32_t source[POOL_SLOTS];   // skyfall cursor [0,16) | injected slab exhausted [16]
+    uint64_t owner[POOL_SLOTS];    // board index within the launch
+    int warp_count[2][PBLOCK / 32];   // double buffered: consecutive compactions alternate, one barrier each
+
+    __device__ __forceinline__ void put(int slot, const CascadeItem<G> &it, uint64_t own)
+    {
+        b0[slot] = it.b.b0;
+        b1[slot] = it.b.b1;
+        b2[slot] = it.b.b2;
+        PPAD_P4(b3[slot] = it.b.b3)
+        t0[slot] = it.tally.t0;
+        t1[slot] = it.tally.t1;
+        t2[slot] = it.tally.t2;
+        t3[slot] = it.tally.t3;
+        t4[slot] = it.tally.t4;
+        const uint32_t nc = it.tally.n_combos > 0xFFFF ? 0xFFFFu : (uint32_t)it.tally.n_combos;
+        counts[slot] = nc | (sat255(it.depth) << 16) | ((it.flags & 0xFFu) << 24);
+        source[slot] = (it.cursor > 0xFFFF ? 0xFFFFu : (uint32_t)it.cursor) | ((it.exhausted ? 1u : 0u) << 16);
+        owner[slot] = own;
+    }
+    __device__ __forceinline__ uint64_t get(int slot, CascadeItem<G> &it) const
+    {
+        it.b.b0 = b0[slot];
+        it.b.b1 = b1[slot];
+        it.b.b2 = b2[slot];
+        PPAD_P4(it.b.b3 = b3[slot])
+        it.tally.t0 = t0[slot];
+        it.tally.t1 = t1[slot];
+        it.tally.t2 = t2[slot];
+        it.tally.t3 = t3[slot];
+        it.tally.t4 = t4[slot];
+        const uint32_t c = counts[slot], q = source[slot];
+        it.tally.n_combos = (int)(c & 0xFFFFu);
+        it.depth = (int)((c >> 16) & 0xFFu);
+        it.flags = c >> 24;
+        it.cursor = (int)(q & 0xFFFFu);
+        it.exhausted = (q >> 16) & 1u;
+        return owner[slot];
+    }
+    // CTA-wide stable compaction (ONE __syncthreads; every thread must call it, `phase` alternates 0/1 from call
+    // to call: the counts of call k live in buffer k & 1, and call k + 2 can only overwrite them after every thread
+    // has passed the barrier of call k + 1, i.e. has finished reading them)
+    __device__ __forceinline__ int compact(bool keep, int &total, int phase)
+    {
+        const unsigned ballot = __ballot_sync(0xFFFFFFFFu, keep);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane == 0) warp_count[phase][warp] = __popc(ballot);
+        __syncthreads();
+        int base = 0, sum = 0;
+#pragma unroll
+        for (int w = 0; w < PBLOCK / 32; w++) {
+            const int c = warp_count[phase][w];
+            if (w < warp) base += c;
+            sum += c;
+        }
+        total = sum;
+        return base + __popc(ballot & ((1u << lane) - 1u));
+    }
+};
+
+template <class G, bool AR>
+__global__ void __launch_bounds__(PBLOCK, PPAD_POOL_MINB) step_pool_kernel(const __grid_constant__ StepKernelArgs a)
+{
+    __shared__ CascadePool<G> pool;
+    typedef typename G::W W;
+    const int tid = threadIdx.x;
+    const int64_t n_tiles = (a.n + PBLOCK - 1) / PBLOCK;
+    const bool sd = a.p.skyfall_damage != 0;
+    int64_t tile = blockIdx.x;
+    int pool_count = 0;                          // CTA-uniform
+    int phase = 0;                               // CTA-uniform: which count buffer the next compaction uses
+
+    for (;;) {
+        // ---- fill: the convergent part of the step for one fresh tile, when the pool is low
+        const bool fill = tile < n_tiles && pool_count <= POOL_FILL_BELOW;
+        if (!fill && pool_count == 0) break;    // no tiles left (pool_count == 0 <= POOL_FILL_BELOW) and pool drained
+        if (fill) {
+            const int64_t i = tile * PBLOCK + tid;
+            const bool valid = i < a.n;
+            State<G> s;
+            CascadeItem<G> it;
+            bool cascading = false;
+            StepPrefix pre;
+            pre.action = 255;
+            pre.flags = 0;
+            pre.evaluate = false;
+            clear_state<G>(s);
+            if (valid) {
+                s = StateIO<G>::load(a.state, i);
+                const RngKey key = board_key(a.p, a.env0 + (uint64_t)i);
+                if (a.paths) {
+                    int len = a.path_lens ? a.path_lens[i] : a.path_len;
+                    len = len > 16 * a.path_words ? 16 * a.path_words : len;
+                    pre = path_prefix<G>(s, a.p, a.paths + (size_t)i * a.path_words, len);
+                } else {
+                    int action = -1;
+                    if (a.actions) {
+                        action = a.actions[i];
+                        if (action == PPAD_SAMPLE) action = -1;
+                    }
+                    pre = step_prefix<G>(s, a.p, key, action);
+                }
+            }
+            it.init(s.b, pre.flags);             // the cascade works on a copy (game.py:366)
+            if (valid && pre.evaluate) {
+                W er, ed;
+                cascading = match_mask<G>(it.b, er, ed) != 0;
+            }
+            if constexpr (AR) {                   // launches with auto_reset; the reset is warp-cooperative
+                const bool need = valid && pre.action == ACT_PASS;
+                const uint32_t f = reset_boards_warp<G, true>(need, s, a.p, a.p.key.step, a.env0 + (uint64_t)i, nullptr, -1, -1, nullptr);
+                if (need) it.flags |= FLAG_EPISODE_DONE | f;
+            }
+            if (valid) {
+                StateIO<G>::store(a.state, i, s.b, s.meta);
+                if (a.action_out) a.action_out[i] = (uint8_t)pre.action;
+                if (a.final_state) StateIO<G>::store(a.final_state, i, it.b, s.meta);   // planes rewritten after a cascade
+                if (a.state_copy) StateIO<G>::store(a.state_copy, i, s.b, s.meta);
+                if (!cascading) {
+                    if (a.reward) a.reward[i] = 0.0;
+                    if (a.info) a.info[i] = it.info();
+                }
+            }
+            int added;
+            const int slot = pool.compact(cascading, added, phase);
+            phase ^= 1;
+            if (cascading) pool.put(pool_count + slot, it, (uint64_t)i);
+            pool_count += added;
+            tile += gridDim.x;
+        }
+        __syncthreads();                          // every put() of this fill and of the previous round is visible
+
+        // ---- round: one cascade iteration for the top m boards of the pool, on dense warps
+        const int m = pool_count < PBLOCK ? pool_count : PBLOCK;
+        const int base = pool_count - m;
+        CascadeItem<G> it;
+        uint64_t own = 0;
+        bool again = false;
+        if (tid < m) {
+            own = pool.get(base + tid, it);
+            const RngKey key = board_key(a.p, a.env0 + own);
+            again = cascade_round<G>(it, sd, a.p.cascade_cap, a.p.team,
+                                     a.slab ? a.slab + (size_t)own * a.p.slab_words : nullptr, a.p.n_inj, key, a.p.sky,
+                                     a.combo_log ? a.combo_log + (size_t)own * a.p.log_cap : nullptr, a.p.log_cap);
+            if (!again) {
+                if (a.reward) a.reward[own] = it.reward();
+                if (a.info) a.info[own] = it.info();
+                if (a.final_state) StateIO<G>::store_planes(a.final_state, own, it.b);   // meta: written by the fill
+            }
+        }
+
+        if (m > 0) {                             // CTA-uniform
+            int survivors;
+            const int slot = pool.compact(again, survivors, phase);   // its barrier: every get() of the round is done
+            phase ^= 1;
+            if (again) pool.put(base + slot, it, own);   // read again only after the barrier at the top of the round
+            pool_count = base + survivors;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-geometry launchers (explicitly instantiated in ppad_step_inst.cu)
+// ------------------------------------------------------------------------------------------------
+enum StepKernelChoice { STEP_KERNEL_OBS = 0, STEP_KERNEL_THREAD = 1, STEP_KERNEL_POOL = 2 };
+
+template <class G>
+int launch_step_g(const ppad_ctx *ctx, const StepKernelArgs &a, int choice, cudaStream_t st)
+{
+    const bool ar = a.p.auto_reset != 0;
+    if (choice == STEP_KERNEL_OBS) {
+        if (ar) step_obs_kernel<G, true, true><<<grid_for(a.n), BLOCK, 0, st>>>(a);
+        else step_obs_kernel<G, true, false><<<grid_for(a.n), BLOCK, 0, st>>>(a);
+        return after_launch("step_obs_kernel");
+    }
+    if (choice == STEP_KERNEL_THREAD) {
+        if (ar) step_obs_kernel<G, false, true><<<grid_for(a.n), BLOCK, 0, st>>>(a);
+        else step_obs_kernel<G, false, false><<<grid_for(a.n), BLOCK, 0, st>>>(a);
+        return after_launch("step_obs_kernel<no obs>");
+    }
+    // persistent: one wave of CTAs, as many as fit
+    const int64_t tiles = (a.n + PBLOCK - 1) / PBLOCK;
+    int64_t grid = (int64_t)ctx->sm_count * ctx->pool_ctas_per_sm;
+    if (grid > tiles) grid = tiles;
+    if (ar) step_pool_kernel<G, true><<<(unsigned)grid, PBLOCK, 0, st>>>(a);
+    else step_pool_kernel<G, false><<<(unsigned)grid, PBLOCK, 0, st>>>(a);
+    return after_launch("step_pool_kernel");
+}
+
+template <class G>
+int launch_rollout_g(const RolloutArgs &a, bool record, cudaStream_t st)
+{
+    if (record) rollout_kernel<G, true><<<grid_for(a.n), BLOCK, 0, st>>>(a);
+    else rollout_kernel<G, false><<<grid_for(a.n), BLOCK, 0, st>>>(a);
+    return after_launch("rollout_kernel");
+}
+
+template <class G>
+int pool_occupancy_g()
+{
+    int ctas = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, step_pool_kernel<G, true>, PBLOCK, 0);
+    return ctas;
+}
+
+#define PPAD_STEP_LAUNCHERS(PREFIX, G)                                                                        \
+    PREFIX template int launch_step_g<G>(const ppad_ctx *, const StepKernelArgs &, int, cudaStream_t);        \
+    PREFIX template int launch_rollout_g<G>(const RolloutArgs &, bool, cudaStream_t);                         \
+    PREFIX template int pool_occupancy_g<G>();
+
+}   // namespace ppad
