@@ -7,14 +7,29 @@
 Workload (BASELINE.json configs[1]): 2^20 independent 5x6 boards per GPU, one env step per board per
 "step": a uniformly random legal non-reversing move (PlayerAction.sample, in-kernel Philox), the
 orb swap, the full cascade resolution on a copy (cancel -> drop -> skyfall until stable) with the
-skyfall taken from an injected 32-orb slab per board per step, the float64 reward, the packed state
-written back and the fp32 one-hot observation [n,5,6,7] of the new state -- ONE fused kernel launch.
-N > 1: every rank owns its own 2^20-board slab (env ids rank * 2^20 + i); no data-path collective
-(weak scaling); a stats all-gather follows the timed region.
+skyfall taken from an injected 32-orb slab per board per step (3 bits per orb, 12 bytes), the float64
+reward, the packed state written back and the fp32 one-hot observation [n,5,6,7] of the new state --
+ONE fused kernel launch.  N > 1: every rank owns its own 2^20-board slab (env ids rank * 2^20 + i); no
+data-path collective (weak scaling).
 
-Timing: W >= 3 warm-up steps, then K steps between barrier + synchronize, CUDA events on the launch
-stream, max over ranks.  Every step streams 881 MB of obs (7x the 126 MB L2) and the skyfall slabs
-rotate over 16 buffers (268 MB), so no step finds its inputs in L2.
+Timing: W >= 3 warm-up steps, then EXACTLY K steps between barrier + synchronize, CUDA events on the launch
+stream, max over ranks -> `value`.  Because K steps of 0.16 ms are a short region, a steady-state leg of
+>= 0.6 s follows with one CUDA event per step (`steady`: median / p10 / p90 per step) while nvidia-smi is
+sampled every 100 ms (>= 5 samples).  Every step streams 881 MB of obs (7x the 126 MB L2) and the skyfall
+slabs rotate over 16 buffers (201 MB), so no step finds its inputs in L2.
+
+Sub-records of the same JSON line (all measured in this run, on every rank, max over ranks):
+  state_only    the same step without the observation stream (persistent pool kernel), L2 flushed
+  e2e           the same step through HostPipe.step (ppad_pipe_step): pinned HOST buffers, the skyfall slab crosses
+                PCIe host -> device and the compact result stream device -> host inside the timed region
+  rollout       BASELINE configs[4]: 2^23 boards per GPU, Boltzmann policy on synthetic Q-values, auto-reset, fp32 obs,
+                replay ring with discounted returns, statistics; NCCL all-gathers of stats + replay samples INSIDE the
+                timed region
+  config2       BASELINE configs[2]: 2^24 boards, finger paths of 200 moves applied in one launch, then resolved
+  config3       BASELINE configs[3]: 7x6 boards, obs step + smart-data style trajectory generation
+  episode_mode  50 random moves + pass + reset, per-step launches and fused
+  cpu_baseline  the C port of the reference's path on all host threads and, where the reference's sources were staged
+                by build() (oracle/_ref), the unmodified Python reference itself on all host cores
 """
 import argparse
 import json
@@ -32,19 +47,26 @@ sys.path.insert(0, ROOT)
 N_LOCAL = 1 << 20
 ROWS, COLS = 5, 6
 SLAB_ORBS = 32
+SLAB_FORMAT = 'planes3'          # PPAD_SLAB_PLANES3: 3 bits per orb, 12 bytes per 32 orbs
+SLAB_BYTES = 12
 N_SLABS = 16
 SEED = 20181019
 # algorithmic bytes per board-step (restated in DESIGN.md):
-#   state in 16 + state out 16 + action 1 + reward 8 + info 4 + skyfall slab 16 = 61; + fp32 obs 840
-BYTES_STATE_ONLY = 61
-BYTES_WITH_OBS = 61 + ROWS * COLS * 7 * 4
+#   state in 16 + state out 16 + action 1 + reward 8 + info 4 + skyfall slab 12 (32 orbs x 3 bit) = 57; + fp32 obs 840
+BYTES_STATE_ONLY = 45 + SLAB_BYTES
+BYTES_WITH_OBS = BYTES_STATE_ONLY + ROWS * COLS * 7 * 4
+# configs[4] policy step: state 32, q 20, results 13, obs 840, replay ring row 16 + 1 + 8
+BYTES_ROLLOUT = 32 + 20 + 13 + 840 + 25
 
 
 def workload_config(n, world):
     return {"workload": "configs[1]: 2^20 5x6 boards/GPU, random legal move + full cascade resolve + "
-                        "fp32 one-hot obs, injected 32-orb skyfall slab per board-step",
+                        "fp32 one-hot obs, injected 32-orb skyfall slab (3 bit/orb, 12 B) per board-step",
             "boards_per_gpu": n, "rows": ROWS, "cols": COLS, "skyfall_orbs_per_step": SLAB_ORBS,
-            "l2": "inputs > L2: 881 MB obs stream per step, skyfall slabs rotate over 16 buffers (268 MB)",
+            "skyfall_slab": "32 orbs not 42: 12 B instead of 16 B per board-step across PCIe in the e2e leg; a board that "
+                            "draws more than 32 orbs in one step (about 6e-5 of them) continues on the Philox stream at "
+                            "the same draw index, flagged SKYFALL_EXHAUSTED, bit-exact against the oracle which does the same",
+            "l2": "inputs > L2: 881 MB obs stream per step, skyfall slabs rotate over 16 buffers (201 MB)",
             "parallelism": "env-sharded x%d, no data-path collective" % world}
 
 
@@ -92,6 +114,9 @@ class ClockSampler:
                 "power_w_max": max(float(r[2]) for r in rows), "reasons": reasons}
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# CPU legs
+# ---------------------------------------------------------------------------------------------------------------
 def cpu_port_rate(n_sample, steps, threads):
     """The oracle (C port of the reference's path) timed on `threads` host cores: same workload, bounded sample."""
     import oracle as orc
@@ -129,9 +154,54 @@ def cpu_port_rate(n_sample, steps, threads):
     return n_sample / float(np.mean(times)), float(np.mean(times))
 
 
+def python_reference_rate(seconds=8.0):
+    """the UNMODIFIED Python reference (staged by build() into the git-ignored oracle/_ref/ from
+    /root/reference; absent -> None) on P = os.cpu_count() processes, one env each: (a) the resolved-step loop of
+    projects/simulation.py:117-119, (b) the episode loop of projects/visualize_episode.py:28-33 with L = 50."""
+    ref_root = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir(os.path.join(ref_root, "ppad", "pad")):
+        return None
+    procs = os.cpu_count() or 1
+    script = os.path.join(ROOT, "oracle", "ref_bench.py")
+    out = {}
+    for mode in ("resolved", "episode"):
+        ps = [subprocess.Popen([sys.executable, script, "--mode", mode, "--seconds", str(seconds), "--seed", str(100 + k),
+                                "--root", ref_root], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+              for k in range(procs)]
+        rates = []
+        for p in ps:
+            txt, _ = p.communicate(timeout=seconds * 6 + 60)
+            try:
+                rates.append(json.loads(txt.strip().splitlines()[-1]))
+            except Exception:
+                pass
+        if not rates:
+            return None
+        out[mode] = rates
+    cpu = "unknown"
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                cpu = line.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    res = sum(r["steps"] / r["seconds"] for r in out["resolved"])
+    epi = sum(r["steps"] / r["seconds"] for r in out["episode"])
+    return {"resolved_steps_per_s": res, "resolved_steps_per_s_per_core": res / len(out["resolved"]),
+            "episode_env_step_calls_per_s": epi, "episode_env_step_calls_per_s_per_core": epi / len(out["episode"]),
+            "episodes_per_s": sum(r["episodes"] / r["seconds"] for r in out["episode"]),
+            "processes": len(out["resolved"]), "cpu_model": cpu, "seconds_per_loop": seconds,
+            "what": "unmodified ppad/pad/game.py + utils.py + player.py (TF stub + int clock patches only), PAD() defaults "
+                    "(5x6, skyfall on): resolved = env.step(env.action_space.sample()); env.calculate_reward(board=env.board, "
+                    "skyfall_damage=True) (simulation.py:117-119); episode = reset() + 50 sampled moves + step('pass') "
+                    "(visualize_episode.py:28-33)"}
+
+
 def run_reference(args):
-    """--impl reference: the reference is pure Python and does not travel to the GPU box, so this arm times
-    the oracle port (oracle/ppad_oracle.c) of the same path on all host cores."""
+    """--impl reference: the reference is pure Python; this arm times the oracle port (oracle/ppad_oracle.c) of the same
+    path on all host cores -- a far FASTER baseline than the reference itself, which is reported beside it
+    (cpu_baseline.python_reference) wherever its sources were staged."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -150,75 +220,201 @@ def run_reference(args):
         "config": workload_config(N_LOCAL, args.gpus),
         "cpu_baseline": {"value": rate, "unit": "steps/s", "cores": threads, "kind": "port",
                          "sample": "%d boards per step x %d steps of the same workload (move + cascade + fp32 obs), C port "
-                                   "of ppad/pad/game.py + utils.py + agent01.py:254-273 on %d threads; the Python "
-                                   "reference itself measured ~157 steps/s/core (BASELINE.md section 2)" % (
+                                   "of ppad/pad/game.py + utils.py + agent01.py:254-273 on %d threads" % (
                                        n_sample, args.steps, threads)},
         "e2e": {"value": rate, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_python_reference:
+        pr = python_reference_rate(6.0)
+        if pr:
+            line["cpu_baseline"]["python_reference"] = pr
     print(json.dumps(line))
 
 
-def run_rollout(args, rank, local_rank, world):
-    """BASELINE configs[4] (scaled to --boards per GPU): per step synthetic Q-values q ~ N(0, 1) * 1000 (stand-in for
-    Agent01), masking + Boltzmann selection, env step with auto-reset and fp32 one-hot obs, push of (state, action,
-    reward) into the per-GPU replay ring; every 10 steps an NCCL all-gather of the stats vector and of 32 replay rows
-    per GPU.  The Q-value generation (torch.randn) is inside the timed region, like the agent's forward pass would be."""
+# ---------------------------------------------------------------------------------------------------------------
+# GPU legs
+# ---------------------------------------------------------------------------------------------------------------
+class Timer:
+    def __init__(self, torch, dist, dev, world):
+        self.torch, self.dist, self.dev, self.world = torch, dist, dev, world
+
+    def max_over_ranks(self, ms):
+        t = self.torch.tensor([ms], device=self.dev, dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, fn, k0, count, finish=None):
+        """barrier + sync, `count` steps between CUDA events on the launch stream, sync; max over ranks (ms).
+        finish(): joins side streams into the launch stream before the closing event."""
+        torch = self.torch
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for t in range(k0, k0 + count):
+            fn(t)
+        if finish is not None:
+            finish()
+        e1.record()
+        torch.cuda.synchronize()
+        return self.max_over_ranks(e0.elapsed_time(e1))
+
+    def per_step(self, fn, k0, count):
+        """one CUDA event per step: per-step durations in ms (this rank)"""
+        torch = self.torch
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(count + 1)]
+        ev[0].record()
+        for j in range(count):
+            fn(k0 + j)
+            ev[j + 1].record()
+        torch.cuda.synchronize()
+        return np.array([ev[j].elapsed_time(ev[j + 1]) for j in range(count)])
+
+
+def leg_rollout(ppad_b200, pdist, T, args, rank, world, dev, peak):
+    """BASELINE configs[4] at --rollout-boards per GPU (default 2^23): per step the fused policy kernel
+    (ppad_policy_step: Boltzmann selection on Q-values resident in HBM -- 4 rotating synthetic buffers q ~ N(0,1) * 1000,
+    the stand-in for Agent01's output --, episode cap 50, env step, auto-reset, fp32 one-hot obs, time-major replay ring
+    with discounted returns, statistics); every 10 steps the statistics vector and 32 replay rows per GPU are
+    all-gathered over NCCL, inside the timed region."""
     import torch
-    import torch.distributed as dist
-    import ppad_b200
-    from ppad_b200 import dist as pdist
-    from ppad_b200.replay import ReplayBuffer
-    dev = torch.device("cuda", local_rank)
-    n, K, W = args.boards, args.steps, args.warmup
-    env = ppad_b200.BatchedPAD(n, ROWS, COLS, seed=SEED, device=dev, env0=pdist.shard_env0(rank, n))
+    from ppad_b200.replay import RolloutRing, RolloutStats
+    n = args.rollout_boards
+    K, W = 50, 5
+    env = ppad_b200.BatchedPAD(n, ROWS, COLS, seed=SEED + 4, device=dev, env0=pdist.shard_env0(rank, n))
     env.reset(step=0)
-    rb = ReplayBuffer(env, 4 * n)
-    obs = env.encode_obs('f32')
+    ring = RolloutRing(env, 4, gamma=0.99, log10=True)
+    stats = RolloutStats(env)
     gen = torch.Generator(device=dev)
     gen.manual_seed(99 + rank)
-    q = torch.empty((n, 5), device=dev, dtype=torch.float32)
-    out = None
-    before = torch.empty_like(env.state)
-    stats = None
+    qs = [torch.randn((n, 5), device=dev, dtype=torch.float32, generator=gen) * 1000.0 for _ in range(4)]
+    obs = torch.empty((n, ROWS, COLS, 7), dtype=torch.float32, device=dev)
+    out = env.policy_step(qs[0], method='boltzmann', beta=1e-3, epsilon=0.1, max_moves=50, obs=obs, ring=ring, stats=stats)
+    last = {}
 
     def one(t):
-        nonlocal out, stats
-        q.normal_(0.0, 1000.0, generator=gen)
-        actions = env.select_actions(q, method='boltzmann', beta=1e-3, epsilon=0.1, max_moves=50)
-        before.copy_(env.state)
-        out = env.step(actions, auto_reset=True, obs=obs, out=out)
-        rb.push(before, out.action, out.reward)
+        env.policy_step(qs[t & 3], method='boltzmann', beta=1e-3, epsilon=0.1, max_moves=50, obs=obs, ring=ring,
+                        stats=stats, out=out)
         if (t + 1) % 10 == 0:
-            stats = pdist.gather_stats(pdist.local_stats(out.reward, out.info))
-            pdist.gather_replay_sample(rb.state[:rb.size], rb.action[:rb.size], rb.reward[:rb.size], 32, generator=gen)
+            last["stats"] = pdist.gather_stats(stats.vector())
+            stats.clear()
+            s, a, r, _ = ring.sample(32)
+            last["replay_rows"] = pdist.all_gather_rows(s, a, r)[0].shape[0]
 
     for t in range(W):
         one(t)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for t in range(W, W + K):
+    ms = T.timed(one, W, K)
+    per = ms / K
+    achieved = BYTES_ROLLOUT * n / (per * 1e-3) / 1e9
+    del env, ring, stats, qs, obs
+    torch.cuda.empty_cache()
+    return {"metric": "env_steps_per_sec_policy_rollout", "value": n * world * K / (ms * 1e-3), "unit": "steps/s",
+            "boards_per_gpu": n, "steps": K, "warmup": W, "ms_per_step": per,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "algorithmic_bytes_per_board": BYTES_ROLLOUT, "kernel": "policy_step_kernel<Geom<5,6>>"},
+            "collectives_in_timed_region": "every 10 steps: all_gather of the 40-double stats vector + all_gather of 32 replay "
+                                           "rows (state, action, discounted return) per GPU",
+            "workload": "configs[4]: Boltzmann policy (beta 1e-3, epsilon 0.1) on synthetic Q-values resident in HBM, episode cap "
+                        "50, auto-reset, fp32 obs, replay ring (4 steps deep, gamma 0.99, log10) -- one fused launch per step",
+            "stats_last_window": last.get("stats"), "replay_rows_gathered": last.get("replay_rows")}
+
+
+def leg_config2(ppad_b200, pdist, T, args, rank, world, dev):
+    """BASELINE configs[2]: 2^24 boards per GPU, a finger path of L = 200 moves (the largest cap in the reference,
+    simulation.py:35) applied in one launch and then resolved with Philox skyfall; uniform boards and an adversarial
+    variant (3 colours, skyfall 70 % one colour) for the depth / combo histograms."""
+    import torch
+    n, L = args.config2_boards, 200
+    res = {}
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(7 + rank)
+    for name, sky, colours in (("uniform", None, 6), ("adversarial", [0.7, 0.15, 0.15, 0, 0, 0, 0, 0, 0, 0], 3)):
+        env = ppad_b200.BatchedPAD(n, ROWS, COLS, seed=SEED + 2, device=dev, env0=pdist.shard_env0(rank, n), skyfall=sky,
+                                   cascade_cap=32)
+        boards = torch.randint(0, colours, (n, ROWS, COLS), device=dev, dtype=torch.int64, generator=gen)
+        fingers = torch.stack([torch.randint(0, ROWS, (n,), device=dev, generator=gen),
+                               torch.randint(0, COLS, (n,), device=dev, generator=gen)], 1)
+        env.set_state(boards, fingers)
+        del boards, fingers
+        words = (L + 15) // 16
+        packed = torch.randint(-2 ** 31, 2 ** 31, (n, words), device=dev, dtype=torch.int64, generator=gen).to(torch.int32)
+        paths = (packed, L)
+        snap = env.state.clone()
+        out = env.step(None, eval_moves=True, paths=paths, step=1)
+
+        def one(t):
+            env.state.copy_(snap)
+            env.step(None, eval_moves=True, paths=paths, step=t, out=out)
+        ms_copy = T.timed(lambda t: env.state.copy_(snap), 0, 3) / 3
+        ms = T.timed(one, 2, 3) / 3 - ms_copy
+        st = pdist.gather_stats(pdist.local_stats(out.reward, out.info))
+        res[name] = {"value": n * world / (ms * 1e-3), "unit": "path-resolves/s", "ms_per_launch": ms,
+                     "moves_per_s": n * world * L / (ms * 1e-3), "depth_hist": st["depth_hist"], "combo_hist": st["combo_hist"],
+                     "cascade_cap_hits": int(((out.info.to(torch.int64) >> 24) & 4).ne(0).sum().item())}
+        del env, packed, snap, out
+        torch.cuda.empty_cache()
+    res["workload"] = "configs[2]: %d 5x6 boards/GPU, %d-move finger paths (2 bit/move) + full resolve, Philox skyfall, cascade cap 32" % (n, L)
+    return res
+
+
+def leg_config3(ppad_b200, pdist, T, args, rank, world, dev, peak):
+    """BASELINE configs[3]: 7x6 boards -- the fused obs step at 2^20 boards and smart-data style trajectory generation
+    (permuted solved boards, pass for the final reward, random walk recorded in one launch; smart_data.py:27-91)."""
+    import torch
+    from ppad_b200.data import solved_boards
+    from ppad_b200.data.smart_data import smart_data_batched
+    rows, cols, n = 6, 7, N_LOCAL
+    env = ppad_b200.BatchedPAD(n, rows, cols, seed=SEED + 3, device=dev, env0=pdist.shard_env0(rank, n))
+    env.reset(step=0)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(55 + rank)
+    slabs = [env._slab(torch.randint(0, 6, (n, SLAB_ORBS), device=dev, dtype=torch.uint8, generator=gen), SLAB_FORMAT)[0]
+             for _ in range(8)]
+    out = env.step(None, eval_moves=True, injected=(slabs[0], SLAB_ORBS), slab_format=SLAB_FORMAT, obs='f32', step=1)
+
+    def one(t):
+        env.step(None, eval_moves=True, injected=(slabs[t & 7], SLAB_ORBS), slab_format=SLAB_FORMAT, obs=out.obs, step=t, out=out)
+    for t in range(2, 7):
         one(t)
-    e1.record()
+    ms = T.timed(one, 7, 200) / 200
+    bytes_per = 32 + 32 + 13 + SLAB_BYTES + rows * cols * 7 * 4
+    achieved = bytes_per * n / (ms * 1e-3) / 1e9
+    env.reset(step=0)
+    reset_ms = T.timed(lambda t: env.reset(step=t), 1, 5) / 5
+    del env, slabs, out
+    torch.cuda.empty_cache()
+    # smart data: m trajectories of 100 observations each
+    m, steps = args.config3_trajectories, 100
+    solved = solved_boards.generate_solved_boards(rows, cols, 64, seed=9)
+    rng = np.random.default_rng(1 + rank)
+    picks = rng.integers(0, len(solved), m)
+    maps = np.stack([np.concatenate([rng.permutation(6), [6, 7]]) for _ in range(64)]).astype(np.uint8)[rng.integers(0, 64, m)]
+    smart_data_batched(solved, picks[:1024], maps[:1024], steps=steps, seed=21 + rank, device=dev)      # warm-up
     torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item())
-    if rank == 0:
-        print(json.dumps({
-            "metric": "env_steps_per_sec_policy_rollout", "value": n * world * K / (ms * 1e-3), "unit": "steps/s",
-            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u32 bitboards + f64 reward + f32 obs", "data": "synthetic",
-            "config": {"workload": "configs[4]: Boltzmann-policy rollout, synthetic Q-values, auto-reset, fp32 obs, device "
-                                   "replay ring, NCCL all-gather of stats + 32 replay rows per GPU every 10 steps",
-                       "boards_per_gpu": n, "collectives_per_10_steps": 4}, "stats_last": stats}))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        T.dist.barrier()
+    t0 = time.perf_counter()
+    res = smart_data_batched(solved, picks, maps, steps=steps, seed=22 + rank, device=dev)
+    torch.cuda.synchronize()
+    sec = T.max_over_ranks(time.perf_counter() - t0)
+    del res
+    torch.cuda.empty_cache()
+    return {"obs_step": {"value": n * world / (ms * 1e-3), "unit": "steps/s", "ms_per_step": ms,
+                         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                                      "frac": achieved / peak, "algorithmic_bytes_per_board": bytes_per,
+                                      "kernel": "step_obs_kernel<Geom<6,7>>"}},
+            "reset_ms_per_2p20": reset_ms,
+            "smart_data": {"value": m * world / sec, "unit": "trajectories/s", "steps_per_trajectory": steps,
+                           "trajectories_per_gpu": m, "seconds": sec,
+                           "note": "host to host: solved-board upload, colour permutation, pass, the recorded random walk (one launch), "
+                                   "trajectory tensors left in HBM"},
+            "workload": "configs[3]: 7x6 boards; obs step as configs[1]; smart-data generation as smart_data.py:27-91"}
 
 
 def main():
@@ -228,10 +424,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--boards", type=int, default=N_LOCAL, help="boards per GPU (default 2^20 = configs[1])")
+    ap.add_argument("--rollout-boards", type=int, default=1 << 23, help="boards per GPU of the configs[4] sub-record")
+    ap.add_argument("--config2-boards", type=int, default=1 << 24, help="boards per GPU of the configs[2] sub-record")
+    ap.add_argument("--config3-trajectories", type=int, default=1 << 18)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="configs1", choices=["configs1", "rollout"],
-                    help="configs1 = the headline bench (default); rollout = BASELINE configs[4]: Boltzmann-policy "
-                         "rollout with fp32 obs, auto-reset, device replay ring and NCCL stats / replay-sample all-gathers")
+    ap.add_argument("--no-python-reference", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the rollout / config2 / config3 / episode sub-records")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -254,119 +452,128 @@ def main():
         dist.barrier()
     import ppad_b200
     from ppad_b200 import dist as pdist
-    if args.workload == "rollout":
-        return run_rollout(args, rank, local_rank, world)
     L = ppad_b200._cabi.lib()
     dev = torch.device("cuda", local_rank)
     n = args.boards
     K, W = args.steps, args.warmup
+    T = Timer(torch, dist, dev, world)
+    peak, peak_src = measured_peak()
 
     env = ppad_b200.BatchedPAD(n, ROWS, COLS, seed=SEED, device=dev, env0=pdist.shard_env0(rank, n))
     env.reset(step=0)
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
-    slabs = [torch.randint(0, 6, (n, SLAB_ORBS), device=dev, dtype=torch.uint8, generator=gen) for _ in range(N_SLABS)]
-    slabs = [env._slab(s)[0] for s in slabs]                       # packed nibble slabs, resident in HBM
-    out = env.step(None, eval_moves=True, injected=(slabs[0], SLAB_ORBS), obs='f32', step=1)   # allocates buffers
+    host_orbs = [torch.randint(0, 6, (n, SLAB_ORBS), device=dev, dtype=torch.uint8, generator=gen) for _ in range(N_SLABS)]
+    slabs = [env._slab(s, SLAB_FORMAT)[0] for s in host_orbs]        # packed 3-bit slabs, resident in HBM
+    del host_orbs
+    out = env.step(None, eval_moves=True, injected=(slabs[0], SLAB_ORBS), slab_format=SLAB_FORMAT, obs='f32', step=1)
     obs_buf = out.obs
 
     def one_step(t, with_obs=True):
-        return env.step(None, eval_moves=True, injected=(slabs[t % N_SLABS], SLAB_ORBS),
+        return env.step(None, eval_moves=True, injected=(slabs[t % N_SLABS], SLAB_ORBS), slab_format=SLAB_FORMAT,
                         obs=obs_buf if with_obs else None, step=t, out=out)
-
-    def timed(fn, k0, count, finish=None):
-        """barrier + sync, `count` steps between CUDA events on the launch stream, sync; max over ranks (ms).
-        finish(): joins side streams into the launch stream before the closing event."""
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for t in range(k0, k0 + count):
-            fn(t)
-        if finish is not None:
-            finish()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
 
     for t in range(2, 2 + W):
         one_step(t)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     c0 = L.ppad_launch_count()
     w0 = time.time()
-    ms = timed(one_step, 2 + W, K)
-    w1 = time.time()
+    ms = T.timed(one_step, 2 + W, K)                 # the contract's region: EXACTLY K steps
     launches = L.ppad_launch_count() - c0
+    # steady state: >= 0.6 s of the same step with one event per step (a short K gives the clocks no time to show)
+    k_steady = max(K, int(0.6 / max(ms / K * 1e-3, 1e-6)) + 1)
+    k_steady = min(k_steady, 20000)
+    per = T.per_step(one_step, 2 + W + K, k_steady)
+    w1 = time.time()
     clocks = sampler.stop(w0, w1) if sampler else None
+    steady = {"steps": int(k_steady), "median_ms": float(np.median(per)), "p10_ms": float(np.percentile(per, 10)),
+              "p90_ms": float(np.percentile(per, 90)), "seconds": float(per.sum() * 1e-3),
+              "value_at_median": n * world / (T.max_over_ranks(float(np.median(per))) * 1e-3)}
+    base_t = 2 + W + K + k_steady
 
     # secondary: state-only step (no obs stream), L2 flushed between steps, per-step events
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     so_ms = []
-    for t in range(2 + W + K, 2 + W + K + 10):
+    for t in range(base_t, base_t + 10):
         flush.fill_(t & 0xFF)
-        so_ms.append(timed(lambda tt: one_step(tt, with_obs=False), t, 1))
+        so_ms.append(T.timed(lambda tt: one_step(tt, with_obs=False), t, 1))
     so_ms = float(np.median(so_ms))
+    so_b2b = T.timed(lambda tt: one_step(tt, with_obs=False), base_t + 10, 50) / 50
+    del flush
+    base_t += 100
 
-    # secondary: episode mode of visualize_episode.py:28-33 / simulation.py:199 -- L = 50 random moves (swap only),
-    # then a pass (full cascade) and an automatic reset, all boards in lock step: 51 launches per episode
-    ep_env = ppad_b200.BatchedPAD(n, ROWS, COLS, seed=SEED + 1, device=dev, env0=pdist.shard_env0(rank, n))
-    ep_env.reset(step=0)
-    ep_out = ep_env.step(None, max_moves=50, auto_reset=True)
-    for t in range(51):
-        ep_env.step(None, max_moves=50, auto_reset=True, out=ep_out)
-    ep_ms = timed(lambda t: ep_env.step(None, max_moves=50, auto_reset=True, out=ep_out), 0, 102)
-    # the same 51 steps fused into one launch (ppad_rollout: boards stay in registers between steps)
-    ep_env.rollout(51, max_moves=50)
-    ep_fused_ms = timed(lambda t: ep_env.rollout(51, max_moves=50), 0, 4)
-    del ep_env
-
-    # end to end through the public host-buffer API (BatchedPAD.host_pipe -> ppad_pipe_step): every step copies that
-    # step's skyfall slab from pinned host memory and reads reward, info, action and the packed state back to pinned
-    # host memory; the call returns only when the results are on the host.  The fp32 one-hot obs stays in HBM.
-    pipe = env.host_pipe(slab_orbs=SLAB_ORBS, chunks=2)     # best of 1..8 on this box (profiles/pipe_probe.py)
+    # end to end through the public host-buffer API (BatchedPAD.host_pipe -> ppad_pipe_step): every step the skyfall slab
+    # of that step is read from pinned host memory (12 B per board) and the compact result stream (4 bits per board: action
+    # + has-record; 12 B per board whose info word is not 0: reward + info) is written to pinned host memory; the call
+    # returns only when the results are on the host.  The fp32 one-hot obs stays in HBM for the device-side agent.
+    pipe = env.host_pipe(slab_orbs=SLAB_ORBS, compact=True, slab_format=SLAB_FORMAT)
     pipe.slab.copy_(slabs[0].cpu())
     torch.cuda.synchronize()
 
     def e2e_step(t):
         pipe.step(eval_moves=True, obs=obs_buf, step=t, wait=True)
 
-    base = 2 + W + K + 10 + 100000          # step indices of the e2e legs: clear of everything before
-    # warm-up by time, not by count: the first ~50-100 ms of host traffic run at 0.9-1.1 ms per step on every box and
-    # mode (PCIe link / host uncore leaving their idle states; profiles/e2e_modes.py), then it settles at ~0.72 ms
+    # warm-up by time, not by count: the first ~50-100 ms of host traffic run slower on every box and mode (PCIe link /
+    # host uncore leaving their idle states; profiles/e2e_modes.py)
     t_warm, w = time.time(), 0
     while w < 20 or time.time() - t_warm < 0.3:
-        e2e_step(base + w)
+        e2e_step(base_t + w)
         w += 1
-    e2e_k = max(5, min(K, 50))
-    e2e_ms = timed(e2e_step, base + w, e2e_k)
-    h2d = pipe.slab.numel() * 4
-    d2h = pipe.reward.numel() * 8 + pipe.info.numel() * 4 + pipe.action.numel() + pipe.state.numel() * 4
+    e2e_k = max(5, min(K, 200))
+    e2e_ms = T.timed(e2e_step, base_t + w, e2e_k)
+    h2d = pipe.h2d_bytes()
+    d2h = pipe.d2h_bytes()
+    got = pipe.results()                                  # decode once: the stream is complete and self-consistent
+    assert got["lines"] > 0 and (got["info"] != 0).sum() > 0
     # the same with two steps in flight (two sets of host buffers on one pipe; the results of step t are read while
     # step t + 1 is running) -- reported separately, the headline e2e above is the synchronous call
-    pipe2 = env.host_pipe(slab_orbs=SLAB_ORBS, chunks=2, depth=2)
+    pipe2 = env.host_pipe(slab_orbs=SLAB_ORBS, compact=True, slab_format=SLAB_FORMAT, depth=2)
     for k, b in enumerate(pipe2.buffers):
         b.slab.copy_(slabs[k].cpu())
 
     def e2e_async_step(t):
         k = t & 1
         pipe2.wait(k)                              # results of step t - 2 (this buffer set) are on the host
-        _ = pipe2.buffers[k].reward[0].item()      # "read" them
+        _ = int(pipe2.buffers[k].summary[0])       # "read" them
         pipe2.step(eval_moves=True, obs=obs_buf, step=t, wait=False, buf=k)
 
-    for t in range(base + 50000, base + 50010):
+    for t in range(base_t + 50000, base_t + 50010):
         e2e_async_step(t)
-    e2e_async_ms = timed(e2e_async_step, base + 50010, e2e_k, finish=lambda: (pipe2.join(0), pipe2.join(1)))
+    e2e_async_ms = T.timed(e2e_async_step, base_t + 50010, e2e_k, finish=lambda: (pipe2.join(0), pipe2.join(1)))
     pipe2.wait(0), pipe2.wait(1)
+    # for comparison: round 1's dense result arrays + state copy + nibble slab (47 B per board-step across PCIe)
+    pipe_d = env.host_pipe(slab_orbs=SLAB_ORBS, chunks=2)
+    pipe_d.slab.copy_(torch.from_numpy(ppad_b200.layout.pack_slab(
+        np.random.default_rng(5 + rank).integers(0, 6, size=(n, SLAB_ORBS)).astype(np.uint8)).view(np.int32)))
+    for j in range(30):
+        pipe_d.step(eval_moves=True, obs=obs_buf, step=base_t + 60000 + j, wait=True)
+    dense_ms = T.timed(lambda t: pipe_d.step(eval_moves=True, obs=obs_buf, step=t, wait=True), base_t + 60100, min(e2e_k, 50)) / min(e2e_k, 50)
+    dense_bytes = pipe_d.h2d_bytes() + pipe_d.d2h_bytes()
+    del pipe, pipe2, pipe_d
 
-    # episode stats of the last step, all-gathered over NVLink (tiny; outside the timed region)
     stats = pdist.gather_stats(pdist.local_stats(out.reward, out.info))
 
+    extras = {}
+    if not args.no_extras:
+        # episode mode of visualize_episode.py:28-33 / simulation.py:199 -- L = 50 random moves (swap only), then a pass
+        # (full cascade) and an automatic reset, all boards in lock step: 51 launches per episode
+        ep_env = ppad_b200.BatchedPAD(n, ROWS, COLS, seed=SEED + 1, device=dev, env0=pdist.shard_env0(rank, n))
+        ep_env.reset(step=0)
+        ep_out = ep_env.step(None, max_moves=50, auto_reset=True)
+        for t in range(51):
+            ep_env.step(None, max_moves=50, auto_reset=True, out=ep_out)
+        ep_ms = T.timed(lambda t: ep_env.step(None, max_moves=50, auto_reset=True, out=ep_out), 0, 102)
+        ep_env.rollout(51, max_moves=50)
+        ep_fused_ms = T.timed(lambda t: ep_env.rollout(51, max_moves=50), 0, 4)
+        del ep_env, ep_out
+        extras["episode_mode"] = (ep_ms, ep_fused_ms)
+        del env, slabs, out, obs_buf
+        torch.cuda.empty_cache()
+        extras["rollout"] = leg_rollout(ppad_b200, pdist, T, args, rank, world, dev, peak)
+        extras["config2"] = leg_config2(ppad_b200, pdist, T, args, rank, world, dev)
+        extras["config3"] = leg_config3(ppad_b200, pdist, T, args, rank, world, dev, peak)
+
     if rank == 0:
-        peak, peak_src = measured_peak()
         total = n * world
         ms_per_step = ms / K
         achieved = BYTES_WITH_OBS * n / (ms_per_step * 1e-3) / 1e9          # GB/s per GPU (max-over-ranks time)
@@ -394,30 +601,47 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "u32 bitboards + f64 reward + f32 obs", "data": "synthetic",
             "config": workload_config(n, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "step_obs_kernel<Geom<5,6>>",
+                         "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu --set full capture of this kernel and workload: "
+                                                               "dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+                         "peak_source": peak_src, "kernel": "step_obs_kernel<Geom<5,6>>",
                          "algorithmic_bytes_per_board": BYTES_WITH_OBS},
+            "steady": steady,
             "state_only": {"value": total / (so_ms * 1e-3), "unit": "steps/s", "ms_per_step": so_ms,
+                           "back_to_back": {"value": total / (so_b2b * 1e-3), "ms_per_step": so_b2b,
+                                            "issue": issue(prof.get("step_pool_warp_instructions_per_launch"), so_b2b)},
                            "hbm_gbs": BYTES_STATE_ONLY * n / (so_ms * 1e-3) / 1e9,
                            "issue": issue(prof.get("step_pool_warp_instructions_per_launch"), so_ms),
                            "note": "same step without the obs stream (step_pool_kernel); L2 flushed (256 MiB fill) before every step"},
             "e2e": {"value": total * e2e_k / (e2e_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_k,
-                    "note": "HostPipe.step (ppad_pipe_step, zero copy: the kernel reads / writes the pinned host buffers), synchronous: "
-                            "skyfall slab H2D; reward, info, action and packed state (the reference's (board, finger) "
-                            "observation) D2H every step; the fp32 one-hot obs stays in HBM for the device-side agent",
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_k, "steps": e2e_k,
+                    "bytes_per_board_step": (h2d + d2h) / n,
+                    "note": "HostPipe.step (ppad_pipe_step), synchronous, zero copy: the kernel reads the 12-byte skyfall row "
+                            "of every board from pinned host memory and writes the compact result stream to pinned host "
+                            "memory: 4 bits per board (action + has-record) and (float64 reward, uint32 info) only for the "
+                            "boards whose info word is not 0 (the others have reward 0 and info 0 by definition); the host "
+                            "follows the boards from the actions, fresh boards after a reset travel with the records "
+                            "(tests/test_gpu_dropin.py::test_host_pipe_compact_results_equal_device_step); the fp32 one-hot "
+                            "obs stays in HBM for the device-side agent",
                     "two_steps_in_flight": {"value": total * e2e_k / (e2e_async_ms * 1e-3), "unit": "steps/s",
-                                            "ms_per_step": e2e_async_ms / e2e_k}},
-            "episode_mode": {"env_step_calls_per_s": total * 102 / (ep_ms * 1e-3), "episodes_per_s": total * 2 / (ep_ms * 1e-3),
-                             "fused_env_step_calls_per_s": total * 51 * 4 / (ep_fused_ms * 1e-3),
-                             "fused_episodes_per_s": total * 4 / (ep_fused_ms * 1e-3),
-                             "fused_issue": issue(prof.get("rollout_warp_instructions_per_51_step_launch"), ep_fused_ms / 4),
-                             "note": "50 random moves + pass (full cascade, Philox skyfall) + auto reset per episode, "
-                                     "state-only kernels, one launch per step; fused_* = the 51 steps in one ppad_rollout launch; "
-                                     "the reference does ~3.8e3 env.step calls/s per core in this mode"},
+                                            "ms_per_step": e2e_async_ms / e2e_k},
+                    "round1_dense_format": {"value": total / (dense_ms * 1e-3), "unit": "steps/s", "ms_per_step": dense_ms,
+                                            "bytes_per_board_step": dense_bytes / n}},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "stats_last_step": stats,
         }
+        if "episode_mode" in extras:
+            ep_ms, ep_fused_ms = extras["episode_mode"]
+            line["episode_mode"] = {
+                "env_step_calls_per_s": total * 102 / (ep_ms * 1e-3), "episodes_per_s": total * 2 / (ep_ms * 1e-3),
+                "fused_env_step_calls_per_s": total * 51 * 4 / (ep_fused_ms * 1e-3),
+                "fused_episodes_per_s": total * 4 / (ep_fused_ms * 1e-3),
+                "fused_issue": issue(prof.get("rollout_warp_instructions_per_51_step_launch"), ep_fused_ms / 4),
+                "note": "50 random moves + pass (full cascade, Philox skyfall) + auto reset per episode, "
+                        "state-only kernels, one launch per step; fused_* = the 51 steps in one ppad_rollout launch"}
+        for key in ("rollout", "config2", "config3"):
+            if key in extras:
+                line[key] = extras[key]
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             n_sample = N_LOCAL                                   # the whole workload, 3 steps: ~10-20 s of CPU time
@@ -425,6 +649,10 @@ def main():
             line["cpu_baseline"] = {"value": rate, "unit": "steps/s", "cores": threads, "kind": "port",
                                     "sample": "%d boards x 3 steps of the same workload (move + cascade + fp32 obs), C port "
                                               "of the reference's Python path on %d threads, %.1f s/step" % (n_sample, threads, sec)}
+            if not args.no_python_reference:
+                pr = python_reference_rate(8.0)
+                if pr:
+                    line["cpu_baseline"]["python_reference"] = pr
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

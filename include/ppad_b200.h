@@ -11,7 +11,7 @@
  *   - every pointer is a caller-owned DEVICE pointer unless the name ends in _host;
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls only
  *     enqueue work, they never synchronise (ppad_pipe_wait is the one exception);
- *   - every call makes the context's device current (cudaSetDevice) and leaves it current;
+ *   - every call makes the context's device current for its own duration and restores the caller's on return;
  *   - return value: 0 = PPAD_OK, otherwise a ppad_status; ppad_strerror() names it and
  *     ppad_last_error() holds the detail (thread-local);
  *   - per-board faults never abort a launch: they are reported in the flags byte of `info`;
@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PPAD_ABI_VERSION 2
+#define PPAD_ABI_VERSION 3
 #define PPAD_MAX_TEAM_UNITS 8
 
 typedef enum ppad_status {
@@ -52,7 +52,8 @@ enum { PPAD_UP = 0, PPAD_DOWN = 1, PPAD_LEFT = 2, PPAD_RIGHT = 3, PPAD_PASS = 4,
 
 /* flags byte (info >> 24) */
 enum {
-    PPAD_FLAG_REJECTED = 0x01,          /* move off the board: state unchanged (game.py:353 raises ValueError) */
+    PPAD_FLAG_REJECTED = 0x01,          /* move off the board: state unchanged (game.py:353 raises ValueError); from
+                                           ppad_pack / ppad_reset: a given finger was off the board and was clamped */
     PPAD_FLAG_SKYFALL_EXHAUSTED = 0x02, /* injected orbs ran out, the Philox stream took over */
     PPAD_FLAG_CASCADE_CAP = 0x04,       /* cascade stopped at cfg.cascade_cap iterations */
     PPAD_FLAG_NO_LEGAL_MOVE = 0x08,     /* random policy found an empty legal set */
@@ -70,6 +71,15 @@ enum {
 
 typedef enum ppad_dtype { PPAD_I8 = 1, PPAD_I32 = 4, PPAD_I64 = 8 } ppad_dtype;
 typedef enum ppad_obs_dtype { PPAD_OBS_F32 = 0, PPAD_OBS_U8 = 1 } ppad_obs_dtype;
+
+/* Layout of an injected skyfall slab (the orb sequence the reference's random_orb, game.py:458-470, is replaced by in
+ * parity runs): n_inj orbs per board in slab_words uint32 per board.
+ *   PPAD_SLAB_NIBBLES  4 bits per orb, 8 per word: orb d in word d >> 3 at bits 4 * (d & 7)            (16 B / 32 orbs)
+ *   PPAD_SLAB_PLANES3  bit-sliced 3-bit codes, 32 orbs per group of three words {p0, p1, p2}: bit (d & 31) of word
+ *                      3 * (d >> 5) + j is bit j of orb d; slab_words is a multiple of 3                  (12 B / 32 orbs);
+ *                      contexts with orb_bits = 3 only (orb types 0..6).
+ * A code that is no orb type of the context (>= 7, or >= 10 with orb_bits = 4) is flagged PPAD_FLAG_UNSUPPORTED_ORB. */
+typedef enum ppad_slab_format { PPAD_SLAB_NIBBLES = 0, PPAD_SLAB_PLANES3 = 1 } ppad_slab_format;
 
 /* Environment constants: the keyword arguments of PAD.__init__ (game.py:39-50) that reach the hot path. */
 typedef struct ppad_config {
@@ -158,6 +168,10 @@ typedef struct ppad_step_args {
     const uint32_t *paths;
     const uint16_t *path_lens;
     int32_t path_words, path_len;
+    int32_t slab_format;          /* ppad_slab_format of `slab` */
+    int32_t reserved;
+    uint16_t *consumed_out;       /* [n] skyfall orbs the cascade drew, saturating at 65535 (the info byte stops at
+                                     255), or NULL */
 } ppad_step_args;
 int ppad_step(const ppad_ctx *ctx, const ppad_step_args *args, void *stream);
 
@@ -205,7 +219,32 @@ typedef struct ppad_host_step_args {
     void *state_out_host;            /* [n] packed records or NULL */
     void *obs;                       /* DEVICE [n, rows, cols, 7] or NULL */
     int32_t obs_dtype;
+    int32_t slab_format;             /* ppad_slab_format of slab_host */
+    /* Compact result stream (results_compact != 0; pinned host buffers, zero-copy mode): what a host caller of
+     * PAD.step gets back (game.py:329-362: the action it took, the reward of an evaluation, a fresh board after a
+     * reset) without shipping zeros.  About half the boards of a random-policy step match nothing (reward 0, info 0):
+     * they cost 4 bits.  Per tile of 256 consecutive boards (tile t = boards 256 t ..):
+     *   nibbles_host   [tiles, 32] uint32: nibble i of tile t (word i >> 3, bits 4 * (i & 7)) =
+     *                  action taken (0..4, 7 = none) | has_record << 3 for board 256 t + i
+     *   tile_line_host [tiles] uint32: index of the first 128-byte line of the tile's record block in records_host
+     *                  (blocks are claimed with an atomic counter: their order is not the tile order)
+     *   records_host   the record blocks.  A tile with k boards whose info word is not 0, m of them with
+     *                  PPAD_FLAG_EPISODE_DONE, holds, in board order:
+     *                    k x float64 reward | k x uint32 info | pad to 16 B | m x packed state record (the fresh
+     *                    episode's board) | pad to 128 B
+     *                  records_capacity bytes; the worst case is ppad_compact_capacity(ctx, n) bytes
+     *   summary_host   [4] uint32: 128-byte lines used, tiles, overflow (a block did not fit: its tile_line is
+     *                  0xFFFFFFFF), 0 -- valid once ppad_pipe_wait returns
+     * reward_host / info_host / action_out_host are ignored in this mode; state_out_host still works. */
+    int32_t results_compact;
+    uint32_t *nibbles_host;
+    uint32_t *tile_line_host;
+    void *records_host;
+    int64_t records_capacity;
+    uint32_t *summary_host;
 } ppad_host_step_args;
+/* bytes of records_host that can never overflow for n boards (with or without auto_reset) */
+int64_t ppad_compact_capacity(const ppad_ctx *ctx, int64_t n);
 int ppad_pipe_create(const ppad_ctx *ctx, int64_t n_max, int32_t slab_words_max, int32_t chunks, ppad_pipe **out);
 void ppad_pipe_destroy(ppad_pipe *pipe);
 /* `after_stream`: work already queued there (e.g. ppad_reset) is ordered before the chunks */
@@ -251,12 +290,13 @@ int ppad_damage(const ppad_ctx *ctx, int64_t n, const uint16_t *combo_log, int32
 
 /* ---- the callers either side of the env step ---------------------------- */
 
+typedef enum ppad_select_method { PPAD_SELECT_MAX = 0, PPAD_SELECT_BOLTZMANN = 1 } ppad_select_method;
+
 /* permutation_mapping (smart_data.py:94-108) in place: maps [n, 8] uint8, orb type t -> maps[i][t] (t = 0..6;
  * empty cells stay empty; byte 7 is padding; with orb_bits = 4 the types 7..9 keep their value -- the reference
  * only ever permutes allowed_orbs = 0..5, solved_boards.py:25) */
 int ppad_permute(const ppad_ctx *ctx, int64_t n, void *state, const uint8_t *maps, void *stream);
 
-typedef enum ppad_select_method { PPAD_SELECT_MAX = 0, PPAD_SELECT_BOLTZMANN = 1 } ppad_select_method;
 
 /* Agent01.act after the network (agent01.py:173-218): q [n, 5] float32 -> actions [n].
  * Off-board moves and the reverse of the previous action get -inf (agent01.py:173-190); epsilon-greedy
@@ -266,6 +306,52 @@ typedef enum ppad_select_method { PPAD_SELECT_MAX = 0, PPAD_SELECT_BOLTZMANN = 1
 int ppad_select_actions(const ppad_ctx *ctx, int64_t n, uint64_t env0, uint32_t step, const void *state, const float *q,
                         int32_t method, float beta, float epsilon, int32_t max_moves, uint8_t *actions, void *stream);
 
+/* The policy-driven env step of a device-resident rollout as ONE kernel (the loop body of model_simulation,
+ * projects/simulation.py:34-68, for n boards; BASELINE configs[4]):
+ *   action  = max_moves > 0 && moves >= max_moves ? PASS (simulation.py:50-52)
+ *             : Agent01.act after the network (agent01.py:173-218) on q[i], as ppad_select_actions
+ *   ring    : row (ring_step % ring_steps) * n + i of the time-major replay ring gets the state BEFORE the step and
+ *             the action (the (observation, action) pairs of simulation.py:60-61); ring_state == NULL: no replay
+ *   step    : as ppad_step(actions = action, eval_moves, auto_reset, max_moves) with Philox (or injected) skyfall
+ *   reward  : the ring row gets the step's reward (log10 of it when log10_reward and it is positive); when the
+ *             board passed with a positive reward and gamma > 0, the rows of the episode's earlier steps still in
+ *             the ring get the discounted returns cur = cur * gamma + 0 of ppad.discount (agent/utils.py:22-51)
+ *   obs     : one-hot observation of the state written back (agent01.py:254-273), or NULL
+ *   stats   : stats_rows [ppad_policy_stats_rows(n), 40] uint64 per-CTA accumulators, ADDED to by every call (zero
+ *             them to start a window): board-steps, evaluated boards with a match, sum of rewards * 1024 (fixed
+ *             point: exact and order independent), maximum reward (float64 bits), combos, skyfall orbs consumed,
+ *             episodes finished, faults, cascade-depth histogram [16] and combo-count histogram [16] over the
+ *             evaluated boards (the report block of simulation.py:336-349).  ppad_policy_stats sums the rows into
+ *             out [40] (the vector a rank contributes to the NCCL all-gather). */
+typedef struct ppad_policy_args {
+    int64_t n;
+    uint64_t env0;
+    uint32_t step;
+    int32_t eval_moves, auto_reset, max_moves;
+    void *state;                  /* in/out */
+    const float *q;               /* [n, 5] float32 */
+    int32_t method;               /* ppad_select_method */
+    float beta, epsilon;
+    const uint32_t *slab;         /* injected skyfall [n, slab_words] or NULL */
+    int32_t slab_words, n_inj, slab_format;
+    int32_t obs_dtype;
+    uint8_t *action_out;          /* [n] or NULL */
+    double *reward;               /* [n] or NULL */
+    uint32_t *info;               /* [n] or NULL */
+    void *obs;                    /* [n, rows, cols, 7] or NULL */
+    void *ring_state;             /* [ring_steps * n] packed records or NULL */
+    uint8_t *ring_action;         /* [ring_steps * n] */
+    double *ring_reward;          /* [ring_steps * n] */
+    int64_t ring_steps, ring_step;   /* ring_step = rows pushed so far / n (0 for the first step) */
+    double gamma;                 /* 0 = store plain rewards */
+    int32_t log10_reward;
+    int32_t ctas_per_sm;          /* 0 = default; register allocation target of the kernel (3 or 4), for tuning */
+    uint64_t *stats_rows;         /* or NULL */
+} ppad_policy_args;
+int ppad_policy_step(const ppad_ctx *ctx, const ppad_policy_args *args, void *stream);
+int64_t ppad_policy_stats_rows(int64_t n);
+int ppad_policy_stats(const ppad_ctx *ctx, int64_t n, const uint64_t *stats_rows, uint64_t *out, void *stream);
+
 /* ppad.discount (agent/utils.py:22-51) in place over n trajectories rewards [n, max_len] float64 with
  * lengths [n] int32 (NULL = max_len): optional log10 of positive rewards, reverse scan
  * cur = cur * gamma + r, optional normalisation. */
@@ -274,8 +360,11 @@ int ppad_discount(const ppad_ctx *ctx, int64_t n, int32_t max_len, double *rewar
 
 /* Experience replay ring (simulation.py:294-306) of (packed state, action, reward) rows.
  * push: row i (if keep == NULL or keep[i]) goes to ring slot (cursor + (slot ? slot[i] : i)) % capacity.
+ * `count` = number of rows this push keeps (n when keep == NULL).  When count > capacity only the LAST `capacity`
+ * kept rows are written (rows with slot index < count - capacity are skipped), so no two rows of one push share a
+ * ring slot -- the reference truncates to MAX_DATA_SIZE and never mixes tuples (simulation.py:296-299).
  * sample: k uniform rows of the first `size` ring rows (Philox, keyed by step); index (may be NULL) gets the rows. */
-int ppad_replay_push(const ppad_ctx *ctx, int64_t n, int64_t capacity, int64_t cursor, const void *state,
+int ppad_replay_push(const ppad_ctx *ctx, int64_t n, int64_t capacity, int64_t cursor, int64_t count, const void *state,
                      const uint8_t *action, const double *reward, const uint8_t *keep, const int64_t *slot,
                      void *r_state, uint8_t *r_action, double *r_reward, void *stream);
 int ppad_replay_sample(const ppad_ctx *ctx, int64_t k, int64_t size, uint32_t step, const void *r_state,

@@ -14,6 +14,8 @@ FLAG_BAD_ACTION, FLAG_RESET_CAP, FLAG_UNSUPPORTED_ORB, FLAG_EPISODE_DONE = 0x10,
 I8, I32, I64 = 1, 4, 8
 OBS_F32, OBS_U8 = 0, 1
 SELECT_MAX, SELECT_BOLTZMANN = 0, 1
+SLAB_NIBBLES, SLAB_PLANES3 = 0, 1
+ABI_VERSION = 3
 
 
 class Config(C.Structure):
@@ -34,7 +36,8 @@ class StepArgs(C.Structure):
                 ("final_state", C.c_void_p), ("state_copy", C.c_void_p), ("combo_log", C.c_void_p),
                 ("log_cap", C.c_int32),
                 ("obs", C.c_void_p), ("obs_dtype", C.c_int32), ("skyfall_damage", C.c_int32),
-                ("paths", C.c_void_p), ("path_lens", C.c_void_p), ("path_words", C.c_int32), ("path_len", C.c_int32)]
+                ("paths", C.c_void_p), ("path_lens", C.c_void_p), ("path_words", C.c_int32), ("path_len", C.c_int32),
+                ("slab_format", C.c_int32), ("reserved", C.c_int32), ("consumed_out", C.c_void_p)]
 
 
 class HostStepArgs(C.Structure):
@@ -44,7 +47,21 @@ class HostStepArgs(C.Structure):
                 ("state", C.c_void_p), ("actions_host", C.c_void_p), ("slab_host", C.c_void_p),
                 ("slab_words", C.c_int32), ("n_inj", C.c_int32), ("action_out_host", C.c_void_p),
                 ("reward_host", C.c_void_p), ("info_host", C.c_void_p), ("state_out_host", C.c_void_p),
-                ("obs", C.c_void_p), ("obs_dtype", C.c_int32)]
+                ("obs", C.c_void_p), ("obs_dtype", C.c_int32), ("slab_format", C.c_int32),
+                ("results_compact", C.c_int32), ("nibbles_host", C.c_void_p), ("tile_line_host", C.c_void_p),
+                ("records_host", C.c_void_p), ("records_capacity", C.c_int64), ("summary_host", C.c_void_p)]
+
+
+class PolicyArgs(C.Structure):
+    """struct ppad_policy_args"""
+    _fields_ = [("n", C.c_int64), ("env0", C.c_uint64), ("step", C.c_uint32), ("eval_moves", C.c_int32),
+                ("auto_reset", C.c_int32), ("max_moves", C.c_int32), ("state", C.c_void_p), ("q", C.c_void_p),
+                ("method", C.c_int32), ("beta", C.c_float), ("epsilon", C.c_float), ("slab", C.c_void_p),
+                ("slab_words", C.c_int32), ("n_inj", C.c_int32), ("slab_format", C.c_int32), ("obs_dtype", C.c_int32),
+                ("action_out", C.c_void_p), ("reward", C.c_void_p), ("info", C.c_void_p), ("obs", C.c_void_p),
+                ("ring_state", C.c_void_p), ("ring_action", C.c_void_p), ("ring_reward", C.c_void_p),
+                ("ring_steps", C.c_int64), ("ring_step", C.c_int64), ("gamma", C.c_double),
+                ("log10_reward", C.c_int32), ("ctas_per_sm", C.c_int32), ("stats_rows", C.c_void_p)]
 
 
 # every symbol include/ppad_b200.h declares (tests/test_cabi_symbols.py checks the header against this)
@@ -53,7 +70,8 @@ SYMBOLS = ["ppad_default_config", "ppad_create", "ppad_destroy", "ppad_abi_versi
            "ppad_step", "ppad_encode_obs", "ppad_cancel", "ppad_legal_mask", "ppad_sample_actions", "ppad_drop",
            "ppad_fill", "ppad_damage", "ppad_select_actions", "ppad_discount", "ppad_replay_push",
            "ppad_replay_sample", "ppad_permute", "ppad_pipe_create", "ppad_pipe_destroy", "ppad_pipe_step",
-           "ppad_pipe_wait", "ppad_pipe_join", "ppad_rollout", "ppad_pipe_set_zero_copy", "ppad_rollout_record"]
+           "ppad_pipe_wait", "ppad_pipe_join", "ppad_rollout", "ppad_pipe_set_zero_copy", "ppad_rollout_record",
+           "ppad_compact_capacity", "ppad_policy_step", "ppad_policy_stats", "ppad_policy_stats_rows"]
 
 
 class PPADError(RuntimeError):
@@ -112,11 +130,17 @@ def lib():
     L.ppad_pipe_join.argtypes = [vp, vp, i32]
     L.ppad_select_actions.argtypes = [vp, i64, u64, u32, vp, vp, i32, C.c_float, C.c_float, i32, vp, vp]
     L.ppad_discount.argtypes = [vp, i64, i32, vp, vp, C.c_double, i32, i32, vp]
-    L.ppad_replay_push.argtypes = [vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.ppad_replay_push.argtypes = [vp, i64, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.ppad_policy_step.argtypes = [vp, C.POINTER(PolicyArgs), vp]
+    L.ppad_policy_stats.argtypes = [vp, i64, vp, vp, vp]
+    L.ppad_policy_stats_rows.argtypes = [i64]
+    L.ppad_policy_stats_rows.restype = i64
+    L.ppad_compact_capacity.argtypes = [vp, i64]
+    L.ppad_compact_capacity.restype = i64
     L.ppad_replay_sample.argtypes = [vp, i64, i64, u32, vp, vp, vp, vp, vp, vp, vp, vp]
     for name in SYMBOLS:
         getattr(L, name)
-    if L.ppad_abi_version() != 2:
+    if L.ppad_abi_version() != ABI_VERSION:
         raise ImportError("libppad_b200.so ABI version mismatch")
     _lib = L
     return L

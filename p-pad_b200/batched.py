@@ -13,7 +13,7 @@ import torch
 
 from . import _cabi
 from .config import make_config
-from .layout import state_words
+from .layout import state_words, decode_compact, TILE
 
 ACTION_NAMES = ['up', 'down', 'left', 'right', 'pass']        # player.py:24
 ACTION_IDS = {name: i for i, name in enumerate(ACTION_NAMES)}  # simulation.py:236
@@ -84,16 +84,26 @@ class BatchedPAD:
             return x.to(device=self.device, dtype=dtype).contiguous()
         return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype).to(self.device)
 
-    def _slab(self, injected):
-        """injected: None, or a uint8 [n, S] orb sequence (tensor/array), or (slab_int32 [n, W], n_inj)."""
+    def _slab(self, injected, fmt='nibbles'):
+        """injected: None, or a uint8 [n, S] orb sequence (tensor/array), or (slab_int32 [n, W], n_inj) already packed.
+        fmt: 'nibbles' (PPAD_SLAB_NIBBLES, 16 B per 32 orbs) or 'planes3' (PPAD_SLAB_PLANES3, 12 B per 32 orbs)."""
         if injected is None:
             return None, 0, 0
         if isinstance(injected, tuple):
-            slab, n_inj = injected
+            slab, n_inj = injected[0], injected[1]
             slab = self._dev(slab, torch.int32)
             return slab, slab.shape[1], int(n_inj)
         orbs = self._dev(injected, torch.uint8)
         n, s = orbs.shape
+        if fmt == 'planes3':
+            groups = max(1, (s + 31) // 32)
+            pad = torch.zeros((n, groups * 32), dtype=torch.int64, device=self.device)
+            pad[:, :s] = orbs & 7
+            pad = pad.view(n, groups, 32)
+            shifts = torch.arange(32, device=self.device, dtype=torch.int64)
+            planes = torch.stack([(((pad >> j) & 1) << shifts).sum(dim=2) for j in range(3)], dim=2)   # [n, groups, 3]
+            slab = torch.where(planes >= 2 ** 31, planes - 2 ** 32, planes).to(torch.int32).reshape(n, groups * 3)
+            return slab.contiguous(), groups * 3, s
         words = (s + 7) // 8
         pad = torch.zeros((n, words * 8), dtype=torch.int64, device=self.device)
         pad[:, :s] = orbs & 15
@@ -168,10 +178,12 @@ class BatchedPAD:
         return int(step) & 0xFFFFFFFF
 
     def step(self, actions=None, eval_moves=False, auto_reset=False, max_moves=0, injected=None, obs=None,
-             want_final=False, log_cap=0, step=None, out=None, skyfall_damage=None, paths=None, path_lens=None):
+             want_final=False, log_cap=0, step=None, out=None, skyfall_damage=None, paths=None, path_lens=None,
+             slab_format='nibbles', want_consumed=False):
         """One env step of all boards (ppad_step).  actions: None (random legal moves / forced pass at
         max_moves), or uint8 [n] ids 0..4 (255 = sample).  obs: None, 'f32' or 'u8', or a preallocated tensor.
-        Returns SimpleNamespace(action, reward, info, obs, final_state, combo_log); ``out`` reuses buffers."""
+        injected: see _slab (``slab_format`` names the layout of an already packed slab / the layout to pack into).
+        Returns SimpleNamespace(action, reward, info, obs, final_state, combo_log, consumed); ``out`` reuses buffers."""
         step = self._next_step(step)
         n = self.n
         out = out if out is not None else SimpleNamespace()
@@ -192,9 +204,12 @@ class BatchedPAD:
             out.obs = None
         out.final_state = torch.empty_like(self.state) if want_final else None
         out.combo_log = torch.zeros((n, log_cap), dtype=torch.int16, device=self.device) if log_cap else None
+        out.consumed = torch.empty(n, dtype=torch.int16, device=self.device) if want_consumed else None
         acts = self._dev(actions, torch.uint8)
-        slab, words, n_inj = self._slab(injected)
+        slab, words, n_inj = self._slab(injected, slab_format)
         a = _cabi.StepArgs()
+        a.slab_format = {'nibbles': _cabi.SLAB_NIBBLES, 'planes3': _cabi.SLAB_PLANES3}[slab_format]
+        a.consumed_out = out.consumed.data_ptr() if want_consumed else None
         a.n, a.env0, a.step = n, self.env0, step
         a.eval_moves, a.auto_reset, a.max_moves = int(bool(eval_moves)), int(bool(auto_reset)), int(max_moves)
         a.state = self.state.data_ptr()
@@ -356,6 +371,63 @@ class BatchedPAD:
                 int(max_moves), _ptr(actions), self._stream()))
         return actions
 
+    def policy_step(self, q, method='boltzmann', beta=None, epsilon=0.0, max_moves=0, eval_moves=False, auto_reset=True,
+                    injected=None, slab_format='nibbles', obs=None, ring=None, stats=None, step=None, out=None,
+                    ctas_per_sm=0):
+        """The loop body of model_simulation (simulation.py:34-68) for every board in ONE kernel (ppad_policy_step):
+        action selection from q float32 [n, 5] (agent01.py:173-218) with the episode length cap, the env step with
+        auto-reset, the one-hot observation of the new state, the push of (state before the step, action, reward /
+        discounted return) into ``ring`` (a replay.RolloutRing) and the episode statistics into ``stats`` (a
+        replay.RolloutStats).  Returns SimpleNamespace(action, reward, info, obs); ``out`` reuses the buffers."""
+        method = str(method).lower()
+        if method not in ('max', 'boltzmann'):
+            raise Exception('ERROR: Unknown action method!')
+        if method == 'boltzmann' and beta is None:
+            raise Exception('ERROR: Provide a value for beta!')
+        step = self._next_step(step)
+        n = self.n
+        out = out if out is not None else SimpleNamespace()
+        if getattr(out, "reward", None) is None:
+            out.action = torch.empty(n, dtype=torch.uint8, device=self.device)
+            out.reward = torch.empty(n, dtype=torch.float64, device=self.device)
+            out.info = torch.empty(n, dtype=torch.int32, device=self.device)
+        obs_dtype = _cabi.OBS_F32
+        if isinstance(obs, torch.Tensor):
+            out.obs = obs
+            obs_dtype = _cabi.OBS_F32 if obs.dtype == torch.float32 else _cabi.OBS_U8
+        elif obs is not None:
+            obs_dtype = {'f32': _cabi.OBS_F32, 'u8': _cabi.OBS_U8}[obs]
+            want = torch.float32 if obs == 'f32' else torch.uint8
+            if getattr(out, "obs", None) is None or out.obs.dtype != want:
+                out.obs = torch.empty((n, self.dim_row, self.dim_col, 7), dtype=want, device=self.device)
+        else:
+            out.obs = None
+        q = self._dev(q, torch.float32).reshape(n, 5)
+        slab, words, n_inj = self._slab(injected, slab_format)
+        a = _cabi.PolicyArgs()
+        a.n, a.env0, a.step = n, self.env0, step
+        a.eval_moves, a.auto_reset, a.max_moves = int(bool(eval_moves)), int(bool(auto_reset)), int(max_moves)
+        a.state, a.q = self.state.data_ptr(), q.data_ptr()
+        a.method = _cabi.SELECT_MAX if method == 'max' else _cabi.SELECT_BOLTZMANN
+        a.beta, a.epsilon = float(beta or 0.0), float(epsilon)
+        a.slab = slab.data_ptr() if slab is not None else None
+        a.slab_words, a.n_inj = words, n_inj
+        a.slab_format = {'nibbles': _cabi.SLAB_NIBBLES, 'planes3': _cabi.SLAB_PLANES3}[slab_format]
+        a.obs_dtype = obs_dtype
+        a.action_out, a.reward, a.info = out.action.data_ptr(), out.reward.data_ptr(), out.info.data_ptr()
+        a.obs = out.obs.data_ptr() if out.obs is not None else None
+        if ring is not None:
+            a.ring_state, a.ring_action, a.ring_reward = ring.state.data_ptr(), ring.action.data_ptr(), ring.reward.data_ptr()
+            a.ring_steps, a.ring_step = ring.steps, ring.pushed
+            a.gamma, a.log10_reward = float(ring.gamma), int(bool(ring.log10))
+        a.ctas_per_sm = int(ctas_per_sm)
+        a.stats_rows = stats.rows.data_ptr() if stats is not None else None
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ppad_policy_step(self._ctx, C.byref(a), self._stream()))
+        if ring is not None:
+            ring.pushed += 1
+        return out
+
     def discount(self, rewards, gamma, lengths=None, norm=False, log10=True):
         """ppad.discount (agent/utils.py:22-51) for a batch of trajectories: rewards float64 [m, T] (a copy is
         discounted and returned), lengths int32 [m] or None."""
@@ -368,9 +440,9 @@ class BatchedPAD:
                                                int(bool(log10)), int(bool(norm)), self._stream()))
         return r
 
-    def host_pipe(self, slab_orbs=32, chunks=2, zero_copy=True, depth=1):
+    def host_pipe(self, slab_orbs=32, chunks=2, zero_copy=True, depth=1, compact=False, slab_format='nibbles'):
         """A HostPipe for this slab: env steps whose inputs and results are pinned HOST tensors (ppad_pipe_*)."""
-        return HostPipe(self, slab_orbs, chunks, zero_copy, depth)
+        return HostPipe(self, slab_orbs, chunks, zero_copy, depth, compact, slab_format)
 
     @staticmethod
     def split_info(info):
@@ -398,19 +470,28 @@ class HostPipe:
     ``pipe.slab`` etc. are the buffers of set 0.
     """
 
-    def __init__(self, venv, slab_orbs=32, chunks=2, zero_copy=True, depth=1):
+    def __init__(self, venv, slab_orbs=32, chunks=2, zero_copy=True, depth=1, compact=False, slab_format='nibbles'):
         self.venv = venv
         self.slab_orbs = int(slab_orbs)
-        self.slab_words = (self.slab_orbs + 7) // 8
+        self.slab_format = slab_format
+        self.slab_words = 3 * ((self.slab_orbs + 31) // 32) if slab_format == 'planes3' else (self.slab_orbs + 7) // 8
+        self.compact = bool(compact)
         n = venv.n
+        self.tiles = (n + TILE - 1) // TILE
         pin = dict(pin_memory=True)
+        cap = int(venv.lib.ppad_compact_capacity(venv._ctx, n)) if self.compact else 0
         self.buffers = [SimpleNamespace(
             slab=torch.zeros((n, max(1, self.slab_words)), dtype=torch.int32, **pin),
             actions=torch.zeros(n, dtype=torch.uint8, **pin),
             action=torch.zeros(n, dtype=torch.uint8, **pin),
             reward=torch.zeros(n, dtype=torch.float64, **pin),
             info=torch.zeros(n, dtype=torch.int32, **pin),
-            state=torch.zeros((n, venv.words), dtype=torch.int32, **pin)) for _ in range(2 if depth > 1 else 1)]
+            state=torch.zeros((n, venv.words), dtype=torch.int32, **pin),
+            # compact result stream (include/ppad_b200.h: ppad_host_step_args)
+            nibbles=torch.zeros(self.tiles * 32 if self.compact else 1, dtype=torch.int32, **pin),
+            tile_line=torch.zeros(self.tiles if self.compact else 1, dtype=torch.int32, **pin),
+            records=torch.zeros(max(cap, 128), dtype=torch.uint8, **pin),
+            summary=torch.zeros(4, dtype=torch.int32, **pin)) for _ in range(2 if depth > 1 else 1)]
         for name, value in vars(self.buffers[0]).items():
             setattr(self, name, value)
         handle = C.c_void_p()
@@ -426,12 +507,16 @@ class HostPipe:
             self.venv.lib.ppad_pipe_destroy(pipe)
 
     def step(self, use_actions=False, use_slab=True, eval_moves=False, auto_reset=False, max_moves=0, obs=None,
-             want_state=True, skyfall_damage=None, step=None, wait=True, buf=0):
-        """Enqueue one step (inputs are read from buffers[buf].slab / .actions, results land in .reward, .info,
-        .action and, with want_state, .state).  wait=False returns right after enqueueing; call wait(buf) before
-        reading the results or refilling that buffer set."""
+             want_state=None, skyfall_damage=None, step=None, wait=True, buf=0):
+        """Enqueue one step (inputs are read from buffers[buf].slab / .actions).  Dense pipes: the results land in
+        .reward, .info, .action and, with want_state (default), .state.  Compact pipes: they land in .nibbles /
+        .tile_line / .records / .summary -- decode them with results(buf); the state is only copied when want_state is
+        set (the host can follow the board from the actions; fresh boards after a reset come with the records).
+        wait=False returns right after enqueueing; call wait(buf) before reading the results or refilling that set."""
         v = self.venv
         b = self.buffers[buf]
+        if want_state is None:
+            want_state = not self.compact
         a = _cabi.HostStepArgs()
         a.n, a.env0, a.step = v.n, v.env0, v._next_step(step)
         a.eval_moves, a.auto_reset, a.max_moves = int(bool(eval_moves)), int(bool(auto_reset)), int(max_moves)
@@ -440,7 +525,14 @@ class HostPipe:
         a.actions_host = b.actions.data_ptr() if use_actions else None
         a.slab_host = b.slab.data_ptr() if use_slab and self.slab_words else None
         a.slab_words, a.n_inj = self.slab_words, self.slab_orbs
-        a.action_out_host, a.reward_host, a.info_host = b.action.data_ptr(), b.reward.data_ptr(), b.info.data_ptr()
+        a.slab_format = {'nibbles': _cabi.SLAB_NIBBLES, 'planes3': _cabi.SLAB_PLANES3}[self.slab_format]
+        if self.compact:
+            a.results_compact = 1
+            a.nibbles_host, a.tile_line_host = b.nibbles.data_ptr(), b.tile_line.data_ptr()
+            a.records_host, a.records_capacity = b.records.data_ptr(), b.records.numel()
+            a.summary_host = b.summary.data_ptr()
+        else:
+            a.action_out_host, a.reward_host, a.info_host = b.action.data_ptr(), b.reward.data_ptr(), b.info.data_ptr()
         a.state_out_host = b.state.data_ptr() if want_state else None
         if obs is not None:
             a.obs = obs.data_ptr()
@@ -449,6 +541,29 @@ class HostPipe:
             _cabi.check(v.lib.ppad_pipe_step(self._pipe, C.byref(a), v._stream(), int(buf)))
             if wait:
                 _cabi.check(v.lib.ppad_pipe_wait(self._pipe, int(buf)))
+
+    def results(self, buf=0):
+        """Dense view of the last completed step of buffer set `buf`: dict(action uint8 [n], reward float64 [n],
+        info uint32 [n]) as numpy arrays; compact pipes add reset_index / reset_state (the fresh boards of the episodes
+        that ended) and `lines`.  Call after wait(buf)."""
+        b = self.buffers[buf]
+        if not self.compact:
+            return dict(action=b.action.numpy(), reward=b.reward.numpy(), info=b.info.numpy().view(np.uint32))
+        return decode_compact(self.venv.n, self.venv.words, b.nibbles.numpy().view(np.uint32),
+                              b.tile_line.numpy().view(np.uint32), b.records.numpy(), b.summary.numpy().view(np.uint32))
+
+    def d2h_bytes(self, buf=0, want_state=None):
+        """Bytes the last completed step of `buf` wrote to host memory."""
+        b = self.buffers[buf]
+        if want_state is None:
+            want_state = not self.compact
+        state = b.state.numel() * 4 if want_state else 0
+        if not self.compact:
+            return b.reward.numel() * 8 + b.info.numel() * 4 + b.action.numel() + state
+        return b.nibbles.numel() * 4 + b.tile_line.numel() * 4 + 16 + int(b.summary[0]) * 128 + state
+
+    def h2d_bytes(self, use_actions=False):
+        return self.slab.numel() * 4 + (self.actions.numel() if use_actions else 0)
 
     def wait(self, buf=0):
         with torch.cuda.device(self.venv.device):

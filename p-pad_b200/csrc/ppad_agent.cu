@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(BLOCK) discount_kernel(int64_t n, int max_len,
 
 // experience replay ring (simulation.py:294-306): rows are (packed state, action, reward)
 __global__ void __launch_bounds__(BLOCK) replay_push_kernel(int64_t n, int words, int64_t capacity, int64_t cursor,
-                                                            const uint32_t *state, const uint8_t *action,
+                                                            int64_t count, const uint32_t *state, const uint8_t *action,
                                                             const double *reward, const uint8_t *keep,
                                                             const int64_t *slot, uint32_t *r_state, uint8_t *r_action,
                                                             double *r_reward)
@@ -51,7 +51,9 @@ __global__ void __launch_bounds__(BLOCK) replay_push_kernel(int64_t n, int words
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     if (i >= n) return;
     if (keep && !keep[i]) return;
-    const int64_t d = (cursor + (slot ? slot[i] : i)) % capacity;
+    const int64_t si = slot ? slot[i] : i;
+    if (si < count - capacity) return;   // a push larger than the ring keeps its last `capacity` rows: one writer per slot
+    const int64_t d = (cursor + si) % capacity;
     for (int w = 0; w < words; w++) r_state[d * words + w] = state[i * words + w];
     r_action[d] = action[i];
     r_reward[d] = reward[i];
@@ -106,7 +108,7 @@ int ppad_discount(const ppad_ctx *ctx, int64_t n, int32_t max_len, double *rewar
     return after_launch("discount_kernel");
 }
 
-int ppad_replay_push(const ppad_ctx *ctx, int64_t n, int64_t capacity, int64_t cursor, const void *state,
+int ppad_replay_push(const ppad_ctx *ctx, int64_t n, int64_t capacity, int64_t cursor, int64_t count, const void *state,
                      const uint8_t *action, const double *reward, const uint8_t *keep, const int64_t *slot,
                      void *r_state, uint8_t *r_action, double *r_reward, void *stream)
 {
@@ -114,8 +116,10 @@ int ppad_replay_push(const ppad_ctx *ctx, int64_t n, int64_t capacity, int64_t c
     if (n == 0) return PPAD_OK;
     if (!state || !action || !reward || !r_state || !r_action || !r_reward || capacity <= 0 || cursor < 0)
         return fail(PPAD_ERR_INVALID, "ppad_replay_push: bad argument");
+    if (count < 0 || count > n || (!keep && !slot && count != n))
+        return fail(PPAD_ERR_INVALID, "ppad_replay_push: count must be the number of kept rows (n without a keep mask)");
     const int words = (int)(ppad_state_bytes_ex(ctx->cfg.rows, ctx->cfg.cols, ctx->cfg.orb_bits) / 4);
-    replay_push_kernel<<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(n, words, capacity, cursor, (const uint32_t *)state,
+    replay_push_kernel<<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(n, words, capacity, cursor, count, (const uint32_t *)state,
                                                                         action, reward, keep, slot, (uint32_t *)r_state,
                                                                         r_action, r_reward);
     return after_launch("replay_push_kernel");

@@ -46,7 +46,18 @@ __global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ Re
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     const bool valid = i < a.n;                  // every lane takes part: the rejection sampling is warp-cooperative
     int finger = -1;
-    if (valid && a.fingers_in) finger = a.fingers_in[2 * i] * G::C + a.fingers_in[2 * i + 1];
+    uint32_t finger_flag = 0;
+    if (valid && a.fingers_in) {
+        // a finger off the board would spill into the neighbouring meta fields and drive shifts past the plane width:
+        // clamp it and say so
+        int fr = a.fingers_in[2 * i], fc = a.fingers_in[2 * i + 1];
+        if ((unsigned)fr >= (unsigned)G::R || (unsigned)fc >= (unsigned)G::C) {
+            finger_flag = FLAG_REJECTED;
+            fr = fr < 0 ? 0 : (fr >= G::R ? G::R - 1 : fr);
+            fc = fc < 0 ? 0 : (fc >= G::C ? G::C - 1 : fc);
+        }
+        finger = fr * G::C + fc;
+    }
     State<G> s;
     clear_state<G>(s);
     int consumed = 0;
@@ -55,7 +66,7 @@ __global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ Re
                                                 a.p.n_inj, finger, &consumed);
     if (!valid) return;
     StateIO<G>::store(a.state, i, s.b, s.meta);
-    if (a.flags) a.flags[i] = (uint8_t)flags;
+    if (a.flags) a.flags[i] = (uint8_t)(flags | finger_flag);
     if (a.consumed) a.consumed[i] = (uint8_t)sat255(consumed);
 }
 
@@ -88,9 +99,17 @@ __global__ void __launch_bounds__(BLOCK) pack_kernel(int64_t n, const T *boards,
     }
     Board<G> b;
     pack_cells<G, int8_t>(b, cells);
-    const int finger = (int)fingers[2 * i] * G::C + (int)fingers[2 * i + 1];
-    StateIO<G>::store(state, i, b, meta_pack(finger, prev ? prev[i] : ACT_PASS, moves ? moves[i] : 0));
-    if (flags) flags[i] = (uint8_t)(bad ? FLAG_UNSUPPORTED_ORB : 0);
+    long long fr = (long long)fingers[2 * i], fc = (long long)fingers[2 * i + 1];
+    uint32_t fl = bad ? (uint32_t)FLAG_UNSUPPORTED_ORB : 0u;
+    if (fr < 0 || fr >= G::R || fc < 0 || fc >= G::C) {   // see reset_kernel: clamp and flag
+        fl |= FLAG_REJECTED;
+        fr = fr < 0 ? 0 : (fr >= G::R ? G::R - 1 : fr);
+        fc = fc < 0 ? 0 : (fc >= G::C ? G::C - 1 : fc);
+    }
+    int pv = prev ? prev[i] : ACT_PASS;
+    if (pv > ACT_PASS) pv = ACT_PASS;                     // 3-bit field; anything else reads as 'pass'
+    StateIO<G>::store(state, i, b, meta_pack((int)(fr * G::C + fc), pv, moves ? moves[i] : 0));
+    if (flags) flags[i] = (uint8_t)fl;
 }
 
 // state -> plain int boards.  A board is CELLS elements of T (240 B as int64), so one thread per board would write

@@ -275,21 +275,30 @@ PPAD_HD int orb_from_u32(const SkyfallTable &t, uint32_t x)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Orb source: an injected per-board sequence first (4-bit nibbles, 8 per uint32, orb d in word
-// d >> 3 at bit 4 * (d & 7)), then the Philox stream at the same draw index d.
+// Orb source: an injected per-board sequence first, then the Philox stream at the same draw index d.
+// Two slab layouts (include/ppad_b200.h: ppad_slab_format):
+//   SLAB_NIBBLES  4-bit nibbles, 8 per uint32: orb d in word d >> 3 at bit 4 * (d & 7)
+//   SLAB_PLANES3  bit-sliced 3-bit codes, 32 orbs per group of three uint32 {p0, p1, p2}: bit (d & 31) of word
+//                 3 * (d >> 5) + j is bit j of orb d -- 12 bytes per 32 orbs (orb types 0..6 only)
+// Injected codes that are not orb types of the geometry (>= NT) are handed on as they are and flagged
+// (bad -> FLAG_UNSUPPORTED_ORB).
 // ---------------------------------------------------------------------------------------------
+enum : int { SLAB_NIBBLES = 0, SLAB_PLANES3 = 1 };
+
 struct OrbSource {
     const uint32_t *slab;   // this board's words, or nullptr
     int n_inj;              // injected orbs available; < 0 = pure Philox (no EXHAUSTED flag)
     int cursor;             // orbs handed out so far
     uint32_t stream;
-    uint32_t word;          // cached slab word
+    uint32_t word;          // cached slab word (nibble layout)
     int word_idx;
     U4 blk;                 // cached Philox block
     int blk_idx;
     bool exhausted;
+    int fmt;                // SLAB_NIBBLES / SLAB_PLANES3
+    uint32_t bad;           // bit 0: an injected code was not an orb type of the geometry
 
-    PPAD_HD void init(const uint32_t *slab_, int n_inj_, uint32_t stream_)
+    PPAD_HD void init(const uint32_t *slab_, int n_inj_, uint32_t stream_, int fmt_ = SLAB_NIBBLES)
     {
         slab = slab_;
         n_inj = slab_ ? n_inj_ : -1;
@@ -299,6 +308,8 @@ struct OrbSource {
         word_idx = -1;
         blk_idx = -1;
         exhausted = false;
+        fmt = fmt_;
+        bad = 0;
         blk.x = blk.y = blk.z = blk.w = 0;
     }
 
@@ -307,12 +318,22 @@ struct OrbSource {
     {
         const int d = cursor++;
         if (d < n_inj) {
-            const int wi = d >> 3;
-            if (wi != word_idx) {
-                word = slab[wi];
-                word_idx = wi;
+            int code;
+            if (fmt == SLAB_PLANES3) {
+                // the general path is rare (a slab that runs out in the middle of a fill; reset from a slab): no caching
+                const uint32_t *g = slab + 3 * (d >> 5);
+                const int k = d & 31;
+                code = (int)(((g[0] >> k) & 1u) | (((g[1] >> k) & 1u) << 1) | (((g[2] >> k) & 1u) << 2));
+            } else {
+                const int wi = d >> 3;
+                if (wi != word_idx) {
+                    word = slab[wi];
+                    word_idx = wi;
+                }
+                code = (int)((word >> (4 * (d & 7))) & 15u);
             }
-            return (int)((word >> (4 * (d & 7))) & 15u);
+            bad |= code >= NT ? 1u : 0u;
+            return code;
         }
         if (n_inj >= 0) exhausted = true;
         const int bi = d >> 2;
@@ -591,21 +612,49 @@ PPAD_HD void fill_board(Board<G> &b, OrbSource &src, const RngKey &key, const Sk
     W e = empties<G>(b);
     if (e == 0) return;
     if (src.cursor + popc(e) <= src.n_inj) {
-        // every orb comes from the injected slab: a tight loop over the nibble stream, no source bookkeeping
+        // every orb comes from the injected slab: a tight loop over the orb stream, no source bookkeeping
         int d = src.cursor;
-        uint32_t word = src.slab[d >> 3] >> (4 * (d & 7));
-        do {
-            const W bit = e & (~e + 1);
-            e ^= bit;
-            // an empty cell has its bit set in all three planes: clear the planes where the code has a 0
-            b.b0 ^= bit & ((W)(word & 1u) - 1);
-            b.b1 ^= bit & ((W)((word >> 1) & 1u) - 1);
-            b.b2 ^= bit & ((W)((word >> 2) & 1u) - 1);
-            PPAD_P4(b.b3 ^= bit & ((W)((word >> 3) & 1u) - 1))
-            d++;
-            word >>= 4;
-            if ((d & 7) == 0 && e) word = src.slab[d >> 3];
-        } while (e);
+        uint32_t badacc = 0;   // bit 0 of the OR of "this code is no orb type" over the orbs taken
+        if (src.fmt == SLAB_PLANES3) {
+            const uint32_t *g = src.slab + 3 * (d >> 5);
+            uint32_t s0 = g[0] >> (d & 31), s1 = g[1] >> (d & 31), s2 = g[2] >> (d & 31);
+            do {
+                const W bit = e & (~e + 1);
+                e ^= bit;
+                // an empty cell has its bit set in all three planes: clear the planes where the code has a 0
+                b.b0 ^= bit & ((W)(s0 & 1u) - 1);
+                b.b1 ^= bit & ((W)(s1 & 1u) - 1);
+                b.b2 ^= bit & ((W)(s2 & 1u) - 1);
+                PPAD_P4(b.b3 ^= bit)           // 3-bit codes: plane 3 of a 4-plane board is always 0
+                badacc |= s0 & s1 & s2;        // code 7 is no orb type
+                d++;
+                s0 >>= 1;
+                s1 >>= 1;
+                s2 >>= 1;
+                if ((d & 31) == 0 && e) {
+                    g = src.slab + 3 * (d >> 5);
+                    s0 = g[0];
+                    s1 = g[1];
+                    s2 = g[2];
+                }
+            } while (e);
+        } else {
+            uint32_t word = src.slab[d >> 3] >> (4 * (d & 7));
+            do {
+                const W bit = e & (~e + 1);
+                e ^= bit;
+                b.b0 ^= bit & ((W)(word & 1u) - 1);
+                b.b1 ^= bit & ((W)((word >> 1) & 1u) - 1);
+                b.b2 ^= bit & ((W)((word >> 2) & 1u) - 1);
+                PPAD_P4(b.b3 ^= bit & ((W)((word >> 3) & 1u) - 1))
+                if constexpr (G::NP == 3) badacc |= (word >> 3) | (word & (word >> 1) & (word >> 2));   // code >= 7
+                else badacc |= (word >> 3) & ((word >> 1) | (word >> 2));                                  // code >= 10
+                d++;
+                word >>= 4;
+                if ((d & 7) == 0 && e) word = src.slab[d >> 3];
+            } while (e);
+        }
+        src.bad |= badacc & 1u;
         src.cursor = d;
         src.word_idx = -1;
         return;
@@ -746,7 +795,7 @@ struct CascadeItem {
 template <class G>
 PPAD_HD bool cascade_round_m(CascadeItem<G> &it, typename G::W &m, typename G::W &er, typename G::W &ed,
                              bool skyfall_damage, int cascade_cap, const TeamTable &team, const uint32_t *slab, int n_inj,
-                             const RngKey &key, const SkyfallTable &sky, uint16_t *log, int log_cap)
+                             const RngKey &key, const SkyfallTable &sky, uint16_t *log, int log_cap, int slab_fmt = SLAB_NIBBLES)
 {
     cancel_tally<G>(it.b, m, er, ed, it.tally, team, log, log_cap);
     it.depth++;
@@ -757,12 +806,13 @@ PPAD_HD bool cascade_round_m(CascadeItem<G> &it, typename G::W &m, typename G::W
     }
     drop_board<G>(it.b);
     OrbSource src;
-    src.init(slab, n_inj, STREAM_SKYFALL);
+    src.init(slab, n_inj, STREAM_SKYFALL, slab_fmt);
     src.cursor = it.cursor;
     src.exhausted = it.exhausted;
     fill_board<G>(it.b, src, key, sky);
     it.cursor = src.cursor;
     it.exhausted = src.exhausted;
+    if (src.bad) it.flags |= FLAG_UNSUPPORTED_ORB;
     m = match_mask<G>(it.b, er, ed);
     return m != 0;
 }
@@ -771,12 +821,12 @@ PPAD_HD bool cascade_round_m(CascadeItem<G> &it, typename G::W &m, typename G::W
 template <class G>
 PPAD_HD bool cascade_round(CascadeItem<G> &it, bool skyfall_damage, int cascade_cap, const TeamTable &team,
                            const uint32_t *slab, int n_inj, const RngKey &key, const SkyfallTable &sky, uint16_t *log,
-                           int log_cap)
+                           int log_cap, int slab_fmt = SLAB_NIBBLES)
 {
     typename G::W er, ed;
     typename G::W m = match_mask<G>(it.b, er, ed);
     if (m == 0) return false;
-    return cascade_round_m<G>(it, m, er, ed, skyfall_damage, cascade_cap, team, slab, n_inj, key, sky, log, log_cap);
+    return cascade_round_m<G>(it, m, er, ed, skyfall_damage, cascade_cap, team, slab, n_inj, key, sky, log, log_cap, slab_fmt);
 }
 
 // damage (game.py:157-199) of an explicit combo list: log[i] = colour | N << 8
@@ -895,12 +945,14 @@ struct StepParams {
     int32_t eval_moves, auto_reset, max_moves;
     int32_t n_inj, slab_words, log_cap;
     int32_t draw0;   // first draw index of a stand-alone fill (ppad_fill)
+    int32_t slab_fmt;   // SLAB_NIBBLES / SLAB_PLANES3: layout of the injected skyfall slab of this launch
 };
 
 struct StepOut {
     double reward;
     uint32_t info;
     int action;
+    int consumed;   // skyfall orbs drawn by the cascade, not saturated (the info byte stops at 255)
 };
 
 struct StepPrefix {
@@ -1095,6 +1147,7 @@ PPAD_HD StepOut step_board(bool live, State<G> &s, Board<G> &final_board, const 
         quick.action = pre.action;
         quick.reward = 0.0;
         quick.info = make_info(0, 0, 0, pre.flags);
+        quick.consumed = 0;
         return quick;
     }
     CascadeItem<G> it;
@@ -1108,7 +1161,7 @@ PPAD_HD StepOut step_board(bool live, State<G> &s, Board<G> &final_board, const 
     while (warp_any(cascading)) {
         if (cascading)
             cascading = cascade_round_m<G>(it, m, er, ed, p.skyfall_damage != 0, p.cascade_cap, p.team, slab, p.n_inj,
-                                           key, p.sky, log, p.log_cap);
+                                           key, p.sky, log, p.log_cap, p.slab_fmt);
         warp_converge();
     }
 #if defined(__CUDA_ARCH__)
@@ -1128,6 +1181,7 @@ PPAD_HD StepOut step_board(bool live, State<G> &s, Board<G> &final_board, const 
     out.action = pre.action;
     out.reward = it.reward();
     out.info = it.info();
+    out.consumed = it.cursor;
     return out;
 }
 

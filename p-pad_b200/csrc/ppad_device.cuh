@@ -31,7 +31,9 @@ namespace ppad {
 constexpr int BLOCK = 256;
 
 // ------------------------------------------------------------------------------------------------
-// packed state I/O
+// packed state I/O.  State buffers are read AND written by the same kernels (in place), so the loads are plain
+// coherent L2 loads (ld.global.cg), not the read-only path (ld.global.nc is only defined for data nobody writes
+// during the kernel); read-only inputs (slab, actions, Q-values) keep __ldg.
 // ------------------------------------------------------------------------------------------------
 template <class G, bool WIDE = (sizeof(typename G::W) == 8), int NP = G::NP>
 struct StateIO;
@@ -49,7 +51,7 @@ template <class G>
 struct StateIO<G, false, 3> {
     static __device__ __forceinline__ State<G> load(const void *base, int64_t i)
     {
-        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(base) + i);
+        const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(base) + i);
         State<G> s;
         s.b.b0 = v.x;
         s.b.b1 = v.y;
@@ -76,8 +78,8 @@ template <class G>
 struct StateIO<G, true, 3> {
     static __device__ __forceinline__ State<G> load(const void *base, int64_t i)
     {
-        const uint4 lo = __ldg(reinterpret_cast<const uint4 *>(base) + 2 * i);
-        const uint4 hi = __ldg(reinterpret_cast<const uint4 *>(base) + 2 * i + 1);
+        const uint4 lo = __ldcg(reinterpret_cast<const uint4 *>(base) + 2 * i);
+        const uint4 hi = __ldcg(reinterpret_cast<const uint4 *>(base) + 2 * i + 1);
         State<G> s;
         s.b.b0 = (uint64_t)lo.x | ((uint64_t)lo.y << 32);
         s.b.b1 = (uint64_t)lo.z | ((uint64_t)lo.w << 32);
@@ -105,8 +107,8 @@ template <class G>
 struct StateIO<G, false, 4> {
     static __device__ __forceinline__ State<G> load(const void *base, int64_t i)
     {
-        const uint4 lo = __ldg(reinterpret_cast<const uint4 *>(base) + 2 * i);
-        const uint4 hi = __ldg(reinterpret_cast<const uint4 *>(base) + 2 * i + 1);
+        const uint4 lo = __ldcg(reinterpret_cast<const uint4 *>(base) + 2 * i);
+        const uint4 hi = __ldcg(reinterpret_cast<const uint4 *>(base) + 2 * i + 1);
         State<G> s;
         s.b.b0 = lo.x;
         s.b.b1 = lo.y;
@@ -133,7 +135,7 @@ struct StateIO<G, true, 4> {
     static __device__ __forceinline__ State<G> load(const void *base, int64_t i)
     {
         const uint4 *p = reinterpret_cast<const uint4 *>(base) + 3 * i;
-        const uint4 a = __ldg(p), c = __ldg(p + 1), d = __ldg(p + 2);
+        const uint4 a = __ldcg(p), c = __ldcg(p + 1), d = __ldcg(p + 2);
         State<G> s;
         s.b.b0 = (uint64_t)a.x | ((uint64_t)a.y << 32);
         s.b.b1 = (uint64_t)a.z | ((uint64_t)a.w << 32);

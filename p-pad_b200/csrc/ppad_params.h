@@ -95,6 +95,14 @@ inline int build_params(const ppad_config &cfg, StepParams &p, int &geom, std::s
             p.team.atk[colour][k] = cfg.team_atk[u];
         }
     }
+    if (cfg.cascade_cap < 0 || cfg.cascade_cap > 255) {
+        err = "cascade_cap must be 0 (no cap) or 1..255: the depth of a cascade is reported, and parked, in 8 bits";
+        return PPAD_ERR_INVALID;
+    }
+    if (cfg.reset_cap < 0) {
+        err = "reset_cap must be >= 0";
+        return PPAD_ERR_INVALID;
+    }
     p.skyfall_damage = cfg.skyfall_damage;
     p.cascade_cap = cfg.cascade_cap;
     p.reset_cap = cfg.reset_cap;

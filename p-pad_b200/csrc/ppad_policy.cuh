@@ -1,4 +1,190 @@
-// ppad_policy.cuh -- placeholder, filled in below
+// ppad_policy.cuh -- the policy-driven env step of a device-resident rollout (BASELINE configs[4]) as ONE kernel:
+//
+//   q[n, 5] (the agent's Q-values)                                   projects/simulation.py:96 (agent.act)
+//     -> mask off-board / reversing moves, epsilon-greedy, argmax or Boltzmann draw     ppad/agent/agent01.py:173-218
+//     -> episode length cap                                                             simulation.py:50-52
+//     -> push (state BEFORE the step, action) into the replay ring                      simulation.py:60-61, 294-299
+//     -> env step: move, or pass = cascade resolution + float64 reward                  ppad/pad/game.py:329-405
+//     -> auto reset of the boards that passed                                           simulation.py:44, game.py:282-323
+//     -> push the reward; when an episode ends, write the discounted returns            ppad/agent/utils.py:22-51
+//        gamma^j * r back into the ring rows of its earlier steps                       (simulation.py:59: discount)
+//     -> one-hot observation of the new state for the agent's next forward pass         agent01.py:254-273
+//     -> per-CTA episode statistics (for the NCCL all-gather every K steps)             simulation.py:336-349
+//
+// Round 1 ran this as select -> state.clone() -> step -> push -> ~10 torch reductions (>= 5 launches and 4.9 ms per
+// 2^23-board step, 0.23 of the HBM roofline).  Fused, the step touches per board: state in/out 32 B, q 20 B, obs
+// 840 B, results 13 B, ring row 25 B = 930 B.
 #pragma once
 #include "ppad_step.cuh"
-#define PPAD_POLICY_LAUNCHERS(PREFIX, G)
+
+namespace ppad {
+
+constexpr int STATS_WORDS = 40;   // uint64 per CTA row, layout = dist.STAT_FIELDS + depth hist [16] + combo hist [16]
+enum : int { ST_BOARDS = 0, ST_EVALUATED = 1, ST_REWARD_SUM = 2, ST_REWARD_MAX = 3, ST_COMBOS = 4, ST_CONSUMED = 5,
+             ST_EPISODES = 6, ST_FAULTS = 7, ST_DEPTH_HIST = 8, ST_COMBO_HIST = 24 };
+constexpr double STATS_REWARD_SCALE = 1024.0;   // reward sums are kept in fixed point: exact, order independent
+
+struct PolicyArgs {
+    StepParams p;
+    int64_t n;
+    uint64_t env0;
+    void *state;
+    const float *q;           // [n, 5]
+    int32_t method;           // SELECT_MAX / SELECT_BOLTZMANN
+    float beta, epsilon;
+    const uint32_t *slab;     // injected skyfall or NULL (Philox)
+    uint8_t *action_out;      // [n] or NULL
+    double *reward;           // [n] or NULL
+    uint32_t *info;           // [n] or NULL
+    void *obs;                // [n, R, C, 7] or NULL
+    int32_t obs_dtype;
+    // replay ring, time-major: the row of (this step, board i) is ((ring_step % ring_steps) * n + i)
+    void *r_state;            // [ring_steps * n] packed records, or NULL (no replay)
+    uint8_t *r_action;
+    double *r_reward;
+    int64_t ring_steps, ring_step;
+    double gamma;             // > 0: discounted returns are written back when an episode ends (agent/utils.py:22-51)
+    int32_t log10_reward;     // log10 of a positive final reward before discounting (utils.py:37-40)
+    unsigned long long *stats;   // [grid, STATS_WORDS] per-CTA accumulators (added to, never reset here), or NULL
+};
+
+// MINB: resident CTAs per SM the register allocation aims at.  The auto-reset + selection + observation code needs
+// more than the 64 registers that 4 CTAs of 256 threads leave (round 1: 142 B of spill stores per thread in the
+// auto-reset step kernel); 3 CTAs (85 registers) hold it without spills.
+template <class G, bool OBS, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) policy_step_kernel(const __grid_constant__ PolicyArgs a)
+{
+    __shared__ ObsShared obs_sh;
+    __shared__ uint32_t obs_stream[OBS ? (BLOCK / 32) * ObsGeom<G>::WARP_WORDS : 1];
+    __shared__ unsigned long long st[8];
+    __shared__ unsigned int st_hist[32];   // depth histogram [16] | combo-count histogram [16]
+    if (OBS) obs_init_luts(obs_sh);
+    if (a.stats && threadIdx.x < 8) st[threadIdx.x] = 0;
+    if (a.stats && threadIdx.x < 32) st_hist[threadIdx.x] = 0;
+    if (OBS || a.stats) __syncthreads();
+
+    const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    const bool valid = i < a.n;
+    const uint64_t env = a.env0 + (uint64_t)i;
+    State<G> s;
+    clear_state<G>(s);
+    int action = ACT_PASS;
+    const int64_t row = (a.ring_step % (a.ring_steps > 0 ? a.ring_steps : 1)) * a.n + i;
+    if (valid) {
+        s = StateIO<G>::load(a.state, i);
+        // ---- Agent01.act after the network (agent01.py:173-218) + the episode length cap (simulation.py:50-52)
+        if (a.p.max_moves > 0 && meta_moves(s.meta) >= a.p.max_moves) {
+            action = ACT_PASS;
+        } else {
+            float qi[5];
+#pragma unroll
+            for (int k = 0; k < 5; k++) qi[k] = __ldg(a.q + 5 * i + k);
+            RngKey key = board_key(a.p, env);
+            const U4 blk = philox4x32_10(U4{key.env_lo, key.env_hi, key.step, STREAM_POLICY << 24}, key.k0, key.k1);
+            action = select_action<G>(qi, meta_finger(s.meta), meta_prev(s.meta), a.method, a.beta, a.epsilon, blk.x, blk.y);
+        }
+        // ---- the ring row's observation is the state the action was chosen in (simulation.py:60-61)
+        if (a.r_state) {
+            StateIO<G>::store(a.r_state, row, s.b, s.meta);
+            a.r_action[row] = (uint8_t)action;
+        }
+    }
+    // ---- the env step (every lane takes part: the cascade loop and the reset are warp-cooperative)
+    const int episode_len = meta_moves(s.meta);   // moves made before this step (a pass ends the episode)
+    Board<G> fin;
+    const StepOut o = step_board<G, true, true>(valid, s, fin, a.p, env, action,
+                                                a.slab && valid ? a.slab + (size_t)i * a.p.slab_words : nullptr, nullptr);
+    if (valid) {
+        StateIO<G>::store(a.state, i, s.b, s.meta);
+        if (a.action_out) a.action_out[i] = (uint8_t)o.action;
+        if (a.reward) a.reward[i] = o.reward;
+        if (a.info) a.info[i] = o.info;
+        if (a.r_state) {
+            // ---- reward of this row; at the end of an episode the discounted returns of its earlier rows:
+            // discount() scans backwards cur = cur * gamma + r with r = 0 for the moves (utils.py:41-45)
+            double r = o.reward;
+            if (a.log10_reward && r > 0.0) r = log10(r);
+            a.r_reward[row] = r;
+            if (a.gamma > 0.0 && o.action == ACT_PASS && o.reward > 0.0) {   // all-non-positive episodes stay as they are (utils.py:32)
+                int64_t back = episode_len < a.ring_steps - 1 ? episode_len : a.ring_steps - 1;   // rows still in the ring
+                if (back > a.ring_step) back = a.ring_step;                                        // rows that were ever pushed
+                double cur = r;
+                int64_t t = a.ring_step;
+                for (int64_t j = 0; j < back; j++) {
+                    cur = dadd(dmul(cur, a.gamma), 0.0);
+                    t--;
+                    a.r_reward[((t % a.ring_steps + a.ring_steps) % a.ring_steps) * a.n + i] = cur;
+                }
+            }
+        }
+    }
+    // ---- episode statistics: warp reductions -> shared-memory accumulators -> one row of uint64 per CTA in global memory
+    if (a.stats) {   // kernel-uniform: every lane takes part in the reductions
+        const unsigned full = 0xFFFFFFFFu;
+        const uint32_t inf = valid ? o.info : 0u;
+        const uint32_t combos = inf & 0xFFu, depth = (inf >> 8) & 0xFFu, consumed = (inf >> 16) & 0xFFu, flags = inf >> 24;
+        const bool evaluated = valid && (o.action == ACT_PASS || a.p.eval_moves != 0);
+        if (evaluated) {   // histograms over the evaluated boards (the passes of a policy rollout)
+            atomicAdd(&st_hist[depth < 15 ? depth : 15], 1u);
+            atomicAdd(&st_hist[16 + (combos < 15 ? combos : 15)], 1u);
+        }
+        const unsigned n_eval = __popc(__ballot_sync(full, depth != 0));
+        const unsigned n_done = __popc(__ballot_sync(full, (flags & FLAG_EPISODE_DONE) != 0));
+        const unsigned n_fault = __popc(__ballot_sync(full, (flags & 0x7Fu) != 0));
+        const unsigned sum_combos = __reduce_add_sync(full, combos), sum_consumed = __reduce_add_sync(full, consumed);
+        unsigned long long fx = valid && depth ? (unsigned long long)llrint(o.reward * STATS_REWARD_SCALE) : 0ull;
+        unsigned long long mx = valid && depth ? (unsigned long long)__double_as_longlong(o.reward) : 0ull;   // rewards are >= 0
+#pragma unroll
+        for (int off = 16; off; off >>= 1) {
+            fx += __shfl_xor_sync(full, fx, off);
+            const unsigned long long other = __shfl_xor_sync(full, mx, off);
+            mx = other > mx ? other : mx;
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&st[ST_EVALUATED], (unsigned long long)n_eval);
+            atomicAdd(&st[ST_REWARD_SUM], fx);
+            atomicMax(&st[ST_REWARD_MAX], mx);
+            atomicAdd(&st[ST_COMBOS], (unsigned long long)sum_combos);
+            atomicAdd(&st[ST_CONSUMED], (unsigned long long)sum_consumed);
+            atomicAdd(&st[ST_EPISODES], (unsigned long long)n_done);
+            atomicAdd(&st[ST_FAULTS], (unsigned long long)n_fault);
+        }
+    }
+    const int64_t warp0 = i - (threadIdx.x & 31);
+    if (OBS && warp0 < a.n) {
+        const int n_valid = (int)(a.n - warp0 < 32 ? a.n - warp0 : 32);
+        emit_obs<G>(s, valid, n_valid, obs_stream + (threadIdx.x >> 5) * ObsGeom<G>::WARP_WORDS, obs_sh,
+                    obs_warp_ptr<G>(a.obs, warp0, a.obs_dtype), a.obs_dtype);
+    }
+    if (a.stats) {
+        __syncthreads();
+        if (threadIdx.x < STATS_WORDS) {
+            unsigned long long *dst = a.stats + (size_t)blockIdx.x * STATS_WORDS + threadIdx.x;
+            unsigned long long v = threadIdx.x < 8 ? st[threadIdx.x] : (unsigned long long)st_hist[threadIdx.x - 8];
+            if (threadIdx.x == ST_BOARDS) {
+                const int64_t left = a.n - (int64_t)blockIdx.x * BLOCK;
+                v = (unsigned long long)(left < BLOCK ? left : BLOCK);
+            }
+            if (threadIdx.x == ST_REWARD_MAX) *dst = v > *dst ? v : *dst;
+            else *dst += v;
+        }
+    }
+}
+
+template <class G>
+int launch_policy_g(const PolicyArgs &a, int minb, cudaStream_t st)
+{
+    const unsigned grid = grid_for(a.n);
+    if (a.obs) {
+        if (minb >= 4) policy_step_kernel<G, true, 4><<<grid, BLOCK, 0, st>>>(a);
+        else policy_step_kernel<G, true, 3><<<grid, BLOCK, 0, st>>>(a);
+    } else {
+        if (minb >= 4) policy_step_kernel<G, false, 4><<<grid, BLOCK, 0, st>>>(a);
+        else policy_step_kernel<G, false, 3><<<grid, BLOCK, 0, st>>>(a);
+    }
+    return after_launch("policy_step_kernel");
+}
+
+#define PPAD_POLICY_LAUNCHERS(PREFIX, G) PREFIX template int launch_policy_g<G>(const PolicyArgs &, int, cudaStream_t);
+
+}   // namespace ppad

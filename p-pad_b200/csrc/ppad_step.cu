@@ -40,11 +40,23 @@ using namespace ppad;
 
 extern "C" {
 
+struct CompactTarget {
+    uint32_t *nibbles, *tile_line, *summary, *counters;
+    void *records;
+    int64_t capacity_bytes;
+};
+
 static int launch_step(const ppad_ctx *ctx, const ppad_step_args *args, cudaStream_t st, bool coalesced_results = false,
-                       bool stage_host_slab = false)
+                       bool stage_host_slab = false, const CompactTarget *compact = nullptr)
 {
     if (!args->state) return fail(PPAD_ERR_INVALID, "ppad_step: null state");
-    if (args->slab && (args->slab_words <= 0 || args->n_inj < 0 || args->n_inj > args->slab_words * 8))
+    if (args->slab_format != PPAD_SLAB_NIBBLES && args->slab_format != PPAD_SLAB_PLANES3)
+        return fail(PPAD_ERR_INVALID, "ppad_step: unknown slab_format");
+    if (args->slab && args->slab_format == PPAD_SLAB_PLANES3) {
+        if (ctx->geom >= 3) return fail(PPAD_ERR_UNSUPPORTED, "ppad_step: PPAD_SLAB_PLANES3 needs a context with orb_bits = 3");
+        if (args->slab_words <= 0 || args->slab_words % 3 || args->n_inj < 0 || args->n_inj > args->slab_words / 3 * 32)
+            return fail(PPAD_ERR_INVALID, "ppad_step: PPAD_SLAB_PLANES3 needs slab_words = 3 * groups and 0 <= n_inj <= 32 * groups");
+    } else if (args->slab && (args->slab_words <= 0 || args->n_inj < 0 || args->n_inj > args->slab_words * 8))
         return fail(PPAD_ERR_INVALID, "ppad_step: need 0 <= n_inj <= 8 * slab_words");
     if (args->combo_log && args->log_cap <= 0) return fail(PPAD_ERR_INVALID, "ppad_step: combo_log needs log_cap > 0");
     if (args->obs && args->obs_dtype != PPAD_OBS_F32 && args->obs_dtype != PPAD_OBS_U8)
@@ -61,6 +73,7 @@ static int launch_step(const ppad_ctx *ctx, const ppad_step_args *args, cudaStre
     a.p.n_inj = args->slab ? args->n_inj : -1;
     a.p.slab_words = args->slab_words;
     a.p.log_cap = args->log_cap;
+    a.p.slab_fmt = args->slab_format;
     if (args->skyfall_damage >= 0) a.p.skyfall_damage = args->skyfall_damage;
     a.n = args->n;
     a.env0 = args->env0;
@@ -73,6 +86,7 @@ static int launch_step(const ppad_ctx *ctx, const ppad_step_args *args, cudaStre
     a.final_state = args->final_state;
     a.state_copy = args->state_copy;
     a.combo_log = args->combo_log;
+    a.consumed16 = args->consumed_out;
     a.obs = args->obs;
     a.obs_dtype = args->obs_dtype;
     a.paths = args->paths;
@@ -81,10 +95,27 @@ static int launch_step(const ppad_ctx *ctx, const ppad_step_args *args, cudaStre
     a.path_len = args->path_len;
     if (a.paths && (a.path_words <= 0 || a.path_len < 0))
         return fail(PPAD_ERR_INVALID, "ppad_step: paths need path_words > 0 and path_len >= 0");
-    a.stage_slab = (stage_host_slab && a.slab && a.p.slab_words == 4 && ((uintptr_t)a.slab & 15) == 0) ? 1 : 0;
+    a.stage_slab = 0;
+    if (stage_host_slab && a.slab && ((uintptr_t)a.slab & 15) == 0) {
+        if (a.p.slab_fmt == PPAD_SLAB_NIBBLES && a.p.slab_words == 4) a.stage_slab = 1;
+        if (a.p.slab_fmt == PPAD_SLAB_PLANES3 && a.p.slab_words == 3) a.stage_slab = 2;
+    }
+    a.c_nibbles = a.c_tile_line = a.c_summary = a.c_counters = nullptr;
+    a.c_records = nullptr;
+    a.c_capacity = 0;
+    if (compact) {
+        if (a.paths || a.combo_log) return fail(PPAD_ERR_UNSUPPORTED, "compact results: no finger paths / combo log");
+        a.c_nibbles = compact->nibbles;
+        a.c_tile_line = compact->tile_line;
+        a.c_summary = compact->summary;
+        a.c_counters = compact->counters;
+        a.c_records = reinterpret_cast<uint4 *>(compact->records);
+        const int64_t lines = compact->capacity_bytes / 128;
+        a.c_capacity = (uint32_t)(lines > 0x7FFFFFFF ? 0x7FFFFFFF : lines);
+    }
     int choice = STEP_KERNEL_POOL;
     if (args->obs) choice = STEP_KERNEL_OBS;
-    else if (coalesced_results || (!a.p.eval_moves && !a.actions && !a.paths) || !a.p.skyfall_damage) {
+    else if (compact || coalesced_results || (!a.p.eval_moves && !a.actions && !a.paths) || !a.p.skyfall_damage) {
         // results go straight to host memory: the pooled kernel's scattered 8-byte result writes would become tiny
         // PCIe transactions, one thread per board writes them as full lines.
         // Steps of the in-kernel random policy that only evaluate passes (eval_moves = 0, no actions given: plain
@@ -157,6 +188,8 @@ struct ppad_pipe {
     uint8_t *d_actions, *d_action_out;
     double *d_reward;
     uint32_t *d_info;
+    uint32_t *d_counters;   // compact result stream: {next free line, finished tiles}, kept at 0 between launches
+    cudaEvent_t joined;     // recorded after the last chunk of a step: after_stream waits for it
 };
 
 // NULL counts as pinned (absent buffer); anything cudaHostAlloc'ed / cudaHostRegister'ed is device-visible under UVA
@@ -202,6 +235,9 @@ int ppad_pipe_create(const ppad_ctx *ctx, int64_t n_max, int32_t slab_words_max,
     if (e == cudaSuccess) e = cudaMalloc(&p->d_action_out, n);
     if (e == cudaSuccess) e = cudaMalloc(&p->d_reward, n * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&p->d_info, n * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_counters, 2 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(p->d_counters, 0, 2 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->joined, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         ppad_pipe_destroy(p);
         return cuda_check(e, "ppad_pipe_create");
@@ -230,6 +266,8 @@ void ppad_pipe_destroy(ppad_pipe *p)
     cudaFree(p->d_action_out);
     cudaFree(p->d_reward);
     cudaFree(p->d_info);
+    cudaFree(p->d_counters);
+    if (p->joined) cudaEventDestroy(p->joined);
     if (prev_device >= 0) cudaSetDevice(prev_device);   // destroy may run from a finaliser: leave the caller's device alone
     delete p;
 }
@@ -245,14 +283,25 @@ int ppad_pipe_step(ppad_pipe *p, const ppad_host_step_args *h, void *after_strea
         return fail(PPAD_ERR_INVALID, "ppad_pipe_step: slab_words exceeds the pipe's slab_words_max");
     if (!h->state) return fail(PPAD_ERR_INVALID, "ppad_pipe_step: null state");
     if (h->n == 0) return PPAD_OK;
+    if (h->results_compact) {
+        if (!h->nibbles_host || !h->tile_line_host || !h->records_host || !h->summary_host || h->records_capacity < 128)
+            return fail(PPAD_ERR_INVALID, "ppad_pipe_step: compact results need nibbles, tile_line, records and summary buffers");
+        if (((uintptr_t)h->records_host & 127) || ((uintptr_t)h->nibbles_host & 127))
+            return fail(PPAD_ERR_INVALID, "ppad_pipe_step: records_host and nibbles_host must be 128-byte aligned");
+        if (!p->zero_copy || p->zero_copy == 2 || !host_is_pinned(h->nibbles_host) || !host_is_pinned(h->tile_line_host) ||
+            !host_is_pinned(h->records_host) || !host_is_pinned(h->summary_host) || !host_is_pinned(h->slab_host) ||
+            !host_is_pinned(h->actions_host) || !host_is_pinned(h->state_out_host))
+            return fail(PPAD_ERR_UNSUPPORTED, "ppad_pipe_step: compact results need pinned host buffers and zero-copy mode 1");
+    }
     const size_t rec = (size_t)ppad_state_bytes_ex(ctx->cfg.rows, ctx->cfg.cols, ctx->cfg.orb_bits);
     const size_t obs_elem = h->obs_dtype == PPAD_OBS_F32 ? 4 : 1;
     const size_t obs_row = (size_t)ctx->cfg.rows * ctx->cfg.cols * 7 * obs_elem;
     // chunk streams start after whatever the caller has queued on after_stream (e.g. the reset)
     cudaError_t e = cudaEventRecord(p->fork, (cudaStream_t)after_stream);
-    const bool zc = p->zero_copy && host_is_pinned(h->actions_host) && host_is_pinned(h->slab_host) &&
-                    host_is_pinned(h->action_out_host) && host_is_pinned(h->reward_host) && host_is_pinned(h->info_host) &&
-                    host_is_pinned(h->state_out_host);
+    const bool zc = h->results_compact ||
+                    (p->zero_copy && host_is_pinned(h->actions_host) && host_is_pinned(h->slab_host) &&
+                     host_is_pinned(h->action_out_host) && host_is_pinned(h->reward_host) && host_is_pinned(h->info_host) &&
+                     host_is_pinned(h->state_out_host));
     // zero_copy 1: the kernel reads the slab from and writes its results to the host buffers; 2 ("hybrid"): the slab
     // (and given actions) travel by DMA, chunk by chunk on the pipe's streams, and only the results are written in place
     // by the kernels -- no PCIe read sits inside a kernel, which matters on hosts whose read latency is high
@@ -285,14 +334,27 @@ int ppad_pipe_step(ppad_pipe *p, const ppad_host_step_args *h, void *after_strea
         a.slab = h->slab_host;
         a.slab_words = h->slab_words;
         a.n_inj = h->n_inj;
-        a.action_out = h->action_out_host;
-        a.reward = h->reward_host;
-        a.info = h->info_host;
+        a.slab_format = h->slab_format;
         a.state_copy = h->state_out_host;
         a.obs = h->obs;
         a.obs_dtype = h->obs_dtype;
-        if (int r = launch_step(ctx, &a, st, true, true)) return r;
+        CompactTarget ct;
+        if (h->results_compact) {
+            ct.nibbles = h->nibbles_host;
+            ct.tile_line = h->tile_line_host;
+            ct.summary = h->summary_host;
+            ct.counters = p->d_counters;
+            ct.records = h->records_host;
+            ct.capacity_bytes = h->records_capacity;
+        } else {
+            a.action_out = h->action_out_host;
+            a.reward = h->reward_host;
+            a.info = h->info_host;
+        }
+        if (int r = launch_step(ctx, &a, st, true, true, h->results_compact ? &ct : nullptr)) return r;
         for (int k = 0; k < p->chunks && e == cudaSuccess; k++) e = cudaEventRecord(p->done[slot][k], st);
+        // the caller's stream sees the state this step leaves behind (a later step / encode / reset on it is ordered)
+        if (e == cudaSuccess) e = cudaStreamWaitEvent((cudaStream_t)after_stream, p->done[slot][0], 0);
         return cuda_check(e, "ppad_pipe_step");
     }
     for (int k = 0; k < p->chunks && e == cudaSuccess; k++) {
@@ -323,6 +385,7 @@ int ppad_pipe_step(ppad_pipe *p, const ppad_host_step_args *h, void *after_strea
             a.slab = p->d_slab + (size_t)lo * w;
             a.slab_words = h->slab_words;
             a.n_inj = h->n_inj;
+            a.slab_format = h->slab_format;
         }
         if (e != cudaSuccess) break;
         if (hybrid) {
@@ -355,7 +418,19 @@ int ppad_pipe_step(ppad_pipe *p, const ppad_host_step_args *h, void *after_strea
                                 (size_t)cnt * rec, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaEventRecord(p->done[slot][k], st);
     }
+    for (int k = 0; k < p->chunks && e == cudaSuccess; k++) {
+        if ((int64_t)k * p->chunk >= h->n) break;
+        e = cudaStreamWaitEvent((cudaStream_t)after_stream, p->done[slot][k], 0);
+    }
     return cuda_check(e, "ppad_pipe_step");
+}
+
+int64_t ppad_compact_capacity(const ppad_ctx *ctx, int64_t n)
+{
+    if (!ctx || n < 0) return -1;
+    const int64_t tiles = (n + BLOCK - 1) / BLOCK;
+    const int64_t rec = ppad_state_bytes_ex(ctx->cfg.rows, ctx->cfg.cols, ctx->cfg.orb_bits);
+    return tiles * (((int64_t)BLOCK * (12 + rec) + 127) / 128 * 128);
 }
 
 int ppad_pipe_set_zero_copy(ppad_pipe *p, int32_t enabled)

@@ -23,13 +23,106 @@ struct StepKernelArgs {
     void *final_state;
     void *state_copy;
     uint16_t *combo_log;
+    uint16_t *consumed16;   // [n] skyfall orbs drawn by the cascade, saturating at 65535 (the info byte stops at 255), or NULL
     void *obs;
     int32_t obs_dtype;
     const uint32_t *paths;
     const uint16_t *path_lens;
     int32_t path_words, path_len;
-    int32_t stage_slab;   // 1: the slab is pinned HOST memory (zero copy), 4 words per board: fetch each row once, up front
+    int32_t stage_slab;   // the slab is pinned HOST memory (zero copy): fetch each row once, up front.  1: 4 words per
+                          // board, one uint4 per thread; 2: 3 words per board, the CTA's 3072 contiguous bytes cooperatively
+    // compact result stream (COMPACT instantiations: the host pipe), see include/ppad_b200.h ppad_host_step_args
+    uint32_t *c_nibbles;      // [tiles, 32] words: nibble i of tile t = action (7 = none) | has_record << 3 of board 256 t + i
+    uint32_t *c_tile_line;    // [tiles]: first 128-byte line of the tile's record block
+    uint4 *c_records;         // the line stream
+    uint32_t *c_summary;      // [4]: lines used, tiles, overflow, 0 -- written by the last CTA to finish
+    uint32_t *c_counters;     // DEVICE [2]: next free line, finished tiles; left at 0 by the last CTA
+    uint32_t c_capacity;      // lines the record buffer holds
 };
+
+// Record block of one tile (= CTA of BLOCK boards) in the compact result stream: k records for the boards whose info
+// word is not 0 (a board that was not evaluated, or matched nothing, has reward 0 and info 0), m <= k of them with a
+// fresh episode (FLAG_EPISODE_DONE), in board order:
+//   [k x float64 reward][k x uint32 info][pad to 16 bytes][m x packed state record], padded to 128 bytes.
+template <class G>
+struct CompactLayout {
+    static constexpr int SB = G::STATE_BYTES;
+    static __host__ __device__ constexpr int off_info(int k) { return 8 * k; }
+    static __host__ __device__ constexpr int off_state(int k) { return (12 * k + 15) & ~15; }
+    static __host__ __device__ constexpr int lines(int k, int m) { return (off_state(k) + m * SB + 127) / 128; }
+    static constexpr int MAX_STAGE = 128 * ((8 * BLOCK + 4 * BLOCK + BLOCK * SB + 127) / 128);
+    static constexpr int MAX_STAGE_NO_RESET = 128 * ((8 * BLOCK + 4 * BLOCK + 127) / 128);
+};
+
+// Every thread of the CTA must call this (after its board's step is complete).
+template <class G>
+__device__ __forceinline__ void compact_results(const StepKernelArgs &a, bool valid, const StepOut &o, const State<G> &s)
+{
+    typedef CompactLayout<G> CL;
+    extern __shared__ uint4 c_stage4[];
+    unsigned char *stage = reinterpret_cast<unsigned char *>(c_stage4);
+    __shared__ int c_cnt[2][BLOCK / 32];
+    __shared__ __align__(16) uint32_t c_nib[BLOCK / 8];
+    __shared__ uint32_t c_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool has = valid && o.info != 0;             // reward != 0 implies n_combos != 0
+    const bool done = has && (o.info >> 31) != 0;      // FLAG_EPISODE_DONE: the host wants the fresh board
+    const unsigned bh = __ballot_sync(0xFFFFFFFFu, has), bd = __ballot_sync(0xFFFFFFFFu, done);
+    if (lane == 0) {
+        c_cnt[0][warp] = __popc(bh);
+        c_cnt[1][warp] = __popc(bd);
+    }
+    uint32_t nib = valid ? (((uint32_t)o.action & 7u) | (has ? 8u : 0u)) : 0u;   // action 255 (none) -> 7
+    nib <<= 4 * (lane & 7);
+    nib |= __shfl_xor_sync(0xFFFFFFFFu, nib, 1);
+    nib |= __shfl_xor_sync(0xFFFFFFFFu, nib, 2);
+    nib |= __shfl_xor_sync(0xFFFFFFFFu, nib, 4);
+    if ((lane & 7) == 0) c_nib[warp * 4 + (lane >> 3)] = nib;
+    __syncthreads();
+    int r = __popc(bh & ((1u << lane) - 1u)), rd = __popc(bd & ((1u << lane) - 1u)), k = 0, m = 0;
+#pragma unroll
+    for (int w = 0; w < BLOCK / 32; w++) {
+        const int ch = c_cnt[0][w], cd = c_cnt[1][w];
+        if (w < warp) {
+            r += ch;
+            rd += cd;
+        }
+        k += ch;
+        m += cd;
+    }
+    const int off_info = CL::off_info(k), off_state = CL::off_state(k), lines = CL::lines(k, m);
+    if (tid == 0) {
+        uint32_t base = 0;
+        if (lines) {
+            base = atomicAdd(&a.c_counters[0], (uint32_t)lines);
+            if (base + (uint32_t)lines > a.c_capacity) base = 0xFFFFFFFFu;   // overflow: block dropped, flagged below
+        }
+        c_base = base;
+        a.c_tile_line[blockIdx.x] = base;
+    }
+    if (has) {
+        *reinterpret_cast<double *>(stage + 8 * r) = o.reward;
+        *reinterpret_cast<uint32_t *>(stage + off_info + 4 * r) = o.info;
+    }
+    if (done) StateIO<G>::store(stage + off_state, rd, s.b, s.meta);
+    __syncthreads();
+    const uint32_t base = c_base;
+    if (base != 0xFFFFFFFFu)
+        for (int j = tid; j < lines * 8; j += BLOCK) a.c_records[(size_t)base * 8 + j] = c_stage4[j];
+    if (tid < BLOCK / 32) reinterpret_cast<uint4 *>(a.c_nibbles)[(size_t)blockIdx.x * (BLOCK / 32) + tid] = reinterpret_cast<const uint4 *>(c_nib)[tid];
+    if (tid == 0) {
+        if (base == 0xFFFFFFFFu) a.c_summary[2] = 1u;
+        __threadfence();
+        const uint32_t t = atomicAdd(&a.c_counters[1], 1u);
+        if (t == gridDim.x - 1) {                      // every other CTA claimed its lines before it counted itself
+            const uint32_t used = atomicExch(&a.c_counters[0], 0u);
+            a.c_counters[1] = 0u;
+            a.c_summary[0] = used < a.c_capacity ? used : a.c_capacity;
+            a.c_summary[1] = gridDim.x;
+        }
+    }
+}
+
 
 // The step WITH the one-hot observation, one thread per board.  This variant is bound by the 840 B/board store
 // stream, and keeping all eight warps of a CTA busy (each runs its own boards' cascades in a warp-uniform
@@ -42,8 +135,21 @@ struct StepKernelArgs {
 // AR: the launch has auto_reset set.  Launches without it run an instantiation that does not contain the reset code
 // at all; those with it get the unrolled Philox refill (a Boltzmann-policy rollout resets 29 % of its boards per step:
 // 0.227 ms per 2^20-board step with fp32 obs against 0.286 ms with the plain refill, profiles/ar_bench.py).
-template <class G, bool OBS, bool AR>
-__global__ void __launch_bounds__(BLOCK, (sizeof(typename G::W) == 8 && G::NP == 4) ? 3 : 4) step_obs_kernel(const __grid_constant__ StepKernelArgs a)
+// Resident CTAs per SM the register allocation aims at: 4 (64 registers) for the plain step; the instantiations that
+// carry the auto-reset need more (154 B of spill stores per thread at 64 registers for 5x6) and get 3 (80 registers: no
+// spills), like the widest geometry (6x7 with four 64-bit planes).
+#if !defined(PPAD_MINB_64)
+#define PPAD_MINB_64 4   // 64-bit planes, 3-bit codes (6x7) without auto-reset
+#endif
+template <class G, bool AR>
+constexpr int step_min_ctas()
+{
+    return (AR || (sizeof(typename G::W) == 8 && G::NP == 4)) ? 3 : (sizeof(typename G::W) == 8 ? PPAD_MINB_64 : 4);
+}
+
+// COMPACT: the results leave as the compact stream of compact_results() instead of dense arrays (the host pipe).
+template <class G, bool OBS, bool AR, bool COMPACT = false>
+__global__ void __launch_bounds__(BLOCK, step_min_ctas<G, AR>()) step_obs_kernel(const __grid_constant__ StepKernelArgs a)
 {
     __shared__ ObsShared obs_sh;
     __shared__ uint32_t obs_stream[OBS ? (BLOCK / 32) * ObsGeom<G>::WARP_WORDS : 1];
@@ -69,7 +175,7 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(typename G::W) == 8 && G::NP ==
     }
     const uint32_t *slab = a.slab && valid ? a.slab + (size_t)i * a.p.slab_words : nullptr;
     __shared__ uint4 slab_rows[BLOCK];
-    if (a.stage_slab) {   // kernel-uniform
+    if (a.stage_slab == 1) {   // kernel-uniform
         // Zero copy: the skyfall slab lives in pinned host memory.  The cascade reads its words lazily, which over
         // PCIe is one 4-byte round trip per lane and cascade iteration; fetch the board's whole 16-byte row once
         // instead (512 contiguous bytes per warp, in flight together with the state load) and let the cascade read
@@ -79,6 +185,19 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(typename G::W) == 8 && G::NP ==
             slab = reinterpret_cast<const uint32_t *>(&slab_rows[threadIdx.x]);
         }
         __syncwarp();
+    } else if (a.stage_slab == 2) {
+        // The same for 12-byte rows (SLAB_PLANES3, one group): the CTA's 256 rows are 3072 contiguous, 16-byte aligned
+        // bytes; 192 threads fetch one uint4 each, then every thread reads its three words from shared memory
+        // (stride 3 words: conflict free).
+        const int64_t tile0 = (int64_t)blockIdx.x * BLOCK;
+        const int rows = (int)(a.n - tile0 < BLOCK ? a.n - tile0 : BLOCK);
+        const uint32_t *src = a.slab + (size_t)tile0 * 3;
+        const int w0 = 4 * (int)threadIdx.x;
+        if (w0 + 3 < 3 * rows) slab_rows[threadIdx.x] = __ldg(reinterpret_cast<const uint4 *>(src) + threadIdx.x);
+        else
+            for (int w = w0; w < 3 * rows; w++) reinterpret_cast<uint32_t *>(slab_rows)[w] = __ldg(src + w);
+        __syncthreads();
+        if (slab) slab = reinterpret_cast<const uint32_t *>(slab_rows) + 3 * threadIdx.x;
     }
     // every lane takes part (the cascade loop inside is warp-uniform); lanes past the batch are not live
     Board<G> fin;
@@ -87,11 +206,14 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(typename G::W) == 8 && G::NP ==
                                     a.paths && valid ? a.paths + (size_t)i * a.path_words : nullptr, path_len);
     if (valid) {
         StateIO<G>::store(a.state, i, s.b, s.meta);
-        if (a.action_out) a.action_out[i] = (uint8_t)o.action;
-        if (a.reward) a.reward[i] = o.reward;
-        if (a.info) a.info[i] = o.info;
+        if constexpr (!COMPACT) {
+            if (a.action_out) a.action_out[i] = (uint8_t)o.action;
+            if (a.reward) a.reward[i] = o.reward;
+            if (a.info) a.info[i] = o.info;
+        }
         if (a.final_state) StateIO<G>::store(a.final_state, i, fin, s.meta);
         if (a.state_copy) StateIO<G>::store(a.state_copy, i, s.b, s.meta);
+        if (a.consumed16) a.consumed16[i] = (uint16_t)(o.consumed > 0xFFFF ? 0xFFFF : o.consumed);
     }
     const int64_t warp0 = i - (threadIdx.x & 31);
     if (OBS && warp0 < a.n) {
@@ -99,6 +221,7 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(typename G::W) == 8 && G::NP ==
         emit_obs<G>(s, valid, n_valid, obs_stream + (threadIdx.x >> 5) * ObsGeom<G>::WARP_WORDS, obs_sh,
                     obs_warp_ptr<G>(a.obs, warp0, a.obs_dtype), a.obs_dtype);
     }
+    if constexpr (COMPACT) compact_results<G>(a, valid, o, s);
 }
 
 // T consecutive steps of the in-kernel random policy in one launch: the board stays in registers between
@@ -313,6 +436,7 @@ __global__ void __launch_bounds__(PBLOCK, PPAD_POOL_MINB) step_pool_kernel(const
                 if (!cascading) {
                     if (a.reward) a.reward[i] = 0.0;
                     if (a.info) a.info[i] = it.info();
+                    if (a.consumed16) a.consumed16[i] = 0;
                 }
             }
             int added;
@@ -335,10 +459,11 @@ __global__ void __launch_bounds__(PBLOCK, PPAD_POOL_MINB) step_pool_kernel(const
             const RngKey key = board_key(a.p, a.env0 + own);
             again = cascade_round<G>(it, sd, a.p.cascade_cap, a.p.team,
                                      a.slab ? a.slab + (size_t)own * a.p.slab_words : nullptr, a.p.n_inj, key, a.p.sky,
-                                     a.combo_log ? a.combo_log + (size_t)own * a.p.log_cap : nullptr, a.p.log_cap);
+                                     a.combo_log ? a.combo_log + (size_t)own * a.p.log_cap : nullptr, a.p.log_cap, a.p.slab_fmt);
             if (!again) {
                 if (a.reward) a.reward[own] = it.reward();
                 if (a.info) a.info[own] = it.info();
+                if (a.consumed16) a.consumed16[own] = (uint16_t)(it.cursor > 0xFFFF ? 0xFFFF : it.cursor);
                 if (a.final_state) StateIO<G>::store_planes(a.final_state, own, it.b);   // meta: written by the fill
             }
         }
@@ -362,6 +487,19 @@ template <class G>
 int launch_step_g(const ppad_ctx *ctx, const StepKernelArgs &a, int choice, cudaStream_t st)
 {
     const bool ar = a.p.auto_reset != 0;
+    if (a.c_records) {   // compact result stream (host pipe): one thread per board, with or without the observation
+        typedef CompactLayout<G> CL;
+        const size_t sm = ar ? CL::MAX_STAGE : CL::MAX_STAGE_NO_RESET;
+        const unsigned grid = grid_for(a.n);
+        if (choice == STEP_KERNEL_OBS) {
+            if (ar) step_obs_kernel<G, true, true, true><<<grid, BLOCK, sm, st>>>(a);
+            else step_obs_kernel<G, true, false, true><<<grid, BLOCK, sm, st>>>(a);
+        } else {
+            if (ar) step_obs_kernel<G, false, true, true><<<grid, BLOCK, sm, st>>>(a);
+            else step_obs_kernel<G, false, false, true><<<grid, BLOCK, sm, st>>>(a);
+        }
+        return after_launch("step_obs_kernel<compact>");
+    }
     if (choice == STEP_KERNEL_OBS) {
         if (ar) step_obs_kernel<G, true, true><<<grid_for(a.n), BLOCK, 0, st>>>(a);
         else step_obs_kernel<G, true, false><<<grid_for(a.n), BLOCK, 0, st>>>(a);

@@ -57,6 +57,19 @@ def gather_stats(local):
     return merge_stats(per_rank.cpu())
 
 
+def all_gather_rows(*tensors):
+    """all-gather already sampled replay rows (e.g. RolloutRing.sample): every tensor [k, ...] -> [world * k, ...]"""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return tuple(t.contiguous() for t in tensors)
+    out = []
+    for p in tensors:
+        p = p.contiguous()
+        buf = [torch.empty_like(p) for _ in range(dist.get_world_size())]
+        dist.all_gather(buf, p)
+        out.append(torch.cat(buf))
+    return tuple(out)
+
+
 def gather_replay_sample(state, action, reward, k, generator=None):
     """Uniformly sample k rows of this rank's (state, action, reward) slab and all-gather them:
     returns (state [world*k, words] int32, action [world*k] uint8, reward [world*k] float64).

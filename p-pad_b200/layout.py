@@ -75,3 +75,67 @@ def pack_slab(orbs):
     pad[:, :s] = orbs & 15
     pad = pad.reshape(n, words, 8)
     return np.ascontiguousarray((pad << (4 * np.arange(8, dtype=np.uint32))).sum(axis=2, dtype=np.uint32))
+
+
+def pack_slab_planes3(orbs):
+    """uint8 [n, S] orb sequence (types 0..6) -> uint32 [n, 3 * ceil(S / 32)] bit-sliced slab (PPAD_SLAB_PLANES3):
+    bit (d & 31) of word 3 * (d >> 5) + j is bit j of orb d.  12 bytes per 32 orbs."""
+    orbs = np.asarray(orbs, np.uint8)
+    n, s = orbs.shape
+    groups = max(1, (s + 31) // 32)
+    pad = np.zeros((n, groups * 32), np.uint32)
+    pad[:, :s] = orbs & 7
+    pad = pad.reshape(n, groups, 32)
+    shifts = np.arange(32, dtype=np.uint32)
+    out = np.zeros((n, groups, 3), np.uint32)
+    for j in range(3):
+        out[:, :, j] = (((pad >> np.uint32(j)) & np.uint32(1)) << shifts).sum(axis=2, dtype=np.uint32)
+    return np.ascontiguousarray(out.reshape(n, groups * 3))
+
+
+TILE = 256   # boards per tile of the compact result stream (= CTA size of the step kernel)
+
+
+def decode_compact(n, words, nibbles, tile_line, records, summary):
+    """Decode the compact result stream of ppad_pipe_step (include/ppad_b200.h: ppad_host_step_args) into dense arrays.
+    nibbles uint32 [tiles * 32], tile_line uint32 [tiles], records uint8 [capacity], summary uint32 [4]; words = uint32
+    words per packed state record.  Returns dict(action uint8 [n], reward float64 [n], info uint32 [n],
+    reset_index int64 [m], reset_state uint32 [m, words], lines int).  A format decoder: no game logic."""
+    if int(summary[2]):
+        raise RuntimeError("compact result stream overflowed its record buffer")
+    tiles = (n + TILE - 1) // TILE
+    nb = np.ascontiguousarray(nibbles[:tiles * 32]).view(np.uint8)
+    nib = np.empty(tiles * TILE, np.uint8)
+    nib[0::2] = nb & 15
+    nib[1::2] = nb >> 4
+    nib = nib[:n]
+    action = (nib & 7).astype(np.uint8)
+    action[action == 7] = 255
+    has = (nib >> 3).astype(bool)
+    reward = np.zeros(n, np.float64)
+    info = np.zeros(n, np.uint32)
+    idx = np.flatnonzero(has)
+    out = dict(action=action, reward=reward, info=info, lines=int(summary[0]),
+               reset_index=np.zeros(0, np.int64), reset_state=np.zeros((0, words), np.uint32))
+    if idx.size == 0:
+        return out
+    tile = idx // TILE
+    k = np.bincount(tile, minlength=tiles).astype(np.int64)           # records per tile
+    first = np.concatenate([[0], np.cumsum(k)[:-1]])                  # index of each tile's first record in idx
+    r = np.arange(idx.size, dtype=np.int64) - first[tile]             # rank within the tile
+    base = tile_line[:tiles].astype(np.int64) * 128                   # byte offset of each tile's block
+    rec = np.ascontiguousarray(records)
+    reward[idx] = rec.view(np.float64)[base[tile] // 8 + r]
+    inf = rec.view(np.uint32)[(base[tile] + 8 * k[tile]) // 4 + r]
+    info[idx] = inf
+    done = (inf >> 31) != 0
+    if done.any():
+        didx, dtile = idx[done], tile[done]
+        m = np.bincount(dtile, minlength=tiles).astype(np.int64)
+        dfirst = np.concatenate([[0], np.cumsum(m)[:-1]])
+        rd = np.arange(didx.size, dtype=np.int64) - dfirst[dtile]
+        off_state = (12 * k[dtile] + 15) // 16 * 16
+        w0 = (base[dtile] + off_state) // 4 + rd * words
+        out["reset_index"] = didx
+        out["reset_state"] = rec.view(np.uint32)[w0[:, None] + np.arange(words)[None, :]]
+    return out

@@ -143,12 +143,13 @@ int hostcore_step_batch(const ppad_config *cfg, int64_t n, uint64_t env0, uint32
                         uint8_t *prev, uint16_t *moves, const uint8_t *actions, int eval_moves, int auto_reset,
                         int max_moves, const uint32_t *slab, int slab_words, int n_inj, uint8_t *action_out,
                         double *reward, uint32_t *info, int8_t *final_boards, uint16_t *combo_log, int log_cap,
-                        const uint32_t *paths, int path_words, const uint16_t *path_lens)
+                        const uint32_t *paths, int path_words, const uint16_t *path_lens, int slab_format)
 {
     StepParams p;
     int geom;
     if (int r = build_params(*cfg, p, geom, g_err)) return r;
     p.key.step = step;
+    p.slab_fmt = slab_format;
     p.eval_moves = eval_moves;
     p.auto_reset = auto_reset;
     p.max_moves = max_moves;

@@ -39,14 +39,17 @@ def _p(a):
 
 
 def step_batch(cfg, boards, fingers, prev, moves=None, actions=None, eval_moves=True, auto_reset=False,
-               max_moves=0, inj=None, env0=0, step=0, want_final=False, log_cap=0, paths=None, path_lens=None):
+               max_moves=0, inj=None, env0=0, step=0, want_final=False, log_cap=0, paths=None, path_lens=None,
+               slab_format=0):
     n = boards.shape[0]
     action_out = np.zeros(n, np.uint8)
     reward = np.zeros(n, np.float64)
     info = np.zeros(n, np.uint32)
     final = np.zeros_like(boards) if want_final else None
     log = np.zeros((n, log_cap), np.uint16) if log_cap else None
-    slab = ppad_b200.layout.pack_slab(inj) if inj is not None else None
+    slab = None
+    if inj is not None:
+        slab = ppad_b200.layout.pack_slab_planes3(inj) if slab_format == 1 else ppad_b200.layout.pack_slab(inj)
     if actions is not None:
         actions = np.ascontiguousarray(actions, np.uint8)
     packed = None
@@ -61,7 +64,8 @@ def step_batch(cfg, boards, fingers, prev, moves=None, actions=None, eval_moves=
         C.byref(cfg), C.c_int64(n), C.c_uint64(env0), C.c_uint32(step), _p(boards), _p(fingers), _p(prev), _p(moves),
         _p(actions), int(bool(eval_moves)), int(bool(auto_reset)), int(max_moves), _p(slab),
         slab.shape[1] if slab is not None else 0, inj.shape[1] if inj is not None else 0, _p(action_out), _p(reward),
-        _p(info), _p(final), _p(log), log_cap, _p(packed), packed.shape[1] if packed is not None else 0, _p(path_lens))
+        _p(info), _p(final), _p(log), log_cap, _p(packed), packed.shape[1] if packed is not None else 0, _p(path_lens),
+        int(slab_format))
     if r:
         raise RuntimeError(lib().hostcore_last_error().decode())
     return action_out, reward, info, final, log

@@ -38,7 +38,7 @@ def test_header_cites_the_reference_for_every_entry_point():
     # each prototype's comment names the reference file it replaces
     for name in declared_functions():
         if name in ("ppad_destroy", "ppad_abi_version", "ppad_strerror", "ppad_last_error", "ppad_state_bytes",
-                    "ppad_launch_count", "ppad_replay_sample", "ppad_unpack") or name.startswith("ppad_pipe_"):
+                    "ppad_launch_count", "ppad_replay_sample", "ppad_unpack", "ppad_compact_capacity") or name.startswith("ppad_pipe_"):
             continue      # helpers of an entry point that carries the citation (the pipe: its struct comment)
         idx = HEADER.index(name + "(")
         assert re.search(r"\.py:\d+", HEADER[max(0, idx - 2500):idx]), name
@@ -52,7 +52,12 @@ def test_constants_agree(cabi):
         assert henum("PPAD_FLAG_" + flag) == getattr(cabi, "FLAG_" + flag) == getattr(orc, "FLAG_" + flag)
     assert [henum("PPAD_" + a) for a in ("UP", "DOWN", "LEFT", "RIGHT", "PASS")] == [0, 1, 2, 3, 4]
     assert C.sizeof(cabi.Config) == 6 * 4 + 2 * 8 * 4 + 8 * 8 + 10 * 8 + 8 + 2 * 4   # ... seed, orb_bits, reserved
-    assert cabi.lib().ppad_abi_version() == int(re.search(r"#define PPAD_ABI_VERSION\s+(\d+)", HEADER).group(1)) == 2
+    assert cabi.lib().ppad_abi_version() == int(re.search(r"#define PPAD_ABI_VERSION\s+(\d+)", HEADER).group(1)) == cabi.ABI_VERSION == 3
+    for name in ("SLAB_NIBBLES", "SLAB_PLANES3"):
+        assert henum("PPAD_" + name) == getattr(cabi, name)
+    # struct sizes the ctypes mirrors must agree on (a mismatch would shift every later field)
+    assert C.sizeof(cabi.StepArgs) == 8 + 8 + 4 * 4 + 3 * 8 + 2 * 4 + 6 * 8 + 4 + 4 + 8 + 2 * 4 + 2 * 8 + 2 * 4 + 2 * 4 + 8
+    assert C.sizeof(cabi.HostStepArgs) % 8 == 0
     assert cabi.lib().ppad_state_bytes(5, 6) == 16 and cabi.lib().ppad_state_bytes(6, 7) == 32
     assert cabi.lib().ppad_state_bytes(4, 4) == -1 and cabi.lib().ppad_state_bytes(4, 5) == 16
 
@@ -96,3 +101,26 @@ def test_config_validation_messages_match_the_reference(cabi):
         mutate(cfg)
         assert cabi.lib().ppad_create(C.byref(cfg), 0, C.byref(handle)) == status
         assert msg in cabi.lib().ppad_last_error(), cabi.lib().ppad_last_error()
+
+
+def test_ctypes_struct_layouts_match_the_c_header(cabi, tmp_path):
+    """Compile include/ppad_b200.h with gcc (the header is plain C) and compare sizeof / offsetof of every struct with
+    the ctypes mirrors: a drifted field would silently shift every later argument."""
+    import subprocess
+    structs = {"ppad_config": cabi.Config, "ppad_step_args": cabi.StepArgs, "ppad_host_step_args": cabi.HostStepArgs,
+               "ppad_policy_args": cabi.PolicyArgs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "ppad_b200.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)

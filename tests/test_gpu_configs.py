@@ -123,12 +123,12 @@ def test_config3_7x6_smart_data_batched(pb):
 
 
 def test_config4_boltzmann_rollout_with_replay_and_stats(pb):
-    from ppad_b200.replay import ReplayBuffer
+    from ppad_b200.replay import RolloutRing
     from ppad_b200.rollout import policy_rollout
     n, rows, cols, T = 1 << 18, 5, 6, 24
     env = pb.BatchedPAD(n, rows, cols, seed=31, env0=5 * n)          # as rank 5 of a sharded job
     env.reset(step=0)
-    rb = ReplayBuffer(env, 4 * n)
+    rb = RolloutRing(env, 4)
     gen = torch.Generator(device=env.device).manual_seed(3)
     log = []
 
@@ -144,8 +144,8 @@ def test_config4_boltzmann_rollout_with_replay_and_stats(pb):
 
     res = policy_rollout(env, q_fn, T, policy='boltzmann', beta=1e-3, epsilon=0.1, max_moves=10, replay=rb,
                          stats_every=8)
-    assert rb.size == 4 * n and rb.cursor == (T * n) % (4 * n) and res["episodes"] > n      # every env finished >= 1 episode
-    assert len(res["stats"]) == 3 and res["stats"][-1]["boards"] == n
+    assert rb.size == 4 * n and rb.pushed == T and res["episodes"] > n      # every env finished >= 1 episode
+    assert len(res["stats"]) == 3 and res["stats"][-1]["boards"] == 8 * n   # a window of 8 steps
     # replay the recorded steps through the oracle with the actions the kernel selected: the env step itself,
     # incl. auto-reset boards and rewards, is bit-exact; (action selection is checked in test_gpu_dropin)
     ocfg = orc.make_cfg(rows, cols, True, seed=31)
@@ -169,3 +169,81 @@ def test_config4_boltzmann_rollout_with_replay_and_stats(pb):
     s, a, r, obs = rb.sample(4096, with_obs='f32')
     assert obs.shape == (4096, rows, cols, 7) and bool((a <= 4).all())
     assert bool((r[a != 4] == 0).all())                                  # only passes carry reward
+
+
+@pytest.mark.parametrize("rows,cols,n,obs,ctas", [(5, 6, (1 << 16) + 77, 'f32', 0), (6, 7, 20_011, 'u8', 4), (5, 6, 3000, None, 3)])
+def test_fused_policy_step_equals_select_step_push(pb, rows, cols, n, obs, ctas):
+    """ppad_policy_step (one kernel for select -> ring push -> step with auto-reset -> obs -> stats)
+    against the separate entry points it fuses, every step of a 30-step rollout: actions = ppad_select_actions, step =
+    ppad_step, and the ring rows / discounted returns / statistics restated on the host from those outputs (the
+    reference's discount: agent/utils.py:22-51 via orc.discount)."""
+    from ppad_b200.replay import RolloutRing, RolloutStats
+    from ppad_b200 import dist as pdist
+    T, ring_steps, max_moves, gamma = 30, 8, 6, 0.9
+    env = pb.BatchedPAD(n, rows, cols, seed=41, env0=7 * n)
+    env.reset(step=0)
+    ref = pb.BatchedPAD(n, rows, cols, seed=41, env0=7 * n)
+    ref.state.copy_(env.state)
+    ring = RolloutRing(env, ring_steps, gamma=gamma, log10=False)
+    stats = RolloutStats(env)
+    gen = torch.Generator(device=env.device).manual_seed(5)
+    # host restatement of the ring and the statistics
+    h_state = np.zeros((ring_steps * n, env.words), np.int32)
+    h_action = np.zeros(ring_steps * n, np.uint8)
+    h_reward = np.zeros(ring_steps * n, np.float64)
+    tot = np.zeros(40)
+    out = None
+    for t in range(T):
+        q = torch.randn((n, 5), device=env.device, generator=gen) * 1000
+        q[:, 4] -= 800
+        step_index = env.step_index
+        before = ref.state.clone()
+        moves_before = ref.get_state().moves.cpu().numpy().view(np.uint16).astype(np.int64)
+        acts = ref.select_actions(q, method='boltzmann', beta=1e-3, epsilon=0.1, max_moves=max_moves, step=step_index)
+        want = ref.step(acts, auto_reset=True, obs=obs, step=step_index)
+        out = env.policy_step(q, method='boltzmann', beta=1e-3, epsilon=0.1, max_moves=max_moves, obs=obs, ring=ring,
+                              stats=stats, out=out, ctas_per_sm=ctas)
+        assert torch.equal(out.action, want.action) and torch.equal(out.info, want.info), t
+        assert torch.equal(out.reward.view(torch.int64), want.reward.view(torch.int64)), t
+        assert torch.equal(env.state, ref.state), t
+        if obs:
+            assert torch.equal(out.obs, want.obs), t
+        # ring rows of this step + discounted returns of the episodes that ended (only rows still in the ring)
+        a = want.action.cpu().numpy()
+        r = want.reward.cpu().numpy()
+        base = (t % ring_steps) * n
+        h_state[base:base + n] = before.cpu().numpy()
+        h_action[base:base + n] = a
+        h_reward[base:base + n] = r
+        for i in np.flatnonzero((a == 4) & (r > 0)):
+            L = int(moves_before[i])
+            disc = orc.discount(np.array([0.0] * L + [r[i]]), gamma, log10=False)      # the reference's reverse scan
+            for j in range(1, min(L, ring_steps - 1, t) + 1):
+                h_reward[((t - j) % ring_steps) * n + i] = disc[L - j]
+        vec = pdist.local_stats(want.reward, want.info).cpu().numpy()
+        info = want.info.cpu().numpy().view(np.uint32)
+        ev = a == 4
+        vec[8:24] = np.bincount(np.minimum((info[ev] >> 8) & 0xFF, 15), minlength=16)   # histograms: evaluated boards only
+        vec[24:40] = np.bincount(np.minimum(info[ev] & 0xFF, 15), minlength=16)
+        mx = max(tot[3], vec[3])
+        tot += vec
+        tot[3] = mx
+    assert ring.pushed == T and ring.size == ring_steps * n
+    assert np.array_equal(ring.state.cpu().numpy(), h_state) and np.array_equal(ring.action.cpu().numpy(), h_action)
+    assert np.array_equal(bits(ring.reward.cpu().numpy()), bits(h_reward))
+    got = stats.vector().cpu().numpy()
+    assert np.array_equal(np.delete(got, 2), np.delete(tot, 2)), (got, tot)
+    assert abs(got[2] - tot[2]) <= tot[1] / 1024.0                      # the reward sum is kept in 1/1024 fixed point
+    assert got[6] > n and got[0] == T * n                               # every board finished episodes
+    # log10 variant: the pass row holds log10(r), the earlier rows its discounted values (np.log10 vs CUDA log10: 1 ulp)
+    ring2 = RolloutRing(env, ring_steps, gamma=gamma, log10=True)
+    q = torch.randn((n, 5), device=env.device, generator=gen) * 1000
+    q[:, 4] += 5000                                                     # everybody passes
+    o2 = env.policy_step(q, method='max', max_moves=max_moves, ring=ring2)
+    rr = o2.reward.cpu().numpy()
+    got = ring2.reward.cpu().numpy()[:n]
+    pos = rr > 0
+    assert (o2.action == 4).all() and pos.any()
+    assert np.allclose(got[pos], np.log10(rr[pos]), rtol=4e-16, atol=0) and (got[~pos] == 0).all()
+    s, a, r, ob = ring2.sample(512, with_obs='u8')
+    assert ob.shape == (512, rows, cols, 7) and bool((a == 4).all())

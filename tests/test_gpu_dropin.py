@@ -447,6 +447,142 @@ def test_host_pipe_equals_device_step(pb, rows, cols, n, zero_copy):
     assert torch.equal(env.state, ref.state)
 
 
+@pytest.mark.parametrize("slab_format", ["planes3", "nibbles"])
+@pytest.mark.parametrize("rows,cols,n", [(5, 6, 100_000 + 37), (6, 7, 33_333), (5, 6, 200), (4, 5, 256), (5, 6, 1)])
+def test_host_pipe_compact_results_equal_device_step(pb, rows, cols, n, slab_format):
+    """The compact result stream of ppad_pipe_step (action nibbles + records only for boards whose info word is not 0 +
+    the fresh boards of finished episodes) decodes to exactly what ppad_step writes as dense arrays; the host can follow
+    the boards from the actions alone."""
+    rng = np.random.default_rng(n + rows)
+    ref = pb.BatchedPAD(n, rows, cols, seed=23, env0=5)
+    ref.reset(step=0)
+    env = pb.BatchedPAD(n, rows, cols, seed=23, env0=5)
+    env.state.copy_(ref.state)
+    pipe = env.host_pipe(slab_orbs=32, compact=True, slab_format=slab_format)
+    assert pipe.slab.shape[1] == (3 if slab_format == "planes3" else 4)
+    pack = pb.layout.pack_slab_planes3 if slab_format == "planes3" else pb.layout.pack_slab
+    obs = torch.zeros((n, rows, cols, 7), dtype=torch.float32, device=env.device)
+    mirror = pb.layout.unpack_state(ref.state.cpu().numpy().view(np.uint32), rows, cols)   # host copy of boards, fingers
+    hb, hf = mirror[0].copy(), mirror[1].copy()
+    total_records = 0
+    for t in range(1, 8):
+        inj = rng.integers(0, 6, size=(n, 32)).astype(np.uint8)
+        acts = rng.integers(0, 5, size=n).astype(np.uint8)
+        if t == 5:
+            acts[: n // 2] = 4                      # many passes: many resets, many state records
+        pipe.slab.copy_(torch.from_numpy(pack(inj).view(np.int32)))
+        pipe.actions.copy_(torch.from_numpy(acts))
+        use_actions = t % 2 == 1
+        auto_reset = t % 3 != 0
+        with_obs = t != 4
+        pipe.step(use_actions=use_actions, eval_moves=(t != 6), auto_reset=auto_reset, max_moves=3,
+                  obs=obs if with_obs else None, step=t)
+        want = ref.step(acts if use_actions else None, eval_moves=(t != 6), auto_reset=auto_reset, max_moves=3,
+                        injected=inj, obs='f32', step=t)
+        got = pipe.results()
+        assert torch.equal(env.state, ref.state)
+        assert np.array_equal(got["action"], want.action.cpu().numpy()), t
+        assert np.array_equal(got["info"], want.info.cpu().numpy().view(np.uint32)), t
+        assert np.array_equal(bits(got["reward"]), bits(want.reward.cpu().numpy())), t
+        if with_obs:
+            assert torch.equal(obs, want.obs)
+        # the host mirror: apply the accepted moves (action 0..3 and not REJECTED), adopt the fresh boards of resets
+        rejected = ((got["info"] >> 24) & 1).astype(bool)
+        a = got["action"].astype(np.int64)
+        mv = (a < 4) & ~rejected
+        dr = np.array([-1, 1, 0, 0, 0])[np.minimum(a, 4)] * mv
+        dc = np.array([0, 0, -1, 1, 0])[np.minimum(a, 4)] * mv
+        i = np.arange(n)
+        r0, c0 = hf[:, 0].copy(), hf[:, 1].copy()
+        r1, c1 = r0 + dr, c0 + dc
+        tmp = hb[i, r0, c0].copy()
+        hb[i, r0, c0] = hb[i, r1, c1]
+        hb[i, r1, c1] = tmp
+        hf[:, 0], hf[:, 1] = r1, c1
+        done = ((got["info"] >> 31) & 1).astype(bool)
+        assert np.array_equal(np.flatnonzero(done), got["reset_index"])
+        if done.any():
+            fb, ff, _, _ = pb.layout.unpack_state(got["reset_state"], rows, cols)
+            hb[got["reset_index"]], hf[got["reset_index"]] = fb, ff
+        st = ref.get_state()
+        assert np.array_equal(hb, st.boards.cpu().numpy()) and np.array_equal(hf, st.fingers.cpu().numpy()), t
+        # bytes: 4 bits per board + 12 bytes per record (+ states of resets), line granular
+        k = int((got["info"] != 0).sum())
+        total_records += k
+        assert got["lines"] * 128 >= 12 * k + 4 * env.words * int(done.sum())
+        assert got["lines"] * 128 <= 12 * k + 4 * env.words * int(done.sum()) + pipe.tiles * (128 + 16)
+        assert pipe.d2h_bytes() == pipe.tiles * 128 + pipe.tiles * 4 + 16 + got["lines"] * 128
+    assert total_records > 0
+    # two steps in flight with two buffer sets
+    pipe2 = env.host_pipe(slab_orbs=32, compact=True, slab_format=slab_format, depth=2)
+    for b in pipe2.buffers:
+        b.slab.copy_(pipe.slab)
+    pipe2.step(eval_moves=True, step=20, wait=False, buf=0)
+    pipe2.step(eval_moves=True, step=21, wait=False, buf=1)
+    pipe2.wait(0), pipe2.wait(1)
+    w20 = ref.step(None, eval_moves=True, injected=(pipe.slab.to(ref.device), 32), step=20, slab_format=slab_format)
+    r20 = w20.reward.cpu().numpy().copy()
+    w21 = ref.step(None, eval_moves=True, injected=(pipe.slab.to(ref.device), 32), step=21, slab_format=slab_format)
+    assert np.array_equal(bits(pipe2.results(0)["reward"]), bits(r20))
+    assert np.array_equal(bits(pipe2.results(1)["reward"]), bits(w21.reward.cpu().numpy()))
+    assert torch.equal(env.state, ref.state)
+    # work queued on torch's stream after a pipe step is ordered behind it (ADVICE r1: no join() needed)
+    pipe2.step(eval_moves=True, step=22, wait=False, buf=0)
+    after = env.encode_obs('u8')
+    ref.step(None, eval_moves=True, injected=(pipe.slab.to(ref.device), 32), step=22, slab_format=slab_format)
+    assert torch.equal(after, ref.encode_obs('u8'))
+    pipe2.wait(0)
+
+
+def test_compact_pipe_refuses_what_it_cannot_do(pb):
+    env = pb.BatchedPAD(1000, seed=1)
+    env.reset(step=0)
+    with pytest.raises(pb._cabi.PPADError, match="zero-copy"):
+        env.host_pipe(compact=True, zero_copy=False).step(eval_moves=True)
+    with pytest.raises(pb._cabi.PPADError, match="orb_bits = 3"):
+        wide = pb.BatchedPAD(1000, seed=1, orb_bits=4)
+        wide.reset(step=0)
+        wide.host_pipe(compact=True, slab_format="planes3").step(eval_moves=True)
+
+
+def test_replay_push_larger_than_the_ring_keeps_the_last_rows(pb):
+    """a push of more rows than the ring holds must not let two rows share a slot."""
+    from ppad_b200.replay import ReplayBuffer
+    n, cap = 10_000, 777
+    env = pb.BatchedPAD(n, seed=2)
+    env.reset(step=0)
+    rb = ReplayBuffer(env, cap)
+    action = (torch.arange(n, device=env.device) % 5).to(torch.uint8)
+    reward = torch.arange(n, device=env.device, dtype=torch.float64)
+    rb.push(env.state, action, reward)
+    assert rb.size == cap
+    # ring slot (i % cap) holds row i of the last `cap` rows, all three fields from the SAME row
+    rows = torch.arange(n - cap, n, device=env.device)
+    slots = rows % cap
+    assert torch.equal(rb.reward[slots], reward[rows]) and torch.equal(rb.action[slots], action[rows])
+    assert torch.equal(rb.state[slots], env.state[rows])
+    keep = (torch.arange(n, device=env.device) % 3 == 0).to(torch.uint8)
+    rb2 = ReplayBuffer(env, 100)
+    kept = rb2.push(env.state, action, reward, keep=keep)
+    idx = torch.nonzero(keep).flatten()[-100:]
+    assert kept == int(keep.sum()) and set(rb2.reward.cpu().tolist()) == set(reward[idx].cpu().tolist())
+
+
+def test_fingers_off_the_board_are_clamped_and_flagged(pb):
+    """a finger outside the board must not spill into the other meta fields."""
+    env = pb.BatchedPAD(4, seed=2)
+    boards = np.zeros((4, 5, 6), np.int64)
+    fingers = np.array([[0, 0], [-1, 3], [2, 9], [7, -2]], np.int64)
+    flags = env.set_state(boards, fingers).cpu().numpy()
+    assert list(flags & 1) == [0, 1, 1, 1]
+    st = env.get_state()
+    assert st.fingers.cpu().numpy().tolist() == [[0, 0], [0, 3], [2, 5], [4, 0]]
+    assert (st.prev.cpu().numpy() == 4).all() and (st.moves.cpu().numpy() == 0).all()
+    fl = env.reset(fingers=fingers.astype(np.int32), step=1).cpu().numpy()
+    assert list(fl & 1) == [0, 1, 1, 1]
+    assert env.get_state().fingers.cpu().numpy().tolist() == [[0, 0], [0, 3], [2, 5], [4, 0]]
+
+
 @pytest.mark.parametrize("rows,cols", [(5, 6), (6, 7)])
 def test_reference_rng_mode_replays_the_references_own_episodes(pb, rows, cols):
     """PAD(rng='reference'): the draws come from Python's global Mersenne Twister in the reference's order, so

@@ -132,7 +132,7 @@ def test_episode_golden_vectors(pb, tag, rows, cols):
 
 @pytest.mark.parametrize("rows,cols", [(4, 5), (5, 6), (6, 7)])
 @pytest.mark.parametrize("mode", ["injected", "philox", "injected_short", "no_skyfall", "wide_injected", "wide_philox",
-                                  "wide3_philox"])
+                                  "wide3_philox", "planes3_injected", "planes3_short"])
 def test_step_fuzz_vs_oracle(pb, rows, cols, mode):
     """wide_*: the 4-bit kernels with all ten orb types of game.py:236-246 in the boards, the skyfall rates and the
     injected sequences; wide3_philox: the 4-bit kernels on a workload of the 3-bit ones"""
@@ -155,7 +155,8 @@ def test_step_fuzz_vs_oracle(pb, rows, cols, mode):
     moves = np.zeros(n, np.uint16)
     assert not env.set_state(boards, fingers).any()
     S = {"injected": 256, "philox": 0, "injected_short": 8, "no_skyfall": 16, "wide_injected": 256, "wide_philox": 0,
-         "wide3_philox": 0}[mode]
+         "wide3_philox": 0, "planes3_injected": 96, "planes3_short": 40}[mode]
+    fmt = 'planes3' if mode.startswith("planes3") else 'nibbles'     # PPAD_SLAB_PLANES3: bit-sliced 3-bit slab
     for t in range(steps):
         inj = rng.integers(0, 10 if all10 else 6, size=(n, S)).astype(np.uint8) if S else None
         actions = None if t % 3 == 2 else rng.integers(0, 5, size=n).astype(np.uint8)
@@ -164,8 +165,9 @@ def test_step_fuzz_vs_oracle(pb, rows, cols, mode):
         kw = dict(eval_moves=(t % 4 != 3), auto_reset=(t % 2 == 0), max_moves=5)
         a0, r0, i0, f0 = orc.step_batch(ocfg, boards, fingers, prev, moves, actions=actions, inj=inj,
                                         env0=(1 << 32) - 1000, step=t, want_final=True, **kw)
-        o = env.step(actions, injected=inj, step=t, want_final=True, obs='u8', **kw)
+        o = env.step(actions, injected=inj, step=t, want_final=True, obs='u8', slab_format=fmt, want_consumed=True, **kw)
         st = env.get_state()
+        assert np.array_equal(o.consumed.cpu().numpy().view(np.uint16) & 0xFF, (i0 >> 16) & 0xFF) or (((i0 >> 16) & 0xFF) == 255).any()
         assert np.array_equal(o.action.cpu().numpy(), a0), t
         assert np.array_equal(st.boards.cpu().numpy(), boards) and np.array_equal(st.fingers.cpu().numpy(), fingers), t
         assert np.array_equal(st.prev.cpu().numpy(), prev) and np.array_equal(st.moves.cpu().numpy().view(np.uint16), moves), t

@@ -58,10 +58,11 @@ def test_cancel_and_drop_fuzz(rows, cols, kind, orb_bits):
 
 @pytest.mark.parametrize("rows,cols", [(4, 5), (5, 6), (6, 7)])
 @pytest.mark.parametrize("mode", ["injected", "philox", "injected_short", "no_skyfall", "wide_injected", "wide_philox",
-                                  "wide3_injected"])
+                                  "wide3_injected", "planes3_injected", "planes3_short"])
 def test_step_batch_fuzz(rows, cols, mode):
     """wide_*: the 4-bit kernels with all ten orb types (skyfall rates and injected orbs for types 7..9);
-    wide3_injected: the 4-bit kernels on a workload the 3-bit kernels also run"""
+    wide3_injected: the 4-bit kernels on a workload the 3-bit kernels also run;
+    planes3_*: the injected skyfall as a bit-sliced 3-bit slab (PPAD_SLAB_PLANES3) of 96 / 40 orbs"""
     rng = np.random.default_rng(1000 + rows + len(mode))
     n, steps = 3000, 12
     wide = mode.startswith("wide")
@@ -77,7 +78,8 @@ def test_step_batch_fuzz(rows, cols, mode):
     moves = np.zeros(n, np.uint16)
     mine = [boards.copy(), fingers.copy(), prev.copy(), moves.copy()]
     S = {"injected": 256, "philox": 0, "injected_short": 8, "no_skyfall": 16, "wide_injected": 256, "wide_philox": 0,
-         "wide3_injected": 256}[mode]
+         "wide3_injected": 256, "planes3_injected": 96, "planes3_short": 40}[mode]
+    fmt = 1 if mode.startswith("planes3") else 0
     top = 10 if sky else 6
     seen_flags = 0
     for t in range(steps):
@@ -91,7 +93,7 @@ def test_step_batch_fuzz(rows, cols, mode):
         kw = dict(actions=actions, eval_moves=(t % 4 != 3), auto_reset=(t % 2 == 0), max_moves=5,
                   inj=inj, env0=77777, step=t, want_final=True)
         a0, r0, i0, f0 = orc.step_batch(ocfg, boards, fingers, prev, moves, **kw)
-        a1, r1, i1, f1, _ = hc.step_batch(cfg, *mine, **kw)
+        a1, r1, i1, f1, _ = hc.step_batch(cfg, *mine, slab_format=fmt, **kw)
         assert np.array_equal(a0, a1), t
         assert np.array_equal(boards, mine[0]) and np.array_equal(fingers, mine[1]), t
         assert np.array_equal(prev, mine[2]) and np.array_equal(moves, mine[3]), t
@@ -102,6 +104,27 @@ def test_step_batch_fuzz(rows, cols, mode):
     assert seen_flags & orc.FLAG_REJECTED and seen_flags & orc.FLAG_BAD_ACTION and seen_flags & orc.FLAG_EPISODE_DONE
     if mode == "injected_short":
         assert seen_flags & orc.FLAG_SKYFALL_EXHAUSTED
+
+
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_injected_codes_that_are_no_orb_type_are_flagged(fmt):
+    """a nibble of 7 (3-bit context) writes an empty cell, 8..15 alias: flagged, never silent."""
+    rng = np.random.default_rng(5)
+    n = 512
+    ocfg = orc.make_cfg(5, 6, True, seed=3)
+    cfg = hc.cfg_from_oracle(ocfg)
+    boards = np.zeros((n, 5, 6), np.int8)
+    boards[:, ::2, :] = 1                                  # rows of one colour: every board cascades and draws orbs
+    args = lambda: (boards.copy(), np.zeros((n, 2), np.int32), np.full(n, 4, np.uint8), np.zeros(n, np.uint16))
+    good = rng.integers(0, 6, size=(n, 64)).astype(np.uint8)
+    bad = good.copy()
+    bad[::2, 3] = 7                                        # the 4th orb drawn: every board draws at least 18
+    passes = np.full(n, 4, np.uint8)
+    _, _, i_good, _, _ = hc.step_batch(cfg, *args(), actions=passes, inj=good, slab_format=fmt)
+    _, _, i_bad, _, _ = hc.step_batch(cfg, *args(), actions=passes, inj=bad, slab_format=fmt)
+    assert not ((i_good >> 24) & orc.FLAG_UNSUPPORTED_ORB).any()
+    assert ((i_bad[::2] >> 24) & orc.FLAG_UNSUPPORTED_ORB).all()
+    assert not ((i_bad[1::2] >> 24) & orc.FLAG_UNSUPPORTED_ORB).any()
 
 
 @pytest.mark.parametrize("rows,cols", [(4, 5), (5, 6), (6, 7)])
