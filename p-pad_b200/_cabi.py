@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libppad_b200.so")
+# PPAD_B200_LIB: an alternative build of the same library (profiles/variants.py A/B experiments)
+LIB_PATH = os.environ.get("PPAD_B200_LIB") or os.path.join(_HERE, "libppad_b200.so")
 MAX_TEAM_UNITS = 8
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3

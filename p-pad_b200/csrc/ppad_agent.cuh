@@ -57,14 +57,16 @@ __device__ __forceinline__ int select_action(const float *q, int finger, int las
         p[a] = ((allowed >> a) & 1) ? expf(beta * (qm[a] - best)) : 0.f;
         sum += p[a];
     }
-    const double u = (double)x1 * (1.0 / 4294967296.0);
-    double cdf = 0.0;
+    // np.random.choice: first a with cdf[a] > u, cdf = cumsum(p / sum).  Compared as cumsum(p) > u * sum in float64
+    // (the same predicate up to the last rounding of the division): no float64 divisions on the hot path.
+    const double us = (double)x1 * (1.0 / 4294967296.0) * (double)sum;
+    double cum = 0.0;
     int pick = arg;
     bool found = false;
 #pragma unroll
     for (int a = 0; a < 5; a++) {
-        cdf += (double)p[a] / (double)sum;
-        if (!found && ((allowed >> a) & 1) && cdf > u) {
+        cum += (double)p[a];
+        if (!found && ((allowed >> a) & 1) && cum > us) {
             pick = a;
             found = true;
         }

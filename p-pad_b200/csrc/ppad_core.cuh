@@ -29,6 +29,15 @@
 #define PPAD_TIGHT_DEFAULT true   // the host build (tests/hostcore) fuzzes the unrolled Philox refill
 #endif
 
+// tuning knobs (profiles/variants.py builds A/B variants with -D...)
+#define PPAD_PRAGMA_(x) _Pragma(#x)
+#define PPAD_PRAGMA(x) PPAD_PRAGMA_(x)
+#if defined(PPAD_PHILOX_NOINLINE) && defined(__CUDACC__)
+#define PPAD_PHILOX_FN __host__ __device__ __noinline__
+#else
+#define PPAD_PHILOX_FN PPAD_HD
+#endif
+
 namespace ppad {
 
 // ---------------------------------------------------------------------------------------------
@@ -201,7 +210,7 @@ struct U4 {
     uint32_t x, y, z, w;
 };
 
-PPAD_HD U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1)
+PPAD_PHILOX_FN U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1)
 {
 #pragma unroll
     for (int r = 0; r < 10; r++) {
@@ -259,6 +268,7 @@ PPAD_HD uint32_t action_word(const U4 &b, uint32_t step)
 struct SkyfallTable {
     uint32_t thr[10];
     uint32_t valid;
+    uint32_t uniform_k;   // K > 0: the valid types are 0 .. K-1 with thr[k-1] == floor(k * 2^32 / K) (host-verified), see below
 };
 
 template <int NT = 7>   // number of orb types of the geometry (7 or 10)
@@ -268,6 +278,14 @@ PPAD_HD int orb_from_u32(const SkyfallTable &t, uint32_t x)
     // x <= thr[i] is a valid type and equals the NUMBER of thresholds below x -- except for x = 0 when the
     // leading types have prob 0 (thr = 0): then it is the first valid type.  The host guarantees
     // thr = 0xFFFFFFFF from the last valid type on, so the count never passes it.
+    if (t.uniform_k) {   // kernel-uniform
+        // K equally likely types 0 .. K-1 (the reference's default skyfall, parameters.py:43, has K = 6): the count of
+        // thresholds floor(k 2^32 / K) below x is floor(x K / 2^32), except that x == k 2^32 / K exactly (an integer
+        // threshold, reached when the low word of x K is 0) still belongs to the type below.  One widening multiply
+        // instead of NT - 1 compares -- 19 % of the instructions of a reset-heavy step (profiles/r02b).
+        const uint64_t wide = (uint64_t)x * t.uniform_k;
+        return (int)(wide >> 32) - (((uint32_t)wide == 0u && x != 0u) ? 1 : 0);
+    }
     int orb = 0;
 #pragma unroll
     for (int i = 0; i < NT - 1; i++) orb += x > t.thr[i] ? 1 : 0;
@@ -702,7 +720,10 @@ PPAD_HD void fill_board(Board<G> &b, OrbSource &src, const RngKey &key, const Sk
 // fill_board(reset=True): every cell gets a draw, row-major.  TIGHT adds the unrolled pure-Philox loop: it pays
 // in the kernels that reset all the time (rollout, reset: 0.49 -> 0.29 ms per 2^20 boards) but its code size
 // slows the step kernels down (0.080 -> 0.087 ms) even though they rarely reset, so they do without it.
-template <class G, bool TIGHT = PPAD_TIGHT_DEFAULT>
+// UNROLL: Philox blocks per loop iteration of the TIGHT path.  2 is fastest where the refill dominates (reset and rollout
+// kernels); the fused policy step, whose instruction footprint already overflows the instruction cache (ncu: no_instruction
+// is its top stall), is faster with 1.
+template <class G, bool TIGHT = PPAD_TIGHT_DEFAULT, int UNROLL = 2>
 PPAD_HD void refill_all(Board<G> &b, OrbSource &src, const RngKey &key, const SkyfallTable &sky)
 {
     typedef typename G::W W;
@@ -712,7 +733,7 @@ PPAD_HD void refill_all(Board<G> &b, OrbSource &src, const RngKey &key, const Sk
         const uint32_t blk0 = (uint32_t)src.cursor >> 2;
         const int l0 = src.cursor & 3;             // the first block may start in the middle
         const int nblk = (l0 + G::CELLS + 3) / 4;
-#pragma unroll 2
+#pragma unroll UNROLL
         for (int q = 0; q < nblk; q++) {
             U4 c;
             c.x = key.env_lo;
@@ -905,6 +926,19 @@ PPAD_HD bool apply_move(State<G> &s, int action)
     return true;
 }
 
+// random finger of a reset (game.py:311-315): draws 0 and 1 of the FINGER stream = words x, y of its block 0
+template <class G>
+PPAD_HD int random_finger(const RngKey &key)
+{
+    U4 c;
+    c.x = key.env_lo;
+    c.y = key.env_hi;
+    c.z = key.step;
+    c.w = STREAM_FINGER << 24;
+    const U4 o = philox4x32_10(c, key.k0, key.k1);
+    return (int)mulhi32(o.x, (uint32_t)G::R) * G::C + (int)mulhi32(o.y, (uint32_t)G::C);
+}
+
 // reset (game.py:303-315): refill the whole board until it holds no 3-run
 template <class G>
 PPAD_HD uint32_t reset_board(State<G> &s, int reset_cap, OrbSource &src, const RngKey &key, const SkyfallTable &sky,
@@ -925,11 +959,7 @@ PPAD_HD uint32_t reset_board(State<G> &s, int reset_cap, OrbSource &src, const R
     }
     if (src.exhausted) flags |= FLAG_SKYFALL_EXHAUSTED;
     int finger = finger_in;
-    if (finger < 0) {
-        const int r = (int)mulhi32(philox_draw(key, STREAM_FINGER, 0), (uint32_t)G::R);
-        const int c = (int)mulhi32(philox_draw(key, STREAM_FINGER, 1), (uint32_t)G::C);
-        finger = r * G::C + c;
-    }
+    if (finger < 0) finger = random_finger<G>(key);
     s.meta = meta_pack(finger, ACT_PASS, 0);   // previous_action = 'pass' (game.py:299)
     return flags;
 }
@@ -1040,7 +1070,7 @@ PPAD_HD RngKey board_key(const StepParams &p, uint64_t env)
 // a board and try consecutive attempt indices speculatively; per board the accepted attempt with the LOWEST
 // index wins, which is exactly the one the sequential loop of game.py:303-308 would have stopped at -- same
 // board, same number of orbs consumed.  Typically 3-4 warp iterations instead of ~10.
-template <class G, bool TIGHT = false>
+template <class G, bool TIGHT = false, int UNROLL = 2>
 __device__ __forceinline__ uint32_t reset_boards_warp(bool need, State<G> &s, const StepParams &p, uint32_t step,
                                                       uint64_t env, const uint32_t *slab, int n_inj, int finger_in,
                                                       int *consumed_out)
@@ -1074,7 +1104,7 @@ __device__ __forceinline__ uint32_t reset_boards_warp(bool need, State<G> &s, co
             src.cursor = att * G::CELLS;
             RngKey key_o = board_key(p, env_o);
             key_o.step = step;
-            refill_all<G, TIGHT>(b, src, key_o, p.sky);
+            refill_all<G, TIGHT, UNROLL>(b, src, key_o, p.sky);
             W er, ed;
             ok = match_mask<G>(b, er, ed) == 0;
         }
@@ -1110,11 +1140,7 @@ __device__ __forceinline__ uint32_t reset_boards_warp(bool need, State<G> &s, co
     if (consumed > 0) {
         if (my_n_inj >= 0 && consumed > my_n_inj) flags |= FLAG_SKYFALL_EXHAUSTED;
         int finger = finger_in;
-        if (finger < 0) {
-            const int r = (int)mulhi32(philox_draw(my_key, STREAM_FINGER, 0), (uint32_t)G::R);
-            const int c = (int)mulhi32(philox_draw(my_key, STREAM_FINGER, 1), (uint32_t)G::C);
-            finger = r * G::C + c;
-        }
+        if (finger < 0) finger = random_finger<G>(my_key);
         s.meta = meta_pack(finger, ACT_PASS, 0);
     }
     if (consumed_out) *consumed_out = consumed;
@@ -1127,7 +1153,7 @@ __device__ __forceinline__ uint32_t reset_boards_warp(bool need, State<G> &s, co
 // the lanes reconverge after every iteration.
 // TIGHT_RESET: the auto-reset uses the unrolled Philox refill; HAS_RESET = false compiles the auto-reset out (kernels
 // launched with auto_reset = 0 do not carry its code).
-template <class G, bool TIGHT_RESET = false, bool HAS_RESET = true>
+template <class G, bool TIGHT_RESET = false, bool HAS_RESET = true, int RESET_UNROLL = 2>
 PPAD_HD StepOut step_board(bool live, State<G> &s, Board<G> &final_board, const StepParams &p, uint64_t env,
                            int action_in, const uint32_t *slab, uint16_t *log, const uint32_t *path = nullptr,
                            int path_len = 0, uint32_t step_offset = 0, const U4 *act_blk = nullptr)
@@ -1168,7 +1194,7 @@ PPAD_HD StepOut step_board(bool live, State<G> &s, Board<G> &final_board, const 
     if constexpr (HAS_RESET) {
         if (p.auto_reset) {   // kernel-uniform
             const bool need = live && pre.action == ACT_PASS;
-            const uint32_t f = reset_boards_warp<G, TIGHT_RESET>(need, s, p, key.step, env, nullptr, -1, -1, nullptr);
+            const uint32_t f = reset_boards_warp<G, TIGHT_RESET, RESET_UNROLL>(need, s, p, key.step, env, nullptr, -1, -1, nullptr);
             if (need) it.flags |= FLAG_EPISODE_DONE | f;
         }
     }

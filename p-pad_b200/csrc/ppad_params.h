@@ -76,6 +76,18 @@ inline int build_params(const ppad_config &cfg, StepParams &p, int &geom, std::s
         err = "skyfall rates sum too far below 1: the reference's fall-through (game.py:470) would emit bombs";
         return PPAD_ERR_UNSUPPORTED;
     }
+    // K equally likely leading types: orb_from_u32 may then replace the compares by one multiply.  Enabled only when
+    // the thresholds the float rule produced ARE floor(k 2^32 / K) -- checked here, not assumed.
+    {
+        int k_valid = 0;
+        while (k_valid < 10 && cfg.skyfall[k_valid] > 0) k_valid++;
+        bool uniform = k_valid >= 2 && (int)(last_valid + 1) == k_valid;
+        for (int i = 0; uniform && i < k_valid; i++) uniform = cfg.skyfall[i] == cfg.skyfall[0];
+        for (int k = 1; uniform && k < k_valid; k++)
+            uniform = p.sky.thr[k - 1] == (uint32_t)(((uint64_t)k << 32) / (uint64_t)k_valid);
+        for (int i = k_valid; uniform && i < 10; i++) uniform = p.sky.thr[i] == 0xFFFFFFFFu;
+        p.sky.uniform_k = uniform ? (uint32_t)k_valid : 0u;
+    }
     // team table, game.py:171-180: per attack colour the (multiplier, atk) of matching units in team order
     for (int u = 0; u < cfg.team_size; u++) {
         const int a = cfg.team_color_1[u], b = cfg.team_color_2[u];

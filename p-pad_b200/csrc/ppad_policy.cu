@@ -96,11 +96,12 @@ int ppad_policy_step(const ppad_ctx *ctx, const ppad_policy_args *args, void *st
     a.r_reward = args->ring_reward;
     a.ring_steps = args->ring_steps;
     a.ring_step = args->ring_step;
+    a.ring_slot = args->ring_steps > 0 ? args->ring_step % args->ring_steps : 0;
     a.gamma = args->gamma;
     a.log10_reward = args->log10_reward;
     a.stats = reinterpret_cast<unsigned long long *>(args->stats_rows);
     int r = PPAD_OK;
-    const int minb = args->ctas_per_sm > 0 ? args->ctas_per_sm : 3;
+    const int minb = args->ctas_per_sm > 0 ? args->ctas_per_sm : 4;
     PPAD_DISPATCH(ctx, (r = launch_policy_g<G>(a, minb, (cudaStream_t)stream)));
     return r;
 }

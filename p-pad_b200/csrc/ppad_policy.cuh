@@ -17,6 +17,10 @@
 #pragma once
 #include "ppad_step.cuh"
 
+#if !defined(PPAD_POLICY_REFILL_UNROLL)
+#define PPAD_POLICY_REFILL_UNROLL 1
+#endif
+
 namespace ppad {
 
 constexpr int STATS_WORDS = 40;   // uint64 per CTA row, layout = dist.STAT_FIELDS + depth hist [16] + combo hist [16]
@@ -43,25 +47,24 @@ struct PolicyArgs {
     uint8_t *r_action;
     double *r_reward;
     int64_t ring_steps, ring_step;
+    int64_t ring_slot;        // ring_step % ring_steps (host-computed: no 64-bit modulo in the kernel)
     double gamma;             // > 0: discounted returns are written back when an episode ends (agent/utils.py:22-51)
     int32_t log10_reward;     // log10 of a positive final reward before discounting (utils.py:37-40)
     unsigned long long *stats;   // [grid, STATS_WORDS] per-CTA accumulators (added to, never reset here), or NULL
 };
 
-// MINB: resident CTAs per SM the register allocation aims at.  The auto-reset + selection + observation code needs
-// more than the 64 registers that 4 CTAs of 256 threads leave (round 1: 142 B of spill stores per thread in the
-// auto-reset step kernel); 3 CTAs (85 registers) hold it without spills.
+// MINB: resident CTAs per SM the register allocation aims at: 4 (64 registers, ~100 B of spills) or 3 (80 registers, no
+// spills).  Measured per 2^20 boards (profiles/r02f_ab.txt): 0.2198 ms with 4 against 0.2250 ms with 3 once the code was
+// made smaller (before: 0.269 against 0.254) -- occupancy beats the spills.
 template <class G, bool OBS, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) policy_step_kernel(const __grid_constant__ PolicyArgs a)
 {
     __shared__ ObsShared obs_sh;
     __shared__ uint32_t obs_stream[OBS ? (BLOCK / 32) * ObsGeom<G>::WARP_WORDS : 1];
-    __shared__ unsigned long long st[8];
-    __shared__ unsigned int st_hist[32];   // depth histogram [16] | combo-count histogram [16]
-    if (OBS) obs_init_luts(obs_sh);
-    if (a.stats && threadIdx.x < 8) st[threadIdx.x] = 0;
-    if (a.stats && threadIdx.x < 32) st_hist[threadIdx.x] = 0;
-    if (OBS || a.stats) __syncthreads();
+    if (OBS) {
+        obs_init_luts(obs_sh);
+        __syncthreads();
+    }
 
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     const bool valid = i < a.n;
@@ -69,7 +72,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) policy_step_kernel(const __grid_c
     State<G> s;
     clear_state<G>(s);
     int action = ACT_PASS;
-    const int64_t row = (a.ring_step % (a.ring_steps > 0 ? a.ring_steps : 1)) * a.n + i;
+    const int64_t row = a.ring_slot * a.n + i;
     if (valid) {
         s = StateIO<G>::load(a.state, i);
         // ---- Agent01.act after the network (agent01.py:173-218) + the episode length cap (simulation.py:50-52)
@@ -92,7 +95,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) policy_step_kernel(const __grid_c
     // ---- the env step (every lane takes part: the cascade loop and the reset are warp-cooperative)
     const int episode_len = meta_moves(s.meta);   // moves made before this step (a pass ends the episode)
     Board<G> fin;
-    const StepOut o = step_board<G, true, true>(valid, s, fin, a.p, env, action,
+    const StepOut o = step_board<G, true, true, PPAD_POLICY_REFILL_UNROLL>(valid, s, fin, a.p, env, action,
                                                 a.slab && valid ? a.slab + (size_t)i * a.p.slab_words : nullptr, nullptr);
     if (valid) {
         StateIO<G>::store(a.state, i, s.b, s.meta);
@@ -109,45 +112,60 @@ __global__ void __launch_bounds__(BLOCK, MINB) policy_step_kernel(const __grid_c
                 int64_t back = episode_len < a.ring_steps - 1 ? episode_len : a.ring_steps - 1;   // rows still in the ring
                 if (back > a.ring_step) back = a.ring_step;                                        // rows that were ever pushed
                 double cur = r;
-                int64_t t = a.ring_step;
+                int64_t slot = a.ring_slot;
                 for (int64_t j = 0; j < back; j++) {
                     cur = dadd(dmul(cur, a.gamma), 0.0);
-                    t--;
-                    a.r_reward[((t % a.ring_steps + a.ring_steps) % a.ring_steps) * a.n + i] = cur;
+                    slot = slot == 0 ? a.ring_steps - 1 : slot - 1;
+                    a.r_reward[slot * a.n + i] = cur;
                 }
             }
         }
     }
-    // ---- episode statistics: warp reductions -> shared-memory accumulators -> one row of uint64 per CTA in global memory
+    // ---- episode statistics: warp reductions, then a handful of 64-bit reductions (RED) into this CTA's row in global
+    // memory -- no shared memory and no barrier, so a warp that is done does not wait for the CTA's slowest one
     if (a.stats) {   // kernel-uniform: every lane takes part in the reductions
         const unsigned full = 0xFFFFFFFFu;
+        unsigned long long *row_st = a.stats + (size_t)blockIdx.x * STATS_WORDS;
         const uint32_t inf = valid ? o.info : 0u;
         const uint32_t combos = inf & 0xFFu, depth = (inf >> 8) & 0xFFu, consumed = (inf >> 16) & 0xFFu, flags = inf >> 24;
         const bool evaluated = valid && (o.action == ACT_PASS || a.p.eval_moves != 0);
-        if (evaluated) {   // histograms over the evaluated boards (the passes of a policy rollout)
-            atomicAdd(&st_hist[depth < 15 ? depth : 15], 1u);
-            atomicAdd(&st_hist[16 + (combos < 15 ? combos : 15)], 1u);
+        // histograms over the evaluated boards (the passes of a policy rollout); most of them match nothing (bin 0 of
+        // both: counted per warp), the others add themselves
+        if (evaluated && depth) {
+            atomicAdd(&row_st[ST_DEPTH_HIST + (depth < 15 ? depth : 15)], 1ull);
+            atomicAdd(&row_st[ST_COMBO_HIST + (combos < 15 ? combos : 15)], 1ull);
         }
+        const unsigned n_zero = __popc(__ballot_sync(full, evaluated && depth == 0));
+        const unsigned n_valid_w = __popc(__ballot_sync(full, valid));
         const unsigned n_eval = __popc(__ballot_sync(full, depth != 0));
         const unsigned n_done = __popc(__ballot_sync(full, (flags & FLAG_EPISODE_DONE) != 0));
         const unsigned n_fault = __popc(__ballot_sync(full, (flags & 0x7Fu) != 0));
         const unsigned sum_combos = __reduce_add_sync(full, combos), sum_consumed = __reduce_add_sync(full, consumed);
         unsigned long long fx = valid && depth ? (unsigned long long)llrint(o.reward * STATS_REWARD_SCALE) : 0ull;
         unsigned long long mx = valid && depth ? (unsigned long long)__double_as_longlong(o.reward) : 0ull;   // rewards are >= 0
+        if (n_eval) {   // warp-uniform
 #pragma unroll
-        for (int off = 16; off; off >>= 1) {
-            fx += __shfl_xor_sync(full, fx, off);
-            const unsigned long long other = __shfl_xor_sync(full, mx, off);
-            mx = other > mx ? other : mx;
+            for (int off = 16; off; off >>= 1) {
+                fx += __shfl_xor_sync(full, fx, off);
+                const unsigned long long other = __shfl_xor_sync(full, mx, off);
+                mx = other > mx ? other : mx;
+            }
         }
         if ((threadIdx.x & 31) == 0) {
-            atomicAdd(&st[ST_EVALUATED], (unsigned long long)n_eval);
-            atomicAdd(&st[ST_REWARD_SUM], fx);
-            atomicMax(&st[ST_REWARD_MAX], mx);
-            atomicAdd(&st[ST_COMBOS], (unsigned long long)sum_combos);
-            atomicAdd(&st[ST_CONSUMED], (unsigned long long)sum_consumed);
-            atomicAdd(&st[ST_EPISODES], (unsigned long long)n_done);
-            atomicAdd(&st[ST_FAULTS], (unsigned long long)n_fault);
+            atomicAdd(&row_st[ST_BOARDS], (unsigned long long)n_valid_w);
+            if (n_zero) {
+                atomicAdd(&row_st[ST_DEPTH_HIST], (unsigned long long)n_zero);
+                atomicAdd(&row_st[ST_COMBO_HIST], (unsigned long long)n_zero);
+            }
+            if (n_eval) {
+                atomicAdd(&row_st[ST_EVALUATED], (unsigned long long)n_eval);
+                atomicAdd(&row_st[ST_REWARD_SUM], fx);
+                atomicMax(&row_st[ST_REWARD_MAX], mx);
+                atomicAdd(&row_st[ST_COMBOS], (unsigned long long)sum_combos);
+                atomicAdd(&row_st[ST_CONSUMED], (unsigned long long)sum_consumed);
+            }
+            if (n_done) atomicAdd(&row_st[ST_EPISODES], (unsigned long long)n_done);
+            if (n_fault) atomicAdd(&row_st[ST_FAULTS], (unsigned long long)n_fault);
         }
     }
     const int64_t warp0 = i - (threadIdx.x & 31);
@@ -155,19 +173,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) policy_step_kernel(const __grid_c
         const int n_valid = (int)(a.n - warp0 < 32 ? a.n - warp0 : 32);
         emit_obs<G>(s, valid, n_valid, obs_stream + (threadIdx.x >> 5) * ObsGeom<G>::WARP_WORDS, obs_sh,
                     obs_warp_ptr<G>(a.obs, warp0, a.obs_dtype), a.obs_dtype);
-    }
-    if (a.stats) {
-        __syncthreads();
-        if (threadIdx.x < STATS_WORDS) {
-            unsigned long long *dst = a.stats + (size_t)blockIdx.x * STATS_WORDS + threadIdx.x;
-            unsigned long long v = threadIdx.x < 8 ? st[threadIdx.x] : (unsigned long long)st_hist[threadIdx.x - 8];
-            if (threadIdx.x == ST_BOARDS) {
-                const int64_t left = a.n - (int64_t)blockIdx.x * BLOCK;
-                v = (unsigned long long)(left < BLOCK ? left : BLOCK);
-            }
-            if (threadIdx.x == ST_REWARD_MAX) *dst = v > *dst ? v : *dst;
-            else *dst += v;
-        }
     }
 }
 

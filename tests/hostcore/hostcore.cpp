@@ -210,6 +210,14 @@ int hostcore_sky_table(const ppad_config *cfg, uint32_t thr[10], uint32_t *valid
     return 0;
 }
 
+int hostcore_uniform_k(const ppad_config *cfg)
+{
+    StepParams p;
+    int geom;
+    if (build_params(*cfg, p, geom, g_err)) return -1;
+    return (int)p.sky.uniform_k;
+}
+
 int hostcore_orb_from_u32(const ppad_config *cfg, uint32_t x)
 {
     StepParams p;

@@ -116,6 +116,10 @@ def sky_table(cfg):
     return list(thr), valid.value
 
 
+def uniform_k(cfg):
+    return lib().hostcore_uniform_k(C.byref(cfg))
+
+
 def orb_from_u32(cfg, x):
     return lib().hostcore_orb_from_u32(C.byref(cfg), C.c_uint32(x))
 

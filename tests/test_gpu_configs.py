@@ -238,7 +238,7 @@ def test_fused_policy_step_equals_select_step_push(pb, rows, cols, n, obs, ctas)
     # log10 variant: the pass row holds log10(r), the earlier rows its discounted values (np.log10 vs CUDA log10: 1 ulp)
     ring2 = RolloutRing(env, ring_steps, gamma=gamma, log10=True)
     q = torch.randn((n, 5), device=env.device, generator=gen) * 1000
-    q[:, 4] += 5000                                                     # everybody passes
+    q[:, 4] += 1e6                                                      # everybody passes
     o2 = env.policy_step(q, method='max', max_moves=max_moves, ring=ring2)
     rr = o2.reward.cpu().numpy()
     got = ring2.reward.cpu().numpy()[:n]

@@ -254,6 +254,34 @@ def test_sky_thresholds_match_float_rule():
             assert hc.orb_from_u32(cfg, int(z["xs"][j])) == z["orbs"][i, j], (i, j)
 
 
+def test_uniform_skyfall_fast_path_is_the_float_rule():
+    """orb_from_u32 replaces the threshold compares by one multiply when K leading types are equally likely; it must
+    return exactly what the reference's rule returns (game.py:464-470: first i with cumsum[i] >= u and prob[i] > 0,
+    u = x / 2^32), including at every threshold and its neighbours."""
+    rng = np.random.default_rng(9)
+    for K in range(2, 11):
+        p = [1.0 / K] * K + [0.0] * (10 - K)
+        cfg = hc.cfg_from_oracle(orc.make_cfg(skyfall=p), orb_bits=4 if K > 7 else None)
+        assert hc.uniform_k(cfg) == K
+        xs = {0, 1, 2, 2 ** 32 - 1, 2 ** 32 - 2, 2 ** 31, 2 ** 31 - 1, 2 ** 31 + 1}
+        for k in range(1, K):
+            t = (k << 32) // K
+            xs.update({t - 2, t - 1, t, t + 1, t + 2})
+        xs.update(int(v) for v in rng.integers(0, 2 ** 32, 2000))
+        for x in sorted(xs):
+            u, acc, want = x / 2.0 ** 32, 0.0, 9
+            for i, pi in enumerate(p):
+                acc += pi
+                if acc >= u and pi > 0:
+                    want = i
+                    break
+            assert hc.orb_from_u32(cfg, x) == want, (K, x)
+    # not uniform, or not the leading types: the compare loop stays
+    assert hc.uniform_k(hc.cfg_from_oracle(orc.make_cfg(skyfall=[0.5, 0.25, 0.25, 0, 0, 0, 0, 0, 0, 0]))) == 0
+    assert hc.uniform_k(hc.cfg_from_oracle(orc.make_cfg(skyfall=[0, 0.5, 0.5, 0, 0, 0, 0, 0, 0, 0]))) == 0
+    assert hc.uniform_k(hc.cfg_from_oracle(orc.make_cfg())) == 6            # the reference's default skyfall
+
+
 def test_philox_matches_oracle():
     rng = np.random.default_rng(5)
     for _ in range(50):
