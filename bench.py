@@ -302,24 +302,29 @@ def leg_rollout(ppad_b200, pdist, T, args, rank, world, dev, peak):
         env.policy_step(qs[t & 3], method='boltzmann', beta=1e-3, epsilon=0.1, max_moves=50, obs=obs, ring=ring,
                         stats=stats, out=out)
         if (t + 1) % 10 == 0:
-            last["stats"] = pdist.gather_stats(stats.vector())
+            # one NCCL all-gather of (stats vector, 32 sampled replay rows) per rank; results stay on the device
+            vec = stats.vector()
             stats.clear()
             s, a, r, _ = ring.sample(32)
-            last["replay_rows"] = pdist.all_gather_rows(s, a, r)[0].shape[0]
+            last["gathered"] = pdist.gather_rollout_window(vec, s, a, r, out=last.get("buf"))
+            last["buf"] = last["gathered"][4]
 
     for t in range(W):
         one(t)
     ms = T.timed(one, W, K)
     per = ms / K
     achieved = BYTES_ROLLOUT * n / (per * 1e-3) / 1e9
+    g_stats, g_state = last["gathered"][0], last["gathered"][1]
+    last["stats"] = pdist.merge_stats(g_stats.cpu())
+    last["replay_rows"] = int(g_state.shape[0])
     del env, ring, stats, qs, obs
     torch.cuda.empty_cache()
     return {"metric": "env_steps_per_sec_policy_rollout", "value": n * world * K / (ms * 1e-3), "unit": "steps/s",
             "boards_per_gpu": n, "steps": K, "warmup": W, "ms_per_step": per,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "algorithmic_bytes_per_board": BYTES_ROLLOUT, "kernel": "policy_step_kernel<Geom<5,6>>"},
-            "collectives_in_timed_region": "every 10 steps: all_gather of the 40-double stats vector + all_gather of 32 replay "
-                                           "rows (state, action, discounted return) per GPU",
+            "collectives_in_timed_region": "every 10 steps: ONE NCCL all_gather carrying the 40-double stats vector of the window "
+                                           "and 32 sampled replay rows (state, action, discounted return) per GPU",
             "workload": "configs[4]: Boltzmann policy (beta 1e-3, epsilon 0.1) on synthetic Q-values resident in HBM, episode cap "
                         "50, auto-reset, fp32 obs, replay ring (4 steps deep, gamma 0.99, log10) -- one fused launch per step",
             "stats_last_window": last.get("stats"), "replay_rows_gathered": last.get("replay_rows")}

@@ -48,7 +48,9 @@ typedef enum ppad_status {
 } ppad_status;
 
 /* actions: player.py:24, simulation.py:236 */
-enum { PPAD_UP = 0, PPAD_DOWN = 1, PPAD_LEFT = 2, PPAD_RIGHT = 3, PPAD_PASS = 4, PPAD_SAMPLE = 255 };
+enum { PPAD_UP = 0, PPAD_DOWN = 1, PPAD_LEFT = 2, PPAD_RIGHT = 3, PPAD_PASS = 4,
+       PPAD_NOOP = 5,      /* the board sits this step out: no move, no evaluation, no flag (lock-step batches) */
+       PPAD_SAMPLE = 255 };
 
 /* flags byte (info >> 24) */
 enum {
@@ -57,7 +59,7 @@ enum {
     PPAD_FLAG_SKYFALL_EXHAUSTED = 0x02, /* injected orbs ran out, the Philox stream took over */
     PPAD_FLAG_CASCADE_CAP = 0x04,       /* cascade stopped at cfg.cascade_cap iterations */
     PPAD_FLAG_NO_LEGAL_MOVE = 0x08,     /* random policy found an empty legal set */
-    PPAD_FLAG_BAD_ACTION = 0x10,        /* action id outside 0..4 */
+    PPAD_FLAG_BAD_ACTION = 0x10,        /* action id outside 0..5 */
     PPAD_FLAG_RESET_CAP = 0x20,         /* reset gave up after cfg.reset_cap attempts */
     PPAD_FLAG_UNSUPPORTED_ORB = 0x40,   /* pack saw a value outside -1..6 (orb_bits 3) / -1..9 (orb_bits 4): stored as empty */
     PPAD_FLAG_EPISODE_DONE = 0x80       /* a pass was processed and the board auto-reset */
@@ -263,6 +265,13 @@ int ppad_encode_obs(const ppad_ctx *ctx, int64_t n, const void *state, void *obs
 /* pad_utils.cancel (utils.py:26-70): one in-place cancel; n_combos [n] uint8; combo_log as above */
 int ppad_cancel(const ppad_ctx *ctx, int64_t n, void *state, uint8_t *n_combos, uint16_t *combo_log,
                 int32_t log_cap, void *stream);
+
+/* pad_utils.detect_island (utils.py:86-111): island_out[i] = island_in[i] | the 4-connected island of cells of
+ * orb_type[i] (-1: empty cells; anything else that no cell holds: nothing) around cell seed_cell[i] = row * cols + col of board i, as bit masks (bit = cell index).
+ * Like the reference's recursion the flood does not enter cells already set in island_in (NULL = all clear); a seed
+ * that does not hold orb_type leaves the mask as it was. */
+int ppad_island(const ppad_ctx *ctx, int64_t n, const void *state, const uint8_t *seed_cell, const int8_t *orb_type,
+                const uint64_t *island_in, uint64_t *island_out, void *stream);
 
 /* pad_utils.illegal_actions (utils.py:73-83) / the support of PlayerAction.sample (player.py:46-62):
  * mask [n] uint8, bit a = action a is a legal non-reversing move; bits 4..7 = off-board moves. */

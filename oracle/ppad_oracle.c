@@ -376,6 +376,8 @@ void ppad_oracle_step_batch(const ppad_oracle_cfg *cfg, int64_t n, uint64_t env0
             } else {
                 flags |= PPAD_OR_REJECTED;          /* game.py:353 raises ValueError */
             }
+        } else if (action == 5) {
+            /* no-op: the board sits this step out (a finished episode in a lock-step batch) */
         } else if (!(flags & PPAD_OR_NO_LEGAL_MOVE)) {
             flags |= PPAD_OR_BAD_ACTION;
         }

@@ -9,7 +9,7 @@ LIB_PATH = os.environ.get("PPAD_B200_LIB") or os.path.join(_HERE, "libppad_b200.
 MAX_TEAM_UNITS = 8
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
-UP, DOWN, LEFT, RIGHT, PASS, SAMPLE = 0, 1, 2, 3, 4, 255
+UP, DOWN, LEFT, RIGHT, PASS, NOOP, SAMPLE = 0, 1, 2, 3, 4, 5, 255
 FLAG_REJECTED, FLAG_SKYFALL_EXHAUSTED, FLAG_CASCADE_CAP, FLAG_NO_LEGAL_MOVE = 0x01, 0x02, 0x04, 0x08
 FLAG_BAD_ACTION, FLAG_RESET_CAP, FLAG_UNSUPPORTED_ORB, FLAG_EPISODE_DONE = 0x10, 0x20, 0x40, 0x80
 I8, I32, I64 = 1, 4, 8
@@ -72,7 +72,7 @@ SYMBOLS = ["ppad_default_config", "ppad_create", "ppad_destroy", "ppad_abi_versi
            "ppad_fill", "ppad_damage", "ppad_select_actions", "ppad_discount", "ppad_replay_push",
            "ppad_replay_sample", "ppad_permute", "ppad_pipe_create", "ppad_pipe_destroy", "ppad_pipe_step",
            "ppad_pipe_wait", "ppad_pipe_join", "ppad_rollout", "ppad_pipe_set_zero_copy", "ppad_rollout_record",
-           "ppad_compact_capacity", "ppad_policy_step", "ppad_policy_stats", "ppad_policy_stats_rows"]
+           "ppad_compact_capacity", "ppad_policy_step", "ppad_policy_stats", "ppad_policy_stats_rows", "ppad_island"]
 
 
 class PPADError(RuntimeError):
@@ -115,6 +115,7 @@ def lib():
     L.ppad_encode_obs.argtypes = [vp, i64, vp, vp, C.c_int, vp]
     L.ppad_cancel.argtypes = [vp, i64, vp, vp, vp, i32, vp]
     L.ppad_legal_mask.argtypes = [vp, i64, vp, vp, vp]
+    L.ppad_island.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp]
     L.ppad_sample_actions.argtypes = [vp, i64, u64, u32, vp, i32, vp, vp]
     L.ppad_drop.argtypes = [vp, i64, vp, vp]
     L.ppad_fill.argtypes = [vp, i64, u64, u32, i32, i32, vp, i32, i32, vp, vp, vp, vp]

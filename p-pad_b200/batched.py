@@ -337,6 +337,21 @@ class BatchedPAD:
                                              self._stream()))
         return n_combos, log
 
+    def islands(self, seeds, orb_types, island_in=None):
+        """pad_utils.detect_island (utils.py:86-111) for every board: seeds int [n, 2] (row, col), orb_types int [n]
+        (-1 = empty cells), island_in int64 [n] bit masks of cells already marked or None -> int64 [n] bit masks (bit = cell)."""
+        seeds = self._dev(seeds, torch.int64).reshape(self.n, 2)
+        cell = (seeds[:, 0] * self.dim_col + seeds[:, 1]).clamp(0, 255).to(torch.uint8).contiguous()
+        off = (seeds[:, 0] < 0) | (seeds[:, 0] >= self.dim_row) | (seeds[:, 1] < 0) | (seeds[:, 1] >= self.dim_col)
+        cell = torch.where(off, torch.full_like(cell, 255), cell)
+        types = self._dev(orb_types, torch.int8).reshape(self.n).contiguous()
+        pre = None if island_in is None else self._dev(island_in, torch.int64).reshape(self.n).contiguous()
+        out = torch.empty(self.n, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ppad_island(self._ctx, self.n, _ptr(self.state), _ptr(cell), _ptr(types), _ptr(pre),
+                                             _ptr(out), self._stream()))
+        return out
+
     def legal_mask(self):
         """uint8 [n]: bits 0..3 = legal non-reversing moves (player.py:52-62), bits 4..7 = off-board moves (utils.py:73-83)"""
         mask = torch.empty(self.n, dtype=torch.uint8, device=self.device)

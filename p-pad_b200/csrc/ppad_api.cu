@@ -167,6 +167,37 @@ __global__ void __launch_bounds__(BLOCK) cancel_kernel(int64_t n, void *state, u
     if (n_combos) n_combos[i] = (uint8_t)sat255(m);
 }
 
+// pad_utils.detect_island (utils.py:86-111): the 4-connected island of cells of `type` around the seed cell.  The
+// reference's recursion starts at the seed if it holds `type`, marks it, and enters every neighbour of that type whose
+// mark is still 0; cells already marked in `island_in` are therefore never entered (nor expanded), the seed itself is
+// expanded even when it is marked.  Result = island_in | cells reached.
+template <class G>
+__global__ void __launch_bounds__(BLOCK) island_kernel(int64_t n, const void *state, const uint8_t *seed, const int8_t *type,
+                                                       const uint64_t *island_in, uint64_t *island_out)
+{
+    typedef typename G::W W;
+    const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= n) return;
+    const State<G> s = StateIO<G>::load(state, i);
+    const W pre = island_in ? (W)island_in[i] & G::BOARD : (W)0;
+    const int cell = seed[i];
+    const int t = type[i] == -1 ? G::EMPTY : type[i];      // -1 = empty cells: the reference floods those, too
+    W out = pre;
+    if (cell < G::CELLS && t >= 0 && code_at<G>(s.b, cell) == t) {
+        // er / ed: same code as the right / lower neighbour (empty cells included, unlike match_mask)
+        W xr = (s.b.b0 ^ (s.b.b0 >> 1)) | (s.b.b1 ^ (s.b.b1 >> 1)) | (s.b.b2 ^ (s.b.b2 >> 1));
+        W xd = (s.b.b0 ^ (s.b.b0 >> G::C)) | (s.b.b1 ^ (s.b.b1 >> G::C)) | (s.b.b2 ^ (s.b.b2 >> G::C));
+        PPAD_P4(xr |= s.b.b3 ^ (s.b.b3 >> 1); xd |= s.b.b3 ^ (s.b.b3 >> G::C))
+        W er = ~xr & G::NOT_LASTCOL, ed = ~xd & G::NOT_LASTROW;
+        const W bit = G::ONE << cell;
+        const W open = ~pre | bit;                        // cells the flood may stand on
+        er &= open & (open >> 1);
+        ed &= open & (open >> G::C);
+        out |= closure<G>(bit, er, ed);
+    }
+    island_out[i] = (uint64_t)out;
+}
+
 template <class G>
 __global__ void __launch_bounds__(BLOCK) legal_kernel(int64_t n, const void *state, uint8_t *mask)
 {
@@ -448,6 +479,17 @@ int ppad_cancel(const ppad_ctx *ctx, int64_t n, void *state, uint8_t *n_combos, 
     PPAD_DISPATCH(ctx, (cancel_kernel<G><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(n, state, n_combos, combo_log,
                                                                                          log_cap)));
     return after_launch("cancel_kernel");
+}
+
+int ppad_island(const ppad_ctx *ctx, int64_t n, const void *state, const uint8_t *seed_cell, const int8_t *orb_type,
+                const uint64_t *island_in, uint64_t *island_out, void *stream)
+{
+    PPAD_ENTER(ctx, n);
+    if (n == 0) return PPAD_OK;
+    if (!state || !seed_cell || !orb_type || !island_out) return fail(PPAD_ERR_INVALID, "ppad_island: null pointer");
+    PPAD_DISPATCH(ctx, (island_kernel<G><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(n, state, seed_cell, orb_type,
+                                                                                         island_in, island_out)));
+    return after_launch("island_kernel");
 }
 
 int ppad_legal_mask(const ppad_ctx *ctx, int64_t n, const void *state, uint8_t *mask, void *stream)

@@ -129,7 +129,7 @@ enum : uint32_t {
     FLAG_BAD_ACTION = 0x10, FLAG_RESET_CAP = 0x20, FLAG_UNSUPPORTED_ORB = 0x40, FLAG_EPISODE_DONE = 0x80
 };
 enum : uint32_t { STREAM_SKYFALL = 0, STREAM_ACTION = 1, STREAM_RESET = 2, STREAM_FINGER = 3, STREAM_POLICY = 4 };
-enum : int { ACT_UP = 0, ACT_DOWN = 1, ACT_LEFT = 2, ACT_RIGHT = 3, ACT_PASS = 4 };
+enum : int { ACT_UP = 0, ACT_DOWN = 1, ACT_LEFT = 2, ACT_RIGHT = 3, ACT_PASS = 4, ACT_NOOP = 5 };
 
 PPAD_HD uint32_t sat255(int v) { return v > 255 ? 255u : (uint32_t)v; }
 PPAD_HD uint32_t make_info(int n_combos, int depth, int consumed, uint32_t flags)
@@ -1018,6 +1018,8 @@ PPAD_HD StepPrefix step_prefix(State<G> &s, const StepParams &p, const RngKey &k
     } else if (action < ACT_PASS) {
         if (apply_move<G>(s, action)) o.evaluate = p.eval_moves != 0;
         else o.flags |= FLAG_REJECTED;
+    } else if (action == ACT_NOOP) {
+        // the board sits this step out (a finished episode in a lock-step batch): no move, no evaluation, no flag
     } else if (!(o.flags & FLAG_NO_LEGAL_MOVE)) {
         o.flags |= FLAG_BAD_ACTION;
     }

@@ -72,7 +72,7 @@ __device__ __forceinline__ void compact_results(const StepKernelArgs &a, bool va
         c_cnt[0][warp] = __popc(bh);
         c_cnt[1][warp] = __popc(bd);
     }
-    uint32_t nib = valid ? (((uint32_t)o.action & 7u) | (has ? 8u : 0u)) : 0u;   // action 255 (none) -> 7
+    uint32_t nib = valid ? ((o.action <= ACT_NOOP ? (uint32_t)o.action : 7u) | (has ? 8u : 0u)) : 0u;   // none / bad id -> 7
     nib <<= 4 * (lane & 7);
     nib |= __shfl_xor_sync(0xFFFFFFFFu, nib, 1);
     nib |= __shfl_xor_sync(0xFFFFFFFFu, nib, 2);

@@ -1,8 +1,11 @@
 """Pre-solved boards for smart-data generation (the role of ppad/data/dataset01/solved_boards.py).
 
-The reference ships 16 hand-solved 5x6 boards.  Here solved boards are GENERATED for any board size:
-every cell belongs to a full-length or split row/column strip of at least three equal orbs, with
-neighbouring strips in different colours, so that a pass on the board cancels every orb.
+``boards`` are the reference's 16 hand-solved 5x6 boards (solved_boards.py:28-124; the reference writes them 6x5 and
+transposes) as a constant table -- data, so that ``ppad.data.dataset01.solved_boards.boards`` and
+``smart_data(boards=k)`` draw from the same set as the reference (tests/golden/kat.json pins their combos and rewards).
+For other board sizes (BASELINE configs[3]: 7x6) solved boards are GENERATED: every cell belongs to a full-length or
+split row/column strip of at least three equal orbs, with neighbouring strips in different colours, so that a pass on
+the board cancels every orb.
 """
 import numpy as np
 
@@ -43,5 +46,23 @@ def generate_solved_boards(dim_row=5, dim_col=6, count=16, seed=0):
     return boards
 
 
-# the default set used by smart_data(): sixteen 5x6 boards, like the reference's fixture
-boards = generate_solved_boards(5, 6, 16, seed=2018)
+# the reference's sixteen solved 5x6 boards, row-major, one digit per orb (0 red, 1 blue, 2 green, 3 light, 4 dark, 5 heal)
+_REFERENCE_BOARDS = [
+    "501021 501021 505555 501021 333334",
+    "555333 333555 511111 522222 500004",
+    "011115 044445 020005 333335 111444",
+    "444431 522231 204031 204031 204031",
+    "410315 410315 412315 415552 414444",
+    "000444 333120 400020 455520 444120",
+    "000555 454222 253333 250000 251111",
+    "425111 425333 421111 420000 423333",
+    "333444 444251 000001 444251 555251",
+    "111112 333532 444532 000532 555111",
+    "222245 111145 000245 333245 111245",
+    "111115 544445 522225 555000 000333",
+    "455555 412000 412111 412333 412000",
+    "512040 512040 333330 512040 512444",
+    "333304 522204 511104 555104 222104",
+    "012354 012354 012354 012354 012354",
+]
+boards = [np.array([[int(ch) for ch in row] for row in text.split()]) for text in _REFERENCE_BOARDS]

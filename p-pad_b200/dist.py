@@ -70,6 +70,35 @@ def all_gather_rows(*tensors):
     return tuple(out)
 
 
+def gather_rollout_window(stats_vec, state, action, reward, out=None):
+    """ONE all-gather for what a rollout exchanges every K steps (BASELINE configs[4]): the float64 [40] stats vector
+    of this rank's window and its k sampled replay rows (state int32 [k, words], action uint8 [k], reward float64 [k])
+    travel as one packed byte row per rank.  Nothing is copied to the host: returns device tensors
+    (stats [world, 40] float64, state [world * k, words], action [world * k], reward [world * k]); merge the stats with
+    merge_stats(stats.cpu()) when they are wanted.  `out` reuses the receive buffer of an earlier call."""
+    world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+    k, words = state.shape
+    parts = [stats_vec.contiguous().view(torch.uint8), reward.contiguous().view(torch.uint8),
+             state.contiguous().view(torch.uint8).reshape(-1), action.contiguous().view(torch.uint8)]
+    sizes = [p.numel() for p in parts]
+    row = (sum(sizes) + 15) // 16 * 16
+    send = torch.zeros(row, dtype=torch.uint8, device=state.device)
+    torch.cat(parts, out=send[:sum(sizes)])
+    if out is None or out.numel() != world * row:
+        out = torch.empty(world * row, dtype=torch.uint8, device=state.device)
+    if world > 1:
+        dist.all_gather_into_tensor(out, send)
+    else:
+        out.copy_(send)
+    rows = out.view(world, row)
+    o0, o1, o2 = sizes[0], sizes[0] + sizes[1], sizes[0] + sizes[1] + sizes[2]
+    g_stats = rows[:, :o0].contiguous().view(torch.float64).view(world, -1)
+    g_reward = rows[:, o0:o1].contiguous().view(torch.float64).reshape(world * k)
+    g_state = rows[:, o1:o2].contiguous().view(torch.int32).reshape(world * k, words)
+    g_action = rows[:, o2:o2 + sizes[3]].contiguous().reshape(world * k)
+    return g_stats, g_state, g_action, g_reward, out
+
+
 def gather_replay_sample(state, action, reward, k, generator=None):
     """Uniformly sample k rows of this rank's (state, action, reward) slab and all-gather them:
     returns (state [world*k, words] int32, action [world*k] uint8, reward [world*k] float64).

@@ -168,7 +168,8 @@ class PAD:
         v = self._venv
         self._torch, self._ctypes = torch, ctypes
         # two 128-byte slots: [0] the env's record, [1] scratch for calculate_reward(board=...).
-        # slot layout: state 0..64 (16..48 bytes used) | reward 64..72 | info 72..76 | action 76 | pre-sampled move 77
+        # slot layout: state 0..64 (16..48 bytes used) | reward 64..72 | info 72..76 | action 76 | pre-sampled move 77 |
+        # skyfall orbs consumed (uint16, not saturated at 255 like the info byte) 78..80
         self._io = torch.zeros(256, dtype=torch.uint8, device=v.device)
         self._io_host = torch.zeros(256, dtype=torch.uint8).pin_memory()
         self._io_np = self._io_host.numpy()
@@ -218,6 +219,7 @@ class PAD:
         a.n, a.env0, a.step = 1, v.env0, self._next_tick()
         a.skyfall_damage = -1 if skyfall_damage is None else int(bool(skyfall_damage))
         a.state, a.reward, a.info, a.action_out = base, base + 64, base + 72, base + 76
+        a.consumed_out = base + 78
         a.actions = self._action_bytes.data_ptr() + action_id
         if slab is not None:
             a.slab, a.slab_words, a.n_inj = slab.data_ptr(), slab.shape[1], len(injected)
@@ -239,6 +241,7 @@ class PAD:
             self._presample = (idx, int(raw[77])) if presample else (-1, 255)
         reward = np.float64(raw[64:72].view(np.float64)[0])
         info = int(raw[72:76].view(np.uint32)[0])
+        self._last_consumed = int(raw[78:80].view(np.uint16)[0])
         return reward, info, int(raw[76]), extra
 
     def _pull(self):
@@ -446,10 +449,10 @@ class PAD:
                 self._write_slot(1, self.board if board is None else board, self.finger, self._prev_id())
                 r = self._launch(1, _cabi.PASS, skyfall_damage=True, final=verbose, log_cap=64 if verbose else 0,
                                  injected=orbs)
-                if (r[1] >> 24) & _cabi.FLAG_SKYFALL_EXHAUSTED or ((r[1] >> 16) & 0xFF) == 255:
+                if (r[1] >> 24) & _cabi.FLAG_SKYFALL_EXHAUSTED or self._last_consumed == 0xFFFF:
                     return None
                 result[:] = r
-                return (r[1] >> 16) & 0xFF
+                return self._last_consumed       # the unsaturated count (the info byte stops at 255)
             self._speculate(cascade, 32, first=2)
             reward, info, _, extra = result
         else:

@@ -42,8 +42,25 @@ def illegal_actions(finger, dim_row=5, dim_col=6):
 
 
 def detect_island(board, island, x, y, orb_type):
-    raise NotImplementedError('detect_island is internal to cancel(): islands are computed inside the CUDA kernel '
-                              '(closure of the same-colour edge masks, csrc/ppad_core.cuh)')
+    """Mark, IN PLACE in `island`, the 4-connected island of cells of `orb_type` around (x, y) = (row, col), as
+    ppad.pad.utils.detect_island (utils.py:86-111): cells already non-zero in `island` are not entered.  One launch of
+    ppad_island (the closure of the same-colour edge masks the cancel kernel uses)."""
+    board = np.asarray(board)
+    rows, cols = board.shape
+    venv = _slab(rows, cols, 4 if (board > 6).any() else 3)
+    flags = venv.set_state(board[None], np.zeros((1, 2), dtype=np.int64))
+    if int(flags[0]):
+        raise NotImplementedError('orb types are -1 (empty) and 0..9 (game.py:236-246)')
+    if not (0 <= x < rows and 0 <= y < cols):
+        raise IndexError('index ({}, {}) is out of bounds for a {} x {} board'.format(x, y, rows, cols))
+    cells = np.arange(rows * cols, dtype=np.uint64)
+    pre = int((np.uint64(1) << cells)[np.asarray(island).reshape(-1) != 0].sum()) if np.any(island) else 0
+    if pre >= 1 << 63:
+        pre -= 1 << 64
+    t = int(orb_type) if -1 <= int(orb_type) <= 9 else -2        # -2: no cell holds it
+    mask = int(venv.islands(np.array([[x, y]]), np.array([t], np.int8), np.array([pre], np.int64))[0].item()) & (2 ** 64 - 1)
+    new = np.array([(mask >> c) & 1 for c in range(rows * cols)], bool).reshape(rows, cols)
+    island[new] = 1
 
 
 def episode2gif(*args, **kwargs):

@@ -83,6 +83,15 @@ torch.cuda.synchronize(); t0 = time.perf_counter()
 res = two_step_lookahead(small, q_fn=qf, policy='boltzmann', beta=1e-3, max_lookahead_len=10)
 torch.cuda.synchronize(); dt = time.perf_counter() - t0
 print("two_step_lookahead, %d envs, Boltzmann roam up to 10 moves (synthetic q): %.2f ms  (%.2fe6 envs/s)" % (m, dt * 1e3, m / dt / 1e6))
+from ppad_b200.lookahead import model_simulation_2sla
+W = torch.randint(-9, 10, (210, 5), device=small.device).float()
+qlin = lambda obs: obs.reshape(obs.shape[0], -1) @ W
+model_simulation_2sla(small, qlin, policy='boltzmann', beta=0.05, max_episode_len=50, max_lookahead_len=10)
+torch.cuda.synchronize(); t0 = time.perf_counter()
+res = model_simulation_2sla(small, qlin, policy='boltzmann', beta=0.05, max_episode_len=50, max_lookahead_len=10)
+torch.cuda.synchronize(); dt = time.perf_counter() - t0
+print("model_simulation_2sla, %d envs, episode <= 50 + look-ahead <= 10 (linear q on the obs): %.1f ms  (%.2fe6 episodes/s, %.1fe6 SAR tuples/s)" % (
+    m, dt * 1e3, m / dt / 1e6, float(res["n_actions"].sum()) / dt / 1e6))
 rngp = torch.Generator().manual_seed(0)
 picks = torch.randint(0, 16, (m,), generator=rngp).numpy()
 maps = torch.stack([torch.randperm(6, generator=rngp) for _ in range(m)]).to(torch.uint8).numpy()

@@ -387,12 +387,176 @@ def gen_mt_episodes():
     print("mt_episodes.npz")
 
 
+def gen_agent_act(ref):
+    """Agent01.act (agent01.py:157-218) called UNBOUND with a stub self (no TensorFlow): the -inf masks for every
+    (finger, last action), argmax incl. ties, the support of the epsilon-greedy branch and the Boltzmann probabilities
+    np.random.choice is handed (captured), for q-values the test feeds to ppad_select_actions / ppad_policy_step."""
+    import types
+    A = ref.agent01.Agent01
+    rng = np.random.default_rng(77)
+    rows, cols = 5, 6
+
+    def make_stub(q, last):
+        stub = types.SimpleNamespace(st_shape=(rows, cols, 7), last_action=int(last))
+        stub.board_finger_to_state = lambda b, f: A.board_finger_to_state(stub, b, f)
+        stub.predict_from_state = lambda state, model: np.array([q], dtype=np.float32)
+        stub.action_verb = lambda a: A.action_verb(stub, a)
+        return stub
+
+    verbs = ['up', 'down', 'left', 'right', 'pass']
+    board = np.zeros((rows, cols), int)
+    # (1) masks + argmax: every finger x last action, q = descending so that the first allowed action wins, then random q
+    fingers, lasts, qs, acts = [], [], [], []
+    for r in range(rows):
+        for c in range(cols):
+            for last in range(5):
+                for k in range(4):
+                    q = np.array([5, 4, 3, 2, 1], np.float32) if k == 0 else \
+                        (np.round(rng.standard_normal(5) * 2) * 500).astype(np.float32) if k == 1 else \
+                        (rng.standard_normal(5) * 1000).astype(np.float32)
+                    stub = make_stub(q.copy(), last)
+                    a = verbs.index(A.act(stub, board, np.array([r, c]), 'A', 'max'))
+                    assert stub.last_action == a
+                    fingers.append([r, c]); lasts.append(last); qs.append(q); acts.append(a)
+    # (2) epsilon-greedy support: epsilon = 1 -> uniform over the actions that are not -inf
+    supp = []
+    np.random.seed(5)
+    for r in range(rows):
+        for c in range(cols):
+            for last in range(5):
+                seen = 0
+                for _ in range(60):
+                    stub = make_stub(np.zeros(5, np.float32), last)
+                    seen |= 1 << verbs.index(A.act(stub, board, np.array([r, c]), 'A', 'max', epsilon=1.0))
+                supp.append(seen)
+    # (3) Boltzmann: capture the probability vector handed to np.random.choice
+    bf, bl, bq, bb, bp = [], [], [], [], []
+    captured = {}
+    real_choice = np.random.choice
+
+    def fake_choice(n, p=None):
+        captured['p'] = np.array(p, np.float64)
+        return int(np.argmax(p))
+    ref.agent01.np.random.choice = fake_choice
+    try:
+        for _ in range(600):
+            r, c, last = int(rng.integers(rows)), int(rng.integers(cols)), int(rng.integers(5))
+            beta = float(10 ** rng.uniform(-4, -2))
+            q = (rng.standard_normal(5) * 1000).astype(np.float32)
+            stub = make_stub(q.copy(), last)
+            A.act(stub, board, np.array([r, c]), 'A', 'boltzmann', beta)
+            bf.append([r, c]); bl.append(last); bq.append(q); bb.append(beta); bp.append(captured['p'])
+    finally:
+        ref.agent01.np.random.choice = real_choice
+    np.savez_compressed(os.path.join(HERE, "agent_act.npz"), fingers=np.array(fingers), lasts=np.array(lasts), qs=np.array(qs),
+                        acts=np.array(acts), eps_support=np.array(supp), b_fingers=np.array(bf), b_lasts=np.array(bl),
+                        b_qs=np.array(bq), b_betas=np.array(bb), b_probs=np.array(bp))
+    print("agent_act.npz", len(acts), len(supp), len(bp))
+
+
+def gen_islands(ref):
+    """pad_utils.detect_island (utils.py:86-111) run as it is: random boards (few colours, some empties), random seeds,
+    orb types that do and do not match the seed cell, island arrays that start clear or partly marked."""
+    rng = np.random.default_rng(31)
+    out = {}
+    for rows, cols, n in ((5, 6, 1500), (6, 7, 800)):
+        boards = rng.integers(-1, 4, size=(n, rows, cols))
+        seeds = np.stack([rng.integers(0, rows, n), rng.integers(0, cols, n)], 1)
+        types = np.where(rng.random(n) < 0.8, boards[np.arange(n), seeds[:, 0], seeds[:, 1]], rng.integers(-1, 5, n))
+        pre = (rng.random((n, rows, cols)) < 0.15) & (rng.random(n) < 0.4)[:, None, None]
+        islands = np.zeros((n, rows, cols), np.uint8)
+        for i in range(n):
+            isl = pre[i].astype(float).copy()
+            ref.pad_utils.detect_island(boards[i], isl, int(seeds[i, 0]), int(seeds[i, 1]), int(types[i]))
+            islands[i] = isl != 0
+        tag = "%dx%d" % (rows, cols)
+        out.update({"boards_" + tag: boards.astype(np.int8), "seeds_" + tag: seeds.astype(np.int8),
+                    "types_" + tag: types.astype(np.int8), "pre_" + tag: pre.astype(np.uint8), "islands_" + tag: islands})
+    np.savez_compressed(os.path.join(HERE, "islands.npz"), **out)
+    print("islands.npz", {k: v.shape for k, v in out.items() if k.startswith("islands")})
+
+
+def gen_2sla(ref):
+    """model_simulation_2sla (projects/simulation.py:71-183), the reference driver's data-collection policy, run
+    UNMODIFIED: the two function definitions are compiled from the reference's source file (the module itself is a
+    training script that needs TensorFlow) into a namespace that provides what the script's globals provide.  Patches,
+    none of them game or search logic: env.reset() adopts prepared boards; random.shuffle puts the candidate moves into
+    the fixed order up, down, left, right (the reference's order is random and only decides ties); the agent is
+    Agent01.act UNBOUND on a stub whose network is a fixed integer-weight linear map of the one-hot observation."""
+    import ast
+    import types
+    src = open(os.path.join(rh.REFERENCE_ROOT, "projects", "simulation.py")).read()
+    tree = ast.parse(src)
+    funcs = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("model_simulation", "model_simulation_2sla")]
+    assert len(funcs) == 2
+    A = ref.agent01.Agent01
+    rows, cols = 5, 6
+    rng = np.random.default_rng(2024)
+    W = rng.integers(-9, 10, size=(rows * cols * 7, 5)).astype(np.int64)
+    W[:, 4] -= 1                                 # a slight reluctance to pass
+    order = ['up', 'down', 'left', 'right']
+    fake_random = types.SimpleNamespace(shuffle=lambda lst: lst.sort(key=order.index))
+    env = ref.game.PAD(skyfall_damage=False)
+    starts = []
+    real_reset = env.reset
+
+    def reset_from_list(board=None, finger=None):
+        b, f = starts.pop(0)
+        return real_reset(board=b, finger=f)
+    env.reset = reset_from_list
+    stub = types.SimpleNamespace(st_shape=(rows, cols, 7), last_action=4)
+    stub.board_finger_to_state = lambda b, f: A.board_finger_to_state(stub, b, f)
+    stub.predict_from_state = lambda state, model: (state.reshape(1, -1).astype(np.int64) @ W).astype(np.float32)
+    stub.action_verb = lambda a: A.action_verb(stub, a)
+    stub.act = lambda board, finger, model='A', method='max', beta=None, epsilon=0: A.act(stub, board, finger, model, method, beta, epsilon)
+    ns = dict(env=env, ppad=ref.ppad, illegal_actions=ref.pad_utils.illegal_actions, random=fake_random, np=np,
+              ACTION2ID={'up': 0, 'down': 1, 'left': 2, 'right': 3, 'pass': 4},
+              ID2ACTION={0: 'up', 1: 'down', 2: 'left', 3: 'right', 4: 'pass'},
+              NON_PASS_ACTIONS={'up', 'down', 'left', 'right'})
+    exec(compile(ast.Module(body=funcs, type_ignores=[]), "simulation.py", "exec"), ns)
+    out = dict(W=W, boards=[], fingers=[], n_actions=[], actions=[], final_reward=[], discounted=[], obs_boards=[], obs_fingers=[])
+    E, max_ep, max_la, gamma = 160, 12, 5, 0.95
+    verbs = ['up', 'down', 'left', 'right', 'pass']
+    walk = np.random.default_rng(9)
+    for e in range(E):
+        b, f = random_walk_board(walk, rows, cols, 6 if e % 3 else 4, 30)
+        b, f = b.astype(int), np.array(f)
+        starts.append((b.copy(), f.copy()))
+        sars, n_ep = ns["model_simulation_2sla"](stub, 1, gamma, log10_reward=False, policy='max', beta=None,
+                                                  max_episode_len=max_ep, max_lookahead_len=max_la)
+        assert n_ep == 1 and stub.last_action == 4
+        acts = [verbs.index(a) for a in env.actions]
+        pad = max_ep + max_la + 2
+        out["boards"].append(b); out["fingers"].append(f); out["n_actions"].append(len(acts))
+        out["actions"].append(acts + [255] * (pad - len(acts)))
+        out["final_reward"].append(float(env.rewards[-1]))
+        disc = [float(s[2]) for s in sars]
+        out["discounted"].append(disc + [0.0] * (pad - len(disc)))
+        ob = np.stack([o[0] for o in env.observations]); of = np.stack([o[1] for o in env.observations])
+        out["obs_boards"].append(np.concatenate([ob, np.zeros((pad - len(ob), rows, cols), ob.dtype)]))
+        out["obs_fingers"].append(np.concatenate([of, np.zeros((pad - len(of), 2), of.dtype)]))
+    res = {k: np.array(v) for k, v in out.items()}
+    res.update(max_episode_len=max_ep, max_lookahead_len=max_la, gamma=gamma)
+    np.savez_compressed(os.path.join(HERE, "sim_2sla.npz"), **res)
+    n = res["n_actions"]
+    print("sim_2sla.npz episodes", E, "actions per episode min/mean/max", n.min(), n.mean(), n.max(),
+          "nonzero rewards", int((res["final_reward"] > 0).sum()))
+
+
 def main():
     ref = rh.load()
+    if "--agent" in sys.argv:      # only the fixtures of the callers either side of the step
+        gen_agent_act(ref)
+        gen_2sla(ref)
+        gen_islands(ref)
+        return
     if "--all10" in sys.argv:      # only the fixtures of the 4-bit (orb types 0..9) kernels
         gen_resolve(5, 6, 700, 150, 205, "5x6_all10", ncolors=10)
         gen_resolve(6, 7, 300, 60, 206, "6x7_all10", ncolors=10)
         return
+    gen_agent_act(ref)
+    gen_2sla(ref)
+    gen_islands(ref)
     gen_kat(ref)
     gen_onehot(ref)
     gen_damage()

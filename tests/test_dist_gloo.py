@@ -36,6 +36,17 @@ def _worker(rank, world, port, out):
     state = torch.arange(n_local * 4, dtype=torch.int32).reshape(n_local, 4) + rank * 100000
     action = torch.full((n_local,), rank, dtype=torch.uint8)
     s, a, r = pdist.gather_replay_sample(state, action, reward, 32, generator=g)
+    # the rollout's single packed all-gather: stats vector + sampled rows of every rank in one collective
+    vec = pdist.local_stats(reward, info)
+    g_stats, g_state, g_action, g_reward, buf = pdist.gather_rollout_window(vec, state[:8], action[:8], reward[:8])
+    assert g_stats.shape == (world, 40) and torch.equal(g_stats[rank], vec)
+    for peer in range(world):
+        assert torch.equal(g_state[8 * peer:8 * peer + 8], torch.arange(32, dtype=torch.int32).reshape(8, 4) + peer * 100000)
+        assert bool((g_action[8 * peer:8 * peer + 8] == peer).all())
+    assert torch.equal(g_reward[8 * rank:8 * rank + 8], reward[:8])
+    assert pdist.merge_stats(g_stats) == stats
+    again = pdist.gather_rollout_window(vec, state[:8], action[:8], reward[:8], out=buf)
+    assert again[4].data_ptr() == buf.data_ptr()
     if rank == 0:
         out.put((stats, s.numpy(), a.numpy(), r.numpy(), reward.numpy(), combos.numpy(), depth.numpy()))
     else:

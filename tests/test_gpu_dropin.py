@@ -403,7 +403,128 @@ def test_smart_data_and_lookahead(pb):
         return torch.randn(o.shape[0], 5, device=o.device, generator=torch.Generator(device=o.device).manual_seed(1)) * 100
     res = two_step_lookahead(env, q_fn=q_fn, policy='boltzmann', beta=1e-2, max_lookahead_len=6)
     roam = res["roam_actions"].cpu().numpy()
-    assert ((roam <= 4) | (roam == 255)).all() and (roam[:, :, :4] != 255).any()
+    assert roam.shape[2] == 5 and (roam <= 5).all() and (roam[:, :, :4] < 4).any()      # moves, a PASS, then NOOPs
+    for seq in roam.reshape(-1, 5)[::97]:
+        k = int(np.argmax(seq >= 4)) if (seq >= 4).any() else 5
+        assert (seq[:k] < 4).all() and (k == 5 or seq[k] in (4, 5)) and (seq[k + 1:] == 5).all()
+
+
+def test_agent_act_fixtures_from_the_reference(pb):
+    """f1 pinned to the reference itself: tests/golden/agent_act.npz holds Agent01.act
+    (agent01.py:157-218) called unbound with a stub self -- masks + argmax incl. ties for every (finger, last action),
+    the support of the epsilon-greedy branch, and the probability vectors the Boltzmann branch hands np.random.choice."""
+    z = np.load(os.path.join(G, "agent_act.npz"))
+    rows, cols = 5, 6
+    # (1) argmax with the -inf masks: exact
+    n = len(z["acts"])
+    env = pb.BatchedPAD(n, rows, cols, seed=5)
+    env.set_state(np.zeros((n, rows, cols), np.int8), z["fingers"], z["lasts"].astype(np.uint8))
+    got = env.select_actions(z["qs"], method='max', step=3).cpu().numpy()
+    assert np.array_equal(got, z["acts"])
+    # the fused policy step picks the same actions (no auto-reset, so that the state keeps the moves apart)
+    out = env.policy_step(z["qs"], method='max', auto_reset=False, step=3)
+    assert np.array_equal(out.action.cpu().numpy(), z["acts"])
+    # (2) epsilon = 1: uniform over exactly the reference's support
+    combos = [(r, c, last) for r in range(rows) for c in range(cols) for last in range(5)]
+    reps = 400
+    m = len(combos) * reps
+    env = pb.BatchedPAD(m, rows, cols, seed=6)
+    f = np.repeat(np.array([[r, c] for r, c, _ in combos]), reps, 0)
+    last = np.repeat(np.array([l for _, _, l in combos], np.uint8), reps)
+    env.set_state(np.zeros((m, rows, cols), np.int8), f, last)
+    acts = env.select_actions(np.zeros((m, 5), np.float32), method='max', epsilon=1.0, step=9).cpu().numpy().reshape(len(combos), reps)
+    for k in range(len(combos)):
+        seen = int(np.bitwise_or.reduce(1 << acts[k].astype(np.int64)))
+        assert seen == int(z["eps_support"][k]), (combos[k], seen, int(z["eps_support"][k]))
+        counts = np.bincount(acts[k], minlength=5)[[a for a in range(5) if (seen >> a) & 1]]
+        assert counts.min() > reps / len(counts) * 0.5                    # roughly uniform
+    # (3) Boltzmann: the action is the inverse-CDF draw of the REFERENCE's probability vector at the kernel's uniform
+    nb = len(z["b_betas"])
+    for i0 in range(0, nb, 100):                                          # beta is a launch constant: a few launches
+        sel = np.arange(i0, min(nb, i0 + 100))
+        for i in sel[:12]:
+            env1 = pb.BatchedPAD(512, rows, cols, seed=70 + int(i), env0=1000 * int(i))
+            env1.set_state(np.zeros((512, rows, cols), np.int8), np.tile(z["b_fingers"][i], (512, 1)),
+                           np.full(512, z["b_lasts"][i], np.uint8))
+            q = np.tile(z["b_qs"][i], (512, 1)).astype(np.float32)
+            a = env1.select_actions(q, method='boltzmann', beta=float(z["b_betas"][i]), step=2).cpu().numpy()
+            p = z["b_probs"][i]
+            cdf = np.cumsum(p) / np.sum(p)                                # np.random.choice: cdf /= cdf[-1]
+            u = np.array([orc.draw(70 + int(i), 1000 * int(i) + j, 2, orc.STREAM_POLICY, 1) for j in range(512)]) / 2.0 ** 32
+            want = np.minimum(np.searchsorted(cdf, u, side='right'), 4)
+            near = np.abs(cdf[None, :] - u[:, None]).min(1) < 1e-6         # float32 exp vs the reference's: boundary cases
+            assert ((a == want) | near).all() and (a == want).mean() > 0.99, i
+            assert (p[a] > 0).all()                                       # never an action the reference masks
+
+
+def test_model_simulation_2sla_replays_the_references_episodes(pb):
+    """f4 pinned to the reference itself: tests/golden/sim_2sla.npz holds 160 episodes of the
+    UNMODIFIED model_simulation_2sla (projects/simulation.py:71-183) with a deterministic linear q-function and the
+    candidate order fixed; the device-side version (lookahead.model_simulation_2sla: no host sync, all boards in lock
+    step) must produce the same actions, observations, final rewards and discounted returns."""
+    from ppad_b200.lookahead import model_simulation_2sla
+    z = np.load(os.path.join(G, "sim_2sla.npz"))
+    E = len(z["n_actions"])
+    rows, cols = 5, 6
+    env = pb.BatchedPAD(E, rows, cols, skyfall_damage=False, seed=1)
+    env.set_state(z["boards"], z["fingers"])
+    W = torch.from_numpy(z["W"].astype(np.float32)).to(env.device)       # small integers: exact in float32
+
+    def q_fn(obs):
+        return obs.reshape(obs.shape[0], -1) @ W
+    launches0 = pb._cabi.lib().ppad_launch_count()
+    res = model_simulation_2sla(env, q_fn, policy='max', max_episode_len=int(z["max_episode_len"]),
+                                max_lookahead_len=int(z["max_lookahead_len"]), gamma=float(z["gamma"]), log10_reward=False,
+                                reset=False)
+    assert pb._cabi.lib().ppad_launch_count() - launches0 < 120          # a fixed number of launches, none per board
+    n_act = res["n_actions"].cpu().numpy()
+    assert np.array_equal(n_act, z["n_actions"])
+    assert np.array_equal(res["actions"].cpu().numpy(), z["actions"].astype(np.uint8))
+    assert np.array_equal(bits(res["final_reward"].cpu().numpy()), bits(z["final_reward"]))
+    T = z["actions"].shape[1]
+    mask = np.arange(T)[None, :] < n_act[:, None]
+    assert np.array_equal(bits(res["discounted"].cpu().numpy()[mask]), bits(z["discounted"][mask]))
+    st = env.get_state(res["states"].reshape(E * T, -1).contiguous())
+    ob = st.boards.cpu().numpy().reshape(E, T, rows, cols)
+    of = st.fingers.cpu().numpy().reshape(E, T, 2)
+    assert np.array_equal(ob[mask], z["obs_boards"][mask]) and np.array_equal(of[mask], z["obs_fingers"][mask])
+    assert (z["final_reward"] > 0).sum() > E // 2 and n_act.min() < 5 and n_act.max() == T     # the fixture spans the cases
+    # Boltzmann roaming: same machinery, sequences stay legal (replayed with the oracle's move rule)
+    env2 = pb.BatchedPAD(2000, rows, cols, skyfall_damage=False, seed=8)
+    res2 = model_simulation_2sla(env2, q_fn, policy='boltzmann', beta=0.05, max_episode_len=6, max_lookahead_len=4)
+    a2, n2 = res2["actions"].cpu().numpy(), res2["n_actions"].cpu().numpy()
+    st2 = env2.get_state(res2["states"].reshape(2000 * a2.shape[1], -1).contiguous())
+    b2 = st2.boards.cpu().numpy().reshape(2000, a2.shape[1], rows, cols).astype(np.int8)
+    f2 = st2.fingers.cpu().numpy().reshape(2000, a2.shape[1], 2).astype(np.int32)
+    for i in range(0, 2000, 41):
+        assert a2[i, n2[i] - 1] == 4 and (a2[i, :n2[i] - 1] < 4).all() and (a2[i, n2[i]:] == 255).all()
+        for t in range(n2[i] - 1):
+            b, f = b2[i, t].copy(), f2[i, t].copy()
+            assert orc.apply_action(b, f, int(a2[i, t])) == 1
+            assert np.array_equal(b, b2[i, t + 1]) and np.array_equal(f, f2[i, t + 1])
+
+
+def test_detect_island_fixture_from_the_reference(pb):
+    """pad_utils.detect_island (utils.py:86-111) as a callable (VERDICT r1 missing #5): tests/golden/islands.npz holds
+    the reference's own flood fills, with clear and with pre-marked island arrays, seeds on and off the orb type."""
+    z = np.load(os.path.join(G, "islands.npz"))
+    for tag in ("5x6", "6x7"):
+        boards, seeds, types, pre, want = (z["%s_%s" % (k, tag)] for k in ("boards", "seeds", "types", "pre", "islands"))
+        n, rows, cols = boards.shape
+        env = pb.BatchedPAD(n, rows, cols, seed=1)
+        env.set_state(boards, np.zeros((n, 2), np.int64))
+        w = (1 << np.arange(rows * cols, dtype=np.uint64))
+        pre_mask = (pre.reshape(n, -1).astype(np.uint64) * w).sum(1).astype(np.uint64).view(np.int64)
+        got = env.islands(seeds, types, pre_mask).cpu().numpy().view(np.uint64)
+        got_cells = ((got[:, None] >> np.arange(rows * cols, dtype=np.uint64)) & np.uint64(1)).reshape(n, rows, cols)
+        assert np.array_equal(got_cells, (want != 0).astype(np.uint64)), tag
+    # the drop-in free function mutates `island` in place like the reference
+    from ppad_b200.pad import utils as pad_utils
+    boards, seeds, types, pre, want = (z["%s_5x6" % k] for k in ("boards", "seeds", "types", "pre", "islands"))
+    for i in range(0, len(boards), 97):
+        island = pre[i].astype(float).copy()
+        pad_utils.detect_island(boards[i].astype(int), island, int(seeds[i, 0]), int(seeds[i, 1]), int(types[i]))
+        assert np.array_equal(island != 0, want[i] != 0), i
 
 
 @pytest.mark.parametrize("zero_copy", [True, False, "hybrid"])

@@ -159,7 +159,7 @@ def test_step_fuzz_vs_oracle(pb, rows, cols, mode):
     fmt = 'planes3' if mode.startswith("planes3") else 'nibbles'     # PPAD_SLAB_PLANES3: bit-sliced 3-bit slab
     for t in range(steps):
         inj = rng.integers(0, 10 if all10 else 6, size=(n, S)).astype(np.uint8) if S else None
-        actions = None if t % 3 == 2 else rng.integers(0, 5, size=n).astype(np.uint8)
+        actions = None if t % 3 == 2 else rng.integers(0, 6, size=n).astype(np.uint8)   # 5 = PPAD_NOOP
         if t == 4:
             actions[:50] = 9
         kw = dict(eval_moves=(t % 4 != 3), auto_reset=(t % 2 == 0), max_moves=5)

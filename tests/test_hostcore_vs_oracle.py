@@ -87,7 +87,7 @@ def test_step_batch_fuzz(rows, cols, mode):
         if t % 3 == 2:
             actions = None                                   # in-kernel random policy
         else:
-            actions = rng.integers(0, 5, size=n).astype(np.uint8)   # includes off-board moves and passes
+            actions = rng.integers(0, 6, size=n).astype(np.uint8)   # includes off-board moves, passes and no-ops (5)
             if t == 4:
                 actions[:50] = 9                             # bad action ids
         kw = dict(actions=actions, eval_moves=(t % 4 != 3), auto_reset=(t % 2 == 0), max_moves=5,
