@@ -6,10 +6,11 @@ namespace ppad {
 
 // Agent01.act after the network (agent01.py:173-218): Q-values -> one action per board
 template <class G>
-__global__ void __launch_bounds__(BLOCK) select_kernel(int64_t n, uint64_t env0, RngKey key, const void *state,
+__global__ void __launch_bounds__(BLOCK) select_kernel(const DynGeomData dg, int64_t n, uint64_t env0, RngKey key, const void *state,
                                                        const float *q, int method, float beta, float epsilon,
                                                        int max_moves, uint8_t *actions)
 {
+    geom_enter<G>(dg);
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     if (i >= n) return;
     const State<G> s = StateIO<G>::load(state, i);
@@ -93,8 +94,7 @@ int ppad_select_actions(const ppad_ctx *ctx, int64_t n, uint64_t env0, uint32_t 
         return fail(PPAD_ERR_INVALID, "ERROR: Unknown action method!");
     RngKey key = ctx->base.key;
     key.step = step;
-    PPAD_DISPATCH(ctx, (select_kernel<G><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(
-                           n, env0, key, state, q, method, beta, epsilon, max_moves, actions)));
+    PPAD_DISPATCH(ctx, (select_kernel<G><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(ctx->base.dyn, n, env0, key, state, q, method, beta, epsilon, max_moves, actions)));
     return after_launch("select_kernel");
 }
 

@@ -14,12 +14,12 @@ enum : int { SELECT_MAX = 0, SELECT_BOLTZMANN = 1 };
 template <class G>
 PPAD_HD int agent_allowed_mask(int finger, int last_action)
 {
-    const int r = finger / G::C, c = finger - r * G::C;
+    const int r = finger / G::cols(), c = finger - r * G::cols();
     int m = 31;
     if (r == 0) m &= ~1;
-    else if (r == G::R - 1) m &= ~2;
+    else if (r == G::rows() - 1) m &= ~2;
     if (c == 0) m &= ~4;
-    else if (c == G::C - 1) m &= ~8;
+    else if (c == G::cols() - 1) m &= ~8;
     if (last_action < 4) m &= ~(1 << (last_action ^ 1));
     return m;
 }

@@ -10,10 +10,11 @@ std::atomic<uint64_t> g_launches{0};
 int pool_occupancy(int geom);   // ppad_step.cu
 
 template <class G>
-__global__ void __launch_bounds__(BLOCK) encode_kernel(int64_t n, const void *state, void *obs, int obs_dtype)
+__global__ void __launch_bounds__(BLOCK) encode_kernel(const DynGeomData dg, int64_t n, const void *state, void *obs, int obs_dtype)
 {
+    geom_enter<G>(dg);
     __shared__ ObsShared obs_sh;
-    __shared__ uint32_t obs_stream[(BLOCK / 32) * ObsGeom<G>::WARP_WORDS];
+    __shared__ uint32_t obs_stream[G::DYNAMIC ? 1 : (BLOCK / 32) * ObsGeom<G>::WARP_WORDS];
     obs_init_luts(obs_sh);
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
@@ -24,8 +25,8 @@ __global__ void __launch_bounds__(BLOCK) encode_kernel(int64_t n, const void *st
     const int64_t warp0 = i - (threadIdx.x & 31);
     if (warp0 < n) {
         const int n_valid = (int)(n - warp0 < 32 ? n - warp0 : 32);
-        emit_obs<G>(s, valid, n_valid, obs_stream + (threadIdx.x >> 5) * ObsGeom<G>::WARP_WORDS, obs_sh,
-                    obs_warp_ptr<G>(obs, warp0, obs_dtype), obs_dtype);
+        emit_obs_any<G>(s, valid, n_valid, obs_stream + (threadIdx.x >> 5) * ObsGeom<G>::WARP_WORDS, obs_sh,
+                        obs_warp_ptr<G>(obs, warp0, obs_dtype), obs_dtype);
     }
 }
 
@@ -43,6 +44,7 @@ struct ResetKernelArgs {
 template <class G>
 __global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ ResetKernelArgs a)
 {
+    geom_enter<G>(a.p.dyn);
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     const bool valid = i < a.n;                  // every lane takes part: the rejection sampling is warp-cooperative
     int finger = -1;
@@ -51,12 +53,12 @@ __global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ Re
         // a finger off the board would spill into the neighbouring meta fields and drive shifts past the plane width:
         // clamp it and say so
         int fr = a.fingers_in[2 * i], fc = a.fingers_in[2 * i + 1];
-        if ((unsigned)fr >= (unsigned)G::R || (unsigned)fc >= (unsigned)G::C) {
+        if ((unsigned)fr >= (unsigned)G::rows() || (unsigned)fc >= (unsigned)G::cols()) {
             finger_flag = FLAG_REJECTED;
-            fr = fr < 0 ? 0 : (fr >= G::R ? G::R - 1 : fr);
-            fc = fc < 0 ? 0 : (fc >= G::C ? G::C - 1 : fc);
+            fr = fr < 0 ? 0 : (fr >= G::rows() ? G::rows() - 1 : fr);
+            fc = fc < 0 ? 0 : (fc >= G::cols() ? G::cols() - 1 : fc);
         }
-        finger = fr * G::C + fc;
+        finger = fr * G::cols() + fc;
     }
     State<G> s;
     clear_state<G>(s);
@@ -74,14 +76,15 @@ __global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ Re
 // consecutive threads on consecutive elements and parks one code byte per cell (0x80 = a value that is no orb type);
 // then every thread packs its own board from there.
 template <class G, class T>
-__global__ void __launch_bounds__(BLOCK) pack_kernel(int64_t n, const T *boards, const T *fingers, const uint8_t *prev,
+__global__ void __launch_bounds__(BLOCK) pack_kernel(const DynGeomData dg, int64_t n, const T *boards, const T *fingers, const uint8_t *prev,
                                                      const uint16_t *moves, void *state, uint8_t *flags)
 {
-    __shared__ uint8_t codes[BLOCK * G::CELLS];
+    geom_enter<G>(dg);
+    __shared__ uint8_t codes[BLOCK * G::MAX_CELLS];
     const int64_t tile0 = (int64_t)blockIdx.x * BLOCK;
     const int64_t left = n - tile0;
-    const int count = (int)(left < BLOCK ? left : BLOCK) * G::CELLS;
-    const T *in = boards + (size_t)tile0 * G::CELLS;
+    const int count = (int)(left < BLOCK ? left : BLOCK) * G::cells();
+    const T *in = boards + (size_t)tile0 * G::cells();
     for (int e = threadIdx.x; e < count; e += BLOCK) {
         const long long v = (long long)in[e];
         codes[e] = v == -1 ? (uint8_t)G::EMPTY : ((v >= 0 && v < G::NTYPES) ? (uint8_t)v : (uint8_t)0x80);
@@ -89,11 +92,11 @@ __global__ void __launch_bounds__(BLOCK) pack_kernel(int64_t n, const T *boards,
     __syncthreads();
     const int64_t i = tile0 + threadIdx.x;
     if (i >= n) return;
-    int8_t cells[G::CELLS];
+    int8_t cells[G::MAX_CELLS];
     bool bad = false;
 #pragma unroll
-    for (int c = 0; c < G::CELLS; c++) {
-        const uint8_t v = codes[threadIdx.x * G::CELLS + c];
+    for (int c = 0; c < G::cells(); c++) {
+        const uint8_t v = codes[threadIdx.x * G::cells() + c];
         bad |= v == 0x80;
         cells[c] = v == 0x80 || v == G::EMPTY ? (int8_t)-1 : (int8_t)v;
     }
@@ -101,14 +104,14 @@ __global__ void __launch_bounds__(BLOCK) pack_kernel(int64_t n, const T *boards,
     pack_cells<G, int8_t>(b, cells);
     long long fr = (long long)fingers[2 * i], fc = (long long)fingers[2 * i + 1];
     uint32_t fl = bad ? (uint32_t)FLAG_UNSUPPORTED_ORB : 0u;
-    if (fr < 0 || fr >= G::R || fc < 0 || fc >= G::C) {   // see reset_kernel: clamp and flag
+    if (fr < 0 || fr >= G::rows() || fc < 0 || fc >= G::cols()) {   // see reset_kernel: clamp and flag
         fl |= FLAG_REJECTED;
-        fr = fr < 0 ? 0 : (fr >= G::R ? G::R - 1 : fr);
-        fc = fc < 0 ? 0 : (fc >= G::C ? G::C - 1 : fc);
+        fr = fr < 0 ? 0 : (fr >= G::rows() ? G::rows() - 1 : fr);
+        fc = fc < 0 ? 0 : (fc >= G::cols() ? G::cols() - 1 : fc);
     }
     int pv = prev ? prev[i] : ACT_PASS;
     if (pv > ACT_PASS) pv = ACT_PASS;                     // 3-bit field; anything else reads as 'pass'
-    StateIO<G>::store(state, i, b, meta_pack((int)(fr * G::C + fc), pv, moves ? moves[i] : 0));
+    StateIO<G>::store(state, i, b, meta_pack((int)(fr * G::cols() + fc), pv, moves ? moves[i] : 0));
     if (flags) flags[i] = (uint8_t)fl;
 }
 
@@ -116,9 +119,10 @@ __global__ void __launch_bounds__(BLOCK) pack_kernel(int64_t n, const T *boards,
 // 32 scattered runs per warp instruction; instead the CTA parks its 256 boards' planes in shared memory and then
 // writes its contiguous output region element by element, consecutive threads -> consecutive addresses.
 template <class G, class T>
-__global__ void __launch_bounds__(BLOCK) unpack_kernel(int64_t n, const void *state, T *boards, T *fingers, uint8_t *prev,
+__global__ void __launch_bounds__(BLOCK) unpack_kernel(const DynGeomData dg, int64_t n, const void *state, T *boards, T *fingers, uint8_t *prev,
                                                        uint16_t *moves)
 {
+    geom_enter<G>(dg);
     typedef typename G::W W;
     __shared__ W planes[G::NP][BLOCK];
     const int64_t tile0 = (int64_t)blockIdx.x * BLOCK;
@@ -131,8 +135,8 @@ __global__ void __launch_bounds__(BLOCK) unpack_kernel(int64_t n, const void *st
         PPAD_P4(planes[3][threadIdx.x] = s.b.b3)
         const int f = meta_finger(s.meta);
         if (fingers) {
-            fingers[2 * i] = (T)(f / G::C);
-            fingers[2 * i + 1] = (T)(f % G::C);
+            fingers[2 * i] = (T)(f / G::cols());
+            fingers[2 * i + 1] = (T)(f % G::cols());
         }
         if (prev) prev[i] = (uint8_t)meta_prev(s.meta);
         if (moves) moves[i] = (uint16_t)meta_moves(s.meta);
@@ -140,10 +144,10 @@ __global__ void __launch_bounds__(BLOCK) unpack_kernel(int64_t n, const void *st
     if (!boards) return;
     __syncthreads();
     const int64_t left = n - tile0;
-    const int count = (int)(left < BLOCK ? left : BLOCK) * G::CELLS;
-    T *out = boards + (size_t)tile0 * G::CELLS;
+    const int count = (int)(left < BLOCK ? left : BLOCK) * G::cells();
+    T *out = boards + (size_t)tile0 * G::cells();
     for (int e = threadIdx.x; e < count; e += BLOCK) {
-        const int b = e / G::CELLS, c = e - b * G::CELLS;
+        const int b = e / G::cells(), c = e - b * G::cells();
         int code = 0;
 #pragma unroll
         for (int j = 0; j < G::NP; j++) code |= (int)((planes[j][b] >> c) & 1) << j;
@@ -152,9 +156,10 @@ __global__ void __launch_bounds__(BLOCK) unpack_kernel(int64_t n, const void *st
 }
 
 template <class G>
-__global__ void __launch_bounds__(BLOCK) cancel_kernel(int64_t n, void *state, uint8_t *n_combos, uint16_t *combo_log,
+__global__ void __launch_bounds__(BLOCK) cancel_kernel(const DynGeomData dg, int64_t n, void *state, uint8_t *n_combos, uint16_t *combo_log,
                                                        int log_cap)
 {
+    geom_enter<G>(dg);
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     if (i >= n) return;
     State<G> s = StateIO<G>::load(state, i);
@@ -172,35 +177,37 @@ __global__ void __launch_bounds__(BLOCK) cancel_kernel(int64_t n, void *state, u
 // mark is still 0; cells already marked in `island_in` are therefore never entered (nor expanded), the seed itself is
 // expanded even when it is marked.  Result = island_in | cells reached.
 template <class G>
-__global__ void __launch_bounds__(BLOCK) island_kernel(int64_t n, const void *state, const uint8_t *seed, const int8_t *type,
+__global__ void __launch_bounds__(BLOCK) island_kernel(const DynGeomData dg, int64_t n, const void *state, const uint8_t *seed, const int8_t *type,
                                                        const uint64_t *island_in, uint64_t *island_out)
 {
+    geom_enter<G>(dg);
     typedef typename G::W W;
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     if (i >= n) return;
     const State<G> s = StateIO<G>::load(state, i);
-    const W pre = island_in ? (W)island_in[i] & G::BOARD : (W)0;
+    const W pre = island_in ? (W)island_in[i] & G::board() : (W)0;
     const int cell = seed[i];
     const int t = type[i] == -1 ? G::EMPTY : type[i];      // -1 = empty cells: the reference floods those, too
     W out = pre;
-    if (cell < G::CELLS && t >= 0 && code_at<G>(s.b, cell) == t) {
+    if (cell < G::cells() && t >= 0 && code_at<G>(s.b, cell) == t) {
         // er / ed: same code as the right / lower neighbour (empty cells included, unlike match_mask)
         W xr = (s.b.b0 ^ (s.b.b0 >> 1)) | (s.b.b1 ^ (s.b.b1 >> 1)) | (s.b.b2 ^ (s.b.b2 >> 1));
-        W xd = (s.b.b0 ^ (s.b.b0 >> G::C)) | (s.b.b1 ^ (s.b.b1 >> G::C)) | (s.b.b2 ^ (s.b.b2 >> G::C));
-        PPAD_P4(xr |= s.b.b3 ^ (s.b.b3 >> 1); xd |= s.b.b3 ^ (s.b.b3 >> G::C))
-        W er = ~xr & G::NOT_LASTCOL, ed = ~xd & G::NOT_LASTROW;
+        W xd = (s.b.b0 ^ (s.b.b0 >> G::cols())) | (s.b.b1 ^ (s.b.b1 >> G::cols())) | (s.b.b2 ^ (s.b.b2 >> G::cols()));
+        PPAD_P4(xr |= s.b.b3 ^ (s.b.b3 >> 1); xd |= s.b.b3 ^ (s.b.b3 >> G::cols()))
+        W er = ~xr & G::not_lastcol(), ed = ~xd & G::not_lastrow();
         const W bit = G::ONE << cell;
         const W open = ~pre | bit;                        // cells the flood may stand on
         er &= open & (open >> 1);
-        ed &= open & (open >> G::C);
+        ed &= open & (open >> G::cols());
         out |= closure<G>(bit, er, ed);
     }
     island_out[i] = (uint64_t)out;
 }
 
 template <class G>
-__global__ void __launch_bounds__(BLOCK) legal_kernel(int64_t n, const void *state, uint8_t *mask)
+__global__ void __launch_bounds__(BLOCK) legal_kernel(const DynGeomData dg, int64_t n, const void *state, uint8_t *mask)
 {
+    geom_enter<G>(dg);
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     if (i >= n) return;
     const State<G> s = StateIO<G>::load(state, i);
@@ -211,9 +218,10 @@ __global__ void __launch_bounds__(BLOCK) legal_kernel(int64_t n, const void *sta
 
 // PlayerAction.sample (player.py:38-66): same draw as the in-kernel policy of step_kernel
 template <class G>
-__global__ void __launch_bounds__(BLOCK) sample_kernel(int64_t n, uint64_t env0, RngKey key, const void *state,
+__global__ void __launch_bounds__(BLOCK) sample_kernel(const DynGeomData dg, int64_t n, uint64_t env0, RngKey key, const void *state,
                                                        int include_pass, uint8_t *actions)
 {
+    geom_enter<G>(dg);
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     if (i >= n) return;
     const State<G> s = StateIO<G>::load(state, i);
@@ -229,8 +237,9 @@ __global__ void __launch_bounds__(BLOCK) sample_kernel(int64_t n, uint64_t env0,
 
 // PAD.drop (game.py:201-221), in place
 template <class G>
-__global__ void __launch_bounds__(BLOCK) drop_kernel(int64_t n, void *state)
+__global__ void __launch_bounds__(BLOCK) drop_kernel(const DynGeomData dg, int64_t n, void *state)
 {
+    geom_enter<G>(dg);
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     if (i >= n) return;
     State<G> s = StateIO<G>::load(state, i);
@@ -242,6 +251,7 @@ __global__ void __launch_bounds__(BLOCK) drop_kernel(int64_t n, void *state)
 template <class G>
 __global__ void __launch_bounds__(BLOCK) fill_kernel(const __grid_constant__ ResetKernelArgs a, int reset_all)
 {
+    geom_enter<G>(a.p.dyn);
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     if (i >= a.n) return;
     RngKey key = a.p.key;
@@ -272,8 +282,9 @@ __global__ void __launch_bounds__(BLOCK) damage_kernel(int64_t n, const __grid_c
 
 // permutation_mapping (smart_data.py:94-108): every orb type t of board i becomes maps[i][t]
 template <class G>
-__global__ void __launch_bounds__(BLOCK) permute_kernel(int64_t n, void *state, const uint8_t *maps)
+__global__ void __launch_bounds__(BLOCK) permute_kernel(const DynGeomData dg, int64_t n, void *state, const uint8_t *maps)
 {
+    geom_enter<G>(dg);
     typedef typename G::W W;
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     if (i >= n) return;
@@ -282,7 +293,7 @@ __global__ void __launch_bounds__(BLOCK) permute_kernel(int64_t n, void *state, 
     const uint64_t lut = (uint64_t)m2.x | ((uint64_t)m2.y << 32);
     W p0 = 0, p1 = 0, p2 = 0, p3 = 0;
 #pragma unroll
-    for (int c = 0; c < G::CELLS; c++) {
+    for (int c = 0; c < G::cells(); c++) {
         const int code = code_at<G>(s.b, c);
         const int to = code > 6 ? code : (int)((lut >> (8 * code)) & 7);   // empty cells and types 7..9 stay
         p0 |= (W)(to & 1) << c;
@@ -302,17 +313,17 @@ __global__ void __launch_bounds__(BLOCK) permute_kernel(int64_t n, void *state, 
 using namespace ppad;
 
 template <class G, class T>
-static void launch_pack(int64_t n, const void *boards, const void *fingers, const uint8_t *prev, const uint16_t *moves,
+static void launch_pack(const ppad_ctx *ctx, int64_t n, const void *boards, const void *fingers, const uint8_t *prev, const uint16_t *moves,
                         void *state, uint8_t *flags, cudaStream_t st)
 {
-    pack_kernel<G, T><<<grid_for(n), BLOCK, 0, st>>>(n, (const T *)boards, (const T *)fingers, prev, moves, state, flags);
+    pack_kernel<G, T><<<grid_for(n), BLOCK, 0, st>>>(ctx->base.dyn, n, (const T *)boards, (const T *)fingers, prev, moves, state, flags);
 }
 
 template <class G, class T>
-static void launch_unpack(int64_t n, const void *state, void *boards, void *fingers, uint8_t *prev, uint16_t *moves,
+static void launch_unpack(const ppad_ctx *ctx, int64_t n, const void *state, void *boards, void *fingers, uint8_t *prev, uint16_t *moves,
                           cudaStream_t st)
 {
-    unpack_kernel<G, T><<<grid_for(n), BLOCK, 0, st>>>(n, state, (T *)boards, (T *)fingers, prev, moves);
+    unpack_kernel<G, T><<<grid_for(n), BLOCK, 0, st>>>(ctx->base.dyn, n, state, (T *)boards, (T *)fingers, prev, moves);
 }
 
 extern "C" {
@@ -359,6 +370,7 @@ int64_t ppad_state_bytes_ex(int rows, int cols, int orb_bits)
     if (rows == 5 && cols == 6) return wide ? G56W::STATE_BYTES : G56::STATE_BYTES;
     if (rows == 6 && cols == 7) return wide ? G67W::STATE_BYTES : G67::STATE_BYTES;
     if (rows == 4 && cols == 5) return wide ? G45W::STATE_BYTES : G45::STATE_BYTES;
+    if (rows >= 1 && cols >= 1 && rows * cols <= 64) return wide ? GDYNW::STATE_BYTES : GDYN::STATE_BYTES;
     return -1;
 }
 
@@ -409,9 +421,9 @@ int ppad_pack(const ppad_ctx *ctx, int64_t n, const void *boards, const void *fi
     if (!boards || !fingers || !state) return fail(PPAD_ERR_INVALID, "ppad_pack: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     switch (dtype) {
-    case PPAD_I8: PPAD_DISPATCH(ctx, (launch_pack<G, int8_t>(n, boards, fingers, prev, moves, state, flags, st))); break;
-    case PPAD_I32: PPAD_DISPATCH(ctx, (launch_pack<G, int32_t>(n, boards, fingers, prev, moves, state, flags, st))); break;
-    case PPAD_I64: PPAD_DISPATCH(ctx, (launch_pack<G, int64_t>(n, boards, fingers, prev, moves, state, flags, st))); break;
+    case PPAD_I8: PPAD_DISPATCH(ctx, (launch_pack<G, int8_t>(ctx, n, boards, fingers, prev, moves, state, flags, st))); break;
+    case PPAD_I32: PPAD_DISPATCH(ctx, (launch_pack<G, int32_t>(ctx, n, boards, fingers, prev, moves, state, flags, st))); break;
+    case PPAD_I64: PPAD_DISPATCH(ctx, (launch_pack<G, int64_t>(ctx, n, boards, fingers, prev, moves, state, flags, st))); break;
     default: return fail(PPAD_ERR_UNSUPPORTED, "ppad_pack: dtype must be PPAD_I8, PPAD_I32 or PPAD_I64");
     }
     return after_launch("pack_kernel");
@@ -425,9 +437,9 @@ int ppad_unpack(const ppad_ctx *ctx, int64_t n, const void *state, void *boards,
     if (!state) return fail(PPAD_ERR_INVALID, "ppad_unpack: null state");
     cudaStream_t st = (cudaStream_t)stream;
     switch (dtype) {
-    case PPAD_I8: PPAD_DISPATCH(ctx, (launch_unpack<G, int8_t>(n, state, boards, fingers, prev, moves, st))); break;
-    case PPAD_I32: PPAD_DISPATCH(ctx, (launch_unpack<G, int32_t>(n, state, boards, fingers, prev, moves, st))); break;
-    case PPAD_I64: PPAD_DISPATCH(ctx, (launch_unpack<G, int64_t>(n, state, boards, fingers, prev, moves, st))); break;
+    case PPAD_I8: PPAD_DISPATCH(ctx, (launch_unpack<G, int8_t>(ctx, n, state, boards, fingers, prev, moves, st))); break;
+    case PPAD_I32: PPAD_DISPATCH(ctx, (launch_unpack<G, int32_t>(ctx, n, state, boards, fingers, prev, moves, st))); break;
+    case PPAD_I64: PPAD_DISPATCH(ctx, (launch_unpack<G, int64_t>(ctx, n, state, boards, fingers, prev, moves, st))); break;
     default: return fail(PPAD_ERR_UNSUPPORTED, "ppad_unpack: dtype must be PPAD_I8, PPAD_I32 or PPAD_I64");
     }
     return after_launch("unpack_kernel");
@@ -465,7 +477,7 @@ int ppad_encode_obs(const ppad_ctx *ctx, int64_t n, const void *state, void *obs
     if (obs_dtype != PPAD_OBS_F32 && obs_dtype != PPAD_OBS_U8)
         return fail(PPAD_ERR_UNSUPPORTED, "ppad_encode_obs: obs_dtype must be PPAD_OBS_F32 or PPAD_OBS_U8");
     if ((uintptr_t)obs & 15) return fail(PPAD_ERR_INVALID, "ppad_encode_obs: obs must be 16-byte aligned");
-    PPAD_DISPATCH(ctx, (encode_kernel<G><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(n, state, obs, obs_dtype)));
+    PPAD_DISPATCH(ctx, (encode_kernel<G><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(ctx->base.dyn, n, state, obs, obs_dtype)));
     return after_launch("encode_kernel");
 }
 
@@ -476,7 +488,7 @@ int ppad_cancel(const ppad_ctx *ctx, int64_t n, void *state, uint8_t *n_combos, 
     if (n == 0) return PPAD_OK;
     if (!state) return fail(PPAD_ERR_INVALID, "ppad_cancel: null state");
     if (combo_log && log_cap <= 0) return fail(PPAD_ERR_INVALID, "ppad_cancel: combo_log needs log_cap > 0");
-    PPAD_DISPATCH(ctx, (cancel_kernel<G><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(n, state, n_combos, combo_log,
+    PPAD_DISPATCH(ctx, (cancel_kernel<G><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(ctx->base.dyn, n, state, n_combos, combo_log,
                                                                                          log_cap)));
     return after_launch("cancel_kernel");
 }
@@ -487,7 +499,7 @@ int ppad_island(const ppad_ctx *ctx, int64_t n, const void *state, const uint8_t
     PPAD_ENTER(ctx, n);
     if (n == 0) return PPAD_OK;
     if (!state || !seed_cell || !orb_type || !island_out) return fail(PPAD_ERR_INVALID, "ppad_island: null pointer");
-    PPAD_DISPATCH(ctx, (island_kernel<G><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(n, state, seed_cell, orb_type,
+    PPAD_DISPATCH(ctx, (island_kernel<G><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(ctx->base.dyn, n, state, seed_cell, orb_type,
                                                                                          island_in, island_out)));
     return after_launch("island_kernel");
 }
@@ -497,7 +509,7 @@ int ppad_legal_mask(const ppad_ctx *ctx, int64_t n, const void *state, uint8_t *
     PPAD_ENTER(ctx, n);
     if (n == 0) return PPAD_OK;
     if (!state || !mask) return fail(PPAD_ERR_INVALID, "ppad_legal_mask: null pointer");
-    PPAD_DISPATCH(ctx, (legal_kernel<G><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(n, state, mask)));
+    PPAD_DISPATCH(ctx, (legal_kernel<G><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(ctx->base.dyn, n, state, mask)));
     return after_launch("legal_kernel");
 }
 
@@ -509,7 +521,7 @@ int ppad_sample_actions(const ppad_ctx *ctx, int64_t n, uint64_t env0, uint32_t 
     if (!state || !actions) return fail(PPAD_ERR_INVALID, "ppad_sample_actions: null pointer");
     RngKey key = ctx->base.key;
     key.step = step;
-    PPAD_DISPATCH(ctx, (sample_kernel<G><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(n, env0, key, state,
+    PPAD_DISPATCH(ctx, (sample_kernel<G><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(ctx->base.dyn, n, env0, key, state,
                                                                                          include_pass, actions)));
     return after_launch("sample_kernel");
 }
@@ -519,7 +531,7 @@ int ppad_drop(const ppad_ctx *ctx, int64_t n, void *state, void *stream)
     PPAD_ENTER(ctx, n);
     if (n == 0) return PPAD_OK;
     if (!state) return fail(PPAD_ERR_INVALID, "ppad_drop: null state");
-    PPAD_DISPATCH(ctx, (drop_kernel<G><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(n, state)));
+    PPAD_DISPATCH(ctx, (drop_kernel<G><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(ctx->base.dyn, n, state)));
     return after_launch("drop_kernel");
 }
 
@@ -566,7 +578,7 @@ int ppad_permute(const ppad_ctx *ctx, int64_t n, void *state, const uint8_t *map
     if (n == 0) return PPAD_OK;
     if (!state || !maps) return fail(PPAD_ERR_INVALID, "ppad_permute: null pointer");
     if ((uintptr_t)maps & 7) return fail(PPAD_ERR_INVALID, "ppad_permute: maps must be 8-byte aligned");
-    PPAD_DISPATCH(ctx, (permute_kernel<G><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(n, state, maps)));
+    PPAD_DISPATCH(ctx, (permute_kernel<G><<<grid_for(n), BLOCK, 0, (cudaStream_t)stream>>>(ctx->base.dyn, n, state, maps)));
     return after_launch("permute_kernel");
 }
 

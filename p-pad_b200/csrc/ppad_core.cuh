@@ -145,9 +145,13 @@ template <> struct WordOf<true> { typedef uint64_t type; };
 
 // NP_ = bit planes per cell: 3 (orb types 0..6, 7 = empty: everything the default skyfall produces) or 4 (orb
 // types 0..9 of game.py:236-246 incl. poison, mortal poison and bomb, 15 = empty).
+// The board dimensions are read through accessor functions (rows(), cols(), cells(), board(), ...): compile-time
+// constants for the specialised geometries below, run-time values for GeomDyn.
 template <int R_, int C_, int NP_ = 3>
 struct Geom {
+    static constexpr bool DYNAMIC = false;
     static constexpr int R = R_, C = C_, CELLS = R_ * C_, NP = NP_;
+    static constexpr int MAX_CELLS = CELLS;               // for array sizes
     static constexpr int EMPTY = (1 << NP_) - 1;          // code of an empty cell (-1 in the reference)
     static constexpr int NTYPES = NP_ == 3 ? 7 : 10;      // orb types 0 .. NTYPES - 1
     static_assert(CELLS <= 64 && R_ >= 3 && C_ >= 3 && (NP_ == 3 || NP_ == 4), "unsupported board size");
@@ -163,13 +167,89 @@ struct Geom {
     }
     static constexpr W row_mask(int r) { return (((W)1 << C_) - 1) << (r * C_); }
     static constexpr W NOT_LASTCOL = BOARD & ~col_mask(C_ - 1);
-    static constexpr W NOT_FIRSTCOL = BOARD & ~col_mask(0);
     static constexpr W NOT_LASTROW = BOARD & ~row_mask(R_ - 1);
     static constexpr int OBS_CH = 7;                      // agent01.py:263 fixes 7 channels
     static constexpr int OBS_ELEMS = CELLS * OBS_CH;      // 210 (5x6) / 294 (6x7)
     // bytes of one packed state record in HBM: NP planes + the meta word, padded to 16 bytes
     static constexpr int STATE_BYTES = (NP_ * (int)sizeof(W) + 4 + 15) / 16 * 16;
+    PPAD_HDC static int rows() { return R_; }
+    PPAD_HDC static int cols() { return C_; }
+    PPAD_HDC static int cells() { return CELLS; }
+    PPAD_HDC static int obs_elems() { return OBS_ELEMS; }
+    PPAD_HDC static W board() { return BOARD; }
+    PPAD_HDC static W not_lastcol() { return NOT_LASTCOL; }
+    PPAD_HDC static W not_lastrow() { return NOT_LASTROW; }
 };
+
+// Run-time board dimensions: any dim_row x dim_col with at most 64 cells (PAD.__init__ accepts every size with at
+// least 13 orbs, game.py:54-68).  The slower path behind the specialised geometries: 64-bit planes, loops that are
+// not unrolled, a simple observation emitter.  The dimensions of the launch live in shared memory (one copy per CTA,
+// written by geom_enter() at the top of every kernel); the host build keeps them in a thread-local.
+struct DynGeomData {
+    int32_t rows, cols, cells, obs_elems;
+    uint64_t board, not_lastcol, not_lastrow;
+};
+
+PPAD_HD DynGeomData &dyn_geom()
+{
+#if defined(__CUDA_ARCH__)
+    __shared__ DynGeomData d;
+    return d;
+#else
+    static thread_local DynGeomData d;
+    return d;
+#endif
+}
+
+inline DynGeomData make_dyn_geom(int rows, int cols)
+{
+    DynGeomData d;
+    d.rows = rows;
+    d.cols = cols;
+    d.cells = rows * cols;
+    d.obs_elems = 7 * rows * cols;
+    d.board = d.cells >= 64 ? ~0ull : ((1ull << d.cells) - 1);
+    uint64_t lastcol = 0, lastrow = 0;
+    for (int r = 0; r < rows; r++) lastcol |= 1ull << (r * cols + cols - 1);
+    for (int c = 0; c < cols; c++) lastrow |= 1ull << ((rows - 1) * cols + c);
+    d.not_lastcol = d.board & ~lastcol;
+    d.not_lastrow = d.board & ~lastrow;
+    return d;
+}
+
+template <int NP_ = 3>
+struct GeomDyn {
+    static constexpr bool DYNAMIC = true;
+    static constexpr int NP = NP_, MAX_CELLS = 64;
+    static constexpr int EMPTY = (1 << NP_) - 1;
+    static constexpr int NTYPES = NP_ == 3 ? 7 : 10;
+    typedef uint64_t W;
+    static constexpr int WBITS = 64;
+    static constexpr W ONE = 1;
+    static constexpr int OBS_CH = 7;
+    static constexpr int STATE_BYTES = (NP_ * 8 + 4 + 15) / 16 * 16;   // 32 / 48: the record layout of the 64-bit geometries
+    PPAD_HD static int rows() { return dyn_geom().rows; }
+    PPAD_HD static int cols() { return dyn_geom().cols; }
+    PPAD_HD static int cells() { return dyn_geom().cells; }
+    PPAD_HD static int obs_elems() { return dyn_geom().obs_elems; }
+    PPAD_HD static W board() { return dyn_geom().board; }
+    PPAD_HD static W not_lastcol() { return dyn_geom().not_lastcol; }
+    PPAD_HD static W not_lastrow() { return dyn_geom().not_lastrow; }
+};
+
+// first statement of every kernel (all threads): publishes the launch's board dimensions for GeomDyn
+template <class G>
+PPAD_HD void geom_enter(const DynGeomData &d)
+{
+    if constexpr (G::DYNAMIC) {
+#if defined(__CUDA_ARCH__)
+        if (threadIdx.x == 0) dyn_geom() = d;
+        __syncthreads();
+#else
+        dyn_geom() = d;
+#endif
+    }
+}
 
 template <class W, int NP>
 struct Planes {
@@ -486,13 +566,13 @@ template <class G>
 PPAD_HD typename G::W match_mask(const Board<G> &b, typename G::W &er, typename G::W &ed)
 {
     typedef typename G::W W;
-    constexpr int C = G::C;
+    const int C = G::cols();
     const W ne = ~empties<G>(b);
     W xr = (b.b0 ^ (b.b0 >> 1)) | (b.b1 ^ (b.b1 >> 1)) | (b.b2 ^ (b.b2 >> 1));
     W xd = (b.b0 ^ (b.b0 >> C)) | (b.b1 ^ (b.b1 >> C)) | (b.b2 ^ (b.b2 >> C));
     PPAD_P4(xr |= b.b3 ^ (b.b3 >> 1); xd |= b.b3 ^ (b.b3 >> C))
-    er = ~xr & ne & G::NOT_LASTCOL;
-    ed = ~xd & ne & G::NOT_LASTROW;
+    er = ~xr & ne & G::not_lastcol();
+    ed = ~xd & ne & G::not_lastrow();
     const W h = er & (er >> 1);
     const W v = ed & (ed >> C);
     return h | (h << 1) | (h << 2) | v | (v << C) | (v << (2 * C));
@@ -503,7 +583,7 @@ template <class G>
 PPAD_HD typename G::W closure(typename G::W g, typename G::W er, typename G::W ed)
 {
     typedef typename G::W W;
-    constexpr int C = G::C;
+    const int C = G::cols();
     for (;;) {
         const W n = g | ((g & er) << 1) | ((g >> 1) & er) | ((g & ed) << C) | ((g >> C) & ed);
         if (n == g) return g;
@@ -609,10 +689,10 @@ template <class G>
 PPAD_HD void drop_board(Board<G> &b)
 {
     typedef typename G::W W;
-    constexpr int C = G::C;
+    const int C = G::cols();
     for (;;) {
         const W e = empties<G>(b);
-        const W fall = ~e & (e >> C) & G::BOARD;
+        const W fall = ~e & (e >> C) & G::board();
         if (fall == 0) return;
         const W dst = fall << C;
         b.b0 = (b.b0 & ~dst) | ((b.b0 & fall) << C) | fall;
@@ -732,7 +812,7 @@ PPAD_HD void refill_all(Board<G> &b, OrbSource &src, const RngKey &key, const Sk
         // pure Philox (the auto-reset of rollouts): one block per four draws, words taken by compile-time index
         const uint32_t blk0 = (uint32_t)src.cursor >> 2;
         const int l0 = src.cursor & 3;             // the first block may start in the middle
-        const int nblk = (l0 + G::CELLS + 3) / 4;
+        const int nblk = (l0 + G::cells() + 3) / 4;
 #pragma unroll UNROLL
         for (int q = 0; q < nblk; q++) {
             U4 c;
@@ -744,7 +824,7 @@ PPAD_HD void refill_all(Board<G> &b, OrbSource &src, const RngKey &key, const Sk
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const int i = 4 * q + k - l0;
-                if (i >= 0 && i < G::CELLS) {
+                if (i >= 0 && i < G::cells()) {
                     const int code = orb_from_u32<G::NTYPES>(sky, k == 0 ? blk.x : (k == 1 ? blk.y : (k == 2 ? blk.z : blk.w)));
                     p0 |= (W)(code & 1) << i;
                     p1 |= (W)((code >> 1) & 1) << i;
@@ -753,10 +833,10 @@ PPAD_HD void refill_all(Board<G> &b, OrbSource &src, const RngKey &key, const Sk
                 }
             }
         }
-        src.cursor += G::CELLS;
+        src.cursor += G::cells();
         src.blk_idx = -1;
     } else {
-        for (int i = 0; i < G::CELLS; i++) {
+        for (int i = 0; i < G::cells(); i++) {
             const int code = src.template next<G::NTYPES>(key, sky);
             p0 |= (W)(code & 1) << i;
             p1 |= (W)((code >> 1) & 1) << i;
@@ -866,12 +946,12 @@ PPAD_HD double damage_of_log(const TeamTable &team, const uint16_t *log, int n)
 template <class G>
 PPAD_HD int legal_mask(int finger, int prev)
 {
-    const int r = finger / G::C, c = finger - r * G::C;
+    const int r = finger / G::cols(), c = finger - r * G::cols();
     int m = 15;
     if (r <= 0) m &= ~1;
-    if (r >= G::R - 1) m &= ~2;
+    if (r >= G::rows() - 1) m &= ~2;
     if (c <= 0) m &= ~4;
-    if (c >= G::C - 1) m &= ~8;
+    if (c >= G::cols() - 1) m &= ~8;
     if (prev < 4) m &= ~(1 << (prev ^ 1));   // opposite of up(0)/down(1)/left(2)/right(3)
     return m;
 }
@@ -913,12 +993,12 @@ PPAD_HD bool apply_move(State<G> &s, int action)
 {
     // straight-line: up = row - 1, down = row + 1, left = col - 1, right = col + 1 (game.py:127-155)
     const int f = meta_finger(s.meta);
-    const int r = f / G::C, c = f - r * G::C;
+    const int r = f / G::cols(), c = f - r * G::cols();
     const int dr = (action == ACT_DOWN ? 1 : 0) - (action == ACT_UP ? 1 : 0);
     const int dc = (action == ACT_RIGHT ? 1 : 0) - (action == ACT_LEFT ? 1 : 0);
     const int nr = r + dr, nc = c + dc;
-    if ((unsigned)nr >= (unsigned)G::R || (unsigned)nc >= (unsigned)G::C) return false;
-    const int t = nr * G::C + nc;
+    if ((unsigned)nr >= (unsigned)G::rows() || (unsigned)nc >= (unsigned)G::cols()) return false;
+    const int t = nr * G::cols() + nc;
     swap_cells<G>(s.b, f, t);
     int moves = meta_moves(s.meta);
     if (moves < 0xFFFF) moves++;
@@ -936,7 +1016,7 @@ PPAD_HD int random_finger(const RngKey &key)
     c.z = key.step;
     c.w = STREAM_FINGER << 24;
     const U4 o = philox4x32_10(c, key.k0, key.k1);
-    return (int)mulhi32(o.x, (uint32_t)G::R) * G::C + (int)mulhi32(o.y, (uint32_t)G::C);
+    return (int)mulhi32(o.x, (uint32_t)G::rows()) * G::cols() + (int)mulhi32(o.y, (uint32_t)G::cols());
 }
 
 // reset (game.py:303-315): refill the whole board until it holds no 3-run
@@ -976,6 +1056,7 @@ struct StepParams {
     int32_t n_inj, slab_words, log_cap;
     int32_t draw0;   // first draw index of a stand-alone fill (ppad_fill)
     int32_t slab_fmt;   // SLAB_NIBBLES / SLAB_PLANES3: layout of the injected skyfall slab of this launch
+    DynGeomData dyn;    // board dimensions for GeomDyn (ignored by the specialised geometries)
 };
 
 struct StepOut {
@@ -1103,7 +1184,7 @@ __device__ __forceinline__ uint32_t reset_boards_warp(bool need, State<G> &s, co
         if (in_range) {
             OrbSource src;
             src.init(reinterpret_cast<const uint32_t *>((uintptr_t)slab_o), n_inj, STREAM_RESET);   // init() ignores n_inj without a slab
-            src.cursor = att * G::CELLS;
+            src.cursor = att * G::cells();
             RngKey key_o = board_key(p, env_o);
             key_o.step = step;
             refill_all<G, TIGHT, UNROLL>(b, src, key_o, p.sky);
@@ -1130,7 +1211,7 @@ __device__ __forceinline__ uint32_t reset_boards_warp(bool need, State<G> &s, co
                 s.b.b1 = w1;
                 s.b.b2 = w2;
                 PPAD_P4(s.b.b3 = w3)
-                consumed = (a_w + 1) * G::CELLS;
+                consumed = (a_w + 1) * G::cells();
                 if (!ok_w) flags |= FLAG_RESET_CAP;
                 got = true;
             }
@@ -1234,18 +1315,18 @@ template <class G, int NW>
 PPAD_HD void obs_mask(const State<G> &s, uint32_t (&w)[NW])
 {
     typedef typename G::W W;
-    constexpr int C = G::C, RB = 7 * C;                       // obs bits per board row
+    constexpr int C = G::cols(), RB = 7 * C;                       // obs bits per board row
     constexpr int CM = C < 6 ? C : 6;                         // columns handled by the multiply
     W plane[7];
 #pragma unroll
     for (int k = 0; k < 6; k++)
     {
-        plane[k] = ((k & 1) ? s.b.b0 : ~s.b.b0) & ((k & 2) ? s.b.b1 : ~s.b.b1) & ((k & 4) ? s.b.b2 : ~s.b.b2) & G::BOARD;
+        plane[k] = ((k & 1) ? s.b.b0 : ~s.b.b0) & ((k & 2) ? s.b.b1 : ~s.b.b1) & ((k & 4) ? s.b.b2 : ~s.b.b2) & G::board();
         PPAD_P4(plane[k] &= ~s.b.b3)   // types 0..5 have bit 3 clear; 6..9 and empty give all-zero colour channels
     }
     plane[6] = G::ONE << meta_finger(s.meta);                 // channel 6 = finger
 #pragma unroll
-    for (int r = 0; r < G::R; r++) {
+    for (int r = 0; r < G::rows(); r++) {
         uint64_t row = 0;
 #pragma unroll
         for (int k = 0; k < 7; k++) {
@@ -1273,7 +1354,7 @@ PPAD_HD uint32_t pack_cells(Board<G> &b, const T *cells)
     typedef typename G::W W;
     W p0 = 0, p1 = 0, p2 = 0, p3 = 0;
     uint32_t flags = 0;
-    for (int i = 0; i < G::CELLS; i++) {
+    for (int i = 0; i < G::cells(); i++) {
         const long long v = (long long)cells[i];
         int code;
         if (v == -1) code = G::EMPTY;
@@ -1297,7 +1378,7 @@ PPAD_HD uint32_t pack_cells(Board<G> &b, const T *cells)
 template <class G, class T>
 PPAD_HD void unpack_cells(const Board<G> &b, T *cells)
 {
-    for (int i = 0; i < G::CELLS; i++) {
+    for (int i = 0; i < G::cells(); i++) {
         const int code = code_at<G>(b, i);
         cells[i] = (T)(code == G::EMPTY ? -1 : code);
     }

@@ -168,7 +168,7 @@ struct StateIO<G, true, 4> {
 // ------------------------------------------------------------------------------------------------
 template <class G>
 struct ObsGeom {
-    static constexpr int NB = G::OBS_ELEMS;          // bits (= elements) per board
+    static constexpr int NB = G::MAX_CELLS * 7;      // bits (= elements) per board (GeomDyn: the most a board can have)
     static constexpr int NW = (NB + 31) / 32 + 1;    // words of a shifted per-board mask
     static constexpr int CNT_LO = NB / 32;           // a board owns CNT_LO or CNT_LO + 1 stream words
     static constexpr int WARP_WORDS = NB;            // 32 boards * NB bits / 32
@@ -273,10 +273,42 @@ __device__ __forceinline__ void emit_obs(const State<G> &s, bool valid, int n_va
     __syncwarp();
 }
 
+// The observation of a warp's boards for run-time board dimensions (GeomDyn): board by board, the planes of the board's
+// lane are broadcast and the 32 lanes write its 7 * cells elements to consecutive addresses.  Every lane must call it.
+template <class G>
+__device__ __forceinline__ void emit_obs_dyn(const State<G> &s, bool valid, int n_valid, void *obs_warp, int obs_dtype)
+{
+    const unsigned full = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, ne = G::obs_elems();
+    (void)valid;
+    for (int b = 0; b < n_valid; b++) {
+        const typename G::W p0 = __shfl_sync(full, s.b.b0, b), p1 = __shfl_sync(full, s.b.b1, b), p2 = __shfl_sync(full, s.b.b2, b);
+        typename G::W p3 = 0;
+        PPAD_P4(p3 = __shfl_sync(full, s.b.b3, b))
+        const int finger = __shfl_sync(full, meta_finger(s.meta), b);
+        for (int e = lane; e < ne; e += 32) {
+            const int cell = e / 7, ch = e - 7 * cell;
+            const int code = (int)(((p0 >> cell) & 1) | (((p1 >> cell) & 1) << 1) | (((p2 >> cell) & 1) << 2) | (((p3 >> cell) & 1) << 3));
+            const bool on = ch < 6 ? code == ch : cell == finger;
+            if (obs_dtype == PPAD_OBS_F32) reinterpret_cast<float *>(obs_warp)[(size_t)b * ne + e] = on ? 1.f : 0.f;
+            else reinterpret_cast<uint8_t *>(obs_warp)[(size_t)b * ne + e] = on ? 1 : 0;
+        }
+    }
+}
+
+// the observation of the warp's boards, whichever geometry
+template <class G>
+__device__ __forceinline__ void emit_obs_any(const State<G> &s, bool valid, int n_valid, uint32_t *stream, const ObsShared &sh,
+                                             void *obs_warp, int obs_dtype)
+{
+    if constexpr (G::DYNAMIC) emit_obs_dyn<G>(s, valid, n_valid, obs_warp, obs_dtype);
+    else emit_obs<G>(s, valid, n_valid, stream, sh, obs_warp, obs_dtype);
+}
+
 template <class G>
 __device__ __forceinline__ void *obs_warp_ptr(void *obs, int64_t warp_board0, int obs_dtype)
 {
-    const size_t elems = (size_t)warp_board0 * G::OBS_ELEMS;
+    const size_t elems = (size_t)warp_board0 * G::obs_elems();
     return obs_dtype == PPAD_OBS_F32 ? (void *)(reinterpret_cast<float *>(obs) + elems)
                                      : (void *)(reinterpret_cast<uint8_t *>(obs) + elems);
 }
@@ -313,8 +345,11 @@ typedef Geom<6, 7> G67;
 typedef Geom<4, 5, 4> G45W;   // 4-bit orb codes: all ten orb types of game.py:236-246
 typedef Geom<5, 6, 4> G56W;
 typedef Geom<6, 7, 4> G67W;
+typedef GeomDyn<3> GDYN;      // any dim_row x dim_col with <= 64 cells at run time
+typedef GeomDyn<4> GDYNW;
 
-// geometry ids of ppad_ctx::geom (build_params): 0 = 5x6, 1 = 6x7, 2 = 4x5; 3..5 = the same with 4-bit orb codes
+// geometry ids of ppad_ctx::geom (build_params): 0 = 5x6, 1 = 6x7, 2 = 4x5; 3..5 = the same with 4-bit orb codes;
+// 6 / 7 = run-time dimensions (GeomDyn) with 3- / 4-bit codes
 template <int ID> struct GeomOf;
 template <> struct GeomOf<0> { typedef G56 type; };
 template <> struct GeomOf<1> { typedef G67 type; };
@@ -322,14 +357,16 @@ template <> struct GeomOf<2> { typedef G45 type; };
 template <> struct GeomOf<3> { typedef G56W type; };
 template <> struct GeomOf<4> { typedef G67W type; };
 template <> struct GeomOf<5> { typedef G45W type; };
+template <> struct GeomOf<6> { typedef GDYN type; };
+template <> struct GeomOf<7> { typedef GDYNW type; };
 
 }   // namespace ppad
 
 struct ppad_ctx {
     ppad_config cfg;
     int device;
-    int geom;   // 0 = 5x6, 1 = 6x7, 2 = 4x5; 3..5 = the same with 4-bit orb codes
-    ppad::StepParams base;
+    int geom;   // 0 = 5x6, 1 = 6x7, 2 = 4x5; 3..5 = the same with 4-bit orb codes; 6 / 7 = run-time dimensions
+    ppad::StepParams base;   // base.dyn: the board dimensions for the run-time geometries
     int sm_count;
     int pool_ctas_per_sm;   // resident CTAs of the persistent step_pool_kernel
 };
@@ -341,7 +378,9 @@ struct ppad_ctx {
         else if ((ctx)->geom == 2) { typedef ppad::G45 G; EXPR; }  \
         else if ((ctx)->geom == 3) { typedef ppad::G56W G; EXPR; } \
         else if ((ctx)->geom == 4) { typedef ppad::G67W G; EXPR; } \
-        else { typedef ppad::G45W G; EXPR; }                       \
+        else if ((ctx)->geom == 5) { typedef ppad::G45W G; EXPR; } \
+        else if ((ctx)->geom == 6) { typedef ppad::GDYN G; EXPR; } \
+        else { typedef ppad::GDYNW G; EXPR; }                      \
     } while (0)
 
 namespace ppad {

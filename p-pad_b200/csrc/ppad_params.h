@@ -11,7 +11,8 @@
 namespace ppad {
 
 // returns PPAD_OK or an error status with `err` set; geom: 0 = 5x6, 1 = 6x7, 2 = 4x5 with 3-bit orb codes,
-// 3..5 = the same boards with 4-bit codes (cfg.orb_bits == 4: orb types 7..9 allowed)
+// 3..5 = the same boards with 4-bit codes (cfg.orb_bits == 4: orb types 7..9 allowed); 6 / 7 = any other
+// dim_row x dim_col with at most 64 cells (run-time dimensions, 3- / 4-bit codes)
 inline int build_params(const ppad_config &cfg, StepParams &p, int &geom, std::string &err)
 {
     std::memset(&p, 0, sizeof(p));
@@ -36,11 +37,8 @@ inline int build_params(const ppad_config &cfg, StepParams &p, int &geom, std::s
         err = "ERROR: The board should allow at least 13 orbs. Please increase board size!";
         return PPAD_ERR_INVALID;
     }
-    if (cfg.rows == 5 && cfg.cols == 6) geom = 0;
-    else if (cfg.rows == 6 && cfg.cols == 7) geom = 1;
-    else if (cfg.rows == 4 && cfg.cols == 5) geom = 2;
-    else {
-        err = "only 4x5, 5x6 and 6x7 boards (rows x cols) have kernel instantiations";
+    if (cfg.rows < 1 || cfg.cols < 1 || cfg.cols * cfg.rows > 64) {
+        err = "boards of more than 64 cells do not fit the packed state (one bit per cell and plane in a 64-bit word)";
         return PPAD_ERR_UNSUPPORTED;
     }
     if (cfg.orb_bits != 0 && cfg.orb_bits != 3 && cfg.orb_bits != 4) {
@@ -48,7 +46,10 @@ inline int build_params(const ppad_config &cfg, StepParams &p, int &geom, std::s
         return PPAD_ERR_INVALID;
     }
     const bool wide = cfg.orb_bits == 4;
-    if (wide) geom += 3;
+    if (cfg.rows == 5 && cfg.cols == 6) geom = wide ? 3 : 0;
+    else if (cfg.rows == 6 && cfg.cols == 7) geom = wide ? 4 : 1;
+    else if (cfg.rows == 4 && cfg.cols == 5) geom = wide ? 5 : 2;
+    else geom = wide ? 7 : 6;            // run-time dimensions: the generic (slower) instantiation
     if (!wide && (cfg.skyfall[7] > 0 || cfg.skyfall[8] > 0 || cfg.skyfall[9] > 0)) {
         err = "orb types 7..9 (poison, mortal poison, bomb) do not fit the 3-bit state: create the context with orb_bits = 4";
         return PPAD_ERR_UNSUPPORTED;
@@ -115,6 +116,7 @@ inline int build_params(const ppad_config &cfg, StepParams &p, int &geom, std::s
         err = "reset_cap must be >= 0";
         return PPAD_ERR_INVALID;
     }
+    p.dyn = make_dyn_geom(cfg.rows, cfg.cols);
     p.skyfall_damage = cfg.skyfall_damage;
     p.cascade_cap = cfg.cascade_cap;
     p.reset_cap = cfg.reset_cap;

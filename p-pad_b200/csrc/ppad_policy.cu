@@ -10,6 +10,8 @@ PPAD_POLICY_LAUNCHERS(extern, G45)
 PPAD_POLICY_LAUNCHERS(extern, G56W)
 PPAD_POLICY_LAUNCHERS(extern, G67W)
 PPAD_POLICY_LAUNCHERS(extern, G45W)
+PPAD_POLICY_LAUNCHERS(extern, GDYN)
+PPAD_POLICY_LAUNCHERS(extern, GDYNW)
 
 // sums the per-CTA rows (max for the reward maximum): out[STATS_WORDS], one CTA
 __global__ void __launch_bounds__(BLOCK) stats_reduce_kernel(const unsigned long long *rows, int64_t n_rows, unsigned long long *out)

@@ -59,8 +59,9 @@ struct PolicyArgs {
 template <class G, bool OBS, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) policy_step_kernel(const __grid_constant__ PolicyArgs a)
 {
+    geom_enter<G>(a.p.dyn);
     __shared__ ObsShared obs_sh;
-    __shared__ uint32_t obs_stream[OBS ? (BLOCK / 32) * ObsGeom<G>::WARP_WORDS : 1];
+    __shared__ uint32_t obs_stream[OBS && !G::DYNAMIC ? (BLOCK / 32) * ObsGeom<G>::WARP_WORDS : 1];
     if (OBS) {
         obs_init_luts(obs_sh);
         __syncthreads();
@@ -171,8 +172,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) policy_step_kernel(const __grid_c
     const int64_t warp0 = i - (threadIdx.x & 31);
     if (OBS && warp0 < a.n) {
         const int n_valid = (int)(a.n - warp0 < 32 ? a.n - warp0 : 32);
-        emit_obs<G>(s, valid, n_valid, obs_stream + (threadIdx.x >> 5) * ObsGeom<G>::WARP_WORDS, obs_sh,
-                    obs_warp_ptr<G>(a.obs, warp0, a.obs_dtype), a.obs_dtype);
+        emit_obs_any<G>(s, valid, n_valid, obs_stream + (threadIdx.x >> 5) * ObsGeom<G>::WARP_WORDS, obs_sh,
+                        obs_warp_ptr<G>(a.obs, warp0, a.obs_dtype), a.obs_dtype);
     }
 }
 

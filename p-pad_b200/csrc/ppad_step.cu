@@ -10,6 +10,8 @@ PPAD_STEP_LAUNCHERS(extern, G45)
 PPAD_STEP_LAUNCHERS(extern, G56W)
 PPAD_STEP_LAUNCHERS(extern, G67W)
 PPAD_STEP_LAUNCHERS(extern, G45W)
+PPAD_STEP_LAUNCHERS(extern, GDYN)
+PPAD_STEP_LAUNCHERS(extern, GDYNW)
 
 int pool_occupancy(int geom)
 {

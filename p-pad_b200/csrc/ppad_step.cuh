@@ -151,8 +151,9 @@ constexpr int step_min_ctas()
 template <class G, bool OBS, bool AR, bool COMPACT = false>
 __global__ void __launch_bounds__(BLOCK, step_min_ctas<G, AR>()) step_obs_kernel(const __grid_constant__ StepKernelArgs a)
 {
+    geom_enter<G>(a.p.dyn);
     __shared__ ObsShared obs_sh;
-    __shared__ uint32_t obs_stream[OBS ? (BLOCK / 32) * ObsGeom<G>::WARP_WORDS : 1];
+    __shared__ uint32_t obs_stream[OBS && !G::DYNAMIC ? (BLOCK / 32) * ObsGeom<G>::WARP_WORDS : 1];
     if (OBS) {
         obs_init_luts(obs_sh);
         __syncthreads();
@@ -218,8 +219,8 @@ __global__ void __launch_bounds__(BLOCK, step_min_ctas<G, AR>()) step_obs_kernel
     const int64_t warp0 = i - (threadIdx.x & 31);
     if (OBS && warp0 < a.n) {
         const int n_valid = (int)(a.n - warp0 < 32 ? a.n - warp0 : 32);
-        emit_obs<G>(s, valid, n_valid, obs_stream + (threadIdx.x >> 5) * ObsGeom<G>::WARP_WORDS, obs_sh,
-                    obs_warp_ptr<G>(a.obs, warp0, a.obs_dtype), a.obs_dtype);
+        emit_obs_any<G>(s, valid, n_valid, obs_stream + (threadIdx.x >> 5) * ObsGeom<G>::WARP_WORDS, obs_sh,
+                        obs_warp_ptr<G>(a.obs, warp0, a.obs_dtype), a.obs_dtype);
     }
     if constexpr (COMPACT) compact_results<G>(a, valid, o, s);
 }
@@ -244,6 +245,7 @@ struct RolloutArgs {
 template <class G, bool RECORD>   // RECORD: the trajectory outputs are compiled in only where they are asked for
 __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ RolloutArgs a)
 {
+    geom_enter<G>(a.p.dyn);
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     const bool valid = i < a.n;
     State<G> s;
@@ -378,6 +380,7 @@ struct CascadePool {
 template <class G, bool AR>
 __global__ void __launch_bounds__(PBLOCK, PPAD_POOL_MINB) step_pool_kernel(const __grid_constant__ StepKernelArgs a)
 {
+    geom_enter<G>(a.p.dyn);
     __shared__ CascadePool<G> pool;
     typedef typename G::W W;
     const int tid = threadIdx.x;

@@ -6,15 +6,24 @@ tests.  They are format converters, not a compute path: no game logic lives here
 import numpy as np
 
 
+# board sizes with specialised kernels; of those, the ones whose planes are 32-bit words.  Every other size (any
+# dim_row x dim_col with at most 64 cells) runs on the run-time-dimension kernels, which use 64-bit planes.
+SPECIALISED = ((4, 5), (5, 6), (6, 7))
+NARROW = ((4, 5), (5, 6))
+
+
+def plane_words(rows, cols):
+    """uint32 words per bit plane of the packed state"""
+    if rows < 1 or cols < 1 or rows * cols > 64:
+        raise ValueError("board too large for the packed state (at most 64 cells)")
+    return 1 if (rows, cols) in NARROW else 2
+
+
 def state_words(rows, cols, orb_bits=3):
     """uint32 words per packed state record (orb_bits planes + the meta word, padded to 16 bytes)."""
-    cells = rows * cols
-    if cells > 64:
-        raise ValueError("board too large for the packed state")
     if orb_bits not in (3, 4):
         raise ValueError("orb_bits must be 3 or 4")
-    plane_words = 1 if cells <= 32 else 2
-    return (orb_bits * plane_words + 1 + 3) // 4 * 4
+    return (orb_bits * plane_words(rows, cols) + 1 + 3) // 4 * 4
 
 
 def pack_state(boards, fingers, prev=None, moves=None, orb_bits=3):
@@ -34,7 +43,7 @@ def pack_state(boards, fingers, prev=None, moves=None, orb_bits=3):
     moves = np.zeros(n, np.uint32) if moves is None else np.asarray(moves).astype(np.uint32)
     meta = (fingers[:, 0] * cols + fingers[:, 1]).astype(np.uint32) | (prev << np.uint32(6)) | (moves << np.uint32(9))
     out = np.zeros((n, state_words(rows, cols, orb_bits)), np.uint32)
-    if cells <= 32:
+    if plane_words(rows, cols) == 1:
         for j, pl in enumerate(planes):
             out[:, j] = pl.astype(np.uint32)
         out[:, orb_bits] = meta
@@ -51,7 +60,7 @@ def unpack_state(state, rows, cols, orb_bits=3):
     state = np.asarray(state, np.uint32)
     n = state.shape[0]
     cells = rows * cols
-    if cells <= 32:
+    if plane_words(rows, cols) == 1:
         planes = [state[:, j].astype(np.uint64) for j in range(orb_bits)]
         meta = state[:, orb_bits]
     else:

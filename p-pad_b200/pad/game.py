@@ -249,7 +249,8 @@ class PAD:
         spread with np.unpackbits; layout.unpack_state is the batched equivalent and the tests compare the two)"""
         v = self._venv
         cells = self.dim_row * self.dim_col
-        pb = 4 if cells <= 32 else 8                          # bytes per plane
+        from .. import layout
+        pb = 4 * layout.plane_words(self.dim_row, self.dim_col)   # bytes per plane
         bits = np.unpackbits(self._io_np[:pb * v.orb_bits].reshape(v.orb_bits, pb), axis=1, bitorder='little')[:, :cells]
         codes = bits[0].astype(int)
         for j in range(1, v.orb_bits):

@@ -32,13 +32,18 @@ def cancel(board):
 
 def illegal_actions(finger, dim_row=5, dim_col=6):
     """Set of off-board directions (utils.py:73-83), read from bits 4..7 of ppad_legal_mask."""
-    venv = _slab(dim_row, dim_col) if (dim_row, dim_col) in ((4, 5), (5, 6), (6, 7)) else None
-    if venv is None:
-        raise NotImplementedError('only 4x5, 5x6 and 6x7 boards have kernel instantiations')
+    venv = _slab(dim_row, dim_col)
     venv.set_state(np.zeros((1, dim_row, dim_col), dtype=np.int64), np.asarray(finger).reshape(1, 2))
     mask = int(venv.legal_mask()[0]) >> 4
     names = ['up', 'down', 'left', 'right']
-    return {names[a] for a in range(4) if (mask >> a) & 1}
+    out = {names[a] for a in range(4) if (mask >> a) & 1}
+    # the reference pairs the checks with `elif` (utils.py:75-82): on a one-row / one-column board it reports 'up' /
+    # 'left' only
+    if dim_row == 1:
+        out.discard('down')
+    if dim_col == 1:
+        out.discard('right')
+    return out
 
 
 def detect_island(board, island, x, y, orb_type):

@@ -12,7 +12,8 @@
 
 using namespace ppad;
 
-// geom: 0 = 5x6, 1 = 6x7, 2 = 4x5 (3-bit orb codes); 3..5 = the same boards with 4-bit codes
+// geom: 0 = 5x6, 1 = 6x7, 2 = 4x5 (3-bit orb codes); 3..5 = the same boards with 4-bit codes; 6 / 7 = run-time
+// dimensions (GeomDyn: the caller sets dyn_geom() first)
 #define HC_DISPATCH(geom, EXPR)                                  \
     do {                                                         \
         if ((geom) == 0) { typedef Geom<5, 6> G; EXPR; }         \
@@ -20,7 +21,9 @@ using namespace ppad;
         else if ((geom) == 2) { typedef Geom<4, 5> G; EXPR; }    \
         else if ((geom) == 3) { typedef Geom<5, 6, 4> G; EXPR; } \
         else if ((geom) == 4) { typedef Geom<6, 7, 4> G; EXPR; } \
-        else { typedef Geom<4, 5, 4> G; EXPR; }                  \
+        else if ((geom) == 5) { typedef Geom<4, 5, 4> G; EXPR; } \
+        else if ((geom) == 6) { typedef GeomDyn<3> G; EXPR; }    \
+        else { typedef GeomDyn<4> G; EXPR; }                     \
     } while (0)
 
 static int shape_geom(int rows, int cols, int orb_bits)
@@ -29,7 +32,10 @@ static int shape_geom(int rows, int cols, int orb_bits)
     if (rows == 5 && cols == 6) g = 0;
     else if (rows == 6 && cols == 7) g = 1;
     else if (rows == 4 && cols == 5) g = 2;
-    else return -1;
+    else if (rows >= 1 && cols >= 1 && rows * cols <= 64) {
+        dyn_geom() = make_dyn_geom(rows, cols);
+        return orb_bits == 4 ? 7 : 6;
+    } else return -1;
     return orb_bits == 4 ? g + 3 : g;
 }
 
@@ -43,8 +49,8 @@ void step_batch(const StepParams &base, int64_t n, uint64_t env0, int8_t *boards
 {
     for (int64_t i = 0; i < n; i++) {
         State<G> s;
-        pack_cells<G, int8_t>(s.b, boards + i * G::CELLS);
-        s.meta = meta_pack(fingers[2 * i] * G::C + fingers[2 * i + 1], prev[i], moves ? moves[i] : 0);
+        pack_cells<G, int8_t>(s.b, boards + i * G::cells());
+        s.meta = meta_pack(fingers[2 * i] * G::cols() + fingers[2 * i + 1], prev[i], moves ? moves[i] : 0);
         int action = actions ? actions[i] : -1;
         if (action == 255) action = -1;
         Board<G> fin;
@@ -52,16 +58,16 @@ void step_batch(const StepParams &base, int64_t n, uint64_t env0, int8_t *boards
                                         slab ? slab + (size_t)i * base.slab_words : nullptr,
                                         combo_log ? combo_log + (size_t)i * base.log_cap : nullptr,
                                         paths ? paths + (size_t)i * path_words : nullptr, paths ? path_lens[i] : 0);
-        unpack_cells<G, int8_t>(s.b, boards + i * G::CELLS);
+        unpack_cells<G, int8_t>(s.b, boards + i * G::cells());
         const int f = meta_finger(s.meta);
-        fingers[2 * i] = f / G::C;
-        fingers[2 * i + 1] = f % G::C;
+        fingers[2 * i] = f / G::cols();
+        fingers[2 * i + 1] = f % G::cols();
         prev[i] = (uint8_t)meta_prev(s.meta);
         if (moves) moves[i] = (uint16_t)meta_moves(s.meta);
         if (action_out) action_out[i] = (uint8_t)o.action;
         if (reward) reward[i] = o.reward;
         if (info) info[i] = o.info;
-        if (final_boards) unpack_cells<G, int8_t>(fin, final_boards + i * G::CELLS);
+        if (final_boards) unpack_cells<G, int8_t>(fin, final_boards + i * G::cells());
     }
 }
 
@@ -77,12 +83,12 @@ void reset_batch(const StepParams &base, int64_t n, uint64_t env0, const uint32_
         OrbSource src;
         src.init(slab ? slab + (size_t)i * base.slab_words : nullptr, base.n_inj, STREAM_RESET);
         State<G> s;
-        const int fin = fingers_in ? fingers_in[2 * i] * G::C + fingers_in[2 * i + 1] : -1;
+        const int fin = fingers_in ? fingers_in[2 * i] * G::cols() + fingers_in[2 * i + 1] : -1;
         const uint32_t fl = reset_board<G>(s, base.reset_cap, src, key, base.sky, fin);
-        unpack_cells<G, int8_t>(s.b, boards + i * G::CELLS);
+        unpack_cells<G, int8_t>(s.b, boards + i * G::cells());
         const int f = meta_finger(s.meta);
-        fingers[2 * i] = f / G::C;
-        fingers[2 * i + 1] = f % G::C;
+        fingers[2 * i] = f / G::cols();
+        fingers[2 * i + 1] = f % G::cols();
         if (flags) flags[i] = (uint8_t)fl;
         if (consumed) consumed[i] = src.cursor;
     }
@@ -93,13 +99,13 @@ void cancel_batch(int64_t n, int8_t *boards, uint8_t *n_combos, uint16_t *combo_
 {
     for (int64_t i = 0; i < n; i++) {
         Board<G> b;
-        pack_cells<G, int8_t>(b, boards + i * G::CELLS);
+        pack_cells<G, int8_t>(b, boards + i * G::cells());
         LogSink sink;
         sink.log = combo_log ? combo_log + (size_t)i * log_cap : nullptr;
         sink.cap = log_cap;
         sink.n = 0;
         const int m = cancel_board<G>(b, [&](int colour, int N) { sink.put(colour, N); });
-        unpack_cells<G, int8_t>(b, boards + i * G::CELLS);
+        unpack_cells<G, int8_t>(b, boards + i * G::cells());
         if (n_combos) n_combos[i] = (uint8_t)sat255(m);
     }
 }
@@ -109,25 +115,29 @@ void drop_batch(int64_t n, int8_t *boards)
 {
     for (int64_t i = 0; i < n; i++) {
         Board<G> b;
-        pack_cells<G, int8_t>(b, boards + i * G::CELLS);
+        pack_cells<G, int8_t>(b, boards + i * G::cells());
         drop_board<G>(b);
-        unpack_cells<G, int8_t>(b, boards + i * G::CELLS);
+        unpack_cells<G, int8_t>(b, boards + i * G::cells());
     }
 }
 
 template <class G>
 void obs_batch(int64_t n, const int8_t *boards, const int32_t *fingers, uint8_t *out)
 {
+    if constexpr (G::DYNAMIC) {
+        (void)n; (void)boards; (void)fingers; (void)out;      // the run-time geometries emit the obs in device code only
+    } else {
     constexpr int NB = G::OBS_ELEMS, NW = (NB + 31) / 32 + 1;
     for (int64_t i = 0; i < n; i++) {
         State<G> s;
-        pack_cells<G, int8_t>(s.b, boards + i * G::CELLS);
-        s.meta = meta_pack(fingers[2 * i] * G::C + fingers[2 * i + 1], 4, 0);
+        pack_cells<G, int8_t>(s.b, boards + i * G::cells());
+        s.meta = meta_pack(fingers[2 * i] * G::cols() + fingers[2 * i + 1], 4, 0);
         uint32_t w[NW] = {0};
         obs_mask<G, NW>(s, w);
         for (int e = 0; e < NB; e++) out[i * NB + e] = (w[e >> 5] >> (e & 31)) & 1;
         for (int e = NB; e < 32 * NW; e++)
             if ((w[e >> 5] >> (e & 31)) & 1) out[i * NB] = 99;   // bits beyond the board must stay clear
+    }
     }
 }
 
@@ -156,6 +166,7 @@ int hostcore_step_batch(const ppad_config *cfg, int64_t n, uint64_t env0, uint32
     p.n_inj = slab ? n_inj : -1;
     p.slab_words = slab_words;
     p.log_cap = log_cap;
+    dyn_geom() = p.dyn;
     HC_DISPATCH(geom, (step_batch<G>(p, n, env0, boards, fingers, prev, moves, actions, slab, action_out, reward, info,
                                      final_boards, combo_log, paths, path_words, path_lens)));
     return 0;
@@ -171,6 +182,7 @@ int hostcore_reset(const ppad_config *cfg, int64_t n, uint64_t env0, uint32_t st
     p.key.step = step;
     p.n_inj = slab ? n_inj : -1;
     p.slab_words = slab_words;
+    dyn_geom() = p.dyn;
     HC_DISPATCH(geom, (reset_batch<G>(p, n, env0, slab, fingers_in, boards, fingers, flags, consumed)));
     return 0;
 }

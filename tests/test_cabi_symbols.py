@@ -59,7 +59,9 @@ def test_constants_agree(cabi):
     assert C.sizeof(cabi.StepArgs) == 8 + 8 + 4 * 4 + 3 * 8 + 2 * 4 + 6 * 8 + 4 + 4 + 8 + 2 * 4 + 2 * 8 + 2 * 4 + 2 * 4 + 8
     assert C.sizeof(cabi.HostStepArgs) % 8 == 0
     assert cabi.lib().ppad_state_bytes(5, 6) == 16 and cabi.lib().ppad_state_bytes(6, 7) == 32
-    assert cabi.lib().ppad_state_bytes(4, 4) == -1 and cabi.lib().ppad_state_bytes(4, 5) == 16
+    assert cabi.lib().ppad_state_bytes(9, 9) == -1 and cabi.lib().ppad_state_bytes(4, 5) == 16
+    # every other size up to 64 cells runs on the run-time-dimension kernels: 64-bit planes
+    assert cabi.lib().ppad_state_bytes(4, 4) == 32 and cabi.lib().ppad_state_bytes_ex(8, 8, 4) == 48
 
 
 def test_default_config_is_the_reference_default(cabi):
@@ -94,7 +96,7 @@ def test_config_validation_messages_match_the_reference(cabi):
             (lambda c: setattr(c, "rows", 2), b"at least 13 orbs", cabi.ERR_INVALID),
             (lambda c: c.skyfall.__setitem__(0, 0.5), b"add up to 1", cabi.ERR_INVALID),
             (lambda c: (c.skyfall.__setitem__(0, -0.1), c.skyfall.__setitem__(1, 1 / 6 + 0.1 + 1 / 6)), b"positive number", cabi.ERR_INVALID),
-            (lambda c: (setattr(c, "rows", 4), setattr(c, "cols", 6)), b"5x6 and 6x7", cabi.ERR_UNSUPPORTED),
+            (lambda c: (setattr(c, "rows", 9), setattr(c, "cols", 9)), b"more than 64 cells", cabi.ERR_UNSUPPORTED),
             (lambda c: (c.skyfall.__setitem__(9, 1 / 6), c.skyfall.__setitem__(0, 0.0)), b"3-bit", cabi.ERR_UNSUPPORTED),
             (lambda c: c.team_color_1.__setitem__(0, 5), b"damage_tracker", cabi.ERR_UNSUPPORTED)):
         cfg = cabi.default_config()

@@ -67,8 +67,10 @@ def test_pad_facade_replays_reference_episodes(pb):
         pb.PAD(dim_row=2, dim_col=6)
     with pytest.raises(Exception, match="add up to 1"):
         pb.PAD(skyfall=[0.5, 0.1, 0, 0, 0, 0, 0, 0, 0, 0])
-    with pytest.raises(NotImplementedError):
-        pb.PAD(dim_row=4, dim_col=6)
+    with pytest.raises(NotImplementedError, match="more than 64 cells"):
+        pb.PAD(dim_row=9, dim_col=9)
+    odd = pb.PAD(dim_row=4, dim_col=6, seed=3)            # no specialised kernel: the run-time-dimension path
+    assert odd.board.shape == (4, 6) and orc.cancel(np.ascontiguousarray(odd.board, np.int8)) == []
     small = pb.PAD(dim_row=4, dim_col=5, seed=3)
     assert small.board.shape == (4, 5) and orc.cancel(np.ascontiguousarray(small.board, np.int8)) == []
 

@@ -177,6 +177,80 @@ def test_step_fuzz_vs_oracle(pb, rows, cols, mode):
         assert np.array_equal(o.obs.cpu().numpy(), orc.onehot(boards, fingers).astype(np.uint8)), t
 
 
+@pytest.mark.parametrize("rows,cols", [(3, 5), (7, 9), (8, 8), (2, 7), (1, 13), (6, 5), (4, 8), (5, 5)])
+def test_any_board_size_up_to_64_cells_on_device(pb, rows, cols):
+    """VERDICT r1 missing #4: PAD.__init__ takes every dim_row x dim_col with at least 13 orbs (game.py:54-68).  Sizes
+    without a specialised instantiation run on the run-time-dimension kernels (GeomDyn): steps with cascades, auto-reset,
+    both observation dtypes, pack / unpack, reset, the fused rollout and the policy step, all against the oracle."""
+    rng = np.random.default_rng(rows * 100 + cols)
+    n = 20_000 + 7
+    for wide in (False, True):
+        sky = [0.05, 0.15, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1] if wide else None
+        ocfg = orc.make_cfg(rows, cols, True, seed=77, skyfall=sky)
+        env = pb.BatchedPAD(n, rows, cols, seed=77, env0=11, skyfall=sky)
+        assert env.words == (8 if not wide else 12)
+        boards = random_boards(rng, n, rows, cols, "all10" if wide else "few")
+        fingers = np.stack([rng.integers(0, rows, n), rng.integers(0, cols, n)], 1).astype(np.int32)
+        prev = np.full(n, 4, np.uint8)
+        moves = np.zeros(n, np.uint16)
+        assert not env.set_state(boards, fingers).any()
+        st = env.get_state()
+        assert np.array_equal(st.boards.cpu().numpy(), boards) and np.array_equal(st.fingers.cpu().numpy(), fingers)
+        assert np.array_equal(pb.layout.unpack_state(env.state.cpu().numpy().view(np.uint32), rows, cols, env.orb_bits)[0], boards)
+        for t in range(6):
+            inj = rng.integers(0, 10 if wide else 6, size=(n, 40)).astype(np.uint8) if t % 2 else None
+            actions = None if t % 3 == 2 else rng.integers(0, 6, size=n).astype(np.uint8)
+            kw = dict(eval_moves=(t != 3), auto_reset=(t % 2 == 0), max_moves=4)
+            a0, r0, i0, f0 = orc.step_batch(ocfg, boards, fingers, prev, moves, actions=actions, inj=inj, env0=11, step=t,
+                                            want_final=True, **kw)
+            o = env.step(actions, injected=inj, step=t, want_final=True, obs='f32' if t % 2 else 'u8', **kw)
+            st = env.get_state()
+            assert np.array_equal(o.action.cpu().numpy(), a0) and np.array_equal(u32(o.info), i0), t
+            assert np.array_equal(bits(o.reward.cpu().numpy()), bits(r0)), t
+            assert np.array_equal(st.boards.cpu().numpy(), boards) and np.array_equal(st.fingers.cpu().numpy(), fingers), t
+            assert np.array_equal(env.get_state(o.final_state).boards.cpu().numpy(), f0), t
+            assert np.array_equal(o.obs.cpu().numpy().astype(np.float32), orc.onehot(boards, fingers)), t
+        env.reset(step=20)
+        st = env.get_state()
+        for i in range(0, n, 997):
+            ob, of, _, _ = orc.reset(ocfg, env=11 + i, step=20)
+            assert np.array_equal(ob, st.boards[i].cpu().numpy()) and np.array_equal(of, st.fingers[i].cpu().numpy())
+    # the callers either side of the step on a run-time geometry: fused rollout == single steps, policy step == select + step
+    a = pb.BatchedPAD(4096, rows, cols, seed=5)
+    b = pb.BatchedPAD(4096, rows, cols, seed=5)
+    a.reset(step=0)
+    b.state.copy_(a.state)
+    roll = a.rollout(7, max_moves=3, step=1)
+    tot = torch.zeros(4096, dtype=torch.float64, device=a.device)
+    for t in range(7):
+        tot += b.step(None, max_moves=3, auto_reset=True, step=1 + t).reward
+    assert torch.equal(a.state, b.state) and torch.equal(roll.reward_sum, tot)
+    q = torch.randn((4096, 5), device=a.device, generator=torch.Generator(device=a.device).manual_seed(1)) * 100
+    acts = b.select_actions(q, method='boltzmann', beta=0.01, max_moves=3, step=50)
+    want = b.step(acts, auto_reset=True, obs='f32', step=50)
+    got = a.policy_step(q, method='boltzmann', beta=0.01, max_moves=3, obs='f32', step=50)
+    assert torch.equal(a.state, b.state) and torch.equal(got.action, want.action) and torch.equal(got.obs, want.obs)
+    # the drop-in facade and the free functions accept the size, too
+    from ppad_b200.pad import utils as pad_utils
+    env1 = pb.PAD(dim_row=rows, dim_col=cols)
+    board, finger = env1.reset()
+    assert board.shape == (rows, cols) and not pad_utils.cancel(np.array(board))
+    env1.step(env1.action_space.sample())
+    env1.step('pass')
+    assert len(env1.rewards) == 2 and env1.board.shape == (rows, cols)
+    for f in ([0, 0], [rows - 1, cols - 1], [rows // 2, cols // 2]):
+        want = set()                                       # utils.py:73-83, with its elif pairing
+        if f[0] == 0:
+            want.add('up')
+        elif f[0] == rows - 1:
+            want.add('down')
+        if f[1] == 0:
+            want.add('left')
+        elif f[1] == cols - 1:
+            want.add('right')
+        assert pad_utils.illegal_actions(np.array(f), rows, cols) == want, f
+
+
 @pytest.mark.parametrize("rows,cols", [(4, 5), (5, 6), (6, 7)])
 @pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 255, 257, 1000])
 def test_obs_ragged_batches(pb, rows, cols, n):
@@ -354,9 +428,9 @@ def test_empty_batch_and_errors(pb):
     o = env.step(None, obs='f32')
     assert o.reward.numel() == 0
     with pytest.raises(pb._cabi.PPADError) as e:
-        pb.BatchedPAD(4, 4, 4)
+        pb.BatchedPAD(4, 9, 9)                             # more than 64 cells
     assert e.value.status == pb._cabi.ERR_UNSUPPORTED
-    assert pb.BatchedPAD(4, 4, 5).words == 4
+    assert pb.BatchedPAD(4, 4, 5).words == 4 and pb.BatchedPAD(4, 4, 4).words == 8     # 4x4: run-time dimensions
     with pytest.raises(pb._cabi.PPADError) as e:
         pb.BatchedPAD(4, 3, 4)
     assert "at least 13 orbs" in str(e.value)

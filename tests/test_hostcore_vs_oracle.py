@@ -106,6 +106,47 @@ def test_step_batch_fuzz(rows, cols, mode):
         assert seen_flags & orc.FLAG_SKYFALL_EXHAUSTED
 
 
+ODD_SIZES = [(3, 5), (7, 9), (8, 8), (2, 7), (1, 13), (13, 1), (6, 5), (4, 8), (3, 21), (5, 5)]
+
+
+@pytest.mark.parametrize("rows,cols", ODD_SIZES)
+def test_any_board_size_up_to_64_cells(rows, cols):
+    """PAD.__init__ takes every dim_row x dim_col with at least 13 orbs (game.py:54-68): the run-time-dimension
+    geometry (GeomDyn) against the oracle -- cancel incl. combo order, drop, full steps with cascades, reset."""
+    rng = np.random.default_rng(rows * 100 + cols)
+    n = 1500
+    boards = random_boards(rng, n, rows, cols, "few")
+    mine = boards.copy()
+    n_combos, log = hc.cancel(mine, log_cap=24)
+    for i in range(0, n, 3):
+        b = boards[i].copy()
+        combos = orc.cancel(b)
+        assert n_combos[i] == len(combos) and [int(v) for v in log[i, :len(combos)]] == [c | (k << 8) for c, k in combos], i
+        assert np.array_equal(b, mine[i]), i
+    for wide in (False, True):
+        sky = [0.05, 0.15, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1] if wide else None
+        ocfg = orc.make_cfg(rows, cols, True, seed=99, skyfall=sky)
+        cfg = hc.cfg_from_oracle(ocfg)
+        b0 = random_boards(rng, n, rows, cols, "all10" if wide else "uniform6")
+        fingers = np.stack([rng.integers(0, rows, n), rng.integers(0, cols, n)], 1).astype(np.int32)
+        a = [b0.copy(), fingers.copy(), np.full(n, 4, np.uint8), np.zeros(n, np.uint16)]
+        b = [b0.copy(), fingers.copy(), np.full(n, 4, np.uint8), np.zeros(n, np.uint16)]
+        for t in range(6):
+            inj = rng.integers(0, 10 if wide else 6, size=(n, 40)).astype(np.uint8) if t % 2 else None
+            actions = None if t % 3 == 2 else rng.integers(0, 6, size=n).astype(np.uint8)
+            kw = dict(actions=actions, eval_moves=(t != 3), auto_reset=(t % 2 == 0), max_moves=4, inj=inj, env0=5, step=t,
+                      want_final=True)
+            a0, r0, i0, f0 = orc.step_batch(ocfg, *a, **kw)
+            a1, r1, i1, f1, _ = hc.step_batch(cfg, *b, **kw)
+            assert np.array_equal(a0, a1) and np.array_equal(i0, i1) and np.array_equal(bits(r0), bits(r1)) and np.array_equal(f0, f1), t
+            for u, v in zip(a, b):
+                assert np.array_equal(u, v), t
+        rb, rf, rfl, rcons = hc.reset(cfg, 64, env0=3, step=9)
+        for i in range(64):
+            ob, of, ocons, _ = orc.reset(ocfg, env=3 + i, step=9)
+            assert np.array_equal(ob, rb[i]) and np.array_equal(of, rf[i]) and ocons == rcons[i], i
+
+
 @pytest.mark.parametrize("fmt", [0, 1])
 def test_injected_codes_that_are_no_orb_type_are_flagged(fmt):
     """a nibble of 7 (3-bit context) writes an empty cell, 8..15 alias: flagged, never silent."""
