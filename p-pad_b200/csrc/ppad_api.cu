@@ -407,11 +407,32 @@ int ppad_create(const ppad_config *cfg, int device, ppad_ctx **out)
         ctx->pool_ctas_per_sm = pool_occupancy(ctx->geom);
     }
     if (ctx->pool_ctas_per_sm <= 0) ctx->pool_ctas_per_sm = 1;
+    {
+        DeviceGuard guard(device);
+        if (cudaMalloc(&ctx->tile_counters, 2 * TILE_COUNTERS * sizeof(uint32_t)) != cudaSuccess ||
+            cudaMemset(ctx->tile_counters, 0, 2 * TILE_COUNTERS * sizeof(uint32_t)) != cudaSuccess) {
+            cudaGetLastError();
+            delete ctx;
+            return fail(PPAD_ERR_CUDA, "ppad_create: allocating the tile counters failed");
+        }
+    }
+    ctx->next_counter = new std::atomic<uint32_t>(0);
+    const char *kind = std::getenv("PPAD_POOL_KIND");
+    ctx->pool_kind = kind ? std::atoi(kind) : 1;
     *out = ctx;
     return PPAD_OK;
 }
 
-void ppad_destroy(ppad_ctx *ctx) { delete ctx; }
+void ppad_destroy(ppad_ctx *ctx)
+{
+    if (!ctx) return;
+    if (ctx->tile_counters) {
+        DeviceGuard guard(ctx->device);
+        cudaFree(ctx->tile_counters);
+    }
+    delete ctx->next_counter;
+    delete ctx;
+}
 
 int ppad_pack(const ppad_ctx *ctx, int64_t n, const void *boards, const void *fingers, int dtype, const uint8_t *prev,
               const uint16_t *moves, void *state, uint8_t *flags, void *stream)

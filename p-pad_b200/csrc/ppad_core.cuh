@@ -646,8 +646,8 @@ PPAD_HD void cancel_colour(const Board<G> &b, typename G::W m, typename G::W &sl
 // With a combo log (parity / debugging; kernel-uniform) every colour takes the generic loop, which then emits the
 // combos in the reference's global order.
 template <class G>
-PPAD_HD void cancel_tally(Board<G> &b, typename G::W m, typename G::W er, typename G::W ed, Tally &tally,
-                          const TeamTable &team, uint16_t *log = nullptr, int log_cap = 0)
+PPAD_HD void cancel_tally(Board<G> &b, typename G::W m, Tally &tally, const TeamTable &team, uint16_t *log = nullptr,
+                          int log_cap = 0)
 {
     typedef typename G::W W;
     W slow = m;
@@ -664,6 +664,10 @@ PPAD_HD void cancel_tally(Board<G> &b, typename G::W m, typename G::W er, typena
                 cancel_colour<G, 9>(b, m, slow, tally, team))
     }
     if (slow) {
+        // the edge masks are only needed here (about one board in twenty): recomputed rather than carried through the
+        // straight-line colour blocks above, where they would cost two registers on the hot path
+        W er, ed;
+        match_mask<G>(b, er, ed);
         // usually those cells still form ONE island (an L, T or cross, a run of 6): one flood fill settles it
         const W first = closure<G>(slow & (~slow + 1), er, ed);
         W todo = first;
@@ -894,11 +898,10 @@ struct CascadeItem {
 // masks) of it.b: cancel; stop if cascades are off or at the cap; else drop, fill and look for matches again.
 // Returns true when the refilled board matches again, with its masks in m / er / ed for the next iteration.
 template <class G>
-PPAD_HD bool cascade_round_m(CascadeItem<G> &it, typename G::W &m, typename G::W &er, typename G::W &ed,
-                             bool skyfall_damage, int cascade_cap, const TeamTable &team, const uint32_t *slab, int n_inj,
+PPAD_HD bool cascade_round_m(CascadeItem<G> &it, typename G::W &m, bool skyfall_damage, int cascade_cap, const TeamTable &team, const uint32_t *slab, int n_inj,
                              const RngKey &key, const SkyfallTable &sky, uint16_t *log, int log_cap, int slab_fmt = SLAB_NIBBLES)
 {
-    cancel_tally<G>(it.b, m, er, ed, it.tally, team, log, log_cap);
+    cancel_tally<G>(it.b, m, it.tally, team, log, log_cap);
     it.depth++;
     if (!skyfall_damage) return false;
     if (cascade_cap > 0 && it.depth >= cascade_cap) {
@@ -914,20 +917,9 @@ PPAD_HD bool cascade_round_m(CascadeItem<G> &it, typename G::W &m, typename G::W
     it.cursor = src.cursor;
     it.exhausted = src.exhausted;
     if (src.bad) it.flags |= FLAG_UNSUPPORTED_ORB;
+    typename G::W er, ed;
     m = match_mask<G>(it.b, er, ed);
     return m != 0;
-}
-
-// The same for a board whose match mask is not at hand (the pooled kernel parks boards between iterations).
-template <class G>
-PPAD_HD bool cascade_round(CascadeItem<G> &it, bool skyfall_damage, int cascade_cap, const TeamTable &team,
-                           const uint32_t *slab, int n_inj, const RngKey &key, const SkyfallTable &sky, uint16_t *log,
-                           int log_cap, int slab_fmt = SLAB_NIBBLES)
-{
-    typename G::W er, ed;
-    typename G::W m = match_mask<G>(it.b, er, ed);
-    if (m == 0) return false;
-    return cascade_round_m<G>(it, m, er, ed, skyfall_damage, cascade_cap, team, slab, n_inj, key, sky, log, log_cap, slab_fmt);
 }
 
 // damage (game.py:157-199) of an explicit combo list: log[i] = colour | N << 8
@@ -1269,7 +1261,7 @@ PPAD_HD StepOut step_board(bool live, State<G> &s, Board<G> &final_board, const 
     }
     while (warp_any(cascading)) {
         if (cascading)
-            cascading = cascade_round_m<G>(it, m, er, ed, p.skyfall_damage != 0, p.cascade_cap, p.team, slab, p.n_inj,
+            cascading = cascade_round_m<G>(it, m, p.skyfall_damage != 0, p.cascade_cap, p.team, slab, p.n_inj,
                                            key, p.sky, log, p.log_cap, p.slab_fmt);
         warp_converge();
     }

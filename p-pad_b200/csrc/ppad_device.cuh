@@ -369,7 +369,11 @@ struct ppad_ctx {
     ppad::StepParams base;   // base.dyn: the board dimensions for the run-time geometries
     int sm_count;
     int pool_ctas_per_sm;   // resident CTAs of the persistent step_pool_kernel
+    uint32_t *tile_counters;            // DEVICE [TILE_COUNTERS]: dynamic tile counters of the warp-pool kernel, one per launch
+    std::atomic<uint32_t> *next_counter;   // round robin over them (launches of one context may overlap on several streams)
+    int pool_kind;          // 1 = warp pool (default), 0 = CTA pool (env PPAD_POOL_KIND, for A/B runs)
 };
+constexpr int TILE_COUNTERS = 256;
 
 #define PPAD_DISPATCH(ctx, EXPR)                                   \
     do {                                                           \

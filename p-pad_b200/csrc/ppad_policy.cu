@@ -13,34 +13,35 @@ PPAD_POLICY_LAUNCHERS(extern, G45W)
 PPAD_POLICY_LAUNCHERS(extern, GDYN)
 PPAD_POLICY_LAUNCHERS(extern, GDYNW)
 
-// sums the per-CTA rows (max for the reward maximum): out[STATS_WORDS], one CTA
+// Sums the per-CTA rows (max for the reward maximum) into out[STATS_WORDS] (zeroed before the launch).  A row is 320
+// contiguous bytes: 6 rows x 40 words per pass of a CTA's 240 working threads, consecutive threads on consecutive words;
+// one 64-bit reduction per word and CTA at the end.  (One CTA walking all rows took 180 us for 8192 rows: a third of
+// the 2^21-board policy step it follows.)
+constexpr int REDUCE_ROWS_PER_PASS = 6;
 __global__ void __launch_bounds__(BLOCK) stats_reduce_kernel(const unsigned long long *rows, int64_t n_rows, unsigned long long *out)
 {
-    __shared__ unsigned long long part[BLOCK / 32][STATS_WORDS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int w = 0; w < STATS_WORDS; w++) {
+    __shared__ unsigned long long part[REDUCE_ROWS_PER_PASS][STATS_WORDS];
+    const int w = threadIdx.x % STATS_WORDS, lane_row = threadIdx.x / STATS_WORDS;
+    const bool is_max = w == ST_REWARD_MAX;
+    if (lane_row < REDUCE_ROWS_PER_PASS) {
         unsigned long long acc = 0;
-        for (int64_t r = threadIdx.x; r < n_rows; r += BLOCK) {
+        for (int64_t r = (int64_t)blockIdx.x * REDUCE_ROWS_PER_PASS + lane_row; r < n_rows; r += (int64_t)gridDim.x * REDUCE_ROWS_PER_PASS) {
             const unsigned long long v = rows[r * STATS_WORDS + w];
-            acc = w == ST_REWARD_MAX ? (v > acc ? v : acc) : acc + v;
+            acc = is_max ? (v > acc ? v : acc) : acc + v;
         }
-        for (int off = 16; off; off >>= 1) {
-            const unsigned long long v = __shfl_xor_sync(0xFFFFFFFFu, acc, off);
-            acc = w == ST_REWARD_MAX ? (v > acc ? v : acc) : acc + v;
-        }
-        if (lane == 0) part[warp][w] = acc;
+        part[lane_row][w] = acc;
     }
     __syncthreads();
     if (threadIdx.x < STATS_WORDS) {
         unsigned long long acc = 0;
-        for (int k = 0; k < BLOCK / 32; k++) {
+        for (int k = 0; k < REDUCE_ROWS_PER_PASS; k++) {
             const unsigned long long v = part[k][threadIdx.x];
-            acc = threadIdx.x == ST_REWARD_MAX ? (v > acc ? v : acc) : acc + v;
+            acc = is_max ? (v > acc ? v : acc) : acc + v;
         }
-        out[threadIdx.x] = acc;
+        if (is_max) atomicMax(&out[threadIdx.x], acc);
+        else atomicAdd(&out[threadIdx.x], acc);
     }
 }
-
 
 }   // namespace ppad
 
@@ -114,9 +115,12 @@ int ppad_policy_stats(const ppad_ctx *ctx, int64_t n, const uint64_t *stats_rows
 {
     PPAD_ENTER(ctx, n);
     if (!stats_rows || !out) return fail(PPAD_ERR_INVALID, "ppad_policy_stats: null pointer");
-    stats_reduce_kernel<<<1, BLOCK, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long *>(stats_rows),
-                                                              ppad_policy_stats_rows(n),
-                                                              reinterpret_cast<unsigned long long *>(out));
+    const int64_t n_rows = ppad_policy_stats_rows(n);
+    if (int r = cuda_check(cudaMemsetAsync(out, 0, STATS_WORDS * sizeof(uint64_t), (cudaStream_t)stream), "ppad_policy_stats")) return r;
+    int64_t grid = (n_rows + REDUCE_ROWS_PER_PASS * 8 - 1) / (REDUCE_ROWS_PER_PASS * 8);   // >= 8 passes per CTA
+    grid = grid < 1 ? 1 : (grid > 2 * ctx->sm_count ? 2 * ctx->sm_count : grid);
+    stats_reduce_kernel<<<(unsigned)grid, BLOCK, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long *>(stats_rows),
+                                                                           n_rows, reinterpret_cast<unsigned long long *>(out));
     return after_launch("stats_reduce_kernel");
 }
 

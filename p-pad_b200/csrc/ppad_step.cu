@@ -115,7 +115,8 @@ static int launch_step(const ppad_ctx *ctx, const ppad_step_args *args, cudaStre
         const int64_t lines = compact->capacity_bytes / 128;
         a.c_capacity = (uint32_t)(lines > 0x7FFFFFFF ? 0x7FFFFFFF : lines);
     }
-    int choice = STEP_KERNEL_POOL;
+    a.tile_counter = nullptr;
+    int choice = ctx->pool_kind == 1 ? STEP_KERNEL_WPOOL : STEP_KERNEL_POOL;
     if (args->obs) choice = STEP_KERNEL_OBS;
     else if (compact || coalesced_results || (!a.p.eval_moves && !a.actions && !a.paths) || !a.p.skyfall_damage) {
         // results go straight to host memory: the pooled kernel's scattered 8-byte result writes would become tiny
@@ -127,6 +128,11 @@ static int launch_step(const ppad_ctx *ctx, const ppad_step_args *args, cudaStre
         // Without skyfall (skyfall_damage = 0: the look-ahead's and smart data's evaluations) a board is cancelled
         // once and never cascades, so there is nothing to pool either: 0.027 against 0.033 ms per 2^20 evaluations.
         choice = STEP_KERNEL_THREAD;
+    }
+    if (choice == STEP_KERNEL_WPOOL) {
+        // a pair of counters per launch, handed out round robin: launches of one context may overlap on several streams
+        // (256 pairs: a pair is reused only after 255 later launches were enqueued)
+        a.tile_counter = ctx->tile_counters + 2 * (ctx->next_counter->fetch_add(1, std::memory_order_relaxed) % TILE_COUNTERS);
     }
     return dispatch_step(ctx, a, choice, st);
 }

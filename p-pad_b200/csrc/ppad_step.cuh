@@ -31,6 +31,8 @@ struct StepKernelArgs {
     int32_t path_words, path_len;
     int32_t stage_slab;   // the slab is pinned HOST memory (zero copy): fetch each row once, up front.  1: 4 words per
                           // board, one uint4 per thread; 2: 3 words per board, the CTA's 3072 contiguous bytes cooperatively
+    uint32_t *tile_counter;   // DEVICE [2]: {next tile, CTAs finished} of the warp-pool kernel; both 0 before the launch and
+                              // left at 0 by the last CTA to finish (no memset between launches)
     // compact result stream (COMPACT instantiations: the host pipe), see include/ppad_b200.h ppad_host_step_args
     uint32_t *c_nibbles;      // [tiles, 32] words: nibble i of tile t = action (7 = none) | has_record << 3 of board 256 t + i
     uint32_t *c_tile_line;    // [tiles]: first 128-byte line of the tile's record block
@@ -309,48 +311,59 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
 #define PPAD_POOL_MINB (1024 / PPAD_POOL_BLOCK)
 #endif
 constexpr int PBLOCK = PPAD_POOL_BLOCK;        // threads per CTA of the pooled kernel
-constexpr int POOL_SLOTS = PBLOCK + PBLOCK / 2;
-constexpr int POOL_FILL_BELOW = PBLOCK / 2;    // fill while pool <= this: pool + PBLOCK <= POOL_SLOTS always holds
+#if !defined(PPAD_POOL_HALVES)
+#define PPAD_POOL_HALVES 3                     // pool capacity in units of PBLOCK / 2
+#endif
+constexpr int POOL_SLOTS = PBLOCK * PPAD_POOL_HALVES / 2;
+constexpr int POOL_FILL_BELOW = POOL_SLOTS - PBLOCK;   // fill while pool <= this: pool + PBLOCK <= POOL_SLOTS always holds
 
 template <class G>
 struct CascadePool {
     typename G::W b0[POOL_SLOTS], b1[POOL_SLOTS], b2[POOL_SLOTS], b3[G::NP > 3 ? POOL_SLOTS : 1];
+    typename G::W mm[POOL_SLOTS];         // match mask of the parked board (computed when it was parked)
     double t0[POOL_SLOTS], t1[POOL_SLOTS], t2[POOL_SLOTS], t3[POOL_SLOTS], t4[POOL_SLOTS];
     uint32_t counts[POOL_SLOTS];   // n_combos [0,16) | depth [16,24) | flags [24,32)
     uint32_t source[POOL_SLOTS];   // skyfall cursor [0,16) | injected slab exhausted [16]
     uint64_t owner[POOL_SLOTS];    // board index within the launch
     int warp_count[2][PBLOCK / 32];   // double buffered: consecutive compactions alternate, one barrier each
 
-    __device__ __forceinline__ void put(int slot, const CascadeItem<G> &it, uint64_t own)
+    __device__ __forceinline__ void put(int slot, const CascadeItem<G> &it, uint64_t own, typename G::W m)
     {
         b0[slot] = it.b.b0;
         b1[slot] = it.b.b1;
         b2[slot] = it.b.b2;
         PPAD_P4(b3[slot] = it.b.b3)
-        t0[slot] = it.tally.t0;
-        t1[slot] = it.tally.t1;
-        t2[slot] = it.tally.t2;
-        t3[slot] = it.tally.t3;
-        t4[slot] = it.tally.t4;
+        mm[slot] = m;
+        if (it.depth) {   // a board parked by the fill has not been tallied yet: its trackers are zero, not stored
+            t0[slot] = it.tally.t0;
+            t1[slot] = it.tally.t1;
+            t2[slot] = it.tally.t2;
+            t3[slot] = it.tally.t3;
+            t4[slot] = it.tally.t4;
+        }
         const uint32_t nc = it.tally.n_combos > 0xFFFF ? 0xFFFFu : (uint32_t)it.tally.n_combos;
         counts[slot] = nc | (sat255(it.depth) << 16) | ((it.flags & 0xFFu) << 24);
         source[slot] = (it.cursor > 0xFFFF ? 0xFFFFu : (uint32_t)it.cursor) | ((it.exhausted ? 1u : 0u) << 16);
         owner[slot] = own;
     }
-    __device__ __forceinline__ uint64_t get(int slot, CascadeItem<G> &it) const
+    __device__ __forceinline__ uint64_t get(int slot, CascadeItem<G> &it, typename G::W &m) const
     {
         it.b.b0 = b0[slot];
         it.b.b1 = b1[slot];
         it.b.b2 = b2[slot];
         PPAD_P4(it.b.b3 = b3[slot])
-        it.tally.t0 = t0[slot];
-        it.tally.t1 = t1[slot];
-        it.tally.t2 = t2[slot];
-        it.tally.t3 = t3[slot];
-        it.tally.t4 = t4[slot];
+        m = mm[slot];
         const uint32_t c = counts[slot], q = source[slot];
         it.tally.n_combos = (int)(c & 0xFFFFu);
         it.depth = (int)((c >> 16) & 0xFFu);
+        it.tally.t0 = it.tally.t1 = it.tally.t2 = it.tally.t3 = it.tally.t4 = 0.0;
+        if (it.depth) {
+            it.tally.t0 = t0[slot];
+            it.tally.t1 = t1[slot];
+            it.tally.t2 = t2[slot];
+            it.tally.t3 = t3[slot];
+            it.tally.t4 = t4[slot];
+        }
         it.flags = c >> 24;
         it.cursor = (int)(q & 0xFFFFu);
         it.exhausted = (q >> 16) & 1u;
@@ -422,9 +435,11 @@ __global__ void __launch_bounds__(PBLOCK, PPAD_POOL_MINB) step_pool_kernel(const
                 }
             }
             it.init(s.b, pre.flags);             // the cascade works on a copy (game.py:366)
+            W m0 = 0;
             if (valid && pre.evaluate) {
                 W er, ed;
-                cascading = match_mask<G>(it.b, er, ed) != 0;
+                m0 = match_mask<G>(it.b, er, ed);
+                cascading = m0 != 0;
             }
             if constexpr (AR) {                   // launches with auto_reset; the reset is warp-cooperative
                 const bool need = valid && pre.action == ACT_PASS;
@@ -445,7 +460,7 @@ __global__ void __launch_bounds__(PBLOCK, PPAD_POOL_MINB) step_pool_kernel(const
             int added;
             const int slot = pool.compact(cascading, added, phase);
             phase ^= 1;
-            if (cascading) pool.put(pool_count + slot, it, (uint64_t)i);
+            if (cascading) pool.put(pool_count + slot, it, (uint64_t)i, m0);
             pool_count += added;
             tile += gridDim.x;
         }
@@ -457,10 +472,11 @@ __global__ void __launch_bounds__(PBLOCK, PPAD_POOL_MINB) step_pool_kernel(const
         CascadeItem<G> it;
         uint64_t own = 0;
         bool again = false;
+        W mk = 0;
         if (tid < m) {
-            own = pool.get(base + tid, it);
+            own = pool.get(base + tid, it, mk);
             const RngKey key = board_key(a.p, a.env0 + own);
-            again = cascade_round<G>(it, sd, a.p.cascade_cap, a.p.team,
+            again = cascade_round_m<G>(it, mk, sd, a.p.cascade_cap, a.p.team,
                                      a.slab ? a.slab + (size_t)own * a.p.slab_words : nullptr, a.p.n_inj, key, a.p.sky,
                                      a.combo_log ? a.combo_log + (size_t)own * a.p.log_cap : nullptr, a.p.log_cap, a.p.slab_fmt);
             if (!again) {
@@ -475,8 +491,198 @@ __global__ void __launch_bounds__(PBLOCK, PPAD_POOL_MINB) step_pool_kernel(const
             int survivors;
             const int slot = pool.compact(again, survivors, phase);   // its barrier: every get() of the round is done
             phase ^= 1;
-            if (again) pool.put(base + slot, it, own);   // read again only after the barrier at the top of the round
+            if (again) pool.put(base + slot, it, own, mk);   // read again only after the barrier at the top of the round
             pool_count = base + survivors;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same recirculating pool at WARP granularity: every warp is autonomous -- it pulls tiles of 32 boards from a
+// global counter, keeps its own pool of cascading boards in its slice of shared memory and never meets a CTA barrier
+// (ncu on step_pool_kernel: the compaction barrier is 33 % of the stall samples).  Tiles are handed out dynamically,
+// so the tail of the launch is one tile of 32 boards per warp instead of one of 256 per CTA.
+// ------------------------------------------------------------------------------------------------
+#if !defined(PPAD_WSLOTS)
+#define PPAD_WSLOTS 64
+#endif
+constexpr int WSLOTS = PPAD_WSLOTS;                      // pool slots per warp: a fill needs 32 free ones
+
+template <class G>
+struct WarpPool {
+    typename G::W b0[WSLOTS], b1[WSLOTS], b2[WSLOTS], b3[G::NP > 3 ? WSLOTS : 1];
+    typename G::W mm[WSLOTS];         // match mask of the parked board (computed when it was parked)
+    double t0[WSLOTS], t1[WSLOTS], t2[WSLOTS], t3[WSLOTS], t4[WSLOTS];
+    uint32_t counts[WSLOTS];   // n_combos [0,16) | depth [16,24) | flags [24,32)
+    uint32_t source[WSLOTS];   // skyfall cursor [0,16) | injected slab exhausted [16]
+    uint64_t owner[WSLOTS];    // board index within the launch
+
+    __device__ __forceinline__ void put(int slot, const CascadeItem<G> &it, uint64_t own, typename G::W m)
+    {
+        b0[slot] = it.b.b0;
+        b1[slot] = it.b.b1;
+        b2[slot] = it.b.b2;
+        PPAD_P4(b3[slot] = it.b.b3)
+        mm[slot] = m;
+        if (it.depth) {   // a board parked by the fill has not been tallied yet: its trackers are zero, not stored
+            t0[slot] = it.tally.t0;
+            t1[slot] = it.tally.t1;
+            t2[slot] = it.tally.t2;
+            t3[slot] = it.tally.t3;
+            t4[slot] = it.tally.t4;
+        }
+        const uint32_t nc = it.tally.n_combos > 0xFFFF ? 0xFFFFu : (uint32_t)it.tally.n_combos;
+        counts[slot] = nc | (sat255(it.depth) << 16) | ((it.flags & 0xFFu) << 24);
+        source[slot] = (it.cursor > 0xFFFF ? 0xFFFFu : (uint32_t)it.cursor) | ((it.exhausted ? 1u : 0u) << 16);
+        owner[slot] = own;
+    }
+    __device__ __forceinline__ uint64_t get(int slot, CascadeItem<G> &it, typename G::W &m) const
+    {
+        it.b.b0 = b0[slot];
+        it.b.b1 = b1[slot];
+        it.b.b2 = b2[slot];
+        PPAD_P4(it.b.b3 = b3[slot])
+        m = mm[slot];
+        const uint32_t c = counts[slot], q = source[slot];
+        it.tally.n_combos = (int)(c & 0xFFFFu);
+        it.depth = (int)((c >> 16) & 0xFFu);
+        it.tally.t0 = it.tally.t1 = it.tally.t2 = it.tally.t3 = it.tally.t4 = 0.0;
+        if (it.depth) {
+            it.tally.t0 = t0[slot];
+            it.tally.t1 = t1[slot];
+            it.tally.t2 = t2[slot];
+            it.tally.t3 = t3[slot];
+            it.tally.t4 = t4[slot];
+        }
+        it.flags = c >> 24;
+        it.cursor = (int)(q & 0xFFFFu);
+        it.exhausted = (q >> 16) & 1u;
+        return owner[slot];
+    }
+};
+
+#if !defined(PPAD_WPOOL_MINB)
+#define PPAD_WPOOL_MINB 4
+#endif
+template <class G, bool AR>
+__global__ void __launch_bounds__(BLOCK, PPAD_WPOOL_MINB) step_wpool_kernel(const __grid_constant__ StepKernelArgs a)
+{
+    geom_enter<G>(a.p.dyn);
+    extern __shared__ __align__(16) unsigned char wpool_raw[];   // BLOCK / 32 WarpPool<G> (dynamic: more than 48 KB)
+    typedef typename G::W W;
+    const unsigned full = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    WarpPool<G> &pool = reinterpret_cast<WarpPool<G> *>(wpool_raw)[threadIdx.x >> 5];
+    const int64_t n_tiles = (a.n + 31) / 32;
+    const bool sd = a.p.skyfall_damage != 0;
+    int count = 0;                               // warp-uniform: boards in this warp's pool
+    bool more = true;                            // warp-uniform: the global counter has not run out
+
+    for (;;) {
+        // ---- fill: the convergent part of the step for one fresh tile of 32 boards, when the pool has room.
+        // (Fetching the next tile index one fill ahead to hide the atomic's round trip -- 17 % of the stall samples --
+        // was slower, 0.0731 against 0.0692 ms: a warp then holds a tile it is not yet working on, and with seven
+        // tiles per warp that costs more at the tail than the latency it hides.)
+        if (more && count <= WSLOTS - 32) {
+            unsigned t32 = 0;
+            if (lane == 0) t32 = atomicAdd(a.tile_counter, 1u);
+            const int64_t tile = (int64_t)__shfl_sync(full, t32, 0);
+            if (tile >= n_tiles) {
+                more = false;
+            } else {
+                const int64_t i = tile * 32 + lane;
+                const bool valid = i < a.n;
+                State<G> s;
+                CascadeItem<G> it;
+                bool cascading = false;
+                StepPrefix pre;
+                pre.action = 255;
+                pre.flags = 0;
+                pre.evaluate = false;
+                clear_state<G>(s);
+                if (valid) {
+                    s = StateIO<G>::load(a.state, i);
+                    const RngKey key = board_key(a.p, a.env0 + (uint64_t)i);
+                    if (a.paths) {
+                        int len = a.path_lens ? a.path_lens[i] : a.path_len;
+                        len = len > 16 * a.path_words ? 16 * a.path_words : len;
+                        pre = path_prefix<G>(s, a.p, a.paths + (size_t)i * a.path_words, len);
+                    } else {
+                        int action = -1;
+                        if (a.actions) {
+                            action = a.actions[i];
+                            if (action == PPAD_SAMPLE) action = -1;
+                        }
+                        pre = step_prefix<G>(s, a.p, key, action);
+                    }
+                }
+                it.init(s.b, pre.flags);             // the cascade works on a copy (game.py:366)
+                W m0 = 0;
+                if (valid && pre.evaluate) {
+                    W er, ed;
+                    m0 = match_mask<G>(it.b, er, ed);
+                    cascading = m0 != 0;
+                }
+                if constexpr (AR) {                   // launches with auto_reset; the reset is warp-cooperative
+                    const bool need = valid && pre.action == ACT_PASS;
+                    const uint32_t f = reset_boards_warp<G, true>(need, s, a.p, a.p.key.step, a.env0 + (uint64_t)i, nullptr, -1, -1, nullptr);
+                    if (need) it.flags |= FLAG_EPISODE_DONE | f;
+                }
+                if (valid) {
+                    StateIO<G>::store(a.state, i, s.b, s.meta);
+                    if (a.action_out) a.action_out[i] = (uint8_t)pre.action;
+                    if (a.final_state) StateIO<G>::store(a.final_state, i, it.b, s.meta);   // planes rewritten after a cascade
+                    if (a.state_copy) StateIO<G>::store(a.state_copy, i, s.b, s.meta);
+                    if (!cascading) {
+                        if (a.reward) a.reward[i] = 0.0;
+                        if (a.info) a.info[i] = it.info();
+                        if (a.consumed16) a.consumed16[i] = 0;
+                    }
+                }
+                const unsigned ballot = __ballot_sync(full, cascading);
+                if (cascading) pool.put(count + __popc(ballot & ((1u << lane) - 1u)), it, (uint64_t)i, m0);
+                count += __popc(ballot);
+                __syncwarp();
+                if (count <= WSLOTS - 32) continue;   // still room for a whole tile: fill on, the rounds run on full warps
+            }
+        }
+        if (count == 0) {
+            if (!more) break;
+            continue;
+        }
+        // ---- round: one cascade iteration for the top min(count, 32) boards of the pool
+        const int m = count < 32 ? count : 32;
+        const int base = count - m;
+        CascadeItem<G> it;
+        uint64_t own = 0;
+        bool again = false;
+        W mk = 0;
+        if (lane < m) {
+            own = pool.get(base + lane, it, mk);
+            const RngKey key = board_key(a.p, a.env0 + own);
+            again = cascade_round_m<G>(it, mk, sd, a.p.cascade_cap, a.p.team,
+                                     a.slab ? a.slab + (size_t)own * a.p.slab_words : nullptr, a.p.n_inj, key, a.p.sky,
+                                     a.combo_log ? a.combo_log + (size_t)own * a.p.log_cap : nullptr, a.p.log_cap, a.p.slab_fmt);
+            if (!again) {
+                if (a.reward) a.reward[own] = it.reward();
+                if (a.info) a.info[own] = it.info();
+                if (a.consumed16) a.consumed16[own] = (uint16_t)(it.cursor > 0xFFFF ? 0xFFFF : it.cursor);
+                if (a.final_state) StateIO<G>::store_planes(a.final_state, own, it.b);   // meta: written by the fill
+            }
+        }
+        __syncwarp();                                // every get() of the round is done before the survivors are put back
+        const unsigned ballot = __ballot_sync(full, again);
+        if (again) pool.put(base + __popc(ballot & ((1u << lane) - 1u)), it, own, mk);
+        count = base + __popc(ballot);
+        __syncwarp();
+    }
+    // the last CTA to finish leaves the counters at 0 for the launch that uses them next
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(a.tile_counter + 1, 1u) == gridDim.x - 1) {
+            a.tile_counter[0] = 0u;
+            a.tile_counter[1] = 0u;
         }
     }
 }
@@ -484,7 +690,7 @@ __global__ void __launch_bounds__(PBLOCK, PPAD_POOL_MINB) step_pool_kernel(const
 // ------------------------------------------------------------------------------------------------
 // per-geometry launchers (explicitly instantiated in ppad_step_inst.cu)
 // ------------------------------------------------------------------------------------------------
-enum StepKernelChoice { STEP_KERNEL_OBS = 0, STEP_KERNEL_THREAD = 1, STEP_KERNEL_POOL = 2 };
+enum StepKernelChoice { STEP_KERNEL_OBS = 0, STEP_KERNEL_THREAD = 1, STEP_KERNEL_POOL = 2, STEP_KERNEL_WPOOL = 3 };
 
 template <class G>
 int launch_step_g(const ppad_ctx *ctx, const StepKernelArgs &a, int choice, cudaStream_t st)
@@ -512,6 +718,28 @@ int launch_step_g(const ppad_ctx *ctx, const StepKernelArgs &a, int choice, cuda
         if (ar) step_obs_kernel<G, false, true><<<grid_for(a.n), BLOCK, 0, st>>>(a);
         else step_obs_kernel<G, false, false><<<grid_for(a.n), BLOCK, 0, st>>>(a);
         return after_launch("step_obs_kernel<no obs>");
+    }
+    if (choice == STEP_KERNEL_WPOOL) {
+        // persistent warps, dynamic tiles of 32 boards
+        const size_t sm = sizeof(WarpPool<G>) * (BLOCK / 32);
+        static int cached_ctas[2] = {0, 0};      // per instantiation (the attribute is per function, all devices alike)
+        int &ctas = cached_ctas[ar ? 1 : 0];
+        if (ctas == 0) {
+            if (ar) {
+                cudaFuncSetAttribute(step_wpool_kernel<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, step_wpool_kernel<G, true>, BLOCK, sm);
+            } else {
+                cudaFuncSetAttribute(step_wpool_kernel<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, step_wpool_kernel<G, false>, BLOCK, sm);
+            }
+            if (ctas <= 0) ctas = 1;
+        }
+        const int64_t want = (a.n + BLOCK - 1) / BLOCK;
+        int64_t grid = (int64_t)ctx->sm_count * (ctas > 0 ? ctas : 1);
+        if (grid > want) grid = want;
+        if (ar) step_wpool_kernel<G, true><<<(unsigned)grid, BLOCK, sm, st>>>(a);
+        else step_wpool_kernel<G, false><<<(unsigned)grid, BLOCK, sm, st>>>(a);
+        return after_launch("step_wpool_kernel");
     }
     // persistent: one wave of CTAs, as many as fit
     const int64_t tiles = (a.n + PBLOCK - 1) / PBLOCK;

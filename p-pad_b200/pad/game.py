@@ -442,6 +442,8 @@ class PAD:
     def calculate_reward(self, board=None, skyfall_damage=True, verbose=False):
         """Damage of all combos of `board` (a copy is evaluated; cancel -> drop -> skyfall until stable when
         skyfall_damage).  One fused kernel launch on the scratch record; the env's own record is not touched."""
+        if verbose is True:
+            return self._calculate_reward_staged(board, skyfall_damage)
         self._write_slot(1, self.board if board is None else board, self.finger, self._prev_id())
         if self.rng == 'reference' and skyfall_damage:
             result = []
@@ -459,13 +461,45 @@ class PAD:
         else:
             reward, info, _, extra = self._launch(1, _cabi.PASS, skyfall_damage=skyfall_damage, final=verbose,
                                                   log_cap=64 if verbose else 0)
-        if verbose is True:
-            n = info & 0xFF
-            print('Board after the cascade:')
-            self.render(self._venv.get_state(extra[0]).boards[0].cpu().numpy())
-            log = extra[1][0, :min(n, 64)].cpu().numpy().view(np.uint16)
-            print([{'color': parameters.int2english[int(v) & 0xFF], 'N': float(int(v) >> 8)} for v in log])
-            print('The total damange is:', reward)
+        return reward
+
+    def _calculate_reward_staged(self, board, skyfall_damage):
+        """calculate_reward(verbose=True): the reference prints the board at every stage of every cascade iteration
+        (game.py:372-403), so this path runs the stages one kernel at a time -- cancel, drop, fill_board -- instead of
+        the fused step.  The skyfall continues at the draw index the previous iteration stopped at, at ONE step index:
+        the result is the one the fused kernel gives (verbose does not change the outcome in the reference either)."""
+        from . import utils as pad_utils
+        board = np.copy(self.board if board is None else board)
+        tick = self._next_tick()
+        drawn = 0
+        all_combos = []
+        while True:
+            print('Board before combo canceling:')
+            self.render(board)
+            combos = pad_utils.cancel(board)
+            print('Board after combo canceling:')
+            self.render(board)
+            if len(combos) < 1:
+                break
+            all_combos += combos
+            if skyfall_damage is False:
+                break
+            board = self.drop(board=board)
+            print('Board after orb drop:')
+            self.render(board)
+            need = int((np.asarray(board) == -1).sum())
+            if self.rng == 'reference':
+                board = self.fill_board(board=board)
+            else:
+                self._push(board)
+                self._venv.fill_board(reset=False, draw0=drawn, step=tick)
+                board[...] = self._venv.get_state().boards[0].cpu().numpy()
+            drawn += need
+            print('Board after fill board:')
+            self.render(board)
+        reward = self.damage(all_combos)
+        print(all_combos)
+        print('The total damange is:', reward)
         return reward
 
     # ------------------------------------------------------------------ game.py:407-427

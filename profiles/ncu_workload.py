@@ -1,38 +1,66 @@
-"""Short workload for ncu captures (round 2): a few launches of every kernel VERDICT r1 asks evidence for.
-    python profiles/ncu_workload.py [n_log2]
-Launch order (after the resets / setup kernels): step_obs_kernel<5x6> x2, step_obs_kernel<5x6, compact> (host pipe) x2,
-policy_step_kernel<5x6> x2, step_obs_kernel<6x7> x2, reset_kernel<6x7> x1, step_pool_kernel<5x6> x2."""
+"""Workload for the ncu captures of round 2: every kernel VERDICT r1 asks evidence for, in its STEADY state (the boards
+have been stepped until the cascade statistics settle) and at the bench's sizes.  Only the section between
+cudaProfilerStart / Stop is profiled:
+
+    ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/prof python profiles/ncu_workload.py
+
+Profiled launches, in order: step_obs_kernel<5x6> x2 (the headline), step_obs_kernel<5x6, compact> x2 (host pipe, zero
+copy), step_pool_kernel<5x6> x2 (state only), policy_step_kernel<5x6> x2 (configs[4], 2^21 boards), step_obs_kernel<6x7>
+x2, reset_kernel<6x7> x1, reset_kernel<5x6> x1, rollout_kernel<5x6> x1 (51 fused steps), stats_reduce_kernel etc. as
+they come."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
 import torch
 import ppad_b200
 from ppad_b200.replay import RolloutRing, RolloutStats
 
-n = 1 << (int(sys.argv[1]) if len(sys.argv) > 1 else 20)
+n = 1 << 20
 dev = torch.device("cuda", 0)
 gen = torch.Generator(device=dev).manual_seed(1)
 env = ppad_b200.BatchedPAD(n, 5, 6, seed=1, device=dev)
 env.reset(step=0)
 slabs = [env._slab(torch.randint(0, 6, (n, 32), device=dev, dtype=torch.uint8, generator=gen), 'planes3')[0] for _ in range(4)]
 out = env.step(None, eval_moves=True, injected=(slabs[0], 32), slab_format='planes3', obs='f32', step=1)
-for t in range(2, 4):
+for t in range(2, 40):
     env.step(None, eval_moves=True, injected=(slabs[t & 3], 32), slab_format='planes3', obs=out.obs, step=t, out=out)
 pipe = env.host_pipe(slab_orbs=32, compact=True, slab_format='planes3')
 pipe.slab.copy_(slabs[0].cpu())
-for t in range(4, 6):
-    pipe.step(eval_moves=True, obs=out.obs, step=t, wait=True)
-ring, stats = RolloutRing(env, 4, gamma=0.99, log10=True), RolloutStats(env)
-qs = [torch.randn((n, 5), device=dev, generator=gen) * 1000 for _ in range(2)]
-for t in range(6, 8):
-    env.policy_step(qs[t & 1], method='boltzmann', beta=1e-3, epsilon=0.1, max_moves=50, obs=out.obs, ring=ring, stats=stats, out=out)
+pipe.step(eval_moves=True, obs=out.obs, step=40, wait=True)
+n2 = 1 << 21
+penv = ppad_b200.BatchedPAD(n2, 5, 6, seed=3, device=dev)
+penv.reset(step=0)
+ring, stats = RolloutRing(penv, 4, gamma=0.99, log10=True), RolloutStats(penv)
+qs = [torch.randn((n2, 5), device=dev, generator=gen) * 1000 for _ in range(2)]
+pobs = torch.empty((n2, 5, 6, 7), dtype=torch.float32, device=dev)
+pout = None
+for t in range(14):
+    pout = penv.policy_step(qs[t & 1], method='boltzmann', beta=1e-3, epsilon=0.1, max_moves=50, obs=pobs, ring=ring, stats=stats, out=pout)
 env7 = ppad_b200.BatchedPAD(n, 6, 7, seed=2, device=dev)
 env7.reset(step=0)
 slab7 = env7._slab(torch.randint(0, 6, (n, 32), device=dev, dtype=torch.uint8, generator=gen), 'planes3')[0]
 out7 = env7.step(None, eval_moves=True, injected=(slab7, 32), slab_format='planes3', obs='f32', step=1)
-env7.step(None, eval_moves=True, injected=(slab7, 32), slab_format='planes3', obs=out7.obs, step=2, out=out7)
-env7.reset(step=3)
-for t in range(8, 10):
-    env.step(None, eval_moves=True, injected=(slabs[t & 3], 32), slab_format='planes3', step=t, out=out)
+for t in range(2, 30):
+    env7.step(None, eval_moves=True, injected=(slab7, 32), slab_format='planes3', obs=out7.obs, step=t, out=out7)
+renv = ppad_b200.BatchedPAD(n, 5, 6, seed=4, device=dev)
+renv.reset(step=0)
+renv.rollout(51, max_moves=50)
 torch.cuda.synchronize()
-print("ncu workload done:", n, "boards; launches", ppad_b200._cabi.lib().ppad_launch_count())
+
+torch.cuda.profiler.start()
+for t in range(40, 42):
+    env.step(None, eval_moves=True, injected=(slabs[t & 3], 32), slab_format='planes3', obs=out.obs, step=t, out=out)
+for t in range(42, 44):
+    pipe.step(eval_moves=True, obs=out.obs, step=t, wait=True)
+for t in range(44, 46):
+    env.step(None, eval_moves=True, injected=(slabs[t & 3], 32), slab_format='planes3', step=t, out=out)
+for t in range(14, 16):
+    penv.policy_step(qs[t & 1], method='boltzmann', beta=1e-3, epsilon=0.1, max_moves=50, obs=pobs, ring=ring, stats=stats, out=pout)
+stats.vector()
+for t in range(30, 32):
+    env7.step(None, eval_moves=True, injected=(slab7, 32), slab_format='planes3', obs=out7.obs, step=t, out=out7)
+env7.reset(step=99)
+renv.reset(step=98)
+renv.rollout(51, max_moves=50)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
+print("ncu workload done; launches", ppad_b200._cabi.lib().ppad_launch_count())

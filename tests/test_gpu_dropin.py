@@ -132,6 +132,31 @@ def test_pad_stage_methods(pb):
     assert 0 <= env.random_orb() <= 5
 
 
+def test_verbose_calculate_reward_prints_every_stage_and_keeps_the_result(pb, capsys):
+    """game.py:372-403: verbose=True prints the board before / after cancel, after drop and after fill for every cascade
+    iteration; it runs stage by stage (cancel, drop, fill kernels) and returns what the fused kernel returns."""
+    board = np.array([[0, 0, 0, 1, 2, 3], [1, 2, 1, 2, 3, 1], [2, 1, 2, 0, 0, 0], [1, 2, 3, 1, 2, 3], [2, 3, 1, 2, 3, 1]])
+    for rng_mode in ('philox', 'reference'):
+        a = pb.PAD(board=board, finger=np.array([4, 0]), seed=11, rng=rng_mode)
+        b = pb.PAD(board=board, finger=np.array([4, 0]), seed=11, rng=rng_mode)
+        if rng_mode == 'reference':
+            import random
+            random.seed(5)
+        quiet = a.calculate_reward(board=a.board, skyfall_damage=True)
+        capsys.readouterr()
+        if rng_mode == 'reference':
+            random.seed(5)
+        loud = b.calculate_reward(board=b.board, skyfall_damage=True, verbose=True)
+        out = capsys.readouterr().out
+        assert bits(quiet) == bits(loud) and quiet >= 3250.0
+        for line in ('Board before combo canceling:', 'Board after combo canceling:', 'Board after orb drop:',
+                     'Board after fill board:', 'The total damange is:'):
+            assert line in out
+        assert out.count('Board before combo canceling:') >= 2 and np.array_equal(b.board, board)
+        b.calculate_reward(board=b.board, skyfall_damage=False, verbose=True)
+        assert 'Board after orb drop:' not in capsys.readouterr().out
+
+
 def test_free_functions_and_compat_namespace(pb):
     kat = json.load(open(os.path.join(G, "kat.json")))["cases"]
     from ppad_b200.pad import utils as pad_utils

@@ -376,9 +376,10 @@ def test_cancel_and_legal_mask(pb):
 
 
 def test_full_size_one_million_boards(pb):
-    """BASELINE.json configs[1]: 2^20 boards, random legal moves, injected skyfall; every board of
-    every step against the oracle, plus size-independent properties."""
-    n, rows, cols, T = 1 << 20, 5, 6, 3
+    """BASELINE.json configs[1] as SURVEY.md 8(d) states it: 2^20 boards, T = 64 steps of random legal moves with
+    injected skyfall; EVERY board of EVERY step against the oracle (action, reward bits, info word, state); in the first
+    steps also the sharding invariance and the size-independent properties.  PPAD_FULL_T overrides T."""
+    n, rows, cols, T = 1 << 20, 5, 6, int(os.environ.get("PPAD_FULL_T", 64))
     rng = np.random.default_rng(42)
     env = pb.BatchedPAD(n, rows, cols, seed=2024)
     assert not env.reset(step=0).any()
@@ -395,7 +396,8 @@ def test_full_size_one_million_boards(pb):
     for t in range(1, T + 1):
         inj = rng.integers(0, 6, size=(n, 32)).astype(np.uint8)
         before = env.state.clone()
-        o = env.step(None, eval_moves=True, injected=inj, step=t, obs='f32')
+        fmt = 'planes3' if t % 2 else 'nibbles'            # both slab layouts
+        o = env.step(None, eval_moves=True, injected=inj, step=t, obs='f32', slab_format=fmt)
         a0, r0, i0, _ = orc.step_batch(ocfg, boards, fingers, prev, moves, actions=None, inj=inj, step=t,
                                        threads=os.cpu_count() or 1)
         assert np.array_equal(o.action.cpu().numpy(), a0)
@@ -404,6 +406,8 @@ def test_full_size_one_million_boards(pb):
         st = env.get_state()
         assert np.array_equal(st.boards.cpu().numpy(), boards) and np.array_equal(st.fingers.cpu().numpy(), fingers)
         depth_hist += np.bincount((i0 >> 8) & 0xFF, minlength=256)
+        if t > 3:
+            continue
         # sharding invariance: two half slabs with env0 offsets reproduce the full slab
         for h, sl in zip(halves, (slice(0, n // 2), slice(n // 2, n))):
             oh = h.step(None, eval_moves=True, injected=inj[sl], step=t)
