@@ -291,20 +291,28 @@ __global__ void __launch_bounds__(BLOCK) permute_kernel(const DynGeomData dg, in
     State<G> s = StateIO<G>::load(state, i);
     const uint2 m2 = *reinterpret_cast<const uint2 *>(maps + 8 * i);
     const uint64_t lut = (uint64_t)m2.x | ((uint64_t)m2.y << 32);
-    W p0 = 0, p1 = 0, p2 = 0, p3 = 0;
-#pragma unroll
-    for (int c = 0; c < G::cells(); c++) {
-        const int code = code_at<G>(s.b, c);
-        const int to = code > 6 ? code : (int)((lut >> (8 * code)) & 7);   // empty cells and types 7..9 stay
-        p0 |= (W)(to & 1) << c;
-        p1 |= (W)((to >> 1) & 1) << c;
-        p2 |= (W)((to >> 2) & 1) << c;
-        PPAD_P4(p3 |= (W)((to >> 3) & 1) << c)
-    }
-    s.b.b0 = p0;
-    s.b.b1 = p1;
-    s.b.b2 = p2;
-    PPAD_P4(s.b.b3 = p3)
+    // bit-sliced: the cells of type t all move to type maps[t] at once (a plane at a time instead of a cell at a time);
+    // empty cells and types 7..9 keep their code
+    W p0 = 0, p1 = 0, p2 = 0, p3 = 0, moved = 0;
+    auto route = [&](W cells, int t) {
+        const int to = (int)((lut >> (8 * t)) & 7);
+        moved |= cells;
+        p0 |= (to & 1) ? cells : (W)0;
+        p1 |= (to & 2) ? cells : (W)0;
+        p2 |= (to & 4) ? cells : (W)0;
+    };
+    route(colour_plane<G, 0>(s.b) & G::board(), 0);
+    route(colour_plane<G, 1>(s.b) & G::board(), 1);
+    route(colour_plane<G, 2>(s.b) & G::board(), 2);
+    route(colour_plane<G, 3>(s.b) & G::board(), 3);
+    route(colour_plane<G, 4>(s.b) & G::board(), 4);
+    route(colour_plane<G, 5>(s.b) & G::board(), 5);
+    route(colour_plane<G, 6>(s.b) & G::board(), 6);
+    const W kept = G::board() & ~moved;
+    s.b.b0 = p0 | (s.b.b0 & kept);
+    s.b.b1 = p1 | (s.b.b1 & kept);
+    s.b.b2 = p2 | (s.b.b2 & kept);
+    PPAD_P4(s.b.b3 = p3 | (s.b.b3 & kept))
     StateIO<G>::store(state, i, s.b, s.meta);
 }
 

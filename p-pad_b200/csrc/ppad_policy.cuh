@@ -56,7 +56,9 @@ struct PolicyArgs {
 // MINB: resident CTAs per SM the register allocation aims at: 4 (64 registers, ~100 B of spills) or 3 (80 registers, no
 // spills).  Measured per 2^20 boards (profiles/r02f_ab.txt): 0.2198 ms with 4 against 0.2250 ms with 3 once the code was
 // made smaller (before: 0.269 against 0.254) -- occupancy beats the spills.
-template <class G, bool OBS, int MINB>
+// INJ: the launch has an injected skyfall slab.  Without one (the usual rollout: Philox skyfall) the instantiation does
+// not carry the slab paths of the skyfall at all -- this kernel is instruction-cache sensitive.
+template <class G, bool OBS, int MINB, bool INJ>
 __global__ void __launch_bounds__(BLOCK, MINB) policy_step_kernel(const __grid_constant__ PolicyArgs a)
 {
     geom_enter<G>(a.p.dyn);
@@ -96,8 +98,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) policy_step_kernel(const __grid_c
     // ---- the env step (every lane takes part: the cascade loop and the reset are warp-cooperative)
     const int episode_len = meta_moves(s.meta);   // moves made before this step (a pass ends the episode)
     Board<G> fin;
-    const StepOut o = step_board<G, true, true, PPAD_POLICY_REFILL_UNROLL>(valid, s, fin, a.p, env, action,
-                                                a.slab && valid ? a.slab + (size_t)i * a.p.slab_words : nullptr, nullptr);
+    const uint32_t *slab = nullptr;
+    if constexpr (INJ) slab = a.slab && valid ? a.slab + (size_t)i * a.p.slab_words : nullptr;
+    const StepOut o = step_board<G, true, true, PPAD_POLICY_REFILL_UNROLL>(valid, s, fin, a.p, env, action, slab, nullptr);
     if (valid) {
         StateIO<G>::store(a.state, i, s.b, s.meta);
         if (a.action_out) a.action_out[i] = (uint8_t)o.action;
@@ -177,16 +180,29 @@ __global__ void __launch_bounds__(BLOCK, MINB) policy_step_kernel(const __grid_c
     }
 }
 
+template <class G, bool OBS, bool INJ>
+void launch_policy_minb(const PolicyArgs &a, int minb, unsigned grid, cudaStream_t st)
+{
+#if defined(PPAD_POLICY_TUNING)      // A/B builds: also the 3-CTAs-per-SM (80 registers, no spills) instantiation
+    if (minb == 3) {
+        policy_step_kernel<G, OBS, 3, INJ><<<grid, BLOCK, 0, st>>>(a);
+        return;
+    }
+#endif
+    (void)minb;
+    policy_step_kernel<G, OBS, 4, INJ><<<grid, BLOCK, 0, st>>>(a);
+}
+
 template <class G>
 int launch_policy_g(const PolicyArgs &a, int minb, cudaStream_t st)
 {
     const unsigned grid = grid_for(a.n);
     if (a.obs) {
-        if (minb >= 4) policy_step_kernel<G, true, 4><<<grid, BLOCK, 0, st>>>(a);
-        else policy_step_kernel<G, true, 3><<<grid, BLOCK, 0, st>>>(a);
+        if (a.slab) launch_policy_minb<G, true, true>(a, minb, grid, st);
+        else launch_policy_minb<G, true, false>(a, minb, grid, st);
     } else {
-        if (minb >= 4) policy_step_kernel<G, false, 4><<<grid, BLOCK, 0, st>>>(a);
-        else policy_step_kernel<G, false, 3><<<grid, BLOCK, 0, st>>>(a);
+        if (a.slab) launch_policy_minb<G, false, true>(a, minb, grid, st);
+        else launch_policy_minb<G, false, false>(a, minb, grid, st);
     }
     return after_launch("policy_step_kernel");
 }
