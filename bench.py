@@ -560,7 +560,7 @@ def main():
         k = t & 1
         pipe2.wait(k)                              # results of step t - 2 (this buffer set) are on the host
         _ = int(pipe2.buffers[k].summary[0])       # "read" them
-        pipe2.step(eval_moves=True, obs=obs_buf, step=t, wait=False, buf=k)
+        pipe2.step(eval_moves=True, obs=obs_buf, step=t, wait=False, buf=k, join=False)
 
     for t in range(base_t + 50000, base_t + 50010):
         e2e_async_step(t)

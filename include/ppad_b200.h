@@ -244,6 +244,11 @@ typedef struct ppad_host_step_args {
     void *records_host;
     int64_t records_capacity;
     uint32_t *summary_host;
+    int32_t no_join;                 /* 0: `after_stream` is made to wait for this step (work queued there later sees the
+                                        state it leaves behind); 1: the caller orders later work itself (ppad_pipe_join /
+                                        ppad_pipe_wait) -- saves one cross-stream dependency per step when steps are
+                                        enqueued back to back */
+    int32_t reserved2;
 } ppad_host_step_args;
 /* bytes of records_host that can never overflow for n boards (with or without auto_reset) */
 int64_t ppad_compact_capacity(const ppad_ctx *ctx, int64_t n);

@@ -50,7 +50,8 @@ class HostStepArgs(C.Structure):
                 ("reward_host", C.c_void_p), ("info_host", C.c_void_p), ("state_out_host", C.c_void_p),
                 ("obs", C.c_void_p), ("obs_dtype", C.c_int32), ("slab_format", C.c_int32),
                 ("results_compact", C.c_int32), ("nibbles_host", C.c_void_p), ("tile_line_host", C.c_void_p),
-                ("records_host", C.c_void_p), ("records_capacity", C.c_int64), ("summary_host", C.c_void_p)]
+                ("records_host", C.c_void_p), ("records_capacity", C.c_int64), ("summary_host", C.c_void_p),
+                ("no_join", C.c_int32), ("reserved2", C.c_int32)]
 
 
 class PolicyArgs(C.Structure):

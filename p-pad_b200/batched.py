@@ -522,12 +522,14 @@ class HostPipe:
             self.venv.lib.ppad_pipe_destroy(pipe)
 
     def step(self, use_actions=False, use_slab=True, eval_moves=False, auto_reset=False, max_moves=0, obs=None,
-             want_state=None, skyfall_damage=None, step=None, wait=True, buf=0):
+             want_state=None, skyfall_damage=None, step=None, wait=True, buf=0, join=True):
         """Enqueue one step (inputs are read from buffers[buf].slab / .actions).  Dense pipes: the results land in
         .reward, .info, .action and, with want_state (default), .state.  Compact pipes: they land in .nibbles /
         .tile_line / .records / .summary -- decode them with results(buf); the state is only copied when want_state is
         set (the host can follow the board from the actions; fresh boards after a reset come with the records).
-        wait=False returns right after enqueueing; call wait(buf) before reading the results or refilling that set."""
+        wait=False returns right after enqueueing; call wait(buf) before reading the results or refilling that set.
+        join=True (default) orders work queued later on torch's current stream behind this step; join=False leaves that
+        to the caller (join() / wait()): one cross-stream dependency less per step when steps are enqueued back to back."""
         v = self.venv
         b = self.buffers[buf]
         if want_state is None:
@@ -549,6 +551,7 @@ class HostPipe:
         else:
             a.action_out_host, a.reward_host, a.info_host = b.action.data_ptr(), b.reward.data_ptr(), b.info.data_ptr()
         a.state_out_host = b.state.data_ptr() if want_state else None
+        a.no_join = 0 if join else 1
         if obs is not None:
             a.obs = obs.data_ptr()
             a.obs_dtype = _cabi.OBS_F32 if obs.dtype == torch.float32 else _cabi.OBS_U8

@@ -362,7 +362,7 @@ int ppad_pipe_step(ppad_pipe *p, const ppad_host_step_args *h, void *after_strea
         if (int r = launch_step(ctx, &a, st, true, true, h->results_compact ? &ct : nullptr)) return r;
         for (int k = 0; k < p->chunks && e == cudaSuccess; k++) e = cudaEventRecord(p->done[slot][k], st);
         // the caller's stream sees the state this step leaves behind (a later step / encode / reset on it is ordered)
-        if (e == cudaSuccess) e = cudaStreamWaitEvent((cudaStream_t)after_stream, p->done[slot][0], 0);
+        if (e == cudaSuccess && !h->no_join) e = cudaStreamWaitEvent((cudaStream_t)after_stream, p->done[slot][0], 0);
         return cuda_check(e, "ppad_pipe_step");
     }
     for (int k = 0; k < p->chunks && e == cudaSuccess; k++) {
@@ -426,7 +426,7 @@ int ppad_pipe_step(ppad_pipe *p, const ppad_host_step_args *h, void *after_strea
                                 (size_t)cnt * rec, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaEventRecord(p->done[slot][k], st);
     }
-    for (int k = 0; k < p->chunks && e == cudaSuccess; k++) {
+    for (int k = 0; k < p->chunks && e == cudaSuccess && !h->no_join; k++) {
         if ((int64_t)k * p->chunk >= h->n) break;
         e = cudaStreamWaitEvent((cudaStream_t)after_stream, p->done[slot][k], 0);
     }

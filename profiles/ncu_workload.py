@@ -5,7 +5,7 @@ cudaProfilerStart / Stop is profiled:
     ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/prof python profiles/ncu_workload.py
 
 Profiled launches, in order: step_obs_kernel<5x6> x2 (the headline), step_obs_kernel<5x6, compact> x2 (host pipe, zero
-copy), step_pool_kernel<5x6> x2 (state only), policy_step_kernel<5x6> x2 (configs[4], 2^21 boards), step_obs_kernel<6x7>
+copy), step_wpool_kernel<5x6> x2 (state only), policy_step_kernel<5x6> x2 (configs[4], 2^21 boards), step_obs_kernel<6x7>
 x2, reset_kernel<6x7> x1, reset_kernel<5x6> x1, rollout_kernel<5x6> x1 (51 fused steps), stats_reduce_kernel etc. as
 they come."""
 import os, sys
