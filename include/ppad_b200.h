@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PPAD_ABI_VERSION 3
+#define PPAD_ABI_VERSION 4
 #define PPAD_MAX_TEAM_UNITS 8
 
 typedef enum ppad_status {
@@ -80,8 +80,17 @@ typedef enum ppad_obs_dtype { PPAD_OBS_F32 = 0, PPAD_OBS_U8 = 1 } ppad_obs_dtype
  *   PPAD_SLAB_PLANES3  bit-sliced 3-bit codes, 32 orbs per group of three words {p0, p1, p2}: bit (d & 31) of word
  *                      3 * (d >> 5) + j is bit j of orb d; slab_words is a multiple of 3                  (12 B / 32 orbs);
  *                      contexts with orb_bits = 3 only (orb types 0..6).
+ *   PPAD_SLAB_CHUNKS10 chunk-major over the batch, ten 3-bit codes per uint32 chunk, bit-sliced inside the chunk: chunk c
+ *                      of board i is slab[c * slab_stride + i], and bit 10 j + k of it is bit j of orb 10 c + k (bits
+ *                      30, 31 unused).  slab_words = chunks per board, n_inj <= 10 * slab_words, slab_stride >= n
+ *                      words.  Made for slabs in pinned HOST memory (ppad_pipe_step in zero-copy mode): the kernel
+ *                      fetches the first slab_eager chunks of every board up front (one 128-byte line per warp and
+ *                      chunk) and a further chunk only when a board's cascade gets that far, so the host may offer 50
+ *                      orbs or more per board while 4 * slab_eager bytes per board cross PCIe (a random-policy step
+ *                      draws 3.5 orbs per board on average; one board in a hundred draws more than 20).
+ *                      ppad_step and ppad_pipe_step (zero copy) only; orb_bits = 3 only.
  * A code that is no orb type of the context (>= 7, or >= 10 with orb_bits = 4) is flagged PPAD_FLAG_UNSUPPORTED_ORB. */
-typedef enum ppad_slab_format { PPAD_SLAB_NIBBLES = 0, PPAD_SLAB_PLANES3 = 1 } ppad_slab_format;
+typedef enum ppad_slab_format { PPAD_SLAB_NIBBLES = 0, PPAD_SLAB_PLANES3 = 1, PPAD_SLAB_CHUNKS10 = 2 } ppad_slab_format;
 
 /* Environment constants: the keyword arguments of PAD.__init__ (game.py:39-50) that reach the hot path. */
 typedef struct ppad_config {
@@ -171,9 +180,11 @@ typedef struct ppad_step_args {
     const uint16_t *path_lens;
     int32_t path_words, path_len;
     int32_t slab_format;          /* ppad_slab_format of `slab` */
-    int32_t reserved;
+    int32_t slab_stride;          /* PPAD_SLAB_CHUNKS10: words between consecutive chunks of one board (>= n); else ignored */
     uint16_t *consumed_out;       /* [n] skyfall orbs the cascade drew, saturating at 65535 (the info byte stops at
                                      255), or NULL */
+    int32_t slab_eager;           /* PPAD_SLAB_CHUNKS10: chunks per board fetched up front, 1..4; 0 = default (2) */
+    int32_t reserved;
 } ppad_step_args;
 int ppad_step(const ppad_ctx *ctx, const ppad_step_args *args, void *stream);
 
@@ -248,6 +259,8 @@ typedef struct ppad_host_step_args {
                                         state it leaves behind); 1: the caller orders later work itself (ppad_pipe_join /
                                         ppad_pipe_wait) -- saves one cross-stream dependency per step when steps are
                                         enqueued back to back */
+    int32_t slab_stride;             /* PPAD_SLAB_CHUNKS10: words between consecutive chunks of one board (>= n) */
+    int32_t slab_eager;              /* PPAD_SLAB_CHUNKS10: chunks per board fetched up front, 1..4; 0 = default (2) */
     int32_t reserved2;
 } ppad_host_step_args;
 /* bytes of records_host that can never overflow for n boards (with or without auto_reset) */

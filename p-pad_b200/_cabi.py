@@ -15,8 +15,9 @@ FLAG_BAD_ACTION, FLAG_RESET_CAP, FLAG_UNSUPPORTED_ORB, FLAG_EPISODE_DONE = 0x10,
 I8, I32, I64 = 1, 4, 8
 OBS_F32, OBS_U8 = 0, 1
 SELECT_MAX, SELECT_BOLTZMANN = 0, 1
-SLAB_NIBBLES, SLAB_PLANES3 = 0, 1
-ABI_VERSION = 3
+SLAB_NIBBLES, SLAB_PLANES3, SLAB_CHUNKS10 = 0, 1, 2
+SLAB_FORMATS = {'nibbles': SLAB_NIBBLES, 'planes3': SLAB_PLANES3, 'chunks10': SLAB_CHUNKS10}
+ABI_VERSION = 4
 
 
 class Config(C.Structure):
@@ -38,7 +39,8 @@ class StepArgs(C.Structure):
                 ("log_cap", C.c_int32),
                 ("obs", C.c_void_p), ("obs_dtype", C.c_int32), ("skyfall_damage", C.c_int32),
                 ("paths", C.c_void_p), ("path_lens", C.c_void_p), ("path_words", C.c_int32), ("path_len", C.c_int32),
-                ("slab_format", C.c_int32), ("reserved", C.c_int32), ("consumed_out", C.c_void_p)]
+                ("slab_format", C.c_int32), ("slab_stride", C.c_int32), ("consumed_out", C.c_void_p),
+                ("slab_eager", C.c_int32), ("reserved", C.c_int32)]
 
 
 class HostStepArgs(C.Structure):
@@ -51,7 +53,7 @@ class HostStepArgs(C.Structure):
                 ("obs", C.c_void_p), ("obs_dtype", C.c_int32), ("slab_format", C.c_int32),
                 ("results_compact", C.c_int32), ("nibbles_host", C.c_void_p), ("tile_line_host", C.c_void_p),
                 ("records_host", C.c_void_p), ("records_capacity", C.c_int64), ("summary_host", C.c_void_p),
-                ("no_join", C.c_int32), ("reserved2", C.c_int32)]
+                ("no_join", C.c_int32), ("slab_stride", C.c_int32), ("slab_eager", C.c_int32), ("reserved2", C.c_int32)]
 
 
 class PolicyArgs(C.Structure):

@@ -86,15 +86,24 @@ class BatchedPAD:
 
     def _slab(self, injected, fmt='nibbles'):
         """injected: None, or a uint8 [n, S] orb sequence (tensor/array), or (slab_int32 [n, W], n_inj) already packed.
-        fmt: 'nibbles' (PPAD_SLAB_NIBBLES, 16 B per 32 orbs) or 'planes3' (PPAD_SLAB_PLANES3, 12 B per 32 orbs)."""
+        fmt: 'nibbles' (PPAD_SLAB_NIBBLES, 16 B per 32 orbs), 'planes3' (PPAD_SLAB_PLANES3, 12 B per 32 orbs) or
+        'chunks10' (PPAD_SLAB_CHUNKS10, chunk-major [W, n]: 4 B per 10 orbs, read on demand; step() only)."""
         if injected is None:
             return None, 0, 0
         if isinstance(injected, tuple):
             slab, n_inj = injected[0], injected[1]
             slab = self._dev(slab, torch.int32)
-            return slab, slab.shape[1], int(n_inj)
+            return slab, slab.shape[0 if fmt == 'chunks10' else 1], int(n_inj)
         orbs = self._dev(injected, torch.uint8)
         n, s = orbs.shape
+        if fmt == 'chunks10':
+            chunks = max(1, (s + 9) // 10)
+            pad = torch.zeros((n, chunks * 10), dtype=torch.int64, device=self.device)
+            pad[:, :s] = orbs & 7
+            pad = pad.view(n, chunks, 10)
+            k = torch.arange(10, device=self.device, dtype=torch.int64)
+            word = sum(((((pad >> j) & 1) << (k + 10 * j)).sum(dim=2)) for j in range(3))   # [n, chunks], < 2^30
+            return word.to(torch.int32).t().contiguous(), chunks, s
         if fmt == 'planes3':
             groups = max(1, (s + 31) // 32)
             pad = torch.zeros((n, groups * 32), dtype=torch.int64, device=self.device)
@@ -208,7 +217,8 @@ class BatchedPAD:
         acts = self._dev(actions, torch.uint8)
         slab, words, n_inj = self._slab(injected, slab_format)
         a = _cabi.StepArgs()
-        a.slab_format = {'nibbles': _cabi.SLAB_NIBBLES, 'planes3': _cabi.SLAB_PLANES3}[slab_format]
+        a.slab_format = _cabi.SLAB_FORMATS[slab_format]
+        a.slab_stride = slab.shape[1] if slab is not None and slab_format == 'chunks10' else 0
         a.consumed_out = out.consumed.data_ptr() if want_consumed else None
         a.n, a.env0, a.step = n, self.env0, step
         a.eval_moves, a.auto_reset, a.max_moves = int(bool(eval_moves)), int(bool(auto_reset)), int(max_moves)
@@ -427,7 +437,7 @@ class BatchedPAD:
         a.beta, a.epsilon = float(beta or 0.0), float(epsilon)
         a.slab = slab.data_ptr() if slab is not None else None
         a.slab_words, a.n_inj = words, n_inj
-        a.slab_format = {'nibbles': _cabi.SLAB_NIBBLES, 'planes3': _cabi.SLAB_PLANES3}[slab_format]
+        a.slab_format = {'nibbles': _cabi.SLAB_NIBBLES, 'planes3': _cabi.SLAB_PLANES3}[slab_format]   # no chunks10 here
         a.obs_dtype = obs_dtype
         a.action_out, a.reward, a.info = out.action.data_ptr(), out.reward.data_ptr(), out.info.data_ptr()
         a.obs = out.obs.data_ptr() if out.obs is not None else None
@@ -455,9 +465,10 @@ class BatchedPAD:
                                                int(bool(log10)), int(bool(norm)), self._stream()))
         return r
 
-    def host_pipe(self, slab_orbs=32, chunks=2, zero_copy=True, depth=1, compact=False, slab_format='nibbles'):
+    def host_pipe(self, slab_orbs=32, chunks=2, zero_copy=True, depth=1, compact=False, slab_format='nibbles',
+                  slab_eager=0):
         """A HostPipe for this slab: env steps whose inputs and results are pinned HOST tensors (ppad_pipe_*)."""
-        return HostPipe(self, slab_orbs, chunks, zero_copy, depth, compact, slab_format)
+        return HostPipe(self, slab_orbs, chunks, zero_copy, depth, compact, slab_format, slab_eager)
 
     @staticmethod
     def split_info(info):
@@ -485,18 +496,23 @@ class HostPipe:
     ``pipe.slab`` etc. are the buffers of set 0.
     """
 
-    def __init__(self, venv, slab_orbs=32, chunks=2, zero_copy=True, depth=1, compact=False, slab_format='nibbles'):
+    def __init__(self, venv, slab_orbs=32, chunks=2, zero_copy=True, depth=1, compact=False, slab_format='nibbles',
+                 slab_eager=0):
         self.venv = venv
+        self.slab_eager = int(slab_eager)   # chunks10: chunks per board the kernel fetches up front (0 = default, 2)
         self.slab_orbs = int(slab_orbs)
         self.slab_format = slab_format
-        self.slab_words = 3 * ((self.slab_orbs + 31) // 32) if slab_format == 'planes3' else (self.slab_orbs + 7) // 8
+        self.slab_words = {'planes3': 3 * ((self.slab_orbs + 31) // 32), 'chunks10': (self.slab_orbs + 9) // 10,
+                           'nibbles': (self.slab_orbs + 7) // 8}[slab_format]
         self.compact = bool(compact)
         n = venv.n
         self.tiles = (n + TILE - 1) // TILE
         pin = dict(pin_memory=True)
         cap = int(venv.lib.ppad_compact_capacity(venv._ctx, n)) if self.compact else 0
         self.buffers = [SimpleNamespace(
-            slab=torch.zeros((n, max(1, self.slab_words)), dtype=torch.int32, **pin),
+            # chunks10 is chunk-major ([W, n], layout.pack_slab_chunks10); the row formats are [n, W]
+            slab=torch.zeros((max(1, self.slab_words), n) if slab_format == 'chunks10' else (n, max(1, self.slab_words)),
+                             dtype=torch.int32, **pin),
             actions=torch.zeros(n, dtype=torch.uint8, **pin),
             action=torch.zeros(n, dtype=torch.uint8, **pin),
             reward=torch.zeros(n, dtype=torch.float64, **pin),
@@ -542,7 +558,9 @@ class HostPipe:
         a.actions_host = b.actions.data_ptr() if use_actions else None
         a.slab_host = b.slab.data_ptr() if use_slab and self.slab_words else None
         a.slab_words, a.n_inj = self.slab_words, self.slab_orbs
-        a.slab_format = {'nibbles': _cabi.SLAB_NIBBLES, 'planes3': _cabi.SLAB_PLANES3}[self.slab_format]
+        a.slab_format = _cabi.SLAB_FORMATS[self.slab_format]
+        a.slab_stride = b.slab.shape[1] if self.slab_format == 'chunks10' else 0
+        a.slab_eager = self.slab_eager
         if self.compact:
             a.results_compact = 1
             a.nibbles_host, a.tile_line_host = b.nibbles.data_ptr(), b.tile_line.data_ptr()
@@ -581,7 +599,23 @@ class HostPipe:
         return b.nibbles.numel() * 4 + b.tile_line.numel() * 4 + 16 + int(b.summary[0]) * 128 + state
 
     def h2d_bytes(self, use_actions=False):
-        return self.slab.numel() * 4 + (self.actions.numel() if use_actions else 0)
+        """Host-to-device bytes of one step.  Row slabs are read whole; of a chunks10 slab the kernel reads the eager
+        chunks of every board (the further chunks a cascade reaches are not counted here: see h2d_bytes_on_demand)."""
+        slab = self.slab.numel() * 4
+        if self.slab_format == 'chunks10':
+            slab = min(self.slab_eager or 2, self.slab_words) * self.slab.shape[1] * 4
+        return slab + (self.actions.numel() if use_actions else 0)
+
+    def h2d_bytes_on_demand(self, info, sector_boards=8):
+        """chunks10: bytes of the chunks beyond the eager ones that the cascades of a step reached, from the consumed
+        counts in its info words (saturating at 255 orbs), counted in 32-byte sectors of 8 neighbouring boards."""
+        if self.slab_format != 'chunks10':
+            return 0
+        import numpy as np
+        consumed = ((np.asarray(info).view(np.uint32) >> 16) & 0xFF).astype(np.int64)
+        consumed = np.pad(consumed, (0, (-len(consumed)) % sector_boards)).reshape(-1, sector_boards).max(axis=1)
+        eager = min(self.slab_eager or 2, self.slab_words)
+        return sum(int((consumed > 10 * c).sum()) * 4 * sector_boards for c in range(eager, self.slab_words))
 
     def wait(self, buf=0):
         with torch.cuda.device(self.venv.device):

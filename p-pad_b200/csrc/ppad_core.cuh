@@ -378,10 +378,18 @@ PPAD_HD int orb_from_u32(const SkyfallTable &t, uint32_t x)
 //   SLAB_NIBBLES  4-bit nibbles, 8 per uint32: orb d in word d >> 3 at bit 4 * (d & 7)
 //   SLAB_PLANES3  bit-sliced 3-bit codes, 32 orbs per group of three uint32 {p0, p1, p2}: bit (d & 31) of word
 //                 3 * (d >> 5) + j is bit j of orb d -- 12 bytes per 32 orbs (orb types 0..6 only)
+//   SLAB_CHUNKS10 chunks of ten 3-bit codes in one uint32, bit-sliced inside the chunk: bit 10 j + k of chunk c is bit j
+//                 of orb 10 c + k (bits 30, 31 unused); the chunks of one board lie `stride` words apart (chunk-major
+//                 over the batch: chunk c of board i at slab[c * stride + i]), so that a warp reads one chunk of its
+//                 32 boards as one line.  Made for a slab that stays in pinned HOST memory: the first n_eager chunks
+//                 are fetched up front by the kernel (`eager`, full lines, all in flight together), every further
+//                 chunk only when the cascade gets there -- the host can offer 50 orbs or more per board while 8 bytes
+//                 per board cross PCIe (orb types 0..6 only).  A read that waits on PCIe in the middle of a cascade
+//                 stalls its whole warp, so n_eager is chosen to make those rare (2: one board in a hundred).
 // Injected codes that are not orb types of the geometry (>= NT) are handed on as they are and flagged
 // (bad -> FLAG_UNSUPPORTED_ORB).
 // ---------------------------------------------------------------------------------------------
-enum : int { SLAB_NIBBLES = 0, SLAB_PLANES3 = 1 };
+enum : int { SLAB_NIBBLES = 0, SLAB_PLANES3 = 1, SLAB_CHUNKS10 = 2 };
 
 struct OrbSource {
     const uint32_t *slab;   // this board's words, or nullptr
@@ -393,11 +401,18 @@ struct OrbSource {
     U4 blk;                 // cached Philox block
     int blk_idx;
     bool exhausted;
-    int fmt;                // SLAB_NIBBLES / SLAB_PLANES3
+    int fmt;                // SLAB_NIBBLES / SLAB_PLANES3 / SLAB_CHUNKS10
     uint32_t bad;           // bit 0: an injected code was not an orb type of the geometry
+    const uint32_t *eager;  // SLAB_CHUNKS10: the first n_eager chunks of this board (fetched up front by the caller)
+    int n_eager;
+    int stride;             // SLAB_CHUNKS10: words between consecutive chunks of this board
 
-    PPAD_HD void init(const uint32_t *slab_, int n_inj_, uint32_t stream_, int fmt_ = SLAB_NIBBLES)
+    PPAD_HD void init(const uint32_t *slab_, int n_inj_, uint32_t stream_, int fmt_ = SLAB_NIBBLES,
+                      const uint32_t *eager_ = nullptr, int n_eager_ = 0, int stride_ = 0)
     {
+        eager = eager_;
+        n_eager = eager_ ? n_eager_ : 0;
+        stride = stride_;
         slab = slab_;
         n_inj = slab_ ? n_inj_ : -1;
         cursor = 0;
@@ -411,6 +426,8 @@ struct OrbSource {
         blk.x = blk.y = blk.z = blk.w = 0;
     }
 
+    PPAD_HD uint32_t chunk(int c) const { return c < n_eager ? eager[c] : slab[(size_t)c * (size_t)stride]; }
+
     template <int NT = 7>
     PPAD_HD int next(const RngKey &key, const SkyfallTable &sky)
     {
@@ -422,6 +439,10 @@ struct OrbSource {
                 const uint32_t *g = slab + 3 * (d >> 5);
                 const int k = d & 31;
                 code = (int)(((g[0] >> k) & 1u) | (((g[1] >> k) & 1u) << 1) | (((g[2] >> k) & 1u) << 2));
+            } else if (fmt == SLAB_CHUNKS10) {
+                const int c = d / 10, k = d - 10 * c;
+                const uint32_t w = chunk(c);
+                code = (int)(((w >> k) & 1u) | (((w >> (10 + k)) & 1u) << 1) | (((w >> (20 + k)) & 1u) << 2));
             } else {
                 const int wi = d >> 3;
                 if (wi != word_idx) {
@@ -740,6 +761,25 @@ PPAD_HD void fill_board(Board<G> &b, OrbSource &src, const RngKey &key, const Sk
                     s2 = g[2];
                 }
             } while (e);
+        } else if (src.fmt == SLAB_CHUNKS10) {
+            int c = d / 10, left = 10 * (c + 1) - d;   // orbs left in the chunk at hand
+            uint32_t w = src.chunk(c) >> (10 - left);
+            do {
+                const W bit = e & (~e + 1);
+                e ^= bit;
+                b.b0 ^= bit & ((W)(w & 1u) - 1);
+                b.b1 ^= bit & ((W)((w >> 10) & 1u) - 1);
+                b.b2 ^= bit & ((W)((w >> 20) & 1u) - 1);
+                PPAD_P4(b.b3 ^= bit)
+                badacc |= w & (w >> 10) & (w >> 20);
+                d++;
+                w >>= 1;
+                if (--left == 0 && e) {
+                    c++;
+                    left = 10;
+                    w = src.chunk(c);
+                }
+            } while (e);
         } else {
             uint32_t word = src.slab[d >> 3] >> (4 * (d & 7));
             do {
@@ -899,7 +939,8 @@ struct CascadeItem {
 // Returns true when the refilled board matches again, with its masks in m / er / ed for the next iteration.
 template <class G>
 PPAD_HD bool cascade_round_m(CascadeItem<G> &it, typename G::W &m, bool skyfall_damage, int cascade_cap, const TeamTable &team, const uint32_t *slab, int n_inj,
-                             const RngKey &key, const SkyfallTable &sky, uint16_t *log, int log_cap, int slab_fmt = SLAB_NIBBLES)
+                             const RngKey &key, const SkyfallTable &sky, uint16_t *log, int log_cap, int slab_fmt = SLAB_NIBBLES,
+                             const uint32_t *slab_eager = nullptr, int slab_n_eager = 0, int slab_stride = 0)
 {
     cancel_tally<G>(it.b, m, it.tally, team, log, log_cap);
     it.depth++;
@@ -910,7 +951,7 @@ PPAD_HD bool cascade_round_m(CascadeItem<G> &it, typename G::W &m, bool skyfall_
     }
     drop_board<G>(it.b);
     OrbSource src;
-    src.init(slab, n_inj, STREAM_SKYFALL, slab_fmt);
+    src.init(slab, n_inj, STREAM_SKYFALL, slab_fmt, slab_eager, slab_n_eager, slab_stride);
     src.cursor = it.cursor;
     src.exhausted = it.exhausted;
     fill_board<G>(it.b, src, key, sky);
@@ -1047,7 +1088,9 @@ struct StepParams {
     int32_t eval_moves, auto_reset, max_moves;
     int32_t n_inj, slab_words, log_cap;
     int32_t draw0;   // first draw index of a stand-alone fill (ppad_fill)
-    int32_t slab_fmt;   // SLAB_NIBBLES / SLAB_PLANES3: layout of the injected skyfall slab of this launch
+    int32_t slab_fmt;   // SLAB_NIBBLES / SLAB_PLANES3 / SLAB_CHUNKS10: layout of the injected skyfall slab of this launch
+    int32_t slab_stride;   // SLAB_CHUNKS10: words between consecutive chunks of one board
+    int32_t slab_eager;    // SLAB_CHUNKS10: chunks per board the kernel fetches up front (1..4)
     DynGeomData dyn;    // board dimensions for GeomDyn (ignored by the specialised geometries)
 };
 
@@ -1231,7 +1274,8 @@ __device__ __forceinline__ uint32_t reset_boards_warp(bool need, State<G> &s, co
 template <class G, bool TIGHT_RESET = false, bool HAS_RESET = true, int RESET_UNROLL = 2>
 PPAD_HD StepOut step_board(bool live, State<G> &s, Board<G> &final_board, const StepParams &p, uint64_t env,
                            int action_in, const uint32_t *slab, uint16_t *log, const uint32_t *path = nullptr,
-                           int path_len = 0, uint32_t step_offset = 0, const U4 *act_blk = nullptr)
+                           int path_len = 0, uint32_t step_offset = 0, const U4 *act_blk = nullptr,
+                           const uint32_t *slab_eager = nullptr)
 {
     RngKey key = board_key(p, env);
     key.step += step_offset;   // fused multi-step rollouts: step index = p.key.step + t
@@ -1262,7 +1306,7 @@ PPAD_HD StepOut step_board(bool live, State<G> &s, Board<G> &final_board, const 
     while (warp_any(cascading)) {
         if (cascading)
             cascading = cascade_round_m<G>(it, m, p.skyfall_damage != 0, p.cascade_cap, p.team, slab, p.n_inj,
-                                           key, p.sky, log, p.log_cap, p.slab_fmt);
+                                           key, p.sky, log, p.log_cap, p.slab_fmt, slab_eager, p.slab_eager, p.slab_stride);
         warp_converge();
     }
 #if defined(__CUDA_ARCH__)

@@ -1,6 +1,7 @@
 // ppad_step.cu -- C ABI of the env step: ppad_step, ppad_rollout(_record) and the host-buffer pipe ppad_pipe_*.
 // The kernels live in ppad_step.cuh and are instantiated per geometry in ppad_step_inst.cu.
 #include "ppad_step.cuh"
+#include <cstdlib>
 
 namespace ppad {
 
@@ -52,9 +53,15 @@ static int launch_step(const ppad_ctx *ctx, const ppad_step_args *args, cudaStre
                        bool stage_host_slab = false, const CompactTarget *compact = nullptr)
 {
     if (!args->state) return fail(PPAD_ERR_INVALID, "ppad_step: null state");
-    if (args->slab_format != PPAD_SLAB_NIBBLES && args->slab_format != PPAD_SLAB_PLANES3)
+    if (args->slab_format != PPAD_SLAB_NIBBLES && args->slab_format != PPAD_SLAB_PLANES3 && args->slab_format != PPAD_SLAB_CHUNKS10)
         return fail(PPAD_ERR_INVALID, "ppad_step: unknown slab_format");
-    if (args->slab && args->slab_format == PPAD_SLAB_PLANES3) {
+    if (args->slab && args->slab_format == PPAD_SLAB_CHUNKS10) {
+        if (ctx->geom >= 3) return fail(PPAD_ERR_UNSUPPORTED, "ppad_step: PPAD_SLAB_CHUNKS10 needs a context with orb_bits = 3");
+        if (args->slab_words <= 0 || args->slab_words > 6000 || args->n_inj < 0 || args->n_inj > args->slab_words * 10 ||
+            (int64_t)args->slab_stride < args->n)
+            return fail(PPAD_ERR_INVALID, "ppad_step: PPAD_SLAB_CHUNKS10 needs 0 <= n_inj <= 10 * slab_words and slab_stride >= n");
+        if (args->paths || args->combo_log) return fail(PPAD_ERR_UNSUPPORTED, "ppad_step: PPAD_SLAB_CHUNKS10 with finger paths / combo log");
+    } else if (args->slab && args->slab_format == PPAD_SLAB_PLANES3) {
         if (ctx->geom >= 3) return fail(PPAD_ERR_UNSUPPORTED, "ppad_step: PPAD_SLAB_PLANES3 needs a context with orb_bits = 3");
         if (args->slab_words <= 0 || args->slab_words % 3 || args->n_inj < 0 || args->n_inj > args->slab_words / 3 * 32)
             return fail(PPAD_ERR_INVALID, "ppad_step: PPAD_SLAB_PLANES3 needs slab_words = 3 * groups and 0 <= n_inj <= 32 * groups");
@@ -76,6 +83,13 @@ static int launch_step(const ppad_ctx *ctx, const ppad_step_args *args, cudaStre
     a.p.slab_words = args->slab_words;
     a.p.log_cap = args->log_cap;
     a.p.slab_fmt = args->slab_format;
+    a.p.slab_stride = args->slab_format == PPAD_SLAB_CHUNKS10 ? args->slab_stride : 0;
+    a.p.slab_eager = 0;
+    if (args->slab && args->slab_format == PPAD_SLAB_CHUNKS10) {
+        if (args->slab_eager < 0 || args->slab_eager > 4) return fail(PPAD_ERR_INVALID, "ppad_step: slab_eager must be 0 (default) or 1..4");
+        a.p.slab_eager = args->slab_eager ? args->slab_eager : 2;
+        if (a.p.slab_eager > args->slab_words) a.p.slab_eager = args->slab_words;
+    }
     if (args->skyfall_damage >= 0) a.p.skyfall_damage = args->skyfall_damage;
     a.n = args->n;
     a.env0 = args->env0;
@@ -102,6 +116,7 @@ static int launch_step(const ppad_ctx *ctx, const ppad_step_args *args, cudaStre
         if (a.p.slab_fmt == PPAD_SLAB_NIBBLES && a.p.slab_words == 4) a.stage_slab = 1;
         if (a.p.slab_fmt == PPAD_SLAB_PLANES3 && a.p.slab_words == 3) a.stage_slab = 2;
     }
+    if (a.slab && a.p.slab_fmt == PPAD_SLAB_CHUNKS10) a.stage_slab = 3;   // the first chunks up front, the rest on demand
     a.c_nibbles = a.c_tile_line = a.c_summary = a.c_counters = nullptr;
     a.c_records = nullptr;
     a.c_capacity = 0;
@@ -118,7 +133,7 @@ static int launch_step(const ppad_ctx *ctx, const ppad_step_args *args, cudaStre
     a.tile_counter = nullptr;
     int choice = ctx->pool_kind == 1 ? STEP_KERNEL_WPOOL : STEP_KERNEL_POOL;
     if (args->obs) choice = STEP_KERNEL_OBS;
-    else if (compact || coalesced_results || (!a.p.eval_moves && !a.actions && !a.paths) || !a.p.skyfall_damage) {
+    else if (compact || coalesced_results || a.stage_slab == 3 || (!a.p.eval_moves && !a.actions && !a.paths) || !a.p.skyfall_damage) {
         // results go straight to host memory: the pooled kernel's scattered 8-byte result writes would become tiny
         // PCIe transactions, one thread per board writes them as full lines.
         // Steps of the in-kernel random policy that only evaluate passes (eval_moves = 0, no actions given: plain
@@ -204,6 +219,10 @@ struct ppad_pipe {
 static bool host_is_pinned(const void *ptr)
 {
     if (!ptr) return true;
+    // profiling aid (profiles/e2e_placement_probe.py): lets a probe put single buffers in device memory to see which of
+    // the PCIe streams of a zero-copy step costs what; never set in production
+    static const bool any_memory = std::getenv("PPAD_PIPE_ANY_MEMORY") != nullptr;
+    if (any_memory) return true;
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) {
         cudaGetLastError();
@@ -315,6 +334,8 @@ int ppad_pipe_step(ppad_pipe *p, const ppad_host_step_args *h, void *after_strea
     // by the kernels -- no PCIe read sits inside a kernel, which matters on hosts whose read latency is high
     const bool hybrid = zc && p->zero_copy == 2;
     const int mode = zc && !hybrid ? 1 : 2;
+    if (h->slab_host && h->slab_format == PPAD_SLAB_CHUNKS10 && mode != 1)
+        return fail(PPAD_ERR_UNSUPPORTED, "ppad_pipe_step: PPAD_SLAB_CHUNKS10 needs pinned host buffers and zero-copy mode 1");
     if (p->last_mode && p->last_mode != mode)   // stream <-> board mapping changes: order behind the previous step
         for (int k = 0; k < p->chunks && e == cudaSuccess; k++)
             for (int j = 0; j < p->chunks && e == cudaSuccess; j++)
@@ -343,6 +364,8 @@ int ppad_pipe_step(ppad_pipe *p, const ppad_host_step_args *h, void *after_strea
         a.slab_words = h->slab_words;
         a.n_inj = h->n_inj;
         a.slab_format = h->slab_format;
+        a.slab_stride = h->slab_stride;
+        a.slab_eager = h->slab_eager;
         a.state_copy = h->state_out_host;
         a.obs = h->obs;
         a.obs_dtype = h->obs_dtype;

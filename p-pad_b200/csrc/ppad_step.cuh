@@ -30,7 +30,9 @@ struct StepKernelArgs {
     const uint16_t *path_lens;
     int32_t path_words, path_len;
     int32_t stage_slab;   // the slab is pinned HOST memory (zero copy): fetch each row once, up front.  1: 4 words per
-                          // board, one uint4 per thread; 2: 3 words per board, the CTA's 3072 contiguous bytes cooperatively
+                          // board, one uint4 per thread; 2: 3 words per board, the CTA's 3072 contiguous bytes cooperatively;
+                          // 3: SLAB_CHUNKS10 (host or device memory): the first p.slab_eager chunks up front, further
+                          // chunks when the cascade asks
     uint32_t *tile_counter;   // DEVICE [2]: {next tile, CTAs finished} of the warp-pool kernel; both 0 before the launch and
                               // left at 0 by the last CTA to finish (no memset between launches)
     // compact result stream (COMPACT instantiations: the host pipe), see include/ppad_b200.h ppad_host_step_args
@@ -177,8 +179,21 @@ __global__ void __launch_bounds__(BLOCK, step_min_ctas<G, AR>()) step_obs_kernel
         }
     }
     const uint32_t *slab = a.slab && valid ? a.slab + (size_t)i * a.p.slab_words : nullptr;
+    const uint32_t *slab_eager = nullptr;
     __shared__ uint4 slab_rows[BLOCK];
-    if (a.stage_slab == 1) {   // kernel-uniform
+    if (a.stage_slab == 3) {   // kernel-uniform
+        // chunk-major slab: a chunk of the warp's 32 boards is one 128-byte line; the eager chunks are in flight together
+        // with the state load and wait in the thread's own 16 bytes of shared memory
+        slab = a.slab && valid ? a.slab + i : nullptr;
+        if (slab) {
+            uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                if (c < a.p.slab_eager) w[c] = __ldg(slab + (size_t)c * (size_t)a.p.slab_stride);
+            slab_rows[threadIdx.x] = make_uint4(w[0], w[1], w[2], w[3]);
+            slab_eager = reinterpret_cast<const uint32_t *>(&slab_rows[threadIdx.x]);
+        }
+    } else if (a.stage_slab == 1) {
         // Zero copy: the skyfall slab lives in pinned host memory.  The cascade reads its words lazily, which over
         // PCIe is one 4-byte round trip per lane and cascade iteration; fetch the board's whole 16-byte row once
         // instead (512 contiguous bytes per warp, in flight together with the state load) and let the cascade read
@@ -206,7 +221,7 @@ __global__ void __launch_bounds__(BLOCK, step_min_ctas<G, AR>()) step_obs_kernel
     Board<G> fin;
     const StepOut o = step_board<G, AR, AR>(valid, s, fin, a.p, a.env0 + (uint64_t)i, action, slab,
                                     a.combo_log && valid ? a.combo_log + (size_t)i * a.p.log_cap : nullptr,
-                                    a.paths && valid ? a.paths + (size_t)i * a.path_words : nullptr, path_len);
+                                    a.paths && valid ? a.paths + (size_t)i * a.path_words : nullptr, path_len, 0, nullptr, slab_eager);
     if (valid) {
         StateIO<G>::store(a.state, i, s.b, s.meta);
         if constexpr (!COMPACT) {

@@ -102,6 +102,24 @@ def pack_slab_planes3(orbs):
     return np.ascontiguousarray(out.reshape(n, groups * 3))
 
 
+def pack_slab_chunks10(orbs, stride=None):
+    """uint8 [n, S] orb sequence (types 0..6) -> uint32 [ceil(S / 10), stride] chunk-major slab (PPAD_SLAB_CHUNKS10):
+    bit 10 j + k of out[c, i] is bit j of orb 10 c + k of board i.  4 bytes per 10 orbs; a kernel reading it from pinned
+    host memory only fetches the chunks a board's cascade reaches."""
+    orbs = np.asarray(orbs, np.uint8)
+    n, s = orbs.shape
+    chunks = max(1, (s + 9) // 10)
+    stride = n if stride is None else int(stride)
+    pad = np.zeros((n, chunks * 10), np.uint32)
+    pad[:, :s] = orbs & 7
+    pad = pad.reshape(n, chunks, 10)
+    k = np.arange(10, dtype=np.uint32)
+    out = np.zeros((chunks, stride), np.uint32)
+    for j in range(3):
+        out[:, :n] |= (((pad >> np.uint32(j)) & np.uint32(1)) << (k + np.uint32(10 * j))).sum(axis=2, dtype=np.uint32).T
+    return out
+
+
 TILE = 256   # boards per tile of the compact result stream (= CTA size of the step kernel)
 
 

@@ -54,10 +54,17 @@ void step_batch(const StepParams &base, int64_t n, uint64_t env0, int8_t *boards
         int action = actions ? actions[i] : -1;
         if (action == 255) action = -1;
         Board<G> fin;
-        const StepOut o = step_board<G>(true, s, fin, base, env0 + (uint64_t)i, action,
-                                        slab ? slab + (size_t)i * base.slab_words : nullptr,
+        // SLAB_CHUNKS10 is chunk-major: board i starts at slab + i, its chunks lie slab_stride words apart, and the
+        // first slab_eager chunks are handed over as a copy (what the step kernel does with the lines it fetches up front)
+        const bool chunked = base.slab_fmt == SLAB_CHUNKS10;
+        const uint32_t *row = slab ? slab + (chunked ? (size_t)i : (size_t)i * base.slab_words) : nullptr;
+        uint32_t eager[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+        if (chunked && row)
+            for (int c = 0; c < base.slab_eager; c++) eager[c] = row[(size_t)c * (size_t)base.slab_stride];
+        const StepOut o = step_board<G>(true, s, fin, base, env0 + (uint64_t)i, action, row,
                                         combo_log ? combo_log + (size_t)i * base.log_cap : nullptr,
-                                        paths ? paths + (size_t)i * path_words : nullptr, paths ? path_lens[i] : 0);
+                                        paths ? paths + (size_t)i * path_words : nullptr, paths ? path_lens[i] : 0, 0,
+                                        nullptr, chunked && row ? eager : nullptr);
         unpack_cells<G, int8_t>(s.b, boards + i * G::cells());
         const int f = meta_finger(s.meta);
         fingers[2 * i] = f / G::cols();
@@ -165,6 +172,8 @@ int hostcore_step_batch(const ppad_config *cfg, int64_t n, uint64_t env0, uint32
     p.max_moves = max_moves;
     p.n_inj = slab ? n_inj : -1;
     p.slab_words = slab_words;
+    p.slab_stride = slab_format == SLAB_CHUNKS10 ? (int32_t)n : 0;
+    p.slab_eager = slab_format == SLAB_CHUNKS10 ? (slab_words < 2 ? slab_words : 2) : 0;
     p.log_cap = log_cap;
     dyn_geom() = p.dyn;
     HC_DISPATCH(geom, (step_batch<G>(p, n, env0, boards, fingers, prev, moves, actions, slab, action_out, reward, info,

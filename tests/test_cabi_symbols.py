@@ -52,11 +52,11 @@ def test_constants_agree(cabi):
         assert henum("PPAD_FLAG_" + flag) == getattr(cabi, "FLAG_" + flag) == getattr(orc, "FLAG_" + flag)
     assert [henum("PPAD_" + a) for a in ("UP", "DOWN", "LEFT", "RIGHT", "PASS")] == [0, 1, 2, 3, 4]
     assert C.sizeof(cabi.Config) == 6 * 4 + 2 * 8 * 4 + 8 * 8 + 10 * 8 + 8 + 2 * 4   # ... seed, orb_bits, reserved
-    assert cabi.lib().ppad_abi_version() == int(re.search(r"#define PPAD_ABI_VERSION\s+(\d+)", HEADER).group(1)) == cabi.ABI_VERSION == 3
+    assert cabi.lib().ppad_abi_version() == int(re.search(r"#define PPAD_ABI_VERSION\s+(\d+)", HEADER).group(1)) == cabi.ABI_VERSION == 4
     for name in ("SLAB_NIBBLES", "SLAB_PLANES3"):
         assert henum("PPAD_" + name) == getattr(cabi, name)
     # struct sizes the ctypes mirrors must agree on (a mismatch would shift every later field)
-    assert C.sizeof(cabi.StepArgs) == 8 + 8 + 4 * 4 + 3 * 8 + 2 * 4 + 6 * 8 + 4 + 4 + 8 + 2 * 4 + 2 * 8 + 2 * 4 + 2 * 4 + 8
+    assert C.sizeof(cabi.StepArgs) == 8 + 8 + 4 * 4 + 3 * 8 + 2 * 4 + 6 * 8 + 4 + 4 + 8 + 2 * 4 + 2 * 8 + 2 * 4 + 2 * 4 + 8 + 2 * 4
     assert C.sizeof(cabi.HostStepArgs) % 8 == 0
     assert cabi.lib().ppad_state_bytes(5, 6) == 16 and cabi.lib().ppad_state_bytes(6, 7) == 32
     assert cabi.lib().ppad_state_bytes(9, 9) == -1 and cabi.lib().ppad_state_bytes(4, 5) == 16

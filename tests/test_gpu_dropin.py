@@ -595,7 +595,7 @@ def test_host_pipe_equals_device_step(pb, rows, cols, n, zero_copy):
     assert torch.equal(env.state, ref.state)
 
 
-@pytest.mark.parametrize("slab_format", ["planes3", "nibbles"])
+@pytest.mark.parametrize("slab_format", ["planes3", "nibbles", "chunks10"])
 @pytest.mark.parametrize("rows,cols,n", [(5, 6, 100_000 + 37), (6, 7, 33_333), (5, 6, 200), (4, 5, 256), (5, 6, 1)])
 def test_host_pipe_compact_results_equal_device_step(pb, rows, cols, n, slab_format):
     """The compact result stream of ppad_pipe_step (action nibbles + records only for boards whose info word is not 0 +
@@ -606,15 +606,18 @@ def test_host_pipe_compact_results_equal_device_step(pb, rows, cols, n, slab_for
     ref.reset(step=0)
     env = pb.BatchedPAD(n, rows, cols, seed=23, env0=5)
     env.state.copy_(ref.state)
-    pipe = env.host_pipe(slab_orbs=32, compact=True, slab_format=slab_format)
-    assert pipe.slab.shape[1] == (3 if slab_format == "planes3" else 4)
-    pack = pb.layout.pack_slab_planes3 if slab_format == "planes3" else pb.layout.pack_slab
+    # chunks10: the chunk-major slab the kernel reads on demand from pinned host memory (50 orbs offered per board)
+    S = 50 if slab_format == "chunks10" else 32
+    pipe = env.host_pipe(slab_orbs=S, compact=True, slab_format=slab_format)
+    assert tuple(pipe.slab.shape) == {"planes3": (n, 3), "nibbles": (n, 4), "chunks10": (5, n)}[slab_format]
+    pack = {"planes3": pb.layout.pack_slab_planes3, "nibbles": pb.layout.pack_slab,
+            "chunks10": pb.layout.pack_slab_chunks10}[slab_format]
     obs = torch.zeros((n, rows, cols, 7), dtype=torch.float32, device=env.device)
     mirror = pb.layout.unpack_state(ref.state.cpu().numpy().view(np.uint32), rows, cols)   # host copy of boards, fingers
     hb, hf = mirror[0].copy(), mirror[1].copy()
     total_records = 0
     for t in range(1, 8):
-        inj = rng.integers(0, 6, size=(n, 32)).astype(np.uint8)
+        inj = rng.integers(0, 6, size=(n, S)).astype(np.uint8)
         acts = rng.integers(0, 5, size=n).astype(np.uint8)
         if t == 5:
             acts[: n // 2] = 4                      # many passes: many resets, many state records
@@ -662,22 +665,22 @@ def test_host_pipe_compact_results_equal_device_step(pb, rows, cols, n, slab_for
         assert pipe.d2h_bytes() == pipe.tiles * 128 + pipe.tiles * 4 + 16 + got["lines"] * 128
     assert total_records > 0
     # two steps in flight with two buffer sets
-    pipe2 = env.host_pipe(slab_orbs=32, compact=True, slab_format=slab_format, depth=2)
+    pipe2 = env.host_pipe(slab_orbs=S, compact=True, slab_format=slab_format, depth=2)
     for b in pipe2.buffers:
         b.slab.copy_(pipe.slab)
     pipe2.step(eval_moves=True, step=20, wait=False, buf=0)
     pipe2.step(eval_moves=True, step=21, wait=False, buf=1)
     pipe2.wait(0), pipe2.wait(1)
-    w20 = ref.step(None, eval_moves=True, injected=(pipe.slab.to(ref.device), 32), step=20, slab_format=slab_format)
+    w20 = ref.step(None, eval_moves=True, injected=(pipe.slab.to(ref.device), S), step=20, slab_format=slab_format)
     r20 = w20.reward.cpu().numpy().copy()
-    w21 = ref.step(None, eval_moves=True, injected=(pipe.slab.to(ref.device), 32), step=21, slab_format=slab_format)
+    w21 = ref.step(None, eval_moves=True, injected=(pipe.slab.to(ref.device), S), step=21, slab_format=slab_format)
     assert np.array_equal(bits(pipe2.results(0)["reward"]), bits(r20))
     assert np.array_equal(bits(pipe2.results(1)["reward"]), bits(w21.reward.cpu().numpy()))
     assert torch.equal(env.state, ref.state)
     # work queued on torch's stream after a pipe step is ordered behind it (no join() needed)
     pipe2.step(eval_moves=True, step=22, wait=False, buf=0)
     after = env.encode_obs('u8')
-    ref.step(None, eval_moves=True, injected=(pipe.slab.to(ref.device), 32), step=22, slab_format=slab_format)
+    ref.step(None, eval_moves=True, injected=(pipe.slab.to(ref.device), S), step=22, slab_format=slab_format)
     assert torch.equal(after, ref.encode_obs('u8'))
     pipe2.wait(0)
 
