@@ -20,8 +20,9 @@ slabs rotate over 16 buffers (201 MB), so no step finds its inputs in L2.
 
 Sub-records of the same JSON line (all measured in this run, on every rank, max over ranks):
   state_only    the same step without the observation stream (persistent pool kernel), L2 flushed
-  e2e           the same step through HostPipe.step (ppad_pipe_step): pinned HOST buffers, the skyfall slab crosses
-                PCIe host -> device and the compact result stream device -> host inside the timed region
+  e2e           the same step through HostPipe.step (ppad_pipe_step): pinned HOST buffers, the skyfall slab (50 orbs
+                offered per board, chunk-major; two chunks = 8 B fetched per board, more on demand) crosses PCIe host ->
+                device and the compact, dictionary-coded result stream device -> host inside the timed region
   rollout       BASELINE configs[4]: 2^23 boards per GPU, Boltzmann policy on synthetic Q-values, auto-reset, fp32 obs,
                 replay ring with discounted returns, statistics; NCCL all-gathers of stats + replay samples INSIDE the
                 timed region
@@ -49,6 +50,12 @@ ROWS, COLS = 5, 6
 SLAB_ORBS = 32
 SLAB_FORMAT = 'planes3'          # PPAD_SLAB_PLANES3: 3 bits per orb, 12 bytes per 32 orbs
 SLAB_BYTES = 12
+# the e2e leg (host buffers): the host OFFERS 50 orbs per board-step as a chunk-major slab (PPAD_SLAB_CHUNKS10, 20 B per
+# board in pinned memory); the kernel fetches the first two chunks of every board (8 B) and a later chunk only for the
+# boards whose cascade draws more than 20 orbs (about 4 in 1000)
+E2E_SLAB_ORBS = 50
+E2E_SLAB_FORMAT = 'chunks10'
+E2E_DICT_ENTRIES = 4096
 N_SLABS = 16
 SEED = 20181019
 # algorithmic bytes per board-step (restated in DESIGN.md):
@@ -531,30 +538,60 @@ def main():
     # of that step is read from pinned host memory (12 B per board) and the compact result stream (4 bits per board: action
     # + has-record; 12 B per board whose info word is not 0: reward + info) is written to pinned host memory; the call
     # returns only when the results are on the host.  The fp32 one-hot obs stays in HBM for the device-side agent.
-    pipe = env.host_pipe(slab_orbs=SLAB_ORBS, compact=True, slab_format=SLAB_FORMAT)
-    pipe.slab.copy_(slabs[0].cpu())
+    e2e_slabs = [env._slab(torch.randint(0, 6, (n, E2E_SLAB_ORBS), device=dev, dtype=torch.uint8, generator=gen),
+                           E2E_SLAB_FORMAT)[0].cpu() for _ in range(2)]
+    pipe = env.host_pipe(slab_orbs=E2E_SLAB_ORBS, compact=True, slab_format=E2E_SLAB_FORMAT)
+    pipe.slab.copy_(e2e_slabs[0])
     torch.cuda.synchronize()
+    # the result dictionary of the compact stream: the (reward, info) pairs one earlier step reported most often (a
+    # frequency count on the host over values the device computed); records in it travel as 16-bit codes, the others
+    # in full -- the decoded results are exact either way (tests/test_gpu_dropin.py)
+    pipe.step(eval_moves=True, obs=obs_buf, step=base_t - 1, wait=True)
+    dict_entries, dict_cover = pipe.learn_dictionary(max_entries=E2E_DICT_ENTRIES)
+    e2e_dict = pipe._dict
 
     def e2e_step(t):
         pipe.step(eval_moves=True, obs=obs_buf, step=t, wait=True)
 
     # warm-up by time, not by count: the first ~50-100 ms of host traffic run slower on every box and mode (PCIe link /
     # host uncore leaving their idle states; profiles/e2e_modes.py)
-    t_warm, w = time.time(), 0
-    while w < 20 or time.time() - t_warm < 0.3:
-        e2e_step(base_t + w)
-        w += 1
+    def warm_by_time(fn, t0, seconds=0.3, at_least=20):
+        """every pipe has its own pinned buffers, and every fresh set of them starts slow"""
+        t_warm, done = time.time(), 0
+        while done < at_least or time.time() - t_warm < seconds:
+            fn(t0 + done)
+            done += 1
+        return done
+
+    w = warm_by_time(e2e_step, base_t)
     e2e_k = max(5, min(K, 200))
     e2e_ms = T.timed(e2e_step, base_t + w, e2e_k)
-    h2d = pipe.h2d_bytes()
-    d2h = pipe.d2h_bytes()
     got = pipe.results()                                  # decode once: the stream is complete and self-consistent
     assert got["lines"] > 0 and (got["info"] != 0).sum() > 0
+    h2d_eager = pipe.h2d_bytes()
+    h2d_lazy = pipe.h2d_bytes_on_demand(got["info"])
+    h2d = h2d_eager + h2d_lazy
+    d2h = pipe.d2h_bytes()
+    e2e_records = int((got["info"] != 0).sum())
+    e2e_escapes = int(got["escapes"])
+    # the decoded stream of the last timed step against the plain device step on a copy of the state before it
+    if rank == 0:
+        chk = ppad_b200.BatchedPAD(n, ROWS, COLS, seed=SEED, device=dev, env0=pdist.shard_env0(rank, n))
+        chk.state.copy_(env.state)
+        pipe.step(eval_moves=True, obs=obs_buf, step=base_t + w + e2e_k, wait=True)
+        got2 = pipe.results()
+        ref = chk.step(None, eval_moves=True, injected=(pipe.slab.to(dev), E2E_SLAB_ORBS), slab_format=E2E_SLAB_FORMAT,
+                       step=base_t + w + e2e_k)
+        assert np.array_equal(got2["reward"].view(np.uint64), ref.reward.cpu().numpy().view(np.uint64))
+        assert np.array_equal(got2["info"], ref.info.cpu().numpy().view(np.uint32))
+        assert np.array_equal(got2["action"], ref.action.cpu().numpy()) and torch.equal(env.state, chk.state)
+        del chk, ref
     # the same with two steps in flight (two sets of host buffers on one pipe; the results of step t are read while
     # step t + 1 is running) -- reported separately, the headline e2e above is the synchronous call
-    pipe2 = env.host_pipe(slab_orbs=SLAB_ORBS, compact=True, slab_format=SLAB_FORMAT, depth=2)
+    pipe2 = env.host_pipe(slab_orbs=E2E_SLAB_ORBS, compact=True, slab_format=E2E_SLAB_FORMAT, depth=2)
     for k, b in enumerate(pipe2.buffers):
-        b.slab.copy_(slabs[k].cpu())
+        b.slab.copy_(e2e_slabs[k])
+    pipe2.set_dictionary(*e2e_dict)
 
     def e2e_async_step(t):
         k = t & 1
@@ -562,19 +599,24 @@ def main():
         _ = int(pipe2.buffers[k].summary[0])       # "read" them
         pipe2.step(eval_moves=True, obs=obs_buf, step=t, wait=False, buf=k, join=False)
 
-    for t in range(base_t + 50000, base_t + 50010):
-        e2e_async_step(t)
-    e2e_async_ms = T.timed(e2e_async_step, base_t + 50010, e2e_k, finish=lambda: (pipe2.join(0), pipe2.join(1)))
+    wa = warm_by_time(e2e_async_step, base_t + 50000)
+    wa += wa & 1                                   # keep the buffer parity
+    e2e_async_ms = T.timed(e2e_async_step, base_t + 50000 + wa, e2e_k, finish=lambda: (pipe2.join(0), pipe2.join(1)))
     pipe2.wait(0), pipe2.wait(1)
     # for comparison: round 1's dense result arrays + state copy + nibble slab (47 B per board-step across PCIe)
     pipe_d = env.host_pipe(slab_orbs=SLAB_ORBS, chunks=2)
     pipe_d.slab.copy_(torch.from_numpy(ppad_b200.layout.pack_slab(
         np.random.default_rng(5 + rank).integers(0, 6, size=(n, SLAB_ORBS)).astype(np.uint8)).view(np.int32)))
-    for j in range(30):
-        pipe_d.step(eval_moves=True, obs=obs_buf, step=base_t + 60000 + j, wait=True)
-    dense_ms = T.timed(lambda t: pipe_d.step(eval_moves=True, obs=obs_buf, step=t, wait=True), base_t + 60100, min(e2e_k, 50)) / min(e2e_k, 50)
+    wd = warm_by_time(lambda t: pipe_d.step(eval_moves=True, obs=obs_buf, step=t, wait=True), base_t + 60000)
+    dense_ms = T.timed(lambda t: pipe_d.step(eval_moves=True, obs=obs_buf, step=t, wait=True), base_t + 60000 + wd, min(e2e_k, 50)) / min(e2e_k, 50)
     dense_bytes = pipe_d.h2d_bytes() + pipe_d.d2h_bytes()
-    del pipe, pipe2, pipe_d
+    # round 2's first compact format: 12-byte slab rows (32 orbs), 12-byte records, no dictionary
+    pipe_c = env.host_pipe(slab_orbs=SLAB_ORBS, compact=True, slab_format=SLAB_FORMAT)
+    pipe_c.slab.copy_(slabs[0].cpu())
+    wc = warm_by_time(lambda t: pipe_c.step(eval_moves=True, obs=obs_buf, step=t, wait=True), base_t + 70000)
+    rows_ms = T.timed(lambda t: pipe_c.step(eval_moves=True, obs=obs_buf, step=t, wait=True), base_t + 70000 + wc, min(e2e_k, 50)) / min(e2e_k, 50)
+    rows_bytes = pipe_c.h2d_bytes() + pipe_c.d2h_bytes()
+    del pipe, pipe2, pipe_d, pipe_c
 
     stats = pdist.gather_stats(pdist.local_stats(out.reward, out.info))
 
@@ -644,15 +686,29 @@ def main():
             "e2e": {"value": total * e2e_k / (e2e_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_k, "steps": e2e_k,
                     "bytes_per_board_step": (h2d + d2h) / n,
-                    "note": "HostPipe.step (ppad_pipe_step), synchronous, zero copy: the kernel reads the 12-byte skyfall row "
-                            "of every board from pinned host memory and writes the compact result stream to pinned host "
-                            "memory: 4 bits per board (action + has-record) and (float64 reward, uint32 info) only for the "
-                            "boards whose info word is not 0 (the others have reward 0 and info 0 by definition); the host "
-                            "follows the boards from the actions, fresh boards after a reset travel with the records "
-                            "(tests/test_gpu_dropin.py::test_host_pipe_compact_results_equal_device_step); the fp32 one-hot "
-                            "obs stays in HBM for the device-side agent",
+                    "h2d_bytes_eager": h2d_eager, "h2d_bytes_on_demand": h2d_lazy,
+                    "h2d_bytes_offered": E2E_SLAB_ORBS // 10 * 4 * n,
+                    "skyfall_orbs_offered_per_board": E2E_SLAB_ORBS,
+                    "dictionary": {"entries": dict_entries, "share_of_records_covered_when_learned": dict_cover,
+                                   "records_last_step": e2e_records, "escapes_last_step": e2e_escapes},
+                    "checked": "the decoded stream of one more step equals ppad_step on device buffers bit for bit "
+                               "(reward, info, action, state), in this run",
+                    "note": "HostPipe.step (ppad_pipe_step), synchronous, zero copy.  In: the host offers 50 skyfall orbs "
+                            "per board in pinned memory (chunk-major, 10 orbs per word); the kernel fetches the first two "
+                            "chunks of every board (8 B) and later chunks only where a cascade gets that far "
+                            "(h2d_bytes_on_demand, counted from the consumed counts in 32-byte sectors).  Out: the compact "
+                            "result stream in pinned memory: 4 bits per board (action + has-record); a board whose info "
+                            "word is not 0 (the others have reward 0 and info 0 by definition) adds a 16-bit code when "
+                            "its (float64 reward, uint32 info) pair is in the pipe's dictionary -- the 4096 most frequent "
+                            "pairs of an earlier step, counted on the host -- and the 12 bytes themselves otherwise; the "
+                            "host follows the boards from the actions, fresh boards after a reset travel with the "
+                            "records (tests/test_gpu_dropin.py::test_host_pipe_compact_results_equal_device_step); the "
+                            "fp32 one-hot obs stays in HBM for the device-side agent",
                     "two_steps_in_flight": {"value": total * e2e_k / (e2e_async_ms * 1e-3), "unit": "steps/s",
                                             "ms_per_step": e2e_async_ms / e2e_k},
+                    "row_slab_plain_records": {"value": total / (rows_ms * 1e-3), "unit": "steps/s", "ms_per_step": rows_ms,
+                                               "bytes_per_board_step": rows_bytes / n,
+                                               "note": "12-byte slab rows (32 orbs) + 12-byte records, no dictionary"},
                     "round1_dense_format": {"value": total / (dense_ms * 1e-3), "unit": "steps/s", "ms_per_step": dense_ms,
                                             "bytes_per_board_step": dense_bytes / n}},
             "gpu_launches": int(launches),

@@ -248,7 +248,15 @@ typedef struct ppad_host_step_args {
      *                  records_capacity bytes; the worst case is ppad_compact_capacity(ctx, n) bytes
      *   summary_host   [4] uint32: 128-byte lines used, tiles, overflow (a block did not fit: its tile_line is
      *                  0xFFFFFFFF), 0 -- valid once ppad_pipe_wait returns
-     * reward_host / info_host / action_out_host are ignored in this mode; state_out_host still works. */
+     * reward_host / info_host / action_out_host are ignored in this mode; state_out_host still works.
+     *
+     * results_compact = 2: the same stream with the records dictionary-coded (ppad_pipe_set_dictionary first).  The
+     * (reward, info) pairs of a step repeat -- every board with one red combo of three orbs at depth 1 reports the
+     * same twelve bytes -- so a record that is in the pipe's dictionary travels as its 16-bit index.  The record block
+     * of a tile with k records, e of them not in the dictionary, m fresh episodes:
+     *   k x uint16 code (dictionary index; 0xFFFF = escape) | pad to 8 B | e x float64 reward | e x uint32 info
+     *   (the escapes, in board order) | pad to 16 B | m x packed state record | pad to 128 B
+     * Decoding is exact whatever the dictionary holds: it only decides how many records escape. */
     int32_t results_compact;
     uint32_t *nibbles_host;
     uint32_t *tile_line_host;
@@ -263,8 +271,15 @@ typedef struct ppad_host_step_args {
     int32_t slab_eager;              /* PPAD_SLAB_CHUNKS10: chunks per board fetched up front, 1..4; 0 = default (2) */
     int32_t reserved2;
 } ppad_host_step_args;
-/* bytes of records_host that can never overflow for n boards (with or without auto_reset) */
+/* bytes of records_host that can never overflow for n boards (with or without auto_reset, with or without a dictionary) */
 int64_t ppad_compact_capacity(const ppad_ctx *ctx, int64_t n);
+/* The dictionary of results_compact = 2: `count` (<= PPAD_DICT_MAX) pairs (rewards[i], infos[i]), typically the most
+ * frequent pairs of an earlier step's results (the host learns them; the library never guesses).  Code i of the stream
+ * means pair i of THIS call's arrays: keep them for decoding.  A pair the hash table cannot place (more than 8
+ * collisions in a row at load factor 1/4: practically never) simply keeps escaping.  Waits for the steps already
+ * enqueued on the pipe; count = 0 removes the dictionary. */
+#define PPAD_DICT_MAX 32768
+int ppad_pipe_set_dictionary(ppad_pipe *pipe, const double *rewards, const uint32_t *infos, int32_t count);
 int ppad_pipe_create(const ppad_ctx *ctx, int64_t n_max, int32_t slab_words_max, int32_t chunks, ppad_pipe **out);
 void ppad_pipe_destroy(ppad_pipe *pipe);
 /* `after_stream`: work already queued there (e.g. ppad_reset) is ordered before the chunks */

@@ -75,7 +75,7 @@ SYMBOLS = ["ppad_default_config", "ppad_create", "ppad_destroy", "ppad_abi_versi
            "ppad_fill", "ppad_damage", "ppad_select_actions", "ppad_discount", "ppad_replay_push",
            "ppad_replay_sample", "ppad_permute", "ppad_pipe_create", "ppad_pipe_destroy", "ppad_pipe_step",
            "ppad_pipe_wait", "ppad_pipe_join", "ppad_rollout", "ppad_pipe_set_zero_copy", "ppad_rollout_record",
-           "ppad_compact_capacity", "ppad_policy_step", "ppad_policy_stats", "ppad_policy_stats_rows", "ppad_island"]
+           "ppad_compact_capacity", "ppad_pipe_set_dictionary", "ppad_policy_step", "ppad_policy_stats", "ppad_policy_stats_rows", "ppad_island"]
 
 
 class PPADError(RuntimeError):
@@ -127,6 +127,7 @@ def lib():
     L.ppad_rollout.argtypes = [vp, i64, u64, u32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     L.ppad_rollout_record.argtypes = [vp, i64, u64, u32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
     L.ppad_pipe_create.argtypes = [vp, i64, i32, i32, C.POINTER(vp)]
+    L.ppad_pipe_set_dictionary.argtypes = [vp, vp, vp, i32]
     L.ppad_pipe_destroy.argtypes = [vp]
     L.ppad_pipe_destroy.restype = None
     L.ppad_pipe_step.argtypes = [vp, C.POINTER(HostStepArgs), vp, i32]

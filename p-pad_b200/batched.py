@@ -500,6 +500,7 @@ class HostPipe:
                  slab_eager=0):
         self.venv = venv
         self.slab_eager = int(slab_eager)   # chunks10: chunks per board the kernel fetches up front (0 = default, 2)
+        self._dict = None                   # (rewards float64 [D], infos uint32 [D]) of the dictionary-coded stream
         self.slab_orbs = int(slab_orbs)
         self.slab_format = slab_format
         self.slab_words = {'planes3': 3 * ((self.slab_orbs + 31) // 32), 'chunks10': (self.slab_orbs + 9) // 10,
@@ -562,7 +563,8 @@ class HostPipe:
         a.slab_stride = b.slab.shape[1] if self.slab_format == 'chunks10' else 0
         a.slab_eager = self.slab_eager
         if self.compact:
-            a.results_compact = 1
+            a.results_compact = 2 if self._dict is not None else 1
+            b.dict = self._dict                     # the stream of this step decodes with the dictionary it was coded with
             a.nibbles_host, a.tile_line_host = b.nibbles.data_ptr(), b.tile_line.data_ptr()
             a.records_host, a.records_capacity = b.records.data_ptr(), b.records.numel()
             a.summary_host = b.summary.data_ptr()
@@ -586,7 +588,44 @@ class HostPipe:
         if not self.compact:
             return dict(action=b.action.numpy(), reward=b.reward.numpy(), info=b.info.numpy().view(np.uint32))
         return decode_compact(self.venv.n, self.venv.words, b.nibbles.numpy().view(np.uint32),
-                              b.tile_line.numpy().view(np.uint32), b.records.numpy(), b.summary.numpy().view(np.uint32))
+                              b.tile_line.numpy().view(np.uint32), b.records.numpy(), b.summary.numpy().view(np.uint32),
+                              dictionary=getattr(b, "dict", None))
+
+    def set_dictionary(self, rewards=None, infos=None):
+        """Dictionary of the compact stream (ppad_pipe_set_dictionary): records whose (reward, info) pair is in it travel
+        as a 16-bit index.  Waits for the steps in flight; decode their results before calling.  None removes it."""
+        if not self.compact:
+            raise ValueError("only compact pipes take a dictionary")
+        if rewards is None or len(rewards) == 0:
+            self._dict = None
+            r = i = None
+            count = 0
+        else:
+            r = np.ascontiguousarray(rewards, np.float64)
+            i = np.ascontiguousarray(infos, np.uint32)
+            assert r.shape == i.shape and r.ndim == 1
+            count = len(r)
+            self._dict = (r, i)
+        with torch.cuda.device(self.venv.device):
+            _cabi.check(self.venv.lib.ppad_pipe_set_dictionary(
+                self._pipe, r.ctypes.data if count else None, i.ctypes.data if count else None, count))
+
+    def learn_dictionary(self, buf=0, max_entries=4096):
+        """Build the dictionary from the results of the last completed step of `buf`: its most frequent (reward, info)
+        pairs.  A host-side frequency count over values the device computed -- no game logic.  Returns the number of
+        entries and the share of that step's records they cover."""
+        got = self.results(buf)
+        has = got["info"] != 0
+        if not has.any():
+            self.set_dictionary(None)
+            return 0, 0.0
+        key = np.empty(int(has.sum()), dtype=[("r", np.uint64), ("i", np.uint32)])
+        key["r"] = got["reward"][has].view(np.uint64)
+        key["i"] = got["info"][has]
+        uniq, counts = np.unique(key, return_counts=True)
+        order = np.argsort(-counts, kind="stable")[:int(max_entries)]
+        self.set_dictionary(uniq["r"][order].view(np.float64), uniq["i"][order])
+        return len(order), float(counts[order].sum()) / float(counts.sum())
 
     def d2h_bytes(self, buf=0, want_state=None):
         """Bytes the last completed step of `buf` wrote to host memory."""

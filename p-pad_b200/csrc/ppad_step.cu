@@ -2,6 +2,7 @@
 // The kernels live in ppad_step.cuh and are instantiated per geometry in ppad_step_inst.cu.
 #include "ppad_step.cuh"
 #include <cstdlib>
+#include <vector>
 
 namespace ppad {
 
@@ -47,6 +48,8 @@ struct CompactTarget {
     uint32_t *nibbles, *tile_line, *summary, *counters;
     void *records;
     int64_t capacity_bytes;
+    const uint4 *dict;     // result dictionary (device hash table) or NULL
+    uint32_t dict_mask;
 };
 
 static int launch_step(const ppad_ctx *ctx, const ppad_step_args *args, cudaStream_t st, bool coalesced_results = false,
@@ -120,6 +123,8 @@ static int launch_step(const ppad_ctx *ctx, const ppad_step_args *args, cudaStre
     a.c_nibbles = a.c_tile_line = a.c_summary = a.c_counters = nullptr;
     a.c_records = nullptr;
     a.c_capacity = 0;
+    a.c_dict = nullptr;
+    a.c_dict_mask = 0;
     if (compact) {
         if (a.paths || a.combo_log) return fail(PPAD_ERR_UNSUPPORTED, "compact results: no finger paths / combo log");
         a.c_nibbles = compact->nibbles;
@@ -129,6 +134,8 @@ static int launch_step(const ppad_ctx *ctx, const ppad_step_args *args, cudaStre
         a.c_records = reinterpret_cast<uint4 *>(compact->records);
         const int64_t lines = compact->capacity_bytes / 128;
         a.c_capacity = (uint32_t)(lines > 0x7FFFFFFF ? 0x7FFFFFFF : lines);
+        a.c_dict = compact->dict;
+        a.c_dict_mask = compact->dict_mask;
     }
     a.tile_counter = nullptr;
     int choice = ctx->pool_kind == 1 ? STEP_KERNEL_WPOOL : STEP_KERNEL_POOL;
@@ -212,6 +219,9 @@ struct ppad_pipe {
     double *d_reward;
     uint32_t *d_info;
     uint32_t *d_counters;   // compact result stream: {next free line, finished tiles}, kept at 0 between launches
+    uint4 *d_dict;          // result dictionary: open-addressed hash table (ppad_step.cuh: dict_lookup) or NULL
+    uint32_t dict_slots;    // power of two
+    int32_t dict_count;     // entries placed
     cudaEvent_t joined;     // recorded after the last chunk of a step: after_stream waits for it
 };
 
@@ -294,6 +304,7 @@ void ppad_pipe_destroy(ppad_pipe *p)
     cudaFree(p->d_reward);
     cudaFree(p->d_info);
     cudaFree(p->d_counters);
+    cudaFree(p->d_dict);
     if (p->joined) cudaEventDestroy(p->joined);
     if (prev_device >= 0) cudaSetDevice(prev_device);   // destroy may run from a finaliser: leave the caller's device alone
     delete p;
@@ -377,6 +388,13 @@ int ppad_pipe_step(ppad_pipe *p, const ppad_host_step_args *h, void *after_strea
             ct.counters = p->d_counters;
             ct.records = h->records_host;
             ct.capacity_bytes = h->records_capacity;
+            ct.dict = nullptr;
+            ct.dict_mask = 0;
+            if (h->results_compact == 2) {
+                if (!p->d_dict) return fail(PPAD_ERR_INVALID, "ppad_pipe_step: results_compact = 2 needs ppad_pipe_set_dictionary first");
+                ct.dict = p->d_dict;
+                ct.dict_mask = p->dict_slots - 1;
+            }
         } else {
             a.action_out = h->action_out_host;
             a.reward = h->reward_host;
@@ -461,7 +479,53 @@ int64_t ppad_compact_capacity(const ppad_ctx *ctx, int64_t n)
     if (!ctx || n < 0) return -1;
     const int64_t tiles = (n + BLOCK - 1) / BLOCK;
     const int64_t rec = ppad_state_bytes_ex(ctx->cfg.rows, ctx->cfg.cols, ctx->cfg.orb_bits);
-    return tiles * (((int64_t)BLOCK * (12 + rec) + 127) / 128 * 128);
+    // worst case of the dictionary-coded stream: every board has a record, none of them is in the dictionary
+    return tiles * (((int64_t)BLOCK * (2 + 12 + rec) + 16 + 127) / 128 * 128);
+}
+
+int ppad_pipe_set_dictionary(ppad_pipe *p, const double *rewards, const uint32_t *infos, int32_t count)
+{
+    if (!p || count < 0 || (count > 0 && (!rewards || !infos)))
+        return fail(PPAD_ERR_INVALID, "ppad_pipe_set_dictionary: bad argument");
+    if (count > PPAD_DICT_MAX) return fail(PPAD_ERR_INVALID, "ppad_pipe_set_dictionary: at most PPAD_DICT_MAX entries");
+    uint32_t slots = 1024;
+    while (slots < 4u * (uint32_t)count) slots <<= 1;      // load factor <= 1/4: short probe sequences
+    std::vector<uint4> table(slots, make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu));
+    int placed = 0;
+    for (int32_t i = 0; i < count; i++) {
+        uint64_t bits;
+        std::memcpy(&bits, &rewards[i], 8);
+        const uint32_t lo = (uint32_t)bits, hi = (uint32_t)(bits >> 32);
+        uint32_t h = dict_hash(lo, hi, infos[i]);
+        for (int probe = 0; probe < DICT_PROBES; probe++, h++) {
+            uint4 &slot = table[h & (slots - 1)];
+            if (slot.w == 0xFFFFFFFFu) {
+                slot = make_uint4(lo, hi, infos[i], (uint32_t)i);   // the code is the caller's index, placed or not
+                placed++;
+                break;
+            }
+            if (slot.x == lo && slot.y == hi && slot.z == infos[i]) break;   // duplicate entry: the first index wins
+        }
+    }
+    DeviceGuard guard(p->ctx->device);
+    // steps already enqueued may still read the old table
+    cudaError_t e = cudaSuccess;
+    for (int k = 0; k < p->chunks && e == cudaSuccess; k++) e = cudaStreamSynchronize(p->streams[k]);
+    if (e == cudaSuccess && p->d_dict) {
+        e = cudaFree(p->d_dict);
+        p->d_dict = nullptr;
+    }
+    p->dict_slots = 0;
+    p->dict_count = 0;
+    if (e == cudaSuccess && count > 0) {
+        e = cudaMalloc(&p->d_dict, (size_t)slots * sizeof(uint4));
+        if (e == cudaSuccess) e = cudaMemcpy(p->d_dict, table.data(), (size_t)slots * sizeof(uint4), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) {
+            p->dict_slots = slots;
+            p->dict_count = placed;
+        }
+    }
+    return cuda_check(e, "ppad_pipe_set_dictionary");
 }
 
 int ppad_pipe_set_zero_copy(ppad_pipe *p, int32_t enabled)

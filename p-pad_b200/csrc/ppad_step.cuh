@@ -42,20 +42,56 @@ struct StepKernelArgs {
     uint32_t *c_summary;      // [4]: lines used, tiles, overflow, 0 -- written by the last CTA to finish
     uint32_t *c_counters;     // DEVICE [2]: next free line, finished tiles; left at 0 by the last CTA
     uint32_t c_capacity;      // lines the record buffer holds
+    const uint4 *c_dict;      // DEVICE: result dictionary (open-addressed hash table, see ResultDict) or NULL
+    uint32_t c_dict_mask;     // slots - 1
 };
+
+// Result dictionary of the compact stream (ppad_pipe_set_dictionary): the (reward, info) pairs of a step repeat -- a
+// board with one red combo of three orbs at depth 1 always reports the same twelve bytes -- so the host hands the pipe
+// the pairs it has seen most often, and a board whose pair is in the dictionary sends its 16-bit index instead.
+// Open addressing, linear probing, at most DICT_PROBES slots per lookup (the builder drops what does not fit); slot =
+// {reward bits lo, hi, info, index}; index 0xFFFFFFFF marks an empty slot.  The reward bit pattern 0x7FF8DEADBEEF0000
+// never occurs (a NaN), so an all-ones slot is unambiguous.
+constexpr int DICT_PROBES = 8;
+constexpr uint32_t DICT_ESCAPE = 0xFFFFu;
+__host__ __device__ inline uint32_t dict_hash(uint32_t lo, uint32_t hi, uint32_t info)
+{
+    uint32_t h = lo * 0x9E3779B1u;
+    h = (h ^ (h >> 15) ^ hi) * 0x85EBCA77u;
+    h = (h ^ (h >> 13) ^ info) * 0xC2B2AE3Du;
+    return h ^ (h >> 16);
+}
+__device__ __forceinline__ uint32_t dict_lookup(const uint4 *dict, uint32_t mask, double reward, uint32_t info)
+{
+    const uint32_t lo = (uint32_t)__double2loint(reward), hi = (uint32_t)__double2hiint(reward);
+    uint32_t h = dict_hash(lo, hi, info);
+#pragma unroll 1
+    for (int probe = 0; probe < DICT_PROBES; probe++, h++) {
+        const uint4 slot = __ldg(dict + (h & mask));
+        if (slot.w == 0xFFFFFFFFu) break;
+        if (slot.x == lo && slot.y == hi && slot.z == info) return slot.w;
+    }
+    return DICT_ESCAPE;
+}
 
 // Record block of one tile (= CTA of BLOCK boards) in the compact result stream: k records for the boards whose info
 // word is not 0 (a board that was not evaluated, or matched nothing, has reward 0 and info 0), m <= k of them with a
 // fresh episode (FLAG_EPISODE_DONE), in board order:
 //   [k x float64 reward][k x uint32 info][pad to 16 bytes][m x packed state record], padded to 128 bytes.
+// With a result dictionary (e <= k of the records are not in it):
+//   [k x uint16 code, 0xFFFF = escape][pad to 8][e x float64 reward][e x uint32 info][pad to 16][m x state], padded to 128.
 template <class G>
 struct CompactLayout {
     static constexpr int SB = G::STATE_BYTES;
     static __host__ __device__ constexpr int off_info(int k) { return 8 * k; }
     static __host__ __device__ constexpr int off_state(int k) { return (12 * k + 15) & ~15; }
     static __host__ __device__ constexpr int lines(int k, int m) { return (off_state(k) + m * SB + 127) / 128; }
-    static constexpr int MAX_STAGE = 128 * ((8 * BLOCK + 4 * BLOCK + BLOCK * SB + 127) / 128);
-    static constexpr int MAX_STAGE_NO_RESET = 128 * ((8 * BLOCK + 4 * BLOCK + 127) / 128);
+    static __host__ __device__ constexpr int d_off_reward(int k) { return (2 * k + 7) & ~7; }
+    static __host__ __device__ constexpr int d_off_info(int k, int e) { return d_off_reward(k) + 8 * e; }
+    static __host__ __device__ constexpr int d_off_state(int k, int e) { return (d_off_info(k, e) + 4 * e + 15) & ~15; }
+    static __host__ __device__ constexpr int d_lines(int k, int e, int m) { return (d_off_state(k, e) + m * SB + 127) / 128; }
+    static constexpr int MAX_STAGE = 128 * ((2 * BLOCK + 8 * BLOCK + 4 * BLOCK + BLOCK * SB + 127) / 128);
+    static constexpr int MAX_STAGE_NO_RESET = 128 * ((2 * BLOCK + 8 * BLOCK + 4 * BLOCK + 127) / 128);
 };
 
 // Every thread of the CTA must call this (after its board's step is complete).
@@ -65,16 +101,22 @@ __device__ __forceinline__ void compact_results(const StepKernelArgs &a, bool va
     typedef CompactLayout<G> CL;
     extern __shared__ uint4 c_stage4[];
     unsigned char *stage = reinterpret_cast<unsigned char *>(c_stage4);
-    __shared__ int c_cnt[2][BLOCK / 32];
+    __shared__ int c_cnt[3][BLOCK / 32];
     __shared__ __align__(16) uint32_t c_nib[BLOCK / 8];
     __shared__ uint32_t c_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool has = valid && o.info != 0;             // reward != 0 implies n_combos != 0
     const bool done = has && (o.info >> 31) != 0;      // FLAG_EPISODE_DONE: the host wants the fresh board
-    const unsigned bh = __ballot_sync(0xFFFFFFFFu, has), bd = __ballot_sync(0xFFFFFFFFu, done);
+    const bool use_dict = a.c_dict != nullptr;          // kernel-uniform
+    uint32_t code = DICT_ESCAPE;
+    if (use_dict && has) code = dict_lookup(a.c_dict, a.c_dict_mask, o.reward, o.info);
+    const bool esc = has && code == DICT_ESCAPE;
+    const unsigned bh = __ballot_sync(0xFFFFFFFFu, has), bd = __ballot_sync(0xFFFFFFFFu, done),
+                   be = __ballot_sync(0xFFFFFFFFu, esc);
     if (lane == 0) {
         c_cnt[0][warp] = __popc(bh);
         c_cnt[1][warp] = __popc(bd);
+        c_cnt[2][warp] = __popc(be);
     }
     uint32_t nib = valid ? ((o.action <= ACT_NOOP ? (uint32_t)o.action : 7u) | (has ? 8u : 0u)) : 0u;   // none / bad id -> 7
     nib <<= 4 * (lane & 7);
@@ -83,18 +125,24 @@ __device__ __forceinline__ void compact_results(const StepKernelArgs &a, bool va
     nib |= __shfl_xor_sync(0xFFFFFFFFu, nib, 4);
     if ((lane & 7) == 0) c_nib[warp * 4 + (lane >> 3)] = nib;
     __syncthreads();
-    int r = __popc(bh & ((1u << lane) - 1u)), rd = __popc(bd & ((1u << lane) - 1u)), k = 0, m = 0;
+    const unsigned below = (1u << lane) - 1u;
+    int r = __popc(bh & below), rd = __popc(bd & below), re = __popc(be & below), k = 0, m = 0, e = 0;
 #pragma unroll
     for (int w = 0; w < BLOCK / 32; w++) {
-        const int ch = c_cnt[0][w], cd = c_cnt[1][w];
+        const int ch = c_cnt[0][w], cd = c_cnt[1][w], ce = c_cnt[2][w];
         if (w < warp) {
             r += ch;
             rd += cd;
+            re += ce;
         }
         k += ch;
         m += cd;
+        e += ce;
     }
-    const int off_info = CL::off_info(k), off_state = CL::off_state(k), lines = CL::lines(k, m);
+    const int off_reward = use_dict ? CL::d_off_reward(k) : 0;
+    const int off_info = use_dict ? CL::d_off_info(k, e) : CL::off_info(k);
+    const int off_state = use_dict ? CL::d_off_state(k, e) : CL::off_state(k);
+    const int lines = use_dict ? CL::d_lines(k, e, m) : CL::lines(k, m);
     if (tid == 0) {
         uint32_t base = 0;
         if (lines) {
@@ -104,7 +152,13 @@ __device__ __forceinline__ void compact_results(const StepKernelArgs &a, bool va
         c_base = base;
         a.c_tile_line[blockIdx.x] = base;
     }
-    if (has) {
+    if (use_dict) {
+        if (has) *reinterpret_cast<uint16_t *>(stage + 2 * r) = (uint16_t)code;
+        if (esc) {
+            *reinterpret_cast<double *>(stage + off_reward + 8 * re) = o.reward;
+            *reinterpret_cast<uint32_t *>(stage + off_info + 4 * re) = o.info;
+        }
+    } else if (has) {
         *reinterpret_cast<double *>(stage + 8 * r) = o.reward;
         *reinterpret_cast<uint32_t *>(stage + off_info + 4 * r) = o.info;
     }

@@ -123,11 +123,12 @@ def pack_slab_chunks10(orbs, stride=None):
 TILE = 256   # boards per tile of the compact result stream (= CTA size of the step kernel)
 
 
-def decode_compact(n, words, nibbles, tile_line, records, summary):
+def decode_compact(n, words, nibbles, tile_line, records, summary, dictionary=None):
     """Decode the compact result stream of ppad_pipe_step (include/ppad_b200.h: ppad_host_step_args) into dense arrays.
     nibbles uint32 [tiles * 32], tile_line uint32 [tiles], records uint8 [capacity], summary uint32 [4]; words = uint32
-    words per packed state record.  Returns dict(action uint8 [n], reward float64 [n], info uint32 [n],
-    reset_index int64 [m], reset_state uint32 [m, words], lines int).  A format decoder: no game logic."""
+    words per packed state record; dictionary = (rewards float64 [D], infos uint32 [D]) for a stream written with
+    results_compact = 2.  Returns dict(action uint8 [n], reward float64 [n], info uint32 [n], reset_index int64 [m],
+    reset_state uint32 [m, words], lines int, escapes int).  A format decoder: no game logic."""
     if int(summary[2]):
         raise RuntimeError("compact result stream overflowed its record buffer")
     tiles = (n + TILE - 1) // TILE
@@ -142,7 +143,7 @@ def decode_compact(n, words, nibbles, tile_line, records, summary):
     reward = np.zeros(n, np.float64)
     info = np.zeros(n, np.uint32)
     idx = np.flatnonzero(has)
-    out = dict(action=action, reward=reward, info=info, lines=int(summary[0]),
+    out = dict(action=action, reward=reward, info=info, lines=int(summary[0]), escapes=0,
                reset_index=np.zeros(0, np.int64), reset_state=np.zeros((0, words), np.uint32))
     if idx.size == 0:
         return out
@@ -152,8 +153,32 @@ def decode_compact(n, words, nibbles, tile_line, records, summary):
     r = np.arange(idx.size, dtype=np.int64) - first[tile]             # rank within the tile
     base = tile_line[:tiles].astype(np.int64) * 128                   # byte offset of each tile's block
     rec = np.ascontiguousarray(records)
-    reward[idx] = rec.view(np.float64)[base[tile] // 8 + r]
-    inf = rec.view(np.uint32)[(base[tile] + 8 * k[tile]) // 4 + r]
+    if dictionary is None:
+        reward[idx] = rec.view(np.float64)[base[tile] // 8 + r]
+        inf = rec.view(np.uint32)[(base[tile] + 8 * k[tile]) // 4 + r]
+        off_state_of = lambda kk, ee: (12 * kk + 15) // 16 * 16
+        e = np.zeros(tiles, np.int64)
+    else:
+        d_reward, d_info = np.asarray(dictionary[0], np.float64), np.asarray(dictionary[1], np.uint32)
+        code = rec.view(np.uint16)[base[tile] // 2 + r].astype(np.int64)
+        esc = code == 0xFFFF
+        if (code[~esc] >= len(d_reward)).any():
+            raise RuntimeError("compact result stream: a code is outside the dictionary it is decoded with")
+        rw = np.zeros(idx.size, np.float64)
+        inf = np.zeros(idx.size, np.uint32)
+        rw[~esc] = d_reward[code[~esc]]
+        inf[~esc] = d_info[code[~esc]]
+        e = np.bincount(tile[esc], minlength=tiles).astype(np.int64)      # escapes per tile
+        if esc.any():
+            etile = tile[esc]
+            efirst = np.concatenate([[0], np.cumsum(e)[:-1]])
+            er = np.arange(etile.size, dtype=np.int64) - efirst[etile]
+            off_r = base[etile] + (2 * k[etile] + 7) // 8 * 8
+            rw[esc] = rec.view(np.float64)[off_r // 8 + er]
+            inf[esc] = rec.view(np.uint32)[(off_r + 8 * e[etile]) // 4 + er]
+        reward[idx] = rw
+        out["escapes"] = int(esc.sum())
+        off_state_of = lambda kk, ee: ((2 * kk + 7) // 8 * 8 + 12 * ee + 15) // 16 * 16
     info[idx] = inf
     done = (inf >> 31) != 0
     if done.any():
@@ -161,7 +186,7 @@ def decode_compact(n, words, nibbles, tile_line, records, summary):
         m = np.bincount(dtile, minlength=tiles).astype(np.int64)
         dfirst = np.concatenate([[0], np.cumsum(m)[:-1]])
         rd = np.arange(didx.size, dtype=np.int64) - dfirst[dtile]
-        off_state = (12 * k[dtile] + 15) // 16 * 16
+        off_state = off_state_of(k[dtile], e[dtile])
         w0 = (base[dtile] + off_state) // 4 + rd * words
         out["reset_index"] = didx
         out["reset_state"] = rec.view(np.uint32)[w0[:, None] + np.arange(words)[None, :]]

@@ -13,7 +13,7 @@ obs = torch.empty((n, 5, 6, 7), dtype=torch.float32, device=dev)
 gen = torch.Generator(device=dev); gen.manual_seed(7)
 
 
-def run(fmt, orbs, with_obs=True, reps=60, eager=0):
+def run(fmt, orbs, with_obs=True, reps=60, eager=0, dict_entries=0):
     env = ppad_b200.BatchedPAD(n, 5, 6, seed=20260, device=dev)
     env.reset(step=0)
     pipe = env.host_pipe(slab_orbs=orbs, compact=True, slab_format=fmt, slab_eager=eager)
@@ -23,6 +23,12 @@ def run(fmt, orbs, with_obs=True, reps=60, eager=0):
     t0, w = time.time(), 0
     while w < 20 or time.time() - t0 < 0.3:
         pipe.step(eval_moves=True, obs=o, step=1 + w, wait=True); w += 1
+
+    cover = 0.0
+    if dict_entries:
+        entries, cover = pipe.learn_dictionary(max_entries=dict_entries)
+        for w in range(10):
+            pipe.step(eval_moves=True, obs=o, step=500 + w, wait=True)
 
     def one(t, idle):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -45,15 +51,17 @@ def run(fmt, orbs, with_obs=True, reps=60, eager=0):
         out[label] = (np.median(ms), ms.min(), ms.max())
     d2h = pipe.d2h_bytes()
     got = pipe.results()
-    print("%-9s %2d orbs eager=%d obs=%d h2d %.2f + %.2f B/board: " % (fmt, orbs, eager, with_obs, pipe.h2d_bytes() / n, pipe.h2d_bytes_on_demand(got["info"]) / n) +
+    print("%-9s %2d orbs eager=%d dict=%d (cover %.3f, escapes %.3f) obs=%d h2d %.2f + %.2f B/board: " % (fmt, orbs, eager, dict_entries, cover, got["escapes"] / max(1, int((got["info"] != 0).sum())), with_obs, pipe.h2d_bytes() / n, pipe.h2d_bytes_on_demand(got["info"]) / n) +
           "; ".join("%s median %.4f ms (min %.4f max %.4f)" % ((k,) + v) for k, v in out.items()) +
           "; d2h %.2f B/board" % (d2h / n), flush=True)
     del pipe, env
 
 
-for rep in range(3):
+for rep in range(2):
     run("planes3", 32, True, reps=100)
     run("chunks10", 50, True, reps=100, eager=2)
-    run("chunks10", 40, True, reps=100, eager=2)
-    run("chunks10", 20, True, reps=100, eager=2)
-    run("chunks10", 50, False, reps=100, eager=2)
+    for d in (256, 1024, 4096, 16384):
+        run("chunks10", 50, True, reps=100, eager=2, dict_entries=d)
+    run("chunks10", 50, True, reps=100, eager=1, dict_entries=4096)
+    run("planes3", 32, True, reps=100, dict_entries=4096)
+    run("chunks10", 50, False, reps=100, eager=2, dict_entries=4096)

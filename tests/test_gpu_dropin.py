@@ -660,14 +660,25 @@ def test_host_pipe_compact_results_equal_device_step(pb, rows, cols, n, slab_for
         # bytes: 4 bits per board + 12 bytes per record (+ states of resets), line granular
         k = int((got["info"] != 0).sum())
         total_records += k
-        assert got["lines"] * 128 >= 12 * k + 4 * env.words * int(done.sum())
-        assert got["lines"] * 128 <= 12 * k + 4 * env.words * int(done.sum()) + pipe.tiles * (128 + 16)
+        # with a dictionary (from step 4 on): 2 bytes per record + 12 per record that is not in it
+        payload = 12 * k if t <= 3 else 2 * k + 12 * got["escapes"]
+        assert got["lines"] * 128 >= payload + 4 * env.words * int(done.sum())
+        assert got["lines"] * 128 <= payload + 4 * env.words * int(done.sum()) + pipe.tiles * (128 + 16 + 8)
         assert pipe.d2h_bytes() == pipe.tiles * 128 + pipe.tiles * 4 + 16 + got["lines"] * 128
+        if t == 3:
+            # dictionary-coded records (results_compact = 2): the most frequent (reward, info) pairs of this step; kept
+            # small so that the later steps hold coded and escaped records side by side
+            entries, cover = pipe.learn_dictionary(max_entries=48)
+            assert entries == 0 or 0 < cover <= 1
+        if t > 3 and n > 50_000:
+            assert 0 < got["escapes"] < k
     assert total_records > 0
     # two steps in flight with two buffer sets
     pipe2 = env.host_pipe(slab_orbs=S, compact=True, slab_format=slab_format, depth=2)
     for b in pipe2.buffers:
         b.slab.copy_(pipe.slab)
+    if pipe._dict is not None:
+        pipe2.set_dictionary(*pipe._dict)
     pipe2.step(eval_moves=True, step=20, wait=False, buf=0)
     pipe2.step(eval_moves=True, step=21, wait=False, buf=1)
     pipe2.wait(0), pipe2.wait(1)

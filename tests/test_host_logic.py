@@ -45,6 +45,91 @@ def test_slab_layout():
         assert np.array_equal((slab[:, d >> 3] >> (4 * (d & 7))) & 15, orbs[:, d])
 
 
+def test_slab_layouts_planes3_and_chunks10():
+    """the two 3-bit slab layouts as include/ppad_b200.h states them"""
+    rng = np.random.default_rng(1)
+    orbs = rng.integers(0, 7, size=(11, 47)).astype(np.uint8)
+    p3 = layout.pack_slab_planes3(orbs)
+    assert p3.shape == (11, 6) and p3.dtype == np.uint32
+    c10 = layout.pack_slab_chunks10(orbs, stride=16)
+    assert c10.shape == (5, 16) and c10.dtype == np.uint32 and not c10[:, 11:].any() and not (c10 >> 30).any()
+    for d in range(47):
+        g, k = d >> 5, d & 31
+        code = sum(((p3[:, 3 * g + j] >> k) & 1) << j for j in range(3))
+        assert np.array_equal(code, orbs[:, d])
+        c, k = divmod(d, 10)
+        code = sum(((c10[c, :11] >> (10 * j + k)) & 1) << j for j in range(3))
+        assert np.array_equal(code, orbs[:, d])
+
+
+def _encode_compact(n, words, action, reward, info, state, dictionary=None, seed=0):
+    """Test-side writer of the compact result stream exactly as include/ppad_b200.h describes it (tiles of 256 boards,
+    record blocks claimed in arbitrary order)."""
+    T = layout.TILE
+    tiles = (n + T - 1) // T
+    nib = np.zeros(tiles * T, np.uint8)
+    has = info != 0
+    nib[:n] = np.where(action > 5, 7, action) | (has.astype(np.uint8) << 3)
+    nibbles = (nib[0::2] | (nib[1::2] << 4)).view(np.uint32)
+    index = {}
+    if dictionary is not None:
+        for j, (r, i) in enumerate(zip(dictionary[0].view(np.uint64), dictionary[1])):
+            index.setdefault((int(r), int(i)), j)
+    blocks, tile_line = {}, np.zeros(tiles, np.uint32)
+    for t in range(tiles):
+        sel = np.flatnonzero(has[t * T:(t + 1) * T]) + t * T
+        k = len(sel)
+        done = sel[(info[sel] >> 31) != 0]
+        if dictionary is None:
+            body = reward[sel].tobytes() + info[sel].tobytes()
+        else:
+            codes = np.array([index.get((int(reward[i:i + 1].view(np.uint64)[0]), int(info[i])), 0xFFFF) for i in sel], np.uint16)
+            esc = sel[codes == 0xFFFF]
+            body = codes.tobytes()
+            body += b"\0" * (-len(body) % 8) + reward[esc].tobytes() + info[esc].tobytes()
+        body += b"\0" * (-len(body) % 16) + state[done].tobytes()
+        body += b"\0" * (-len(body) % 128)
+        blocks[t] = body
+    order = np.random.default_rng(seed).permutation(tiles)
+    records, line = b"", 0
+    for t in order:
+        tile_line[t] = line
+        records += blocks[t]
+        line += len(blocks[t]) // 128
+    summary = np.array([line, tiles, 0, 0], np.uint32)
+    return nibbles, tile_line, np.frombuffer(records + b"\0" * 128, np.uint8), summary
+
+
+@pytest.mark.parametrize("n", [1, 255, 256, 1000, 5000])
+@pytest.mark.parametrize("with_dict", [False, True])
+def test_decode_compact_round_trip(n, with_dict):
+    """layout.decode_compact against a writer of the documented format: plain 12-byte records and dictionary-coded ones
+    (16-bit codes, escapes in full), fresh-episode state records, ragged last tile."""
+    rng = np.random.default_rng(n)
+    words = 4
+    action = rng.integers(0, 5, n).astype(np.uint8)
+    action[rng.random(n) < 0.05] = 255
+    pool_r = np.round(rng.random(40) * 1e4, 2)
+    pool_i = rng.integers(1, 2 ** 31, 40).astype(np.uint32)
+    pick = rng.integers(0, 40, n)
+    reward, info = pool_r[pick].copy(), pool_i[pick].copy()
+    rare = rng.random(n) < 0.1                                   # pairs no dictionary holds
+    reward[rare] = rng.random(int(rare.sum())) * 1e5
+    info[rng.random(n) < 0.1] |= np.uint32(1 << 31)             # finished episodes: a state record follows
+    none = rng.random(n) < 0.4                                   # no record at all
+    reward[none], info[none] = 0.0, 0
+    state = rng.integers(0, 2 ** 32, size=(n, words), dtype=np.uint64).astype(np.uint32)
+    dictionary = (pool_r[:30].copy(), pool_i[:30].copy()) if with_dict else None     # 10 pool pairs stay outside
+    stream = _encode_compact(n, words, action, reward, info, state, dictionary, seed=n)
+    got = layout.decode_compact(n, words, *stream, dictionary=dictionary)
+    assert np.array_equal(got["action"], action)
+    assert np.array_equal(got["reward"].view(np.uint64), reward.view(np.uint64)) and np.array_equal(got["info"], info)
+    done = np.flatnonzero((info >> 31) != 0)
+    assert np.array_equal(got["reset_index"], done) and np.array_equal(got["reset_state"], state[done])
+    if with_dict and n >= 1000:
+        assert 0 < got["escapes"] < int((info != 0).sum())
+
+
 def test_make_config_translates_team_and_skyfall():
     team = [dict(color_1='red', color_2=None, atk=12.5), dict(color_1='dark', color_2='light', atk=3)]
     cfg = ppad_b200.make_config(6, 7, skyfall=[0.5, 0.5, 0, 0, 0, 0, 0, 0, 0, 0], skyfall_damage=False, team=team, seed=(1 << 63) + 5)
