@@ -51,17 +51,13 @@ def run(fmt, orbs, with_obs=True, reps=60, eager=0, dict_entries=0):
         out[label] = (np.median(ms), ms.min(), ms.max())
     d2h = pipe.d2h_bytes()
     got = pipe.results()
-    print("%-9s %2d orbs eager=%d dict=%d (cover %.3f, escapes %.3f) obs=%d h2d %.2f + %.2f B/board: " % (fmt, orbs, eager, dict_entries, cover, got["escapes"] / max(1, int((got["info"] != 0).sum())), with_obs, pipe.h2d_bytes() / n, pipe.h2d_bytes_on_demand(got["info"]) / n) +
+    print("%-9s %2d orbs eager=0x%x dict=%d (cover %.3f, escapes %.3f) obs=%d h2d %.2f + %.2f B/board: " % (fmt, orbs, eager, dict_entries, cover, got["escapes"] / max(1, int((got["info"] != 0).sum())), with_obs, pipe.h2d_bytes() / n, pipe.h2d_bytes_on_demand(got["info"]) / n) +
           "; ".join("%s median %.4f ms (min %.4f max %.4f)" % ((k,) + v) for k, v in out.items()) +
           "; d2h %.2f B/board" % (d2h / n), flush=True)
     del pipe, env
 
 
 for rep in range(2):
-    run("planes3", 32, True, reps=100)
-    run("chunks10", 50, True, reps=100, eager=2)
-    for d in (256, 1024, 4096, 16384):
-        run("chunks10", 50, True, reps=100, eager=2, dict_entries=d)
+    run("chunks10", 50, True, reps=100, eager=2, dict_entries=4096)
     run("chunks10", 50, True, reps=100, eager=1, dict_entries=4096)
-    run("planes3", 32, True, reps=100, dict_entries=4096)
-    run("chunks10", 50, False, reps=100, eager=2, dict_entries=4096)
+    run("chunks10", 10, True, reps=100, eager=1, dict_entries=4096)
