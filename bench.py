@@ -20,8 +20,8 @@ slabs rotate over 16 buffers (201 MB), so no step finds its inputs in L2.
 
 Sub-records of the same JSON line (all measured in this run, on every rank, max over ranks):
   state_only    the same step without the observation stream (persistent pool kernel), L2 flushed
-  e2e           the same step through HostPipe.step (ppad_pipe_step): pinned HOST buffers, the skyfall slab (50 orbs
-                offered per board, chunk-major; two chunks = 8 B fetched per board, more on demand) crosses PCIe host ->
+  e2e           the same step through HostPipe.step (ppad_pipe_step): pinned HOST buffers, the skyfall slab (54 orbs
+                offered per board, chunk-major; three chunks = 6 B fetched per board, more on demand) crosses PCIe host ->
                 device and the compact, dictionary-coded result stream device -> host inside the timed region
   rollout       BASELINE configs[4]: 2^23 boards per GPU, Boltzmann policy on synthetic Q-values, auto-reset, fp32 obs,
                 replay ring with discounted returns, statistics; NCCL all-gathers of stats + replay samples INSIDE the
@@ -50,11 +50,11 @@ ROWS, COLS = 5, 6
 SLAB_ORBS = 32
 SLAB_FORMAT = 'planes3'          # PPAD_SLAB_PLANES3: 3 bits per orb, 12 bytes per 32 orbs
 SLAB_BYTES = 12
-# the e2e leg (host buffers): the host OFFERS 50 orbs per board-step as a chunk-major slab (PPAD_SLAB_CHUNKS10, 20 B per
-# board in pinned memory); the kernel fetches the first two chunks of every board (8 B) and a later chunk only for the
-# boards whose cascade draws more than 20 orbs (about 4 in 1000)
-E2E_SLAB_ORBS = 50
-E2E_SLAB_FORMAT = 'chunks10'
+# the e2e leg (host buffers): the host OFFERS 54 orbs per board-step as a chunk-major slab (PPAD_SLAB_CHUNKS6: six base-6
+# orbs per uint16, 18 B per board in pinned memory); the kernel fetches the first three chunks of every board (6 B) and a
+# later chunk only for the boards whose cascade draws more than 18 orbs (about 7 in 1000)
+E2E_SLAB_ORBS = 54
+E2E_SLAB_FORMAT = 'chunks6'
 E2E_DICT_ENTRIES = 4096
 N_SLABS = 16
 SEED = 20181019
@@ -570,6 +570,7 @@ def main():
     assert got["lines"] > 0 and (got["info"] != 0).sum() > 0
     h2d_eager = pipe.h2d_bytes()
     h2d_lazy = pipe.h2d_bytes_on_demand(got["info"])
+    pipe_slab_bytes = pipe.slab.numel() * pipe.slab.element_size()
     h2d = h2d_eager + h2d_lazy
     d2h = pipe.d2h_bytes()
     e2e_records = int((got["info"] != 0).sum())
@@ -687,16 +688,16 @@ def main():
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_k, "steps": e2e_k,
                     "bytes_per_board_step": (h2d + d2h) / n,
                     "h2d_bytes_eager": h2d_eager, "h2d_bytes_on_demand": h2d_lazy,
-                    "h2d_bytes_offered": E2E_SLAB_ORBS // 10 * 4 * n,
+                    "h2d_bytes_offered": pipe_slab_bytes,
                     "skyfall_orbs_offered_per_board": E2E_SLAB_ORBS,
                     "dictionary": {"entries": dict_entries, "share_of_records_covered_when_learned": dict_cover,
                                    "records_last_step": e2e_records, "escapes_last_step": e2e_escapes},
                     "checked": "the decoded stream of one more step equals ppad_step on device buffers bit for bit "
                                "(reward, info, action, state), in this run",
-                    "note": "HostPipe.step (ppad_pipe_step), synchronous, zero copy.  In: the host offers 50 skyfall orbs "
-                            "per board in pinned memory (chunk-major, 10 orbs per word); the kernel fetches the first two "
-                            "chunks of every board (8 B) and later chunks only where a cascade gets that far "
-                            "(h2d_bytes_on_demand, counted from the consumed counts in 32-byte sectors).  Out: the compact "
+                    "note": "HostPipe.step (ppad_pipe_step), synchronous, zero copy.  In: the host offers 54 skyfall orbs "
+                            "per board in pinned memory (chunk-major, six base-6 orbs per uint16); the kernel fetches the "
+                            "first three chunks of every board (18 orbs, 6 B) and later chunks only where a cascade gets "
+                            "that far (h2d_bytes_on_demand, counted from the consumed counts in 32-byte sectors).  Out: the compact "
                             "result stream in pinned memory: 4 bits per board (action + has-record); a board whose info "
                             "word is not 0 (the others have reward 0 and info 0 by definition) adds a 16-bit code when "
                             "its (float64 reward, uint32 info) pair is in the pipe's dictionary -- the 4096 most frequent "

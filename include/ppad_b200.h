@@ -89,8 +89,15 @@ typedef enum ppad_obs_dtype { PPAD_OBS_F32 = 0, PPAD_OBS_U8 = 1 } ppad_obs_dtype
  *                      orbs or more per board while 4 * slab_eager bytes per board cross PCIe (a random-policy step
  *                      draws 3.5 orbs per board on average; one board in a hundred draws more than 20).
  *                      ppad_step and ppad_pipe_step (zero copy) only; orb_bits = 3 only.
+ *   PPAD_SLAB_CHUNKS6  the same chunk-major, eager / on-demand scheme with uint16 chunks of SIX orbs as base-6 digits
+ *                      (orb 6 c + k of board i = (chunk / 6^k) % 6, chunk = ((const uint16_t *)slab)[c * slab_stride + i]):
+ *                      the six skyfall colours 0..5 in 15.5 of 16 bits.  slab_words = chunks per board, n_inj <= 6 *
+ *                      slab_words, slab_stride >= n in uint16 units, slab_eager 1..8 (default 3: 18 orbs, 6 bytes per
+ *                      board).  A chunk value >= 46656 is no encoding: flagged PPAD_FLAG_UNSUPPORTED_ORB.
  * A code that is no orb type of the context (>= 7, or >= 10 with orb_bits = 4) is flagged PPAD_FLAG_UNSUPPORTED_ORB. */
-typedef enum ppad_slab_format { PPAD_SLAB_NIBBLES = 0, PPAD_SLAB_PLANES3 = 1, PPAD_SLAB_CHUNKS10 = 2 } ppad_slab_format;
+typedef enum ppad_slab_format {
+    PPAD_SLAB_NIBBLES = 0, PPAD_SLAB_PLANES3 = 1, PPAD_SLAB_CHUNKS10 = 2, PPAD_SLAB_CHUNKS6 = 3
+} ppad_slab_format;
 
 /* Environment constants: the keyword arguments of PAD.__init__ (game.py:39-50) that reach the hot path. */
 typedef struct ppad_config {
@@ -180,10 +187,12 @@ typedef struct ppad_step_args {
     const uint16_t *path_lens;
     int32_t path_words, path_len;
     int32_t slab_format;          /* ppad_slab_format of `slab` */
-    int32_t slab_stride;          /* PPAD_SLAB_CHUNKS10: words between consecutive chunks of one board (>= n); else ignored */
+    int32_t slab_stride;          /* chunk-major slabs: elements (uint32 / uint16) between consecutive chunks of one board
+                                     (>= n); else ignored */
     uint16_t *consumed_out;       /* [n] skyfall orbs the cascade drew, saturating at 65535 (the info byte stops at
                                      255), or NULL */
-    int32_t slab_eager;           /* PPAD_SLAB_CHUNKS10: chunks per board fetched up front, 1..4; 0 = default (2) */
+    int32_t slab_eager;           /* chunk-major slabs: chunks per board fetched up front; 0 = default (CHUNKS10: 2 of
+                                     1..4, CHUNKS6: 3 of 1..8) */
     int32_t reserved;
 } ppad_step_args;
 int ppad_step(const ppad_ctx *ctx, const ppad_step_args *args, void *stream);
@@ -267,8 +276,8 @@ typedef struct ppad_host_step_args {
                                         state it leaves behind); 1: the caller orders later work itself (ppad_pipe_join /
                                         ppad_pipe_wait) -- saves one cross-stream dependency per step when steps are
                                         enqueued back to back */
-    int32_t slab_stride;             /* PPAD_SLAB_CHUNKS10: words between consecutive chunks of one board (>= n) */
-    int32_t slab_eager;              /* PPAD_SLAB_CHUNKS10: chunks per board fetched up front, 1..4; 0 = default (2) */
+    int32_t slab_stride;             /* chunk-major slabs: elements between consecutive chunks of one board (>= n) */
+    int32_t slab_eager;              /* chunk-major slabs: chunks per board fetched up front; 0 = default */
     int32_t reserved2;
 } ppad_host_step_args;
 /* bytes of records_host that can never overflow for n boards (with or without auto_reset, with or without a dictionary) */

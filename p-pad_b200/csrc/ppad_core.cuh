@@ -386,10 +386,15 @@ PPAD_HD int orb_from_u32(const SkyfallTable &t, uint32_t x)
 //                 chunk only when the cascade gets there -- the host can offer 50 orbs or more per board while 8 bytes
 //                 per board cross PCIe (orb types 0..6 only).  A read that waits on PCIe in the middle of a cascade
 //                 stalls its whole warp, so n_eager is chosen to make those rare (2: one board in a hundred).
+//   SLAB_CHUNKS6  the same chunk-major, eager / on-demand scheme with chunks of SIX orbs as base-6 digits in one uint16
+//                 (orb 6 c + k = (chunk c / 6^k) % 6: the six skyfall colours 0..5 at log2(6^6) = 15.5 of 16 bits);
+//                 slab and stride are in uint16 units.  Three eager chunks = 18 orbs in 6 bytes per board.  A chunk
+//                 value >= 6^6 is no encoding and is flagged like a bad code.
 // Injected codes that are not orb types of the geometry (>= NT) are handed on as they are and flagged
 // (bad -> FLAG_UNSUPPORTED_ORB).
 // ---------------------------------------------------------------------------------------------
-enum : int { SLAB_NIBBLES = 0, SLAB_PLANES3 = 1, SLAB_CHUNKS10 = 2 };
+enum : int { SLAB_NIBBLES = 0, SLAB_PLANES3 = 1, SLAB_CHUNKS10 = 2, SLAB_CHUNKS6 = 3 };
+PPAD_HD uint32_t div6_u16(uint32_t w) { return (w * 43691u) >> 18; }   // floor(w / 6), exact for w < 65536
 
 struct OrbSource {
     const uint32_t *slab;   // this board's words, or nullptr
@@ -427,6 +432,13 @@ struct OrbSource {
     }
 
     PPAD_HD uint32_t chunk(int c) const { return c < n_eager ? eager[c] : slab[(size_t)c * (size_t)stride]; }
+    PPAD_HD uint32_t chunk16(int c)   // SLAB_CHUNKS6: slab, eager and stride in uint16 units
+    {
+        const uint32_t w = c < n_eager ? reinterpret_cast<const uint16_t *>(eager)[c]
+                                       : reinterpret_cast<const uint16_t *>(slab)[(size_t)c * (size_t)stride];
+        bad |= w >= 46656u ? 1u : 0u;
+        return w;
+    }
 
     template <int NT = 7>
     PPAD_HD int next(const RngKey &key, const SkyfallTable &sky)
@@ -439,6 +451,11 @@ struct OrbSource {
                 const uint32_t *g = slab + 3 * (d >> 5);
                 const int k = d & 31;
                 code = (int)(((g[0] >> k) & 1u) | (((g[1] >> k) & 1u) << 1) | (((g[2] >> k) & 1u) << 2));
+            } else if (fmt == SLAB_CHUNKS6) {
+                const int c = d / 6;
+                uint32_t w = chunk16(c);
+                for (int k = d - 6 * c; k > 0; k--) w = div6_u16(w);
+                code = (int)(w - 6u * div6_u16(w));
             } else if (fmt == SLAB_CHUNKS10) {
                 const int c = d / 10, k = d - 10 * c;
                 const uint32_t w = chunk(c);
@@ -759,6 +776,26 @@ PPAD_HD void fill_board(Board<G> &b, OrbSource &src, const RngKey &key, const Sk
                     s0 = g[0];
                     s1 = g[1];
                     s2 = g[2];
+                }
+            } while (e);
+        } else if (src.fmt == SLAB_CHUNKS6) {
+            int c = d / 6, left = 6 * (c + 1) - d;     // orbs left in the chunk at hand
+            uint32_t w = src.chunk16(c);
+            for (int k = left; k < 6; k++) w = div6_u16(w);   // drop the digits already handed out
+            do {
+                const W bit = e & (~e + 1);
+                e ^= bit;
+                const uint32_t q = div6_u16(w), digit = w - 6u * q;
+                w = q;
+                b.b0 ^= bit & ((W)(digit & 1u) - 1);
+                b.b1 ^= bit & ((W)((digit >> 1) & 1u) - 1);
+                b.b2 ^= bit & ((W)(digit >> 2) - 1);
+                PPAD_P4(b.b3 ^= bit)
+                d++;
+                if (--left == 0 && e) {
+                    c++;
+                    left = 6;
+                    w = src.chunk16(c);
                 }
             } while (e);
         } else if (src.fmt == SLAB_CHUNKS10) {

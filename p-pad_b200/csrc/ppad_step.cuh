@@ -241,9 +241,17 @@ __global__ void __launch_bounds__(BLOCK, step_min_ctas<G, AR>()) step_obs_kernel
         slab = a.slab && valid ? a.slab + i : nullptr;
         if (slab) {
             uint32_t w[4] = {0, 0, 0, 0};
+            if (a.p.slab_fmt == SLAB_CHUNKS6) {       // uint16 chunks: up to 8 eager ones fill the same 16 bytes
+                const uint16_t *s16 = reinterpret_cast<const uint16_t *>(a.slab) + i;
+                slab = reinterpret_cast<const uint32_t *>(s16);
 #pragma unroll
-            for (int c = 0; c < 4; c++)
-                if (c < a.p.slab_eager) w[c] = __ldg(slab + (size_t)c * (size_t)a.p.slab_stride);
+                for (int c = 0; c < 8; c++)
+                    if (c < a.p.slab_eager) w[c >> 1] |= (uint32_t)__ldg(s16 + (size_t)c * (size_t)a.p.slab_stride) << (16 * (c & 1));
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    if (c < a.p.slab_eager) w[c] = __ldg(slab + (size_t)c * (size_t)a.p.slab_stride);
+            }
             slab_rows[threadIdx.x] = make_uint4(w[0], w[1], w[2], w[3]);
             slab_eager = reinterpret_cast<const uint32_t *>(&slab_rows[threadIdx.x]);
         }

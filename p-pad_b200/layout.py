@@ -120,6 +120,22 @@ def pack_slab_chunks10(orbs, stride=None):
     return out
 
 
+def pack_slab_chunks6(orbs, stride=None):
+    """uint8 [n, S] orb sequence (colours 0..5) -> uint16 [ceil(S / 6), stride] chunk-major slab (PPAD_SLAB_CHUNKS6):
+    out[c, i] = sum_k orb[i, 6 c + k] * 6^k.  2 bytes per 6 orbs."""
+    orbs = np.asarray(orbs, np.uint8)
+    if orbs.size and orbs.max() > 5:
+        raise ValueError("PPAD_SLAB_CHUNKS6 holds the colours 0..5 only")
+    n, s = orbs.shape
+    chunks = max(1, (s + 5) // 6)
+    stride = n if stride is None else int(stride)
+    pad = np.zeros((n, chunks * 6), np.uint32)
+    pad[:, :s] = orbs
+    out = np.zeros((chunks, stride), np.uint16)
+    out[:, :n] = (pad.reshape(n, chunks, 6) * (6 ** np.arange(6, dtype=np.uint32))).sum(axis=2).astype(np.uint16).T
+    return out
+
+
 TILE = 256   # boards per tile of the compact result stream (= CTA size of the step kernel)
 
 

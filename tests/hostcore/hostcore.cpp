@@ -56,10 +56,15 @@ void step_batch(const StepParams &base, int64_t n, uint64_t env0, int8_t *boards
         Board<G> fin;
         // SLAB_CHUNKS10 is chunk-major: board i starts at slab + i, its chunks lie slab_stride words apart, and the
         // first slab_eager chunks are handed over as a copy (what the step kernel does with the lines it fetches up front)
-        const bool chunked = base.slab_fmt == SLAB_CHUNKS10;
+        const bool chunked = base.slab_fmt == SLAB_CHUNKS10 || base.slab_fmt == SLAB_CHUNKS6;
         const uint32_t *row = slab ? slab + (chunked ? (size_t)i : (size_t)i * base.slab_words) : nullptr;
         uint32_t eager[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-        if (chunked && row)
+        if (base.slab_fmt == SLAB_CHUNKS6 && slab) {   // uint16 chunks
+            const uint16_t *r16 = reinterpret_cast<const uint16_t *>(slab) + i;
+            row = reinterpret_cast<const uint32_t *>(r16);
+            for (int c = 0; c < base.slab_eager; c++)
+                reinterpret_cast<uint16_t *>(eager)[c] = r16[(size_t)c * (size_t)base.slab_stride];
+        } else if (chunked && row)
             for (int c = 0; c < base.slab_eager; c++) eager[c] = row[(size_t)c * (size_t)base.slab_stride];
         const StepOut o = step_board<G>(true, s, fin, base, env0 + (uint64_t)i, action, row,
                                         combo_log ? combo_log + (size_t)i * base.log_cap : nullptr,
@@ -172,8 +177,10 @@ int hostcore_step_batch(const ppad_config *cfg, int64_t n, uint64_t env0, uint32
     p.max_moves = max_moves;
     p.n_inj = slab ? n_inj : -1;
     p.slab_words = slab_words;
-    p.slab_stride = slab_format == SLAB_CHUNKS10 ? (int32_t)n : 0;
-    p.slab_eager = slab_format == SLAB_CHUNKS10 ? (slab_words < 2 ? slab_words : 2) : 0;
+    const bool chunk_major = slab_format == SLAB_CHUNKS10 || slab_format == SLAB_CHUNKS6;
+    p.slab_stride = chunk_major ? (int32_t)n : 0;
+    const int eager = slab_format == SLAB_CHUNKS6 ? 3 : 2;
+    p.slab_eager = chunk_major ? (slab_words < eager ? slab_words : eager) : 0;
     p.log_cap = log_cap;
     dyn_geom() = p.dyn;
     HC_DISPATCH(geom, (step_batch<G>(p, n, env0, boards, fingers, prev, moves, actions, slab, action_out, reward, info,

@@ -59,12 +59,13 @@ def test_cancel_and_drop_fuzz(rows, cols, kind, orb_bits):
 @pytest.mark.parametrize("rows,cols", [(4, 5), (5, 6), (6, 7)])
 @pytest.mark.parametrize("mode", ["injected", "philox", "injected_short", "no_skyfall", "wide_injected", "wide_philox",
                                   "wide3_injected", "planes3_injected", "planes3_short", "chunks10_injected",
-                                  "chunks10_short"])
+                                  "chunks10_short", "chunks6_injected", "chunks6_short"])
 def test_step_batch_fuzz(rows, cols, mode):
     """wide_*: the 4-bit kernels with all ten orb types (skyfall rates and injected orbs for types 7..9);
     wide3_injected: the 4-bit kernels on a workload the 3-bit kernels also run;
     planes3_*: the injected skyfall as a bit-sliced 3-bit slab (PPAD_SLAB_PLANES3) of 96 / 40 orbs;
-    chunks10_*: as a chunk-major slab of ten orbs per word (PPAD_SLAB_CHUNKS10) of 95 / 23 orbs"""
+    chunks10_*: as a chunk-major slab of ten orbs per word (PPAD_SLAB_CHUNKS10) of 95 / 23 orbs;
+    chunks6_*: as a chunk-major slab of six base-6 orbs per uint16 (PPAD_SLAB_CHUNKS6) of 95 / 23 orbs"""
     rng = np.random.default_rng(1000 + rows + len(mode))
     n, steps = 3000, 12
     wide = mode.startswith("wide")
@@ -81,8 +82,8 @@ def test_step_batch_fuzz(rows, cols, mode):
     mine = [boards.copy(), fingers.copy(), prev.copy(), moves.copy()]
     S = {"injected": 256, "philox": 0, "injected_short": 8, "no_skyfall": 16, "wide_injected": 256, "wide_philox": 0,
          "wide3_injected": 256, "planes3_injected": 96, "planes3_short": 40,
-         "chunks10_injected": 95, "chunks10_short": 23}[mode]
-    fmt = 1 if mode.startswith("planes3") else (2 if mode.startswith("chunks10") else 0)
+         "chunks10_injected": 95, "chunks10_short": 23, "chunks6_injected": 95, "chunks6_short": 23}[mode]
+    fmt = 1 if mode.startswith("planes3") else (2 if mode.startswith("chunks10") else (3 if mode.startswith("chunks6") else 0))
     top = 10 if sky else 6
     seen_flags = 0
     for t in range(steps):
@@ -105,7 +106,7 @@ def test_step_batch_fuzz(rows, cols, mode):
         assert np.array_equal(f0, f1), t
         seen_flags |= int(np.bitwise_or.reduce(i0 >> 24))
     assert seen_flags & orc.FLAG_REJECTED and seen_flags & orc.FLAG_BAD_ACTION and seen_flags & orc.FLAG_EPISODE_DONE
-    if mode in ("injected_short", "chunks10_short"):
+    if mode in ("injected_short", "chunks10_short", "chunks6_short"):
         assert seen_flags & orc.FLAG_SKYFALL_EXHAUSTED
 
 
