@@ -58,9 +58,6 @@ def run(fmt, orbs, with_obs=True, reps=60, eager=0, dict_entries=0):
 
 
 for rep in range(2):
-    run("chunks10", 50, True, reps=100, eager=2, dict_entries=4096)
     run("chunks6", 54, True, reps=100, eager=3, dict_entries=4096)
-    run("chunks6", 54, True, reps=100, eager=4, dict_entries=4096)
-    run("chunks6", 54, True, reps=100, eager=2, dict_entries=4096)
-    run("chunks6", 18, True, reps=100, eager=3, dict_entries=4096)
+    run("chunks10", 50, True, reps=100, eager=2, dict_entries=4096)
     run("chunks6", 54, False, reps=100, eager=3, dict_entries=4096)
