@@ -70,9 +70,11 @@ def workload_config(n, world):
     return {"workload": "configs[1]: 2^20 5x6 boards/GPU, random legal move + full cascade resolve + "
                         "fp32 one-hot obs, injected 32-orb skyfall slab (3 bit/orb, 12 B) per board-step",
             "boards_per_gpu": n, "rows": ROWS, "cols": COLS, "skyfall_orbs_per_step": SLAB_ORBS,
-            "skyfall_slab": "32 orbs not 42: 12 B instead of 16 B per board-step across PCIe in the e2e leg; a board that "
-                            "draws more than 32 orbs in one step (about 6e-5 of them) continues on the Philox stream at "
-                            "the same draw index, flagged SKYFALL_EXHAUSTED, bit-exact against the oracle which does the same",
+            "skyfall_slab": "device-timed legs: 32 injected orbs per board-step resident in HBM (bit-sliced, 12 B); a board "
+                            "that draws more than 32 orbs in one step (about 6e-5 of them) continues on the Philox stream at "
+                            "the same draw index, flagged SKYFALL_EXHAUSTED, bit-exact against the oracle which does the same.  "
+                            "e2e leg: the host offers 54 orbs per board-step in pinned memory (chunk-major, base 6), of which "
+                            "18 (6 B) cross PCIe for every board and the rest on demand",
             "l2": "inputs > L2: 881 MB obs stream per step, skyfall slabs rotate over 16 buffers (201 MB)",
             "parallelism": "env-sharded x%d, no data-path collective" % world}
 

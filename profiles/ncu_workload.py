@@ -5,7 +5,8 @@ cudaProfilerStart / Stop is profiled:
     ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/prof python profiles/ncu_workload.py
 
 Profiled launches, in order: step_obs_kernel<5x6> x2 (the headline), step_obs_kernel<5x6, compact> x2 (host pipe, zero
-copy), step_wpool_kernel<5x6> x2 (state only), policy_step_kernel<5x6> x2 (configs[4], 2^21 boards), step_obs_kernel<6x7>
+copy: chunk-major base-6 slab in pinned memory, 3 eager chunks, dictionary-coded result stream -- the e2e leg of
+bench.py), step_wpool_kernel<5x6> x2 (state only), policy_step_kernel<5x6> x2 (configs[4], 2^21 boards), step_obs_kernel<6x7>
 x2, reset_kernel<6x7> x1, reset_kernel<5x6> x1, rollout_kernel<5x6> x1 (51 fused steps), stats_reduce_kernel etc. as
 they come."""
 import os, sys
@@ -23,9 +24,12 @@ slabs = [env._slab(torch.randint(0, 6, (n, 32), device=dev, dtype=torch.uint8, g
 out = env.step(None, eval_moves=True, injected=(slabs[0], 32), slab_format='planes3', obs='f32', step=1)
 for t in range(2, 40):
     env.step(None, eval_moves=True, injected=(slabs[t & 3], 32), slab_format='planes3', obs=out.obs, step=t, out=out)
-pipe = env.host_pipe(slab_orbs=32, compact=True, slab_format='planes3')
-pipe.slab.copy_(slabs[0].cpu())
+pipe = env.host_pipe(slab_orbs=54, compact=True, slab_format='chunks6')
+pipe.slab.copy_(env._slab(torch.randint(0, 6, (n, 54), device=dev, dtype=torch.uint8, generator=gen), 'chunks6')[0].cpu())
 pipe.step(eval_moves=True, obs=out.obs, step=40, wait=True)
+pipe.learn_dictionary(max_entries=4096)
+for t in range(3):
+    pipe.step(eval_moves=True, obs=out.obs, step=37 + t, wait=True)
 n2 = 1 << 21
 penv = ppad_b200.BatchedPAD(n2, 5, 6, seed=3, device=dev)
 penv.reset(step=0)
