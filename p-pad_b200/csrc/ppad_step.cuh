@@ -61,15 +61,22 @@ __host__ __device__ inline uint32_t dict_hash(uint32_t lo, uint32_t hi, uint32_t
     h = (h ^ (h >> 13) ^ info) * 0xC2B2AE3Du;
     return h ^ (h >> 16);
 }
-__device__ __forceinline__ uint32_t dict_lookup(const uint4 *dict, uint32_t mask, double reward, uint32_t info)
+// The first probe is issued by the caller as soon as the step's results are known (dict_first), so that its trip to L2
+// runs under the observation stores; dict_lookup finishes the search after them.
+__device__ __forceinline__ uint4 dict_first(const uint4 *dict, uint32_t mask, double reward, uint32_t info)
+{
+    return __ldg(dict + (dict_hash((uint32_t)__double2loint(reward), (uint32_t)__double2hiint(reward), info) & mask));
+}
+__device__ __forceinline__ uint32_t dict_lookup(const uint4 *dict, uint32_t mask, double reward, uint32_t info, uint4 slot)
 {
     const uint32_t lo = (uint32_t)__double2loint(reward), hi = (uint32_t)__double2hiint(reward);
     uint32_t h = dict_hash(lo, hi, info);
 #pragma unroll 1
-    for (int probe = 0; probe < DICT_PROBES; probe++, h++) {
-        const uint4 slot = __ldg(dict + (h & mask));
+    for (int probe = 0; probe < DICT_PROBES; probe++) {
         if (slot.w == 0xFFFFFFFFu) break;
         if (slot.x == lo && slot.y == hi && slot.z == info) return slot.w;
+        h++;
+        slot = __ldg(dict + (h & mask));
     }
     return DICT_ESCAPE;
 }
@@ -96,7 +103,8 @@ struct CompactLayout {
 
 // Every thread of the CTA must call this (after its board's step is complete).
 template <class G>
-__device__ __forceinline__ void compact_results(const StepKernelArgs &a, bool valid, const StepOut &o, const State<G> &s)
+__device__ __forceinline__ void compact_results(const StepKernelArgs &a, bool valid, const StepOut &o, const State<G> &s,
+                                                const uint4 &first_slot)
 {
     typedef CompactLayout<G> CL;
     extern __shared__ uint4 c_stage4[];
@@ -109,7 +117,7 @@ __device__ __forceinline__ void compact_results(const StepKernelArgs &a, bool va
     const bool done = has && (o.info >> 31) != 0;      // FLAG_EPISODE_DONE: the host wants the fresh board
     const bool use_dict = a.c_dict != nullptr;          // kernel-uniform
     uint32_t code = DICT_ESCAPE;
-    if (use_dict && has) code = dict_lookup(a.c_dict, a.c_dict_mask, o.reward, o.info);
+    if (use_dict && has) code = dict_lookup(a.c_dict, a.c_dict_mask, o.reward, o.info, first_slot);
     const bool esc = has && code == DICT_ESCAPE;
     const unsigned bh = __ballot_sync(0xFFFFFFFFu, has), bd = __ballot_sync(0xFFFFFFFFu, done),
                    be = __ballot_sync(0xFFFFFFFFu, esc);
@@ -295,13 +303,17 @@ __global__ void __launch_bounds__(BLOCK, step_min_ctas<G, AR>()) step_obs_kernel
         if (a.state_copy) StateIO<G>::store(a.state_copy, i, s.b, s.meta);
         if (a.consumed16) a.consumed16[i] = (uint16_t)(o.consumed > 0xFFFF ? 0xFFFF : o.consumed);
     }
+    uint4 first_slot = make_uint4(0, 0, 0, 0xFFFFFFFFu);
+    if constexpr (COMPACT) {
+        if (a.c_dict && valid && o.info != 0) first_slot = dict_first(a.c_dict, a.c_dict_mask, o.reward, o.info);
+    }
     const int64_t warp0 = i - (threadIdx.x & 31);
     if (OBS && warp0 < a.n) {
         const int n_valid = (int)(a.n - warp0 < 32 ? a.n - warp0 : 32);
         emit_obs_any<G>(s, valid, n_valid, obs_stream + (threadIdx.x >> 5) * ObsGeom<G>::WARP_WORDS, obs_sh,
                         obs_warp_ptr<G>(a.obs, warp0, a.obs_dtype), a.obs_dtype);
     }
-    if constexpr (COMPACT) compact_results<G>(a, valid, o, s);
+    if constexpr (COMPACT) compact_results<G>(a, valid, o, s, first_slot);
 }
 
 // T consecutive steps of the in-kernel random policy in one launch: the board stays in registers between
