@@ -696,6 +696,46 @@ def test_host_pipe_compact_results_equal_device_step(pb, rows, cols, n, slab_for
     pipe2.wait(0)
 
 
+def test_full_size_host_pipe_coded_stream_equals_device_step(pb):
+    """BASELINE configs[1] through the host pipe exactly as bench.py's e2e leg runs it -- 2^20 boards, the chunk-major
+    base-6 slab in pinned memory with three eager chunks (54 orbs offered), the dictionary-coded compact stream with a
+    dictionary learned from the first step -- against ppad_step on device buffers, every board, every step."""
+    n, S = 1 << 20, 54
+    rng = np.random.default_rng(7)
+    ref = pb.BatchedPAD(n, 5, 6, seed=99, env0=1 << 33)
+    ref.reset(step=0)
+    env = pb.BatchedPAD(n, 5, 6, seed=99, env0=1 << 33)
+    env.state.copy_(ref.state)
+    pipe = env.host_pipe(slab_orbs=S, compact=True, slab_format="chunks6")
+    obs = torch.zeros((n, 5, 6, 7), dtype=torch.float32, device=env.device)
+    escapes, records, lazy = 0, 0, 0
+    for t in range(1, 9):
+        inj = rng.integers(0, 6, size=(n, S)).astype(np.uint8)
+        if t == 5:
+            inj[:, :] = inj[:, :1]                      # one colour per board: long cascades, reads far past the eager chunks
+        pipe.slab.copy_(torch.from_numpy(pb.layout.pack_slab_chunks6(inj).view(np.int16)))
+        pipe.step(eval_moves=True, auto_reset=(t % 4 == 0), max_moves=6, obs=obs, step=t)
+        want = ref.step(None, eval_moves=True, auto_reset=(t % 4 == 0), max_moves=6, injected=inj, obs='f32', step=t)
+        got = pipe.results()
+        assert torch.equal(env.state, ref.state), t
+        assert np.array_equal(got["action"], want.action.cpu().numpy()), t
+        assert np.array_equal(got["info"], want.info.cpu().numpy().view(np.uint32)), t
+        assert np.array_equal(bits(got["reward"]), bits(want.reward.cpu().numpy())), t
+        assert torch.equal(obs, want.obs), t
+        if t == 1:
+            entries, cover = pipe.learn_dictionary(max_entries=4096)
+            assert entries > 100 and cover > 0.9
+        else:
+            escapes += got["escapes"]
+            records += int((got["info"] != 0).sum())
+            lazy += pipe.h2d_bytes_on_demand(got["info"])
+    # coded and escaped records side by side (the dictionary of step 1 knows neither the one-colour cascades of step 5
+    # nor the flags of the auto-reset steps: those escape, and decode exactly all the same)
+    assert 0 < escapes < 0.8 * records
+    assert lazy > 0                                      # some cascades did read past the 18 eager orbs
+    assert pipe.h2d_bytes() == 6 * n
+
+
 def test_compact_pipe_refuses_what_it_cannot_do(pb):
     env = pb.BatchedPAD(1000, seed=1)
     env.reset(step=0)
