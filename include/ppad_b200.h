@@ -94,9 +94,13 @@ typedef enum ppad_obs_dtype { PPAD_OBS_F32 = 0, PPAD_OBS_U8 = 1 } ppad_obs_dtype
  *                      the six skyfall colours 0..5 in 15.5 of 16 bits.  slab_words = chunks per board, n_inj <= 6 *
  *                      slab_words, slab_stride >= n in uint16 units, slab_eager 1..8 (default 3: 18 orbs, 6 bytes per
  *                      board).  A chunk value >= 46656 is no encoding: flagged PPAD_FLAG_UNSUPPORTED_ORB.
+ *   PPAD_SLAB_CHUNKS6T the same uint16 chunks, chunk-major per TILE of 256 boards: chunk c of board i =
+ *                      ((const uint16_t *)slab)[((i / 256) * slab_words + c) * 256 + i % 256]; the buffer holds
+ *                      ceil(n / 256) * slab_words * 256 elements and is 16-byte aligned; slab_stride is ignored.  The
+ *                      eager chunks of a CTA's 256 boards are one contiguous block: full 128-byte lines across PCIe.
  * A code that is no orb type of the context (>= 7, or >= 10 with orb_bits = 4) is flagged PPAD_FLAG_UNSUPPORTED_ORB. */
 typedef enum ppad_slab_format {
-    PPAD_SLAB_NIBBLES = 0, PPAD_SLAB_PLANES3 = 1, PPAD_SLAB_CHUNKS10 = 2, PPAD_SLAB_CHUNKS6 = 3
+    PPAD_SLAB_NIBBLES = 0, PPAD_SLAB_PLANES3 = 1, PPAD_SLAB_CHUNKS10 = 2, PPAD_SLAB_CHUNKS6 = 3, PPAD_SLAB_CHUNKS6T = 4
 } ppad_slab_format;
 
 /* Environment constants: the keyword arguments of PAD.__init__ (game.py:39-50) that reach the hot path. */

@@ -15,9 +15,10 @@ FLAG_BAD_ACTION, FLAG_RESET_CAP, FLAG_UNSUPPORTED_ORB, FLAG_EPISODE_DONE = 0x10,
 I8, I32, I64 = 1, 4, 8
 OBS_F32, OBS_U8 = 0, 1
 SELECT_MAX, SELECT_BOLTZMANN = 0, 1
-SLAB_NIBBLES, SLAB_PLANES3, SLAB_CHUNKS10, SLAB_CHUNKS6 = 0, 1, 2, 3
-SLAB_FORMATS = {'nibbles': SLAB_NIBBLES, 'planes3': SLAB_PLANES3, 'chunks10': SLAB_CHUNKS10, 'chunks6': SLAB_CHUNKS6}
-CHUNK_MAJOR = {'chunks10': (10, 4, 2), 'chunks6': (6, 2, 3)}   # orbs per chunk, bytes per chunk, default eager chunks
+SLAB_NIBBLES, SLAB_PLANES3, SLAB_CHUNKS10, SLAB_CHUNKS6, SLAB_CHUNKS6T = 0, 1, 2, 3, 4
+SLAB_FORMATS = {'nibbles': SLAB_NIBBLES, 'planes3': SLAB_PLANES3, 'chunks10': SLAB_CHUNKS10, 'chunks6': SLAB_CHUNKS6,
+                'chunks6t': SLAB_CHUNKS6T}
+CHUNK_MAJOR = {'chunks10': (10, 4, 2), 'chunks6': (6, 2, 3), 'chunks6t': (6, 2, 3)}   # orbs per chunk, bytes per chunk, default eager chunks
 ABI_VERSION = 4
 
 

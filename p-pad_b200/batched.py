@@ -92,17 +92,22 @@ class BatchedPAD:
             return None, 0, 0
         if isinstance(injected, tuple):
             slab, n_inj = injected[0], injected[1]
-            slab = self._dev(slab, torch.int16 if fmt == 'chunks6' else torch.int32)
-            return slab, slab.shape[0 if fmt in _cabi.CHUNK_MAJOR else 1], int(n_inj)
+            slab = self._dev(slab, torch.int16 if fmt in ('chunks6', 'chunks6t') else torch.int32)
+            return slab, slab.shape[1 if fmt == 'chunks6t' else (0 if fmt in _cabi.CHUNK_MAJOR else 1)], int(n_inj)
         orbs = self._dev(injected, torch.uint8)
         n, s = orbs.shape
-        if fmt == 'chunks6':
+        if fmt in ('chunks6', 'chunks6t'):
             chunks = max(1, (s + 5) // 6)
             pad = torch.zeros((n, chunks * 6), dtype=torch.int64, device=self.device)
             pad[:, :s] = orbs
             word = (pad.view(n, chunks, 6) * (6 ** torch.arange(6, device=self.device, dtype=torch.int64))).sum(dim=2)
-            word = torch.where(word >= 2 ** 15, word - 2 ** 16, word)          # uint16 bit pattern in an int16 tensor
-            return word.to(torch.int16).t().contiguous(), chunks, s
+            word = torch.where(word >= 2 ** 15, word - 2 ** 16, word).to(torch.int16)   # uint16 bit pattern in an int16 tensor
+            if fmt == 'chunks6t':                          # [tiles, chunks, 256]
+                tiles = max(1, (n + 255) // 256)
+                pad2 = torch.zeros((tiles * 256, chunks), dtype=torch.int16, device=self.device)
+                pad2[:n] = word
+                return pad2.view(tiles, 256, chunks).permute(0, 2, 1).contiguous(), chunks, s
+            return word.t().contiguous(), chunks, s
         if fmt == 'chunks10':
             chunks = max(1, (s + 9) // 10)
             pad = torch.zeros((n, chunks * 10), dtype=torch.int64, device=self.device)
@@ -225,7 +230,7 @@ class BatchedPAD:
         slab, words, n_inj = self._slab(injected, slab_format)
         a = _cabi.StepArgs()
         a.slab_format = _cabi.SLAB_FORMATS[slab_format]
-        a.slab_stride = slab.shape[1] if slab is not None and slab_format in _cabi.CHUNK_MAJOR else 0
+        a.slab_stride = slab.shape[-1] if slab is not None and slab_format in _cabi.CHUNK_MAJOR else 0
         a.consumed_out = out.consumed.data_ptr() if want_consumed else None
         a.n, a.env0, a.step = n, self.env0, step
         a.eval_moves, a.auto_reset, a.max_moves = int(bool(eval_moves)), int(bool(auto_reset)), int(max_moves)
@@ -511,7 +516,8 @@ class HostPipe:
         self.slab_orbs = int(slab_orbs)
         self.slab_format = slab_format
         self.slab_words = {'planes3': 3 * ((self.slab_orbs + 31) // 32), 'chunks10': (self.slab_orbs + 9) // 10,
-                           'chunks6': (self.slab_orbs + 5) // 6, 'nibbles': (self.slab_orbs + 7) // 8}[slab_format]
+                           'chunks6': (self.slab_orbs + 5) // 6, 'chunks6t': (self.slab_orbs + 5) // 6,
+                           'nibbles': (self.slab_orbs + 7) // 8}[slab_format]
         self.compact = bool(compact)
         n = venv.n
         self.tiles = (n + TILE - 1) // TILE
@@ -519,8 +525,9 @@ class HostPipe:
         cap = int(venv.lib.ppad_compact_capacity(venv._ctx, n)) if self.compact else 0
         self.buffers = [SimpleNamespace(
             # chunks10 / chunks6 are chunk-major ([W, n], layout.pack_slab_chunks10 / _chunks6); the row formats are [n, W]
-            slab=torch.zeros((max(1, self.slab_words), n) if slab_format in _cabi.CHUNK_MAJOR else (n, max(1, self.slab_words)),
-                             dtype=torch.int16 if slab_format == 'chunks6' else torch.int32, **pin),
+            slab=torch.zeros(((n + 255) // 256, max(1, self.slab_words), 256) if slab_format == 'chunks6t' else
+                             ((max(1, self.slab_words), n) if slab_format in _cabi.CHUNK_MAJOR else (n, max(1, self.slab_words))),
+                             dtype=torch.int16 if slab_format in ('chunks6', 'chunks6t') else torch.int32, **pin),
             actions=torch.zeros(n, dtype=torch.uint8, **pin),
             action=torch.zeros(n, dtype=torch.uint8, **pin),
             reward=torch.zeros(n, dtype=torch.float64, **pin),
@@ -567,7 +574,7 @@ class HostPipe:
         a.slab_host = b.slab.data_ptr() if use_slab and self.slab_words else None
         a.slab_words, a.n_inj = self.slab_words, self.slab_orbs
         a.slab_format = _cabi.SLAB_FORMATS[self.slab_format]
-        a.slab_stride = b.slab.shape[1] if self.slab_format in _cabi.CHUNK_MAJOR else 0
+        a.slab_stride = b.slab.shape[-1] if self.slab_format in _cabi.CHUNK_MAJOR else 0
         a.slab_eager = self.slab_eager
         if self.compact:
             a.results_compact = 2 if self._dict is not None else 1
@@ -650,7 +657,8 @@ class HostPipe:
         slab = self.slab.numel() * 4
         if self.slab_format in _cabi.CHUNK_MAJOR:
             per, size, default = _cabi.CHUNK_MAJOR[self.slab_format]
-            slab = min(self.slab_eager or default, self.slab_words) * self.slab.shape[1] * size
+            boards = self.slab.shape[0] * 256 if self.slab_format == 'chunks6t' else self.slab.shape[1]
+            slab = min(self.slab_eager or default, self.slab_words) * boards * size
         return slab + (self.actions.numel() if use_actions else 0)
 
     def h2d_bytes_on_demand(self, info):

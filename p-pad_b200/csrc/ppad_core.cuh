@@ -393,7 +393,13 @@ PPAD_HD int orb_from_u32(const SkyfallTable &t, uint32_t x)
 // Injected codes that are not orb types of the geometry (>= NT) are handed on as they are and flagged
 // (bad -> FLAG_UNSUPPORTED_ORB).
 // ---------------------------------------------------------------------------------------------
-enum : int { SLAB_NIBBLES = 0, SLAB_PLANES3 = 1, SLAB_CHUNKS10 = 2, SLAB_CHUNKS6 = 3 };
+//   SLAB_CHUNKS6T the same uint16 chunks, chunk-major per TILE of 256 boards instead of over the whole batch: chunk c of
+//                 board i at ((i / 256) * chunks_per_board + c) * 256 + i % 256.  The eager chunks of a CTA's 256
+//                 boards are then ONE contiguous block (1536 bytes for three chunks: twelve full 128-byte lines
+//                 instead of 24 half lines), fetched cooperatively.  To the per-board code it is SLAB_CHUNKS6 with a
+//                 chunk stride of 256.
+// A chunk value >= 6^6 is no encoding and is flagged like a bad code.
+enum : int { SLAB_NIBBLES = 0, SLAB_PLANES3 = 1, SLAB_CHUNKS10 = 2, SLAB_CHUNKS6 = 3, SLAB_CHUNKS6T = 4 };
 PPAD_HD uint32_t div6_u16(uint32_t w) { return (w * 43691u) >> 18; }   // floor(w / 6), exact for w < 65536
 
 struct OrbSource {
@@ -411,13 +417,15 @@ struct OrbSource {
     const uint32_t *eager;  // SLAB_CHUNKS10: the first n_eager chunks of this board (fetched up front by the caller)
     int n_eager;
     int stride;             // SLAB_CHUNKS10: words between consecutive chunks of this board
+    int estride;            // elements between consecutive EAGER chunks of this board where the caller keeps them
 
     PPAD_HD void init(const uint32_t *slab_, int n_inj_, uint32_t stream_, int fmt_ = SLAB_NIBBLES,
-                      const uint32_t *eager_ = nullptr, int n_eager_ = 0, int stride_ = 0)
+                      const uint32_t *eager_ = nullptr, int n_eager_ = 0, int stride_ = 0, int estride_ = 1)
     {
         eager = eager_;
         n_eager = eager_ ? n_eager_ : 0;
         stride = stride_;
+        estride = estride_;
         slab = slab_;
         n_inj = slab_ ? n_inj_ : -1;
         cursor = 0;
@@ -434,7 +442,7 @@ struct OrbSource {
     PPAD_HD uint32_t chunk(int c) const { return c < n_eager ? eager[c] : slab[(size_t)c * (size_t)stride]; }
     PPAD_HD uint32_t chunk16(int c)   // SLAB_CHUNKS6: slab, eager and stride in uint16 units
     {
-        const uint32_t w = c < n_eager ? reinterpret_cast<const uint16_t *>(eager)[c]
+        const uint32_t w = c < n_eager ? reinterpret_cast<const uint16_t *>(eager)[c * estride]
                                        : reinterpret_cast<const uint16_t *>(slab)[(size_t)c * (size_t)stride];
         bad |= w >= 46656u ? 1u : 0u;
         return w;
@@ -977,7 +985,8 @@ struct CascadeItem {
 template <class G>
 PPAD_HD bool cascade_round_m(CascadeItem<G> &it, typename G::W &m, bool skyfall_damage, int cascade_cap, const TeamTable &team, const uint32_t *slab, int n_inj,
                              const RngKey &key, const SkyfallTable &sky, uint16_t *log, int log_cap, int slab_fmt = SLAB_NIBBLES,
-                             const uint32_t *slab_eager = nullptr, int slab_n_eager = 0, int slab_stride = 0)
+                             const uint32_t *slab_eager = nullptr, int slab_n_eager = 0, int slab_stride = 0,
+                             int slab_estride = 1)
 {
     cancel_tally<G>(it.b, m, it.tally, team, log, log_cap);
     it.depth++;
@@ -988,7 +997,7 @@ PPAD_HD bool cascade_round_m(CascadeItem<G> &it, typename G::W &m, bool skyfall_
     }
     drop_board<G>(it.b);
     OrbSource src;
-    src.init(slab, n_inj, STREAM_SKYFALL, slab_fmt, slab_eager, slab_n_eager, slab_stride);
+    src.init(slab, n_inj, STREAM_SKYFALL, slab_fmt, slab_eager, slab_n_eager, slab_stride, slab_estride);
     src.cursor = it.cursor;
     src.exhausted = it.exhausted;
     fill_board<G>(it.b, src, key, sky);
@@ -1128,6 +1137,7 @@ struct StepParams {
     int32_t slab_fmt;   // SLAB_NIBBLES / SLAB_PLANES3 / SLAB_CHUNKS10: layout of the injected skyfall slab of this launch
     int32_t slab_stride;   // SLAB_CHUNKS10: words between consecutive chunks of one board
     int32_t slab_eager;    // SLAB_CHUNKS10: chunks per board the kernel fetches up front (1..4)
+    int32_t slab_estride;  // elements between the eager chunks of one board where the kernel keeps them (1; tile-major: 256)
     DynGeomData dyn;    // board dimensions for GeomDyn (ignored by the specialised geometries)
 };
 
@@ -1343,7 +1353,8 @@ PPAD_HD StepOut step_board(bool live, State<G> &s, Board<G> &final_board, const 
     while (warp_any(cascading)) {
         if (cascading)
             cascading = cascade_round_m<G>(it, m, p.skyfall_damage != 0, p.cascade_cap, p.team, slab, p.n_inj,
-                                           key, p.sky, log, p.log_cap, p.slab_fmt, slab_eager, p.slab_eager, p.slab_stride);
+                                           key, p.sky, log, p.log_cap, p.slab_fmt, slab_eager, p.slab_eager, p.slab_stride,
+                                           p.slab_estride);
         warp_converge();
     }
 #if defined(__CUDA_ARCH__)

@@ -56,17 +56,20 @@ static int launch_step(const ppad_ctx *ctx, const ppad_step_args *args, cudaStre
                        bool stage_host_slab = false, const CompactTarget *compact = nullptr)
 {
     if (!args->state) return fail(PPAD_ERR_INVALID, "ppad_step: null state");
-    const bool chunked = args->slab_format == PPAD_SLAB_CHUNKS10 || args->slab_format == PPAD_SLAB_CHUNKS6;
+    const bool six = args->slab_format == PPAD_SLAB_CHUNKS6 || args->slab_format == PPAD_SLAB_CHUNKS6T;
+    const bool chunked = args->slab_format == PPAD_SLAB_CHUNKS10 || six;
     if (args->slab_format != PPAD_SLAB_NIBBLES && args->slab_format != PPAD_SLAB_PLANES3 && !chunked)
         return fail(PPAD_ERR_INVALID, "ppad_step: unknown slab_format");
     if (args->slab && chunked) {
-        const int per = args->slab_format == PPAD_SLAB_CHUNKS6 ? 6 : 10;
+        const int per = six ? 6 : 10;
         if (ctx->geom >= 3) return fail(PPAD_ERR_UNSUPPORTED, "ppad_step: chunk-major slabs need a context with orb_bits = 3");
         if (args->slab_words <= 0 || args->slab_words > 6000 || args->n_inj < 0 || args->n_inj > args->slab_words * per ||
-            (int64_t)args->slab_stride < args->n)
+            (args->slab_format != PPAD_SLAB_CHUNKS6T && (int64_t)args->slab_stride < args->n))
             return fail(PPAD_ERR_INVALID, "ppad_step: chunk-major slabs need 0 <= n_inj <= orbs per chunk * slab_words and slab_stride >= n");
+        if (args->slab_format == PPAD_SLAB_CHUNKS6T && ((uintptr_t)args->slab & 15))
+            return fail(PPAD_ERR_INVALID, "ppad_step: PPAD_SLAB_CHUNKS6T slab must be 16-byte aligned");
         if (args->paths || args->combo_log) return fail(PPAD_ERR_UNSUPPORTED, "ppad_step: chunk-major slabs with finger paths / combo log");
-        if (args->slab_format == PPAD_SLAB_CHUNKS6 && ((uintptr_t)args->slab & 1))
+        if (six && ((uintptr_t)args->slab & 1))
             return fail(PPAD_ERR_INVALID, "ppad_step: PPAD_SLAB_CHUNKS6 slab must be 2-byte aligned");
     } else if (args->slab && args->slab_format == PPAD_SLAB_PLANES3) {
         if (ctx->geom >= 3) return fail(PPAD_ERR_UNSUPPORTED, "ppad_step: PPAD_SLAB_PLANES3 needs a context with orb_bits = 3");
@@ -90,13 +93,14 @@ static int launch_step(const ppad_ctx *ctx, const ppad_step_args *args, cudaStre
     a.p.slab_words = args->slab_words;
     a.p.log_cap = args->log_cap;
     a.p.slab_fmt = args->slab_format;
-    a.p.slab_stride = chunked ? args->slab_stride : 0;
+    a.p.slab_stride = chunked ? (args->slab_format == PPAD_SLAB_CHUNKS6T ? BLOCK : args->slab_stride) : 0;
     a.p.slab_eager = 0;
+    a.p.slab_estride = args->slab_format == PPAD_SLAB_CHUNKS6T ? BLOCK : 1;
     if (args->slab && chunked) {
-        const int most = args->slab_format == PPAD_SLAB_CHUNKS6 ? 8 : 4;   // the eager chunks of a board wait in 16 bytes
+        const int most = six ? 8 : 4;   // the eager chunks of a board wait in 16 bytes
         if (args->slab_eager < 0 || args->slab_eager > most)
             return fail(PPAD_ERR_INVALID, "ppad_step: slab_eager must be 0 (default) or 1..4 (PPAD_SLAB_CHUNKS6: 1..8)");
-        a.p.slab_eager = args->slab_eager ? args->slab_eager : (args->slab_format == PPAD_SLAB_CHUNKS6 ? 3 : 2);
+        a.p.slab_eager = args->slab_eager ? args->slab_eager : (six ? 3 : 2);
         if (a.p.slab_eager > args->slab_words) a.p.slab_eager = args->slab_words;
     }
     if (args->skyfall_damage >= 0) a.p.skyfall_damage = args->skyfall_damage;
@@ -125,7 +129,10 @@ static int launch_step(const ppad_ctx *ctx, const ppad_step_args *args, cudaStre
         if (a.p.slab_fmt == PPAD_SLAB_NIBBLES && a.p.slab_words == 4) a.stage_slab = 1;
         if (a.p.slab_fmt == PPAD_SLAB_PLANES3 && a.p.slab_words == 3) a.stage_slab = 2;
     }
-    if (a.slab && chunked) a.stage_slab = 3;   // the first chunks up front, the rest on demand
+    if (a.slab && chunked) {
+        a.stage_slab = args->slab_format == PPAD_SLAB_CHUNKS6T ? 4 : 3;
+        if (a.stage_slab == 4) a.p.slab_fmt = PPAD_SLAB_CHUNKS6;   // to the per-board code: uint16 chunks, 256 apart
+    }   // the first chunks up front, the rest on demand
     a.c_nibbles = a.c_tile_line = a.c_summary = a.c_counters = nullptr;
     a.c_records = nullptr;
     a.c_capacity = 0;
@@ -146,7 +153,7 @@ static int launch_step(const ppad_ctx *ctx, const ppad_step_args *args, cudaStre
     a.tile_counter = nullptr;
     int choice = ctx->pool_kind == 1 ? STEP_KERNEL_WPOOL : STEP_KERNEL_POOL;
     if (args->obs) choice = STEP_KERNEL_OBS;
-    else if (compact || coalesced_results || a.stage_slab == 3 || (!a.p.eval_moves && !a.actions && !a.paths) || !a.p.skyfall_damage) {
+    else if (compact || coalesced_results || a.stage_slab >= 3 || (!a.p.eval_moves && !a.actions && !a.paths) || !a.p.skyfall_damage) {
         // results go straight to host memory: the pooled kernel's scattered 8-byte result writes would become tiny
         // PCIe transactions, one thread per board writes them as full lines.
         // Steps of the in-kernel random policy that only evaluate passes (eval_moves = 0, no actions given: plain
@@ -351,7 +358,7 @@ int ppad_pipe_step(ppad_pipe *p, const ppad_host_step_args *h, void *after_strea
     // by the kernels -- no PCIe read sits inside a kernel, which matters on hosts whose read latency is high
     const bool hybrid = zc && p->zero_copy == 2;
     const int mode = zc && !hybrid ? 1 : 2;
-    if (h->slab_host && (h->slab_format == PPAD_SLAB_CHUNKS10 || h->slab_format == PPAD_SLAB_CHUNKS6) && mode != 1)
+    if (h->slab_host && h->slab_format >= PPAD_SLAB_CHUNKS10 && mode != 1)
         return fail(PPAD_ERR_UNSUPPORTED, "ppad_pipe_step: chunk-major slabs need pinned host buffers and zero-copy mode 1");
     if (p->last_mode && p->last_mode != mode)   // stream <-> board mapping changes: order behind the previous step
         for (int k = 0; k < p->chunks && e == cudaSuccess; k++)

@@ -32,7 +32,7 @@ struct StepKernelArgs {
     int32_t stage_slab;   // the slab is pinned HOST memory (zero copy): fetch each row once, up front.  1: 4 words per
                           // board, one uint4 per thread; 2: 3 words per board, the CTA's 3072 contiguous bytes cooperatively;
                           // 3: SLAB_CHUNKS10 (host or device memory): the first p.slab_eager chunks up front, further
-                          // chunks when the cascade asks
+                          // chunks when the cascade asks; 4: SLAB_CHUNKS6T: the same, the CTA's eager block cooperatively
     uint32_t *tile_counter;   // DEVICE [2]: {next tile, CTAs finished} of the warp-pool kernel; both 0 before the launch and
                               // left at 0 by the last CTA to finish (no memset between launches)
     // compact result stream (COMPACT instantiations: the host pipe), see include/ppad_b200.h ppad_host_step_args
@@ -262,6 +262,17 @@ __global__ void __launch_bounds__(BLOCK, step_min_ctas<G, AR>()) step_obs_kernel
             }
             slab_rows[threadIdx.x] = make_uint4(w[0], w[1], w[2], w[3]);
             slab_eager = reinterpret_cast<const uint32_t *>(&slab_rows[threadIdx.x]);
+        }
+    } else if (a.stage_slab == 4) {   // kernel-uniform
+        // tile-major uint16 chunks: the eager chunks of the CTA's 256 boards are 512 * slab_eager contiguous bytes
+        const uint16_t *tile = reinterpret_cast<const uint16_t *>(a.slab) + (size_t)blockIdx.x * (size_t)a.p.slab_words * BLOCK;
+        if ((int)threadIdx.x < 32 * a.p.slab_eager) slab_rows[threadIdx.x] = __ldg(reinterpret_cast<const uint4 *>(tile) + threadIdx.x);
+        __syncthreads();
+        if (valid) {
+            slab = reinterpret_cast<const uint32_t *>(tile + threadIdx.x);
+            slab_eager = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint16_t *>(slab_rows) + threadIdx.x);
+        } else {
+            slab = nullptr;
         }
     } else if (a.stage_slab == 1) {
         // Zero copy: the skyfall slab lives in pinned host memory.  The cascade reads its words lazily, which over

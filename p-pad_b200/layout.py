@@ -136,6 +136,17 @@ def pack_slab_chunks6(orbs, stride=None):
     return out
 
 
+def pack_slab_chunks6t(orbs):
+    """uint8 [n, S] orb sequence (colours 0..5) -> uint16 [ceil(n / 256), ceil(S / 6), 256] tile-major slab
+    (PPAD_SLAB_CHUNKS6T): out[i // 256, c, i % 256] = sum_k orb[i, 6 c + k] * 6^k."""
+    flat = pack_slab_chunks6(orbs)                       # [chunks, n]
+    chunks, n = flat.shape
+    tiles = max(1, (n + 255) // 256)
+    pad = np.zeros((chunks, tiles * 256), np.uint16)
+    pad[:, :n] = flat
+    return np.ascontiguousarray(pad.reshape(chunks, tiles, 256).transpose(1, 0, 2))
+
+
 TILE = 256   # boards per tile of the compact result stream (= CTA size of the step kernel)
 
 

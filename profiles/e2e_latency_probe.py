@@ -57,7 +57,8 @@ def run(fmt, orbs, with_obs=True, reps=60, eager=0, dict_entries=0):
     del pipe, env
 
 
-for rep in range(2):
+for rep in range(3):
     run("chunks6", 54, True, reps=100, eager=3, dict_entries=4096)
-    run("chunks10", 50, True, reps=100, eager=2, dict_entries=4096)
-    run("chunks6", 54, False, reps=100, eager=3, dict_entries=4096)
+    run("chunks6t", 54, True, reps=100, eager=3, dict_entries=4096)
+    run("chunks6t", 54, True, reps=100, eager=4, dict_entries=4096)
+    run("chunks6t", 54, True, reps=100, eager=2, dict_entries=4096)

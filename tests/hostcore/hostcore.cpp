@@ -45,7 +45,7 @@ template <class G>
 void step_batch(const StepParams &base, int64_t n, uint64_t env0, int8_t *boards, int32_t *fingers, uint8_t *prev,
                 uint16_t *moves, const uint8_t *actions, const uint32_t *slab, uint8_t *action_out, double *reward,
                 uint32_t *info, int8_t *final_boards, uint16_t *combo_log, const uint32_t *paths = nullptr,
-                int path_words = 0, const uint16_t *path_lens = nullptr)
+                int path_words = 0, const uint16_t *path_lens = nullptr, bool tile_major = false)
 {
     for (int64_t i = 0; i < n; i++) {
         State<G> s;
@@ -56,11 +56,13 @@ void step_batch(const StepParams &base, int64_t n, uint64_t env0, int8_t *boards
         Board<G> fin;
         // SLAB_CHUNKS10 is chunk-major: board i starts at slab + i, its chunks lie slab_stride words apart, and the
         // first slab_eager chunks are handed over as a copy (what the step kernel does with the lines it fetches up front)
+        // (SLAB_CHUNKS6T, tile-major, is SLAB_CHUNKS6 to the per-board code: see hostcore_step_batch)
         const bool chunked = base.slab_fmt == SLAB_CHUNKS10 || base.slab_fmt == SLAB_CHUNKS6;
         const uint32_t *row = slab ? slab + (chunked ? (size_t)i : (size_t)i * base.slab_words) : nullptr;
         uint32_t eager[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
         if (base.slab_fmt == SLAB_CHUNKS6 && slab) {   // uint16 chunks
-            const uint16_t *r16 = reinterpret_cast<const uint16_t *>(slab) + i;
+            const uint16_t *r16 = reinterpret_cast<const uint16_t *>(slab) +
+                                  (tile_major ? (size_t)(i / 256) * base.slab_words * 256 + (size_t)(i % 256) : (size_t)i);
             row = reinterpret_cast<const uint32_t *>(r16);
             for (int c = 0; c < base.slab_eager; c++)
                 reinterpret_cast<uint16_t *>(eager)[c] = r16[(size_t)c * (size_t)base.slab_stride];
@@ -177,14 +179,17 @@ int hostcore_step_batch(const ppad_config *cfg, int64_t n, uint64_t env0, uint32
     p.max_moves = max_moves;
     p.n_inj = slab ? n_inj : -1;
     p.slab_words = slab_words;
+    const bool tile_major = slab_format == SLAB_CHUNKS6T;      // what launch_step does: uint16 chunks, 256 apart
+    if (tile_major) p.slab_fmt = slab_format = SLAB_CHUNKS6;
     const bool chunk_major = slab_format == SLAB_CHUNKS10 || slab_format == SLAB_CHUNKS6;
-    p.slab_stride = chunk_major ? (int32_t)n : 0;
+    p.slab_stride = chunk_major ? (tile_major ? 256 : (int32_t)n) : 0;
+    p.slab_estride = 1;
     const int eager = slab_format == SLAB_CHUNKS6 ? 3 : 2;
     p.slab_eager = chunk_major ? (slab_words < eager ? slab_words : eager) : 0;
     p.log_cap = log_cap;
     dyn_geom() = p.dyn;
     HC_DISPATCH(geom, (step_batch<G>(p, n, env0, boards, fingers, prev, moves, actions, slab, action_out, reward, info,
-                                     final_boards, combo_log, paths, path_words, path_lens)));
+                                     final_boards, combo_log, paths, path_words, path_lens, tile_major)));
     return 0;
 }
 

@@ -50,7 +50,8 @@ def step_batch(cfg, boards, fingers, prev, moves=None, actions=None, eval_moves=
     slab = None
     if inj is not None:
         slab = {0: ppad_b200.layout.pack_slab, 1: ppad_b200.layout.pack_slab_planes3,
-                2: ppad_b200.layout.pack_slab_chunks10, 3: ppad_b200.layout.pack_slab_chunks6}[slab_format](inj)
+                2: ppad_b200.layout.pack_slab_chunks10, 3: ppad_b200.layout.pack_slab_chunks6,
+                4: ppad_b200.layout.pack_slab_chunks6t}[slab_format](inj)
     if actions is not None:
         actions = np.ascontiguousarray(actions, np.uint8)
     packed = None
@@ -64,7 +65,7 @@ def step_batch(cfg, boards, fingers, prev, moves=None, actions=None, eval_moves=
     r = lib().hostcore_step_batch(
         C.byref(cfg), C.c_int64(n), C.c_uint64(env0), C.c_uint32(step), _p(boards), _p(fingers), _p(prev), _p(moves),
         _p(actions), int(bool(eval_moves)), int(bool(auto_reset)), int(max_moves), _p(slab),
-        (slab.shape[0] if slab_format in (2, 3) else slab.shape[1]) if slab is not None else 0,
+        (slab.shape[0] if slab_format in (2, 3) else slab.shape[1]) if slab is not None else 0,   # chunks / words per board
         inj.shape[1] if inj is not None else 0, _p(action_out), _p(reward),
         _p(info), _p(final), _p(log), log_cap, _p(packed), packed.shape[1] if packed is not None else 0, _p(path_lens),
         int(slab_format))

@@ -595,7 +595,7 @@ def test_host_pipe_equals_device_step(pb, rows, cols, n, zero_copy):
     assert torch.equal(env.state, ref.state)
 
 
-@pytest.mark.parametrize("slab_format", ["planes3", "nibbles", "chunks10", "chunks6"])
+@pytest.mark.parametrize("slab_format", ["planes3", "nibbles", "chunks10", "chunks6", "chunks6t"])
 @pytest.mark.parametrize("rows,cols,n", [(5, 6, 100_000 + 37), (6, 7, 33_333), (5, 6, 200), (4, 5, 256), (5, 6, 1)])
 def test_host_pipe_compact_results_equal_device_step(pb, rows, cols, n, slab_format):
     """The compact result stream of ppad_pipe_step (action nibbles + records only for boards whose info word is not 0 +
@@ -607,11 +607,13 @@ def test_host_pipe_compact_results_equal_device_step(pb, rows, cols, n, slab_for
     env = pb.BatchedPAD(n, rows, cols, seed=23, env0=5)
     env.state.copy_(ref.state)
     # chunks10: the chunk-major slab the kernel reads on demand from pinned host memory (50 orbs offered per board)
-    S = {"chunks10": 50, "chunks6": 54}.get(slab_format, 32)
+    S = {"chunks10": 50, "chunks6": 54, "chunks6t": 54}.get(slab_format, 32)
     pipe = env.host_pipe(slab_orbs=S, compact=True, slab_format=slab_format)
-    assert tuple(pipe.slab.shape) == {"planes3": (n, 3), "nibbles": (n, 4), "chunks10": (5, n), "chunks6": (9, n)}[slab_format]
+    assert tuple(pipe.slab.shape) == {"planes3": (n, 3), "nibbles": (n, 4), "chunks10": (5, n), "chunks6": (9, n),
+                                     "chunks6t": ((n + 255) // 256, 9, 256)}[slab_format]
     pack = {"planes3": pb.layout.pack_slab_planes3, "nibbles": pb.layout.pack_slab,
-            "chunks10": pb.layout.pack_slab_chunks10, "chunks6": pb.layout.pack_slab_chunks6}[slab_format]
+            "chunks10": pb.layout.pack_slab_chunks10, "chunks6": pb.layout.pack_slab_chunks6,
+            "chunks6t": pb.layout.pack_slab_chunks6t}[slab_format]
     obs = torch.zeros((n, rows, cols, 7), dtype=torch.float32, device=env.device)
     mirror = pb.layout.unpack_state(ref.state.cpu().numpy().view(np.uint32), rows, cols)   # host copy of boards, fingers
     hb, hf = mirror[0].copy(), mirror[1].copy()
@@ -621,7 +623,7 @@ def test_host_pipe_compact_results_equal_device_step(pb, rows, cols, n, slab_for
         acts = rng.integers(0, 5, size=n).astype(np.uint8)
         if t == 5:
             acts[: n // 2] = 4                      # many passes: many resets, many state records
-        pipe.slab.copy_(torch.from_numpy(pack(inj).view(np.int16 if slab_format == "chunks6" else np.int32)))
+        pipe.slab.copy_(torch.from_numpy(pack(inj).view(np.int16 if slab_format.startswith("chunks6") else np.int32)))
         pipe.actions.copy_(torch.from_numpy(acts))
         use_actions = t % 2 == 1
         auto_reset = t % 3 != 0
@@ -698,7 +700,7 @@ def test_host_pipe_compact_results_equal_device_step(pb, rows, cols, n, slab_for
 
 def test_full_size_host_pipe_coded_stream_equals_device_step(pb):
     """BASELINE configs[1] through the host pipe exactly as bench.py's e2e leg runs it -- 2^20 boards, the chunk-major
-    base-6 slab in pinned memory with three eager chunks (54 orbs offered), the dictionary-coded compact stream with a
+    base-6 slab (tile-major) in pinned memory with three eager chunks (54 orbs offered), the dictionary-coded compact stream with a
     dictionary learned from the first step -- against ppad_step on device buffers, every board, every step."""
     n, S = 1 << 20, 54
     rng = np.random.default_rng(7)
@@ -706,14 +708,14 @@ def test_full_size_host_pipe_coded_stream_equals_device_step(pb):
     ref.reset(step=0)
     env = pb.BatchedPAD(n, 5, 6, seed=99, env0=1 << 33)
     env.state.copy_(ref.state)
-    pipe = env.host_pipe(slab_orbs=S, compact=True, slab_format="chunks6")
+    pipe = env.host_pipe(slab_orbs=S, compact=True, slab_format="chunks6t")
     obs = torch.zeros((n, 5, 6, 7), dtype=torch.float32, device=env.device)
     escapes, records, lazy = 0, 0, 0
     for t in range(1, 9):
         inj = rng.integers(0, 6, size=(n, S)).astype(np.uint8)
         if t == 5:
             inj[:, :] = inj[:, :1]                      # one colour per board: long cascades, reads far past the eager chunks
-        pipe.slab.copy_(torch.from_numpy(pb.layout.pack_slab_chunks6(inj).view(np.int16)))
+        pipe.slab.copy_(torch.from_numpy(pb.layout.pack_slab_chunks6t(inj).view(np.int16)))
         pipe.step(eval_moves=True, auto_reset=(t % 4 == 0), max_moves=6, obs=obs, step=t)
         want = ref.step(None, eval_moves=True, auto_reset=(t % 4 == 0), max_moves=6, injected=inj, obs='f32', step=t)
         got = pipe.results()

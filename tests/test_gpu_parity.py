@@ -133,7 +133,7 @@ def test_episode_golden_vectors(pb, tag, rows, cols):
 @pytest.mark.parametrize("rows,cols", [(4, 5), (5, 6), (6, 7)])
 @pytest.mark.parametrize("mode", ["injected", "philox", "injected_short", "no_skyfall", "wide_injected", "wide_philox",
                                   "wide3_philox", "planes3_injected", "planes3_short", "chunks10_injected",
-                                  "chunks10_short", "chunks6_injected", "chunks6_short"])
+                                  "chunks10_short", "chunks6_injected", "chunks6_short", "chunks6t_injected"])
 def test_step_fuzz_vs_oracle(pb, rows, cols, mode):
     """wide_*: the 4-bit kernels with all ten orb types of game.py:236-246 in the boards, the skyfall rates and the
     injected sequences; wide3_philox: the 4-bit kernels on a workload of the 3-bit ones"""
@@ -157,10 +157,10 @@ def test_step_fuzz_vs_oracle(pb, rows, cols, mode):
     assert not env.set_state(boards, fingers).any()
     S = {"injected": 256, "philox": 0, "injected_short": 8, "no_skyfall": 16, "wide_injected": 256, "wide_philox": 0,
          "wide3_philox": 0, "planes3_injected": 96, "planes3_short": 40, "chunks10_injected": 95, "chunks10_short": 23,
-         "chunks6_injected": 95, "chunks6_short": 23}[mode]
+         "chunks6_injected": 95, "chunks6_short": 23, "chunks6t_injected": 95}[mode]
     # PPAD_SLAB_PLANES3: bit-sliced 3-bit slab; PPAD_SLAB_CHUNKS10: chunk-major, ten orbs per word, read on demand
     # PPAD_SLAB_CHUNKS6: chunk-major, six base-6 orbs per uint16
-    fmt = {"planes3": 'planes3', "chunks10": 'chunks10', "chunks6": 'chunks6'}.get(mode.split("_")[0], 'nibbles')
+    fmt = {"planes3": 'planes3', "chunks10": 'chunks10', "chunks6": 'chunks6', "chunks6t": 'chunks6t'}.get(mode.split("_")[0], 'nibbles')
     for t in range(steps):
         inj = rng.integers(0, 10 if all10 else 6, size=(n, S)).astype(np.uint8) if S else None
         actions = None if t % 3 == 2 else rng.integers(0, 6, size=n).astype(np.uint8)   # 5 = PPAD_NOOP

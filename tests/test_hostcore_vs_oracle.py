@@ -59,7 +59,7 @@ def test_cancel_and_drop_fuzz(rows, cols, kind, orb_bits):
 @pytest.mark.parametrize("rows,cols", [(4, 5), (5, 6), (6, 7)])
 @pytest.mark.parametrize("mode", ["injected", "philox", "injected_short", "no_skyfall", "wide_injected", "wide_philox",
                                   "wide3_injected", "planes3_injected", "planes3_short", "chunks10_injected",
-                                  "chunks10_short", "chunks6_injected", "chunks6_short"])
+                                  "chunks10_short", "chunks6_injected", "chunks6_short", "chunks6t_injected"])
 def test_step_batch_fuzz(rows, cols, mode):
     """wide_*: the 4-bit kernels with all ten orb types (skyfall rates and injected orbs for types 7..9);
     wide3_injected: the 4-bit kernels on a workload the 3-bit kernels also run;
@@ -82,8 +82,8 @@ def test_step_batch_fuzz(rows, cols, mode):
     mine = [boards.copy(), fingers.copy(), prev.copy(), moves.copy()]
     S = {"injected": 256, "philox": 0, "injected_short": 8, "no_skyfall": 16, "wide_injected": 256, "wide_philox": 0,
          "wide3_injected": 256, "planes3_injected": 96, "planes3_short": 40,
-         "chunks10_injected": 95, "chunks10_short": 23, "chunks6_injected": 95, "chunks6_short": 23}[mode]
-    fmt = 1 if mode.startswith("planes3") else (2 if mode.startswith("chunks10") else (3 if mode.startswith("chunks6") else 0))
+         "chunks10_injected": 95, "chunks10_short": 23, "chunks6_injected": 95, "chunks6_short": 23, "chunks6t_injected": 95}[mode]
+    fmt = {"planes3": 1, "chunks10": 2, "chunks6": 3, "chunks6t": 4}.get(mode.split("_")[0], 0)
     top = 10 if sky else 6
     seen_flags = 0
     for t in range(steps):
