@@ -400,7 +400,7 @@ def test_full_size_one_million_boards(pb):
     for t in range(1, T + 1):
         inj = rng.integers(0, 6, size=(n, 32)).astype(np.uint8)
         before = env.state.clone()
-        fmt = ('planes3', 'nibbles', 'chunks6', 'chunks10')[t % 4]   # all four slab layouts
+        fmt = ('planes3', 'nibbles', 'chunks6', 'chunks10', 'chunks6t')[t % 5]   # all five slab layouts
         o = env.step(None, eval_moves=True, injected=inj, step=t, obs='f32', slab_format=fmt)
         a0, r0, i0, _ = orc.step_batch(ocfg, boards, fingers, prev, moves, actions=None, inj=inj, step=t,
                                        threads=os.cpu_count() or 1)
