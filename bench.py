@@ -50,12 +50,12 @@ ROWS, COLS = 5, 6
 SLAB_ORBS = 32
 SLAB_FORMAT = 'planes3'          # PPAD_SLAB_PLANES3: 3 bits per orb, 12 bytes per 32 orbs
 SLAB_BYTES = 12
-# the e2e leg (host buffers): the host OFFERS 54 orbs per board-step as a chunk-major slab (PPAD_SLAB_CHUNKS6T: six base-6
-# orbs per uint16, chunk-major per tile of 256 boards, 18 B per board in pinned memory); the kernel fetches the first three
-# chunks of every board (6 B; one contiguous 1536-byte block per CTA) and a later chunk only for the boards whose cascade
-# draws more than 18 orbs (about 7 in 1000)
+# the e2e leg (host buffers): the host OFFERS 54 orbs per board-step as a chunk-major slab (PPAD_SLAB_CHUNKS6: six base-6
+# orbs per uint16, 18 B per board in pinned memory); the kernel fetches the first three chunks of every board (6 B) and a
+# later chunk only for the boards whose cascade draws more than 18 orbs (about 7 in 1000).  (The tile-major variant
+# PPAD_SLAB_CHUNKS6T is 2 % faster on one GPU and 10 % slower on eight: profiles/r02ao_e2e_multi_8gpu.txt.)
 E2E_SLAB_ORBS = 54
-E2E_SLAB_FORMAT = 'chunks6t'
+E2E_SLAB_FORMAT = 'chunks6'
 E2E_DICT_ENTRIES = 4096
 N_SLABS = 16
 SEED = 20181019
@@ -703,9 +703,8 @@ def main():
                     "checked": "the decoded stream of one more step equals ppad_step on device buffers bit for bit "
                                "(reward, info, action, state), in this run",
                     "note": "HostPipe.step (ppad_pipe_step), synchronous, zero copy.  In: the host offers 54 skyfall orbs "
-                            "per board in pinned memory (six base-6 orbs per uint16, chunk-major per tile of 256 boards); the "
-                            "kernel fetches the first three chunks of every board (18 orbs, 6 B: one contiguous block per "
-                            "CTA) and later chunks only where a cascade gets "
+                            "per board in pinned memory (chunk-major, six base-6 orbs per uint16); the kernel fetches the "
+                            "first three chunks of every board (18 orbs, 6 B) and later chunks only where a cascade gets "
                             "that far (h2d_bytes_on_demand, counted from the consumed counts in 32-byte sectors).  Out: the compact "
                             "result stream in pinned memory: 4 bits per board (action + has-record); a board whose info "
                             "word is not 0 (the others have reward 0 and info 0 by definition) adds a 16-bit code when "

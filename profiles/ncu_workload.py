@@ -24,8 +24,8 @@ slabs = [env._slab(torch.randint(0, 6, (n, 32), device=dev, dtype=torch.uint8, g
 out = env.step(None, eval_moves=True, injected=(slabs[0], 32), slab_format='planes3', obs='f32', step=1)
 for t in range(2, 40):
     env.step(None, eval_moves=True, injected=(slabs[t & 3], 32), slab_format='planes3', obs=out.obs, step=t, out=out)
-pipe = env.host_pipe(slab_orbs=54, compact=True, slab_format='chunks6t')
-pipe.slab.copy_(env._slab(torch.randint(0, 6, (n, 54), device=dev, dtype=torch.uint8, generator=gen), 'chunks6t')[0].cpu())
+pipe = env.host_pipe(slab_orbs=54, compact=True, slab_format='chunks6')
+pipe.slab.copy_(env._slab(torch.randint(0, 6, (n, 54), device=dev, dtype=torch.uint8, generator=gen), 'chunks6')[0].cpu())
 pipe.step(eval_moves=True, obs=out.obs, step=40, wait=True)
 pipe.learn_dictionary(max_entries=4096)
 for t in range(3):
