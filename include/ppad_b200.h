@@ -286,7 +286,9 @@ typedef struct ppad_host_step_args {
 } ppad_host_step_args;
 /* bytes of records_host that can never overflow for n boards (with or without auto_reset, with or without a dictionary) */
 int64_t ppad_compact_capacity(const ppad_ctx *ctx, int64_t n);
-/* The dictionary of results_compact = 2: `count` (<= PPAD_DICT_MAX) pairs (rewards[i], infos[i]), typically the most
+/* The dictionary of results_compact = 2 -- a transport coding of what PAD.step appends to env.rewards (game.py:357-362)
+ * and of the counters calculate_reward keeps (game.py:364-405); nothing of the game is decided by it: `count`
+ * (<= PPAD_DICT_MAX) pairs (rewards[i], infos[i]), typically the most
  * frequent pairs of an earlier step's results (the host learns them; the library never guesses).  Code i of the stream
  * means pair i of THIS call's arrays: keep them for decoding.  A pair the hash table cannot place (more than 8
  * collisions in a row at load factor 1/4: practically never) simply keeps escaping.  Waits for the steps already
