@@ -749,6 +749,42 @@ def test_compact_pipe_refuses_what_it_cannot_do(pb):
         wide.host_pipe(compact=True, slab_format="planes3").step(eval_moves=True)
 
 
+def test_chunk_major_slabs_argument_checks_and_bad_chunks(pb):
+    """The chunk-major slab formats refuse what they cannot do (4-bit contexts, finger paths, a stride shorter than the
+    batch, too many eager chunks, the dictionary mode without a dictionary, non-zero-copy pipes) and flag a uint16 chunk
+    that is no base-6 encoding like any other bad orb code."""
+    n = 3000
+    env = pb.BatchedPAD(n, seed=1)
+    env.reset(step=0)
+    orbs = np.random.default_rng(0).integers(0, 6, size=(n, 30)).astype(np.uint8)
+    good = torch.from_numpy(pb.layout.pack_slab_chunks6(orbs).view(np.int16))
+    with pytest.raises(pb._cabi.PPADError, match="slab_stride >= n"):
+        env.step(None, eval_moves=True, injected=(good[:, :n - 1].contiguous(), 30), slab_format='chunks6')
+    with pytest.raises(pb._cabi.PPADError, match="finger paths"):
+        env.step(None, eval_moves=True, injected=(good, 30), slab_format='chunks6', paths=np.zeros((n, 4), np.uint8))
+    with pytest.raises(pb._cabi.PPADError, match="orb_bits = 3"):
+        wide = pb.BatchedPAD(n, seed=1, orb_bits=4)
+        wide.reset(step=0)
+        wide.step(None, eval_moves=True, injected=(good, 30), slab_format='chunks6')
+    with pytest.raises(ValueError, match="0..5"):
+        pb.layout.pack_slab_chunks6(np.full((4, 6), 6, np.uint8))
+    pipe = env.host_pipe(slab_orbs=30, compact=True, slab_format='chunks6', slab_eager=9)
+    with pytest.raises(pb._cabi.PPADError, match="slab_eager"):
+        pipe.step(eval_moves=True)
+    with pytest.raises(pb._cabi.PPADError, match="zero-copy"):
+        env.host_pipe(slab_orbs=30, slab_format='chunks6', zero_copy=False).step(eval_moves=True)
+    # a chunk >= 6^6 in the first chunk of every second board: flagged on the boards that draw orbs, nowhere else
+    boards = np.zeros((n, 5, 6), np.int8)
+    boards[:, ::2, :] = 1                                  # rows of one colour: every board cascades and draws orbs
+    env.set_state(boards, np.zeros((n, 2), np.int32))
+    bad = good.clone()
+    bad[0, ::2] = -1                                       # 0xFFFF
+    passes = np.full(n, 4, np.uint8)
+    o = env.step(passes, injected=(bad, 30), slab_format='chunks6')
+    flags = o.info.cpu().numpy().view(np.uint32) >> 24
+    assert (flags[::2] & orc.FLAG_UNSUPPORTED_ORB).all() and not (flags[1::2] & orc.FLAG_UNSUPPORTED_ORB).any()
+
+
 def test_replay_push_larger_than_the_ring_keeps_the_last_rows(pb):
     """a push of more rows than the ring holds must not let two rows share a slot."""
     from ppad_b200.replay import ReplayBuffer
