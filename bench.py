@@ -625,7 +625,13 @@ def main():
     wc = warm_by_time(lambda t: pipe_c.step(eval_moves=True, obs=obs_buf, step=t, wait=True), base_t + 70000)
     rows_ms = T.timed(lambda t: pipe_c.step(eval_moves=True, obs=obs_buf, step=t, wait=True), base_t + 70000 + wc, min(e2e_k, 50)) / min(e2e_k, 50)
     rows_bytes = pipe_c.h2d_bytes() + pipe_c.d2h_bytes()
-    del pipe, pipe2, pipe_d, pipe_c
+    # the headline's slab (chunk-major, on demand) with plain 12-byte records: what the dictionary alone is worth
+    pipe_n = env.host_pipe(slab_orbs=E2E_SLAB_ORBS, compact=True, slab_format=E2E_SLAB_FORMAT)
+    pipe_n.slab.copy_(e2e_slabs[0])
+    wn = warm_by_time(lambda t: pipe_n.step(eval_moves=True, obs=obs_buf, step=t, wait=True), base_t + 80000)
+    nodict_ms = T.timed(lambda t: pipe_n.step(eval_moves=True, obs=obs_buf, step=t, wait=True), base_t + 80000 + wn, min(e2e_k, 50)) / min(e2e_k, 50)
+    nodict_bytes = pipe_n.h2d_bytes() + pipe_n.h2d_bytes_on_demand(pipe_n.results()["info"]) + pipe_n.d2h_bytes()
+    del pipe, pipe2, pipe_d, pipe_c, pipe_n
 
     stats = pdist.gather_stats(pdist.local_stats(out.reward, out.info))
 
@@ -715,6 +721,9 @@ def main():
                             "fp32 one-hot obs stays in HBM for the device-side agent",
                     "two_steps_in_flight": {"value": total * e2e_k / (e2e_async_ms * 1e-3), "unit": "steps/s",
                                             "ms_per_step": e2e_async_ms / e2e_k},
+                    "without_dictionary": {"value": total / (nodict_ms * 1e-3), "unit": "steps/s", "ms_per_step": nodict_ms,
+                                           "bytes_per_board_step": nodict_bytes / n,
+                                           "note": "the same slab, every record as its 12 bytes (results_compact = 1)"},
                     "row_slab_plain_records": {"value": total / (rows_ms * 1e-3), "unit": "steps/s", "ms_per_step": rows_ms,
                                                "bytes_per_board_step": rows_bytes / n,
                                                "note": "12-byte slab rows (32 orbs) + 12-byte records, no dictionary"},
