@@ -13,7 +13,7 @@ import torch
 
 from . import _cabi
 from .config import make_config
-from .layout import state_words, decode_compact, TILE
+from .layout import state_words, decode_compact, chunk_bytes_on_demand, TILE
 
 ACTION_NAMES = ['up', 'down', 'left', 'right', 'pass']        # player.py:24
 ACTION_IDS = {name: i for i, name in enumerate(ACTION_NAMES)}  # simulation.py:236
@@ -662,16 +662,12 @@ class HostPipe:
         return slab + (self.actions.numel() if use_actions else 0)
 
     def h2d_bytes_on_demand(self, info):
-        """chunks10: bytes of the chunks beyond the eager ones that the cascades of a step reached, from the consumed
-        counts in its info words (saturating at 255 orbs), counted in 32-byte sectors of 8 neighbouring boards."""
+        """Chunk-major slabs: bytes of the chunks beyond the eager ones that the cascades of a step reached
+        (layout.chunk_bytes_on_demand: from the consumed counts in its info words, in 32-byte sectors)."""
         if self.slab_format not in _cabi.CHUNK_MAJOR:
             return 0
         per, size, default = _cabi.CHUNK_MAJOR[self.slab_format]
-        sector_boards = 32 // size
-        consumed = ((np.asarray(info).view(np.uint32) >> 16) & 0xFF).astype(np.int64)
-        consumed = np.pad(consumed, (0, (-len(consumed)) % sector_boards)).reshape(-1, sector_boards).max(axis=1)
-        eager = min(self.slab_eager or default, self.slab_words)
-        return sum(int((consumed > per * c).sum()) * 32 for c in range(eager, self.slab_words))
+        return chunk_bytes_on_demand(info, per, size, min(self.slab_eager or default, self.slab_words), self.slab_words)
 
     def wait(self, buf=0):
         with torch.cuda.device(self.venv.device):

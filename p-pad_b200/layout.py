@@ -147,6 +147,17 @@ def pack_slab_chunks6t(orbs):
     return np.ascontiguousarray(pad.reshape(chunks, tiles, 256).transpose(1, 0, 2))
 
 
+def chunk_bytes_on_demand(info, orbs_per_chunk, chunk_bytes, eager, chunks):
+    """Bytes of the chunks beyond the `eager` ones that the cascades of one step reached in a chunk-major slab, from the
+    consumed counts in the step's info words (bits 16..23, saturating at 255 orbs): chunk c of a board is read when the
+    board drew more than orbs_per_chunk * c orbs; counted in 32-byte sectors of neighbouring boards (a sector is fetched
+    once however many of its boards ask for it).  Accounting only: no game logic."""
+    sector_boards = 32 // chunk_bytes
+    consumed = ((np.asarray(info).view(np.uint32) >> 16) & 0xFF).astype(np.int64)
+    consumed = np.pad(consumed, (0, (-len(consumed)) % sector_boards)).reshape(-1, sector_boards).max(axis=1)
+    return sum(int((consumed > orbs_per_chunk * c).sum()) * 32 for c in range(eager, chunks))
+
+
 TILE = 256   # boards per tile of the compact result stream (= CTA size of the step kernel)
 
 

@@ -130,6 +130,22 @@ def test_decode_compact_round_trip(n, with_dict):
         assert 0 < got["escapes"] < int((info != 0).sum())
 
 
+def test_chunk_bytes_on_demand_counts_sectors():
+    """the e2e leg's host-to-device accounting for chunk-major slabs: a chunk beyond the eager ones is fetched for a
+    32-byte sector of neighbouring boards when any of them drew far enough"""
+    info = np.zeros(64, np.uint32)
+    assert layout.chunk_bytes_on_demand(info, 6, 2, 3, 9) == 0
+    info[5] = 19 << 16                      # 19 orbs: reaches chunk 3 (orbs 18..23) of a uint16 slab with 3 eager chunks
+    assert layout.chunk_bytes_on_demand(info, 6, 2, 3, 9) == 32
+    info[6] = 25 << 16                      # same sector of 16 boards: chunk 3 once, chunk 4 once
+    assert layout.chunk_bytes_on_demand(info, 6, 2, 3, 9) == 64
+    info[40] = 18 << 16                     # exactly the eager orbs: nothing more
+    assert layout.chunk_bytes_on_demand(info, 6, 2, 3, 9) == 64
+    info[41] = 255 << 16                    # saturated: every chunk the slab has (3..8) in that other sector
+    assert layout.chunk_bytes_on_demand(info, 6, 2, 3, 9) == 64 + 6 * 32
+    assert layout.chunk_bytes_on_demand(info, 10, 4, 2, 5) == 32 * (1 + 3)   # uint32 chunks of 10 orbs, sectors of 8 boards
+
+
 def test_make_config_translates_team_and_skyfall():
     team = [dict(color_1='red', color_2=None, atk=12.5), dict(color_1='dark', color_2='light', atk=3)]
     cfg = ppad_b200.make_config(6, 7, skyfall=[0.5, 0.5, 0, 0, 0, 0, 0, 0, 0, 0], skyfall_damage=False, team=team, seed=(1 << 63) + 5)
