@@ -7,7 +7,8 @@
 Workload (BASELINE.json configs[1]): 2^20 independent 5x6 boards per GPU, one env step per board per
 "step": a uniformly random legal non-reversing move (PlayerAction.sample, in-kernel Philox), the
 orb swap, the full cascade resolution on a copy (cancel -> drop -> skyfall until stable) with the
-skyfall taken from an injected 32-orb slab per board per step (3 bits per orb, 12 bytes), the float64
+skyfall taken from an injected 50-orb slab per board per step (chunk-major, ten 3-bit codes per uint32: the kernel
+reads 8 bytes per board up front and a later chunk only where a cascade draws more than 20 orbs), the float64
 reward, the packed state written back and the fp32 one-hot observation [n,5,6,7] of the new state --
 ONE fused kernel launch.  N > 1: every rank owns its own 2^20-board slab (env ids rank * 2^20 + i); no
 data-path collective (weak scaling).
@@ -16,7 +17,7 @@ Timing: W >= 3 warm-up steps, then EXACTLY K steps between barrier + synchronize
 stream, max over ranks -> `value`.  Because K steps of 0.16 ms are a short region, a steady-state leg of
 >= 0.6 s follows with one CUDA event per step (`steady`: median / p10 / p90 per step) while nvidia-smi is
 sampled every 100 ms (>= 5 samples).  Every step streams 881 MB of obs (7x the 126 MB L2) and the skyfall
-slabs rotate over 16 buffers (201 MB), so no step finds its inputs in L2.
+slabs rotate over 16 buffers (336 MB), so no step finds its inputs in L2.
 
 Sub-records of the same JSON line (all measured in this run, on every rank, max over ranks):
   state_only    the same step without the observation stream (persistent pool kernel), L2 flushed
@@ -47,6 +48,14 @@ sys.path.insert(0, ROOT)
 
 N_LOCAL = 1 << 20
 ROWS, COLS = 5, 6
+# the headline (device-timed) leg: 50 injected orbs per board-step resident in HBM as a chunk-major slab (PPAD_SLAB_CHUNKS10,
+# ten 3-bit codes per uint32, 20 B per board); the kernel reads the first two chunks of every board (8 B) and a later one
+# only where a cascade draws more than 20 orbs.  Faster than the 32-orb row slab it replaces (0.151 against 0.154 ms,
+# profiles/r02av_device_slab_formats.txt) and no board runs past its slab (SURVEY.md section 8d asks for >= 42 orbs).
+OBS_SLAB_ORBS = 50
+OBS_SLAB_FORMAT = 'chunks10'
+OBS_SLAB_BYTES = 8
+# the state-only leg (the pooled kernels read row slabs) and configs[3]: 32 orbs, bit-sliced rows
 SLAB_ORBS = 32
 SLAB_FORMAT = 'planes3'          # PPAD_SLAB_PLANES3: 3 bits per orb, 12 bytes per 32 orbs
 SLAB_BYTES = 12
@@ -60,23 +69,26 @@ E2E_DICT_ENTRIES = 4096
 N_SLABS = 16
 SEED = 20181019
 # algorithmic bytes per board-step (restated in DESIGN.md):
-#   state in 16 + state out 16 + action 1 + reward 8 + info 4 + skyfall slab 12 (32 orbs x 3 bit) = 57; + fp32 obs 840
+#   state in 16 + state out 16 + action 1 + reward 8 + info 4 = 45; + skyfall read: 8 (two eager chunks of the 50-orb slab;
+#   the row slab of the state-only leg: 12); + fp32 obs 840
 BYTES_STATE_ONLY = 45 + SLAB_BYTES
-BYTES_WITH_OBS = BYTES_STATE_ONLY + ROWS * COLS * 7 * 4
+BYTES_WITH_OBS = 45 + OBS_SLAB_BYTES + ROWS * COLS * 7 * 4
 # configs[4] policy step: state 32, q 20, results 13, obs 840, replay ring row 16 + 1 + 8
 BYTES_ROLLOUT = 32 + 20 + 13 + 840 + 25
 
 
 def workload_config(n, world):
     return {"workload": "configs[1]: 2^20 5x6 boards/GPU, random legal move + full cascade resolve + "
-                        "fp32 one-hot obs, injected 32-orb skyfall slab (3 bit/orb, 12 B) per board-step",
-            "boards_per_gpu": n, "rows": ROWS, "cols": COLS, "skyfall_orbs_per_step": SLAB_ORBS,
-            "skyfall_slab": "device-timed legs: 32 injected orbs per board-step resident in HBM (bit-sliced, 12 B); a board "
-                            "that draws more than 32 orbs in one step (about 6e-5 of them) continues on the Philox stream at "
-                            "the same draw index, flagged SKYFALL_EXHAUSTED, bit-exact against the oracle which does the same.  "
-                            "e2e leg: the host offers 54 orbs per board-step in pinned memory (chunk-major, base 6), of which "
-                            "18 (6 B) cross PCIe for every board and the rest on demand",
-            "l2": "inputs > L2: 881 MB obs stream per step, skyfall slabs rotate over 16 buffers (201 MB)",
+                        "fp32 one-hot obs, injected 50-orb skyfall slab per board-step",
+            "boards_per_gpu": n, "rows": ROWS, "cols": COLS, "skyfall_orbs_per_step": OBS_SLAB_ORBS,
+            "skyfall_slab": "device-timed leg: 50 injected orbs per board-step resident in HBM (chunk-major, ten 3-bit codes "
+                            "per uint32: 20 B per board, of which the kernel reads 8 B for every board and the rest where a "
+                            "cascade draws it); no board ran past its slab.  e2e leg: the host offers 54 orbs per board-step "
+                            "in pinned memory (chunk-major, base 6), of which 18 (6 B) cross PCIe for every board and the "
+                            "rest on demand.  (state_only sub-record: 32-orb row slab, 12 B; a board that draws more "
+                            "continues on the Philox stream at the same draw index, flagged SKYFALL_EXHAUSTED, as the "
+                            "oracle does)",
+            "l2": "inputs > L2: 881 MB obs stream per step, skyfall slabs rotate over 16 buffers (336 MB)",
             "parallelism": "env-sharded x%d, no data-path collective" % world}
 
 
@@ -145,7 +157,7 @@ def cpu_port_rate(n_sample, steps, threads):
     fingers[:] = np.tile(fingers[:base], (reps, 1))[:n_sample]
     prev = np.full(n_sample, 4, np.uint8)
     moves = np.zeros(n_sample, np.uint16)
-    inj = rng.integers(0, 6, size=(n_sample, SLAB_ORBS)).astype(np.uint8)
+    inj = rng.integers(0, 6, size=(n_sample, OBS_SLAB_ORBS)).astype(np.uint8)
     obs = np.zeros((n_sample, ROWS, COLS, 7), np.float32)
     from concurrent.futures import ThreadPoolExecutor
 
@@ -483,15 +495,23 @@ def main():
     env.reset(step=0)
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
-    host_orbs = [torch.randint(0, 6, (n, SLAB_ORBS), device=dev, dtype=torch.uint8, generator=gen) for _ in range(N_SLABS)]
-    slabs = [env._slab(s, SLAB_FORMAT)[0] for s in host_orbs]        # packed 3-bit slabs, resident in HBM
+    host_orbs = [torch.randint(0, 6, (n, OBS_SLAB_ORBS), device=dev, dtype=torch.uint8, generator=gen) for _ in range(N_SLABS)]
+    obs_slabs = [env._slab(s, OBS_SLAB_FORMAT)[0] for s in host_orbs]             # chunk-major slabs, resident in HBM
+    slabs = [env._slab(s[:, :SLAB_ORBS].contiguous(), SLAB_FORMAT)[0] for s in host_orbs]   # row slabs of the same orbs
     del host_orbs
-    out = env.step(None, eval_moves=True, injected=(slabs[0], SLAB_ORBS), slab_format=SLAB_FORMAT, obs='f32', step=1)
+    out = env.step(None, eval_moves=True, injected=(obs_slabs[0], OBS_SLAB_ORBS), slab_format=OBS_SLAB_FORMAT, obs='f32', step=1)
     obs_buf = out.obs
 
+    so_out = [None]
+
     def one_step(t, with_obs=True):
-        return env.step(None, eval_moves=True, injected=(slabs[t % N_SLABS], SLAB_ORBS), slab_format=SLAB_FORMAT,
-                        obs=obs_buf if with_obs else None, step=t, out=out)
+        if with_obs:
+            return env.step(None, eval_moves=True, injected=(obs_slabs[t % N_SLABS], OBS_SLAB_ORBS),
+                            slab_format=OBS_SLAB_FORMAT, obs=obs_buf, step=t, out=out)
+        # its own result buffers: `out` keeps the last step of the headline leg for stats_last_step
+        so_out[0] = env.step(None, eval_moves=True, injected=(slabs[t % N_SLABS], SLAB_ORBS), slab_format=SLAB_FORMAT,
+                             obs=None, step=t, out=so_out[0])
+        return so_out[0]
 
     for t in range(2, 2 + W):
         one_step(t)
@@ -649,7 +669,7 @@ def main():
         ep_fused_ms = T.timed(lambda t: ep_env.rollout(51, max_moves=50), 0, 4)
         del ep_env, ep_out
         extras["episode_mode"] = (ep_ms, ep_fused_ms)
-        del env, slabs, out, obs_buf
+        del env, slabs, obs_slabs, out, obs_buf
         torch.cuda.empty_cache()
         extras["rollout"] = leg_rollout(ppad_b200, pdist, T, args, rank, world, dev, peak)
         extras["config2"] = leg_config2(ppad_b200, pdist, T, args, rank, world, dev)

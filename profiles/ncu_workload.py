@@ -21,9 +21,11 @@ gen = torch.Generator(device=dev).manual_seed(1)
 env = ppad_b200.BatchedPAD(n, 5, 6, seed=1, device=dev)
 env.reset(step=0)
 slabs = [env._slab(torch.randint(0, 6, (n, 32), device=dev, dtype=torch.uint8, generator=gen), 'planes3')[0] for _ in range(4)]
-out = env.step(None, eval_moves=True, injected=(slabs[0], 32), slab_format='planes3', obs='f32', step=1)
+# the headline step of bench.py: 50 injected orbs per board as a chunk-major slab in HBM
+oslabs = [env._slab(torch.randint(0, 6, (n, 50), device=dev, dtype=torch.uint8, generator=gen), 'chunks10')[0] for _ in range(4)]
+out = env.step(None, eval_moves=True, injected=(oslabs[0], 50), slab_format='chunks10', obs='f32', step=1)
 for t in range(2, 40):
-    env.step(None, eval_moves=True, injected=(slabs[t & 3], 32), slab_format='planes3', obs=out.obs, step=t, out=out)
+    env.step(None, eval_moves=True, injected=(oslabs[t & 3], 50), slab_format='chunks10', obs=out.obs, step=t, out=out)
 pipe = env.host_pipe(slab_orbs=54, compact=True, slab_format='chunks6')
 pipe.slab.copy_(env._slab(torch.randint(0, 6, (n, 54), device=dev, dtype=torch.uint8, generator=gen), 'chunks6')[0].cpu())
 pipe.step(eval_moves=True, obs=out.obs, step=40, wait=True)
@@ -52,7 +54,7 @@ torch.cuda.synchronize()
 
 torch.cuda.profiler.start()
 for t in range(40, 42):
-    env.step(None, eval_moves=True, injected=(slabs[t & 3], 32), slab_format='planes3', obs=out.obs, step=t, out=out)
+    env.step(None, eval_moves=True, injected=(oslabs[t & 3], 50), slab_format='chunks10', obs=out.obs, step=t, out=out)
 for t in range(42, 44):
     pipe.step(eval_moves=True, obs=out.obs, step=t, wait=True)
 for t in range(44, 46):
