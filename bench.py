@@ -51,7 +51,8 @@ ROWS, COLS = 5, 6
 # the headline (device-timed) leg: 50 injected orbs per board-step resident in HBM as a chunk-major slab (PPAD_SLAB_CHUNKS10,
 # ten 3-bit codes per uint32, 20 B per board); the kernel reads the first two chunks of every board (8 B) and a later one
 # only where a cascade draws more than 20 orbs.  Faster than the 32-orb row slab it replaces (0.151 against 0.154 ms,
-# profiles/r02av_device_slab_formats.txt) and no board runs past its slab (SURVEY.md section 8d asks for >= 42 orbs).
+# profiles/r02av_device_slab_formats.txt), and one board-step in two million runs past its slab instead of one in 12 000
+# (SURVEY.md section 8d asks for >= 42 orbs).
 OBS_SLAB_ORBS = 50
 OBS_SLAB_FORMAT = 'chunks10'
 OBS_SLAB_BYTES = 8
@@ -83,7 +84,8 @@ def workload_config(n, world):
             "boards_per_gpu": n, "rows": ROWS, "cols": COLS, "skyfall_orbs_per_step": OBS_SLAB_ORBS,
             "skyfall_slab": "device-timed leg: 50 injected orbs per board-step resident in HBM (chunk-major, ten 3-bit codes "
                             "per uint32: 20 B per board, of which the kernel reads 8 B for every board and the rest where a "
-                            "cascade draws it); no board ran past its slab.  e2e leg: the host offers 54 orbs per board-step "
+                            "cascade draws it); about one board-step in two million draws more than 50 orbs and continues on the "
+                            "Philox stream at the same draw index, flagged SKYFALL_EXHAUSTED, as the oracle does (stats_last_step.faults).  e2e leg: the host offers 54 orbs per board-step "
                             "in pinned memory (chunk-major, base 6), of which 18 (6 B) cross PCIe for every board and the "
                             "rest on demand.  (state_only sub-record: 32-orb row slab, 12 B; a board that draws more "
                             "continues on the Philox stream at the same draw index, flagged SKYFALL_EXHAUSTED, as the "
